@@ -1,0 +1,174 @@
+/* gcgpu.h — C ABI of libgcgpu.so: the B200 (sm_100a) implementation of SuperPlus gap_closer's
+ * k-mer count/lookup and Smith-Waterman/CIGAR inner loops.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own (it is one C program), so
+ * the entry points below are *batched* forms of the reference functions they replace; the C
+ * shims in superplus_b200/gap_closer/ keep every prototype of kmer.h / ont.h / sw.h / cigar.h /
+ * hash.h and forward to these.  All paths below are relative to
+ * /root/reference/gap_closer.
+ *
+ * Conventions
+ *   - plain C types only; no CUDA or torch types in any signature
+ *   - every function returns 0 on success or a negative GCG_E* code; gcg_last_error() returns a
+ *     thread-local message.  (Reference behaviour is err_mesg -> abort, utils.c:217-230; the
+ *     shims turn a non-zero return into err_mesg.)
+ *   - one gcg_ctx per process and device; calls on one ctx are serialised by the caller
+ *     (the reference API is not thread safe either, hash.h:13-15)
+ *   - input sequences are borrowed for the duration of the call; outputs returned through
+ *     `**` are owned by the library and released with the matching *_free
+ *   - there is NO CPU fallback: without a CUDA device gcg_init fails
+ */
+#ifndef GCGPU_H
+#define GCGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCG_OK          0
+#define GCG_ECUDA      -1   /* CUDA runtime error */
+#define GCG_EINVAL     -2   /* bad argument */
+#define GCG_ENOMEM     -3   /* host or device allocation failed */
+#define GCG_ERANGE     -4   /* input exceeds a documented limit */
+
+typedef struct gcg_ctx gcg_ctx;
+typedef struct gcg_seqs gcg_seqs;     /* device-resident 2-bit packed sequence set */
+typedef struct gcg_ascii gcg_ascii;   /* device-resident ASCII sequence set (bench: inputs already in HBM) */
+typedef struct gcg_table gcg_table;   /* device-resident contig k-mer table */
+typedef struct gcg_hits gcg_hits;     /* device-resident anchor list */
+typedef struct gcg_swbatch gcg_swbatch; /* device-resident SW pair batch */
+
+/* ------------------------------------------------------------------ context ---------- */
+int  gcg_device_count (void);
+int  gcg_init (int device, gcg_ctx ** out);
+void gcg_destroy (gcg_ctx * ctx);
+const char * gcg_last_error (void);
+/* number of host threads used for staging / back-fill (the reference's n_thread, main.c:142) */
+int  gcg_set_host_threads (gcg_ctx * ctx, int n_thread);
+/* the CUDA stream every kernel of this ctx is launched on, as an opaque cudaStream_t */
+void * gcg_stream (gcg_ctx * ctx);
+int  gcg_sync (gcg_ctx * ctx);
+/* per-kernel CUDA-event timing: enable, run, then read "name ms launches\n" lines */
+int  gcg_prof_enable (gcg_ctx * ctx, int on);
+int  gcg_prof_reset (gcg_ctx * ctx);
+int  gcg_prof_report (gcg_ctx * ctx, char * buf, int64_t cap);
+/* number of kernels launched by this ctx since creation */
+int64_t gcg_launch_count (gcg_ctx * ctx);
+
+/* ------------------------------------------------------------------ sequences -------- */
+/* K1: ASCII -> 2 bit, base2int(b) = (b>>1)&3 (bio.h:24; kseq1.h:28-35).  Host pointers. */
+int  gcg_seqs_upload (gcg_ctx * ctx, const char * const * seq, const int32_t * len, int64_t n, gcg_seqs ** out);
+/* same, from one concatenated buffer: sequence i is buf[off[i] .. off[i+1]) */
+int  gcg_seqs_upload_concat (gcg_ctx * ctx, const char * buf, const int64_t * off, int64_t n, gcg_seqs ** out);
+/* stage ASCII on the device without packing, then pack on the device only (K1 alone) */
+int  gcg_ascii_upload_concat (gcg_ctx * ctx, const char * buf, const int64_t * off, int64_t n, gcg_ascii ** out);
+int  gcg_seqs_pack (gcg_ctx * ctx, const gcg_ascii * a, gcg_seqs ** out);
+void gcg_ascii_free (gcg_ascii * a);
+void gcg_seqs_free (gcg_seqs * s);
+int64_t gcg_seqs_count (const gcg_seqs * s);
+int64_t gcg_seqs_bases (const gcg_seqs * s);
+int64_t gcg_seqs_kmers (const gcg_seqs * s, int k);   /* sum over sequences of max(0, len-k+1) */
+
+/* ------------------------------------------------------------------ contig k-mers ---- */
+/* replaces chop_contig_seqs2kmers (kmer.c:155-184 / 37-121): one 24-byte record per contig
+ * position p in [0, len-k], laid out exactly like kmer_t (def.h:58-66):
+ *   u64 kseq @0, i32 hs_id @8 (= crc32(kseq bytes) % n_thread, kmer.c:88, crc32.h:70-81),
+ *   i32 tid @12, i32 pos @16, u16 flag @20 (KMER_REV=1), i16 kmer_len @22.
+ * kmers_out[i] must have room for max(0,len[i]-k+1) records; n_kmer_out[i] receives that count. */
+int  gcg_chop_contigs (gcg_ctx * ctx, const gcg_seqs * contigs, int k, int n_thread,
+                       void * const * kmers_out, int32_t * n_kmer_out);
+
+/* replaces kmer_hash_init/clear + put_contig_kmers2hashs (kmer.c:187-213 / 124-152 ->
+ * hash.c:113-152): distinct canonical k-mers of all contigs with multiplicity {1, >=2} and the
+ * (tid,pos,flag) of the single occurrence when multiplicity is 1.  1 <= k <= 31. */
+int  gcg_table_build_seqs (gcg_ctx * ctx, const gcg_seqs * contigs, int k, gcg_table ** out);
+int  gcg_table_build (gcg_ctx * ctx, const char * const * contig_seq, const int32_t * contig_len,
+                      int32_t n_contig, int k, gcg_table ** out);
+void gcg_table_free (gcg_table * t);
+/* replaces kmer_stat + kmer_stat2 (kmer.c:265-312): out[0] scaffold total, out[1] scaffold
+ * unique, out[2] ONT total, out[3] ONT unique (the latter two reflect all searches since the
+ * table was built, as the reference's anchored sets do, ont.c:230-254). */
+int  gcg_table_stats (gcg_ctx * ctx, gcg_table * t, int64_t out[4]);
+/* debugging / parity: dump every distinct key (unordered).  multi_out is 1 or 2 (2 = ">= 2").
+ * For multi==1 entries tid/pos/rev describe the occurrence; for others they are unspecified
+ * (the reference keeps the first occurrence, which no caller can observe). */
+int64_t gcg_table_size (gcg_ctx * ctx, gcg_table * t);
+int  gcg_table_dump (gcg_ctx * ctx, gcg_table * t, int64_t cap, uint64_t * key, int32_t * multi_out,
+                     int32_t * tid, int32_t * pos, uint8_t * rev);
+
+/* ------------------------------------------------------------------ ONT search ------- */
+/* one anchored ONT position (ont.c:171-178,195-202): the canonical k-mer at `pos` of read
+ * `read` occurs exactly once (both strands) over all contigs, at contig `tid` position `cpos`.
+ * flags bit0 = KMER_REV of the contig occurrence (def.h:52), bit1 = ONT_KMER_REV (def.h:108). */
+typedef struct {
+  int32_t read;
+  int32_t pos;
+  int32_t tid;
+  uint32_t cpos_flags;      /* (cpos << 2) | flags ; contigs are limited to 2^30 bases */
+} gcg_hit;
+
+/* replaces search_kmers_on_ont_reads' SEARCH + REHASH phases (ont.c:407-480 / 141-254).
+ * Result is sorted by (read,pos). */
+int  gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * reads, int k, gcg_hits ** out);
+int64_t gcg_hits_count (const gcg_hits * h);
+int  gcg_hits_download (gcg_ctx * ctx, const gcg_hits * h, gcg_hit * dst, int64_t cap);
+void gcg_hits_free (gcg_hits * h);
+/* host-buffer form: hits_out receives a library-owned pinned array, release with gcg_free */
+int  gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
+                 int64_t n_read, int k, gcg_hit ** hits_out, int64_t * n_hit);
+void gcg_free (void * p);
+
+/* ------------------------------------------------------------------ Smith-Waterman --- */
+#define GCG_SWOS_SOFTCLIP      0   /* sw.h:20-23 */
+#define GCG_SWOS_LEADING_INDEL 1
+#define GCG_SWOS_INDEL         2
+#define GCG_SWOS_IGNORE        3
+
+#define GCG_SW_ASIS  0   /* traceback exactly as shipped (sw.c:289-319 never re-fetches the cell) */
+#define GCG_SW_FIXED 1   /* cell re-fetched every step (the evidently intended behaviour)       */
+
+typedef struct {
+  int32_t type_c;                       /* alphabet size, symbols are 0..type_c-1 (sw.c:216) */
+  int32_t del_o, del_e, ins_o, ins_e;   /* sw.h:52-55 */
+  int32_t strategy;                     /* overhang strategy */
+  /* border scores the aligner holds (state of init_matrix_values, sw.c:61-110):
+   * kind 0 = zeros; kind 1 = row0[j] = -b_ins_o-(j-1)*b_ins_e, col0[i] = -b_del_o-(i-1)*b_del_e */
+  int32_t border_kind;
+  int32_t b_del_o, b_del_e, b_ins_o, b_ins_e;
+  int32_t mat[64];                      /* type_c x type_c, row = query symbol (sw.c:216); type_c <= 8 */
+} gcg_sw_params;
+
+typedef struct {
+  int32_t score;             /* sw_t.score            (sw.h:44) */
+  int32_t alignment_offset;  /* sw_t.alignment_offset (sw.h:45) */
+  int32_t has_softclip;      /* sw_t.has_softclip     (sw.h:51) */
+  int32_t bt_tidx, bt_qidx;  /* end cell chosen by sw.c:259-280 */
+  int32_t n_cigar;           /* number of BAM-encoded ops */
+  int64_t cigar_off;         /* offset of the first op in the shared uint32 pool */
+} gcg_sw_result;
+
+/* host-buffer form of a batch of sw_align calls (sw.c:400-414).  qry/tgt are integer-coded
+ * symbols, pair p is qry[qoff[p]..qoff[p+1]) vs tgt[toff[p]..toff[p+1]).  results[n];
+ * *cigar_pool is a library-owned pinned uint32 array (release with gcg_free). */
+int  gcg_sw_batch (gcg_ctx * ctx, const gcg_sw_params * P, int mode,
+                   const char * qry, const int64_t * qoff, const char * tgt, const int64_t * toff, int64_t n,
+                   gcg_sw_result * results, uint32_t ** cigar_pool, int64_t * n_cigar_pool);
+
+/* device-resident form: upload once, align many times (bench `value`), download results */
+int  gcg_swbatch_upload (gcg_ctx * ctx, const char * qry, const int64_t * qoff, const char * tgt,
+                         const int64_t * toff, int64_t n, gcg_swbatch ** out);
+int  gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_params * P, int mode);
+int  gcg_swbatch_download (gcg_ctx * ctx, gcg_swbatch * b, gcg_sw_result * results,
+                           uint32_t ** cigar_pool, int64_t * n_cigar_pool);
+int64_t gcg_swbatch_cells (const gcg_swbatch * b);
+/* which kernel family the last gcg_swbatch_align used per pair: counts[0] packed-s16 pairs,
+ * counts[1] generic-s32 pairs */
+int  gcg_swbatch_path_counts (const gcg_swbatch * b, int64_t counts[2]);
+void gcg_swbatch_free (gcg_swbatch * b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

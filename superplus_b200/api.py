@@ -1,0 +1,396 @@
+"""ctypes binding of libgcgpu.so (include/gcgpu.h) for tests, bench.py and the multi-GPU driver.
+
+The product is the C-ABI library plus the C shims in superplus_b200/gap_closer/ (the reference
+is a C program); this module is only the Python-side handle on the same entry points.  It
+fails loudly when the CUDA library is missing or no B200 is visible — there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgcgpu.so")
+
+SOFTCLIP, LEADING_INDEL, INDEL, IGNORE = 0, 1, 2, 3
+SW_ASIS, SW_FIXED = 0, 1
+
+HIT_DTYPE = np.dtype([("read", "<i4"), ("pos", "<i4"), ("tid", "<i4"), ("cpos_flags", "<u4")])
+SWRES_DTYPE = np.dtype([("score", "<i4"), ("alignment_offset", "<i4"), ("has_softclip", "<i4"),
+                        ("bt_tidx", "<i4"), ("bt_qidx", "<i4"), ("n_cigar", "<i4"), ("cigar_off", "<i8")])
+KMER_DTYPE = np.dtype([("kseq", "<u8"), ("hs_id", "<i4"), ("tid", "<i4"), ("pos", "<i4"), ("flag", "<u2"), ("kmer_len", "<i2")])
+
+EXPORTS = [
+    "gcg_device_count", "gcg_init", "gcg_destroy", "gcg_last_error", "gcg_set_host_threads", "gcg_stream", "gcg_sync",
+    "gcg_prof_enable", "gcg_prof_reset", "gcg_prof_report", "gcg_launch_count",
+    "gcg_seqs_upload", "gcg_seqs_upload_concat", "gcg_ascii_upload_concat", "gcg_seqs_pack", "gcg_ascii_free",
+    "gcg_seqs_free", "gcg_seqs_count", "gcg_seqs_bases", "gcg_seqs_kmers",
+    "gcg_chop_contigs", "gcg_table_build_seqs", "gcg_table_build", "gcg_table_free", "gcg_table_stats",
+    "gcg_table_size", "gcg_table_dump",
+    "gcg_search_seqs", "gcg_hits_count", "gcg_hits_download", "gcg_hits_free", "gcg_search", "gcg_free",
+    "gcg_sw_batch", "gcg_swbatch_upload", "gcg_swbatch_align", "gcg_swbatch_download", "gcg_swbatch_cells",
+    "gcg_swbatch_path_counts", "gcg_swbatch_free",
+]
+
+
+class GcgError(RuntimeError):
+    pass
+
+
+class SWParams(C.Structure):
+    _fields_ = [("type_c", C.c_int32),
+                ("del_o", C.c_int32), ("del_e", C.c_int32), ("ins_o", C.c_int32), ("ins_e", C.c_int32),
+                ("strategy", C.c_int32),
+                ("border_kind", C.c_int32),
+                ("b_del_o", C.c_int32), ("b_del_e", C.c_int32), ("b_ins_o", C.c_int32), ("b_ins_e", C.c_int32),
+                ("mat", C.c_int32 * 64)]
+
+
+def default_mat(type_c=5, match=1, mismatch=-5):
+    """gc_graph.c:74-77,87-107"""
+    m = np.full((type_c, type_c), mismatch, dtype=np.int32)
+    np.fill_diagonal(m, match)
+    return m
+
+
+def make_sw_params(mat=None, del_o=2, del_e=1, ins_o=2, ins_e=1, strategy=SOFTCLIP, border=None) -> SWParams:
+    if mat is None:
+        mat = default_mat()
+    mat = np.ascontiguousarray(mat, dtype=np.int32)
+    p = SWParams()
+    p.type_c = mat.shape[0]
+    p.del_o, p.del_e, p.ins_o, p.ins_e = del_o, del_e, ins_o, ins_e
+    p.strategy = strategy
+    if border is None:
+        border = (0, 0, 0, 0, 0) if strategy == SOFTCLIP else (1, del_o, del_e, ins_o, ins_e)
+    p.border_kind, p.b_del_o, p.b_del_e, p.b_ins_o, p.b_ins_e = border
+    for i, v in enumerate(mat.reshape(-1)):
+        p.mat[i] = int(v)
+    return p
+
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH):
+    """Load libgcgpu.so.  Raises when it has not been built — never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise GcgError("libgcgpu.so is missing (%s): run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "or `make -C superplus_b200/csrc`; there is no CPU fallback" % path)
+    L = C.CDLL(path)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.gcg_last_error.restype = C.c_char_p
+    L.gcg_init.argtypes = [C.c_int, C.POINTER(vp)]
+    L.gcg_destroy.argtypes = [vp]
+    L.gcg_set_host_threads.argtypes = [vp, C.c_int]
+    L.gcg_stream.restype = vp
+    L.gcg_stream.argtypes = [vp]
+    L.gcg_sync.argtypes = [vp]
+    L.gcg_prof_enable.argtypes = [vp, C.c_int]
+    L.gcg_prof_reset.argtypes = [vp]
+    L.gcg_prof_report.argtypes = [vp, C.c_char_p, i64]
+    L.gcg_launch_count.restype = i64
+    L.gcg_launch_count.argtypes = [vp]
+    L.gcg_seqs_upload.argtypes = [vp, vp, vp, i64, C.POINTER(vp)]
+    L.gcg_seqs_upload_concat.argtypes = [vp, vp, vp, i64, C.POINTER(vp)]
+    L.gcg_ascii_upload_concat.argtypes = [vp, vp, vp, i64, C.POINTER(vp)]
+    L.gcg_seqs_pack.argtypes = [vp, vp, C.POINTER(vp)]
+    L.gcg_ascii_free.argtypes = [vp]
+    L.gcg_seqs_free.argtypes = [vp]
+    for f in (L.gcg_seqs_count, L.gcg_seqs_bases):
+        f.restype = i64
+        f.argtypes = [vp]
+    L.gcg_seqs_kmers.restype = i64
+    L.gcg_seqs_kmers.argtypes = [vp, C.c_int]
+    L.gcg_chop_contigs.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
+    L.gcg_table_build_seqs.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
+    L.gcg_table_build.argtypes = [vp, vp, vp, i32, C.c_int, C.POINTER(vp)]
+    L.gcg_table_free.argtypes = [vp]
+    L.gcg_table_stats.argtypes = [vp, vp, vp]
+    L.gcg_table_size.restype = i64
+    L.gcg_table_size.argtypes = [vp, vp]
+    L.gcg_table_dump.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
+    L.gcg_search_seqs.argtypes = [vp, vp, vp, C.c_int, C.POINTER(vp)]
+    L.gcg_hits_count.restype = i64
+    L.gcg_hits_count.argtypes = [vp]
+    L.gcg_hits_download.argtypes = [vp, vp, vp, i64]
+    L.gcg_hits_free.argtypes = [vp]
+    L.gcg_search.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(i64)]
+    L.gcg_free.argtypes = [vp]
+    L.gcg_sw_batch.argtypes = [vp, C.POINTER(SWParams), C.c_int, vp, vp, vp, vp, i64, vp, C.POINTER(vp), C.POINTER(i64)]
+    L.gcg_swbatch_upload.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(vp)]
+    L.gcg_swbatch_align.argtypes = [vp, vp, C.POINTER(SWParams), C.c_int]
+    L.gcg_swbatch_download.argtypes = [vp, vp, vp, C.POINTER(vp), C.POINTER(i64)]
+    L.gcg_swbatch_cells.restype = i64
+    L.gcg_swbatch_cells.argtypes = [vp]
+    L.gcg_swbatch_path_counts.argtypes = [vp, vp]
+    L.gcg_swbatch_free.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _concat(seqs):
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    if len(seqs) and off[-1] > 0:
+        buf = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.uint8) for s in seqs]))
+    else:
+        buf = np.zeros(1, np.uint8)
+    return buf, off
+
+
+class Context:
+    """One per process and GPU (gcg_ctx)."""
+
+    def __init__(self, device: int = 0, host_threads: int | None = None):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        self._chk(self.L.gcg_init(device, C.byref(self.h)))
+        if host_threads:
+            self._chk(self.L.gcg_set_host_threads(self.h, host_threads))
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise GcgError("libgcgpu error %d: %s" % (rc, self.L.gcg_last_error().decode()))
+
+    def close(self):
+        if self.h:
+            self.L.gcg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    # ---- plumbing ------------------------------------------------------------------------
+    def stream_ptr(self) -> int:
+        return int(self.L.gcg_stream(self.h) or 0)
+
+    def sync(self):
+        self._chk(self.L.gcg_sync(self.h))
+
+    def launches(self) -> int:
+        return int(self.L.gcg_launch_count(self.h))
+
+    def prof(self, on: bool):
+        self._chk(self.L.gcg_prof_enable(self.h, 1 if on else 0))
+
+    def prof_reset(self):
+        self._chk(self.L.gcg_prof_reset(self.h))
+
+    def prof_report(self) -> dict:
+        buf = C.create_string_buffer(1 << 16)
+        self._chk(self.L.gcg_prof_report(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, n = line.split()
+            out[name] = (float(ms), int(n))
+        return out
+
+    # ---- sequences -----------------------------------------------------------------------
+    def upload(self, seqs) -> "Seqs":
+        """list of uint8 ASCII arrays -> device 2-bit stream (K1), via the concatenated entry point"""
+        buf, off = _concat(seqs)
+        return self.upload_concat(buf, off)
+
+    def upload_concat(self, buf: np.ndarray, off: np.ndarray) -> "Seqs":
+        h = C.c_void_p()
+        self._chk(self.L.gcg_seqs_upload_concat(self.h, buf.ctypes.data, off.ctypes.data, len(off) - 1, C.byref(h)))
+        return Seqs(self, h)
+
+    def upload_ptrs(self, seqs) -> "Seqs":
+        """same through the pointer-array entry point the C shims use"""
+        arrs = [np.ascontiguousarray(s, dtype=np.uint8) for s in seqs]
+        n = len(arrs)
+        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+        lens = np.array([len(a) for a in arrs], dtype=np.int32)
+        h = C.c_void_p()
+        self._chk(self.L.gcg_seqs_upload(self.h, C.cast(ptrs, C.c_void_p), lens.ctypes.data, n, C.byref(h)))
+        return Seqs(self, h)
+
+    def stage_ascii(self, seqs) -> "Ascii":
+        buf, off = _concat(seqs)
+        h = C.c_void_p()
+        self._chk(self.L.gcg_ascii_upload_concat(self.h, buf.ctypes.data, off.ctypes.data, len(off) - 1, C.byref(h)))
+        return Ascii(self, h)
+
+    def pack(self, a: "Ascii") -> "Seqs":
+        h = C.c_void_p()
+        self._chk(self.L.gcg_seqs_pack(self.h, a.h, C.byref(h)))
+        return Seqs(self, h)
+
+    # ---- k-mers --------------------------------------------------------------------------
+    def chop_contigs(self, contigs: "Seqs", lens, k: int, n_thread: int = 1):
+        """-> list of KMER_DTYPE arrays, one per contig (the kmer_t records of def.h:58-66)"""
+        n = len(lens)
+        outs = [np.zeros(max(0, int(l) - k + 1), dtype=KMER_DTYPE) for l in lens]
+        keep = [o if len(o) else np.zeros(1, dtype=KMER_DTYPE) for o in outs]
+        ptrs = (C.c_void_p * max(n, 1))(*[o.ctypes.data for o in keep])
+        nk = np.zeros(max(n, 1), dtype=np.int32)
+        self._chk(self.L.gcg_chop_contigs(self.h, contigs.h, k, n_thread, C.cast(ptrs, C.c_void_p), nk.ctypes.data))
+        assert all(int(nk[i]) == len(outs[i]) for i in range(n))
+        return outs
+
+    def table_build(self, contigs: "Seqs", k: int) -> "KmerTable":
+        h = C.c_void_p()
+        self._chk(self.L.gcg_table_build_seqs(self.h, contigs.h, k, C.byref(h)))
+        return KmerTable(self, h, k)
+
+    def search(self, table: "KmerTable", reads: "Seqs") -> np.ndarray:
+        h = C.c_void_p()
+        self._chk(self.L.gcg_search_seqs(self.h, table.h, reads.h, table.k, C.byref(h)))
+        try:
+            n = int(self.L.gcg_hits_count(h))
+            out = np.zeros(n, dtype=HIT_DTYPE)
+            self._chk(self.L.gcg_hits_download(self.h, h, out.ctypes.data, n))
+        finally:
+            self.L.gcg_hits_free(h)
+        return out
+
+    def search_device(self, table: "KmerTable", reads: "Seqs") -> int:
+        """search leaving the anchors on the device (bench `value`); returns the anchor count"""
+        h = C.c_void_p()
+        self._chk(self.L.gcg_search_seqs(self.h, table.h, reads.h, table.k, C.byref(h)))
+        n = int(self.L.gcg_hits_count(h))
+        self.L.gcg_hits_free(h)
+        return n
+
+    def search_host(self, table: "KmerTable", reads) -> np.ndarray:
+        """the shim-facing call: host pointers in, pinned host anchors out (gcg_search)"""
+        arrs = [np.ascontiguousarray(s, dtype=np.uint8) for s in reads]
+        n = len(arrs)
+        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+        lens = np.array([len(a) for a in arrs], dtype=np.int32)
+        return self.search_host_ptrs(table, ptrs, lens, n)
+
+    def search_host_ptrs(self, table, ptrs, lens, n) -> np.ndarray:
+        hp = C.c_void_p()
+        nh = C.c_int64()
+        self._chk(self.L.gcg_search(self.h, table.h, C.cast(ptrs, C.c_void_p), lens.ctypes.data, n, table.k, C.byref(hp), C.byref(nh)))
+        try:
+            if nh.value:
+                out = np.frombuffer((C.c_char * (nh.value * HIT_DTYPE.itemsize)).from_address(hp.value), dtype=HIT_DTYPE).copy()
+            else:
+                out = np.zeros(0, dtype=HIT_DTYPE)
+        finally:
+            self.L.gcg_free(hp)
+        return out
+
+    # ---- SW ------------------------------------------------------------------------------
+    def sw_batch(self, P: SWParams, qrys, tgts, mode: int = SW_ASIS):
+        """host-buffer form.  -> (results SWRES_DTYPE[n], list of cigar uint32 arrays)"""
+        qbuf, qoff = _concat(qrys)
+        tbuf, toff = _concat(tgts)
+        n = len(qrys)
+        res = np.zeros(n, dtype=SWRES_DTYPE)
+        pool = C.c_void_p()
+        npool = C.c_int64()
+        self._chk(self.L.gcg_sw_batch(self.h, C.byref(P), mode, qbuf.ctypes.data, qoff.ctypes.data, tbuf.ctypes.data,
+                                      toff.ctypes.data, n, res.ctypes.data, C.byref(pool), C.byref(npool)))
+        try:
+            cp = np.frombuffer((C.c_char * (npool.value * 4)).from_address(pool.value), dtype=np.uint32).copy() if npool.value else np.zeros(0, np.uint32)
+        finally:
+            self.L.gcg_free(pool)
+        cigs = [cp[int(r["cigar_off"]):int(r["cigar_off"]) + int(r["n_cigar"])] for r in res]
+        return res, cigs
+
+    def swbatch_upload(self, qry2d: np.ndarray, tgt2d: np.ndarray) -> "SWBatch":
+        n = qry2d.shape[0]
+        qoff = (np.arange(n + 1, dtype=np.int64) * qry2d.shape[1])
+        toff = (np.arange(n + 1, dtype=np.int64) * tgt2d.shape[1])
+        return self.swbatch_upload_concat(np.ascontiguousarray(qry2d, dtype=np.uint8).reshape(-1), qoff,
+                                          np.ascontiguousarray(tgt2d, dtype=np.uint8).reshape(-1), toff)
+
+    def swbatch_upload_concat(self, qbuf, qoff, tbuf, toff) -> "SWBatch":
+        h = C.c_void_p()
+        qb = qbuf if len(qbuf) else np.zeros(1, np.uint8)
+        tb = tbuf if len(tbuf) else np.zeros(1, np.uint8)
+        self._chk(self.L.gcg_swbatch_upload(self.h, qb.ctypes.data, qoff.ctypes.data, tb.ctypes.data, toff.ctypes.data, len(qoff) - 1, C.byref(h)))
+        return SWBatch(self, h, len(qoff) - 1)
+
+
+class _Handle:
+    _free = None
+
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+
+    def free(self):
+        if self.h:
+            getattr(self.ctx.L, self._free)(self.h)
+            self.h = C.c_void_p()
+
+
+class Ascii(_Handle):
+    _free = "gcg_ascii_free"
+
+
+class Seqs(_Handle):
+    _free = "gcg_seqs_free"
+
+    @property
+    def n(self):
+        return int(self.ctx.L.gcg_seqs_count(self.h))
+
+    @property
+    def bases(self):
+        return int(self.ctx.L.gcg_seqs_bases(self.h))
+
+    def kmers(self, k):
+        return int(self.ctx.L.gcg_seqs_kmers(self.h, k))
+
+
+class KmerTable(_Handle):
+    _free = "gcg_table_free"
+
+    def __init__(self, ctx, h, k):
+        super().__init__(ctx, h)
+        self.k = k
+
+    def stats(self):
+        out = np.zeros(4, dtype=np.int64)
+        self.ctx._chk(self.ctx.L.gcg_table_stats(self.ctx.h, self.h, out.ctypes.data))
+        return tuple(int(x) for x in out)
+
+    def dump(self):
+        """-> key, multi(1|2), tid, pos, rev sorted by key"""
+        n = int(self.ctx.L.gcg_table_size(self.ctx.h, self.h))
+        key = np.zeros(max(n, 1), np.uint64); multi = np.zeros(max(n, 1), np.int32); tid = np.zeros(max(n, 1), np.int32)
+        pos = np.zeros(max(n, 1), np.int32); rev = np.zeros(max(n, 1), np.uint8)
+        self.ctx._chk(self.ctx.L.gcg_table_dump(self.ctx.h, self.h, n, key.ctypes.data, multi.ctypes.data, tid.ctypes.data,
+                                                pos.ctypes.data, rev.ctypes.data))
+        o = np.argsort(key[:n], kind="stable")
+        return key[:n][o], multi[:n][o], tid[:n][o], pos[:n][o], rev[:n][o]
+
+
+class SWBatch(_Handle):
+    _free = "gcg_swbatch_free"
+
+    def __init__(self, ctx, h, n):
+        super().__init__(ctx, h)
+        self.n = n
+
+    def align(self, P: SWParams, mode: int = SW_ASIS):
+        self.ctx._chk(self.ctx.L.gcg_swbatch_align(self.ctx.h, self.h, C.byref(P), mode))
+
+    def cells(self) -> int:
+        return int(self.ctx.L.gcg_swbatch_cells(self.h))
+
+    def path_counts(self):
+        c = np.zeros(2, dtype=np.int64)
+        self.ctx._chk(self.ctx.L.gcg_swbatch_path_counts(self.h, c.ctypes.data))
+        return int(c[0]), int(c[1])
+
+    def download(self):
+        res = np.zeros(self.n, dtype=SWRES_DTYPE)
+        pool = C.c_void_p()
+        npool = C.c_int64()
+        self.ctx._chk(self.ctx.L.gcg_swbatch_download(self.ctx.h, self.h, res.ctypes.data, C.byref(pool), C.byref(npool)))
+        try:
+            cp = np.frombuffer((C.c_char * (npool.value * 4)).from_address(pool.value), dtype=np.uint32).copy() if npool.value else np.zeros(0, np.uint32)
+        finally:
+            self.ctx.L.gcg_free(pool)
+        cigs = [cp[int(r["cigar_off"]):int(r["cigar_off"]) + int(r["n_cigar"])] for r in res]
+        return res, cigs

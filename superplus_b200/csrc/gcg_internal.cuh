@@ -1,0 +1,136 @@
+// Internal declarations shared by the translation units of libgcgpu.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/gcgpu.h"
+
+void gcg_set_error (const char * fmt, ...);
+
+#define GCG_CUDA(x)                                                                              \
+  do {                                                                                           \
+    cudaError_t e_ = (x);                                                                        \
+    if (e_ != cudaSuccess) {                                                                     \
+      gcg_set_error ("%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString (e_));           \
+      return GCG_ECUDA;                                                                          \
+    }                                                                                            \
+  } while (0)
+
+#define GCG_CHECK(cond, code, ...)                                                               \
+  do {                                                                                           \
+    if (!(cond)) { gcg_set_error (__VA_ARGS__); return (code); }                                 \
+  } while (0)
+
+struct gcg_prof_entry {
+  double ms = 0.0;
+  int64_t launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+// Staging: pinned host + device ring used to move ASCII sequences (host -> HBM).
+struct gcg_stage {
+  char * h[2] = {nullptr, nullptr};
+  char * d[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  size_t cap = 0;
+};
+
+struct gcg_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int host_threads = 4;
+  cudaStream_t stream = nullptr;
+  bool prof = false;
+  std::map<std::string, gcg_prof_entry> prof_map;
+  int64_t launches = 0;
+  gcg_stage stage;
+  // small device scratch for reductions / counters
+  unsigned long long * d_counters = nullptr;   // 16 x u64
+  unsigned long long * h_counters = nullptr;   // pinned mirror
+};
+
+// RAII scope around one kernel launch: counts it and, when profiling is on, brackets it
+// with CUDA events on the ctx stream (resolved lazily in gcg_prof_report).
+struct gcg_kscope {
+  gcg_ctx * ctx;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const char * name;
+  gcg_kscope (gcg_ctx * c, const char * n) : ctx (c), name (n)
+  {
+    ++ctx->launches;
+    if (ctx->prof) {
+      cudaEventCreate (&e0);
+      cudaEventCreate (&e1);
+      cudaEventRecord (e0, ctx->stream);
+    }
+  }
+  ~gcg_kscope ()
+  {
+    if (ctx->prof) {
+      cudaEventRecord (e1, ctx->stream);
+      gcg_prof_entry & p = ctx->prof_map[name];
+      p.pending.emplace_back (e0, e1);
+      ++p.launches;
+    }
+  }
+};
+
+// ---- device-resident sequence sets ---------------------------------------------------------
+// Layout shared by ASCII staging and the 2-bit stream: sequence i starts at "word" woff[i];
+// a word is 32 bases = 32 ASCII bytes = one uint64 of 2-bit codes, first base in the two most
+// significant bits.  Every sequence is padded to a whole number of words; padding content is
+// never interpreted (positions with pos + k > len are masked).
+struct gcg_ascii {
+  gcg_ctx * ctx = nullptr;
+  int64_t n = 0, n_words = 0, n_bases = 0;
+  char * d_ascii = nullptr;                 // n_words * 32 bytes
+  int64_t * d_woff = nullptr;               // n + 1
+  int32_t * d_len = nullptr;                // n
+  std::vector<int64_t> h_woff;
+  std::vector<int32_t> h_len;
+};
+
+struct gcg_seqs {
+  gcg_ctx * ctx = nullptr;
+  int64_t n = 0, n_words = 0, n_bases = 0;
+  uint64_t * d_packed = nullptr;            // n_words + 2 (slack, zero)
+  int64_t * d_woff = nullptr;               // n + 1
+  int32_t * d_len = nullptr;                // n
+  std::vector<int64_t> h_woff;
+  std::vector<int32_t> h_len;
+};
+
+// ---- contig k-mer table ---------------------------------------------------------------------
+// Open addressing, 32-byte buckets of four 8-byte key words (one DRAM sector per probe).
+//   key word: bits 0..61 = canonical k-mer + 1 (0 = empty), bit 62 = bucket overflowed
+//   (only meaningful on slot 0 of a bucket), bit 63 = seen more than once.
+//   vals[slot]: bit 0 = KMER_REV, bits 1..31 = contig position, bits 32..62 = contig index.
+//   ont[slot/16]: 2 bits per slot, bit0 = anchored >= once, bit1 = anchored >= twice.
+struct gcg_table {
+  gcg_ctx * ctx = nullptr;
+  int k = 0;
+  uint32_t n_bucket = 0;
+  uint64_t n_slot = 0;
+  unsigned long long * d_keys = nullptr;
+  unsigned long long * d_vals = nullptr;
+  uint32_t * d_ont = nullptr;
+  int64_t n_inserted = 0;                  // k-mer occurrences inserted
+};
+
+struct gcg_hits {
+  gcg_ctx * ctx = nullptr;
+  int64_t n = 0;
+  gcg_hit * d_hits = nullptr;
+};
+
+#define GCG_KEY_MASK 0x3FFFFFFFFFFFFFFFULL
+#define GCG_KEY_OVF  0x4000000000000000ULL
+#define GCG_KEY_MULTI 0x8000000000000000ULL
+
+int gcg_stage_reserve (gcg_ctx * ctx);

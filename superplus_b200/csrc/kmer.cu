@@ -1,0 +1,941 @@
+// K1..K6: 2-bit packing, canonical k-mer extraction, open-addressed HBM table build,
+// ONT search with anchor compaction, ONT-side multiplicity and statistics.
+//
+// Reference semantics restated (paths relative to /root/reference/gap_closer):
+//   base code      bio.h:22-24            A=0 C=1 T=2 G=3 (N -> 3), complement = code ^ 2
+//   rolling k-mer  kseq1.h:28-59          fwd = ((fwd<<2)&mask)|b ; rc = (rc>>2)|(comp(b)<<2(k-1))
+//   canonical      kmer.c:86-94, ont.c:161-167   fwd < rc ? (fwd, flag 0) : (rc, flag REV)
+//   table          kmer.c:124-152 -> hash.c:113-152   distinct keys with multiplicity
+//   search         ont.c:141-204          anchor <=> key present with multi == 1
+//   ONT counts     ont.c:230-254          multiplicity of each anchored k-mer over all reads
+//   stats          kmer.c:265-312
+#include <algorithm>
+#include <stdio.h>
+#include <string.h>
+#include <thread>
+
+#include "gcg_internal.cuh"
+
+// =============================================================================================
+// device helpers
+// =============================================================================================
+__device__ __forceinline__ uint32_t pack4 (uint32_t x)
+{
+  // four ASCII bytes (first base in the low byte) -> 8 bits, first base in the top two bits
+  return (((x >> 1) & 0x03030303u) * 0x40100401u) >> 24;
+}
+
+__device__ __forceinline__ uint64_t revcomp64 (uint64_t x, int k)
+{
+  // kseq1.h:37-46: complement (^2 per base), reverse the 2-bit groups, drop the unused tail
+  x ^= 0xAAAAAAAAAAAAAAAAULL;
+  x = ((x & 0x3333333333333333ULL) << 2) | ((x >> 2) & 0x3333333333333333ULL);
+  x = ((x & 0x0F0F0F0F0F0F0F0FULL) << 4) | ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL);
+  uint32_t lo = (uint32_t) x, hi = (uint32_t) (x >> 32);
+  lo = __byte_perm (lo, 0, 0x0123);
+  hi = __byte_perm (hi, 0, 0x0123);
+  x = ((uint64_t) lo << 32) | hi;
+  return x >> (64 - 2 * k);
+}
+
+__device__ __forceinline__ uint32_t kmer_hash32 (uint64_t key)
+{
+  uint32_t h = (uint32_t) key ^ ((uint32_t) (key >> 32) * 0x9E3779B1u);
+  h ^= h >> 16; h *= 0x85EBCA6Bu;
+  h ^= h >> 13; h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+
+// largest s in [0,n) with woff[s] <= w  (woff has n+1 entries, woff[n] > w)
+__device__ __forceinline__ int64_t find_seq (const int64_t * __restrict__ woff, int64_t n, int64_t w)
+{
+  int64_t lo = 0, hi = n;          // invariant: woff[lo] <= w < woff[hi]
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (__ldg (woff + mid) <= w) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// Per-lane rolling state over the 32 k-mer start positions of one packed word.
+struct kroll {
+  uint64_t fwd, rc, nxt, mask;
+  int shift_rc;
+  __device__ __forceinline__ void init (uint64_t hi, uint64_t lo, int k)
+  {
+    mask = (1ULL << (2 * k)) - 1;       // k <= 31
+    fwd = hi >> (64 - 2 * k);
+    rc = revcomp64 (fwd, k);
+    nxt = (hi << (2 * k)) | (lo >> (64 - 2 * k));
+    shift_rc = 2 * (k - 1);
+  }
+  __device__ __forceinline__ void step ()
+  {
+    uint64_t b = nxt >> 62;
+    nxt <<= 2;
+    fwd = ((fwd << 2) | b) & mask;
+    rc = (rc >> 2) | ((b ^ 2ULL) << shift_rc);
+  }
+};
+
+// =============================================================================================
+// K1  ASCII -> 2 bit
+// =============================================================================================
+__global__ void __launch_bounds__ (256)
+k1_pack_kernel (const uint4 * __restrict__ ascii, uint64_t * __restrict__ packed, int64_t n_words)
+{
+  int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t w = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+    uint4 a = __ldg (ascii + 2 * w), b = __ldg (ascii + 2 * w + 1);
+    uint32_t hi = (pack4 (a.x) << 24) | (pack4 (a.y) << 16) | (pack4 (a.z) << 8) | pack4 (a.w);
+    uint32_t lo = (pack4 (b.x) << 24) | (pack4 (b.y) << 16) | (pack4 (b.z) << 8) | pack4 (b.w);
+    packed[w] = ((uint64_t) hi << 32) | lo;
+  }
+}
+
+// =============================================================================================
+// K2+K3  contig chop + table insert
+// =============================================================================================
+__global__ void __launch_bounds__ (256)
+k23_build_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff,
+                  const int32_t * __restrict__ len, int64_t n_seq, int64_t n_words, int k,
+                  unsigned long long * __restrict__ keys, unsigned long long * __restrict__ vals, uint32_t n_bucket)
+{
+  int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t w = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+    int64_t s = find_seq (woff, n_seq, w);
+    int32_t L = __ldg (len + s);
+    int32_t p0 = (int32_t) ((w - __ldg (woff + s)) << 5);
+    int32_t nvalid = L - k + 1 - p0;             // number of valid starts in this word
+    if (nvalid <= 0) continue;
+    if (nvalid > 32) nvalid = 32;
+    kroll r;
+    r.init (packed[w], packed[w + 1], k);
+    for (int j = 0; j < nvalid; ++j) {
+      if (j) r.step ();
+      bool fw = r.fwd < r.rc;
+      unsigned long long key = (fw ? r.fwd : r.rc) + 1ULL;
+      unsigned long long val = ((unsigned long long) s << 32) | ((unsigned long long) (uint32_t) (p0 + j) << 1) | (fw ? 0ULL : 1ULL);
+      uint32_t b = __umulhi (kmer_hash32 (key - 1ULL), n_bucket);
+      for (;;) {
+        unsigned long long * slot = keys + 4ULL * b;
+        bool done = false;
+#pragma unroll
+        for (int i = 0; i < 4 && !done; ++i) {
+          unsigned long long cur = __ldcg (slot + i);
+          if (cur == 0ULL) {
+            unsigned long long old = atomicCAS (slot + i, 0ULL, key);
+            if (old == 0ULL) { vals[4ULL * b + i] = val; done = true; break; }
+            cur = old;
+          }
+          if ((cur & GCG_KEY_MASK) == key) {
+            if (!(cur & GCG_KEY_MULTI)) atomicOr (slot + i, GCG_KEY_MULTI);
+            done = true;
+          }
+        }
+        if (done) break;
+        // bucket is full of other keys: flag the overflow on slot 0 and move on
+        if (!(__ldcg (slot) & GCG_KEY_OVF)) atomicOr (slot, GCG_KEY_OVF);
+        b = (b + 1 == n_bucket) ? 0 : b + 1;
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// K4+K5  ONT chop + lookup + multi==1 filter + ONT-side multiplicity + anchor append
+// =============================================================================================
+#define K4_WARP_CAP 128     // per-warp staging records in shared memory
+
+struct raw_hit { unsigned long long gpos, val; };   // gpos = word*32 + j ; val bit63 = ONT_KMER_REV
+
+template <bool COUNT_ONT>
+__global__ void __launch_bounds__ (256)
+k45_search_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff,
+                   const int32_t * __restrict__ len, int64_t n_seq, int64_t n_words, int k,
+                   const unsigned long long * __restrict__ keys, const unsigned long long * __restrict__ vals,
+                   uint32_t * __restrict__ ont, uint32_t n_bucket,
+                   uint32_t * __restrict__ hitmask, raw_hit * __restrict__ raw, unsigned long long raw_cap,
+                   unsigned long long * __restrict__ raw_count)
+{
+  __shared__ raw_hit s_buf[8][K4_WARP_CAP];
+  __shared__ int s_cnt[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) s_cnt[wid] = 0;
+  __syncwarp ();
+  int64_t n_iter = (n_words + 31) >> 5;                // warp-granular tiles of 32 words
+  int64_t wstride = (int64_t) gridDim.x * (blockDim.x >> 5);
+  for (int64_t tile = (int64_t) blockIdx.x * (blockDim.x >> 5) + wid; tile < n_iter; tile += wstride) {
+    int64_t w = (tile << 5) + lane;
+    int nvalid = 0;
+    int32_t p0 = 0;
+    kroll r;
+    r.fwd = r.rc = r.nxt = r.mask = 0; r.shift_rc = 0;
+    if (w < n_words) {
+      int64_t s = find_seq (woff, n_seq, w);
+      int32_t L = __ldg (len + s);
+      p0 = (int32_t) ((w - __ldg (woff + s)) << 5);
+      nvalid = L - k + 1 - p0;
+      nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
+      if (nvalid) r.init (__ldg (packed + w), __ldg (packed + w + 1), k);
+    }
+    uint32_t mymask = 0;
+    int nmax = __reduce_max_sync (0xffffffffu, nvalid);
+    for (int j = 0; j < nmax; ++j) {
+      bool hit = false;
+      unsigned long long hval = 0;
+      if (j < nvalid) {
+        if (j) r.step ();
+        bool fw = r.fwd < r.rc;
+        unsigned long long key = (fw ? r.fwd : r.rc) + 1ULL;
+        uint32_t b = __umulhi (kmer_hash32 (key - 1ULL), n_bucket);
+        for (;;) {
+          const ulonglong2 * bp = reinterpret_cast<const ulonglong2 *> (keys + 4ULL * b);
+          ulonglong2 q0 = __ldg (bp), q1 = __ldg (bp + 1);
+          int found = -1;
+          unsigned long long fk = 0;
+          if ((q0.x & GCG_KEY_MASK) == key) { found = 0; fk = q0.x; }
+          else if ((q0.y & GCG_KEY_MASK) == key) { found = 1; fk = q0.y; }
+          else if ((q1.x & GCG_KEY_MASK) == key) { found = 2; fk = q1.x; }
+          else if ((q1.y & GCG_KEY_MASK) == key) { found = 3; fk = q1.y; }
+          if (found >= 0) {
+            if (!(fk & GCG_KEY_MULTI)) {            // multi == 1  (ont.c:171,195)
+              unsigned long long slot = 4ULL * b + found;
+              hit = true;
+              hval = __ldg (vals + slot) | (fw ? 0ULL : 0x8000000000000000ULL);
+              if (COUNT_ONT) {
+                // ONT-side multiplicity state (ont.c:245): 2 bits per slot
+                uint32_t sh = (uint32_t) (slot & 15) * 2;
+                uint32_t old = atomicOr (ont + (slot >> 4), 1u << sh);
+                if ((old >> sh) & 1u) { if (!((old >> sh) & 2u)) atomicOr (ont + (slot >> 4), 2u << sh); }
+              }
+            }
+            break;
+          }
+          if (!(q0.x & GCG_KEY_OVF)) break;         // bucket never overflowed: key absent
+          b = (b + 1 == n_bucket) ? 0 : b + 1;
+        }
+      }
+      unsigned bal = __ballot_sync (0xffffffffu, hit);
+      if (bal) {
+        int base = s_cnt[wid];
+        if (hit) {
+          int rank = __popc (bal & ((1u << lane) - 1));
+          raw_hit h; h.gpos = ((unsigned long long) w << 5) | (unsigned) j; h.val = hval;
+          s_buf[wid][base + rank] = h;
+          mymask |= 1u << j;
+        }
+        __syncwarp ();
+        int cnt = base + __popc (bal);
+        if (cnt > K4_WARP_CAP - 32) {               // flush: one global atomic per batch
+          unsigned long long g = 0;
+          if (lane == 0) g = atomicAdd (raw_count, (unsigned long long) cnt);
+          g = __shfl_sync (0xffffffffu, g, 0);
+          for (int i = lane; i < cnt; i += 32) if (g + i < raw_cap) raw[g + i] = s_buf[wid][i];
+          cnt = 0;
+        }
+        __syncwarp ();
+        if (lane == 0) s_cnt[wid] = cnt;
+        __syncwarp ();
+      }
+    }
+    if (w < n_words) hitmask[w] = mymask;
+  }
+  __syncwarp ();
+  int cnt = s_cnt[wid];
+  if (cnt > 0) {
+    unsigned long long g = 0;
+    if (lane == 0) g = atomicAdd (raw_count, (unsigned long long) cnt);
+    g = __shfl_sync (0xffffffffu, g, 0);
+    for (int i = lane; i < cnt; i += 32) if (g + i < raw_cap) raw[g + i] = s_buf[wid][i];
+  }
+}
+
+// ---- ordered compaction: prefix popcount over the per-word hit masks, then scatter ----------
+#define SCAN_ITEMS 8
+#define SCAN_BLOCK 256
+#define SCAN_TILE (SCAN_ITEMS * SCAN_BLOCK)
+
+__global__ void __launch_bounds__ (SCAN_BLOCK)
+scan_reduce_kernel (const uint32_t * __restrict__ mask, int64_t n, uint32_t * __restrict__ block_sum)
+{
+  __shared__ uint32_t s[SCAN_BLOCK / 32];
+  int64_t base = (int64_t) blockIdx.x * SCAN_TILE;
+  uint32_t v = 0;
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    int64_t idx = base + (int64_t) i * SCAN_BLOCK + threadIdx.x;
+    if (idx < n) v += __popc (mask[idx]);
+  }
+  v = __reduce_add_sync (0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads ();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int i = 0; i < SCAN_BLOCK / 32; ++i) t += s[i];
+    block_sum[blockIdx.x] = t;
+  }
+}
+
+// single block: exclusive scan of block sums in place
+__global__ void __launch_bounds__ (1024)
+scan_blocksums_kernel (uint32_t * __restrict__ block_sum, int64_t nb)
+{
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads ();
+  for (int64_t base = 0; base < nb; base += 1024) {
+    int64_t idx = base + threadIdx.x;
+    uint32_t v = idx < nb ? block_sum[idx] : 0, x = v;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+    __syncthreads ();
+    if (threadIdx.x < 32) {
+      uint32_t wv = s_warp[threadIdx.x], wx = wv;
+      for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (0xffffffffu, wx, o); if (threadIdx.x >= o) wx += y; }
+      s_warp[threadIdx.x] = wx - wv;
+    }
+    __syncthreads ();
+    uint32_t excl = x - v + s_warp[threadIdx.x >> 5] + s_carry;
+    if (idx < nb) block_sum[idx] = excl;
+    __syncthreads ();
+    if (threadIdx.x == 1023) s_carry = excl + v;
+    __syncthreads ();
+  }
+}
+
+__global__ void __launch_bounds__ (SCAN_BLOCK)
+scan_apply_kernel (const uint32_t * __restrict__ mask, int64_t n, const uint32_t * __restrict__ block_off,
+                   uint32_t * __restrict__ prefix)
+{
+  // items are laid out blocked-by-thread here so that each thread scans SCAN_ITEMS consecutive words
+  __shared__ uint32_t s_warp[SCAN_BLOCK / 32];
+  int64_t base = (int64_t) blockIdx.x * SCAN_TILE + (int64_t) threadIdx.x * SCAN_ITEMS;
+  uint32_t c[SCAN_ITEMS], t = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) { int64_t idx = base + i; c[i] = idx < n ? __popc (mask[idx]) : 0; t += c[i]; }
+  uint32_t x = t;
+  for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+  __syncthreads ();
+  if (threadIdx.x < 32) {
+    uint32_t wv = threadIdx.x < SCAN_BLOCK / 32 ? s_warp[threadIdx.x] : 0, wx = wv;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (0xffffffffu, wx, o); if (threadIdx.x >= o) wx += y; }
+    if (threadIdx.x < SCAN_BLOCK / 32) s_warp[threadIdx.x] = wx - wv;
+  }
+  __syncthreads ();
+  uint32_t run = x - t + s_warp[threadIdx.x >> 5] + block_off[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) { int64_t idx = base + i; if (idx < n) prefix[idx] = run; run += c[i]; }
+}
+
+__global__ void __launch_bounds__ (256)
+hits_scatter_kernel (const raw_hit * __restrict__ raw, int64_t n_raw, const uint32_t * __restrict__ mask,
+                     const uint32_t * __restrict__ prefix, const int64_t * __restrict__ woff, int64_t n_seq,
+                     gcg_hit * __restrict__ out)
+{
+  int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_raw; i += stride) {
+    raw_hit h = raw[i];
+    int64_t w = (int64_t) (h.gpos >> 5);
+    int j = (int) (h.gpos & 31);
+    uint32_t rank = prefix[w] + __popc (mask[w] & ((1u << j) - 1));
+    int64_t s = find_seq (woff, n_seq, w);
+    gcg_hit o;
+    o.read = (int32_t) s;
+    o.pos = (int32_t) ((w - __ldg (woff + s)) << 5) + j;
+    o.tid = (int32_t) ((h.val >> 32) & 0x7FFFFFFFu);
+    uint32_t cpos = (uint32_t) (h.val >> 1) & 0x7FFFFFFFu;
+    uint32_t flags = (uint32_t) (h.val & 1ULL) | ((h.val >> 63) ? 2u : 0u);
+    o.cpos_flags = (cpos << 2) | flags;
+    out[rank] = o;
+  }
+}
+
+// =============================================================================================
+// K6  statistics
+// =============================================================================================
+__global__ void __launch_bounds__ (256)
+k6_stats_kernel (const unsigned long long * __restrict__ keys, uint64_t n_slot, const uint32_t * __restrict__ ont,
+                 unsigned long long * __restrict__ out4)
+{
+  unsigned long long total = 0, uniq = 0, ot = 0, ou = 0;
+  int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t) n_slot; i += stride) {
+    unsigned long long kw = keys[i];
+    if (kw & GCG_KEY_MASK) { ++total; if (!(kw & GCG_KEY_MULTI)) ++uniq; }
+  }
+  int64_t n_ont = (int64_t) ((n_slot + 15) >> 4);
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_ont; i += stride) {
+    uint32_t v = ont[i];
+    uint32_t ge1 = v & 0x55555555u, ge2 = (v >> 1) & 0x55555555u;
+    ot += __popc (ge1);
+    ou += __popc (ge1 & ~ge2);
+  }
+  for (int o = 16; o; o >>= 1) {
+    total += __shfl_down_sync (0xffffffffu, total, o);
+    uniq += __shfl_down_sync (0xffffffffu, uniq, o);
+    ot += __shfl_down_sync (0xffffffffu, ot, o);
+    ou += __shfl_down_sync (0xffffffffu, ou, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (total) atomicAdd (out4 + 0, total);
+    if (uniq) atomicAdd (out4 + 1, uniq);
+    if (ot) atomicAdd (out4 + 2, ot);
+    if (ou) atomicAdd (out4 + 3, ou);
+  }
+}
+
+__global__ void __launch_bounds__ (256)
+table_dump_kernel (const unsigned long long * __restrict__ keys, const unsigned long long * __restrict__ vals,
+                   uint64_t n_slot, unsigned long long * __restrict__ counter, int64_t cap,
+                   uint64_t * __restrict__ key_out, int32_t * __restrict__ multi, int32_t * __restrict__ tid,
+                   int32_t * __restrict__ pos, uint8_t * __restrict__ rev)
+{
+  int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t) n_slot; i += stride) {
+    unsigned long long kw = keys[i];
+    if (!(kw & GCG_KEY_MASK)) continue;
+    unsigned long long o = atomicAdd (counter, 1ULL);
+    if ((int64_t) o >= cap) continue;
+    unsigned long long v = vals[i];
+    key_out[o] = (kw & GCG_KEY_MASK) - 1ULL;
+    multi[o] = (kw & GCG_KEY_MULTI) ? 2 : 1;
+    tid[o] = (int32_t) ((v >> 32) & 0x7FFFFFFFu);
+    pos[o] = (int32_t) ((v >> 1) & 0x7FFFFFFFu);
+    rev[o] = (uint8_t) (v & 1ULL);
+  }
+}
+
+// =============================================================================================
+// contig chop to kmer_t records (def.h:58-66) for the unchanged host consumers
+// =============================================================================================
+__constant__ uint32_t c_crc_table[256];
+
+struct __align__ (8) kmer_rec { uint64_t kseq; int32_t hs_id, tid, pos; uint16_t flag; int16_t kmer_len; };
+
+__global__ void __launch_bounds__ (256)
+chop_records_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff,
+                     const int32_t * __restrict__ len, const int64_t * __restrict__ koff, int64_t n_seq,
+                     int64_t n_words, int k, uint32_t n_thread, kmer_rec * __restrict__ out)
+{
+  int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t w = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+    int64_t s = find_seq (woff, n_seq, w);
+    int32_t L = __ldg (len + s);
+    int32_t p0 = (int32_t) ((w - __ldg (woff + s)) << 5);
+    int32_t nvalid = L - k + 1 - p0;
+    if (nvalid <= 0) continue;
+    if (nvalid > 32) nvalid = 32;
+    kroll r;
+    r.init (packed[w], packed[w + 1], k);
+    kmer_rec * dst = out + __ldg (koff + s) + p0;
+    for (int j = 0; j < nvalid; ++j) {
+      if (j) r.step ();
+      bool fw = r.fwd < r.rc;
+      uint64_t key = fw ? r.fwd : r.rc;
+      // crc32.h:70-81 over the 8 little-endian bytes of the key (kmer.h:46-49)
+      uint32_t crc = 0xffffffffu;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) crc = c_crc_table[(crc ^ (uint32_t) (key >> (8 * b))) & 0xff] ^ (crc >> 8);
+      crc ^= 0xffffffffu;
+      kmer_rec rec;
+      rec.kseq = key;
+      rec.hs_id = (int32_t) (crc % n_thread);
+      rec.tid = (int32_t) s;
+      rec.pos = p0 + j;
+      rec.flag = fw ? 0 : 1;
+      rec.kmer_len = (int16_t) k;
+      dst[j] = rec;
+    }
+  }
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+static int grid_for (gcg_ctx * ctx, int64_t n_threads_wanted, int block, int max_blocks_per_sm)
+{
+  int64_t nb = (n_threads_wanted + block - 1) / block;
+  int64_t cap = (int64_t) ctx->sm_count * max_blocks_per_sm;
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  return (int) nb;
+}
+
+struct seq_src {
+  const char * const * ptrs = nullptr;   // pointer-array form
+  const char * buf = nullptr;            // concatenated form
+  const int64_t * off = nullptr;
+  const char * at (int64_t i) const { return ptrs ? ptrs[i] : buf + off[i]; }
+};
+
+static int make_layout (const int32_t * len, const int64_t * off, int64_t n, std::vector<int64_t> & woff,
+                        std::vector<int32_t> & hlen, int64_t & n_words, int64_t & n_bases)
+{
+  woff.resize ((size_t) n + 1);
+  hlen.resize ((size_t) n);
+  int64_t w = 0, b = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t l = len ? (int64_t) len[i] : off[i + 1] - off[i];
+    GCG_CHECK (l >= 0 && l <= 0x7FFFFFFF, GCG_ERANGE, "sequence %lld has length %lld outside int32", (long long) i, (long long) l);
+    woff[(size_t) i] = w;
+    hlen[(size_t) i] = (int32_t) l;
+    w += (l + 31) >> 5;
+    b += l;
+  }
+  woff[(size_t) n] = w;
+  n_words = w;
+  n_bases = b;
+  return GCG_OK;
+}
+
+// copy the ASCII bytes that fall into words [w0,w1) into dst (dst[0] is byte 32*w0)
+static void gather_range (const seq_src & src, const std::vector<int64_t> & woff, const std::vector<int32_t> & len,
+                          int64_t s_begin, int64_t s_end, int64_t w0, int64_t w1, char * dst)
+{
+  for (int64_t s = s_begin; s < s_end; ++s) {
+    int64_t sw0 = woff[(size_t) s], l = len[(size_t) s];
+    if (l == 0) continue;
+    int64_t b0 = sw0 * 32, b1 = b0 + l;                 // byte range of the sequence in the flat layout
+    int64_t c0 = std::max (b0, w0 * 32), c1 = std::min (b1, w1 * 32);
+    if (c1 <= c0) continue;
+    memcpy (dst + (c0 - w0 * 32), src.at (s) + (c0 - b0), (size_t) (c1 - c0));
+  }
+}
+
+// Streams the flat ASCII layout to the device in 64 MiB chunks through the pinned ring and calls
+// `consume(d_chunk, w0, nw)` (enqueued on ctx->stream) for each chunk.
+template <class F>
+static int stream_ascii (gcg_ctx * ctx, const seq_src & src, const std::vector<int64_t> & woff,
+                         const std::vector<int32_t> & len, int64_t n, int64_t n_words, F consume)
+{
+  int rc = gcg_stage_reserve (ctx);
+  if (rc) return rc;
+  const int64_t chunk_words = (int64_t) (ctx->stage.cap / 32);
+  bool used[2] = {false, false};
+  int64_t s_lo = 0;
+  int c = 0;
+  for (int64_t w0 = 0; w0 < n_words; w0 += chunk_words, ++c) {
+    int64_t w1 = std::min (n_words, w0 + chunk_words);
+    int slot = c & 1;
+    if (used[slot]) GCG_CUDA (cudaEventSynchronize (ctx->stage.ev[slot]));
+    // sequences overlapping [w0,w1)
+    while (s_lo + 1 < n && woff[(size_t) s_lo + 1] <= w0) ++s_lo;
+    int64_t s_hi = std::upper_bound (woff.begin () + s_lo, woff.begin () + n, w1 - 1) - woff.begin ();
+    if (s_hi > n) s_hi = n;
+    char * dst = ctx->stage.h[slot];
+    int64_t ns = s_hi - s_lo;
+    int nt = ctx->host_threads;
+    if ((w1 - w0) * 32 < (1 << 20) || ns < 2 * nt) nt = 1;
+    if (nt <= 1) gather_range (src, woff, len, s_lo, s_hi, w0, w1, dst);
+    else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nt; ++t) {
+        int64_t a = s_lo + ns * t / nt, b = s_lo + ns * (t + 1) / nt;
+        th.emplace_back ([&, a, b] () { gather_range (src, woff, len, a, b, w0, w1, dst); });
+      }
+      for (auto & t : th) t.join ();
+    }
+    GCG_CUDA (cudaMemcpyAsync (ctx->stage.d[slot], dst, (size_t) (w1 - w0) * 32, cudaMemcpyHostToDevice, ctx->stream));
+    rc = consume (ctx->stage.d[slot], w0, w1 - w0);
+    if (rc) return rc;
+    GCG_CUDA (cudaEventRecord (ctx->stage.ev[slot], ctx->stream));
+    used[slot] = true;
+  }
+  return GCG_OK;
+}
+
+static int launch_pack (gcg_ctx * ctx, const char * d_ascii, uint64_t * d_packed, int64_t nw)
+{
+  if (nw <= 0) return GCG_OK;
+  gcg_kscope ks (ctx, "k1_pack");
+  k1_pack_kernel<<<grid_for (ctx, nw, 256, 8), 256, 0, ctx->stream>>> ((const uint4 *) d_ascii, d_packed, nw);
+  GCG_CUDA (cudaGetLastError ());
+  return GCG_OK;
+}
+
+static int seqs_alloc (gcg_ctx * ctx, gcg_seqs * s)
+{
+  GCG_CUDA (cudaMalloc (&s->d_packed, (size_t) (s->n_words + 2) * 8));
+  GCG_CUDA (cudaMemsetAsync (s->d_packed + s->n_words, 0, 16, ctx->stream));
+  GCG_CUDA (cudaMalloc (&s->d_woff, (size_t) (s->n + 1) * 8));
+  GCG_CUDA (cudaMalloc (&s->d_len, (size_t) std::max<int64_t> (s->n, 1) * 4));
+  GCG_CUDA (cudaMemcpyAsync (s->d_woff, s->h_woff.data (), (size_t) (s->n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (s->n) GCG_CUDA (cudaMemcpyAsync (s->d_len, s->h_len.data (), (size_t) s->n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  return GCG_OK;
+}
+
+static int seqs_upload_impl (gcg_ctx * ctx, const seq_src & src, const int32_t * len, int64_t n, gcg_seqs ** out)
+{
+  GCG_CHECK (ctx && out && n >= 0, GCG_EINVAL, "gcg_seqs_upload: bad argument");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  gcg_seqs * s = new gcg_seqs ();
+  s->ctx = ctx; s->n = n;
+  int rc = make_layout (len, src.off, n, s->h_woff, s->h_len, s->n_words, s->n_bases);
+  if (!rc) rc = seqs_alloc (ctx, s);
+  if (!rc) rc = stream_ascii (ctx, src, s->h_woff, s->h_len, n, s->n_words,
+                              [&] (char * d, int64_t w0, int64_t nw) { return launch_pack (ctx, d, s->d_packed + w0, nw); });
+  if (!rc && cudaStreamSynchronize (ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_seqs_upload: stream sync failed"); rc = GCG_ECUDA; }
+  if (rc) { gcg_seqs_free (s); return rc; }
+  *out = s;
+  return GCG_OK;
+}
+
+extern "C" int gcg_seqs_upload (gcg_ctx * ctx, const char * const * seq, const int32_t * len, int64_t n, gcg_seqs ** out)
+{
+  GCG_CHECK (n == 0 || (seq && len), GCG_EINVAL, "gcg_seqs_upload: NULL input");
+  seq_src src; src.ptrs = seq;
+  return seqs_upload_impl (ctx, src, len, n, out);
+}
+
+extern "C" int gcg_seqs_upload_concat (gcg_ctx * ctx, const char * buf, const int64_t * off, int64_t n, gcg_seqs ** out)
+{
+  GCG_CHECK (off && (buf || n == 0), GCG_EINVAL, "gcg_seqs_upload_concat: NULL input");
+  seq_src src; src.buf = buf; src.off = off;
+  return seqs_upload_impl (ctx, src, nullptr, n, out);
+}
+
+extern "C" int gcg_ascii_upload_concat (gcg_ctx * ctx, const char * buf, const int64_t * off, int64_t n, gcg_ascii ** out)
+{
+  GCG_CHECK (ctx && out && off && n >= 0, GCG_EINVAL, "gcg_ascii_upload_concat: bad argument");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  gcg_ascii * a = new gcg_ascii ();
+  a->ctx = ctx; a->n = n;
+  seq_src src; src.buf = buf; src.off = off;
+  int rc = make_layout (nullptr, off, n, a->h_woff, a->h_len, a->n_words, a->n_bases);
+  if (rc) { delete a; return rc; }
+  GCG_CUDA (cudaMalloc (&a->d_ascii, (size_t) std::max<int64_t> (a->n_words, 1) * 32));
+  GCG_CUDA (cudaMalloc (&a->d_woff, (size_t) (n + 1) * 8));
+  GCG_CUDA (cudaMalloc (&a->d_len, (size_t) std::max<int64_t> (n, 1) * 4));
+  GCG_CUDA (cudaMemcpyAsync (a->d_woff, a->h_woff.data (), (size_t) (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (n) GCG_CUDA (cudaMemcpyAsync (a->d_len, a->h_len.data (), (size_t) n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  rc = stream_ascii (ctx, src, a->h_woff, a->h_len, n, a->n_words, [&] (char * d, int64_t w0, int64_t nw) {
+    GCG_CUDA (cudaMemcpyAsync (a->d_ascii + w0 * 32, d, (size_t) nw * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+    return GCG_OK;
+  });
+  if (!rc) GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+  if (rc) { gcg_ascii_free (a); return rc; }
+  *out = a;
+  return GCG_OK;
+}
+
+extern "C" int gcg_seqs_pack (gcg_ctx * ctx, const gcg_ascii * a, gcg_seqs ** out)
+{
+  GCG_CHECK (ctx && a && out, GCG_EINVAL, "gcg_seqs_pack: bad argument");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  gcg_seqs * s = new gcg_seqs ();
+  s->ctx = ctx; s->n = a->n; s->n_words = a->n_words; s->n_bases = a->n_bases;
+  s->h_woff = a->h_woff; s->h_len = a->h_len;
+  int rc = seqs_alloc (ctx, s);
+  if (!rc) rc = launch_pack (ctx, a->d_ascii, s->d_packed, s->n_words);
+  if (rc) { gcg_seqs_free (s); return rc; }
+  *out = s;
+  return GCG_OK;
+}
+
+extern "C" void gcg_ascii_free (gcg_ascii * a)
+{
+  if (!a) return;
+  cudaFree (a->d_ascii); cudaFree (a->d_woff); cudaFree (a->d_len);
+  delete a;
+}
+
+extern "C" void gcg_seqs_free (gcg_seqs * s)
+{
+  if (!s) return;
+  cudaFree (s->d_packed); cudaFree (s->d_woff); cudaFree (s->d_len);
+  delete s;
+}
+
+extern "C" int64_t gcg_seqs_count (const gcg_seqs * s) { return s ? s->n : 0; }
+extern "C" int64_t gcg_seqs_bases (const gcg_seqs * s) { return s ? s->n_bases : 0; }
+extern "C" int64_t gcg_seqs_kmers (const gcg_seqs * s, int k)
+{
+  if (!s) return 0;
+  int64_t t = 0;
+  for (int32_t l : s->h_len) if (l >= k) t += l - k + 1;
+  return t;
+}
+
+// ---- table ------------------------------------------------------------------------------------
+extern "C" void gcg_table_free (gcg_table * t)
+{
+  if (!t) return;
+  cudaFree (t->d_keys); cudaFree (t->d_vals); cudaFree (t->d_ont);
+  delete t;
+}
+
+extern "C" int gcg_table_build_seqs (gcg_ctx * ctx, const gcg_seqs * contigs, int k, gcg_table ** out)
+{
+  GCG_CHECK (ctx && contigs && out, GCG_EINVAL, "gcg_table_build: bad argument");
+  GCG_CHECK (k >= 1 && k <= 31, GCG_ERANGE, "gcg_table_build: k=%d outside [1,31] (kseq1_t is one uint64, kseq1.h:20,73)", k);
+  GCG_CHECK (contigs->n < 0x7FFFFFFF, GCG_ERANGE, "gcg_table_build: too many contigs");
+  for (int32_t l : contigs->h_len)
+    GCG_CHECK (l <= (1 << 30), GCG_ERANGE, "gcg_table_build: contig longer than 2^30 bases");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  int64_t n_kmers = gcg_seqs_kmers (contigs, k);
+  gcg_table * t = new gcg_table ();
+  t->ctx = ctx; t->k = k;
+  // load factor <= 0.5 over 4-slot buckets
+  int64_t nb = (n_kmers + 1) / 2 + 64;
+  GCG_CHECK (nb < 0xFFFFFFFFLL, GCG_ERANGE, "gcg_table_build: %lld k-mers exceed the bucket index range", (long long) n_kmers);
+  t->n_bucket = (uint32_t) nb;
+  t->n_slot = (uint64_t) nb * 4;
+  t->n_inserted = n_kmers;
+  size_t ont_words = (size_t) ((t->n_slot + 15) >> 4);
+  cudaError_t e;
+  if ((e = cudaMalloc (&t->d_keys, t->n_slot * 8)) != cudaSuccess || (e = cudaMalloc (&t->d_vals, t->n_slot * 8)) != cudaSuccess ||
+      (e = cudaMalloc (&t->d_ont, ont_words * 4)) != cudaSuccess) {
+    gcg_set_error ("gcg_table_build: cudaMalloc of %llu slots failed: %s", (unsigned long long) t->n_slot, cudaGetErrorString (e));
+    gcg_table_free (t);
+    return GCG_ENOMEM;
+  }
+  GCG_CUDA (cudaMemsetAsync (t->d_keys, 0, t->n_slot * 8, ctx->stream));
+  GCG_CUDA (cudaMemsetAsync (t->d_ont, 0, ont_words * 4, ctx->stream));
+  if (contigs->n_words > 0 && n_kmers > 0) {
+    gcg_kscope ks (ctx, "k23_build");
+    k23_build_kernel<<<grid_for (ctx, contigs->n_words, 256, 8), 256, 0, ctx->stream>>> (
+        contigs->d_packed, contigs->d_woff, contigs->d_len, contigs->n, contigs->n_words, k, t->d_keys, t->d_vals, t->n_bucket);
+    GCG_CUDA (cudaGetLastError ());
+  }
+  *out = t;
+  return GCG_OK;
+}
+
+extern "C" int gcg_table_build (gcg_ctx * ctx, const char * const * contig_seq, const int32_t * contig_len,
+                                int32_t n_contig, int k, gcg_table ** out)
+{
+  gcg_seqs * s = nullptr;
+  int rc = gcg_seqs_upload (ctx, contig_seq, contig_len, n_contig, &s);
+  if (rc) return rc;
+  rc = gcg_table_build_seqs (ctx, s, k, out);
+  if (!rc && cudaStreamSynchronize (ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_table_build: sync failed"); rc = GCG_ECUDA; }
+  gcg_seqs_free (s);
+  return rc;
+}
+
+extern "C" int gcg_table_stats (gcg_ctx * ctx, gcg_table * t, int64_t out[4])
+{
+  GCG_CHECK (ctx && t && out, GCG_EINVAL, "gcg_table_stats: bad argument");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  GCG_CUDA (cudaMemsetAsync (ctx->d_counters, 0, 4 * 8, ctx->stream));
+  {
+    gcg_kscope ks (ctx, "k6_stats");
+    k6_stats_kernel<<<grid_for (ctx, (int64_t) t->n_slot, 256, 8), 256, 0, ctx->stream>>> (t->d_keys, t->n_slot, t->d_ont, ctx->d_counters);
+    GCG_CUDA (cudaGetLastError ());
+  }
+  GCG_CUDA (cudaMemcpyAsync (ctx->h_counters, ctx->d_counters, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+  for (int i = 0; i < 4; ++i) out[i] = (int64_t) ctx->h_counters[i];
+  return GCG_OK;
+}
+
+extern "C" int64_t gcg_table_size (gcg_ctx * ctx, gcg_table * t)
+{
+  int64_t st[4];
+  if (gcg_table_stats (ctx, t, st)) return -1;
+  return st[0];
+}
+
+extern "C" int gcg_table_dump (gcg_ctx * ctx, gcg_table * t, int64_t cap, uint64_t * key, int32_t * multi_out,
+                               int32_t * tid, int32_t * pos, uint8_t * rev)
+{
+  GCG_CHECK (ctx && t && cap >= 0, GCG_EINVAL, "gcg_table_dump: bad argument");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  uint64_t * dk; int32_t * dm, * dt, * dp; uint8_t * dr;
+  size_t c = (size_t) std::max<int64_t> (cap, 1);
+  GCG_CUDA (cudaMalloc (&dk, c * 8)); GCG_CUDA (cudaMalloc (&dm, c * 4)); GCG_CUDA (cudaMalloc (&dt, c * 4));
+  GCG_CUDA (cudaMalloc (&dp, c * 4)); GCG_CUDA (cudaMalloc (&dr, c));
+  GCG_CUDA (cudaMemsetAsync (ctx->d_counters + 8, 0, 8, ctx->stream));
+  {
+    gcg_kscope ks (ctx, "table_dump");
+    table_dump_kernel<<<grid_for (ctx, (int64_t) t->n_slot, 256, 8), 256, 0, ctx->stream>>> (
+        t->d_keys, t->d_vals, t->n_slot, ctx->d_counters + 8, cap, dk, dm, dt, dp, dr);
+    GCG_CUDA (cudaGetLastError ());
+  }
+  GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+  GCG_CUDA (cudaMemcpy (key, dk, (size_t) cap * 8, cudaMemcpyDeviceToHost));
+  GCG_CUDA (cudaMemcpy (multi_out, dm, (size_t) cap * 4, cudaMemcpyDeviceToHost));
+  GCG_CUDA (cudaMemcpy (tid, dt, (size_t) cap * 4, cudaMemcpyDeviceToHost));
+  GCG_CUDA (cudaMemcpy (pos, dp, (size_t) cap * 4, cudaMemcpyDeviceToHost));
+  GCG_CUDA (cudaMemcpy (rev, dr, (size_t) cap, cudaMemcpyDeviceToHost));
+  cudaFree (dk); cudaFree (dm); cudaFree (dt); cudaFree (dp); cudaFree (dr);
+  return GCG_OK;
+}
+
+// ---- search -----------------------------------------------------------------------------------
+extern "C" void gcg_hits_free (gcg_hits * h)
+{
+  if (!h) return;
+  cudaFree (h->d_hits);
+  delete h;
+}
+
+extern "C" int64_t gcg_hits_count (const gcg_hits * h) { return h ? h->n : 0; }
+
+extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * reads, int k, gcg_hits ** out)
+{
+  GCG_CHECK (ctx && t && reads && out, GCG_EINVAL, "gcg_search: bad argument");
+  GCG_CHECK (k == t->k, GCG_EINVAL, "gcg_search: k=%d but the table was built with k=%d", k, t->k);
+  GCG_CHECK (reads->n < 0x7FFFFFFF, GCG_ERANGE, "gcg_search: too many reads");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  gcg_hits * h = new gcg_hits ();
+  h->ctx = ctx;
+  int64_t n_words = reads->n_words;
+  int64_t n_kmers = gcg_seqs_kmers (reads, k);
+  if (n_words == 0 || n_kmers == 0) { *out = h; return GCG_OK; }
+
+  uint32_t * d_mask = nullptr, * d_prefix = nullptr, * d_bsum = nullptr;
+  raw_hit * d_raw = nullptr;
+  int64_t nb = (n_words + SCAN_TILE - 1) / SCAN_TILE;
+  int64_t n_tiles = (n_words + 31) >> 5;
+  // Anchors are a few percent of the positions on noisy reads; size the unordered buffer for a
+  // quarter of them.  If that overflows, the first pass has still produced the exact count, the
+  // complete hit masks and the ONT multiplicity state; a second pass (ONT counting off) then
+  // re-emits the records into a buffer of exactly that size.
+  int64_t raw_cap = n_kmers <= (1 << 22) ? n_kmers : std::max<int64_t> (n_kmers / 4, 1 << 22);
+  int rc = GCG_OK;
+  cudaError_t e;
+  if ((e = cudaMalloc (&d_mask, (size_t) n_words * 4)) != cudaSuccess || (e = cudaMalloc (&d_prefix, (size_t) n_words * 4)) != cudaSuccess ||
+      (e = cudaMalloc (&d_bsum, (size_t) nb * 4)) != cudaSuccess || (e = cudaMalloc (&d_raw, (size_t) raw_cap * sizeof (raw_hit))) != cudaSuccess) {
+    gcg_set_error ("gcg_search: cudaMalloc failed: %s", cudaGetErrorString (e));
+    rc = GCG_ENOMEM;
+  }
+  for (int pass = 0; pass < 2 && !rc; ++pass) {
+    GCG_CUDA (cudaMemsetAsync (ctx->d_counters + 4, 0, 8, ctx->stream));
+    {
+      gcg_kscope ks (ctx, pass == 0 ? "k45_search" : "k45_search_retry");
+      int grid = grid_for (ctx, n_tiles * 32, 256, 6);
+      if (pass == 0)
+        k45_search_kernel<true><<<grid, 256, 0, ctx->stream>>> (
+            reads->d_packed, reads->d_woff, reads->d_len, reads->n, n_words, k, t->d_keys, t->d_vals, t->d_ont, t->n_bucket,
+            d_mask, d_raw, (unsigned long long) raw_cap, ctx->d_counters + 4);
+      else
+        k45_search_kernel<false><<<grid, 256, 0, ctx->stream>>> (
+            reads->d_packed, reads->d_woff, reads->d_len, reads->n, n_words, k, t->d_keys, t->d_vals, t->d_ont, t->n_bucket,
+            d_mask, d_raw, (unsigned long long) raw_cap, ctx->d_counters + 4);
+      GCG_CUDA (cudaGetLastError ());
+    }
+    GCG_CUDA (cudaMemcpyAsync (ctx->h_counters + 4, ctx->d_counters + 4, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+    int64_t n_raw = (int64_t) ctx->h_counters[4];
+    if (n_raw > raw_cap) {
+      if (pass == 1) { gcg_set_error ("gcg_search: anchor buffer overflow on retry"); rc = GCG_ERANGE; break; }
+      cudaFree (d_raw); d_raw = nullptr;
+      raw_cap = n_raw;
+      if ((e = cudaMalloc (&d_raw, (size_t) raw_cap * sizeof (raw_hit))) != cudaSuccess) {
+        gcg_set_error ("gcg_search: cudaMalloc failed: %s", cudaGetErrorString (e));
+        rc = GCG_ENOMEM;
+      }
+      continue;
+    }
+    h->n = n_raw;
+    if (n_raw > 0) {
+      GCG_CHECK (n_raw < 0xFFFFFFFFLL, GCG_ERANGE, "gcg_search: more than 2^32 anchors in one call");
+      GCG_CUDA (cudaMalloc (&h->d_hits, (size_t) n_raw * sizeof (gcg_hit)));
+      { gcg_kscope ks (ctx, "scan_reduce");
+        scan_reduce_kernel<<<(unsigned) nb, SCAN_BLOCK, 0, ctx->stream>>> (d_mask, n_words, d_bsum); }
+      { gcg_kscope ks (ctx, "scan_blocksums");
+        scan_blocksums_kernel<<<1, 1024, 0, ctx->stream>>> (d_bsum, nb); }
+      { gcg_kscope ks (ctx, "scan_apply");
+        scan_apply_kernel<<<(unsigned) nb, SCAN_BLOCK, 0, ctx->stream>>> (d_mask, n_words, d_bsum, d_prefix); }
+      { gcg_kscope ks (ctx, "hits_scatter");
+        hits_scatter_kernel<<<grid_for (ctx, n_raw, 256, 8), 256, 0, ctx->stream>>> (d_raw, n_raw, d_mask, d_prefix, reads->d_woff, reads->n, h->d_hits); }
+      GCG_CUDA (cudaGetLastError ());
+      GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+    }
+    break;
+  }
+  cudaFree (d_mask); cudaFree (d_prefix); cudaFree (d_bsum); cudaFree (d_raw);
+  if (rc) { gcg_hits_free (h); return rc; }
+  *out = h;
+  return GCG_OK;
+}
+
+extern "C" int gcg_hits_download (gcg_ctx * ctx, const gcg_hits * h, gcg_hit * dst, int64_t cap)
+{
+  GCG_CHECK (ctx && h && (dst || cap == 0), GCG_EINVAL, "gcg_hits_download: bad argument");
+  int64_t n = std::min (cap, h->n);
+  if (n > 0) {
+    GCG_CUDA (cudaMemcpyAsync (dst, h->d_hits, (size_t) n * sizeof (gcg_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+  }
+  return GCG_OK;
+}
+
+extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
+                           int64_t n_read, int k, gcg_hit ** hits_out, int64_t * n_hit)
+{
+  GCG_CHECK (hits_out && n_hit, GCG_EINVAL, "gcg_search: NULL output");
+  gcg_seqs * s = nullptr;
+  gcg_hits * h = nullptr;
+  int rc = gcg_seqs_upload (ctx, read_seq, read_len, n_read, &s);
+  if (rc) return rc;
+  rc = gcg_search_seqs (ctx, t, s, k, &h);
+  gcg_seqs_free (s);
+  if (rc) return rc;
+  *n_hit = h->n;
+  *hits_out = nullptr;
+  if (h->n > 0) {
+    cudaError_t e = cudaHostAlloc ((void **) hits_out, (size_t) h->n * sizeof (gcg_hit), cudaHostAllocDefault);
+    if (e != cudaSuccess) { gcg_set_error ("gcg_search: pinned alloc failed: %s", cudaGetErrorString (e)); gcg_hits_free (h); return GCG_ENOMEM; }
+    rc = gcg_hits_download (ctx, h, *hits_out, h->n);
+  }
+  gcg_hits_free (h);
+  return rc;
+}
+
+// ---- contig chop to host kmer_t arrays --------------------------------------------------------
+static bool g_crc_ready = false;
+static int crc_table_upload ()
+{
+  if (g_crc_ready) return GCG_OK;
+  uint32_t tbl[256];
+  for (uint32_t i = 0; i < 256; ++i) {          // reflected CRC-32, polynomial 0xEDB88320 (== crc32.h:15-68)
+    uint32_t c = i;
+    for (int j = 0; j < 8; ++j) c = (c & 1) ? (0xEDB88320u ^ (c >> 1)) : (c >> 1);
+    tbl[i] = c;
+  }
+  GCG_CUDA (cudaMemcpyToSymbol (c_crc_table, tbl, sizeof tbl));
+  g_crc_ready = true;
+  return GCG_OK;
+}
+
+extern "C" int gcg_chop_contigs (gcg_ctx * ctx, const gcg_seqs * contigs, int k, int n_thread,
+                                 void * const * kmers_out, int32_t * n_kmer_out)
+{
+  GCG_CHECK (ctx && contigs && kmers_out && n_kmer_out, GCG_EINVAL, "gcg_chop_contigs: bad argument");
+  GCG_CHECK (k >= 1 && k <= 31 && n_thread >= 1, GCG_ERANGE, "gcg_chop_contigs: k=%d n_thread=%d out of range", k, n_thread);
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  int rc = crc_table_upload ();
+  if (rc) return rc;
+  int64_t n = contigs->n;
+  std::vector<int64_t> koff ((size_t) n + 1);
+  int64_t tot = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    koff[(size_t) i] = tot;
+    int32_t l = contigs->h_len[(size_t) i];
+    n_kmer_out[i] = l >= k ? l - k + 1 : 0;
+    tot += n_kmer_out[i];
+  }
+  koff[(size_t) n] = tot;
+  if (tot == 0) return GCG_OK;
+  int64_t * d_koff; kmer_rec * d_rec;
+  GCG_CUDA (cudaMalloc (&d_koff, (size_t) (n + 1) * 8));
+  GCG_CUDA (cudaMalloc (&d_rec, (size_t) tot * sizeof (kmer_rec)));
+  GCG_CUDA (cudaMemcpyAsync (d_koff, koff.data (), (size_t) (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    gcg_kscope ks (ctx, "chop_records");
+    chop_records_kernel<<<grid_for (ctx, contigs->n_words, 256, 8), 256, 0, ctx->stream>>> (
+        contigs->d_packed, contigs->d_woff, contigs->d_len, d_koff, n, contigs->n_words, k, (uint32_t) n_thread, d_rec);
+    GCG_CUDA (cudaGetLastError ());
+  }
+  GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+  for (int64_t i = 0; i < n; ++i)
+    if (n_kmer_out[i] > 0)
+      GCG_CUDA (cudaMemcpy (kmers_out[i], d_rec + koff[(size_t) i], (size_t) n_kmer_out[i] * sizeof (kmer_rec), cudaMemcpyDeviceToHost));
+  cudaFree (d_koff); cudaFree (d_rec);
+  return GCG_OK;
+}

@@ -95,9 +95,18 @@ def mutate(seq: np.ndarray, err: float, rng: np.random.Generator) -> np.ndarray:
 
 
 def make_gap_closer_input(genome_len: int, n_gaps: int, coverage: float, seed: int,
-                          err: float = 0.10, mean_len: float = 10_000.0) -> GapCloserInput:
+                          err: float = 0.10, mean_len: float = 10_000.0, n_repeats: int = 0) -> GapCloserInput:
     rng = np.random.Generator(np.random.PCG64(seed))
     genome = random_genome(genome_len, rng)
+    # optional repeats (forward or reverse-complement copies) so that multi >= 2 k-mers exist
+    for _ in range(n_repeats):
+        L = int(rng.integers(200, 3000))
+        a = int(rng.integers(0, genome_len - L))
+        b = int(rng.integers(0, genome_len - L))
+        seg = genome[a:a + L].copy()
+        if rng.random() < 0.5:
+            seg = revcomp(seg)
+        genome[b:b + L] = seg
     scaffold = genome.copy()
     gaps = []
     if n_gaps > 0:
@@ -158,6 +167,7 @@ CONFIGS = {
     # small cases for unit tests
     "tiny": dict(genome_len=60_000, n_gaps=4, coverage=8.0, seed=7),
     "small": dict(genome_len=200_000, n_gaps=10, coverage=10.0, seed=11),
+    "repeats": dict(genome_len=120_000, n_gaps=6, coverage=6.0, seed=13, n_repeats=25),
 }
 
 

@@ -1,0 +1,109 @@
+"""GPU parity: CUDA k-mer path (through the C ABI) vs the CPU oracle, bit exact."""
+import numpy as np
+import pytest
+
+from superplus_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def asc(s):
+    return np.frombuffer(s.encode(), dtype=np.uint8).copy()
+
+
+def check_case(ctx, oracle, contigs, reads, k, via_ptrs=False):
+    # ---- oracle
+    h = oracle.table_build(contigs, k)
+    o_st = oracle.table_stats(h)
+    o_key, o_multi, o_tid, o_pos, o_rev = oracle.table_dump(h)
+    o_hits, o_ont = oracle.search(h, reads, k)
+    oracle.table_free(h)
+    # ---- CUDA
+    up = ctx.upload_ptrs if via_ptrs else ctx.upload
+    cs = up(contigs)
+    rs = up(reads)
+    assert cs.bases == sum(len(c) for c in contigs) and rs.kmers(k) == sum(max(0, len(r) - k + 1) for r in reads)
+    t = ctx.table_build(cs, k)
+    g_key, g_multi, g_tid, g_pos, g_rev = t.dump()
+    assert np.array_equal(g_key, o_key)
+    assert np.array_equal(g_multi, np.minimum(o_multi, 2))
+    u = o_multi == 1
+    assert np.array_equal(g_tid[u], o_tid[u]) and np.array_equal(g_pos[u], o_pos[u]) and np.array_equal(g_rev[u], o_rev[u])
+    hits = ctx.search(t, rs)
+    st = t.stats()
+    assert st[:2] == o_st, (st, o_st)
+    assert st[2:] == o_ont, (st, o_ont)
+    assert len(hits) == len(o_hits["read"])
+    assert np.array_equal(hits["read"], o_hits["read"].astype(np.int32))
+    assert np.array_equal(hits["pos"], o_hits["pos"])
+    assert np.array_equal(hits["tid"], o_hits["tid"])
+    assert np.array_equal(hits["cpos_flags"] >> 2, o_hits["cpos"].astype(np.uint32))
+    assert np.array_equal(hits["cpos_flags"] & 1, o_hits["krev"])
+    assert np.array_equal((hits["cpos_flags"] >> 1) & 1, o_hits["orev"])
+    # kmer_t records for the unchanged host consumers
+    recs = ctx.chop_contigs(cs, [len(c) for c in contigs], k, n_thread=3)
+    for i, c in enumerate(contigs):
+        ks, rv = oracle.chop(c, k)
+        r = recs[i]
+        assert np.array_equal(r["kseq"], ks) and np.array_equal(r["flag"], rv)
+        assert np.all(r["tid"] == i) and np.array_equal(r["pos"], np.arange(len(ks), dtype=np.int32)) and np.all(r["kmer_len"] == k)
+    t.free(); cs.free(); rs.free()
+    return len(hits)
+
+
+@pytest.mark.parametrize("name,k", [("tiny", 25), ("repeats", 25), ("repeats", 17), ("small", 31), ("tiny", 5)])
+def test_synthetic_parity(ctx, oracle, name, k):
+    inp = synth.make_config(name)
+    n = check_case(ctx, oracle, inp.contigs, inp.reads, k)
+    assert n > 0 or k < 12      # short k: every k-mer repeats, nothing anchors
+
+
+def test_pointer_entry_point(ctx, oracle):
+    inp = synth.make_config("tiny")
+    check_case(ctx, oracle, inp.contigs, inp.reads, 25, via_ptrs=True)
+
+
+def test_edge_cases(ctx, oracle):
+    rng = np.random.default_rng(3)
+    g = synth.random_genome(5000, rng)
+    contigs = [g[:40], g[40:40], g[100:124], g[200:225], g[300:1500], asc("acgtnACGTN" * 9), g[2000:5000], g[300:900]]
+    reads = [g[0:0], g[5:20], g[200:225], g[190:260], asc("NNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNN"), g[310:1400],
+             synth.revcomp(g[2100:4000]), np.char.lower(g[2500:2600].view("S1")).view(np.uint8).copy(),
+             asc("ACGTNRYKM" * 20), g[299:325]]
+    for k in (25, 24, 31, 1, 13):
+        check_case(ctx, oracle, contigs, reads, k)
+
+
+def test_empty_inputs(ctx, oracle):
+    rng = np.random.default_rng(4)
+    g = synth.random_genome(300, rng)
+    check_case(ctx, oracle, [g], [], 25)
+    check_case(ctx, oracle, [], [g], 25)
+    check_case(ctx, oracle, [g[:10]], [g], 25)
+
+
+def test_search_host_form(ctx, oracle):
+    inp = synth.make_config("tiny")
+    cs = ctx.upload(inp.contigs)
+    t = ctx.table_build(cs, 25)
+    a = ctx.search_host(t, inp.reads)
+    rs = ctx.upload(inp.reads)
+    b = ctx.search(t, rs)
+    assert np.array_equal(a, b)
+    t.free(); cs.free(); rs.free()
+
+
+def test_error_paths(ctx):
+    inp = synth.make_config("tiny")
+    cs = ctx.upload(inp.contigs)
+    with pytest.raises(api.GcgError):
+        ctx.table_build(cs, 32)
+    with pytest.raises(api.GcgError):
+        ctx.table_build(cs, 0)
+    t = ctx.table_build(cs, 25)
+    t.k = 21
+    rs = ctx.upload(inp.reads[:2])
+    with pytest.raises(api.GcgError):
+        ctx.search(t, rs)
+    t.k = 25
+    t.free(); cs.free(); rs.free()
