@@ -38,6 +38,8 @@ struct gcg_stage {
   char * h[2] = {nullptr, nullptr};
   char * d[2] = {nullptr, nullptr};
   cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool busy[2] = {false, false};      // an async copy out of h[i] has been enqueued and not yet waited for
+  int next = 0;                       // slot the next staged chunk uses
   size_t cap = 0;
 };
 

@@ -144,111 +144,94 @@ k23_build_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
 }
 
 // =============================================================================================
-// K4+K5  ONT chop + lookup + multi==1 filter + ONT-side multiplicity + anchor append
+// K4+K5  ONT chop + lookup + multi==1 filter + ONT-side multiplicity
+//   One thread per packed word (32 k-mer start positions).  Each probe is ONE 256-bit load of a
+//   32-byte bucket (LDG.E.256: one L1 wavefront and one L2/DRAM sector per lookup).  Probes are
+//   issued four at a time so every thread keeps four sectors in flight.  The kernel only records
+//   a 32-bit anchor mask per word (plain coalesced store) and the ONT multiplicity state; the
+//   anchors themselves are emitted in (read,pos) order by hits_emit_kernel after a prefix sum
+//   over the masks, which re-probes just the anchored positions (a few percent).
 // =============================================================================================
-#define K4_WARP_CAP 128     // per-warp staging records in shared memory
+struct __align__ (32) bucket4 { unsigned long long a, b, c, d; };
 
-struct raw_hit { unsigned long long gpos, val; };   // gpos = word*32 + j ; val bit63 = ONT_KMER_REV
+__device__ __forceinline__ bucket4 ld_bucket (const unsigned long long * p)
+{
+  bucket4 r;
+  asm volatile ("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p));
+  return r;
+}
 
-template <bool COUNT_ONT>
+// slot index (0..3) of `key` in the bucket or -1; *kw receives the matching key word
+__device__ __forceinline__ int bucket_find (const bucket4 & q, unsigned long long key, unsigned long long * kw)
+{
+  if ((q.a & GCG_KEY_MASK) == key) { *kw = q.a; return 0; }
+  if ((q.b & GCG_KEY_MASK) == key) { *kw = q.b; return 1; }
+  if ((q.c & GCG_KEY_MASK) == key) { *kw = q.c; return 2; }
+  if ((q.d & GCG_KEY_MASK) == key) { *kw = q.d; return 3; }
+  return -1;
+}
+
+// full probe sequence starting from an already loaded home bucket; returns slot index or ~0
+__device__ __forceinline__ unsigned long long table_lookup (const unsigned long long * __restrict__ keys, uint32_t n_bucket,
+                                                           uint32_t b, bucket4 q, unsigned long long key, unsigned long long * kw)
+{
+  for (;;) {
+    int f = bucket_find (q, key, kw);
+    if (f >= 0) return 4ULL * b + f;
+    if (!(q.a & GCG_KEY_OVF)) return ~0ULL;          // bucket never overflowed: key absent
+    b = (b + 1 == n_bucket) ? 0 : b + 1;
+    q = ld_bucket (keys + 4ULL * b);
+  }
+}
+
+#define K4_UNROLL 4
+
 __global__ void __launch_bounds__ (256)
 k45_search_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff,
                    const int32_t * __restrict__ len, int64_t n_seq, int64_t n_words, int k,
-                   const unsigned long long * __restrict__ keys, const unsigned long long * __restrict__ vals,
-                   uint32_t * __restrict__ ont, uint32_t n_bucket,
-                   uint32_t * __restrict__ hitmask, raw_hit * __restrict__ raw, unsigned long long raw_cap,
-                   unsigned long long * __restrict__ raw_count)
+                   const unsigned long long * __restrict__ keys, uint32_t * __restrict__ ont, uint32_t n_bucket,
+                   uint32_t * __restrict__ hitmask)
 {
-  __shared__ raw_hit s_buf[8][K4_WARP_CAP];
-  __shared__ int s_cnt[8];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) s_cnt[wid] = 0;
-  __syncwarp ();
-  int64_t n_iter = (n_words + 31) >> 5;                // warp-granular tiles of 32 words
-  int64_t wstride = (int64_t) gridDim.x * (blockDim.x >> 5);
-  for (int64_t tile = (int64_t) blockIdx.x * (blockDim.x >> 5) + wid; tile < n_iter; tile += wstride) {
-    int64_t w = (tile << 5) + lane;
-    int nvalid = 0;
-    int32_t p0 = 0;
-    kroll r;
-    r.fwd = r.rc = r.nxt = r.mask = 0; r.shift_rc = 0;
-    if (w < n_words) {
-      int64_t s = find_seq (woff, n_seq, w);
-      int32_t L = __ldg (len + s);
-      p0 = (int32_t) ((w - __ldg (woff + s)) << 5);
-      nvalid = L - k + 1 - p0;
-      nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
-      if (nvalid) r.init (__ldg (packed + w), __ldg (packed + w + 1), k);
-    }
+  int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t w = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+    int64_t s = find_seq (woff, n_seq, w);
+    int32_t L = __ldg (len + s);
+    int32_t p0 = (int32_t) ((w - __ldg (woff + s)) << 5);
+    int nvalid = L - k + 1 - p0;
+    nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
     uint32_t mymask = 0;
-    int nmax = __reduce_max_sync (0xffffffffu, nvalid);
-    for (int j = 0; j < nmax; ++j) {
-      bool hit = false;
-      unsigned long long hval = 0;
-      if (j < nvalid) {
-        if (j) r.step ();
-        bool fw = r.fwd < r.rc;
-        unsigned long long key = (fw ? r.fwd : r.rc) + 1ULL;
-        uint32_t b = __umulhi (kmer_hash32 (key - 1ULL), n_bucket);
-        for (;;) {
-          const ulonglong2 * bp = reinterpret_cast<const ulonglong2 *> (keys + 4ULL * b);
-          ulonglong2 q0 = __ldg (bp), q1 = __ldg (bp + 1);
-          int found = -1;
-          unsigned long long fk = 0;
-          if ((q0.x & GCG_KEY_MASK) == key) { found = 0; fk = q0.x; }
-          else if ((q0.y & GCG_KEY_MASK) == key) { found = 1; fk = q0.y; }
-          else if ((q1.x & GCG_KEY_MASK) == key) { found = 2; fk = q1.x; }
-          else if ((q1.y & GCG_KEY_MASK) == key) { found = 3; fk = q1.y; }
-          if (found >= 0) {
-            if (!(fk & GCG_KEY_MULTI)) {            // multi == 1  (ont.c:171,195)
-              unsigned long long slot = 4ULL * b + found;
-              hit = true;
-              hval = __ldg (vals + slot) | (fw ? 0ULL : 0x8000000000000000ULL);
-              if (COUNT_ONT) {
-                // ONT-side multiplicity state (ont.c:245): 2 bits per slot
-                uint32_t sh = (uint32_t) (slot & 15) * 2;
-                uint32_t old = atomicOr (ont + (slot >> 4), 1u << sh);
-                if ((old >> sh) & 1u) { if (!((old >> sh) & 2u)) atomicOr (ont + (slot >> 4), 2u << sh); }
-              }
+    if (nvalid) {
+      kroll r;
+      r.init (__ldg (packed + w), __ldg (packed + w + 1), k);
+      for (int j0 = 0; j0 < nvalid; j0 += K4_UNROLL) {
+        unsigned long long key[K4_UNROLL];
+        uint32_t bk[K4_UNROLL];
+        bucket4 q[K4_UNROLL];
+#pragma unroll
+        for (int u = 0; u < K4_UNROLL; ++u) {
+          if (j0 + u) r.step ();                     // harmless past nvalid: state is discarded
+          key[u] = (r.fwd < r.rc ? r.fwd : r.rc) + 1ULL;
+          bk[u] = __umulhi (kmer_hash32 (key[u] - 1ULL), n_bucket);
+          q[u] = ld_bucket (keys + 4ULL * bk[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < K4_UNROLL; ++u) {
+          if (j0 + u < nvalid) {
+            unsigned long long kw;
+            unsigned long long slot = table_lookup (keys, n_bucket, bk[u], q[u], key[u], &kw);
+            if (slot != ~0ULL && !(kw & GCG_KEY_MULTI)) {      // multi == 1  (ont.c:171,195)
+              mymask |= 1u << (j0 + u);
+              // ONT-side multiplicity state (ont.c:245): 2 bits per slot
+              uint32_t sh = (uint32_t) (slot & 15) * 2;
+              uint32_t old = atomicOr (ont + (slot >> 4), 1u << sh);
+              if (((old >> sh) & 3u) == 1u) atomicOr (ont + (slot >> 4), 2u << sh);
             }
-            break;
           }
-          if (!(q0.x & GCG_KEY_OVF)) break;         // bucket never overflowed: key absent
-          b = (b + 1 == n_bucket) ? 0 : b + 1;
         }
-      }
-      unsigned bal = __ballot_sync (0xffffffffu, hit);
-      if (bal) {
-        int base = s_cnt[wid];
-        if (hit) {
-          int rank = __popc (bal & ((1u << lane) - 1));
-          raw_hit h; h.gpos = ((unsigned long long) w << 5) | (unsigned) j; h.val = hval;
-          s_buf[wid][base + rank] = h;
-          mymask |= 1u << j;
-        }
-        __syncwarp ();
-        int cnt = base + __popc (bal);
-        if (cnt > K4_WARP_CAP - 32) {               // flush: one global atomic per batch
-          unsigned long long g = 0;
-          if (lane == 0) g = atomicAdd (raw_count, (unsigned long long) cnt);
-          g = __shfl_sync (0xffffffffu, g, 0);
-          for (int i = lane; i < cnt; i += 32) if (g + i < raw_cap) raw[g + i] = s_buf[wid][i];
-          cnt = 0;
-        }
-        __syncwarp ();
-        if (lane == 0) s_cnt[wid] = cnt;
-        __syncwarp ();
       }
     }
-    if (w < n_words) hitmask[w] = mymask;
-  }
-  __syncwarp ();
-  int cnt = s_cnt[wid];
-  if (cnt > 0) {
-    unsigned long long g = 0;
-    if (lane == 0) g = atomicAdd (raw_count, (unsigned long long) cnt);
-    g = __shfl_sync (0xffffffffu, g, 0);
-    for (int i = lane; i < cnt; i += 32) if (g + i < raw_cap) raw[g + i] = s_buf[wid][i];
+    hitmask[w] = mymask;
   }
 }
 
@@ -279,7 +262,7 @@ scan_reduce_kernel (const uint32_t * __restrict__ mask, int64_t n, uint32_t * __
 
 // single block: exclusive scan of block sums in place
 __global__ void __launch_bounds__ (1024)
-scan_blocksums_kernel (uint32_t * __restrict__ block_sum, int64_t nb)
+scan_blocksums_kernel (uint32_t * __restrict__ block_sum, int64_t nb, unsigned long long * __restrict__ total)
 {
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
@@ -303,6 +286,7 @@ scan_blocksums_kernel (uint32_t * __restrict__ block_sum, int64_t nb)
     if (threadIdx.x == 1023) s_carry = excl + v;
     __syncthreads ();
   }
+  if (threadIdx.x == 0) *total = s_carry;
 }
 
 __global__ void __launch_bounds__ (SCAN_BLOCK)
@@ -330,26 +314,57 @@ scan_apply_kernel (const uint32_t * __restrict__ mask, int64_t n, const uint32_t
   for (int i = 0; i < SCAN_ITEMS; ++i) { int64_t idx = base + i; if (idx < n) prefix[idx] = run; run += c[i]; }
 }
 
+// anchors in (read,pos) order.  A warp owns 32 consecutive words; the set bits of their masks
+// are dealt round-robin to the lanes (balanced, independent loads, coalesced output).  Only the
+// anchored positions (a few percent) are re-probed here to fetch (tid,pos,flag).
 __global__ void __launch_bounds__ (256)
-hits_scatter_kernel (const raw_hit * __restrict__ raw, int64_t n_raw, const uint32_t * __restrict__ mask,
-                     const uint32_t * __restrict__ prefix, const int64_t * __restrict__ woff, int64_t n_seq,
-                     gcg_hit * __restrict__ out)
+hits_emit_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff, int64_t n_seq,
+                  int64_t n_words, int k, const unsigned long long * __restrict__ keys,
+                  const unsigned long long * __restrict__ vals, uint32_t n_bucket,
+                  const uint32_t * __restrict__ mask, const uint32_t * __restrict__ prefix, gcg_hit * __restrict__ out)
 {
-  int64_t stride = (int64_t) gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_raw; i += stride) {
-    raw_hit h = raw[i];
-    int64_t w = (int64_t) (h.gpos >> 5);
-    int j = (int) (h.gpos & 31);
-    uint32_t rank = prefix[w] + __popc (mask[w] & ((1u << j) - 1));
-    int64_t s = find_seq (woff, n_seq, w);
-    gcg_hit o;
-    o.read = (int32_t) s;
-    o.pos = (int32_t) ((w - __ldg (woff + s)) << 5) + j;
-    o.tid = (int32_t) ((h.val >> 32) & 0x7FFFFFFFu);
-    uint32_t cpos = (uint32_t) (h.val >> 1) & 0x7FFFFFFFu;
-    uint32_t flags = (uint32_t) (h.val & 1ULL) | ((h.val >> 63) ? 2u : 0u);
-    o.cpos_flags = (cpos << 2) | flags;
-    out[rank] = o;
+  __shared__ uint32_t s_excl[8][33];
+  __shared__ uint32_t s_mask[8][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int64_t n_tiles = (n_words + 31) >> 5;
+  int64_t wstride = (int64_t) gridDim.x * (blockDim.x >> 5);
+  for (int64_t tile = (int64_t) blockIdx.x * (blockDim.x >> 5) + wid; tile < n_tiles; tile += wstride) {
+    int64_t w = (tile << 5) + lane;
+    uint32_t m = w < n_words ? mask[w] : 0;
+    uint32_t c = __popc (m), x = c;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (0xffffffffu, x, o); if (lane >= o) x += y; }
+    uint32_t total = __shfl_sync (0xffffffffu, x, 31);
+    if (total == 0) continue;
+    uint32_t base = prefix[tile << 5];
+    __syncwarp ();
+    s_excl[wid][lane] = x - c;
+    s_mask[wid][lane] = m;
+    if (lane == 31) s_excl[wid][32] = total;
+    __syncwarp ();
+    for (uint32_t h = lane; h < total; h += 32) {
+      int lo = 0, hi = 32;                          // s_excl[lo] <= h < s_excl[hi]
+#pragma unroll
+      for (int it = 0; it < 5; ++it) { int mid = (lo + hi) >> 1; if (s_excl[wid][mid] <= h) lo = mid; else hi = mid; }
+      uint32_t mm = s_mask[wid][lo];
+      int j = __fns (mm, 0, (int) (h - s_excl[wid][lo]) + 1);
+      int64_t ww = (tile << 5) + lo;
+      int64_t s = find_seq (woff, n_seq, ww);
+      int32_t p0 = (int32_t) ((ww - __ldg (woff + s)) << 5);
+      uint64_t wh = __ldg (packed + ww), wl = __ldg (packed + ww + 1);
+      uint64_t xw = j ? ((wh << (2 * j)) | (wl >> (64 - 2 * j))) : wh;
+      uint64_t fwd = xw >> (64 - 2 * k), rc = revcomp64 (fwd, k);
+      bool fw = fwd < rc;
+      unsigned long long key = (fw ? fwd : rc) + 1ULL, kw;
+      uint32_t b = __umulhi (kmer_hash32 (key - 1ULL), n_bucket);
+      unsigned long long slot = table_lookup (keys, n_bucket, b, ld_bucket (keys + 4ULL * b), key, &kw);
+      unsigned long long v = __ldg (vals + slot);   // slot is valid: the mask bit says the key is present
+      int4 hh;                                      // gcg_hit {read, pos, tid, cpos_flags} as one 16-byte store
+      hh.x = (int32_t) s;
+      hh.y = p0 + j;
+      hh.z = (int32_t) ((v >> 32) & 0x7FFFFFFFu);
+      hh.w = (int32_t) ((((uint32_t) (v >> 1) & 0x3FFFFFFFu) << 2) | (uint32_t) (v & 1ULL) | (fw ? 0u : 2u));
+      reinterpret_cast<int4 *> (out)[base + h] = hh;
+    }
   }
 }
 
@@ -514,13 +529,13 @@ static int stream_ascii (gcg_ctx * ctx, const seq_src & src, const std::vector<i
   int rc = gcg_stage_reserve (ctx);
   if (rc) return rc;
   const int64_t chunk_words = (int64_t) (ctx->stage.cap / 32);
-  bool used[2] = {false, false};
   int64_t s_lo = 0;
-  int c = 0;
-  for (int64_t w0 = 0; w0 < n_words; w0 += chunk_words, ++c) {
+  for (int64_t w0 = 0; w0 < n_words; w0 += chunk_words) {
     int64_t w1 = std::min (n_words, w0 + chunk_words);
-    int slot = c & 1;
-    if (used[slot]) GCG_CUDA (cudaEventSynchronize (ctx->stage.ev[slot]));
+    int slot = ctx->stage.next;
+    ctx->stage.next ^= 1;
+    // the pinned slot may still feed a copy enqueued by an earlier call on this context
+    if (ctx->stage.busy[slot]) { GCG_CUDA (cudaEventSynchronize (ctx->stage.ev[slot])); ctx->stage.busy[slot] = false; }
     // sequences overlapping [w0,w1)
     while (s_lo + 1 < n && woff[(size_t) s_lo + 1] <= w0) ++s_lo;
     int64_t s_hi = std::upper_bound (woff.begin () + s_lo, woff.begin () + n, w1 - 1) - woff.begin ();
@@ -542,7 +557,7 @@ static int stream_ascii (gcg_ctx * ctx, const seq_src & src, const std::vector<i
     rc = consume (ctx->stage.d[slot], w0, w1 - w0);
     if (rc) return rc;
     GCG_CUDA (cudaEventRecord (ctx->stage.ev[slot], ctx->stream));
-    used[slot] = true;
+    ctx->stage.busy[slot] = true;
   }
   return GCG_OK;
 }
@@ -786,69 +801,51 @@ extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * r
   int64_t n_words = reads->n_words;
   int64_t n_kmers = gcg_seqs_kmers (reads, k);
   if (n_words == 0 || n_kmers == 0) { *out = h; return GCG_OK; }
+  if (n_kmers >= 0xFFFFFFFFLL) {
+    gcg_set_error ("gcg_search: %lld positions in one call exceed the 32-bit anchor index; split the read set (gcg_search does)", (long long) n_kmers);
+    gcg_hits_free (h);
+    return GCG_ERANGE;
+  }
 
   uint32_t * d_mask = nullptr, * d_prefix = nullptr, * d_bsum = nullptr;
-  raw_hit * d_raw = nullptr;
   int64_t nb = (n_words + SCAN_TILE - 1) / SCAN_TILE;
-  int64_t n_tiles = (n_words + 31) >> 5;
-  // Anchors are a few percent of the positions on noisy reads; size the unordered buffer for a
-  // quarter of them.  If that overflows, the first pass has still produced the exact count, the
-  // complete hit masks and the ONT multiplicity state; a second pass (ONT counting off) then
-  // re-emits the records into a buffer of exactly that size.
-  int64_t raw_cap = n_kmers <= (1 << 22) ? n_kmers : std::max<int64_t> (n_kmers / 4, 1 << 22);
   int rc = GCG_OK;
   cudaError_t e;
   if ((e = cudaMalloc (&d_mask, (size_t) n_words * 4)) != cudaSuccess || (e = cudaMalloc (&d_prefix, (size_t) n_words * 4)) != cudaSuccess ||
-      (e = cudaMalloc (&d_bsum, (size_t) nb * 4)) != cudaSuccess || (e = cudaMalloc (&d_raw, (size_t) raw_cap * sizeof (raw_hit))) != cudaSuccess) {
+      (e = cudaMalloc (&d_bsum, (size_t) nb * 4)) != cudaSuccess) {
     gcg_set_error ("gcg_search: cudaMalloc failed: %s", cudaGetErrorString (e));
     rc = GCG_ENOMEM;
   }
-  for (int pass = 0; pass < 2 && !rc; ++pass) {
-    GCG_CUDA (cudaMemsetAsync (ctx->d_counters + 4, 0, 8, ctx->stream));
-    {
-      gcg_kscope ks (ctx, pass == 0 ? "k45_search" : "k45_search_retry");
-      int grid = grid_for (ctx, n_tiles * 32, 256, 6);
-      if (pass == 0)
-        k45_search_kernel<true><<<grid, 256, 0, ctx->stream>>> (
-            reads->d_packed, reads->d_woff, reads->d_len, reads->n, n_words, k, t->d_keys, t->d_vals, t->d_ont, t->n_bucket,
-            d_mask, d_raw, (unsigned long long) raw_cap, ctx->d_counters + 4);
-      else
-        k45_search_kernel<false><<<grid, 256, 0, ctx->stream>>> (
-            reads->d_packed, reads->d_woff, reads->d_len, reads->n, n_words, k, t->d_keys, t->d_vals, t->d_ont, t->n_bucket,
-            d_mask, d_raw, (unsigned long long) raw_cap, ctx->d_counters + 4);
-      GCG_CUDA (cudaGetLastError ());
-    }
-    GCG_CUDA (cudaMemcpyAsync (ctx->h_counters + 4, ctx->d_counters + 4, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    GCG_CUDA (cudaStreamSynchronize (ctx->stream));
-    int64_t n_raw = (int64_t) ctx->h_counters[4];
-    if (n_raw > raw_cap) {
-      if (pass == 1) { gcg_set_error ("gcg_search: anchor buffer overflow on retry"); rc = GCG_ERANGE; break; }
-      cudaFree (d_raw); d_raw = nullptr;
-      raw_cap = n_raw;
-      if ((e = cudaMalloc (&d_raw, (size_t) raw_cap * sizeof (raw_hit))) != cudaSuccess) {
-        gcg_set_error ("gcg_search: cudaMalloc failed: %s", cudaGetErrorString (e));
+  while (!rc) {
+    { gcg_kscope ks (ctx, "k45_search");
+      k45_search_kernel<<<grid_for (ctx, n_words, 256, 8), 256, 0, ctx->stream>>> (
+          reads->d_packed, reads->d_woff, reads->d_len, reads->n, n_words, k, t->d_keys, t->d_ont, t->n_bucket, d_mask); }
+    { gcg_kscope ks (ctx, "scan_reduce");
+      scan_reduce_kernel<<<(unsigned) nb, SCAN_BLOCK, 0, ctx->stream>>> (d_mask, n_words, d_bsum); }
+    { gcg_kscope ks (ctx, "scan_blocksums");
+      scan_blocksums_kernel<<<1, 1024, 0, ctx->stream>>> (d_bsum, nb, ctx->d_counters + 4); }
+    { gcg_kscope ks (ctx, "scan_apply");
+      scan_apply_kernel<<<(unsigned) nb, SCAN_BLOCK, 0, ctx->stream>>> (d_mask, n_words, d_bsum, d_prefix); }
+    if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_search: kernel launch failed"); rc = GCG_ECUDA; break; }
+    if (cudaMemcpyAsync (ctx->h_counters + 4, ctx->d_counters + 4, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize (ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_search: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; break; }
+    int64_t n_hit = (int64_t) ctx->h_counters[4];
+    h->n = n_hit;
+    if (n_hit > 0) {
+      if ((e = cudaMalloc (&h->d_hits, (size_t) n_hit * sizeof (gcg_hit))) != cudaSuccess) {
+        gcg_set_error ("gcg_search: cudaMalloc of %lld anchors failed: %s", (long long) n_hit, cudaGetErrorString (e));
         rc = GCG_ENOMEM;
+        break;
       }
-      continue;
-    }
-    h->n = n_raw;
-    if (n_raw > 0) {
-      GCG_CHECK (n_raw < 0xFFFFFFFFLL, GCG_ERANGE, "gcg_search: more than 2^32 anchors in one call");
-      GCG_CUDA (cudaMalloc (&h->d_hits, (size_t) n_raw * sizeof (gcg_hit)));
-      { gcg_kscope ks (ctx, "scan_reduce");
-        scan_reduce_kernel<<<(unsigned) nb, SCAN_BLOCK, 0, ctx->stream>>> (d_mask, n_words, d_bsum); }
-      { gcg_kscope ks (ctx, "scan_blocksums");
-        scan_blocksums_kernel<<<1, 1024, 0, ctx->stream>>> (d_bsum, nb); }
-      { gcg_kscope ks (ctx, "scan_apply");
-        scan_apply_kernel<<<(unsigned) nb, SCAN_BLOCK, 0, ctx->stream>>> (d_mask, n_words, d_bsum, d_prefix); }
-      { gcg_kscope ks (ctx, "hits_scatter");
-        hits_scatter_kernel<<<grid_for (ctx, n_raw, 256, 8), 256, 0, ctx->stream>>> (d_raw, n_raw, d_mask, d_prefix, reads->d_woff, reads->n, h->d_hits); }
-      GCG_CUDA (cudaGetLastError ());
-      GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+      { gcg_kscope ks (ctx, "hits_emit");
+        hits_emit_kernel<<<grid_for (ctx, ((n_words + 31) >> 5) * 32, 256, 8), 256, 0, ctx->stream>>> (
+            reads->d_packed, reads->d_woff, reads->n, n_words, k, t->d_keys, t->d_vals, t->n_bucket, d_mask, d_prefix, h->d_hits); }
+      if (cudaGetLastError () != cudaSuccess || cudaStreamSynchronize (ctx->stream) != cudaSuccess) {
+        gcg_set_error ("gcg_search: emit failed: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; }
     }
     break;
   }
-  cudaFree (d_mask); cudaFree (d_prefix); cudaFree (d_bsum); cudaFree (d_raw);
+  cudaFree (d_mask); cudaFree (d_prefix); cudaFree (d_bsum);
   if (rc) { gcg_hits_free (h); return rc; }
   *out = h;
   return GCG_OK;

@@ -1,9 +1,896 @@
-// placeholder until the SW kernels land (next commit)
+// K7..K9: batched Smith-Waterman fill (anti-diagonal wavefront inside a warp), end-cell selection
+// with the reference's tie rules, trace spill (4 bits/cell) to HBM and CIGAR emission.
+//
+// Reference semantics restated (paths relative to /root/reference/gap_closer):
+//   DP cell         sw.c:203-252   ms = H[i-1][j-1] + mat[q*type_c+t]
+//                                  ds = max(H[i-1][j]-del_o  (only if strictly greater), ds[i-1][j]-del_e)
+//                                  is = max(H[i][j-1]-ins_o  (only if strictly greater), is[i][j-1]-ins_e)
+//                                  H  = ms if ms>=ds && ms>=is ; else is if is>ds ; else ds
+//   borders         sw.c:61-110    row 0 / column 0: is = ds = -inf, run lengths 0, scores 0 or affine
+//   end cell        sw.c:254-280   last column (last maximum wins), then last row (strictly greater,
+//                                  or equal and closer to the diagonal)
+//   traceback       sw.c:282-335   as shipped the cell is never re-fetched (GCG_SW_ASIS); GCG_SW_FIXED re-fetches
+//   cigar           cigar.c:82-125 BAM encoding (len<<4 | op), "MIDNSHP=XB", reversed at the end
+//
+// Arithmetic.  Every DP value v is carried as 16*v + tag.  The four low bits make the reference's
+// tie rules fall out of a plain integer max and leave the traceback flags in place:
+//   I candidates : open 0b0000, extend 0b0001      (extend wins a tie  <=> open needs strictly greater)
+//   D candidates : open 0b0100, extend 0b0110      (D beats I on a tie <=> "is > ds" needed for I)
+//   M candidate  :      0b1000                     (M wins every tie)
+// so  trace nibble = ((D|I) & 3) | (H & 12):  bit0 I-extended, bit1 D-extended, bit2 H==D, bit3 H==M.
+// Two kernels share this scheme: a packed one (two alignments per warp in the halves of
+// s16x2 registers: VIADD.16x2 / VIMNMX.S16x2 / VIADDMNMX.S16x2, scores by PRMT from byte
+// profiles) and a generic s32 one (any alphabet <= 8, any lengths).  Which pairs may use the packed
+// kernel is decided on the host from provable value bounds — never from the data.
+//
+// Wavefront.  Lane l of a warp owns 8 consecutive query columns of a 256-column band and walks
+// down the target rows; at step s it is on row s-l+1 and receives H and I of its left neighbour's
+// last column by __shfl_up_sync.  The last column of a band is parked (shared memory in the packed
+// kernel, an L2-resident scratch in the generic one) for lane 0 of the next band.
+//
+// Trace layout per alignment (what hits HBM, 0.5 byte per cell, fully coalesced 128-byte rows):
+//   word[(band * (tlen+31) + step) * 32 + lane], nibble of column c at bit shift(c)
+#include <algorithm>
+#include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "gcg_internal.cuh"
-extern "C" int gcg_sw_batch (gcg_ctx *, const gcg_sw_params *, int, const char *, const int64_t *, const char *, const int64_t *, int64_t, gcg_sw_result *, uint32_t **, int64_t *) { gcg_set_error ("sw: not built yet"); return GCG_EINVAL; }
-extern "C" int gcg_swbatch_upload (gcg_ctx *, const char *, const int64_t *, const char *, const int64_t *, int64_t, gcg_swbatch **) { gcg_set_error ("sw: not built yet"); return GCG_EINVAL; }
-extern "C" int gcg_swbatch_align (gcg_ctx *, gcg_swbatch *, const gcg_sw_params *, int) { gcg_set_error ("sw: not built yet"); return GCG_EINVAL; }
-extern "C" int gcg_swbatch_download (gcg_ctx *, gcg_swbatch *, gcg_sw_result *, uint32_t **, int64_t *) { gcg_set_error ("sw: not built yet"); return GCG_EINVAL; }
-extern "C" int64_t gcg_swbatch_cells (const gcg_swbatch *) { return 0; }
-extern "C" int gcg_swbatch_path_counts (const gcg_swbatch *, int64_t *) { return GCG_EINVAL; }
-extern "C" void gcg_swbatch_free (gcg_swbatch *) {}
+
+#define SW_BAND 256
+#define SW_COLS 8
+
+struct sw_task {
+  long long qoff, toff;             // offsets into the batch symbol buffers
+  int qlen, tlen;
+  unsigned long long trace_off;     // in u32 words, into the wave's trace buffer
+  long long edge_off;               // in ints, into the wave's edge buffer: lastcol[tlen] then lastrow[qlen]
+  int pair;                         // index in the batch
+  int pad;
+};
+
+struct sw_end { int score, bt_tidx, bt_qidx, seg_len; };
+
+struct sw_consts {
+  int type_c, del_o, del_e, ins_o, ins_e, strategy;
+  int border_kind, b_del_o, b_del_e, b_ins_o, b_ins_e;
+  int mat16[64];                    // 16*mat + 8
+  unsigned prof4[4];                // packed kernel: byte t of prof4[q] = (signed char)(16*mat[q][t]+8)
+};
+
+__constant__ sw_consts c_sw;
+
+__host__ __device__ __forceinline__ int sw_shift (int c) { return c < 4 ? 4 * (3 - c) : 16 + 4 * (7 - c); }
+
+__device__ __forceinline__ int sw_brow (int j)   // border score of row 0, column j (sw.c:96-102)
+{
+  return (c_sw.border_kind && j >= 1) ? -c_sw.b_ins_o - (j - 1) * c_sw.b_ins_e : 0;
+}
+__device__ __forceinline__ int sw_bcol (int i)   // border score of column 0, row i (sw.c:104-109)
+{
+  return (c_sw.border_kind && i >= 1) ? -c_sw.b_del_o - (i - 1) * c_sw.b_del_e : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// end-cell selection by one warp over the parked last column / last row (sw.c:254-280)
+// ---------------------------------------------------------------------------------------------
+__device__ void sw_pick_end (const int * edges, int qlen, int tlen, int lane, sw_end * out)
+{
+  const int * lastcol = edges, * lastrow = edges + tlen;
+  // last column: the LAST maximum wins (>=)
+  int best = INT_MIN, bi = tlen;
+  for (int idx = lane; idx < tlen; idx += 32) {
+    int v = __ldcg (lastcol + idx);
+    if (v >= best) { best = v; bi = idx + 1; }
+  }
+  for (int o = 16; o; o >>= 1) {
+    int ob = __shfl_xor_sync (0xffffffffu, best, o), oi = __shfl_xor_sync (0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi > bi && ob != INT_MIN)) { best = ob; bi = oi; }
+  }
+  if (tlen == 0) bi = 0;
+  int bt_t = bi, bt_q = qlen, score = best, seg = 0;
+  if (tlen == 0) score = INT_MIN;
+  if (c_sw.strategy != GCG_SWOS_LEADING_INDEL && qlen > 0) {
+    int m2 = INT_MIN;
+    for (int idx = lane; idx < qlen; idx += 32) m2 = max (m2, __ldcg (lastrow + idx));
+    for (int o = 16; o; o >>= 1) m2 = max (m2, __shfl_xor_sync (0xffffffffu, m2, o));
+    if (m2 >= score) {
+      // among columns holding m2: smallest |tlen - j|, first such j
+      int bd = INT_MAX, bj = INT_MAX;
+      for (int idx = lane; idx < qlen; idx += 32) {
+        if (__ldcg (lastrow + idx) == m2) {
+          int j = idx + 1, d = abs (tlen - j);
+          if (d < bd || (d == bd && j < bj)) { bd = d; bj = j; }
+        }
+      }
+      for (int o = 16; o; o >>= 1) {
+        int od = __shfl_xor_sync (0xffffffffu, bd, o), oj = __shfl_xor_sync (0xffffffffu, bj, o);
+        if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+      }
+      bool take = m2 > score || bd < abs (bt_t - bt_q);
+      if (take) { bt_t = tlen; bt_q = bj; score = m2; seg = qlen - bj; }
+    }
+  }
+  if (score == INT_MIN) score = sw_brow (bt_q);      // only reachable with tlen == 0: cell (0, bt_q)
+  if (lane == 0) { out->score = score; out->bt_tidx = bt_t; out->bt_qidx = bt_q; out->seg_len = seg; }
+}
+
+// degenerate alignments (an empty side): the "last column / last row" are border cells
+__device__ void sw_fill_degenerate (int * edges, int qlen, int tlen, int lane)
+{
+  if (qlen == 0) for (int i = lane; i < tlen; i += 32) __stcg (edges + i, sw_bcol (i + 1));
+  if (tlen == 0) for (int j = lane; j < qlen; j += 32) __stcg (edges + tlen + j, sw_brow (j + 1));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7 generic: one alignment per warp, s32 values
+// ---------------------------------------------------------------------------------------------
+#define SW_NEG32 (-(1 << 29))
+
+__global__ void __launch_bounds__ (128)
+sw_fill_generic_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restrict__ tgt,
+                        const sw_task * __restrict__ tasks, const int * __restrict__ items, int n_items,
+                        int * __restrict__ counter, uint32_t * __restrict__ trace, int * __restrict__ edges,
+                        int2 * __restrict__ bound, long long bound_stride, sw_end * __restrict__ ends)
+{
+  __shared__ int s_mat[64];
+  if (threadIdx.x < 64) s_mat[threadIdx.x] = c_sw.mat16[threadIdx.x];
+  __syncthreads ();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int2 * mybound = bound + (long long) (blockIdx.x * 4 + wid) * bound_stride;
+  const int type_c = c_sw.type_c;
+  const int cDO = -16 * c_sw.del_o + 4, cDE = -16 * c_sw.del_e, cIO = -16 * c_sw.ins_o, cIE = -16 * c_sw.ins_e;
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd (counter, 1);
+    item = __shfl_sync (0xffffffffu, item, 0);
+    if (item >= n_items) break;
+    const sw_task tk = tasks[items[item]];
+    const int qlen = tk.qlen, tlen = tk.tlen;
+    int * my_edges = edges + tk.edge_off;
+    if (qlen == 0 || tlen == 0) {
+      sw_fill_degenerate (my_edges, qlen, tlen, lane);
+    } else {
+      const uint8_t * q = qry + tk.qoff, * t = tgt + tk.toff;
+      uint32_t * tr = trace + tk.trace_off;
+      const int nsteps = tlen + 31, nbands = (qlen + SW_BAND - 1) / SW_BAND;
+      const int lastband = (qlen - 1) / SW_BAND, lastlane = ((qlen - 1) % SW_BAND) / SW_COLS, cstar = (qlen - 1) % SW_COLS;
+      for (int band = 0; band < nbands; ++band) {
+        const int j0 = band * SW_BAND + lane * SW_COLS;
+        int qs[SW_COLS], Hup[SW_COLS], Dup[SW_COLS];
+#pragma unroll
+        for (int c = 0; c < SW_COLS; ++c) {
+          qs[c] = (j0 + c < qlen ? (int) q[j0 + c] : 0) * type_c;
+          Hup[c] = 16 * sw_brow (j0 + c + 1);
+          Dup[c] = SW_NEG32;
+        }
+        int prevInH = 16 * sw_brow (j0), outH = 0, outI = SW_NEG32;
+        for (int step = 0; step < nsteps; ++step) {
+          int inH = __shfl_up_sync (0xffffffffu, outH, 1), inI = __shfl_up_sync (0xffffffffu, outI, 1);
+          const int i = step - lane + 1;
+          const bool active = i >= 1 && i <= tlen;
+          if (lane == 0 && active) {
+            if (band == 0) { inH = 16 * sw_bcol (i); inI = SW_NEG32; }
+            else { int2 b = __ldcg (mybound + i); inH = b.x; inI = b.y; }
+          }
+          if (active) {
+            const int ts = t[i - 1];
+            int Hd = prevInH, Hl = inH, Il = inI;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int c = 0; c < SW_COLS; ++c) {
+              int s = s_mat[qs[c] + ts];
+              int dE = (Dup[c] | 2) + cDE;
+              int D = __viaddmax_s32 (Hup[c], cDO, dE);
+              int iE = (Il | 1) + cIE;
+              int I = __viaddmax_s32 (Hl, cIO, iE);
+              int g = max (D, I);
+              int H = __viaddmax_s32 (Hd, s, g);
+              int Hc = H & ~15;
+              acc |= ((uint32_t) (((D | I) & 3) | (H & 12))) << sw_shift (c);
+              Hd = Hup[c]; Hup[c] = Hc; Dup[c] = D; Hl = Hc; Il = I;
+            }
+            prevInH = inH;
+            outH = Hl; outI = Il;
+            tr[((size_t) band * nsteps + step) * 32 + lane] = acc;
+            if (lane == 31 && band + 1 < nbands) __stcg (mybound + i, make_int2 (outH, outI));
+            if (band == lastband && lane == lastlane) {
+              int v = 0;
+#pragma unroll
+              for (int c = 0; c < SW_COLS; ++c) if (c == cstar) v = Hup[c];
+              __stcg (my_edges + (i - 1), v >> 4);
+            }
+            if (i == tlen) {
+#pragma unroll
+              for (int c = 0; c < SW_COLS; ++c) if (j0 + c < qlen) __stcg (my_edges + tlen + j0 + c, Hup[c] >> 4);
+            }
+          }
+        }
+        __syncwarp ();
+      }
+    }
+    __syncwarp ();
+    sw_pick_end (my_edges, qlen, tlen, lane, ends + tk.pair);
+    __syncwarp ();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7 packed: two alignments per warp in s16x2 halves.  Shared memory per warp (rows = tmax):
+//   bH[rows], bI[rows]  last column of the previous band (both alignments packed)
+//   tsel[rows]          PRMT selector for the two target symbols of that row
+// ---------------------------------------------------------------------------------------------
+#define SW_NEG16V (-2040)                     // "minus infinity" in score units for the packed kernel
+#define SW_PACKED_MAXROWS 2040
+
+// PRMT in its default mode: selector nibble bit 3 replicates the sign of the selected byte
+// (__byte_perm masks that bit away, so the instruction is issued directly)
+__device__ __forceinline__ uint32_t prmt (uint32_t a, uint32_t b, uint32_t sel)
+{
+  uint32_t d;
+  asm ("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack16 (int v) { return ((uint32_t) v & 0xFFFFu) * 0x10001u; }
+__device__ __forceinline__ int half_lo (uint32_t x) { return (int) (short) (x & 0xFFFFu); }
+__device__ __forceinline__ int half_hi (uint32_t x) { return ((int) x) >> 16; }
+
+__global__ void __launch_bounds__ (32, 20)
+sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restrict__ tgt,
+                       const sw_task * __restrict__ tasks, const int2 * __restrict__ items, int n_items,
+                       int * __restrict__ counter, uint32_t * __restrict__ trace, int * __restrict__ edges,
+                       uint2 * __restrict__ bound, int rows_cap, sw_end * __restrict__ ends)
+{
+  // shared: one PRMT selector per target row.  The last column of the previous band (H, I of both
+  // alignments, 8 bytes per row) lives in an L2-resident scratch: lane 31 parks it row by row, all
+  // 32 lanes fetch the next 32 rows in one coalesced load a full 32 steps before lane 0 needs them.
+  extern __shared__ unsigned short tsel[];
+  const int lane = threadIdx.x;
+  uint2 * bnd = bound + (size_t) blockIdx.x * rows_cap;
+  const uint32_t cDO = pack16 (-16 * c_sw.del_o + 4), cDE = pack16 (-16 * c_sw.del_e);
+  const uint32_t cIO = pack16 (-16 * c_sw.ins_o), cIE = pack16 (-16 * c_sw.ins_e);
+  const uint32_t NEG2 = pack16 (16 * SW_NEG16V);
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd (counter, 1);
+    item = __shfl_sync (0xffffffffu, item, 0);
+    if (item >= n_items) break;
+    const int2 it = items[item];
+    const sw_task ta = tasks[it.x];
+    const bool has_b = it.y >= 0;
+    const sw_task tb = tasks[has_b ? it.y : it.x];
+    const int QL = max (ta.qlen, tb.qlen), TL = max (ta.tlen, tb.tlen);   // both > 0 (host guarantees)
+    const uint8_t * qa = qry + ta.qoff, * qb = qry + tb.qoff, * tga = tgt + ta.toff, * tgb = tgt + tb.toff;
+    uint32_t * tra = trace + ta.trace_off, * trb = trace + tb.trace_off;
+    int * ea = edges + ta.edge_off, * eb = edges + tb.edge_off;
+    const int nsa = ta.tlen + 31, nsb = tb.tlen + 31, nba = (ta.qlen + SW_BAND - 1) / SW_BAND, nbb = (tb.qlen + SW_BAND - 1) / SW_BAND;
+    const int nsteps = TL + 31, nbands = (QL + SW_BAND - 1) / SW_BAND;
+    // per-row PRMT selectors: byte0 <- profA[tA], byte1 <- its sign, byte2 <- profB[tB], byte3 <- its sign
+    __syncwarp ();
+    for (int r = lane; r < TL; r += 32) {
+      uint32_t sa = r < ta.tlen ? tga[r] : 0, sb = r < tb.tlen ? tgb[r] : 0;
+      tsel[r] = (unsigned short) (sa | ((sa | 8u) << 4) | ((4u + sb) << 8) | ((12u + sb) << 12));
+    }
+    __syncwarp ();
+    for (int band = 0; band < nbands; ++band) {
+      const int j0 = band * SW_BAND + lane * SW_COLS;
+      uint32_t PA[SW_COLS], PB[SW_COLS], Hup[SW_COLS], Dup[SW_COLS];
+#pragma unroll
+      for (int c = 0; c < SW_COLS; ++c) {
+        PA[c] = c_sw.prof4[j0 + c < ta.qlen ? qa[j0 + c] : 0];
+        PB[c] = c_sw.prof4[j0 + c < tb.qlen ? qb[j0 + c] : 0];
+        Hup[c] = pack16 (16 * sw_brow (j0 + c + 1));
+        Dup[c] = NEG2;
+      }
+      uint32_t prevInH = pack16 (16 * sw_brow (j0)), outH = 0, outI = NEG2;
+      // boundary prefetch registers: rows [32k, 32k+32) of the previous band, one row per lane
+      uint2 pf_cur = make_uint2 (0u, NEG2), pf_nxt = make_uint2 (0u, NEG2);
+      if (band > 0) {
+        if (lane < TL) pf_cur = __ldcg (bnd + lane);
+        if (32 + lane < TL) pf_nxt = __ldcg (bnd + 32 + lane);
+      }
+      // everything that does not change inside the step loop
+      const bool wrA = band < nba, wrB = has_b && band < nbb;
+      uint32_t * pa = tra + ((size_t) band * nsa) * 32 + lane;
+      uint32_t * pb = trb + ((size_t) band * nsb) * 32 + lane;
+      const bool park = lane == 31 && band + 1 < nbands;
+      const bool ownA = j0 < ta.qlen && ta.qlen <= j0 + SW_COLS, ownB = has_b && j0 < tb.qlen && tb.qlen <= j0 + SW_COLS;
+      const int edgeA = ownA ? 1 : ta.tlen, edgeB = ownB ? 1 : (has_b ? tb.tlen : 0x7fffffff);   // rows >= edge need the slow path
+      const int tlenA = ta.tlen, tlenB = tb.tlen;
+      const uint32_t col0H = pack16 (16 * sw_bcol (1)), col0step = pack16 (-16 * c_sw.b_del_e * (c_sw.border_kind ? 1 : 0));
+      uint32_t col0 = col0H;                                       // 16 * border score of column 0, row `step + 1`
+      for (int step = 0; step < nsteps; ++step) {
+        uint32_t inH = __shfl_up_sync (0xffffffffu, outH, 1), inI = __shfl_up_sync (0xffffffffu, outI, 1);
+        const int i = step - lane + 1;
+        if (band > 0) {
+          // lane 0 is on row step+1: its left neighbour is row `step` of the parked column
+          uint32_t bh = __shfl_sync (0xffffffffu, pf_cur.x, step & 31), bi = __shfl_sync (0xffffffffu, pf_cur.y, step & 31);
+          if (lane == 0) { inH = bh; inI = bi; }
+          if ((step & 31) == 31) {
+            pf_cur = pf_nxt;
+            int r = step + 33 + lane;                    // rows of the chunk after the next one
+            if (r < TL) pf_nxt = __ldcg (bnd + r);
+          }
+        } else {
+          if (lane == 0) { inH = col0; inI = NEG2; }
+          col0 = __vadd2 (col0, col0step);
+        }
+        if (i >= 1 && i <= TL) {
+          const uint32_t sel = tsel[i - 1];
+          uint32_t Hd = prevInH, Hl = inH, Il = inI, accA = 0, accB = 0;
+#pragma unroll
+          for (int c = 0; c < SW_COLS; ++c) {
+            uint32_t s = prmt (PA[c], PB[c], sel);
+            uint32_t dE = __vadd2 (Dup[c] | 0x00020002u, cDE);
+            uint32_t D = __viaddmax_s16x2 (Hup[c], cDO, dE);
+            uint32_t iE = __vadd2 (Il | 0x00010001u, cIE);
+            uint32_t I = __viaddmax_s16x2 (Hl, cIO, iE);
+            uint32_t g = __vmaxs2 (D, I);
+            uint32_t H = __viaddmax_s16x2 (Hd, s, g);
+            uint32_t Hc = H & 0xFFF0FFF0u;
+            uint32_t nib = ((D | I) & 0x00030003u) | (H & 0x000C000Cu);
+            if (c < 4) accA = (accA << 4) | nib; else accB = (accB << 4) | nib;
+            Hd = Hup[c]; Hup[c] = Hc; Dup[c] = D; Hl = Hc; Il = I;
+          }
+          prevInH = inH;
+          outH = Hl; outI = Il;
+          if (wrA && i <= tlenA) pa[(uint32_t) step * 32u] = __byte_perm (accA, accB, 0x5410);
+          if (wrB && i <= tlenB) pb[(uint32_t) step * 32u] = __byte_perm (accA, accB, 0x7632);
+          // park the last column for the next band.  Row r is written at step r+31 and was fetched
+          // (for this band) no later than step r-1, so reusing the buffer in place is safe.
+          if (park) __stcg (bnd + (i - 1), make_uint2 (outH, outI));
+          if (i >= edgeA || i >= edgeB) {
+            // rare: this lane holds the last column of an alignment, or is on its last row
+            if (ownA && i <= tlenA) {
+              uint32_t v = 0; const int cs = (ta.qlen - 1) % SW_COLS;
+#pragma unroll
+              for (int c = 0; c < SW_COLS; ++c) if (c == cs) v = Hup[c];
+              __stcg (ea + (i - 1), half_lo (v) >> 4);
+            }
+            if (ownB && i <= tlenB) {
+              uint32_t v = 0; const int cs = (tb.qlen - 1) % SW_COLS;
+#pragma unroll
+              for (int c = 0; c < SW_COLS; ++c) if (c == cs) v = Hup[c];
+              __stcg (eb + (i - 1), half_hi (v) >> 4);
+            }
+            if (i == tlenA) {
+#pragma unroll
+              for (int c = 0; c < SW_COLS; ++c) if (j0 + c < ta.qlen) __stcg (ea + tlenA + j0 + c, half_lo (Hup[c]) >> 4);
+            }
+            if (has_b && i == tlenB) {
+#pragma unroll
+              for (int c = 0; c < SW_COLS; ++c) if (j0 + c < tb.qlen) __stcg (eb + tlenB + j0 + c, half_hi (Hup[c]) >> 4);
+            }
+          }
+        }
+      }
+      __syncwarp ();
+    }
+    __syncwarp ();
+    sw_pick_end (ea, ta.qlen, ta.tlen, lane, ends + ta.pair);
+    if (has_b) sw_pick_end (eb, tb.qlen, tb.tlen, lane, ends + tb.pair);
+    __syncwarp ();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K9 traceback -> CIGAR, one thread per alignment (sw.c:282-335, cigar.c:82-125)
+// ---------------------------------------------------------------------------------------------
+struct sw_cell_view {
+  const uint32_t * tr;
+  int nsteps;
+  __device__ __forceinline__ uint32_t nib (int i, int j) const   // interior cell, 1-based
+  {
+    int col = j - 1, band = col >> 8, lane = (col & 255) >> 3, c = col & 7;
+    uint32_t w = __ldg (tr + ((size_t) band * nsteps + (i - 1 + lane)) * 32 + lane);
+    return (w >> sw_shift (c)) & 15u;
+  }
+  // status as the CIGAR op the reference would take: 0 = M, 2 = D, 1 = I (the else branch, also for border cells)
+  // len = ml / dl / il of that cell (sw.c:221-249)
+  __device__ void fetch (int i, int j, uint32_t * op, uint32_t * len) const
+  {
+    if (i < 1 || j < 1) { *op = 1; *len = 0; return; }
+    uint32_t n = nib (i, j);
+    if (n & 8u) {                              // M: ml = consecutive M cells up the diagonal
+      uint32_t l = 0;
+      while (i >= 1 && j >= 1 && (nib (i, j) & 8u)) { ++l; --i; --j; }
+      *op = 0; *len = l;
+    } else if (n & 4u) {                       // D: dl = 1 + D-extended flags walking up
+      uint32_t l = 0;
+      while (i >= 1) { ++l; if (!(nib (i, j) & 2u)) break; --i; }
+      *op = 2; *len = l;
+    } else {                                   // I: il = 1 + I-extended flags walking left
+      uint32_t l = 0;
+      while (j >= 1) { ++l; if (!(nib (i, j) & 1u)) break; --j; }
+      *op = 1; *len = l;
+    }
+  }
+};
+
+template <bool WRITE>
+__device__ int sw_walk (const sw_cell_view & cv, int mode, int qlen, int tlen, const sw_end & e,
+                        uint32_t * out, int n_total, int * align_off, int * softclip)
+{
+  int n = 0;
+  auto emit = [&] (uint32_t v) { if (WRITE) out[n_total - 1 - n] = v; ++n; };   // written reversed (cigar_reverse)
+  int bt_t = e.bt_tidx, bt_q = e.bt_qidx;
+  uint32_t seg = (uint32_t) e.seg_len, pre = 0, op = 1, len = 0;
+  const int strategy = c_sw.strategy;
+  *softclip = 0;
+  if (seg > 0 && strategy == GCG_SWOS_SOFTCLIP) { emit ((seg << 4) | 4u); seg = 0; *softclip = 1; }
+  cv.fetch (bt_t, bt_q, &op, &len);
+  bool inited = false;
+  do {
+    if (mode == GCG_SW_FIXED && inited) cv.fetch (bt_t, bt_q, &op, &len);
+    if (op == 0) { bt_t -= (int) len; bt_q -= (int) len; }
+    else if (op == 2) bt_t -= (int) len;
+    else bt_q -= (int) len;
+    if (inited && op != pre) { emit ((seg << 4) | pre); seg = 0; }
+    seg += len;
+    pre = op;
+    inited = true;
+    if (len == 0) break;      // border end cell: an index is already 0, the reference leaves the loop as well
+  } while (bt_t > 0 && bt_q > 0);
+  emit ((seg << 4) | pre);
+  if (strategy == GCG_SWOS_SOFTCLIP) {
+    if (bt_q > 0) emit ((((uint32_t) bt_q) << 4) | 4u);
+    *align_off = bt_t;
+  } else {
+    if (bt_t > 0) emit ((((uint32_t) bt_t) << 4) | 2u);
+    if (bt_q > 0) emit ((((uint32_t) bt_q) << 4) | 1u);
+    *align_off = 0;
+  }
+  return n;
+}
+
+__global__ void __launch_bounds__ (128)
+sw_cigar_kernel (const sw_task * __restrict__ tasks, int n_tasks, const uint32_t * __restrict__ trace,
+                 const sw_end * __restrict__ ends, int mode, uint32_t * __restrict__ pool, unsigned long long pool_cap,
+                 unsigned long long * __restrict__ cursor, gcg_sw_result * __restrict__ results)
+{
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_tasks) return;
+  const sw_task tk = tasks[idx];
+  const sw_end e = ends[tk.pair];
+  sw_cell_view cv;
+  cv.tr = trace + tk.trace_off;
+  cv.nsteps = tk.tlen + 31;
+  int off = 0, sc = 0;
+  int n = sw_walk<false> (cv, mode, tk.qlen, tk.tlen, e, nullptr, 0, &off, &sc);
+  unsigned long long at = atomicAdd (cursor, (unsigned long long) n);
+  gcg_sw_result r;
+  r.score = e.score; r.alignment_offset = off; r.has_softclip = sc;
+  r.bt_tidx = e.bt_tidx; r.bt_qidx = e.bt_qidx; r.n_cigar = n; r.cigar_off = (long long) at;
+  results[tk.pair] = r;
+  if (at + (unsigned long long) n <= pool_cap) sw_walk<true> (cv, mode, tk.qlen, tk.tlen, e, pool + at, n, &off, &sc);
+}
+
+// per-pair maximum symbol (decides whether a pair may use the 4-letter packed kernel)
+__global__ void __launch_bounds__ (128)
+sw_maxsym_kernel (const uint8_t * __restrict__ qry, const long long * __restrict__ qoff,
+                  const uint8_t * __restrict__ tgt, const long long * __restrict__ toff, long long n, int * __restrict__ maxsym)
+{
+  __shared__ int s[4];
+  for (long long p = blockIdx.x; p < n; p += gridDim.x) {
+    int m = 0;
+    for (long long i = qoff[p] + threadIdx.x; i < qoff[p + 1]; i += blockDim.x) m = max (m, (int) qry[i]);
+    for (long long i = toff[p] + threadIdx.x; i < toff[p + 1]; i += blockDim.x) m = max (m, (int) tgt[i]);
+    m = __reduce_max_sync (0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+    __syncthreads ();
+    if (threadIdx.x == 0) maxsym[p] = max (max (s[0], s[1]), max (s[2], s[3]));
+    __syncthreads ();
+  }
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+struct gcg_swbatch {
+  gcg_ctx * ctx = nullptr;
+  int64_t n = 0;
+  std::vector<long long> qoff, toff;
+  uint8_t * d_qry = nullptr, * d_tgt = nullptr;
+  long long * d_qoff = nullptr, * d_toff = nullptr;
+  int * d_maxsym = nullptr;
+  std::vector<int> maxsym;
+  int64_t cells = 0;
+  // results of the last align
+  gcg_sw_result * d_results = nullptr;
+  sw_end * d_ends = nullptr;
+  uint32_t * d_pool = nullptr;
+  unsigned long long pool_cap = 0, pool_used = 0;
+  int64_t n_packed = 0, n_generic = 0;
+  bool aligned = false;
+};
+
+extern "C" void gcg_swbatch_free (gcg_swbatch * b)
+{
+  if (!b) return;
+  cudaFree (b->d_qry); cudaFree (b->d_tgt); cudaFree (b->d_qoff); cudaFree (b->d_toff); cudaFree (b->d_maxsym);
+  cudaFree (b->d_results); cudaFree (b->d_ends); cudaFree (b->d_pool);
+  delete b;
+}
+
+extern "C" int64_t gcg_swbatch_cells (const gcg_swbatch * b) { return b ? b->cells : 0; }
+
+extern "C" int gcg_swbatch_path_counts (const gcg_swbatch * b, int64_t counts[2])
+{
+  GCG_CHECK (b && counts, GCG_EINVAL, "gcg_swbatch_path_counts: bad argument");
+  counts[0] = b->n_packed; counts[1] = b->n_generic;
+  return GCG_OK;
+}
+
+static int h2d_chunked (gcg_ctx * ctx, void * dst, const void * src, size_t bytes)
+{
+  // pageable source -> pinned ring -> device, double buffered
+  int rc = gcg_stage_reserve (ctx);
+  if (rc) return rc;
+  size_t off = 0;
+  while (off < bytes) {
+    int slot = ctx->stage.next;
+    ctx->stage.next ^= 1;
+    size_t nb = std::min (ctx->stage.cap, bytes - off);
+    if (ctx->stage.busy[slot]) { GCG_CUDA (cudaEventSynchronize (ctx->stage.ev[slot])); ctx->stage.busy[slot] = false; }
+    memcpy (ctx->stage.h[slot], (const char *) src + off, nb);
+    GCG_CUDA (cudaMemcpyAsync ((char *) dst + off, ctx->stage.h[slot], nb, cudaMemcpyHostToDevice, ctx->stream));
+    GCG_CUDA (cudaEventRecord (ctx->stage.ev[slot], ctx->stream));
+    ctx->stage.busy[slot] = true;
+    off += nb;
+  }
+  return GCG_OK;
+}
+
+extern "C" int gcg_swbatch_upload (gcg_ctx * ctx, const char * qry, const int64_t * qoff, const char * tgt,
+                                   const int64_t * toff, int64_t n, gcg_swbatch ** out)
+{
+  GCG_CHECK (ctx && out && qoff && toff && n >= 0, GCG_EINVAL, "gcg_swbatch_upload: bad argument");
+  GCG_CHECK (n < 0x7FFFFFFF, GCG_ERANGE, "gcg_swbatch_upload: too many pairs");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  gcg_swbatch * b = new gcg_swbatch ();
+  b->ctx = ctx; b->n = n;
+  b->qoff.assign (qoff, qoff + n + 1);
+  b->toff.assign (toff, toff + n + 1);
+  for (int64_t p = 0; p < n; ++p) {
+    long long ql = qoff[p + 1] - qoff[p], tl = toff[p + 1] - toff[p];
+    if (ql < 0 || tl < 0 || ql > (1 << 24) || tl > (1 << 24)) {
+      gcg_set_error ("gcg_swbatch_upload: pair %lld has lengths %lld x %lld outside [0, 2^24]", (long long) p, ql, tl);
+      delete b; return GCG_ERANGE;
+    }
+    b->cells += ql * tl;
+  }
+  size_t qb = (size_t) qoff[n], tb = (size_t) toff[n];
+  int rc = GCG_OK;
+  cudaError_t e;
+  if ((e = cudaMalloc (&b->d_qry, std::max<size_t> (qb, 16))) != cudaSuccess || (e = cudaMalloc (&b->d_tgt, std::max<size_t> (tb, 16))) != cudaSuccess ||
+      (e = cudaMalloc (&b->d_qoff, (size_t) (n + 1) * 8)) != cudaSuccess || (e = cudaMalloc (&b->d_toff, (size_t) (n + 1) * 8)) != cudaSuccess ||
+      (e = cudaMalloc (&b->d_maxsym, (size_t) std::max<int64_t> (n, 1) * 4)) != cudaSuccess ||
+      (e = cudaMalloc (&b->d_results, (size_t) std::max<int64_t> (n, 1) * sizeof (gcg_sw_result))) != cudaSuccess ||
+      (e = cudaMalloc (&b->d_ends, (size_t) std::max<int64_t> (n, 1) * sizeof (sw_end))) != cudaSuccess) {
+    gcg_set_error ("gcg_swbatch_upload: cudaMalloc failed: %s", cudaGetErrorString (e));
+    gcg_swbatch_free (b);
+    return GCG_ENOMEM;
+  }
+  if (qb) rc = h2d_chunked (ctx, b->d_qry, qry, qb);
+  if (!rc && tb) rc = h2d_chunked (ctx, b->d_tgt, tgt, tb);
+  if (!rc) {
+    cudaMemcpyAsync (b->d_qoff, b->qoff.data (), (size_t) (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync (b->d_toff, b->toff.data (), (size_t) (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+    b->maxsym.assign ((size_t) n, 0);
+    if (n > 0) {
+      { gcg_kscope ks (ctx, "sw_maxsym");
+        int grid = (int) std::min<int64_t> (n, (int64_t) ctx->sm_count * 16);
+        sw_maxsym_kernel<<<grid, 128, 0, ctx->stream>>> (b->d_qry, b->d_qoff, b->d_tgt, b->d_toff, n, b->d_maxsym); }
+      cudaMemcpyAsync (b->maxsym.data (), b->d_maxsym, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (cudaStreamSynchronize (ctx->stream) != cudaSuccess || cudaGetLastError () != cudaSuccess) {
+      gcg_set_error ("gcg_swbatch_upload: %s", cudaGetErrorString (cudaGetLastError ()));
+      rc = GCG_ECUDA;
+    }
+  }
+  if (rc) { gcg_swbatch_free (b); return rc; }
+  *out = b;
+  return GCG_OK;
+}
+
+// value bounds (score units) of everything the DP can produce for a qlen x tlen alignment
+static void sw_bounds (const gcg_sw_params * P, long long qlen, long long tlen, long long * lo, long long * hi)
+{
+  long long mx = 0, mn = 0;
+  for (int i = 0; i < P->type_c * P->type_c; ++i) { mx = std::max<long long> (mx, P->mat[i]); mn = std::min<long long> (mn, P->mat[i]); }
+  long long row_min = 0, col_min = 0;     // most negative border scores
+  if (P->border_kind) {
+    row_min = std::min<long long> (0, -(long long) P->b_ins_o - (qlen - 1) * (long long) P->b_ins_e);
+    col_min = std::min<long long> (0, -(long long) P->b_del_o - (tlen - 1) * (long long) P->b_del_e);
+    if (P->b_ins_e < 0) row_min = std::min<long long> (row_min, -(long long) P->b_ins_o);
+    if (P->b_del_e < 0) col_min = std::min<long long> (col_min, -(long long) P->b_del_o);
+  }
+  // H(i,j) >= border_row(j) - del_o - (i-1) del_e  and  >= border_col(i) - ins_o - (j-1) ins_e
+  long long l1 = row_min - P->del_o - std::max<long long> (0, tlen - 1) * P->del_e;
+  long long l2 = col_min - P->ins_o - std::max<long long> (0, qlen - 1) * P->ins_e;
+  long long hmin = std::max (l1, l2);
+  // every candidate the kernels form from an H >= hmin: H - open, (H - open) - extend, H + mat
+  long long omax = std::max (P->del_o, P->ins_o), emax = std::max (P->del_e, P->ins_e);
+  *lo = hmin + std::min (mn, -(omax + emax)) - 1;
+  // H <= best border (<= 0 when penalties are non-negative) + min(q,t) * max score
+  long long bmax = 0;
+  if (P->border_kind) {
+    if (P->b_ins_o < 0 || P->b_ins_e < 0) bmax = std::max (bmax, -(long long) P->b_ins_o + std::max<long long> (0, -(long long) P->b_ins_e) * qlen);
+    if (P->b_del_o < 0 || P->b_del_e < 0) bmax = std::max (bmax, -(long long) P->b_del_o + std::max<long long> (0, -(long long) P->b_del_e) * tlen);
+  }
+  *hi = bmax + std::min (qlen, tlen) * mx + 1;
+}
+
+static bool sw_params_packable (const gcg_sw_params * P)
+{
+  if (P->type_c < 1) return false;
+  if (P->del_o < 0 || P->del_e < 0 || P->ins_o < 0 || P->ins_e < 0) return false;   // lower bound derivation needs penalties >= 0
+  if (P->del_e > 8 || P->ins_e > 8 || P->del_o > 64 || P->ins_o > 64) return false;
+  int n = std::min (P->type_c, 4);
+  for (int q = 0; q < n; ++q)
+    for (int t = 0; t < n; ++t) {
+      int v = 16 * P->mat[q * P->type_c + t] + 8;
+      if (v < -128 || v > 127) return false;
+    }
+  return true;
+}
+
+extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_params * P, int mode)
+{
+  GCG_CHECK (ctx && b && P, GCG_EINVAL, "gcg_swbatch_align: bad argument");
+  GCG_CHECK (mode == GCG_SW_ASIS || mode == GCG_SW_FIXED, GCG_EINVAL, "gcg_swbatch_align: mode %d", mode);
+  GCG_CHECK (P->type_c >= 1 && P->type_c <= 8, GCG_ERANGE, "gcg_swbatch_align: type_c=%d outside [1,8]", P->type_c);
+  GCG_CHECK (P->strategy >= 0 && P->strategy <= 3, GCG_EINVAL, "gcg_swbatch_align: overhang strategy %d", P->strategy);
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  const int64_t n = b->n;
+  b->n_packed = b->n_generic = 0;
+  b->pool_used = 0;
+  b->aligned = false;
+  if (n == 0) { b->aligned = true; return GCG_OK; }
+  for (int64_t p = 0; p < n; ++p)
+    GCG_CHECK (b->maxsym[(size_t) p] < P->type_c, GCG_EINVAL, "gcg_swbatch_align: pair %lld holds symbol %d >= type_c %d (sw.c:216 would index outside mat)",
+               (long long) p, b->maxsym[(size_t) p], P->type_c);
+
+  // ---- constants
+  sw_consts hc;
+  memset (&hc, 0, sizeof hc);
+  hc.type_c = P->type_c; hc.del_o = P->del_o; hc.del_e = P->del_e; hc.ins_o = P->ins_o; hc.ins_e = P->ins_e;
+  hc.strategy = P->strategy; hc.border_kind = P->border_kind;
+  hc.b_del_o = P->b_del_o; hc.b_del_e = P->b_del_e; hc.b_ins_o = P->b_ins_o; hc.b_ins_e = P->b_ins_e;
+  for (int i = 0; i < P->type_c * P->type_c; ++i) hc.mat16[i] = 16 * P->mat[i] + 8;
+  const bool packable = sw_params_packable (P) && getenv ("GCG_SW_FORCE_GENERIC") == nullptr;
+  if (packable) {
+    int nn = std::min (P->type_c, 4);
+    for (int q = 0; q < 4; ++q) {
+      unsigned w = 0;
+      for (int t = 0; t < 4; ++t) {
+        int v = (q < nn && t < nn) ? 16 * P->mat[q * P->type_c + t] + 8 : 8;
+        w |= ((unsigned) (v & 0xFF)) << (8 * t);
+      }
+      hc.prof4[q] = w;
+    }
+  }
+  GCG_CUDA (cudaMemcpyToSymbolAsync (c_sw, &hc, sizeof hc, 0, cudaMemcpyHostToDevice, ctx->stream));
+
+  // ---- classify
+  std::vector<int> packed_ids, generic_ids;
+  std::vector<sw_task> tasks ((size_t) n);
+  for (int64_t p = 0; p < n; ++p) {
+    sw_task & t = tasks[(size_t) p];
+    t.qoff = b->qoff[(size_t) p]; t.toff = b->toff[(size_t) p];
+    t.qlen = (int) (b->qoff[(size_t) p + 1] - t.qoff); t.tlen = (int) (b->toff[(size_t) p + 1] - t.toff);
+    t.pair = (int) p; t.pad = 0; t.trace_off = 0; t.edge_off = 0;
+    long long lo, hi;
+    sw_bounds (P, t.qlen, t.tlen, &lo, &hi);
+    GCG_CHECK (lo > -(1LL << 24) && hi < (1LL << 24), GCG_ERANGE, "gcg_swbatch_align: pair %lld: score range [%lld,%lld] exceeds the s32 kernel", (long long) p, lo, hi);
+    bool pk = packable && t.qlen > 0 && t.tlen > 0 && t.tlen <= SW_PACKED_MAXROWS && b->maxsym[(size_t) p] < 4 &&
+              lo >= -2030 && hi <= 2040;
+    (pk ? packed_ids : generic_ids).push_back ((int) p);
+  }
+  std::sort (packed_ids.begin (), packed_ids.end (), [&] (int a, int c) {
+    const sw_task & x = tasks[(size_t) a], & y = tasks[(size_t) c];
+    if (x.tlen != y.tlen) return x.tlen < y.tlen;
+    if (x.qlen != y.qlen) return x.qlen < y.qlen;
+    return a < c;
+  });
+  b->n_packed = (int64_t) packed_ids.size ();
+  b->n_generic = (int64_t) generic_ids.size ();
+
+  // ---- memory plan: trace + edge buffers for one wave
+  size_t free_b = 0, total_b = 0;
+  GCG_CUDA (cudaMemGetInfo (&free_b, &total_b));
+  unsigned long long budget_words = (unsigned long long) (std::min<size_t> (free_b / 2, (size_t) 64 << 30) / 4);
+  if (const char * e = getenv ("GCG_SW_TRACE_BUDGET_MB")) budget_words = (unsigned long long) atoll (e) * (1 << 20) / 4;
+  auto trace_words = [] (const sw_task & t) -> unsigned long long {
+    if (t.qlen == 0 || t.tlen == 0) return 0;
+    return (unsigned long long) ((t.qlen + SW_BAND - 1) / SW_BAND) * (unsigned long long) (t.tlen + 31) * 32ULL;
+  };
+  unsigned long long max_single = 0;
+  for (auto & t : tasks) max_single = std::max (max_single, trace_words (t));
+  GCG_CHECK (2 * max_single <= budget_words || max_single == 0, GCG_ENOMEM, "gcg_swbatch_align: one alignment needs %llu MB of trace, more than the budget",
+             (unsigned long long) (max_single * 4 >> 20));
+
+  // wave construction: work units in launch order (packed items first, then generic), cut by budget
+  struct unit { int a, b; bool packed; };
+  std::vector<unit> units;
+  for (size_t i = 0; i < packed_ids.size (); i += 2) units.push_back ({packed_ids[i], i + 1 < packed_ids.size () ? packed_ids[i + 1] : -1, true});
+  for (int id : generic_ids) units.push_back ({id, -1, false});
+
+  uint32_t * d_trace = nullptr; int * d_edges = nullptr; sw_task * d_tasks = nullptr; int * d_items = nullptr; int * d_counter = nullptr;
+  int2 * d_bound = nullptr;
+  uint2 * d_pbound = nullptr; size_t packed_bound_rows = 0;
+  sw_task * d_wave_tasks = nullptr;
+  unsigned long long total_trace = 0; long long total_edges = 0;
+  for (auto & t : tasks) { total_trace += trace_words (t); total_edges += (long long) t.qlen + t.tlen; }
+  unsigned long long trace_cap = std::min (budget_words, std::max<unsigned long long> (total_trace, 32));
+  int rc = GCG_OK;
+  cudaError_t ce;
+  // the per-launch work lists are small; allocate for the whole batch once
+  long long max_tlen = 1;
+  for (auto & t : tasks) max_tlen = std::max<long long> (max_tlen, t.tlen);
+  const int gen_blocks = ctx->sm_count * 4;          // 4 warps per block, 4 blocks per SM resident
+  long long bound_stride = max_tlen + 1;
+  if ((ce = cudaMalloc (&d_trace, (size_t) trace_cap * 4)) != cudaSuccess ||
+      (ce = cudaMalloc (&d_edges, (size_t) std::max<long long> (total_edges, 1) * 4)) != cudaSuccess ||
+      (ce = cudaMalloc (&d_tasks, (size_t) n * sizeof (sw_task))) != cudaSuccess ||
+      (ce = cudaMalloc (&d_wave_tasks, (size_t) n * sizeof (sw_task))) != cudaSuccess ||
+      (ce = cudaMalloc (&d_items, (size_t) n * 8)) != cudaSuccess ||
+      (ce = cudaMalloc (&d_counter, 2 * sizeof (int))) != cudaSuccess ||
+      (generic_ids.size () && (ce = cudaMalloc (&d_bound, (size_t) gen_blocks * 4 * (size_t) bound_stride * sizeof (int2))) != cudaSuccess)) {
+    gcg_set_error ("gcg_swbatch_align: cudaMalloc failed: %s", cudaGetErrorString (ce));
+    rc = GCG_ENOMEM;
+  }
+  // edge offsets are global for the batch (small: 4 bytes per symbol)
+  if (!rc) {
+    long long eo = 0;
+    for (auto & t : tasks) { t.edge_off = eo; eo += (long long) t.qlen + t.tlen; }
+  }
+  // CIGAR pool: start from a typical size, grow on demand
+  if (!rc) {
+    unsigned long long want = std::max<unsigned long long> (1 << 16, (unsigned long long) n * 64);
+    if (const char * e = getenv ("GCG_SW_POOL_INIT")) { want = (unsigned long long) atoll (e); cudaFree (b->d_pool); b->d_pool = nullptr; b->pool_cap = 0; }
+    if (b->pool_cap < want) {
+      cudaFree (b->d_pool); b->d_pool = nullptr; b->pool_cap = 0;
+      if ((ce = cudaMalloc (&b->d_pool, (size_t) want * 4)) != cudaSuccess) { gcg_set_error ("gcg_swbatch_align: cigar pool: %s", cudaGetErrorString (ce)); rc = GCG_ENOMEM; }
+      else b->pool_cap = want;
+    }
+  }
+  unsigned long long * d_cursor = ctx->d_counters + 10;
+  if (!rc) GCG_CUDA (cudaMemsetAsync (d_cursor, 0, 8, ctx->stream));
+
+  // resident warps of the packed kernel (one warp per block)
+  int packed_slots = 0;
+  if (!rc && !packed_ids.empty ()) {
+    int max_t = 32, per_sm = 0;
+    for (int id : packed_ids) max_t = std::max (max_t, tasks[(size_t) id].tlen);
+    GCG_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, sw_fill_packed_kernel, 32, (size_t) ((max_t + 31) & ~31) * 2));
+    packed_slots = ctx->sm_count * std::max (per_sm, 1);
+  }
+
+  size_t u0 = 0;
+  while (!rc && u0 < units.size ()) {
+    // ---- cut a wave
+    unsigned long long used = 0;
+    size_t u1 = u0;
+    while (u1 < units.size ()) {
+      unsigned long long need = trace_words (tasks[(size_t) units[u1].a]) + (units[u1].b >= 0 ? trace_words (tasks[(size_t) units[u1].b]) : 0);
+      if (used + need > trace_cap && u1 > u0) break;
+      used += need;
+      ++u1;
+    }
+    // A wave that was cut by the trace budget runs as whole rounds of the resident warps: with
+    // equal-cost units (the usual batch) a partial last round would leave most SMs idle.
+    if (u1 < units.size () && units[u0].packed && packed_slots > 0) {
+      size_t np = 0;
+      while (u0 + np < u1 && units[u0 + np].packed) ++np;
+      if (np >= (size_t) packed_slots) u1 = u0 + (np / packed_slots) * packed_slots;
+    }
+    // assign trace offsets, build launch lists
+    std::vector<int2> pitems; std::vector<int> gitems; std::vector<sw_task> wave_tasks;
+    unsigned long long off = 0;
+    int rows_cap = 32;
+    for (size_t u = u0; u < u1; ++u) {
+      for (int id : {units[u].a, units[u].b}) {
+        if (id < 0) continue;
+        sw_task & t = tasks[(size_t) id];
+        t.trace_off = off; off += trace_words (t);
+        wave_tasks.push_back (t);
+        if (units[u].packed) rows_cap = std::max (rows_cap, t.tlen);
+      }
+      if (units[u].packed) pitems.push_back (make_int2 (units[u].a, units[u].b));
+      else gitems.push_back (units[u].a);
+    }
+    rows_cap = (rows_cap + 31) & ~31;
+    GCG_CUDA (cudaMemcpyAsync (d_tasks, tasks.data (), (size_t) n * sizeof (sw_task), cudaMemcpyHostToDevice, ctx->stream));
+    GCG_CUDA (cudaMemcpyAsync (d_wave_tasks, wave_tasks.data (), wave_tasks.size () * sizeof (sw_task), cudaMemcpyHostToDevice, ctx->stream));
+    GCG_CUDA (cudaMemsetAsync (d_counter, 0, 2 * sizeof (int), ctx->stream));
+    if (!pitems.empty ()) {
+      GCG_CUDA (cudaMemcpyAsync (d_items, pitems.data (), pitems.size () * sizeof (int2), cudaMemcpyHostToDevice, ctx->stream));
+      size_t smem = (size_t) rows_cap * 2;
+      int per_sm = 0;
+      GCG_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, sw_fill_packed_kernel, 32, smem));
+      if (per_sm < 1) per_sm = 1;
+      int grid = (int) std::min<size_t> (pitems.size (), (size_t) ctx->sm_count * per_sm);
+      if (packed_bound_rows < (size_t) grid * rows_cap) {
+        cudaFree (d_pbound); d_pbound = nullptr;
+        packed_bound_rows = (size_t) ctx->sm_count * per_sm * rows_cap;
+        if ((ce = cudaMalloc (&d_pbound, packed_bound_rows * sizeof (uint2))) != cudaSuccess) { gcg_set_error ("gcg_swbatch_align: boundary scratch: %s", cudaGetErrorString (ce)); rc = GCG_ENOMEM; break; }
+      }
+      gcg_kscope ks (ctx, "k7_sw_fill_packed");
+      sw_fill_packed_kernel<<<grid, 32, smem, ctx->stream>>> (b->d_qry, b->d_tgt, d_tasks, (const int2 *) d_items, (int) pitems.size (),
+                                                              d_counter, d_trace, d_edges, d_pbound, rows_cap, b->d_ends);
+      GCG_CUDA (cudaGetLastError ());
+    }
+    if (!gitems.empty ()) {
+      int * d_gitems = d_items + 2 * pitems.size ();
+      GCG_CUDA (cudaMemcpyAsync (d_gitems, gitems.data (), gitems.size () * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
+      int grid = (int) std::min<size_t> ((gitems.size () + 3) / 4, (size_t) gen_blocks);
+      gcg_kscope ks (ctx, "k7_sw_fill_generic");
+      sw_fill_generic_kernel<<<grid, 128, 0, ctx->stream>>> (b->d_qry, b->d_tgt, d_tasks, d_gitems, (int) gitems.size (), d_counter + 1,
+                                                             d_trace, d_edges, d_bound, bound_stride, b->d_ends);
+      GCG_CUDA (cudaGetLastError ());
+    }
+    // ---- CIGAR for the wave; grow the pool and redo the wave's CIGARs if it overflowed
+    unsigned long long wave_start = b->pool_used;
+    for (int attempt = 0; attempt < 3 && !rc; ++attempt) {
+      { gcg_kscope ks (ctx, "k9_sw_cigar");
+        int nt = (int) wave_tasks.size ();
+        sw_cigar_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>> (d_wave_tasks, nt, d_trace, b->d_ends, mode, b->d_pool, b->pool_cap, d_cursor, b->d_results); }
+      GCG_CUDA (cudaGetLastError ());
+      GCG_CUDA (cudaMemcpyAsync (ctx->h_counters + 10, d_cursor, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+      unsigned long long cur = ctx->h_counters[10];
+      if (cur <= b->pool_cap) { b->pool_used = cur; break; }
+      // grow: keep what earlier waves wrote
+      unsigned long long ncap = std::max (cur + (cur - wave_start) * (unsigned long long) (units.size () - u1) / std::max<size_t> (u1 - u0, 1), b->pool_cap * 2);
+      uint32_t * np = nullptr;
+      if ((ce = cudaMalloc (&np, (size_t) ncap * 4)) != cudaSuccess) { gcg_set_error ("gcg_swbatch_align: cigar pool growth to %llu ops failed: %s", ncap, cudaGetErrorString (ce)); rc = GCG_ENOMEM; break; }
+      if (wave_start) GCG_CUDA (cudaMemcpyAsync (np, b->d_pool, (size_t) wave_start * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+      GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+      cudaFree (b->d_pool);
+      b->d_pool = np; b->pool_cap = ncap;
+      ctx->h_counters[10] = wave_start;
+      GCG_CUDA (cudaMemcpyAsync (d_cursor, ctx->h_counters + 10, 8, cudaMemcpyHostToDevice, ctx->stream));
+      GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+      if (attempt == 2) { gcg_set_error ("gcg_swbatch_align: cigar pool overflow persists"); rc = GCG_ERANGE; }
+    }
+    u0 = u1;
+  }
+  if (!rc && cudaStreamSynchronize (ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_swbatch_align: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; }
+  cudaFree (d_trace); cudaFree (d_edges); cudaFree (d_tasks); cudaFree (d_wave_tasks); cudaFree (d_items); cudaFree (d_counter); cudaFree (d_bound); cudaFree (d_pbound);
+  if (!rc) b->aligned = true;
+  return rc;
+}
+
+extern "C" int gcg_swbatch_download (gcg_ctx * ctx, gcg_swbatch * b, gcg_sw_result * results,
+                                     uint32_t ** cigar_pool, int64_t * n_cigar_pool)
+{
+  GCG_CHECK (ctx && b && results && cigar_pool && n_cigar_pool, GCG_EINVAL, "gcg_swbatch_download: bad argument");
+  GCG_CHECK (b->aligned, GCG_EINVAL, "gcg_swbatch_download: no alignment has been run on this batch");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  *cigar_pool = nullptr;
+  *n_cigar_pool = (int64_t) b->pool_used;
+  if (b->n) GCG_CUDA (cudaMemcpyAsync (results, b->d_results, (size_t) b->n * sizeof (gcg_sw_result), cudaMemcpyDeviceToHost, ctx->stream));
+  if (b->pool_used) {
+    cudaError_t e = cudaHostAlloc ((void **) cigar_pool, (size_t) b->pool_used * 4, cudaHostAllocDefault);
+    if (e != cudaSuccess) { gcg_set_error ("gcg_swbatch_download: pinned alloc failed: %s", cudaGetErrorString (e)); return GCG_ENOMEM; }
+    GCG_CUDA (cudaMemcpyAsync (*cigar_pool, b->d_pool, (size_t) b->pool_used * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+  return GCG_OK;
+}
+
+extern "C" int gcg_sw_batch (gcg_ctx * ctx, const gcg_sw_params * P, int mode,
+                             const char * qry, const int64_t * qoff, const char * tgt, const int64_t * toff, int64_t n,
+                             gcg_sw_result * results, uint32_t ** cigar_pool, int64_t * n_cigar_pool)
+{
+  gcg_swbatch * b = nullptr;
+  int rc = gcg_swbatch_upload (ctx, qry, qoff, tgt, toff, n, &b);
+  if (rc) return rc;
+  rc = gcg_swbatch_align (ctx, b, P, mode);
+  if (!rc) rc = gcg_swbatch_download (ctx, b, results, cigar_pool, n_cigar_pool);
+  gcg_swbatch_free (b);
+  return rc;
+}

@@ -1,0 +1,24 @@
+/* gcg_bridge.h — process-wide handle on libgcgpu.so shared by the replacement files of this
+ * directory (kmer.c, ont.c, sw.c).  Not part of the reference's API surface. */
+#ifndef GCG_BRIDGE_H
+#define GCG_BRIDGE_H
+
+#include "gcgpu.h"
+
+struct ctg_s;
+
+typedef struct {
+  gcg_ctx * ctx;          /* one context per process (device from $GC_DEVICE, default 0) */
+  gcg_seqs * contigs;     /* 2-bit contigs of the last chop_contig_seqs2kmers */
+  gcg_table * table;      /* table of the last put_contig_kmers2hashs */
+  int kmer_len;
+  int n_thread;
+} gcg_bridge_t;
+
+gcg_bridge_t * gcg_bridge (void);            /* lazily creates the context; aborts via err_mesg on failure */
+void gcg_bridge_drop_table (void);
+void gcg_bridge_drop_contigs (void);
+void gcg_bridge_shutdown (void);
+#define GCG_CK(call) do { int rc_ = (call); if (rc_ != 0) err_mesg ("[%s] %s failed (%d): %s", __func__, #call, rc_, gcg_last_error ()); } while (0)
+
+#endif

@@ -1,0 +1,224 @@
+/* ont.c — replacement for gap_closer/ont.c: same prototypes (ont.h:50-59).  The per-base
+ * crc32 + chained-hash probe loop of the reference (ont.c:141-204) and its thread pool
+ * (ont.c:316-400) are gone; search_kmers_on_ont_reads is now a batcher over libgcgpu:
+ *
+ *   SEARCH   (reference ont.c:361-368 -> chop1ont2kmer/chop1segm ont.c:141-223)
+ *            + REHASH (reference ont.c:371-377 -> rehash1okseq ont.c:230-254)
+ *                 -> gcg_search: reads to HBM, canonical k-mers, table probes, ONT-side
+ *                    multiplicity, anchors back in (read,pos) order
+ *   back-fill of the dense okmers[] the unchanged consumers index by read position
+ *            (ctg_graph.c:603-651): host threads, one 16-byte store per anchor
+ *   UNANKOR  (reference ont.c:381-388 -> find_unankor_segs ont.c:264-309): derived from the
+ *            sorted anchor list instead of re-scanning 16 bytes per ONT base
+ *
+ * okmer->kmer points at &ctgs[tid].kmers[cpos] (what the reference's search phase stores,
+ * ont.c:174); the reference later re-points it to a byte-identical copy inside anchored_ksets
+ * (ont.c:245,253).  The anchored sets stay empty host objects (main.c:68-72 creates and frees
+ * them); their only reader, kmer_stat2, prints the device-side counters (kmer.c).
+ */
+#include <time.h>
+#include <stdio.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include <pthread.h>
+
+#include "mp.h"
+#include "ont.h"
+#include "rseq.h"
+#include "utils.h"
+#include "gcg_bridge.h"
+
+/* ------------------------------------------------------------------ back-fill ---------- */
+typedef struct {
+  const gcg_hit * hits;
+  int64_t beg, end;
+  mp_t(okseq) * okseqs;
+  mp_t(ctg) * ctgs;
+} fill_arg_t;
+
+static void *
+fill_core (void * data)
+{
+  fill_arg_t * a = (fill_arg_t *) data;
+  int64_t i;
+  for (i = a->beg; i < a->end; ++i) {
+    const gcg_hit * h = a->hits + i;
+    okseq_t * okseq = a->okseqs->pool + h->read;
+    ont_kmer_t * ok = okseq->okmers->pool + h->pos;
+    kmer_t * km = a->ctgs->pool[h->tid].kmers + (h->cpos_flags >> 2);
+    ok->kmer = km;
+    ok->ont_pos = h->pos;
+    ok->hs_id = (int16_t) km->hs_id;
+    ok->flag = (h->cpos_flags & 2u) ? ONT_KMER_REV : 0;
+  }
+  return NULL;
+}
+
+/* maximal runs of un-anchored positions of every read, from the sorted anchors */
+static void
+rebuild_segs (mp_t(okseq) * okseqs, const gcg_hit * hits, int64_t n_hit)
+{
+  int64_t r, n_reads = mp_cnt (okseqs), h = 0;
+  for (r = 0; r < n_reads; ++r) {
+    okseq_t * okseq = mp_at (okseq, okseqs, r);
+    int64_t n = mp_cnt (okseq->okmers), cur = 0;
+    ont_seg_t * seg;
+    mp_clear (oseg, okseq->segs, NULL);
+    while (h < n_hit && hits[h].read == r) {
+      if (hits[h].pos > cur) {
+        seg = mp_alloc (oseg, okseq->segs);
+        seg->beg = (int32_t) cur;
+        seg->end = hits[h].pos;
+      }
+      cur = (int64_t) hits[h].pos + 1;
+      ++h;
+    }
+    if (cur < n) {
+      seg = mp_alloc (oseg, okseq->segs);
+      seg->beg = (int32_t) cur;
+      seg->end = (int32_t) n;
+    }
+  }
+}
+
+int
+search_kmers_on_ont_reads (mp_t(rs) * ont_seqs, mp_t(ctg) * ctg_seqs,
+    xh_t ** ctg_khashs, mp_t(okseq) * okseqs, xh_set_t(kmer) ** anchored_ksets,
+    const char * prefix, int n_thread, int kmer_len)
+{
+  int i, nt;
+  time_t time_beg, mod_tbeg;
+  int64_t r, n_reads, n_hit = 0;
+  const char ** ptrs;
+  int32_t * lens;
+  gcg_hit * hits = NULL;
+  pthread_t * pids;
+  fill_arg_t * args;
+  gcg_bridge_t * br = gcg_bridge ();
+
+  time (&time_beg);
+  if (br->table == NULL)
+    err_mesg ("[%s] put_contig_kmers2hashs has not been called", __func__);
+  if (kmer_len != br->kmer_len)
+    err_mesg ("[%s] kmer_len %d differs from the table's %d", __func__, kmer_len, br->kmer_len);
+  nt = n_thread > 0 ? n_thread : 1;
+  GCG_CK (gcg_set_host_threads (br->ctx, nt));
+
+  /* search + ONT-side multiplicity on the device */
+  time (&mod_tbeg);
+  n_reads = mp_cnt (ont_seqs);
+  ptrs = (const char **) ckalloc (n_reads + 1, sizeof (char *));
+  lens = (int32_t *) ckalloc (n_reads + 1, sizeof (int32_t));
+  for (r = 0; r < n_reads; ++r) {
+    /* the reference searches okseq->seq over its single segment [0, l) (ont.c:207-223, 505-507) */
+    okseq_t * okseq = mp_at (okseq, okseqs, r);
+    ptrs[r] = okseq->seq->b;
+    lens[r] = okseq->seq->l;
+  }
+  GCG_CK (gcg_search (br->ctx, br->table, ptrs, lens, n_reads, kmer_len, &hits, &n_hit));
+  printf ("\n  chop and search ont kmers cost: %lds\n", time (NULL) - mod_tbeg);
+
+  /* back-fill okmers[] (the reference's REHASH phase re-pointed the same entries) */
+  time (&mod_tbeg);
+  if (nt > n_hit / 4096 + 1) nt = (int) (n_hit / 4096 + 1);
+  pids = (pthread_t *) ckalloc (nt, sizeof (pthread_t));
+  args = (fill_arg_t *) ckalloc (nt, sizeof (fill_arg_t));
+  for (i = 0; i < nt; ++i) {
+    args[i].hits = hits;
+    args[i].beg = n_hit * i / nt;
+    args[i].end = n_hit * (i + 1) / nt;
+    args[i].okseqs = okseqs;
+    args[i].ctgs = ctg_seqs;
+    ckpthread_create (pids + i, NULL, fill_core, (void *) (args + i));
+  }
+  for (i = 0; i < nt; ++i)
+    ckpthread_join (pids[i]);
+  printf ("\n  re-hash ont kmers cost: %lds\n", time (NULL) - mod_tbeg);
+
+  /* un-anchored segments */
+  time (&mod_tbeg);
+  rebuild_segs (okseqs, hits, n_hit);
+  printf ("\n  find un-ankored positions on onts costs: %lds\n", time (NULL) - mod_tbeg);
+
+  gcg_free (hits);
+  free (pids); free (args); free (ptrs); free (lens);
+
+  printf ("\n  search ONT kmers total cost: %lds\n", time (NULL) - time_beg);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ okseq set-up -------- */
+typedef struct {
+  int64_t * cursor;
+  mp_t(rs) * ont_seqs;
+  mp_t(okseq) * okseqs;
+} init_arg_t;
+
+static void *
+init_core (void * data)
+{
+  init_arg_t * a = (init_arg_t *) data;
+  int64_t n = mp_cnt (a->ont_seqs), i;
+  for (;;) {
+    rseq_t * r;
+    okseq_t * okseq;
+    ont_seg_t * seg;
+    i = __sync_fetch_and_add (a->cursor, 1);
+    if (i >= n) break;
+    r = mp_at (rs, a->ont_seqs, i);
+    okseq = a->okseqs->pool + i;
+    okseq->seq = r;
+    okseq->ont_id = (int) i;
+    mp_resize (okmer, okseq->okmers, r->l);      /* zero-filled: okmer->kmer == NULL means no anchor */
+    okseq->okmers->n = r->l;
+    mp_clear (oseg, okseq->segs, NULL);
+    seg = mp_alloc (oseg, okseq->segs);
+    seg->beg = 0;
+    seg->end = r->l;
+  }
+  return NULL;
+}
+
+/* same post-conditions as reference ont.c:483-512; the per-read zeroed allocations (16 bytes per
+ * ONT base, the largest single phase of the reference run) are spread over the host cores */
+int
+ont_kseqs_init (mp_t(rs) * ont_seqs, mp_t(okseq) * okseqs)
+{
+  int i, nt;
+  int64_t cursor = 0, n = mp_cnt (ont_seqs);
+  long ncpu = sysconf (_SC_NPROCESSORS_ONLN);
+  pthread_t * pids;
+  init_arg_t arg;
+
+  mp_resize (okseq, okseqs, n);
+  okseqs->n = n;
+
+  nt = ncpu > 16 ? 16 : (ncpu < 1 ? 1 : (int) ncpu);
+  if (nt > n) nt = n > 0 ? (int) n : 1;
+  arg.cursor = &cursor; arg.ont_seqs = ont_seqs; arg.okseqs = okseqs;
+  pids = (pthread_t *) ckalloc (nt, sizeof (pthread_t));
+  for (i = 0; i < nt; ++i)
+    ckpthread_create (pids + i, NULL, init_core, (void *) &arg);
+  for (i = 0; i < nt; ++i)
+    ckpthread_join (pids[i]);
+  free (pids);
+  return 0;
+}
+
+int
+ont_kseqs_dump (mp_t(okseq) * okseqs)
+{
+  int64_t i, j;
+  for (i = 0; i < mp_cnt (okseqs); ++i) {
+    okseq_t * okseq = mp_at (okseq, okseqs, i);
+    printf ("> ont %ld\n", i);
+    for (j = 0; j < mp_cnt (okseq->okmers); ++j) {
+      ont_kmer_t * ok = mp_at (okmer, okseq->okmers, j);
+      if (ok->kmer != NULL)
+        printf ("%d:%d:%d\n", ok->ont_pos, ok->kmer->kmer_len, ok->kmer->tid);
+    }
+  }
+  return 0;
+}

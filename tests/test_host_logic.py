@@ -1,0 +1,113 @@
+"""CPU: host-side pieces that need no GPU — synthetic data, contig splitting, the host C
+containers of the shim library (hash.c, cigar.c, hash_func.c replacement files)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from superplus_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "superplus_b200", "_build", "libgcshim.so")
+
+
+def test_synth_is_deterministic():
+    a, b = synth.make_config("tiny"), synth.make_config("tiny")
+    assert np.array_equal(a.scaffold, b.scaffold) and len(a.reads) == len(b.reads)
+    assert all(np.array_equal(x, y) for x, y in zip(a.reads, b.reads))
+
+
+def test_split_contigs_matches_reference_state_machine():
+    s = np.frombuffer(b"NNACGTNNNNACnGGTTN", dtype=np.uint8)
+    parts = [bytes(x) for x in synth.split_contigs(s)]
+    assert parts == [b"", b"ACGT", b"AC", b"GGTT"]
+    assert [bytes(x) for x in synth.split_contigs(np.frombuffer(b"ACGT", dtype=np.uint8))] == [b"ACGT"]
+    assert synth.split_contigs(np.zeros(0, np.uint8)) == []
+
+
+def test_sw_pairs_shape():
+    q, t = synth.make_sw_pairs(3, 500, 120, seed=1)
+    assert q.shape == (3, 500) and t.shape == (3, 120) and q.max() <= 3 and t.max() <= 3
+
+
+needs_shim = pytest.mark.skipif(not os.path.exists(SHIM), reason="libgcshim.so not built")
+
+
+@needs_shim
+def test_shim_cigar_container():
+    L = C.CDLL(SHIM)
+
+    class Cigar(C.Structure):
+        _fields_ = [("c", C.POINTER(C.c_uint32)), ("n", C.c_int32), ("m", C.c_int32)]
+
+    L.cigar_init.restype = C.POINTER(Cigar)
+    L.cigar_add.argtypes = [C.POINTER(Cigar), C.c_uint32]
+    L.cigar2ref_len.argtypes = [C.POINTER(Cigar)]
+    L.cigar2qry_len.argtypes = [C.POINTER(Cigar)]
+    c = L.cigar_init()
+    ops = [(5, 4), (10, 0), (0, 2), (2, 1), (3, 2), (7, 0), (1, 5)]
+    for l, o in ops:
+        L.cigar_add(c, (l << 4) | o)
+    assert c.contents.n == 7 and c.contents.m == 8
+    assert L.cigar2ref_len(c) == 20 and L.cigar2qry_len(c) == 24
+    assert L.cigar_has_zero_size_element(c) == 1
+    L.cigar_reverse(c)
+    assert [c.contents.c[i] for i in range(7)] == [(l << 4) | o for l, o in ops[::-1]]
+    out = L.cigar_init()
+    L.cigar_unclip(c, out)
+    assert out.contents.n == 5
+    d = L.cigar_init()
+    for l, o in [(3, 2), (0, 0), (4, 0), (2, 2)]:
+        L.cigar_add(d, (l << 4) | o)
+    L.cigar_cleanup(d, out)
+    assert [out.contents.c[i] for i in range(out.contents.n)] == [(4 << 4) | 0, (2 << 4) | 2]
+
+
+@needs_shim
+def test_shim_blizzard_hash_matches_fixture():
+    L = C.CDLL(SHIM)
+    L.blizzard_hash_func.restype = C.c_uint64
+    L.blizzard_hash_func.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    L.hash_func_init()
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "sw_vectors.json")))["blizzard"]
+    for w, vals in gold.items():
+        assert [L.blizzard_hash_func(w.encode(), len(w), ht) for ht in (0, 1, 2)] == vals
+
+
+@needs_shim
+def test_shim_hash_set_semantics():
+    """_xh_* contract of hash.h:60-110: insertion order pool, multiplicity, growth"""
+    L = C.CDLL(SHIM)
+    HF = C.CFUNCTYPE(C.c_uint64, C.c_void_p)
+    EQ = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
+    hf = HF(lambda p: C.cast(p, C.POINTER(C.c_uint64))[0])
+    eq = EQ(lambda a, b: int(C.cast(a, C.POINTER(C.c_uint64))[0] == C.cast(b, C.POINTER(C.c_uint64))[0]))
+
+    class Item(C.Structure):
+        pass
+    Item._fields_ = [("key", C.c_void_p), ("val", C.c_void_p), ("hash_val", C.c_uint64), ("id", C.c_int64),
+                     ("multi_deleted", C.c_uint32), ("next", C.POINTER(Item))]
+
+    class XH(C.Structure):
+        _fields_ = [("size", C.c_uint64), ("max", C.c_uint64), ("cnt", C.c_uint64), ("del_c", C.c_uint64), ("load_factor", C.c_double),
+                    ("hash_func", C.c_void_p), ("is_equal_func", C.c_void_p), ("pool", C.POINTER(Item)), ("slots", C.c_void_p)]
+
+    L._xh_init.restype = C.POINTER(XH)
+    L._xh_init.argtypes = [C.c_int64, C.c_double, HF, EQ]
+    L._xh_set_add.argtypes = [C.POINTER(XH), C.c_void_p]
+    L._xh_set_search3.restype = C.POINTER(Item)
+    L._xh_set_search3.argtypes = [C.POINTER(XH), C.c_void_p]
+    h = L._xh_init(16, 0.75, hf, eq)
+    assert h.contents.size == 256 and h.contents.max == 192
+    keys = (C.c_uint64 * 1000)(*[(i * 7919) % 600 for i in range(1000)])
+    rets = [L._xh_set_add(h, C.addressof(keys) + 8 * i) for i in range(1000)]
+    assert rets.count(1) == 600 and rets.count(2) == 400 and h.contents.cnt == 600
+    assert h.contents.size > 256                               # grew through next_prime
+    probe = C.c_uint64(7919 % 600)
+    it = L._xh_set_search3(h, C.addressof(probe))
+    assert it and (it.contents.multi_deleted & 0x7FFFFFFF) == 2 and it.contents.id == 1
+    missing = C.c_uint64(100000)
+    assert not L._xh_set_search3(h, C.addressof(missing))
+    assert [h.contents.pool[i].id for i in range(5)] == [0, 1, 2, 3, 4]

@@ -1,0 +1,78 @@
+"""CPU: the oracle against the reference binaries/libraries in oracle/_ref, live.  Skipped when
+oracle/_ref has not been built (it is built in the container that holds /root/reference and
+travels with the snapshot)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from superplus_b200 import synth
+
+pytestmark = pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref not built")
+
+
+def test_sw_random_against_reference_library(oracle):
+    rng = np.random.default_rng(99)
+    for it in range(120):
+        ql, tl = int(rng.integers(1, 160)), int(rng.integers(1, 160))
+        t = rng.integers(0, 5, tl).astype(np.uint8)
+        q = (synth.mutate(t, 0.2, rng) % 5) if rng.random() < 0.5 else rng.integers(0, 5, ql).astype(np.uint8)
+        if len(q) == 0:
+            q = np.array([0], np.uint8)
+        strategy = int(rng.integers(0, 4))
+        mat = rng.integers(-6, 4, size=(5, 5)).astype(np.int32)
+        np.fill_diagonal(mat, rng.integers(1, 6, size=5))
+        pen = tuple(int(x) for x in rng.integers(1, 7, size=4))
+        for mode, name in ((0, "asis"), (1, "fixed")):
+            R = orc.RefSW(name)
+            R.set(mat, pen[0], pen[1], pen[2], pen[3], strategy)
+            r = R.align(q, t)
+            R.close()
+            g = oracle.sw_align(orc.make_params(mat, pen[0], pen[1], pen[2], pen[3], strategy), q, t, mode)
+            assert (r["score"], r["offset"], r["softclip"], orc.cigar_str(r["cigar"])) == \
+                   (g["score"], g["offset"], g["softclip"], orc.cigar_str(g["cigar"])), (it, name)
+
+
+def test_sw_trace_bits_match_reference_cells(oracle):
+    """the 4 trace bits per cell the CUDA path spills are exactly the reference's (status, dl>1, il>1)"""
+    rng = np.random.default_rng(5)
+    t = rng.integers(0, 4, 70).astype(np.uint8)
+    q = synth.mutate(t, 0.2, rng) % 4
+    R = orc.RefSW("asis"); R.set(); R.align(q, t)
+    g = oracle.sw_align(orc.make_params(), q, t, 0, want_trace=True)
+    for i in range(1, len(t) + 1, 7):
+        for j in range(1, len(q) + 1, 5):
+            c = R.cell(i, j)
+            st = {1: 1, 2: 2, 4: 3}[c["status"]]
+            assert int(g["trace"][i, j]) == st | ((c["dl"] > 1) << 2) | ((c["il"] > 1) << 3)
+    R.close()
+
+
+def test_kmer_pipeline_against_reference_harness(oracle):
+    inp = synth.make_config("repeats")
+    with tempfile.TemporaryDirectory() as tmp:
+        fa, fq = os.path.join(tmp, "r.fa"), os.path.join(tmp, "r.fq")
+        synth.write_fasta(fa, inp.scaffold); synth.write_fastq(fq, inp.reads)
+        info, hits, table, ctgk = orc.run_ref_kmer(fa, fq, 21, os.path.join(tmp, "out"), n_thread=2, dump=2)
+    contigs = inp.contigs
+    h = oracle.table_build(contigs, 21)
+    key, multi, tid, pos, rev = oracle.table_dump(h)
+    T = table[np.argsort(table["kseq"], kind="stable")]
+    assert np.array_equal(T["kseq"], key) and np.array_equal(T["multi"], multi)
+    assert np.array_equal(T["tid"], tid) and np.array_equal(T["pos"], pos) and np.array_equal(T["flag"], rev)
+    H, ont = oracle.search(h, inp.reads, 21)
+    assert (oracle.table_stats(h) + ont) == (info["scaf_total"], info["scaf_unique"], info["ont_total"], info["ont_unique"])
+    assert np.array_equal(H["read"], hits["read"]) and np.array_equal(H["pos"], hits["pos"]) and np.array_equal(H["cpos"], hits["cpos"])
+    ks = np.concatenate([oracle.chop(c, 21)[0] for c in contigs])
+    assert np.array_equal(ks, ctgk["kseq"])
+    oracle.table_free(h)
+
+
+def test_blizzard_against_reference(oracle):
+    R = orc.RefSW("asis")
+    for w in (b"chr1", b"scaffold_9", b"", b"MixedCase_name"):
+        for ht in (0, 1, 2, 3):
+            assert oracle.blizzard(w, ht) == R.blizzard(w, ht)
+    R.close()
