@@ -56,6 +56,11 @@ int  gcg_prof_reset (gcg_ctx * ctx);
 int  gcg_prof_report (gcg_ctx * ctx, char * buf, int64_t cap);
 /* number of kernels launched by this ctx since creation */
 int64_t gcg_launch_count (gcg_ctx * ctx);
+/* measured roofline denominators of this device: packed s16x2 add+max lane-ops per second
+ * (one lane-op = one VIADDMNMX.S16x2 on one thread = two 16-bit results), and device copy
+ * bandwidth in bytes per second (read + write) */
+int  gcg_ubench_int16 (gcg_ctx * ctx, double * lane_ops_per_s);
+int  gcg_ubench_hbm (gcg_ctx * ctx, double * bytes_per_s);
 
 /* ------------------------------------------------------------------ sequences -------- */
 /* K1: ASCII -> 2 bit, base2int(b) = (b>>1)&3 (bio.h:24; kseq1.h:28-35).  Host pointers. */

@@ -11,6 +11,7 @@
 //   stats          kmer.c:265-312
 #include <algorithm>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <thread>
 
@@ -862,25 +863,56 @@ extern "C" int gcg_hits_download (gcg_ctx * ctx, const gcg_hits * h, gcg_hit * d
   return GCG_OK;
 }
 
+// Host-buffer search.  Read sets with more than 2^31 k-mer start positions (cfg5: 5 G) are cut
+// into consecutive groups of whole reads; every group is uploaded, searched and its anchors are
+// appended (read indices shifted back to the caller's numbering), so the result is still in
+// (read,pos) order.  The ONT multiplicity state accumulates in the table across the groups.
 extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
                            int64_t n_read, int k, gcg_hit ** hits_out, int64_t * n_hit)
 {
-  GCG_CHECK (hits_out && n_hit, GCG_EINVAL, "gcg_search: NULL output");
-  gcg_seqs * s = nullptr;
-  gcg_hits * h = nullptr;
-  int rc = gcg_seqs_upload (ctx, read_seq, read_len, n_read, &s);
-  if (rc) return rc;
-  rc = gcg_search_seqs (ctx, t, s, k, &h);
-  gcg_seqs_free (s);
-  if (rc) return rc;
-  *n_hit = h->n;
+  GCG_CHECK (ctx && t && hits_out && n_hit && n_read >= 0 && (n_read == 0 || (read_seq && read_len)), GCG_EINVAL, "gcg_search: bad argument");
   *hits_out = nullptr;
-  if (h->n > 0) {
-    cudaError_t e = cudaHostAlloc ((void **) hits_out, (size_t) h->n * sizeof (gcg_hit), cudaHostAllocDefault);
-    if (e != cudaSuccess) { gcg_set_error ("gcg_search: pinned alloc failed: %s", cudaGetErrorString (e)); gcg_hits_free (h); return GCG_ENOMEM; }
-    rc = gcg_hits_download (ctx, h, *hits_out, h->n);
+  *n_hit = 0;
+  int64_t group_limit = (int64_t) 1 << 31;
+  if (const char * e = getenv ("GCG_SEARCH_GROUP_KMERS")) group_limit = std::max<int64_t> (1, atoll (e));
+  std::vector<std::pair<int64_t, int64_t>> groups;       // [first read, last read)
+  int64_t g0 = 0, acc = 0;
+  for (int64_t r = 0; r < n_read; ++r) {
+    int64_t kk = read_len[r] >= k ? (int64_t) read_len[r] - k + 1 : 0;
+    if (acc + kk > group_limit && r > g0) { groups.emplace_back (g0, r); g0 = r; acc = 0; }
+    acc += kk;
   }
-  gcg_hits_free (h);
+  groups.emplace_back (g0, n_read);
+
+  std::vector<gcg_hits *> parts;
+  int64_t total = 0;
+  int rc = GCG_OK;
+  for (auto & g : groups) {
+    gcg_seqs * s = nullptr;
+    gcg_hits * h = nullptr;
+    rc = gcg_seqs_upload (ctx, read_seq + g.first, read_len + g.first, g.second - g.first, &s);
+    if (!rc) rc = gcg_search_seqs (ctx, t, s, k, &h);
+    gcg_seqs_free (s);
+    if (rc) break;
+    parts.push_back (h);
+    total += h->n;
+  }
+  if (!rc && total > 0) {
+    cudaError_t e = cudaHostAlloc ((void **) hits_out, (size_t) total * sizeof (gcg_hit), cudaHostAllocDefault);
+    if (e != cudaSuccess) { gcg_set_error ("gcg_search: pinned alloc of %lld anchors failed: %s", (long long) total, cudaGetErrorString (e)); rc = GCG_ENOMEM; }
+    int64_t at = 0;
+    for (size_t gi = 0; gi < parts.size () && !rc; ++gi) {
+      rc = gcg_hits_download (ctx, parts[gi], *hits_out + at, parts[gi]->n);
+      if (!rc && groups[gi].first != 0) {
+        int32_t shift = (int32_t) groups[gi].first;
+        for (int64_t i = 0; i < parts[gi]->n; ++i) (*hits_out)[at + i].read += shift;
+      }
+      at += parts[gi]->n;
+    }
+    if (rc) { cudaFreeHost (*hits_out); *hits_out = nullptr; }
+  }
+  for (gcg_hits * h : parts) gcg_hits_free (h);
+  if (!rc) *n_hit = total;
   return rc;
 }
 

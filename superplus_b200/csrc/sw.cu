@@ -488,8 +488,26 @@ sw_maxsym_kernel (const uint8_t * __restrict__ qry, const long long * __restrict
 // =============================================================================================
 // host side
 // =============================================================================================
+// device scratch that survives between align calls on the same batch (cudaMalloc of tens of GB of
+// trace is far more expensive than the kernels that fill it)
+struct sw_devbuf {
+  void * p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve (size_t bytes)
+  {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree (p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc (&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release () { if (p) cudaFree (p); p = nullptr; cap = 0; }
+};
+
 struct gcg_swbatch {
   gcg_ctx * ctx = nullptr;
+  sw_devbuf s_trace, s_edges, s_tasks, s_wave_tasks, s_items, s_counter, s_bound, s_pbound;
   int64_t n = 0;
   std::vector<long long> qoff, toff;
   uint8_t * d_qry = nullptr, * d_tgt = nullptr;
@@ -511,6 +529,8 @@ extern "C" void gcg_swbatch_free (gcg_swbatch * b)
   if (!b) return;
   cudaFree (b->d_qry); cudaFree (b->d_tgt); cudaFree (b->d_qoff); cudaFree (b->d_toff); cudaFree (b->d_maxsym);
   cudaFree (b->d_results); cudaFree (b->d_ends); cudaFree (b->d_pool);
+  b->s_trace.release (); b->s_edges.release (); b->s_tasks.release (); b->s_wave_tasks.release ();
+  b->s_items.release (); b->s_counter.release (); b->s_bound.release (); b->s_pbound.release ();
   delete b;
 }
 
@@ -720,7 +740,7 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
 
   uint32_t * d_trace = nullptr; int * d_edges = nullptr; sw_task * d_tasks = nullptr; int * d_items = nullptr; int * d_counter = nullptr;
   int2 * d_bound = nullptr;
-  uint2 * d_pbound = nullptr; size_t packed_bound_rows = 0;
+  uint2 * d_pbound = nullptr;
   sw_task * d_wave_tasks = nullptr;
   unsigned long long total_trace = 0; long long total_edges = 0;
   for (auto & t : tasks) { total_trace += trace_words (t); total_edges += (long long) t.qlen + t.tlen; }
@@ -732,16 +752,23 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
   for (auto & t : tasks) max_tlen = std::max<long long> (max_tlen, t.tlen);
   const int gen_blocks = ctx->sm_count * 4;          // 4 warps per block, 4 blocks per SM resident
   long long bound_stride = max_tlen + 1;
-  if ((ce = cudaMalloc (&d_trace, (size_t) trace_cap * 4)) != cudaSuccess ||
-      (ce = cudaMalloc (&d_edges, (size_t) std::max<long long> (total_edges, 1) * 4)) != cudaSuccess ||
-      (ce = cudaMalloc (&d_tasks, (size_t) n * sizeof (sw_task))) != cudaSuccess ||
-      (ce = cudaMalloc (&d_wave_tasks, (size_t) n * sizeof (sw_task))) != cudaSuccess ||
-      (ce = cudaMalloc (&d_items, (size_t) n * 8)) != cudaSuccess ||
-      (ce = cudaMalloc (&d_counter, 2 * sizeof (int))) != cudaSuccess ||
-      (generic_ids.size () && (ce = cudaMalloc (&d_bound, (size_t) gen_blocks * 4 * (size_t) bound_stride * sizeof (int2))) != cudaSuccess)) {
+  // keep the trace buffer of an earlier align on this batch whenever it can hold whole alignments
+  // (the memory it occupies is no longer "free", so the budget above shrinks on later calls)
+  if (b->s_trace.cap / 4 >= std::max<unsigned long long> (2 * max_single, 32))
+    trace_cap = std::min<unsigned long long> (std::max<unsigned long long> (total_trace, 32), b->s_trace.cap / 4);
+  if ((ce = b->s_trace.reserve ((size_t) trace_cap * 4)) != cudaSuccess ||
+      (ce = b->s_edges.reserve ((size_t) std::max<long long> (total_edges, 1) * 4)) != cudaSuccess ||
+      (ce = b->s_tasks.reserve ((size_t) n * sizeof (sw_task))) != cudaSuccess ||
+      (ce = b->s_wave_tasks.reserve ((size_t) n * sizeof (sw_task))) != cudaSuccess ||
+      (ce = b->s_items.reserve ((size_t) n * 8)) != cudaSuccess ||
+      (ce = b->s_counter.reserve (2 * sizeof (int))) != cudaSuccess ||
+      (generic_ids.size () && (ce = b->s_bound.reserve ((size_t) gen_blocks * 4 * (size_t) bound_stride * sizeof (int2))) != cudaSuccess)) {
     gcg_set_error ("gcg_swbatch_align: cudaMalloc failed: %s", cudaGetErrorString (ce));
     rc = GCG_ENOMEM;
   }
+  d_trace = (uint32_t *) b->s_trace.p; d_edges = (int *) b->s_edges.p; d_tasks = (sw_task *) b->s_tasks.p;
+  d_wave_tasks = (sw_task *) b->s_wave_tasks.p; d_items = (int *) b->s_items.p; d_counter = (int *) b->s_counter.p;
+  d_bound = (int2 *) b->s_bound.p;
   // edge offsets are global for the batch (small: 4 bytes per symbol)
   if (!rc) {
     long long eo = 0;
@@ -813,11 +840,9 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
       GCG_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, sw_fill_packed_kernel, 32, smem));
       if (per_sm < 1) per_sm = 1;
       int grid = (int) std::min<size_t> (pitems.size (), (size_t) ctx->sm_count * per_sm);
-      if (packed_bound_rows < (size_t) grid * rows_cap) {
-        cudaFree (d_pbound); d_pbound = nullptr;
-        packed_bound_rows = (size_t) ctx->sm_count * per_sm * rows_cap;
-        if ((ce = cudaMalloc (&d_pbound, packed_bound_rows * sizeof (uint2))) != cudaSuccess) { gcg_set_error ("gcg_swbatch_align: boundary scratch: %s", cudaGetErrorString (ce)); rc = GCG_ENOMEM; break; }
-      }
+      if ((ce = b->s_pbound.reserve ((size_t) ctx->sm_count * per_sm * rows_cap * sizeof (uint2))) != cudaSuccess) {
+        gcg_set_error ("gcg_swbatch_align: boundary scratch: %s", cudaGetErrorString (ce)); rc = GCG_ENOMEM; break; }
+      d_pbound = (uint2 *) b->s_pbound.p;
       gcg_kscope ks (ctx, "k7_sw_fill_packed");
       sw_fill_packed_kernel<<<grid, 32, smem, ctx->stream>>> (b->d_qry, b->d_tgt, d_tasks, (const int2 *) d_items, (int) pitems.size (),
                                                               d_counter, d_trace, d_edges, d_pbound, rows_cap, b->d_ends);
@@ -859,7 +884,6 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
     u0 = u1;
   }
   if (!rc && cudaStreamSynchronize (ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_swbatch_align: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; }
-  cudaFree (d_trace); cudaFree (d_edges); cudaFree (d_tasks); cudaFree (d_wave_tasks); cudaFree (d_items); cudaFree (d_counter); cudaFree (d_bound); cudaFree (d_pbound);
   if (!rc) b->aligned = true;
   return rc;
 }
