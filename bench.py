@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the gap-closing hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one pass of the hot path over one batch of synthetic input:
+  k-mer part (the JSON line's `value`): BASELINE.json configs[1] — 4.6 Mb synthetic scaffold, 500
+      N-gaps, 30x simulated ONT (10 % error), k = 25: 2-bit pack of contigs and reads, contig
+      k-mer table build, ONT search with anchor emission in (read,pos) order, statistics.
+      Unit = ONT k-mers looked up per second (whole job, all ranks).
+  SW part (the `sw` object): BASELINE.json configs[2] shape — ONT-read(10 kb) x gap-flank(2 kb)
+      pairs, default scoring of gc_graph.c:74-77, fill + trace spill + end cell + CIGAR, as
+      many pairs per step as fill two whole waves of resident warps.  Unit = GCUPS.
+`value` is measured with the inputs resident in HBM (CUDA events on the library's stream, max
+over ranks); `e2e` is the same metric through the host-buffer C-ABI calls the C shims use
+(gcg_table_build + gcg_search, gcg_sw_batch), host<->device copies inside the timed region.
+N > 1: one process per GPU; reads / pairs are sharded by batch, the contig table is replicated
+(SURVEY §8e), no collective on the data path -> weak scaling.
+
+--impl reference times the reference's own CPU code (oracle/_ref, built unmodified from
+/root/reference/gap_closer) on the box's host cores, same metric and config, bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from superplus_b200 import synth  # noqa: E402
+
+K = 25
+WORKLOAD = "cfg2"
+SW_QLEN, SW_TLEN = 10_000, 2_000
+BYTES_PER_LOOKUP, BYTES_PER_HIT = 16.25, 16.0        # SURVEY §8(d) algorithmic bytes
+OPS_PER_CELL = 12.0                                  # SURVEY §8(d) integer ops per DP cell
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    """per-launch DRAM bytes of `kernel` from the committed ncu capture, or None"""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock and throttle reasons through NVML while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        if self.nv is None or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def make_workload(rank):
+    """cfg2; rank r > 0 draws its own read batch (same scaffold) — reads are sharded by batch"""
+    cfg = synth.CONFIGS[WORKLOAD]
+    if rank == 0:
+        inp = synth.make_config(WORKLOAD)
+        return inp.contigs, inp.reads, inp
+    base = synth.make_gap_closer_input(cfg["genome_len"], cfg["n_gaps"], 0.0, cfg["seed"])
+    reads = synth.make_reads(base.genome, cfg["coverage"], cfg["seed"] + 1000 * rank)
+    return base.contigs, reads, base
+
+
+def reference_available():
+    from oracle import oracle as orc
+    return orc.have_ref()
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own code on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_kmer(contig_scaffold, reads, n_thread, tmp):
+    """runs oracle/_ref/ref_kmer (reference contig.c/rseq.c/kmer.c/hash.c/ont.c) and returns
+    (ONT k-mers per second over chop+put+search, info dict)"""
+    from oracle import oracle as orc
+    fa, fq = os.path.join(tmp, "b.fa"), os.path.join(tmp, "b.fq")
+    synth.write_fasta(fa, contig_scaffold)
+    synth.write_fastq(fq, reads)
+    info, _, _, _ = orc.run_ref_kmer(fa, fq, K, os.path.join(tmp, "b"), n_thread=n_thread, dump=0)
+    t = info["t_chop"] + info["t_put"] + info["t_search"]
+    return info["n_ont_kmers"] / t, info
+
+
+def cpu_sw(n_thread, pairs_per_thread, seed=46):
+    from oracle import oracle as orc
+    n = n_thread * pairs_per_thread
+    q, t = synth.make_sw_pairs(n, SW_QLEN, SW_TLEN, seed=seed)
+    R = orc.RefSW("asis")
+    sec, scores = R.bench(n_thread, q, t)
+    R.close()
+    return n * SW_QLEN * SW_TLEN / sec / 1e9, n, scores
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    if not reference_available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built (needs /root/reference at build time)"}))
+        return
+    inp = synth.make_config(WORKLOAD)
+    sub = inp.reads[: max(1, len(inp.reads) // 8)]             # bounded sample: 1/8 of the cfg2 reads
+    vals, sw_vals, times = [], [], []
+    with tempfile.TemporaryDirectory() as tmp:
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            v, info = cpu_kmer(inp.scaffold, sub, cores, tmp)
+            g, npairs, _ = cpu_sw(cores, 1)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                vals.append(v); sw_vals.append(g); times.append(dt)
+    value = statistics.mean(vals)
+    sample = "full cfg2 scaffold (4.6 Mb, 500 gaps) x the first 1/8 of its 30x ONT reads (%d reads, %d k-mers) per step; chop+put+search timed inside ref_kmer" % (len(sub), info["n_ont_kmers"])
+    line = {
+        "impl": "reference", "metric": "kmers_per_s", "value": value, "unit": "k-mers/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "cfg2: 4.6 Mb synthetic scaffolds, 500 N-gaps, 30x ONT (10% error), k=25; reference CPU code (kmer.c, hash.c, ont.c) on the host cores",
+                   "k": K, "threads": cores},
+        "cpu_baseline": {"value": value, "unit": "k-mers/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "sw": {"metric": "sw_gcups", "value": statistics.mean(sw_vals), "unit": "GCUPS", "impl": "reference",
+               "cpu_baseline": {"value": statistics.mean(sw_vals), "unit": "GCUPS", "cores": cores, "kind": "reference",
+                                "sample": "%d pairs of 10 kb x 2 kb per step, one reference sw_t per core (sw.c:400-414)" % cores},
+               "e2e": {"value": statistics.mean(sw_vals), "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    from superplus_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    torch.cuda.set_device(local_rank)
+    ctx = api.Context(local_rank, host_threads=min(16, max(1, (os.cpu_count() or 8) // max(world, 1))))
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local_rank))
+
+    contigs, reads, inp = make_workload(rank)
+    n_ont_kmers = sum(max(0, len(r) - K + 1) for r in reads)
+    n_ctg_kmers = sum(max(0, len(c) - K + 1) for c in contigs)
+    read_bytes, ctg_bytes = sum(len(r) for r in reads), sum(len(c) for c in contigs)
+
+    # inputs resident in HBM before the timed region (ASCII, as the reference's inputs are)
+    a_ctg, a_reads = ctx.stage_ascii(contigs), ctx.stage_ascii(reads)
+
+    def kmer_step():
+        cs = ctx.pack(a_ctg)
+        rs = ctx.pack(a_reads)
+        t = ctx.table_build(cs, K)
+        n_hit = ctx.search_device(t, rs)
+        st = t.stats()
+        t.free(); cs.free(); rs.free()
+        return n_hit, st
+
+    # SW batch resident in HBM: two whole waves of the packed kernel (5920 pairs each on a 148-SM part)
+    sw_pairs = args.sw_pairs
+    bq, bt = synth.make_sw_pairs(min(sw_pairs, 512), SW_QLEN, SW_TLEN, seed=46 + rank)
+    reps = (sw_pairs + len(bq) - 1) // len(bq)
+    q2, t2 = np.tile(bq, (reps, 1))[:sw_pairs], np.tile(bt, (reps, 1))[:sw_pairs]
+    swb = ctx.swbatch_upload(q2, t2)
+    P = api.make_sw_params()
+    sw_cells = swb.cells()
+
+    def sw_step():
+        swb.align(P, api.SW_ASIS)
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        n_hit, st = kmer_step()
+        sw_step()
+    r_int16 = ctx.ubench_int16()
+
+    # ---- timed: k-mer steps
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.prof(True); ctx.prof_reset()
+    launches0 = ctx.launches()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        n_hit, st = kmer_step()
+    e1.record(stream)
+    barrier()
+    kmer_ms = allmax(e0.elapsed_time(e1)) / args.steps
+    kprof = ctx.prof_report()
+    kmer_launches = ctx.launches() - launches0
+
+    # ---- timed: SW steps
+    ctx.prof_reset()
+    launches1 = ctx.launches()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for _ in range(args.steps):
+        sw_step()
+    e3.record(stream)
+    barrier()
+    sw_ms = allmax(e2.elapsed_time(e3)) / args.steps
+    sprof = ctx.prof_report()
+    sw_launches = ctx.launches() - launches1
+    ctx.prof(False)
+    clocks = sampler.result()
+
+    # ---- end to end through the host-buffer C ABI (what the C shims call)
+    arrs = [np.ascontiguousarray(r) for r in reads]
+    import ctypes as C
+    rptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    rlens = np.array([len(a) for a in arrs], dtype=np.int32)
+    carrs = [np.ascontiguousarray(c) for c in contigs]
+    cptrs = (C.c_void_p * max(1, len(carrs)))(*[a.ctypes.data for a in carrs])
+    clens = np.array([len(a) for a in carrs], dtype=np.int32)
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_hits = 0
+
+    def e2e_kmer():
+        h = C.c_void_p()
+        ctx._chk(ctx.L.gcg_table_build(ctx.h, C.cast(cptrs, C.c_void_p), clens.ctypes.data, len(carrs), K, C.byref(h)))
+        tab = api.KmerTable(ctx, h, K)
+        hits = ctx.search_host_ptrs(tab, rptrs, rlens, len(arrs))
+        s4 = tab.stats()
+        tab.free()
+        return len(hits), s4
+
+    e2e_kmer()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_hits, e2e_st = e2e_kmer()
+    barrier()
+    e2e_kmer_s = allmax(time.perf_counter() - t0) / e2e_steps
+    assert e2e_hits == n_hit and e2e_st == st, "e2e and device-resident paths disagree"
+
+    sw_e2e_pairs = min(sw_pairs, 2960 * 2)
+    qe, te = q2[:sw_e2e_pairs], t2[:sw_e2e_pairs]
+    ctx.sw_batch(P, list(qe[:64]), list(te[:64]), api.SW_ASIS)
+    barrier()
+    t0 = time.perf_counter()
+    res_e2e, cig_e2e = None, None
+    for _ in range(2):
+        qb, qo = np.ascontiguousarray(qe).reshape(-1), np.arange(sw_e2e_pairs + 1, dtype=np.int64) * SW_QLEN
+        tb, to = np.ascontiguousarray(te).reshape(-1), np.arange(sw_e2e_pairs + 1, dtype=np.int64) * SW_TLEN
+        res = np.zeros(sw_e2e_pairs, dtype=api.SWRES_DTYPE)
+        pool, npool = C.c_void_p(), C.c_int64()
+        ctx._chk(ctx.L.gcg_sw_batch(ctx.h, C.byref(P), api.SW_ASIS, qb.ctypes.data, qo.ctypes.data, tb.ctypes.data, to.ctypes.data,
+                                    sw_e2e_pairs, res.ctypes.data, C.byref(pool), C.byref(npool)))
+        n_ops = npool.value
+        ctx.L.gcg_free(pool)
+    barrier()
+    e2e_sw_s = allmax(time.perf_counter() - t0) / 2
+
+    # ---- aggregate over ranks
+    tot_ont_kmers = allsum(float(n_ont_kmers))
+    tot_cells = allsum(float(sw_cells))
+    tot_e2e_cells = allsum(float(sw_e2e_pairs) * SW_QLEN * SW_TLEN)
+    value = tot_ont_kmers / (kmer_ms * 1e-3)
+    sw_value = tot_cells / (sw_ms * 1e-3) / 1e9
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak_gbs, peak_src = measured_peaks()
+    k45_ms = kprof.get("k45_search", (0.0, 1))
+    k45_avg = k45_ms[0] / max(1, k45_ms[1])
+    alg_bytes = BYTES_PER_LOOKUP * n_ont_kmers + BYTES_PER_HIT * n_hit
+    achieved = alg_bytes / (k45_avg * 1e-3) / 1e9 if k45_avg > 0 else 0.0
+    fill = sprof.get("k7_sw_fill_packed", (0.0, 1))
+    fill_gcups = sw_cells / (fill[0] / args.steps * 1e-3) / 1e9 if fill[0] > 0 else 0.0
+    sw_peak = r_int16 * 2.0 / OPS_PER_CELL / 1e9          # 16-bit results per second / 12 ops per cell
+
+    line = {
+        "metric": "kmers_per_s", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": kmer_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "cfg2: 4.6 Mb synthetic scaffolds, 500 N-gaps, 30x ONT (10% error), k=25 — pack + contig table build + ONT search + ordered anchors + stats per step",
+                   "k": K, "contigs": len(contigs), "reads_per_gpu": len(reads), "ont_kmers_per_gpu": n_ont_kmers, "contig_kmers": n_ctg_kmers,
+                   "anchors_per_gpu": int(n_hit), "stats": list(st), "parallelism": "reads sharded by batch, table replicated (no data-path collective)",
+                   "l2": "inputs larger than L2 (138 MB ASCII reads + 106 MB table per step vs 126 MB L2); no explicit flush"},
+        "e2e": {"value": tot_ont_kmers / e2e_kmer_s, "unit": "k-mers/s", "h2d_bytes_per_step": int(read_bytes + ctg_bytes),
+                "d2h_bytes_per_step": int(n_hit * 16 + 32), "ms_per_step": e2e_kmer_s * 1e3,
+                "api": "gcg_table_build + gcg_search (host pointers in, pinned anchors out) + gcg_table_stats"},
+        "gpu_launches": int(kmer_launches + sw_launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k45_search_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": achieved / peak_gbs, "traffic": ncu_traffic("k45_search_kernel"), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k45_avg,
+                     "kernel_ms_per_step": {k_: v[0] / args.steps for k_, v in sorted(kprof.items())}},
+        "sw": {"metric": "sw_gcups", "value": sw_value, "unit": "GCUPS", "ms_per_step": sw_ms, "dtype": "s16x2",
+               "config": {"workload": "cfg3 shape: ONT-read(10 kb) x gap-flank(2 kb) pairs, default scoring (+1/-5/2/1, softclip), as-is traceback; fill + trace spill + end cell + CIGAR",
+                          "pairs_per_gpu_per_step": int(sw_pairs), "cells_per_gpu_per_step": int(sw_cells), "paths": list(swb.path_counts()),
+                          "l2": "10.4 MB of trace per pair (123 GB per step) streams through L2"},
+               "e2e": {"value": tot_e2e_cells / e2e_sw_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(sw_e2e_pairs * (SW_QLEN + SW_TLEN)),
+                       "d2h_bytes_per_step": int(sw_e2e_pairs * 32 + n_ops * 4), "pairs_per_step": int(sw_e2e_pairs), "api": "gcg_sw_batch (host buffers)"},
+               "roofline": {"bound": "int_alu", "kernel": "sw_fill_packed_kernel", "achieved": fill_gcups, "peak": sw_peak, "unit": "GCUPS",
+                            "frac": fill_gcups / sw_peak if sw_peak else None, "traffic": ncu_traffic("sw_fill_packed_kernel"),
+                            "peak_source": "measured in this run: VIADDMNMX.S16x2 issue rate %.2f T lane-ops/s x 2 halves / 12 integer ops per cell (SURVEY 8d)" % (r_int16 / 1e12),
+                            "secondary": {"bound": "hbm", "achieved": 0.5 * sw_cells / (fill[0] / args.steps * 1e-3) / 1e9 if fill[0] > 0 else 0.0,
+                                          "peak": peak_gbs, "unit": "GB/s", "note": "trace spill, 0.5 byte per cell"},
+                            "kernel_ms_per_step": {k_: v[0] / args.steps for k_, v in sorted(sprof.items())}}},
+    }
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the reference itself on the host cores
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        try:
+            if reference_available():
+                with tempfile.TemporaryDirectory() as tmp:
+                    v, info = cpu_kmer(inp.scaffold, reads, cores, tmp)
+                line["cpu_baseline"] = {"value": v, "unit": "k-mers/s", "cores": cores, "kind": "reference",
+                                        "sample": "the full cfg2 workload once (%d ONT k-mers); reference chop %.2fs + hash %.2fs + search/rehash %.2fs on %d threads" %
+                                                  (info["n_ont_kmers"], info["t_chop"], info["t_put"], info["t_search"], cores)}
+                assert [info["scaf_total"], info["scaf_unique"], info["ont_total"], info["ont_unique"]] == list(st), "GPU and reference statistics differ"
+                assert info["n_hits"] == n_hit, "GPU and reference anchor counts differ"
+                g, npairs, scores = cpu_sw(cores, 2, seed=46)
+                line["sw"]["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": cores, "kind": "reference",
+                                              "sample": "%d pairs of 10 kb x 2 kb, one reference sw_t per core" % npairs}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "k-mers/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref not built"}
+        except Exception as e:      # the baseline must never sink the bench line
+            line["cpu_baseline"] = {"value": None, "unit": "k-mers/s", "cores": cores, "kind": "reference", "sample": "failed: %r" % (e,)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sw-pairs", type=int, default=11840)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3                      # timing rule: at least three warm-up steps
+    rank, local_rank, world = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

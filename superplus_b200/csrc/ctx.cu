@@ -46,6 +46,13 @@ extern "C" int gcg_init (int device, gcg_ctx ** out)
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   GCG_CUDA (cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking));
+  {
+    // keep freed blocks in the stream-ordered pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    GCG_CUDA (cudaDeviceGetDefaultMemPool (&pool, device));
+    unsigned long long keep = ~0ULL;
+    GCG_CUDA (cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   GCG_CUDA (cudaMalloc (&ctx->d_counters, 16 * sizeof (unsigned long long)));
   GCG_CUDA (cudaHostAlloc (&ctx->h_counters, 16 * sizeof (unsigned long long), cudaHostAllocDefault));
   *out = ctx;

@@ -136,3 +136,18 @@ struct gcg_hits {
 #define GCG_KEY_MULTI 0x8000000000000000ULL
 
 int gcg_stage_reserve (gcg_ctx * ctx);
+
+// stream-ordered device allocations from the context's pool: no device synchronisation, freed
+// blocks are reused by the next call (the pool never trims, see gcg_init)
+static inline cudaError_t gcg_dmalloc (gcg_ctx * ctx, void ** p, size_t bytes)
+{
+  return cudaMallocAsync (p, bytes ? bytes : 16, ctx->stream);
+}
+template <class T> static inline cudaError_t gcg_dmalloc (gcg_ctx * ctx, T ** p, size_t bytes)
+{
+  return gcg_dmalloc (ctx, (void **) p, bytes);
+}
+static inline void gcg_dfree (gcg_ctx * ctx, void * p)
+{
+  if (p) cudaFreeAsync (p, ctx->stream);
+}

@@ -574,10 +574,10 @@ static int launch_pack (gcg_ctx * ctx, const char * d_ascii, uint64_t * d_packed
 
 static int seqs_alloc (gcg_ctx * ctx, gcg_seqs * s)
 {
-  GCG_CUDA (cudaMalloc (&s->d_packed, (size_t) (s->n_words + 2) * 8));
+  GCG_CUDA (gcg_dmalloc (ctx, &s->d_packed, (size_t) (s->n_words + 2) * 8));
   GCG_CUDA (cudaMemsetAsync (s->d_packed + s->n_words, 0, 16, ctx->stream));
-  GCG_CUDA (cudaMalloc (&s->d_woff, (size_t) (s->n + 1) * 8));
-  GCG_CUDA (cudaMalloc (&s->d_len, (size_t) std::max<int64_t> (s->n, 1) * 4));
+  GCG_CUDA (gcg_dmalloc (ctx, &s->d_woff, (size_t) (s->n + 1) * 8));
+  GCG_CUDA (gcg_dmalloc (ctx, &s->d_len, (size_t) std::max<int64_t> (s->n, 1) * 4));
   GCG_CUDA (cudaMemcpyAsync (s->d_woff, s->h_woff.data (), (size_t) (s->n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
   if (s->n) GCG_CUDA (cudaMemcpyAsync (s->d_len, s->h_len.data (), (size_t) s->n * 4, cudaMemcpyHostToDevice, ctx->stream));
   return GCG_OK;
@@ -622,9 +622,9 @@ extern "C" int gcg_ascii_upload_concat (gcg_ctx * ctx, const char * buf, const i
   seq_src src; src.buf = buf; src.off = off;
   int rc = make_layout (nullptr, off, n, a->h_woff, a->h_len, a->n_words, a->n_bases);
   if (rc) { delete a; return rc; }
-  GCG_CUDA (cudaMalloc (&a->d_ascii, (size_t) std::max<int64_t> (a->n_words, 1) * 32));
-  GCG_CUDA (cudaMalloc (&a->d_woff, (size_t) (n + 1) * 8));
-  GCG_CUDA (cudaMalloc (&a->d_len, (size_t) std::max<int64_t> (n, 1) * 4));
+  GCG_CUDA (gcg_dmalloc (ctx, &a->d_ascii, (size_t) std::max<int64_t> (a->n_words, 1) * 32));
+  GCG_CUDA (gcg_dmalloc (ctx, &a->d_woff, (size_t) (n + 1) * 8));
+  GCG_CUDA (gcg_dmalloc (ctx, &a->d_len, (size_t) std::max<int64_t> (n, 1) * 4));
   GCG_CUDA (cudaMemcpyAsync (a->d_woff, a->h_woff.data (), (size_t) (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
   if (n) GCG_CUDA (cudaMemcpyAsync (a->d_len, a->h_len.data (), (size_t) n * 4, cudaMemcpyHostToDevice, ctx->stream));
   rc = stream_ascii (ctx, src, a->h_woff, a->h_len, n, a->n_words, [&] (char * d, int64_t w0, int64_t nw) {
@@ -654,14 +654,14 @@ extern "C" int gcg_seqs_pack (gcg_ctx * ctx, const gcg_ascii * a, gcg_seqs ** ou
 extern "C" void gcg_ascii_free (gcg_ascii * a)
 {
   if (!a) return;
-  cudaFree (a->d_ascii); cudaFree (a->d_woff); cudaFree (a->d_len);
+  gcg_dfree (a->ctx, a->d_ascii); gcg_dfree (a->ctx, a->d_woff); gcg_dfree (a->ctx, a->d_len);
   delete a;
 }
 
 extern "C" void gcg_seqs_free (gcg_seqs * s)
 {
   if (!s) return;
-  cudaFree (s->d_packed); cudaFree (s->d_woff); cudaFree (s->d_len);
+  gcg_dfree (s->ctx, s->d_packed); gcg_dfree (s->ctx, s->d_woff); gcg_dfree (s->ctx, s->d_len);
   delete s;
 }
 
@@ -679,7 +679,7 @@ extern "C" int64_t gcg_seqs_kmers (const gcg_seqs * s, int k)
 extern "C" void gcg_table_free (gcg_table * t)
 {
   if (!t) return;
-  cudaFree (t->d_keys); cudaFree (t->d_vals); cudaFree (t->d_ont);
+  gcg_dfree (t->ctx, t->d_keys); gcg_dfree (t->ctx, t->d_vals); gcg_dfree (t->ctx, t->d_ont);
   delete t;
 }
 
@@ -702,8 +702,8 @@ extern "C" int gcg_table_build_seqs (gcg_ctx * ctx, const gcg_seqs * contigs, in
   t->n_inserted = n_kmers;
   size_t ont_words = (size_t) ((t->n_slot + 15) >> 4);
   cudaError_t e;
-  if ((e = cudaMalloc (&t->d_keys, t->n_slot * 8)) != cudaSuccess || (e = cudaMalloc (&t->d_vals, t->n_slot * 8)) != cudaSuccess ||
-      (e = cudaMalloc (&t->d_ont, ont_words * 4)) != cudaSuccess) {
+  if ((e = gcg_dmalloc (ctx, &t->d_keys, t->n_slot * 8)) != cudaSuccess || (e = gcg_dmalloc (ctx, &t->d_vals, t->n_slot * 8)) != cudaSuccess ||
+      (e = gcg_dmalloc (ctx, &t->d_ont, ont_words * 4)) != cudaSuccess) {
     gcg_set_error ("gcg_table_build: cudaMalloc of %llu slots failed: %s", (unsigned long long) t->n_slot, cudaGetErrorString (e));
     gcg_table_free (t);
     return GCG_ENOMEM;
@@ -762,8 +762,8 @@ extern "C" int gcg_table_dump (gcg_ctx * ctx, gcg_table * t, int64_t cap, uint64
   GCG_CUDA (cudaSetDevice (ctx->device));
   uint64_t * dk; int32_t * dm, * dt, * dp; uint8_t * dr;
   size_t c = (size_t) std::max<int64_t> (cap, 1);
-  GCG_CUDA (cudaMalloc (&dk, c * 8)); GCG_CUDA (cudaMalloc (&dm, c * 4)); GCG_CUDA (cudaMalloc (&dt, c * 4));
-  GCG_CUDA (cudaMalloc (&dp, c * 4)); GCG_CUDA (cudaMalloc (&dr, c));
+  GCG_CUDA (gcg_dmalloc (ctx, &dk, c * 8)); GCG_CUDA (gcg_dmalloc (ctx, &dm, c * 4)); GCG_CUDA (gcg_dmalloc (ctx, &dt, c * 4));
+  GCG_CUDA (gcg_dmalloc (ctx, &dp, c * 4)); GCG_CUDA (gcg_dmalloc (ctx, &dr, c));
   GCG_CUDA (cudaMemsetAsync (ctx->d_counters + 8, 0, 8, ctx->stream));
   {
     gcg_kscope ks (ctx, "table_dump");
@@ -777,7 +777,7 @@ extern "C" int gcg_table_dump (gcg_ctx * ctx, gcg_table * t, int64_t cap, uint64
   GCG_CUDA (cudaMemcpy (tid, dt, (size_t) cap * 4, cudaMemcpyDeviceToHost));
   GCG_CUDA (cudaMemcpy (pos, dp, (size_t) cap * 4, cudaMemcpyDeviceToHost));
   GCG_CUDA (cudaMemcpy (rev, dr, (size_t) cap, cudaMemcpyDeviceToHost));
-  cudaFree (dk); cudaFree (dm); cudaFree (dt); cudaFree (dp); cudaFree (dr);
+  gcg_dfree (ctx, dk); gcg_dfree (ctx, dm); gcg_dfree (ctx, dt); gcg_dfree (ctx, dp); gcg_dfree (ctx, dr);
   return GCG_OK;
 }
 
@@ -785,7 +785,7 @@ extern "C" int gcg_table_dump (gcg_ctx * ctx, gcg_table * t, int64_t cap, uint64
 extern "C" void gcg_hits_free (gcg_hits * h)
 {
   if (!h) return;
-  cudaFree (h->d_hits);
+  gcg_dfree (h->ctx, h->d_hits);
   delete h;
 }
 
@@ -812,8 +812,8 @@ extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * r
   int64_t nb = (n_words + SCAN_TILE - 1) / SCAN_TILE;
   int rc = GCG_OK;
   cudaError_t e;
-  if ((e = cudaMalloc (&d_mask, (size_t) n_words * 4)) != cudaSuccess || (e = cudaMalloc (&d_prefix, (size_t) n_words * 4)) != cudaSuccess ||
-      (e = cudaMalloc (&d_bsum, (size_t) nb * 4)) != cudaSuccess) {
+  if ((e = gcg_dmalloc (ctx, &d_mask, (size_t) n_words * 4)) != cudaSuccess || (e = gcg_dmalloc (ctx, &d_prefix, (size_t) n_words * 4)) != cudaSuccess ||
+      (e = gcg_dmalloc (ctx, &d_bsum, (size_t) nb * 4)) != cudaSuccess) {
     gcg_set_error ("gcg_search: cudaMalloc failed: %s", cudaGetErrorString (e));
     rc = GCG_ENOMEM;
   }
@@ -833,7 +833,7 @@ extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * r
     int64_t n_hit = (int64_t) ctx->h_counters[4];
     h->n = n_hit;
     if (n_hit > 0) {
-      if ((e = cudaMalloc (&h->d_hits, (size_t) n_hit * sizeof (gcg_hit))) != cudaSuccess) {
+      if ((e = gcg_dmalloc (ctx, &h->d_hits, (size_t) n_hit * sizeof (gcg_hit))) != cudaSuccess) {
         gcg_set_error ("gcg_search: cudaMalloc of %lld anchors failed: %s", (long long) n_hit, cudaGetErrorString (e));
         rc = GCG_ENOMEM;
         break;
@@ -846,7 +846,7 @@ extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * r
     }
     break;
   }
-  cudaFree (d_mask); cudaFree (d_prefix); cudaFree (d_bsum);
+  gcg_dfree (ctx, d_mask); gcg_dfree (ctx, d_prefix); gcg_dfree (ctx, d_bsum);
   if (rc) { gcg_hits_free (h); return rc; }
   *out = h;
   return GCG_OK;
@@ -952,8 +952,8 @@ extern "C" int gcg_chop_contigs (gcg_ctx * ctx, const gcg_seqs * contigs, int k,
   koff[(size_t) n] = tot;
   if (tot == 0) return GCG_OK;
   int64_t * d_koff; kmer_rec * d_rec;
-  GCG_CUDA (cudaMalloc (&d_koff, (size_t) (n + 1) * 8));
-  GCG_CUDA (cudaMalloc (&d_rec, (size_t) tot * sizeof (kmer_rec)));
+  GCG_CUDA (gcg_dmalloc (ctx, &d_koff, (size_t) (n + 1) * 8));
+  GCG_CUDA (gcg_dmalloc (ctx, &d_rec, (size_t) tot * sizeof (kmer_rec)));
   GCG_CUDA (cudaMemcpyAsync (d_koff, koff.data (), (size_t) (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
   {
     gcg_kscope ks (ctx, "chop_records");
@@ -965,6 +965,6 @@ extern "C" int gcg_chop_contigs (gcg_ctx * ctx, const gcg_seqs * contigs, int k,
   for (int64_t i = 0; i < n; ++i)
     if (n_kmer_out[i] > 0)
       GCG_CUDA (cudaMemcpy (kmers_out[i], d_rec + koff[(size_t) i], (size_t) n_kmer_out[i] * sizeof (kmer_rec), cudaMemcpyDeviceToHost));
-  cudaFree (d_koff); cudaFree (d_rec);
+  gcg_dfree (ctx, d_koff); gcg_dfree (ctx, d_rec);
   return GCG_OK;
 }

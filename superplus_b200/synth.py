@@ -134,6 +134,25 @@ def make_gap_closer_input(genome_len: int, n_gaps: int, coverage: float, seed: i
     return GapCloserInput(scaffold=scaffold, genome=genome, gaps=gaps, reads=reads)
 
 
+def make_reads(genome: np.ndarray, coverage: float, seed: int, err: float = 0.10, mean_len: float = 10_000.0) -> list:
+    """an independent batch of simulated ONT reads over `genome` (multi-GPU runs: one batch per rank)"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    genome_len = len(genome)
+    target_bases = int(coverage * genome_len)
+    reads, total = [], 0
+    while total < target_bases:
+        L = int(np.clip(rng.gamma(4.0, mean_len / 4.0), 1000, 60000))
+        L = min(L, genome_len)
+        st = int(rng.integers(0, genome_len - L + 1))
+        frag = genome[st:st + L]
+        if rng.random() < 0.5:
+            frag = revcomp(frag)
+        r = mutate(frag, err, rng)
+        reads.append(r)
+        total += len(r)
+    return reads
+
+
 def write_fasta(path: str, seq: np.ndarray, name: str = "scaffold1", width: int = 60) -> None:
     n = len(seq)
     full = n // width
