@@ -308,10 +308,17 @@ def run_ours(args, rank, local_rank, world):
         h = C.c_void_p()
         ctx._chk(ctx.L.gcg_table_build(ctx.h, C.cast(cptrs, C.c_void_p), clens.ctypes.data, len(carrs), K, C.byref(h)))
         tab = api.KmerTable(ctx, h, K)
-        hits = ctx.search_host_ptrs(tab, rptrs, rlens, len(arrs))
+        hp, nh = C.c_void_p(), C.c_int64()
+        ctx._chk(ctx.L.gcg_search(ctx.h, tab.h, C.cast(rptrs, C.c_void_p), rlens.ctypes.data, len(arrs), K, C.byref(hp), C.byref(nh)))
+        # the anchors are now in (library-owned, pinned) host memory: read the last one, release
+        if nh.value:
+            view = np.frombuffer((C.c_char * (nh.value * api.HIT_DTYPE.itemsize)).from_address(hp.value), dtype=api.HIT_DTYPE)
+            assert int(view["read"][-1]) < len(arrs)
+            del view
+        ctx.L.gcg_free(hp)
         s4 = tab.stats()
         tab.free()
-        return len(hits), s4
+        return nh.value, s4
 
     e2e_kmer()
     barrier()
@@ -324,11 +331,13 @@ def run_ours(args, rank, local_rank, world):
 
     sw_e2e_pairs = min(sw_pairs, 2960 * 2)
     qe, te = q2[:sw_e2e_pairs], t2[:sw_e2e_pairs]
-    ctx.sw_batch(P, list(qe[:64]), list(te[:64]), api.SW_ASIS)
+    e2e_sw_steps = 3
     barrier()
-    t0 = time.perf_counter()
     res_e2e, cig_e2e = None, None
-    for _ in range(2):
+    for it in range(1 + e2e_sw_steps):                 # one untimed warm-up call of the same shape
+        if it == 1:
+            barrier()
+            t0 = time.perf_counter()
         qb, qo = np.ascontiguousarray(qe).reshape(-1), np.arange(sw_e2e_pairs + 1, dtype=np.int64) * SW_QLEN
         tb, to = np.ascontiguousarray(te).reshape(-1), np.arange(sw_e2e_pairs + 1, dtype=np.int64) * SW_TLEN
         res = np.zeros(sw_e2e_pairs, dtype=api.SWRES_DTYPE)
@@ -338,7 +347,7 @@ def run_ours(args, rank, local_rank, world):
         n_ops = npool.value
         ctx.L.gcg_free(pool)
     barrier()
-    e2e_sw_s = allmax(time.perf_counter() - t0) / 2
+    e2e_sw_s = allmax(time.perf_counter() - t0) / e2e_sw_steps
 
     # ---- aggregate over ranks
     tot_ont_kmers = allsum(float(n_ont_kmers))

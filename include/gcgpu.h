@@ -61,6 +61,9 @@ int64_t gcg_launch_count (gcg_ctx * ctx);
  * bandwidth in bytes per second (read + write) */
 int  gcg_ubench_int16 (gcg_ctx * ctx, double * lane_ops_per_s);
 int  gcg_ubench_hbm (gcg_ctx * ctx, double * bytes_per_s);
+/* independent random 32-byte bucket loads per second from a table of `table_bytes` (the probe
+ * pattern of gcg_search; small tables measure the L2-resident case, large ones HBM) */
+int  gcg_ubench_gather (gcg_ctx * ctx, int64_t table_bytes, double * lookups_per_s);
 
 /* ------------------------------------------------------------------ sequences -------- */
 /* K1: ASCII -> 2 bit, base2int(b) = (b>>1)&3 (bio.h:24; kseq1.h:28-35).  Host pointers. */

@@ -24,7 +24,7 @@ KMER_DTYPE = np.dtype([("kseq", "<u8"), ("hs_id", "<i4"), ("tid", "<i4"), ("pos"
 
 EXPORTS = [
     "gcg_device_count", "gcg_init", "gcg_destroy", "gcg_last_error", "gcg_set_host_threads", "gcg_stream", "gcg_sync",
-    "gcg_prof_enable", "gcg_prof_reset", "gcg_prof_report", "gcg_launch_count", "gcg_ubench_int16", "gcg_ubench_hbm",
+    "gcg_prof_enable", "gcg_prof_reset", "gcg_prof_report", "gcg_launch_count", "gcg_ubench_int16", "gcg_ubench_hbm", "gcg_ubench_gather",
     "gcg_seqs_upload", "gcg_seqs_upload_concat", "gcg_ascii_upload_concat", "gcg_seqs_pack", "gcg_ascii_free",
     "gcg_seqs_free", "gcg_seqs_count", "gcg_seqs_bases", "gcg_seqs_kmers",
     "gcg_chop_contigs", "gcg_table_build_seqs", "gcg_table_build", "gcg_table_free", "gcg_table_stats",
@@ -98,6 +98,7 @@ def load_library(path: str = LIB_PATH):
     L.gcg_launch_count.argtypes = [vp]
     L.gcg_ubench_int16.argtypes = [vp, C.POINTER(C.c_double)]
     L.gcg_ubench_hbm.argtypes = [vp, C.POINTER(C.c_double)]
+    L.gcg_ubench_gather.argtypes = [vp, i64, C.POINTER(C.c_double)]
     L.gcg_seqs_upload.argtypes = [vp, vp, vp, i64, C.POINTER(vp)]
     L.gcg_seqs_upload_concat.argtypes = [vp, vp, vp, i64, C.POINTER(vp)]
     L.gcg_ascii_upload_concat.argtypes = [vp, vp, vp, i64, C.POINTER(vp)]
@@ -199,6 +200,11 @@ class Context:
     def ubench_hbm(self) -> float:
         v = C.c_double()
         self._chk(self.L.gcg_ubench_hbm(self.h, C.byref(v)))
+        return v.value
+
+    def ubench_gather(self, table_bytes: int) -> float:
+        v = C.c_double()
+        self._chk(self.L.gcg_ubench_gather(self.h, int(table_bytes), C.byref(v)))
         return v.value
 
     # ---- sequences -----------------------------------------------------------------------

@@ -1,7 +1,12 @@
 // Context, error reporting, per-kernel CUDA-event profiling, pinned staging ring.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <chrono>
+#include <mutex>
+#include <thread>
 
 #include "gcg_internal.cuh"
 
@@ -45,6 +50,7 @@ extern "C" int gcg_init (int device, gcg_ctx ** out)
   gcg_ctx * ctx = new gcg_ctx ();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->trace = getenv ("GCG_TRACE") != nullptr;
   GCG_CUDA (cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking));
   {
     // keep freed blocks in the stream-ordered pool instead of returning them to the driver
@@ -74,6 +80,7 @@ extern "C" void gcg_destroy (gcg_ctx * ctx)
   cudaFree (ctx->d_counters);
   cudaFreeHost (ctx->h_counters);
   cudaStreamDestroy (ctx->stream);
+  gcg_pinned_trim ();
   delete ctx;
 }
 
@@ -156,7 +163,74 @@ int gcg_stage_reserve (gcg_ctx * ctx)
   return GCG_OK;
 }
 
+// ---- pinned result buffers ---------------------------------------------------------------------
+// Results handed to the caller (anchor lists, CIGAR pools) live in page-locked host memory.
+// Pinning costs far more than the copy it serves (tens of ms per 100 MB), so blocks released with
+// gcg_free are parked and handed out again by the next call that fits; gcg_destroy returns the
+// parked blocks to the driver.
+struct pinned_block { void * p; size_t cap; bool in_use; };
+static std::mutex g_pin_mu;
+static std::vector<pinned_block> g_pin;
+
+void * gcg_pinned_alloc (size_t bytes)
+{
+  if (bytes == 0) bytes = 16;
+  std::lock_guard<std::mutex> lk (g_pin_mu);
+  int best = -1;
+  for (size_t i = 0; i < g_pin.size (); ++i)
+    if (!g_pin[i].in_use && g_pin[i].cap >= bytes && (best < 0 || g_pin[i].cap < g_pin[(size_t) best].cap)) best = (int) i;
+  if (best >= 0) { g_pin[(size_t) best].in_use = true; return g_pin[(size_t) best].p; }
+  // nothing parked fits: drop the parked blocks (bounds what the cache holds), allocate with headroom
+  for (size_t i = 0; i < g_pin.size ();) {
+    if (!g_pin[i].in_use) { cudaFreeHost (g_pin[i].p); g_pin.erase (g_pin.begin () + (long) i); } else ++i;
+  }
+  size_t cap = bytes + bytes / 8;
+  void * p = nullptr;
+  if (cudaHostAlloc (&p, cap, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError ();
+    cap = bytes;
+    if (cudaHostAlloc (&p, cap, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError (); return nullptr; }
+  }
+  g_pin.push_back ({p, cap, true});
+  return p;
+}
+
+void gcg_pinned_trim (void)
+{
+  std::lock_guard<std::mutex> lk (g_pin_mu);
+  for (size_t i = 0; i < g_pin.size ();) {
+    if (!g_pin[i].in_use) { cudaFreeHost (g_pin[i].p); g_pin.erase (g_pin.begin () + (long) i); } else ++i;
+  }
+}
+
 extern "C" void gcg_free (void * p)
 {
-  if (p) cudaFreeHost (p);
+  if (!p) return;
+  std::lock_guard<std::mutex> lk (g_pin_mu);
+  for (auto & b : g_pin)
+    if (b.p == p) { b.in_use = false; return; }
+  cudaFreeHost (p);
+}
+
+// ---- host-side phase trace (GCG_TRACE=1): wall-clock between marks, printed to stderr -----------
+static std::chrono::steady_clock::time_point g_trace_t0;
+void gcg_trace_mark (gcg_ctx * ctx, const char * label)
+{
+  if (!ctx || !ctx->trace) return;
+  auto now = std::chrono::steady_clock::now ();
+  if (label) fprintf (stderr, "[gcg] %-28s %9.3f ms\n", label, std::chrono::duration<double, std::milli> (now - g_trace_t0).count ());
+  g_trace_t0 = now;
+}
+
+void gcg_par_memcpy (gcg_ctx * ctx, void * dst, const void * src, size_t bytes)
+{
+  int nt = ctx ? ctx->host_threads : 1;
+  if (bytes < ((size_t) 4 << 20) || nt <= 1) { memcpy (dst, src, bytes); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; ++t) {
+    size_t a = bytes * (size_t) t / (size_t) nt, b = bytes * (size_t) (t + 1) / (size_t) nt;
+    a &= ~(size_t) 63; if (t + 1 < nt) b &= ~(size_t) 63;
+    th.emplace_back ([=] () { memcpy ((char *) dst + a, (const char *) src + a, b - a); });
+  }
+  for (auto & t : th) t.join ();
 }

@@ -49,6 +49,7 @@ struct gcg_ctx {
   int host_threads = 4;
   cudaStream_t stream = nullptr;
   bool prof = false;
+  bool trace = false;                 // GCG_TRACE: print host-side phase times
   std::map<std::string, gcg_prof_entry> prof_map;
   int64_t launches = 0;
   gcg_stage stage;
@@ -104,14 +105,17 @@ struct gcg_seqs {
   uint64_t * d_packed = nullptr;            // n_words + 2 (slack, zero)
   int64_t * d_woff = nullptr;               // n + 1
   int32_t * d_len = nullptr;                // n
+  int32_t * d_tseq = nullptr;               // per 32-word tile: index of the sequence holding its first word
   std::vector<int64_t> h_woff;
   std::vector<int32_t> h_len;
 };
 
 // ---- contig k-mer table ---------------------------------------------------------------------
 // Open addressing, 32-byte buckets of four 8-byte key words (one DRAM sector per probe).
-//   key word: bits 0..61 = canonical k-mer + 1 (0 = empty), bit 62 = bucket overflowed
-//   (only meaningful on slot 0 of a bucket), bit 63 = seen more than once.
+//   key word: bits 0..61 = canonical k-mer + 1 (0 = empty), bit 63 = seen more than once,
+//   bit 62 of slot f of a bucket = some key with fingerprint f (= hash & 3) did not fit into this
+//   bucket and went on to the next one (a 4-bit filter: an absent key continues its probe
+//   sequence only when a key of its own fingerprint overflowed here).
 //   vals[slot]: bit 0 = KMER_REV, bits 1..31 = contig position, bits 32..62 = contig index.
 //   ont[slot/16]: 2 bits per slot, bit0 = anchored >= once, bit1 = anchored >= twice.
 struct gcg_table {
@@ -136,6 +140,10 @@ struct gcg_hits {
 #define GCG_KEY_MULTI 0x8000000000000000ULL
 
 int gcg_stage_reserve (gcg_ctx * ctx);
+void * gcg_pinned_alloc (size_t bytes);      // parked-block cache, released with gcg_free
+void gcg_pinned_trim (void);
+void gcg_trace_mark (gcg_ctx * ctx, const char * label);   // label == NULL restarts the clock
+void gcg_par_memcpy (gcg_ctx * ctx, void * dst, const void * src, size_t bytes);   // memcpy over the ctx's host threads
 
 // stream-ordered device allocations from the context's pool: no device synchronisation, freed
 // blocks are reused by the next call (the pool never trims, see gcg_init)

@@ -59,6 +59,23 @@ __device__ __forceinline__ int64_t find_seq (const int64_t * __restrict__ woff, 
   return lo;
 }
 
+// same, starting from a hint h <= answer (the sequence of the first word of the 32-word tile, built
+// on the host): reads are hundreds of words long, so this is almost always zero or one step
+__device__ __forceinline__ int64_t find_seq_from (const int64_t * __restrict__ woff, int64_t n, int64_t w, int64_t h)
+{
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+    if (h + 1 >= n || __ldg (woff + h + 1) > w) return h;
+    ++h;
+  }
+  int64_t lo = h, hi = n;            // many short or empty sequences inside one tile: finish by bisection
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (__ldg (woff + mid) <= w) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 // Per-lane rolling state over the 32 k-mer start positions of one packed word.
 struct kroll {
   uint64_t fwd, rc, nxt, mask;
@@ -118,7 +135,8 @@ k23_build_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
       bool fw = r.fwd < r.rc;
       unsigned long long key = (fw ? r.fwd : r.rc) + 1ULL;
       unsigned long long val = ((unsigned long long) s << 32) | ((unsigned long long) (uint32_t) (p0 + j) << 1) | (fw ? 0ULL : 1ULL);
-      uint32_t b = __umulhi (kmer_hash32 (key - 1ULL), n_bucket);
+      const uint32_t hsh = kmer_hash32 (key - 1ULL), fp = hsh & 3u;
+      uint32_t b = __umulhi (hsh, n_bucket);
       for (;;) {
         unsigned long long * slot = keys + 4ULL * b;
         bool done = false;
@@ -136,8 +154,8 @@ k23_build_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
           }
         }
         if (done) break;
-        // bucket is full of other keys: flag the overflow on slot 0 and move on
-        if (!(__ldcg (slot) & GCG_KEY_OVF)) atomicOr (slot, GCG_KEY_OVF);
+        // bucket is full of other keys: leave the key's overflow mark (bit 62 of slot `fp`) and move on
+        if (!(__ldcg (slot + fp) & GCG_KEY_OVF)) atomicOr (slot + fp, GCG_KEY_OVF);
         b = (b + 1 == n_bucket) ? 0 : b + 1;
       }
     }
@@ -145,13 +163,18 @@ k23_build_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
 }
 
 // =============================================================================================
-// K4+K5  ONT chop + lookup + multi==1 filter + ONT-side multiplicity
-//   One thread per packed word (32 k-mer start positions).  Each probe is ONE 256-bit load of a
-//   32-byte bucket (LDG.E.256: one L1 wavefront and one L2/DRAM sector per lookup).  Probes are
-//   issued four at a time so every thread keeps four sectors in flight.  The kernel only records
-//   a 32-bit anchor mask per word (plain coalesced store) and the ONT multiplicity state; the
-//   anchors themselves are emitted in (read,pos) order by hits_emit_kernel after a prefix sum
-//   over the masks, which re-probes just the anchored positions (a few percent).
+// K4+K5  ONT chop + lookup + multi==1 filter
+//   One thread per packed word (32 k-mer start positions), one warp per tile of 32 words.  Each
+//   probe is ONE 256-bit load of a 32-byte bucket (LDG.E.256: one L1 wavefront and one L2/DRAM
+//   sector per lookup), issued four at a time so every thread keeps four sectors in flight.  The
+//   main loop is branch-free per probe: "present with multiplicity 1" is one masked 64-bit compare
+//   per slot, and the few probes whose key may have overflowed into a later bucket (bit 62 of slot
+//   `hash & 3` is set and the home bucket did not match) are only noted in a second mask; they are
+//   finished after the loop, dealt round-robin over the warp's lanes, so no lane waits on another
+//   lane's dependent load inside the hot loop.  The kernel writes a 32-bit anchor mask per word
+//   (plain coalesced store); the anchors themselves, and the ONT-side multiplicity (ont.c:245), are
+//   produced by hits_emit_kernel after a prefix sum over the masks, which re-probes just the
+//   anchored positions (a few percent).
 // =============================================================================================
 struct __align__ (32) bucket4 { unsigned long long a, b, c, d; };
 
@@ -173,66 +196,120 @@ __device__ __forceinline__ int bucket_find (const bucket4 & q, unsigned long lon
   return -1;
 }
 
-// full probe sequence starting from an already loaded home bucket; returns slot index or ~0
+// has a key with fingerprint fp (hash & 3) ever been pushed out of this bucket?
+__device__ __forceinline__ bool bucket_ovf (const bucket4 & q, uint32_t fp)
+{
+  uint32_t h0 = (uint32_t) (q.a >> 32), h1 = (uint32_t) (q.b >> 32), h2 = (uint32_t) (q.c >> 32), h3 = (uint32_t) (q.d >> 32);
+  uint32_t h = (fp & 2u) ? ((fp & 1u) ? h3 : h2) : ((fp & 1u) ? h1 : h0);
+  return (h & 0x40000000u) != 0;
+}
+
+// key present with multiplicity 1 in this bucket (key has bits 62/63 clear, so one compare does both)
+__device__ __forceinline__ bool bucket_has_unique (const bucket4 & q, unsigned long long key)
+{
+  return ((q.a & ~GCG_KEY_OVF) == key) | ((q.b & ~GCG_KEY_OVF) == key) | ((q.c & ~GCG_KEY_OVF) == key) | ((q.d & ~GCG_KEY_OVF) == key);
+}
+
+// full probe sequence starting from an already loaded bucket; returns slot index or ~0
 __device__ __forceinline__ unsigned long long table_lookup (const unsigned long long * __restrict__ keys, uint32_t n_bucket,
-                                                           uint32_t b, bucket4 q, unsigned long long key, unsigned long long * kw)
+                                                           uint32_t b, bucket4 q, unsigned long long key, uint32_t fp, unsigned long long * kw)
 {
   for (;;) {
     int f = bucket_find (q, key, kw);
     if (f >= 0) return 4ULL * b + f;
-    if (!(q.a & GCG_KEY_OVF)) return ~0ULL;          // bucket never overflowed: key absent
+    if (!bucket_ovf (q, fp)) return ~0ULL;           // no key of this fingerprint ever left the bucket: absent
     b = (b + 1 == n_bucket) ? 0 : b + 1;
     q = ld_bucket (keys + 4ULL * b);
   }
 }
 
-#define K4_UNROLL 4
-
-__global__ void __launch_bounds__ (256)
-k45_search_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff,
-                   const int32_t * __restrict__ len, int64_t n_seq, int64_t n_words, int k,
-                   const unsigned long long * __restrict__ keys, uint32_t * __restrict__ ont, uint32_t n_bucket,
-                   uint32_t * __restrict__ hitmask)
+// canonical key (+1) of the k-mer starting at bit offset 2j of the 128-bit window (wh, wl)
+__device__ __forceinline__ unsigned long long key_at (uint64_t wh, uint64_t wl, int j, int k, bool * fw)
 {
-  int64_t stride = (int64_t) gridDim.x * blockDim.x;
-  for (int64_t w = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
-    int64_t s = find_seq (woff, n_seq, w);
-    int32_t L = __ldg (len + s);
-    int32_t p0 = (int32_t) ((w - __ldg (woff + s)) << 5);
-    int nvalid = L - k + 1 - p0;
-    nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
-    uint32_t mymask = 0;
+  uint64_t xw = j ? ((wh << (2 * j)) | (wl >> (64 - 2 * j))) : wh;
+  uint64_t fwd = xw >> (64 - 2 * k), rc = revcomp64 (fwd, k);
+  *fw = fwd < rc;
+  return (*fw ? fwd : rc) + 1ULL;
+}
+
+#define K4_UNROLL 4
+#define K4_WARPS 8
+
+__global__ void __launch_bounds__ (32 * K4_WARPS)
+k45_search_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff,
+                   const int32_t * __restrict__ len, const int32_t * __restrict__ tile_seq, int64_t n_seq, int64_t n_words, int k,
+                   const unsigned long long * __restrict__ keys, uint32_t n_bucket, uint32_t * __restrict__ hitmask)
+{
+  __shared__ uint32_t s_excl[K4_WARPS][33];
+  __shared__ uint32_t s_pend[K4_WARPS][32];
+  __shared__ uint32_t s_add[K4_WARPS][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t n_tiles = (n_words + 31) >> 5;
+  const int64_t wstride = (int64_t) gridDim.x * K4_WARPS;
+  for (int64_t tile = (int64_t) blockIdx.x * K4_WARPS + wid; tile < n_tiles; tile += wstride) {
+    const int64_t w = (tile << 5) + lane;
+    uint32_t mymask = 0, pend = 0;
+    int nvalid = 0;
+    if (w < n_words) {
+      int64_t s = find_seq_from (woff, n_seq, w, __ldg (tile_seq + tile));
+      int32_t L = __ldg (len + s);
+      int32_t p0 = (int32_t) ((w - __ldg (woff + s)) << 5);
+      nvalid = L - k + 1 - p0;
+      nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
+    }
     if (nvalid) {
       kroll r;
       r.init (__ldg (packed + w), __ldg (packed + w + 1), k);
       for (int j0 = 0; j0 < nvalid; j0 += K4_UNROLL) {
         unsigned long long key[K4_UNROLL];
-        uint32_t bk[K4_UNROLL];
+        uint32_t fp[K4_UNROLL];
         bucket4 q[K4_UNROLL];
 #pragma unroll
         for (int u = 0; u < K4_UNROLL; ++u) {
           if (j0 + u) r.step ();                     // harmless past nvalid: state is discarded
           key[u] = (r.fwd < r.rc ? r.fwd : r.rc) + 1ULL;
-          bk[u] = __umulhi (kmer_hash32 (key[u] - 1ULL), n_bucket);
-          q[u] = ld_bucket (keys + 4ULL * bk[u]);
+          uint32_t h = kmer_hash32 (key[u] - 1ULL);
+          fp[u] = h & 3u;
+          q[u] = ld_bucket (keys + 4ULL * __umulhi (h, n_bucket));
         }
 #pragma unroll
         for (int u = 0; u < K4_UNROLL; ++u) {
-          if (j0 + u < nvalid) {
-            unsigned long long kw;
-            unsigned long long slot = table_lookup (keys, n_bucket, bk[u], q[u], key[u], &kw);
-            if (slot != ~0ULL && !(kw & GCG_KEY_MULTI)) {      // multi == 1  (ont.c:171,195)
-              mymask |= 1u << (j0 + u);
-              // ONT-side multiplicity state (ont.c:245): 2 bits per slot
-              uint32_t sh = (uint32_t) (slot & 15) * 2;
-              uint32_t old = atomicOr (ont + (slot >> 4), 1u << sh);
-              if (((old >> sh) & 3u) == 1u) atomicOr (ont + (slot >> 4), 2u << sh);
-            }
-          }
+          const bool valid = j0 + u < nvalid;
+          const bool hit = bucket_has_unique (q[u], key[u]);        // multi == 1  (ont.c:171,195)
+          const bool more = !hit && bucket_ovf (q[u], fp[u]);
+          mymask |= (uint32_t) (valid && hit) << (j0 + u);
+          pend |= (uint32_t) (valid && more) << (j0 + u);
         }
       }
     }
-    hitmask[w] = mymask;
+    // ---- the rare probes that have to look at later buckets, dealt round-robin over the lanes
+    uint32_t c = __popc (pend), x = c;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (0xffffffffu, x, o); if (lane >= o) x += y; }
+    const uint32_t total = __shfl_sync (0xffffffffu, x, 31);
+    if (total) {
+      __syncwarp ();
+      s_excl[wid][lane] = x - c;
+      s_pend[wid][lane] = pend;
+      s_add[wid][lane] = 0;
+      if (lane == 31) s_excl[wid][32] = total;
+      __syncwarp ();
+      for (uint32_t h = lane; h < total; h += 32) {
+        int lo = 0, hi = 32;                          // s_excl[lo] <= h < s_excl[hi]
+#pragma unroll
+        for (int it = 0; it < 5; ++it) { int mid = (lo + hi) >> 1; if (s_excl[wid][mid] <= h) lo = mid; else hi = mid; }
+        const int j = __fns (s_pend[wid][lo], 0, (int) (h - s_excl[wid][lo]) + 1);
+        const int64_t ww = (tile << 5) + lo;
+        bool fw;
+        unsigned long long kw, key = key_at (__ldg (packed + ww), __ldg (packed + ww + 1), j, k, &fw);
+        uint32_t hs = kmer_hash32 (key - 1ULL), b = __umulhi (hs, n_bucket);
+        b = (b + 1 == n_bucket) ? 0 : b + 1;          // the home bucket has been looked at
+        unsigned long long slot = table_lookup (keys, n_bucket, b, ld_bucket (keys + 4ULL * b), key, hs & 3u, &kw);
+        if (slot != ~0ULL && !(kw & GCG_KEY_MULTI)) atomicOr (&s_add[wid][lo], 1u << j);
+      }
+      __syncwarp ();
+      mymask |= s_add[wid][lane];
+    }
+    if (w < n_words) hitmask[w] = mymask;
   }
 }
 
@@ -319,9 +396,9 @@ scan_apply_kernel (const uint32_t * __restrict__ mask, int64_t n, const uint32_t
 // are dealt round-robin to the lanes (balanced, independent loads, coalesced output).  Only the
 // anchored positions (a few percent) are re-probed here to fetch (tid,pos,flag).
 __global__ void __launch_bounds__ (256)
-hits_emit_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff, int64_t n_seq,
-                  int64_t n_words, int k, const unsigned long long * __restrict__ keys,
-                  const unsigned long long * __restrict__ vals, uint32_t n_bucket,
+hits_emit_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff, const int32_t * __restrict__ tile_seq,
+                  int64_t n_seq, int64_t n_words, int k, const unsigned long long * __restrict__ keys,
+                  const unsigned long long * __restrict__ vals, uint32_t * __restrict__ ont, uint32_t n_bucket,
                   const uint32_t * __restrict__ mask, const uint32_t * __restrict__ prefix, gcg_hit * __restrict__ out)
 {
   __shared__ uint32_t s_excl[8][33];
@@ -337,6 +414,7 @@ hits_emit_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
     uint32_t total = __shfl_sync (0xffffffffu, x, 31);
     if (total == 0) continue;
     uint32_t base = prefix[tile << 5];
+    const int64_t s_hint = __ldg (tile_seq + tile);
     __syncwarp ();
     s_excl[wid][lane] = x - c;
     s_mask[wid][lane] = m;
@@ -349,16 +427,19 @@ hits_emit_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
       uint32_t mm = s_mask[wid][lo];
       int j = __fns (mm, 0, (int) (h - s_excl[wid][lo]) + 1);
       int64_t ww = (tile << 5) + lo;
-      int64_t s = find_seq (woff, n_seq, ww);
+      int64_t s = find_seq_from (woff, n_seq, ww, s_hint);
       int32_t p0 = (int32_t) ((ww - __ldg (woff + s)) << 5);
-      uint64_t wh = __ldg (packed + ww), wl = __ldg (packed + ww + 1);
-      uint64_t xw = j ? ((wh << (2 * j)) | (wl >> (64 - 2 * j))) : wh;
-      uint64_t fwd = xw >> (64 - 2 * k), rc = revcomp64 (fwd, k);
-      bool fw = fwd < rc;
-      unsigned long long key = (fw ? fwd : rc) + 1ULL, kw;
-      uint32_t b = __umulhi (kmer_hash32 (key - 1ULL), n_bucket);
-      unsigned long long slot = table_lookup (keys, n_bucket, b, ld_bucket (keys + 4ULL * b), key, &kw);
+      bool fw;
+      unsigned long long kw, key = key_at (__ldg (packed + ww), __ldg (packed + ww + 1), j, k, &fw);
+      uint32_t hs = kmer_hash32 (key - 1ULL), b = __umulhi (hs, n_bucket);
+      unsigned long long slot = table_lookup (keys, n_bucket, b, ld_bucket (keys + 4ULL * b), key, hs & 3u, &kw);
       unsigned long long v = __ldg (vals + slot);   // slot is valid: the mask bit says the key is present
+      {
+        // ONT-side multiplicity state (ont.c:245): 2 bits per slot, saturating at "twice or more"
+        uint32_t sh = (uint32_t) (slot & 15) * 2;
+        uint32_t old = atomicOr (ont + (slot >> 4), 1u << sh);
+        if (((old >> sh) & 3u) == 1u) atomicOr (ont + (slot >> 4), 2u << sh);
+      }
       int4 hh;                                      // gcg_hit {read, pos, tid, cpos_flags} as one 16-byte store
       hh.x = (int32_t) s;
       hh.y = p0 + j;
@@ -580,6 +661,17 @@ static int seqs_alloc (gcg_ctx * ctx, gcg_seqs * s)
   GCG_CUDA (gcg_dmalloc (ctx, &s->d_len, (size_t) std::max<int64_t> (s->n, 1) * 4));
   GCG_CUDA (cudaMemcpyAsync (s->d_woff, s->h_woff.data (), (size_t) (s->n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
   if (s->n) GCG_CUDA (cudaMemcpyAsync (s->d_len, s->h_len.data (), (size_t) s->n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  // tile -> sequence hints (largest s with woff[s] <= 32*tile)
+  const int64_t n_tiles = (s->n_words + 31) >> 5;
+  std::vector<int32_t> tseq ((size_t) std::max<int64_t> (n_tiles, 1), 0);
+  int64_t cur = 0;
+  for (int64_t t = 0; t < n_tiles; ++t) {
+    while (cur + 1 < s->n && s->h_woff[(size_t) cur + 1] <= (t << 5)) ++cur;
+    tseq[(size_t) t] = (int32_t) cur;
+  }
+  GCG_CUDA (gcg_dmalloc (ctx, &s->d_tseq, tseq.size () * 4));
+  // (pageable source: the copy is staged by the runtime before the call returns)
+  GCG_CUDA (cudaMemcpyAsync (s->d_tseq, tseq.data (), tseq.size () * 4, cudaMemcpyHostToDevice, ctx->stream));
   return GCG_OK;
 }
 
@@ -661,7 +753,7 @@ extern "C" void gcg_ascii_free (gcg_ascii * a)
 extern "C" void gcg_seqs_free (gcg_seqs * s)
 {
   if (!s) return;
-  gcg_dfree (s->ctx, s->d_packed); gcg_dfree (s->ctx, s->d_woff); gcg_dfree (s->ctx, s->d_len);
+  gcg_dfree (s->ctx, s->d_packed); gcg_dfree (s->ctx, s->d_woff); gcg_dfree (s->ctx, s->d_len); gcg_dfree (s->ctx, s->d_tseq);
   delete s;
 }
 
@@ -819,8 +911,8 @@ extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * r
   }
   while (!rc) {
     { gcg_kscope ks (ctx, "k45_search");
-      k45_search_kernel<<<grid_for (ctx, n_words, 256, 8), 256, 0, ctx->stream>>> (
-          reads->d_packed, reads->d_woff, reads->d_len, reads->n, n_words, k, t->d_keys, t->d_ont, t->n_bucket, d_mask); }
+      k45_search_kernel<<<grid_for (ctx, ((n_words + 31) >> 5) * 32, 32 * K4_WARPS, 8), 32 * K4_WARPS, 0, ctx->stream>>> (
+          reads->d_packed, reads->d_woff, reads->d_len, reads->d_tseq, reads->n, n_words, k, t->d_keys, t->n_bucket, d_mask); }
     { gcg_kscope ks (ctx, "scan_reduce");
       scan_reduce_kernel<<<(unsigned) nb, SCAN_BLOCK, 0, ctx->stream>>> (d_mask, n_words, d_bsum); }
     { gcg_kscope ks (ctx, "scan_blocksums");
@@ -840,7 +932,7 @@ extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * r
       }
       { gcg_kscope ks (ctx, "hits_emit");
         hits_emit_kernel<<<grid_for (ctx, ((n_words + 31) >> 5) * 32, 256, 8), 256, 0, ctx->stream>>> (
-            reads->d_packed, reads->d_woff, reads->n, n_words, k, t->d_keys, t->d_vals, t->n_bucket, d_mask, d_prefix, h->d_hits); }
+            reads->d_packed, reads->d_woff, reads->d_tseq, reads->n, n_words, k, t->d_keys, t->d_vals, t->d_ont, t->n_bucket, d_mask, d_prefix, h->d_hits); }
       if (cudaGetLastError () != cudaSuccess || cudaStreamSynchronize (ctx->stream) != cudaSuccess) {
         gcg_set_error ("gcg_search: emit failed: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; }
     }
@@ -890,16 +982,20 @@ extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * re
   for (auto & g : groups) {
     gcg_seqs * s = nullptr;
     gcg_hits * h = nullptr;
+    gcg_trace_mark (ctx, nullptr);
     rc = gcg_seqs_upload (ctx, read_seq + g.first, read_len + g.first, g.second - g.first, &s);
+    gcg_trace_mark (ctx, "search: reads to HBM + pack");
     if (!rc) rc = gcg_search_seqs (ctx, t, s, k, &h);
+    gcg_trace_mark (ctx, "search: probe + emit");
     gcg_seqs_free (s);
     if (rc) break;
     parts.push_back (h);
     total += h->n;
   }
   if (!rc && total > 0) {
-    cudaError_t e = cudaHostAlloc ((void **) hits_out, (size_t) total * sizeof (gcg_hit), cudaHostAllocDefault);
-    if (e != cudaSuccess) { gcg_set_error ("gcg_search: pinned alloc of %lld anchors failed: %s", (long long) total, cudaGetErrorString (e)); rc = GCG_ENOMEM; }
+    *hits_out = (gcg_hit *) gcg_pinned_alloc ((size_t) total * sizeof (gcg_hit));
+    if (!*hits_out) { gcg_set_error ("gcg_search: pinned alloc of %lld anchors failed", (long long) total); rc = GCG_ENOMEM; }
+    gcg_trace_mark (ctx, "search: pinned result");
     int64_t at = 0;
     for (size_t gi = 0; gi < parts.size () && !rc; ++gi) {
       rc = gcg_hits_download (ctx, parts[gi], *hits_out + at, parts[gi]->n);
@@ -909,7 +1005,8 @@ extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * re
       }
       at += parts[gi]->n;
     }
-    if (rc) { cudaFreeHost (*hits_out); *hits_out = nullptr; }
+    if (rc) { gcg_free (*hits_out); *hits_out = nullptr; }
+    gcg_trace_mark (ctx, "search: anchors to host");
   }
   for (gcg_hits * h : parts) gcg_hits_free (h);
   if (!rc) *n_hit = total;

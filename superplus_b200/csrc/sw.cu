@@ -490,19 +490,21 @@ sw_maxsym_kernel (const uint8_t * __restrict__ qry, const long long * __restrict
 // =============================================================================================
 // device scratch that survives between align calls on the same batch (cudaMalloc of tens of GB of
 // trace is far more expensive than the kernels that fill it)
+// (all of it comes from the context's stream-ordered pool, which never trims: a batch that is
+// freed hands its trace buffer to the next batch without a trip to the driver)
 struct sw_devbuf {
   void * p = nullptr;
   size_t cap = 0;
-  cudaError_t reserve (size_t bytes)
+  cudaError_t reserve (gcg_ctx * ctx, size_t bytes)
   {
     if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree (p);
+    gcg_dfree (ctx, p);
     p = nullptr; cap = 0;
-    cudaError_t e = cudaMalloc (&p, bytes);
+    cudaError_t e = gcg_dmalloc (ctx, &p, bytes);
     if (e == cudaSuccess) cap = bytes;
     return e;
   }
-  void release () { if (p) cudaFree (p); p = nullptr; cap = 0; }
+  void release (gcg_ctx * ctx) { gcg_dfree (ctx, p); p = nullptr; cap = 0; }
 };
 
 struct gcg_swbatch {
@@ -527,10 +529,11 @@ struct gcg_swbatch {
 extern "C" void gcg_swbatch_free (gcg_swbatch * b)
 {
   if (!b) return;
-  cudaFree (b->d_qry); cudaFree (b->d_tgt); cudaFree (b->d_qoff); cudaFree (b->d_toff); cudaFree (b->d_maxsym);
-  cudaFree (b->d_results); cudaFree (b->d_ends); cudaFree (b->d_pool);
-  b->s_trace.release (); b->s_edges.release (); b->s_tasks.release (); b->s_wave_tasks.release ();
-  b->s_items.release (); b->s_counter.release (); b->s_bound.release (); b->s_pbound.release ();
+  gcg_ctx * ctx = b->ctx;
+  gcg_dfree (ctx, b->d_qry); gcg_dfree (ctx, b->d_tgt); gcg_dfree (ctx, b->d_qoff); gcg_dfree (ctx, b->d_toff); gcg_dfree (ctx, b->d_maxsym);
+  gcg_dfree (ctx, b->d_results); gcg_dfree (ctx, b->d_ends); gcg_dfree (ctx, b->d_pool);
+  b->s_trace.release (ctx); b->s_edges.release (ctx); b->s_tasks.release (ctx); b->s_wave_tasks.release (ctx);
+  b->s_items.release (ctx); b->s_counter.release (ctx); b->s_bound.release (ctx); b->s_pbound.release (ctx);
   delete b;
 }
 
@@ -554,7 +557,7 @@ static int h2d_chunked (gcg_ctx * ctx, void * dst, const void * src, size_t byte
     ctx->stage.next ^= 1;
     size_t nb = std::min (ctx->stage.cap, bytes - off);
     if (ctx->stage.busy[slot]) { GCG_CUDA (cudaEventSynchronize (ctx->stage.ev[slot])); ctx->stage.busy[slot] = false; }
-    memcpy (ctx->stage.h[slot], (const char *) src + off, nb);
+    gcg_par_memcpy (ctx, ctx->stage.h[slot], (const char *) src + off, nb);
     GCG_CUDA (cudaMemcpyAsync ((char *) dst + off, ctx->stage.h[slot], nb, cudaMemcpyHostToDevice, ctx->stream));
     GCG_CUDA (cudaEventRecord (ctx->stage.ev[slot], ctx->stream));
     ctx->stage.busy[slot] = true;
@@ -584,11 +587,11 @@ extern "C" int gcg_swbatch_upload (gcg_ctx * ctx, const char * qry, const int64_
   size_t qb = (size_t) qoff[n], tb = (size_t) toff[n];
   int rc = GCG_OK;
   cudaError_t e;
-  if ((e = cudaMalloc (&b->d_qry, std::max<size_t> (qb, 16))) != cudaSuccess || (e = cudaMalloc (&b->d_tgt, std::max<size_t> (tb, 16))) != cudaSuccess ||
-      (e = cudaMalloc (&b->d_qoff, (size_t) (n + 1) * 8)) != cudaSuccess || (e = cudaMalloc (&b->d_toff, (size_t) (n + 1) * 8)) != cudaSuccess ||
-      (e = cudaMalloc (&b->d_maxsym, (size_t) std::max<int64_t> (n, 1) * 4)) != cudaSuccess ||
-      (e = cudaMalloc (&b->d_results, (size_t) std::max<int64_t> (n, 1) * sizeof (gcg_sw_result))) != cudaSuccess ||
-      (e = cudaMalloc (&b->d_ends, (size_t) std::max<int64_t> (n, 1) * sizeof (sw_end))) != cudaSuccess) {
+  if ((e = gcg_dmalloc (ctx, &b->d_qry, std::max<size_t> (qb, 16))) != cudaSuccess || (e = gcg_dmalloc (ctx, &b->d_tgt, std::max<size_t> (tb, 16))) != cudaSuccess ||
+      (e = gcg_dmalloc (ctx, &b->d_qoff, (size_t) (n + 1) * 8)) != cudaSuccess || (e = gcg_dmalloc (ctx, &b->d_toff, (size_t) (n + 1) * 8)) != cudaSuccess ||
+      (e = gcg_dmalloc (ctx, &b->d_maxsym, (size_t) std::max<int64_t> (n, 1) * 4)) != cudaSuccess ||
+      (e = gcg_dmalloc (ctx, &b->d_results, (size_t) std::max<int64_t> (n, 1) * sizeof (gcg_sw_result))) != cudaSuccess ||
+      (e = gcg_dmalloc (ctx, &b->d_ends, (size_t) std::max<int64_t> (n, 1) * sizeof (sw_end))) != cudaSuccess) {
     gcg_set_error ("gcg_swbatch_upload: cudaMalloc failed: %s", cudaGetErrorString (e));
     gcg_swbatch_free (b);
     return GCG_ENOMEM;
@@ -694,6 +697,7 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
   }
   GCG_CUDA (cudaMemcpyToSymbolAsync (c_sw, &hc, sizeof hc, 0, cudaMemcpyHostToDevice, ctx->stream));
 
+  gcg_trace_mark (ctx, "sw.align: constants");
   // ---- classify
   std::vector<int> packed_ids, generic_ids;
   std::vector<sw_task> tasks ((size_t) n);
@@ -718,9 +722,20 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
   b->n_packed = (int64_t) packed_ids.size ();
   b->n_generic = (int64_t) generic_ids.size ();
 
+  gcg_trace_mark (ctx, "sw.align: classify");
   // ---- memory plan: trace + edge buffers for one wave
   size_t free_b = 0, total_b = 0;
   GCG_CUDA (cudaMemGetInfo (&free_b, &total_b));
+  {
+    // memory parked in the stream-ordered pool is as good as free: the next allocation reuses it
+    cudaMemPool_t pool;
+    unsigned long long reserved = 0, used = 0;
+    if (cudaDeviceGetDefaultMemPool (&pool, ctx->device) == cudaSuccess &&
+        cudaMemPoolGetAttribute (pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute (pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+      free_b += (size_t) (reserved - used);
+    free_b += b->s_trace.cap;              // this batch's own trace buffer is reused or replaced
+  }
   unsigned long long budget_words = (unsigned long long) (std::min<size_t> (free_b / 2, (size_t) 64 << 30) / 4);
   if (const char * e = getenv ("GCG_SW_TRACE_BUDGET_MB")) budget_words = (unsigned long long) atoll (e) * (1 << 20) / 4;
   auto trace_words = [] (const sw_task & t) -> unsigned long long {
@@ -756,13 +771,13 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
   // (the memory it occupies is no longer "free", so the budget above shrinks on later calls)
   if (b->s_trace.cap / 4 >= std::max<unsigned long long> (2 * max_single, 32))
     trace_cap = std::min<unsigned long long> (std::max<unsigned long long> (total_trace, 32), b->s_trace.cap / 4);
-  if ((ce = b->s_trace.reserve ((size_t) trace_cap * 4)) != cudaSuccess ||
-      (ce = b->s_edges.reserve ((size_t) std::max<long long> (total_edges, 1) * 4)) != cudaSuccess ||
-      (ce = b->s_tasks.reserve ((size_t) n * sizeof (sw_task))) != cudaSuccess ||
-      (ce = b->s_wave_tasks.reserve ((size_t) n * sizeof (sw_task))) != cudaSuccess ||
-      (ce = b->s_items.reserve ((size_t) n * 8)) != cudaSuccess ||
-      (ce = b->s_counter.reserve (2 * sizeof (int))) != cudaSuccess ||
-      (generic_ids.size () && (ce = b->s_bound.reserve ((size_t) gen_blocks * 4 * (size_t) bound_stride * sizeof (int2))) != cudaSuccess)) {
+  if ((ce = b->s_trace.reserve (ctx, (size_t) trace_cap * 4)) != cudaSuccess ||
+      (ce = b->s_edges.reserve (ctx, (size_t) std::max<long long> (total_edges, 1) * 4)) != cudaSuccess ||
+      (ce = b->s_tasks.reserve (ctx, (size_t) n * sizeof (sw_task))) != cudaSuccess ||
+      (ce = b->s_wave_tasks.reserve (ctx, (size_t) n * sizeof (sw_task))) != cudaSuccess ||
+      (ce = b->s_items.reserve (ctx, (size_t) n * 8)) != cudaSuccess ||
+      (ce = b->s_counter.reserve (ctx, 2 * sizeof (int))) != cudaSuccess ||
+      (generic_ids.size () && (ce = b->s_bound.reserve (ctx, (size_t) gen_blocks * 4 * (size_t) bound_stride * sizeof (int2))) != cudaSuccess)) {
     gcg_set_error ("gcg_swbatch_align: cudaMalloc failed: %s", cudaGetErrorString (ce));
     rc = GCG_ENOMEM;
   }
@@ -777,15 +792,16 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
   // CIGAR pool: start from a typical size, grow on demand
   if (!rc) {
     unsigned long long want = std::max<unsigned long long> (1 << 16, (unsigned long long) n * 64);
-    if (const char * e = getenv ("GCG_SW_POOL_INIT")) { want = (unsigned long long) atoll (e); cudaFree (b->d_pool); b->d_pool = nullptr; b->pool_cap = 0; }
+    if (const char * e = getenv ("GCG_SW_POOL_INIT")) { want = (unsigned long long) atoll (e); gcg_dfree (ctx, b->d_pool); b->d_pool = nullptr; b->pool_cap = 0; }
     if (b->pool_cap < want) {
-      cudaFree (b->d_pool); b->d_pool = nullptr; b->pool_cap = 0;
-      if ((ce = cudaMalloc (&b->d_pool, (size_t) want * 4)) != cudaSuccess) { gcg_set_error ("gcg_swbatch_align: cigar pool: %s", cudaGetErrorString (ce)); rc = GCG_ENOMEM; }
+      gcg_dfree (ctx, b->d_pool); b->d_pool = nullptr; b->pool_cap = 0;
+      if ((ce = gcg_dmalloc (ctx, &b->d_pool, (size_t) want * 4)) != cudaSuccess) { gcg_set_error ("gcg_swbatch_align: cigar pool: %s", cudaGetErrorString (ce)); rc = GCG_ENOMEM; }
       else b->pool_cap = want;
     }
   }
   unsigned long long * d_cursor = ctx->d_counters + 10;
   if (!rc) GCG_CUDA (cudaMemsetAsync (d_cursor, 0, 8, ctx->stream));
+  gcg_trace_mark (ctx, "sw.align: scratch");
 
   // resident warps of the packed kernel (one warp per block)
   int packed_slots = 0;
@@ -840,7 +856,7 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
       GCG_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, sw_fill_packed_kernel, 32, smem));
       if (per_sm < 1) per_sm = 1;
       int grid = (int) std::min<size_t> (pitems.size (), (size_t) ctx->sm_count * per_sm);
-      if ((ce = b->s_pbound.reserve ((size_t) ctx->sm_count * per_sm * rows_cap * sizeof (uint2))) != cudaSuccess) {
+      if ((ce = b->s_pbound.reserve (ctx, (size_t) ctx->sm_count * per_sm * rows_cap * sizeof (uint2))) != cudaSuccess) {
         gcg_set_error ("gcg_swbatch_align: boundary scratch: %s", cudaGetErrorString (ce)); rc = GCG_ENOMEM; break; }
       d_pbound = (uint2 *) b->s_pbound.p;
       gcg_kscope ks (ctx, "k7_sw_fill_packed");
@@ -857,6 +873,7 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
                                                              d_trace, d_edges, d_bound, bound_stride, b->d_ends);
       GCG_CUDA (cudaGetLastError ());
     }
+    gcg_trace_mark (ctx, "sw.align: wave launched");
     // ---- CIGAR for the wave; grow the pool and redo the wave's CIGARs if it overflowed
     unsigned long long wave_start = b->pool_used;
     for (int attempt = 0; attempt < 3 && !rc; ++attempt) {
@@ -871,16 +888,17 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
       // grow: keep what earlier waves wrote
       unsigned long long ncap = std::max (cur + (cur - wave_start) * (unsigned long long) (units.size () - u1) / std::max<size_t> (u1 - u0, 1), b->pool_cap * 2);
       uint32_t * np = nullptr;
-      if ((ce = cudaMalloc (&np, (size_t) ncap * 4)) != cudaSuccess) { gcg_set_error ("gcg_swbatch_align: cigar pool growth to %llu ops failed: %s", ncap, cudaGetErrorString (ce)); rc = GCG_ENOMEM; break; }
+      if ((ce = gcg_dmalloc (ctx, &np, (size_t) ncap * 4)) != cudaSuccess) { gcg_set_error ("gcg_swbatch_align: cigar pool growth to %llu ops failed: %s", ncap, cudaGetErrorString (ce)); rc = GCG_ENOMEM; break; }
       if (wave_start) GCG_CUDA (cudaMemcpyAsync (np, b->d_pool, (size_t) wave_start * 4, cudaMemcpyDeviceToDevice, ctx->stream));
       GCG_CUDA (cudaStreamSynchronize (ctx->stream));
-      cudaFree (b->d_pool);
+      gcg_dfree (ctx, b->d_pool);
       b->d_pool = np; b->pool_cap = ncap;
       ctx->h_counters[10] = wave_start;
       GCG_CUDA (cudaMemcpyAsync (d_cursor, ctx->h_counters + 10, 8, cudaMemcpyHostToDevice, ctx->stream));
       GCG_CUDA (cudaStreamSynchronize (ctx->stream));
       if (attempt == 2) { gcg_set_error ("gcg_swbatch_align: cigar pool overflow persists"); rc = GCG_ERANGE; }
     }
+    gcg_trace_mark (ctx, "sw.align: wave done");
     u0 = u1;
   }
   if (!rc && cudaStreamSynchronize (ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_swbatch_align: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; }
@@ -898,8 +916,8 @@ extern "C" int gcg_swbatch_download (gcg_ctx * ctx, gcg_swbatch * b, gcg_sw_resu
   *n_cigar_pool = (int64_t) b->pool_used;
   if (b->n) GCG_CUDA (cudaMemcpyAsync (results, b->d_results, (size_t) b->n * sizeof (gcg_sw_result), cudaMemcpyDeviceToHost, ctx->stream));
   if (b->pool_used) {
-    cudaError_t e = cudaHostAlloc ((void **) cigar_pool, (size_t) b->pool_used * 4, cudaHostAllocDefault);
-    if (e != cudaSuccess) { gcg_set_error ("gcg_swbatch_download: pinned alloc failed: %s", cudaGetErrorString (e)); return GCG_ENOMEM; }
+    *cigar_pool = (uint32_t *) gcg_pinned_alloc ((size_t) b->pool_used * 4);
+    if (!*cigar_pool) { gcg_set_error ("gcg_swbatch_download: pinned alloc of %llu CIGAR ops failed", b->pool_used); return GCG_ENOMEM; }
     GCG_CUDA (cudaMemcpyAsync (*cigar_pool, b->d_pool, (size_t) b->pool_used * 4, cudaMemcpyDeviceToHost, ctx->stream));
   }
   GCG_CUDA (cudaStreamSynchronize (ctx->stream));
@@ -911,10 +929,14 @@ extern "C" int gcg_sw_batch (gcg_ctx * ctx, const gcg_sw_params * P, int mode,
                              gcg_sw_result * results, uint32_t ** cigar_pool, int64_t * n_cigar_pool)
 {
   gcg_swbatch * b = nullptr;
+  gcg_trace_mark (ctx, nullptr);
   int rc = gcg_swbatch_upload (ctx, qry, qoff, tgt, toff, n, &b);
   if (rc) return rc;
+  gcg_trace_mark (ctx, "sw: pairs to HBM");
   rc = gcg_swbatch_align (ctx, b, P, mode);
+  gcg_trace_mark (ctx, "sw: fill + cigar");
   if (!rc) rc = gcg_swbatch_download (ctx, b, results, cigar_pool, n_cigar_pool);
+  gcg_trace_mark (ctx, "sw: results to host");
   gcg_swbatch_free (b);
   return rc;
 }
