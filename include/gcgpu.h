@@ -128,6 +128,46 @@ int  gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, co
                  int64_t n_read, int k, gcg_hit ** hits_out, int64_t * n_hit);
 void gcg_free (void * p);
 
+/* ------------------------------------------------------------------ partitioned table  */
+/* Multi-GPU form of the same tables (BASELINE configs[3]): the reference splits its
+ * k-mer tables into n_thread partitions by crc32(kseq) % n_thread (kmer.c:88,124-152;
+ * ont.c:169,193) and lets every thread scan all k-mers for its own share.  Here a partition is
+ * one GPU: k-mers are routed to their owner, exchanged (NCCL all-to-all, done by the caller on
+ * the device buffers below), inserted / looked up there, and the answers travel back.  Every
+ * d_* argument is a DEVICE pointer; all work is enqueued on the ctx stream (gcg_stream), which
+ * the caller must order its exchange after.  Which hash picks the owner is unobservable (the
+ * partition id never leaves kmer.c/ont.c), so it is a 64-bit mix independent of the bucket hash. */
+#define GCG_MAX_PART 16
+typedef struct gcg_route gcg_route;   /* stable partition plan of the k-mers of one tile range */
+
+/* owner partition of a canonical k-mer value (host side, for tests and host bookkeeping) */
+int  gcg_kmer_owner (uint64_t canonical_kmer, int n_part);
+/* sequences are addressed in tiles of 32 packed words (1024 bases): number of tiles of a set */
+int64_t gcg_seqs_tiles (const gcg_seqs * s);
+/* count the k-mers of tiles [tile_begin, tile_end) by owner: counts[n_part].  `s` is borrowed
+ * and must outlive the plan.  One range holds fewer than 2^32 k-mer positions. */
+int  gcg_route_plan (gcg_ctx * ctx, const gcg_seqs * s, int k, int n_part, int64_t tile_begin, int64_t tile_end,
+                     gcg_route ** out, int64_t * counts);
+int64_t gcg_route_kmers (const gcg_route * r);
+/* write the range's k-mers grouped by owner (segment d starts at counts[0]+..+counts[d-1]);
+ * inside a segment the order is (sequence, position).
+ *   keys:    8 bytes  = canonical k-mer + 1                      (search side, ont.c:161-170)
+ *   records: 16 bytes = {canonical k-mer + 1, tid<<32 | pos<<1 | KMER_REV}  (build side, kmer.c:86-94) */
+int  gcg_route_keys (gcg_ctx * ctx, gcg_route * r, void * d_send);
+int  gcg_route_records (gcg_ctx * ctx, gcg_route * r, void * d_send);
+/* owner side: an empty table sized for n_records occurrences; insert received records; answer
+ * received keys.  An answer is the 8-byte value word (tid<<32 | pos<<1 | KMER_REV) of a key present
+ * exactly once (ont.c:171,195), all ones otherwise.  Lookups also count the ONT-side
+ * multiplicity of ont.c:245 in the owner's table, so gcg_table_stats of the partitions add up
+ * to the reference's four numbers. */
+int  gcg_table_create (gcg_ctx * ctx, int64_t n_records, int k, gcg_table ** out);
+int  gcg_table_insert_records (gcg_ctx * ctx, gcg_table * t, const void * d_records, int64_t n);
+int  gcg_table_lookup_keys (gcg_ctx * ctx, gcg_table * t, const void * d_keys, int64_t n, void * d_answers);
+/* requester side: answers in the order gcg_route_keys wrote the keys -> anchors of the range in
+ * (read,pos) order (read = index in `s`). */
+int  gcg_route_collect (gcg_ctx * ctx, gcg_route * r, const void * d_answers, gcg_hits ** out);
+void gcg_route_free (gcg_route * r);
+
 /* ------------------------------------------------------------------ Smith-Waterman --- */
 #define GCG_SWOS_SOFTCLIP      0   /* sw.h:20-23 */
 #define GCG_SWOS_LEADING_INDEL 1

@@ -32,7 +32,10 @@ EXPORTS = [
     "gcg_search_seqs", "gcg_hits_count", "gcg_hits_download", "gcg_hits_free", "gcg_search", "gcg_free",
     "gcg_sw_batch", "gcg_swbatch_upload", "gcg_swbatch_align", "gcg_swbatch_download", "gcg_swbatch_cells",
     "gcg_swbatch_path_counts", "gcg_swbatch_free",
+    "gcg_kmer_owner", "gcg_seqs_tiles", "gcg_route_plan", "gcg_route_kmers", "gcg_route_keys", "gcg_route_records",
+    "gcg_route_collect", "gcg_route_free", "gcg_table_create", "gcg_table_insert_records", "gcg_table_lookup_keys",
 ]
+MAX_PART = 16
 
 
 class GcgError(RuntimeError):
@@ -133,6 +136,19 @@ def load_library(path: str = LIB_PATH):
     L.gcg_swbatch_cells.argtypes = [vp]
     L.gcg_swbatch_path_counts.argtypes = [vp, vp]
     L.gcg_swbatch_free.argtypes = [vp]
+    L.gcg_kmer_owner.argtypes = [C.c_uint64, C.c_int]
+    L.gcg_seqs_tiles.restype = i64
+    L.gcg_seqs_tiles.argtypes = [vp]
+    L.gcg_route_plan.argtypes = [vp, vp, C.c_int, C.c_int, i64, i64, C.POINTER(vp), vp]
+    L.gcg_route_kmers.restype = i64
+    L.gcg_route_kmers.argtypes = [vp]
+    L.gcg_route_keys.argtypes = [vp, vp, vp]
+    L.gcg_route_records.argtypes = [vp, vp, vp]
+    L.gcg_route_collect.argtypes = [vp, vp, vp, C.POINTER(vp)]
+    L.gcg_route_free.argtypes = [vp]
+    L.gcg_table_create.argtypes = [vp, i64, C.c_int, C.POINTER(vp)]
+    L.gcg_table_insert_records.argtypes = [vp, vp, vp, i64]
+    L.gcg_table_lookup_keys.argtypes = [vp, vp, vp, i64, vp]
     _lib = L
     return L
 
@@ -296,6 +312,18 @@ class Context:
             self.L.gcg_free(hp)
         return out
 
+    # ---- partitioned table (device pointers; the exchange between the calls is the caller's) ----
+    def route_plan(self, seqs: "Seqs", k: int, n_part: int, tile_begin: int, tile_end: int) -> "Route":
+        h = C.c_void_p()
+        counts = np.zeros(MAX_PART, dtype=np.int64)
+        self._chk(self.L.gcg_route_plan(self.h, seqs.h, k, n_part, tile_begin, tile_end, C.byref(h), counts.ctypes.data))
+        return Route(self, h, counts[:n_part].copy())
+
+    def table_create(self, n_records: int, k: int) -> "KmerTable":
+        h = C.c_void_p()
+        self._chk(self.L.gcg_table_create(self.h, int(n_records), k, C.byref(h)))
+        return KmerTable(self, h, k)
+
     # ---- SW ------------------------------------------------------------------------------
     def sw_batch(self, P: SWParams, qrys, tgts, mode: int = SW_ASIS):
         """host-buffer form.  -> (results SWRES_DTYPE[n], list of cigar uint32 arrays)"""
@@ -359,6 +387,48 @@ class Seqs(_Handle):
     def kmers(self, k):
         return int(self.ctx.L.gcg_seqs_kmers(self.h, k))
 
+    @property
+    def tiles(self):
+        return int(self.ctx.L.gcg_seqs_tiles(self.h))
+
+
+class Hits(_Handle):
+    """device-resident anchor list (gcg_hits)"""
+    _free = "gcg_hits_free"
+
+    @property
+    def n(self):
+        return int(self.ctx.L.gcg_hits_count(self.h))
+
+    def download(self) -> np.ndarray:
+        out = np.zeros(self.n, dtype=HIT_DTYPE)
+        self.ctx._chk(self.ctx.L.gcg_hits_download(self.ctx.h, self.h, out.ctypes.data, len(out)))
+        return out
+
+
+class Route(_Handle):
+    """stable partition plan of the k-mers of one tile range by owner (gcg_route)"""
+    _free = "gcg_route_free"
+
+    def __init__(self, ctx, h, counts):
+        super().__init__(ctx, h)
+        self.counts = counts
+
+    @property
+    def kmers(self):
+        return int(self.ctx.L.gcg_route_kmers(self.h))
+
+    def keys(self, d_send: int):
+        self.ctx._chk(self.ctx.L.gcg_route_keys(self.ctx.h, self.h, d_send))
+
+    def records(self, d_send: int):
+        self.ctx._chk(self.ctx.L.gcg_route_records(self.ctx.h, self.h, d_send))
+
+    def collect(self, d_answers: int) -> Hits:
+        h = C.c_void_p()
+        self.ctx._chk(self.ctx.L.gcg_route_collect(self.ctx.h, self.h, d_answers, C.byref(h)))
+        return Hits(self.ctx, h)
+
 
 class KmerTable(_Handle):
     _free = "gcg_table_free"
@@ -371,6 +441,12 @@ class KmerTable(_Handle):
         out = np.zeros(4, dtype=np.int64)
         self.ctx._chk(self.ctx.L.gcg_table_stats(self.ctx.h, self.h, out.ctypes.data))
         return tuple(int(x) for x in out)
+
+    def insert_records(self, d_records: int, n: int):
+        self.ctx._chk(self.ctx.L.gcg_table_insert_records(self.ctx.h, self.h, d_records, int(n)))
+
+    def lookup_keys(self, d_keys: int, n: int, d_answers: int):
+        self.ctx._chk(self.ctx.L.gcg_table_lookup_keys(self.ctx.h, self.h, d_keys, int(n), d_answers))
 
     def dump(self):
         """-> key, multi(1|2), tid, pos, rev sorted by key"""

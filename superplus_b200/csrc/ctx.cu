@@ -59,8 +59,8 @@ extern "C" int gcg_init (int device, gcg_ctx ** out)
     unsigned long long keep = ~0ULL;
     GCG_CUDA (cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
-  GCG_CUDA (cudaMalloc (&ctx->d_counters, 16 * sizeof (unsigned long long)));
-  GCG_CUDA (cudaHostAlloc (&ctx->h_counters, 16 * sizeof (unsigned long long), cudaHostAllocDefault));
+  GCG_CUDA (cudaMalloc (&ctx->d_counters, 64 * sizeof (unsigned long long)));
+  GCG_CUDA (cudaHostAlloc (&ctx->h_counters, 64 * sizeof (unsigned long long), cudaHostAllocDefault));
   *out = ctx;
   return GCG_OK;
 }

@@ -54,7 +54,7 @@ struct gcg_ctx {
   int64_t launches = 0;
   gcg_stage stage;
   // small device scratch for reductions / counters
-  unsigned long long * d_counters = nullptr;   // 16 x u64
+  unsigned long long * d_counters = nullptr;   // 64 x u64 ([16..48) = per-partition totals of gcg_route_plan)
   unsigned long long * h_counters = nullptr;   // pinned mirror
 };
 
@@ -140,6 +140,9 @@ struct gcg_hits {
 #define GCG_KEY_MULTI 0x8000000000000000ULL
 
 int gcg_stage_reserve (gcg_ctx * ctx);
+int gcg_table_alloc (gcg_ctx * ctx, int64_t n_kmers, int k, gcg_table ** out);
+int64_t gcg_mask_scan_blocks (int64_t n_words);
+int gcg_mask_scan (gcg_ctx * ctx, const uint32_t * d_mask, int64_t n_words, uint32_t * d_prefix, uint32_t * d_bsum, int64_t * total);
 void * gcg_pinned_alloc (size_t bytes);      // parked-block cache, released with gcg_free
 void gcg_pinned_trim (void);
 void gcg_trace_mark (gcg_ctx * ctx, const char * label);   // label == NULL restarts the clock

@@ -16,86 +16,7 @@
 #include <thread>
 
 #include "gcg_internal.cuh"
-
-// =============================================================================================
-// device helpers
-// =============================================================================================
-__device__ __forceinline__ uint32_t pack4 (uint32_t x)
-{
-  // four ASCII bytes (first base in the low byte) -> 8 bits, first base in the top two bits
-  return (((x >> 1) & 0x03030303u) * 0x40100401u) >> 24;
-}
-
-__device__ __forceinline__ uint64_t revcomp64 (uint64_t x, int k)
-{
-  // kseq1.h:37-46: complement (^2 per base), reverse the 2-bit groups, drop the unused tail
-  x ^= 0xAAAAAAAAAAAAAAAAULL;
-  x = ((x & 0x3333333333333333ULL) << 2) | ((x >> 2) & 0x3333333333333333ULL);
-  x = ((x & 0x0F0F0F0F0F0F0F0FULL) << 4) | ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL);
-  uint32_t lo = (uint32_t) x, hi = (uint32_t) (x >> 32);
-  lo = __byte_perm (lo, 0, 0x0123);
-  hi = __byte_perm (hi, 0, 0x0123);
-  x = ((uint64_t) lo << 32) | hi;
-  return x >> (64 - 2 * k);
-}
-
-__device__ __forceinline__ uint32_t kmer_hash32 (uint64_t key)
-{
-  uint32_t h = (uint32_t) key ^ ((uint32_t) (key >> 32) * 0x9E3779B1u);
-  h ^= h >> 16; h *= 0x85EBCA6Bu;
-  h ^= h >> 13; h *= 0xC2B2AE35u;
-  h ^= h >> 16;
-  return h;
-}
-
-// largest s in [0,n) with woff[s] <= w  (woff has n+1 entries, woff[n] > w)
-__device__ __forceinline__ int64_t find_seq (const int64_t * __restrict__ woff, int64_t n, int64_t w)
-{
-  int64_t lo = 0, hi = n;          // invariant: woff[lo] <= w < woff[hi]
-  while (hi - lo > 1) {
-    int64_t mid = (lo + hi) >> 1;
-    if (__ldg (woff + mid) <= w) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-
-// same, starting from a hint h <= answer (the sequence of the first word of the 32-word tile, built
-// on the host): reads are hundreds of words long, so this is almost always zero or one step
-__device__ __forceinline__ int64_t find_seq_from (const int64_t * __restrict__ woff, int64_t n, int64_t w, int64_t h)
-{
-#pragma unroll 1
-  for (int i = 0; i < 4; ++i) {
-    if (h + 1 >= n || __ldg (woff + h + 1) > w) return h;
-    ++h;
-  }
-  int64_t lo = h, hi = n;            // many short or empty sequences inside one tile: finish by bisection
-  while (hi - lo > 1) {
-    int64_t mid = (lo + hi) >> 1;
-    if (__ldg (woff + mid) <= w) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-
-// Per-lane rolling state over the 32 k-mer start positions of one packed word.
-struct kroll {
-  uint64_t fwd, rc, nxt, mask;
-  int shift_rc;
-  __device__ __forceinline__ void init (uint64_t hi, uint64_t lo, int k)
-  {
-    mask = (1ULL << (2 * k)) - 1;       // k <= 31
-    fwd = hi >> (64 - 2 * k);
-    rc = revcomp64 (fwd, k);
-    nxt = (hi << (2 * k)) | (lo >> (64 - 2 * k));
-    shift_rc = 2 * (k - 1);
-  }
-  __device__ __forceinline__ void step ()
-  {
-    uint64_t b = nxt >> 62;
-    nxt <<= 2;
-    fwd = ((fwd << 2) | b) & mask;
-    rc = (rc >> 2) | ((b ^ 2ULL) << shift_rc);
-  }
-};
+#include "kmer_dev.cuh"
 
 // =============================================================================================
 // K1  ASCII -> 2 bit
@@ -135,29 +56,7 @@ k23_build_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
       bool fw = r.fwd < r.rc;
       unsigned long long key = (fw ? r.fwd : r.rc) + 1ULL;
       unsigned long long val = ((unsigned long long) s << 32) | ((unsigned long long) (uint32_t) (p0 + j) << 1) | (fw ? 0ULL : 1ULL);
-      const uint32_t hsh = kmer_hash32 (key - 1ULL), fp = hsh & 3u;
-      uint32_t b = __umulhi (hsh, n_bucket);
-      for (;;) {
-        unsigned long long * slot = keys + 4ULL * b;
-        bool done = false;
-#pragma unroll
-        for (int i = 0; i < 4 && !done; ++i) {
-          unsigned long long cur = __ldcg (slot + i);
-          if (cur == 0ULL) {
-            unsigned long long old = atomicCAS (slot + i, 0ULL, key);
-            if (old == 0ULL) { vals[4ULL * b + i] = val; done = true; break; }
-            cur = old;
-          }
-          if ((cur & GCG_KEY_MASK) == key) {
-            if (!(cur & GCG_KEY_MULTI)) atomicOr (slot + i, GCG_KEY_MULTI);
-            done = true;
-          }
-        }
-        if (done) break;
-        // bucket is full of other keys: leave the key's overflow mark (bit 62 of slot `fp`) and move on
-        if (!(__ldcg (slot + fp) & GCG_KEY_OVF)) atomicOr (slot + fp, GCG_KEY_OVF);
-        b = (b + 1 == n_bucket) ? 0 : b + 1;
-      }
+      table_insert (keys, vals, n_bucket, key, val);
     }
   }
 }
@@ -176,62 +75,6 @@ k23_build_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
 //   produced by hits_emit_kernel after a prefix sum over the masks, which re-probes just the
 //   anchored positions (a few percent).
 // =============================================================================================
-struct __align__ (32) bucket4 { unsigned long long a, b, c, d; };
-
-__device__ __forceinline__ bucket4 ld_bucket (const unsigned long long * p)
-{
-  bucket4 r;
-  asm volatile ("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-                : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p));
-  return r;
-}
-
-// slot index (0..3) of `key` in the bucket or -1; *kw receives the matching key word
-__device__ __forceinline__ int bucket_find (const bucket4 & q, unsigned long long key, unsigned long long * kw)
-{
-  if ((q.a & GCG_KEY_MASK) == key) { *kw = q.a; return 0; }
-  if ((q.b & GCG_KEY_MASK) == key) { *kw = q.b; return 1; }
-  if ((q.c & GCG_KEY_MASK) == key) { *kw = q.c; return 2; }
-  if ((q.d & GCG_KEY_MASK) == key) { *kw = q.d; return 3; }
-  return -1;
-}
-
-// has a key with fingerprint fp (hash & 3) ever been pushed out of this bucket?
-__device__ __forceinline__ bool bucket_ovf (const bucket4 & q, uint32_t fp)
-{
-  uint32_t h0 = (uint32_t) (q.a >> 32), h1 = (uint32_t) (q.b >> 32), h2 = (uint32_t) (q.c >> 32), h3 = (uint32_t) (q.d >> 32);
-  uint32_t h = (fp & 2u) ? ((fp & 1u) ? h3 : h2) : ((fp & 1u) ? h1 : h0);
-  return (h & 0x40000000u) != 0;
-}
-
-// key present with multiplicity 1 in this bucket (key has bits 62/63 clear, so one compare does both)
-__device__ __forceinline__ bool bucket_has_unique (const bucket4 & q, unsigned long long key)
-{
-  return ((q.a & ~GCG_KEY_OVF) == key) | ((q.b & ~GCG_KEY_OVF) == key) | ((q.c & ~GCG_KEY_OVF) == key) | ((q.d & ~GCG_KEY_OVF) == key);
-}
-
-// full probe sequence starting from an already loaded bucket; returns slot index or ~0
-__device__ __forceinline__ unsigned long long table_lookup (const unsigned long long * __restrict__ keys, uint32_t n_bucket,
-                                                           uint32_t b, bucket4 q, unsigned long long key, uint32_t fp, unsigned long long * kw)
-{
-  for (;;) {
-    int f = bucket_find (q, key, kw);
-    if (f >= 0) return 4ULL * b + f;
-    if (!bucket_ovf (q, fp)) return ~0ULL;           // no key of this fingerprint ever left the bucket: absent
-    b = (b + 1 == n_bucket) ? 0 : b + 1;
-    q = ld_bucket (keys + 4ULL * b);
-  }
-}
-
-// canonical key (+1) of the k-mer starting at bit offset 2j of the 128-bit window (wh, wl)
-__device__ __forceinline__ unsigned long long key_at (uint64_t wh, uint64_t wl, int j, int k, bool * fw)
-{
-  uint64_t xw = j ? ((wh << (2 * j)) | (wl >> (64 - 2 * j))) : wh;
-  uint64_t fwd = xw >> (64 - 2 * k), rc = revcomp64 (fwd, k);
-  *fw = fwd < rc;
-  return (*fw ? fwd : rc) + 1ULL;
-}
-
 #define K4_UNROLL 4
 #define K4_WARPS 8
 
@@ -775,20 +618,15 @@ extern "C" void gcg_table_free (gcg_table * t)
   delete t;
 }
 
-extern "C" int gcg_table_build_seqs (gcg_ctx * ctx, const gcg_seqs * contigs, int k, gcg_table ** out)
+// zeroed table sized for n_kmers inserted occurrences (load factor <= 0.5 over 4-slot buckets)
+int gcg_table_alloc (gcg_ctx * ctx, int64_t n_kmers, int k, gcg_table ** out)
 {
-  GCG_CHECK (ctx && contigs && out, GCG_EINVAL, "gcg_table_build: bad argument");
-  GCG_CHECK (k >= 1 && k <= 31, GCG_ERANGE, "gcg_table_build: k=%d outside [1,31] (kseq1_t is one uint64, kseq1.h:20,73)", k);
-  GCG_CHECK (contigs->n < 0x7FFFFFFF, GCG_ERANGE, "gcg_table_build: too many contigs");
-  for (int32_t l : contigs->h_len)
-    GCG_CHECK (l <= (1 << 30), GCG_ERANGE, "gcg_table_build: contig longer than 2^30 bases");
+  GCG_CHECK (k >= 1 && k <= 31, GCG_ERANGE, "gcg_table: k=%d outside [1,31] (kseq1_t is one uint64, kseq1.h:20,73)", k);
   GCG_CUDA (cudaSetDevice (ctx->device));
-  int64_t n_kmers = gcg_seqs_kmers (contigs, k);
   gcg_table * t = new gcg_table ();
   t->ctx = ctx; t->k = k;
-  // load factor <= 0.5 over 4-slot buckets
   int64_t nb = (n_kmers + 1) / 2 + 64;
-  GCG_CHECK (nb < 0xFFFFFFFFLL, GCG_ERANGE, "gcg_table_build: %lld k-mers exceed the bucket index range", (long long) n_kmers);
+  if (nb >= 0xFFFFFFFFLL) { delete t; gcg_set_error ("gcg_table: %lld k-mers exceed the bucket index range", (long long) n_kmers); return GCG_ERANGE; }
   t->n_bucket = (uint32_t) nb;
   t->n_slot = (uint64_t) nb * 4;
   t->n_inserted = n_kmers;
@@ -796,12 +634,27 @@ extern "C" int gcg_table_build_seqs (gcg_ctx * ctx, const gcg_seqs * contigs, in
   cudaError_t e;
   if ((e = gcg_dmalloc (ctx, &t->d_keys, t->n_slot * 8)) != cudaSuccess || (e = gcg_dmalloc (ctx, &t->d_vals, t->n_slot * 8)) != cudaSuccess ||
       (e = gcg_dmalloc (ctx, &t->d_ont, ont_words * 4)) != cudaSuccess) {
-    gcg_set_error ("gcg_table_build: cudaMalloc of %llu slots failed: %s", (unsigned long long) t->n_slot, cudaGetErrorString (e));
+    gcg_set_error ("gcg_table: cudaMalloc of %llu slots failed: %s", (unsigned long long) t->n_slot, cudaGetErrorString (e));
     gcg_table_free (t);
     return GCG_ENOMEM;
   }
   GCG_CUDA (cudaMemsetAsync (t->d_keys, 0, t->n_slot * 8, ctx->stream));
   GCG_CUDA (cudaMemsetAsync (t->d_ont, 0, ont_words * 4, ctx->stream));
+  *out = t;
+  return GCG_OK;
+}
+
+extern "C" int gcg_table_build_seqs (gcg_ctx * ctx, const gcg_seqs * contigs, int k, gcg_table ** out)
+{
+  GCG_CHECK (ctx && contigs && out, GCG_EINVAL, "gcg_table_build: bad argument");
+  GCG_CHECK (k >= 1 && k <= 31, GCG_ERANGE, "gcg_table_build: k=%d outside [1,31] (kseq1_t is one uint64, kseq1.h:20,73)", k);
+  GCG_CHECK (contigs->n < 0x7FFFFFFF, GCG_ERANGE, "gcg_table_build: too many contigs");
+  for (int32_t l : contigs->h_len)
+    GCG_CHECK (l <= (1 << 30), GCG_ERANGE, "gcg_table_build: contig longer than 2^30 bases");
+  int64_t n_kmers = gcg_seqs_kmers (contigs, k);
+  gcg_table * t = nullptr;
+  int rc = gcg_table_alloc (ctx, n_kmers, k, &t);
+  if (rc) return rc;
   if (contigs->n_words > 0 && n_kmers > 0) {
     gcg_kscope ks (ctx, "k23_build");
     k23_build_kernel<<<grid_for (ctx, contigs->n_words, 256, 8), 256, 0, ctx->stream>>> (
@@ -874,6 +727,26 @@ extern "C" int gcg_table_dump (gcg_ctx * ctx, gcg_table * t, int64_t cap, uint64
 }
 
 // ---- search -----------------------------------------------------------------------------------
+// exclusive prefix sum of popcount(mask[w]) into prefix[w]; *total = number of set bits.  bsum holds
+// (n_words + SCAN_TILE - 1) / SCAN_TILE words of scratch.  Synchronises the stream.
+int64_t gcg_mask_scan_blocks (int64_t n_words) { return (n_words + SCAN_TILE - 1) / SCAN_TILE; }
+
+int gcg_mask_scan (gcg_ctx * ctx, const uint32_t * d_mask, int64_t n_words, uint32_t * d_prefix, uint32_t * d_bsum, int64_t * total)
+{
+  int64_t nb = gcg_mask_scan_blocks (n_words);
+  { gcg_kscope ks (ctx, "scan_reduce");
+    scan_reduce_kernel<<<(unsigned) nb, SCAN_BLOCK, 0, ctx->stream>>> (d_mask, n_words, d_bsum); }
+  { gcg_kscope ks (ctx, "scan_blocksums");
+    scan_blocksums_kernel<<<1, 1024, 0, ctx->stream>>> (d_bsum, nb, ctx->d_counters + 4); }
+  { gcg_kscope ks (ctx, "scan_apply");
+    scan_apply_kernel<<<(unsigned) nb, SCAN_BLOCK, 0, ctx->stream>>> (d_mask, n_words, d_bsum, d_prefix); }
+  GCG_CUDA (cudaGetLastError ());
+  GCG_CUDA (cudaMemcpyAsync (ctx->h_counters + 4, ctx->d_counters + 4, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+  *total = (int64_t) ctx->h_counters[4];
+  return GCG_OK;
+}
+
 extern "C" void gcg_hits_free (gcg_hits * h)
 {
   if (!h) return;
@@ -913,16 +786,9 @@ extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * r
     { gcg_kscope ks (ctx, "k45_search");
       k45_search_kernel<<<grid_for (ctx, ((n_words + 31) >> 5) * 32, 32 * K4_WARPS, 8), 32 * K4_WARPS, 0, ctx->stream>>> (
           reads->d_packed, reads->d_woff, reads->d_len, reads->d_tseq, reads->n, n_words, k, t->d_keys, t->n_bucket, d_mask); }
-    { gcg_kscope ks (ctx, "scan_reduce");
-      scan_reduce_kernel<<<(unsigned) nb, SCAN_BLOCK, 0, ctx->stream>>> (d_mask, n_words, d_bsum); }
-    { gcg_kscope ks (ctx, "scan_blocksums");
-      scan_blocksums_kernel<<<1, 1024, 0, ctx->stream>>> (d_bsum, nb, ctx->d_counters + 4); }
-    { gcg_kscope ks (ctx, "scan_apply");
-      scan_apply_kernel<<<(unsigned) nb, SCAN_BLOCK, 0, ctx->stream>>> (d_mask, n_words, d_bsum, d_prefix); }
     if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_search: kernel launch failed"); rc = GCG_ECUDA; break; }
-    if (cudaMemcpyAsync (ctx->h_counters + 4, ctx->d_counters + 4, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-        cudaStreamSynchronize (ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_search: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; break; }
-    int64_t n_hit = (int64_t) ctx->h_counters[4];
+    int64_t n_hit = 0;
+    if ((rc = gcg_mask_scan (ctx, d_mask, n_words, d_prefix, d_bsum, &n_hit)) != 0) break;
     h->n = n_hit;
     if (n_hit > 0) {
       if ((e = gcg_dmalloc (ctx, &h->d_hits, (size_t) n_hit * sizeof (gcg_hit))) != cudaSuccess) {

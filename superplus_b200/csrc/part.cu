@@ -1,0 +1,534 @@
+// Hash-partitioned contig k-mer table: the device half of the multi-GPU exchange
+// (BASELINE configs[3]: "k-mer table hash-partitioned over 8x B200, NVLink all-to-all").
+//
+// The reference partitions its tables the same way on the host: every k-mer goes to table
+// crc32(kseq) % n_thread (kmer.c:88,124-152; ont.c:169,193) and every thread scans all k-mers for
+// its own share.  Here a partition is one GPU.  Which hash picks the owner is unobservable
+// (SURVEY F5), so the owner is a 64-bit mix that is independent of the in-table bucket hash.
+//
+//   route  : stable partition of the k-mers of a tile range by owner.  A warp owns a tile of 32
+//            packed words (1024 k-mer start positions); per-lane per-owner counts live in shared
+//            memory, a warp scan turns them into cursors, so the position of every k-mer inside
+//            its owner's segment is a pure function of (tile, word, j): segment order is
+//            (read, pos) order, the collect pass can recompute it, nothing is tagged or sorted.
+//   insert : owner side of the build, 16-byte {key+1, tid<<32 | pos<<1 | rev} records.
+//   lookup : owner side of the search, 8-byte keys in, 8-byte answers out (the value word of a
+//            key present exactly once, ont.c:171,195; all ones otherwise); also counts the ONT-side
+//            multiplicity (ont.c:245) — at the owner it sees the hits of every rank.
+//   collect: answers (in the order the keys were sent) -> anchors in (read,pos) order.
+#include <algorithm>
+#include <stdio.h>
+#include <string.h>
+
+#include "gcg_internal.cuh"
+#include "kmer_dev.cuh"
+
+#define RT_WARPS 8
+#define GCG_ANS_MISS 0xFFFFFFFFFFFFFFFFULL
+
+struct gcg_route {
+  gcg_ctx * ctx = nullptr;
+  const gcg_seqs * seqs = nullptr;          // borrowed
+  int k = 0, n_part = 0;
+  int64_t tile0 = 0, n_tiles = 0;           // tiles [tile0, tile0 + n_tiles) of 32 words
+  int64_t n_kmers = 0;                      // k-mer start positions in the range
+  uint32_t * d_off = nullptr;               // [n_part][n_tiles]: count, then exclusive offset inside the owner's segment
+  uint32_t * d_bsum = nullptr;
+  int64_t * d_seg = nullptr;                // [n_part + 1] segment starts (records)
+  int64_t counts[GCG_MAX_PART] = {0};
+};
+
+// ---- owner of a canonical k-mer ---------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t kmer_owner (uint64_t key, uint32_t n_part)
+{
+  uint64_t x = key * 0x9E3779B97F4A7C15ULL;
+  x ^= x >> 29;
+  x *= 0xBF58476D1CE4E5B9ULL;
+  const uint32_t hi = (uint32_t) (x >> 32);          // (the usual closing x ^= x >> 32 only touches the low half)
+#ifdef __CUDA_ARCH__
+  return __umulhi (hi, n_part);
+#else
+  return (uint32_t) (((uint64_t) hi * (uint64_t) n_part) >> 32);
+#endif
+}
+
+extern "C" int gcg_kmer_owner (uint64_t canonical_kmer, int n_part)
+{
+  if (n_part < 1 || n_part > GCG_MAX_PART) return -1;
+  return (int) kmer_owner (canonical_kmer, (uint32_t) n_part);
+}
+
+extern "C" int64_t gcg_seqs_tiles (const gcg_seqs * s) { return s ? (s->n_words + 31) >> 5 : 0; }
+
+// ---- the shared walk over one tile ---------------------------------------------------------------
+// number of valid k-mer starts in word w and, through *s_out / *p0_out, its sequence and first position
+__device__ __forceinline__ int word_valid (const int64_t * __restrict__ woff, const int32_t * __restrict__ len,
+                                           const int32_t * __restrict__ tile_seq, int64_t n_seq, int64_t n_words,
+                                           int64_t tile, int64_t w, int k, int64_t * s_out, int32_t * p0_out)
+{
+  if (w >= n_words) return 0;
+  int64_t s = find_seq_from (woff, n_seq, w, __ldg (tile_seq + tile));
+  int32_t p0 = (int32_t) ((w - __ldg (woff + s)) << 5);
+  int nvalid = __ldg (len + s) - k + 1 - p0;
+  *s_out = s; *p0_out = p0;
+  return nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
+}
+
+// per-lane counts of this word's k-mers by owner, into cnt[d][lane]
+__device__ __forceinline__ void lane_counts (const uint64_t * __restrict__ packed, int64_t w, int nvalid, int k, uint32_t n_part,
+                                             uint32_t (* cnt)[32], int lane)
+{
+  for (uint32_t d = 0; d < n_part; ++d) cnt[d][lane] = 0;
+  if (!nvalid) return;
+  kroll r;
+  r.init (__ldg (packed + w), __ldg (packed + w + 1), k);
+  for (int j = 0; j < nvalid; ++j) {
+    if (j) r.step ();
+    ++cnt[kmer_owner (r.fwd < r.rc ? r.fwd : r.rc, n_part)][lane];
+  }
+}
+
+// cnt[d][lane] <- off[d][tile] + exclusive warp scan of cnt[d][.]  (the lane's cursor inside segment d)
+__device__ __forceinline__ void lane_cursors (uint32_t (* cnt)[32], const uint32_t * __restrict__ off, int64_t n_tiles, int64_t t,
+                                              uint32_t n_part, int lane)
+{
+  for (uint32_t d = 0; d < n_part; ++d) {
+    uint32_t c = cnt[d][lane], x = c;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (0xffffffffu, x, o); if (lane >= o) x += y; }
+    cnt[d][lane] = __ldg (off + (int64_t) d * n_tiles + t) + x - c;
+  }
+}
+
+__global__ void __launch_bounds__ (32 * RT_WARPS)
+route_count_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff, const int32_t * __restrict__ len,
+                    const int32_t * __restrict__ tile_seq, int64_t n_seq, int64_t n_words, int k, uint32_t n_part,
+                    int64_t tile0, int64_t n_tiles, uint32_t * __restrict__ cnt_out)
+{
+  __shared__ uint32_t s_cnt[RT_WARPS][GCG_MAX_PART][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t wstride = (int64_t) gridDim.x * RT_WARPS;
+  for (int64_t t = (int64_t) blockIdx.x * RT_WARPS + wid; t < n_tiles; t += wstride) {
+    const int64_t tile = tile0 + t, w = (tile << 5) + lane;
+    int64_t s; int32_t p0;
+    const int nvalid = word_valid (woff, len, tile_seq, n_seq, n_words, tile, w, k, &s, &p0);
+    lane_counts (packed, w, nvalid, k, n_part, s_cnt[wid], lane);
+    for (uint32_t d = 0; d < n_part; ++d) {
+      uint32_t tot = __reduce_add_sync (0xffffffffu, s_cnt[wid][d][lane]);
+      if (lane == 0) cnt_out[(int64_t) d * n_tiles + t] = tot;
+    }
+  }
+}
+
+// WHAT: 0 = 8-byte keys (key + 1), 1 = 16-byte records {key + 1, tid << 32 | pos << 1 | rev}
+template <int WHAT>
+__global__ void __launch_bounds__ (32 * RT_WARPS)
+route_scatter_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff, const int32_t * __restrict__ len,
+                      const int32_t * __restrict__ tile_seq, int64_t n_seq, int64_t n_words, int k, uint32_t n_part,
+                      int64_t tile0, int64_t n_tiles, const uint32_t * __restrict__ off, const int64_t * __restrict__ seg,
+                      unsigned long long * __restrict__ out)
+{
+  __shared__ uint32_t s_cnt[RT_WARPS][GCG_MAX_PART][32];
+  __shared__ int64_t s_seg[GCG_MAX_PART];
+  if (threadIdx.x < n_part) s_seg[threadIdx.x] = seg[threadIdx.x];
+  __syncthreads ();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t wstride = (int64_t) gridDim.x * RT_WARPS;
+  for (int64_t t = (int64_t) blockIdx.x * RT_WARPS + wid; t < n_tiles; t += wstride) {
+    const int64_t tile = tile0 + t, w = (tile << 5) + lane;
+    int64_t s; int32_t p0;
+    const int nvalid = word_valid (woff, len, tile_seq, n_seq, n_words, tile, w, k, &s, &p0);
+    lane_counts (packed, w, nvalid, k, n_part, s_cnt[wid], lane);
+    lane_cursors (s_cnt[wid], off, n_tiles, t, n_part, lane);
+    if (!nvalid) continue;
+    kroll r;
+    r.init (__ldg (packed + w), __ldg (packed + w + 1), k);
+    for (int j = 0; j < nvalid; ++j) {
+      if (j) r.step ();
+      const bool fw = r.fwd < r.rc;
+      const unsigned long long key = fw ? r.fwd : r.rc;
+      const uint32_t d = kmer_owner (key, n_part);
+      const int64_t at = s_seg[d] + s_cnt[wid][d][lane]++;
+      if (WHAT == 0) out[at] = key + 1ULL;
+      else {
+        ulonglong2 rec;
+        rec.x = key + 1ULL;
+        rec.y = ((unsigned long long) s << 32) | ((unsigned long long) (uint32_t) (p0 + j) << 1) | (fw ? 0ULL : 1ULL);
+        reinterpret_cast<ulonglong2 *> (out)[at] = rec;
+      }
+    }
+  }
+}
+
+// EMIT 0: mask[w] = bit j set <=> the answer of k-mer j of word w is a hit
+// EMIT 1: anchors written at hits[prefix[w] ...] in position order
+template <int EMIT>
+__global__ void __launch_bounds__ (32 * RT_WARPS)
+route_collect_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff, const int32_t * __restrict__ len,
+                      const int32_t * __restrict__ tile_seq, int64_t n_seq, int64_t n_words, int k, uint32_t n_part,
+                      int64_t tile0, int64_t n_tiles, const uint32_t * __restrict__ off, const int64_t * __restrict__ seg,
+                      const unsigned long long * __restrict__ ans, uint32_t * __restrict__ mask,
+                      const uint32_t * __restrict__ prefix, gcg_hit * __restrict__ hits)
+{
+  __shared__ uint32_t s_cnt[RT_WARPS][GCG_MAX_PART][32];
+  __shared__ int64_t s_seg[GCG_MAX_PART];
+  if (threadIdx.x < n_part) s_seg[threadIdx.x] = seg[threadIdx.x];
+  __syncthreads ();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t wstride = (int64_t) gridDim.x * RT_WARPS;
+  for (int64_t t = (int64_t) blockIdx.x * RT_WARPS + wid; t < n_tiles; t += wstride) {
+    const int64_t tile = tile0 + t, w = (tile << 5) + lane, wl = (t << 5) + lane;    // wl: word index inside the range
+    int64_t s; int32_t p0;
+    const int nvalid = word_valid (woff, len, tile_seq, n_seq, n_words, tile, w, k, &s, &p0);
+    if (EMIT) {
+      // nothing to do for a tile without anchors
+      const uint32_t m = w < n_words ? __ldg (mask + wl) : 0u;
+      if (!__any_sync (0xffffffffu, m != 0u)) continue;
+    }
+    lane_counts (packed, w, nvalid, k, n_part, s_cnt[wid], lane);
+    lane_cursors (s_cnt[wid], off, n_tiles, t, n_part, lane);
+    uint32_t m = 0;
+    if (nvalid) {
+      uint32_t at_hit = EMIT ? __ldg (prefix + wl) : 0u;
+      kroll r;
+      r.init (__ldg (packed + w), __ldg (packed + w + 1), k);
+      for (int j = 0; j < nvalid; ++j) {
+        if (j) r.step ();
+        const bool fw = r.fwd < r.rc;
+        const uint32_t d = kmer_owner (fw ? r.fwd : r.rc, n_part);
+        const unsigned long long v = __ldg (ans + s_seg[d] + s_cnt[wid][d][lane]++);
+        if (v == GCG_ANS_MISS) continue;
+        m |= 1u << j;
+        if (EMIT) {
+          int4 hh;                                    // gcg_hit {read, pos, tid, cpos_flags}
+          hh.x = (int32_t) s;
+          hh.y = p0 + j;
+          hh.z = (int32_t) ((v >> 32) & 0x7FFFFFFFu);
+          hh.w = (int32_t) ((((uint32_t) (v >> 1) & 0x3FFFFFFFu) << 2) | (uint32_t) (v & 1ULL) | (fw ? 0u : 2u));
+          reinterpret_cast<int4 *> (hits)[at_hit++] = hh;
+        }
+      }
+    }
+    if (!EMIT && w < n_words) mask[wl] = m;
+  }
+}
+
+// ---- owner side -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__ (256)
+insert_records_kernel (const ulonglong2 * __restrict__ recs, int64_t n, unsigned long long * __restrict__ keys,
+                       unsigned long long * __restrict__ vals, uint32_t n_bucket)
+{
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    ulonglong2 r = __ldg (recs + i);
+    table_insert (keys, vals, n_bucket, r.x, r.y);
+  }
+}
+
+#define LK_UNROLL 4
+__global__ void __launch_bounds__ (256)
+lookup_keys_kernel (const unsigned long long * __restrict__ qkeys, int64_t n, const unsigned long long * __restrict__ keys,
+                    const unsigned long long * __restrict__ vals, uint32_t * __restrict__ ont, uint32_t n_bucket,
+                    unsigned long long * __restrict__ ans)
+{
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * LK_UNROLL) {
+    unsigned long long key[LK_UNROLL];
+    uint32_t hs[LK_UNROLL];
+    bucket4 q[LK_UNROLL];
+#pragma unroll
+    for (int u = 0; u < LK_UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      key[u] = i < n ? __ldg (qkeys + i) : 1ULL;
+      hs[u] = kmer_hash32 (key[u] - 1ULL);
+      q[u] = ld_bucket (keys + 4ULL * __umulhi (hs[u], n_bucket));
+    }
+#pragma unroll
+    for (int u = 0; u < LK_UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= n) continue;
+      unsigned long long kw, a = GCG_ANS_MISS;
+      const unsigned long long slot = table_lookup (keys, n_bucket, __umulhi (hs[u], n_bucket), q[u], key[u], hs[u] & 3u, &kw);
+      if (slot != ~0ULL && !(kw & GCG_KEY_MULTI)) {            // multi == 1  (ont.c:171,195)
+        a = __ldg (vals + slot);
+        const uint32_t sh = (uint32_t) (slot & 15) * 2;        // ONT-side multiplicity (ont.c:245), saturating at 2
+        const uint32_t old = atomicOr (ont + (slot >> 4), 1u << sh);
+        if (((old >> sh) & 3u) == 1u) atomicOr (ont + (slot >> 4), 2u << sh);
+      }
+      ans[i] = a;
+    }
+  }
+}
+
+// ---- batched exclusive scan of u32 rows (n_part rows of n values) ---------------------------------
+#define PS_ITEMS 8
+#define PS_BLOCK 256
+#define PS_TILE (PS_ITEMS * PS_BLOCK)
+
+__global__ void __launch_bounds__ (PS_BLOCK)
+rows_reduce_kernel (const uint32_t * __restrict__ v, int64_t n, int64_t nb, uint32_t * __restrict__ bsum)
+{
+  __shared__ uint32_t s[PS_BLOCK / 32];
+  const uint32_t * row = v + (int64_t) blockIdx.y * n;
+  int64_t base = (int64_t) blockIdx.x * PS_TILE;
+  uint32_t a = 0;
+  for (int i = 0; i < PS_ITEMS; ++i) {
+    int64_t idx = base + (int64_t) i * PS_BLOCK + threadIdx.x;
+    if (idx < n) a += row[idx];
+  }
+  a = __reduce_add_sync (0xffffffffu, a);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = a;
+  __syncthreads ();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int i = 0; i < PS_BLOCK / 32; ++i) t += s[i];
+    bsum[(int64_t) blockIdx.y * nb + blockIdx.x] = t;
+  }
+}
+
+// one block per row: exclusive scan of the row's block sums in place, row total to totals[row]
+__global__ void __launch_bounds__ (1024)
+rows_blocksums_kernel (uint32_t * __restrict__ bsum, int64_t nb, unsigned long long * __restrict__ totals)
+{
+  __shared__ uint32_t s_warp[32];
+  __shared__ unsigned long long s_carry;
+  uint32_t * row = bsum + (int64_t) blockIdx.x * nb;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads ();
+  for (int64_t base = 0; base < nb; base += 1024) {
+    int64_t idx = base + threadIdx.x;
+    uint32_t v = idx < nb ? row[idx] : 0, x = v;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+    __syncthreads ();
+    if (threadIdx.x < 32) {
+      uint32_t wv = s_warp[threadIdx.x], wx = wv;
+      for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (0xffffffffu, wx, o); if (threadIdx.x >= o) wx += y; }
+      s_warp[threadIdx.x] = wx - wv;
+    }
+    __syncthreads ();
+    unsigned long long excl = (unsigned long long) (x - v + s_warp[threadIdx.x >> 5]) + s_carry;
+    if (idx < nb) row[idx] = (uint32_t) excl;
+    __syncthreads ();
+    if (threadIdx.x == 1023) s_carry = excl + v;
+    __syncthreads ();
+  }
+  if (threadIdx.x == 0) totals[blockIdx.x] = s_carry;
+}
+
+__global__ void __launch_bounds__ (PS_BLOCK)
+rows_apply_kernel (uint32_t * __restrict__ v, int64_t n, int64_t nb, const uint32_t * __restrict__ bsum)
+{
+  __shared__ uint32_t s_warp[PS_BLOCK / 32];
+  uint32_t * row = v + (int64_t) blockIdx.y * n;
+  int64_t base = (int64_t) blockIdx.x * PS_TILE + (int64_t) threadIdx.x * PS_ITEMS;
+  uint32_t c[PS_ITEMS], t = 0;
+#pragma unroll
+  for (int i = 0; i < PS_ITEMS; ++i) { int64_t idx = base + i; c[i] = idx < n ? row[idx] : 0; t += c[i]; }
+  uint32_t x = t;
+  for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+  __syncthreads ();
+  if (threadIdx.x < 32) {
+    uint32_t wv = threadIdx.x < PS_BLOCK / 32 ? s_warp[threadIdx.x] : 0, wx = wv;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (0xffffffffu, wx, o); if (threadIdx.x >= o) wx += y; }
+    if (threadIdx.x < PS_BLOCK / 32) s_warp[threadIdx.x] = wx - wv;
+  }
+  __syncthreads ();
+  uint32_t run = x - t + s_warp[threadIdx.x >> 5] + bsum[(int64_t) blockIdx.y * nb + blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < PS_ITEMS; ++i) { int64_t idx = base + i; if (idx < n) row[idx] = run; run += c[i]; }
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+static int warp_grid (gcg_ctx * ctx, int64_t n_tiles)
+{
+  int64_t nb = (n_tiles + RT_WARPS - 1) / RT_WARPS, cap = (int64_t) ctx->sm_count * 8;
+  return (int) std::max<int64_t> (1, std::min (nb, cap));
+}
+
+static int flat_grid (gcg_ctx * ctx, int64_t n, int per_thread)
+{
+  int64_t nb = (n + 256LL * per_thread - 1) / (256LL * per_thread), cap = (int64_t) ctx->sm_count * 8;
+  return (int) std::max<int64_t> (1, std::min (nb, cap));
+}
+
+extern "C" void gcg_route_free (gcg_route * r)
+{
+  if (!r) return;
+  gcg_dfree (r->ctx, r->d_off); gcg_dfree (r->ctx, r->d_bsum); gcg_dfree (r->ctx, r->d_seg);
+  delete r;
+}
+
+extern "C" int gcg_route_plan (gcg_ctx * ctx, const gcg_seqs * s, int k, int n_part, int64_t tile_begin, int64_t tile_end,
+                               gcg_route ** out, int64_t * counts)
+{
+  GCG_CHECK (ctx && s && out && counts, GCG_EINVAL, "gcg_route_plan: bad argument");
+  GCG_CHECK (k >= 1 && k <= 31, GCG_ERANGE, "gcg_route_plan: k=%d outside [1,31]", k);
+  GCG_CHECK (n_part >= 1 && n_part <= GCG_MAX_PART, GCG_ERANGE, "gcg_route_plan: %d partitions outside [1,%d]", n_part, GCG_MAX_PART);
+  const int64_t all_tiles = (s->n_words + 31) >> 5;
+  GCG_CHECK (tile_begin >= 0 && tile_begin <= tile_end && tile_end <= all_tiles, GCG_EINVAL,
+             "gcg_route_plan: tile range [%lld,%lld) outside [0,%lld]", (long long) tile_begin, (long long) tile_end, (long long) all_tiles);
+  GCG_CHECK (s->n < 0x7FFFFFFF, GCG_ERANGE, "gcg_route_plan: too many sequences");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  gcg_route * r = new gcg_route ();
+  r->ctx = ctx; r->seqs = s; r->k = k; r->n_part = n_part; r->tile0 = tile_begin; r->n_tiles = tile_end - tile_begin;
+  // positions in the range (host side: sequences are word aligned, so whole words belong to one sequence)
+  {
+    const int64_t w_lo = tile_begin << 5, w_hi = std::min (s->n_words, tile_end << 5);
+    int64_t tot = 0;
+    size_t i = (size_t) (std::upper_bound (s->h_woff.begin (), s->h_woff.end (), w_lo) - s->h_woff.begin ());
+    i = i ? i - 1 : 0;
+    for (; i < (size_t) s->n && s->h_woff[i] < w_hi; ++i) {
+      const int64_t nk = (int64_t) s->h_len[i] - k + 1;                       // valid starts are positions [0, nk)
+      const int64_t a = std::max<int64_t> ((w_lo - s->h_woff[i]) << 5, 0), b = std::min<int64_t> ((w_hi - s->h_woff[i]) << 5, nk);
+      if (b > a) tot += b - a;
+    }
+    r->n_kmers = tot;
+  }
+  if (r->n_kmers >= 0xFFFFFFFFLL) {
+    gcg_set_error ("gcg_route_plan: %lld positions in one range exceed the 32-bit segment offsets; split the range", (long long) r->n_kmers);
+    delete r;
+    return GCG_ERANGE;
+  }
+  for (int d = 0; d < n_part; ++d) counts[d] = 0;
+  const int64_t nt = r->n_tiles;
+  int rc = GCG_OK;
+  cudaError_t e;
+  const int64_t nb = (nt + PS_TILE - 1) / PS_TILE;
+  if ((e = gcg_dmalloc (ctx, &r->d_off, (size_t) std::max<int64_t> (nt, 1) * n_part * 4)) != cudaSuccess ||
+      (e = gcg_dmalloc (ctx, &r->d_bsum, (size_t) std::max<int64_t> (nb, 1) * n_part * 4)) != cudaSuccess ||
+      (e = gcg_dmalloc (ctx, &r->d_seg, (GCG_MAX_PART + 1) * 8)) != cudaSuccess) {
+    gcg_set_error ("gcg_route_plan: cudaMalloc failed: %s", cudaGetErrorString (e));
+    gcg_route_free (r);
+    return GCG_ENOMEM;
+  }
+  int64_t seg[GCG_MAX_PART + 1] = {0};
+  if (nt > 0 && r->n_kmers > 0) {
+    { gcg_kscope ks (ctx, "route_count");
+      route_count_kernel<<<warp_grid (ctx, nt), 32 * RT_WARPS, 0, ctx->stream>>> (
+          s->d_packed, s->d_woff, s->d_len, s->d_tseq, s->n, s->n_words, k, (uint32_t) n_part, r->tile0, nt, r->d_off); }
+    { gcg_kscope ks (ctx, "route_scan");
+      rows_reduce_kernel<<<dim3 ((unsigned) nb, (unsigned) n_part), PS_BLOCK, 0, ctx->stream>>> (r->d_off, nt, nb, r->d_bsum); }
+    { gcg_kscope ks (ctx, "route_scan");
+      rows_blocksums_kernel<<<n_part, 1024, 0, ctx->stream>>> (r->d_bsum, nb, ctx->d_counters + 16); }
+    { gcg_kscope ks (ctx, "route_scan");
+      rows_apply_kernel<<<dim3 ((unsigned) nb, (unsigned) n_part), PS_BLOCK, 0, ctx->stream>>> (r->d_off, nt, nb, r->d_bsum); }
+    if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_route_plan: kernel launch failed"); rc = GCG_ECUDA; }
+    if (!rc && (cudaMemcpyAsync (ctx->h_counters + 16, ctx->d_counters + 16, (size_t) n_part * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                cudaStreamSynchronize (ctx->stream) != cudaSuccess)) {
+      gcg_set_error ("gcg_route_plan: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; }
+    if (!rc) {
+      int64_t tot = 0;
+      for (int d = 0; d < n_part; ++d) { counts[d] = r->counts[d] = (int64_t) ctx->h_counters[16 + d]; tot += counts[d]; }
+      if (tot != r->n_kmers) { gcg_set_error ("gcg_route_plan: counted %lld k-mers, expected %lld", (long long) tot, (long long) r->n_kmers); rc = GCG_ECUDA; }
+    }
+  }
+  if (!rc) {
+    for (int d = 0; d < n_part; ++d) seg[d + 1] = seg[d] + r->counts[d];
+    // (pageable source: staged by the runtime before the call returns)
+    if (cudaMemcpyAsync (r->d_seg, seg, sizeof seg, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_route_plan: copy failed"); rc = GCG_ECUDA; }
+  }
+  if (rc) { gcg_route_free (r); return rc; }
+  *out = r;
+  return GCG_OK;
+}
+
+extern "C" int64_t gcg_route_kmers (const gcg_route * r) { return r ? r->n_kmers : 0; }
+
+template <int WHAT>
+static int route_scatter (gcg_ctx * ctx, gcg_route * r, void * d_send, const char * name)
+{
+  GCG_CHECK (ctx && r && (d_send || r->n_kmers == 0), GCG_EINVAL, "%s: bad argument", name);
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  if (r->n_kmers == 0) return GCG_OK;
+  const gcg_seqs * s = r->seqs;
+  gcg_kscope ks (ctx, WHAT ? "route_records" : "route_keys");
+  route_scatter_kernel<WHAT><<<warp_grid (ctx, r->n_tiles), 32 * RT_WARPS, 0, ctx->stream>>> (
+      s->d_packed, s->d_woff, s->d_len, s->d_tseq, s->n, s->n_words, r->k, (uint32_t) r->n_part, r->tile0, r->n_tiles,
+      r->d_off, r->d_seg, (unsigned long long *) d_send);
+  GCG_CUDA (cudaGetLastError ());
+  return GCG_OK;
+}
+
+extern "C" int gcg_route_keys (gcg_ctx * ctx, gcg_route * r, void * d_send) { return route_scatter<0> (ctx, r, d_send, "gcg_route_keys"); }
+extern "C" int gcg_route_records (gcg_ctx * ctx, gcg_route * r, void * d_send) { return route_scatter<1> (ctx, r, d_send, "gcg_route_records"); }
+
+extern "C" int gcg_route_collect (gcg_ctx * ctx, gcg_route * r, const void * d_answers, gcg_hits ** out)
+{
+  GCG_CHECK (ctx && r && out && (d_answers || r->n_kmers == 0), GCG_EINVAL, "gcg_route_collect: bad argument");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  gcg_hits * h = new gcg_hits ();
+  h->ctx = ctx;
+  if (r->n_kmers == 0) { *out = h; return GCG_OK; }
+  const gcg_seqs * s = r->seqs;
+  const int64_t n_words = std::min (s->n_words, (r->tile0 + r->n_tiles) << 5) - (r->tile0 << 5);
+  uint32_t * d_mask = nullptr, * d_prefix = nullptr, * d_bsum = nullptr;
+  int rc = GCG_OK;
+  cudaError_t e;
+  if ((e = gcg_dmalloc (ctx, &d_mask, (size_t) n_words * 4)) != cudaSuccess || (e = gcg_dmalloc (ctx, &d_prefix, (size_t) n_words * 4)) != cudaSuccess ||
+      (e = gcg_dmalloc (ctx, &d_bsum, (size_t) gcg_mask_scan_blocks (n_words) * 4)) != cudaSuccess) {
+    gcg_set_error ("gcg_route_collect: cudaMalloc failed: %s", cudaGetErrorString (e));
+    rc = GCG_ENOMEM;
+  }
+  while (!rc) {
+    { gcg_kscope ks (ctx, "route_collect_mask");
+      route_collect_kernel<0><<<warp_grid (ctx, r->n_tiles), 32 * RT_WARPS, 0, ctx->stream>>> (
+          s->d_packed, s->d_woff, s->d_len, s->d_tseq, s->n, s->n_words, r->k, (uint32_t) r->n_part, r->tile0, r->n_tiles,
+          r->d_off, r->d_seg, (const unsigned long long *) d_answers, d_mask, nullptr, nullptr); }
+    if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_route_collect: kernel launch failed"); rc = GCG_ECUDA; break; }
+    int64_t n_hit = 0;
+    if ((rc = gcg_mask_scan (ctx, d_mask, n_words, d_prefix, d_bsum, &n_hit)) != 0) break;
+    h->n = n_hit;
+    if (n_hit > 0) {
+      if ((e = gcg_dmalloc (ctx, &h->d_hits, (size_t) n_hit * sizeof (gcg_hit))) != cudaSuccess) {
+        gcg_set_error ("gcg_route_collect: cudaMalloc of %lld anchors failed: %s", (long long) n_hit, cudaGetErrorString (e));
+        rc = GCG_ENOMEM;
+        break;
+      }
+      { gcg_kscope ks (ctx, "route_collect_emit");
+        route_collect_kernel<1><<<warp_grid (ctx, r->n_tiles), 32 * RT_WARPS, 0, ctx->stream>>> (
+            s->d_packed, s->d_woff, s->d_len, s->d_tseq, s->n, s->n_words, r->k, (uint32_t) r->n_part, r->tile0, r->n_tiles,
+            r->d_off, r->d_seg, (const unsigned long long *) d_answers, d_mask, d_prefix, h->d_hits); }
+      if (cudaGetLastError () != cudaSuccess || cudaStreamSynchronize (ctx->stream) != cudaSuccess) {
+        gcg_set_error ("gcg_route_collect: emit failed: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; }
+    }
+    break;
+  }
+  gcg_dfree (ctx, d_mask); gcg_dfree (ctx, d_prefix); gcg_dfree (ctx, d_bsum);
+  if (rc) { gcg_hits_free (h); return rc; }
+  *out = h;
+  return GCG_OK;
+}
+
+// ---- owner side ------------------------------------------------------------------------------------
+extern "C" int gcg_table_create (gcg_ctx * ctx, int64_t n_records, int k, gcg_table ** out)
+{
+  GCG_CHECK (ctx && out && n_records >= 0, GCG_EINVAL, "gcg_table_create: bad argument");
+  return gcg_table_alloc (ctx, n_records, k, out);
+}
+
+extern "C" int gcg_table_insert_records (gcg_ctx * ctx, gcg_table * t, const void * d_records, int64_t n)
+{
+  GCG_CHECK (ctx && t && n >= 0 && (d_records || n == 0), GCG_EINVAL, "gcg_table_insert_records: bad argument");
+  GCG_CHECK (n <= t->n_inserted, GCG_ERANGE, "gcg_table_insert_records: %lld records into a table created for %lld", (long long) n, (long long) t->n_inserted);
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  if (n == 0) return GCG_OK;
+  gcg_kscope ks (ctx, "part_insert");
+  insert_records_kernel<<<flat_grid (ctx, n, 1), 256, 0, ctx->stream>>> ((const ulonglong2 *) d_records, n, t->d_keys, t->d_vals, t->n_bucket);
+  GCG_CUDA (cudaGetLastError ());
+  return GCG_OK;
+}
+
+extern "C" int gcg_table_lookup_keys (gcg_ctx * ctx, gcg_table * t, const void * d_keys, int64_t n, void * d_answers)
+{
+  GCG_CHECK (ctx && t && n >= 0 && ((d_keys && d_answers) || n == 0), GCG_EINVAL, "gcg_table_lookup_keys: bad argument");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  if (n == 0) return GCG_OK;
+  gcg_kscope ks (ctx, "part_lookup");
+  lookup_keys_kernel<<<flat_grid (ctx, n, LK_UNROLL), 256, 0, ctx->stream>>> (
+      (const unsigned long long *) d_keys, n, t->d_keys, t->d_vals, t->d_ont, t->n_bucket, (unsigned long long *) d_answers);
+  GCG_CUDA (cudaGetLastError ());
+  return GCG_OK;
+}

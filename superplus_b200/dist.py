@@ -1,0 +1,299 @@
+"""Multi-GPU driver of the k-mer path: hash-partitioned contig table with an all-to-all exchange.
+
+SURVEY §8e / BASELINE configs[3].  The reference already partitions its tables — table
+`crc32(kseq) % n_thread` per thread (kmer.c:88,124-152; ont.c:169,193) — and lets every thread
+scan all k-mers for its share.  Here a partition is one GPU (one process per GPU):
+
+  build  : rank r chops its slice of the contig tiles, routes {k-mer, tid, pos, strand} records to
+           their owners (all-to-all, 16 B per contig k-mer), the owner inserts them.
+  search : rank r chops its own read batch, routes the canonical k-mers to their owners
+           (all-to-all, 8 B per ONT k-mer), the owner answers (value word of a k-mer present
+           exactly once, ont.c:171,195 — or a miss) and counts the ONT-side multiplicity
+           (ont.c:245); answers return by the reverse all-to-all (8 B) and are turned into
+           anchors in (read,pos) order.
+  stats  : all-reduce of the four counters of kmer.c:265-312.
+
+The device work is libgcgpu's (`gcg_route_*`, `gcg_table_insert_records`, `gcg_table_lookup_keys`
+through `DeviceOps`); this module is only the orchestration and the collectives
+(`torch.distributed`: NCCL over NVLink on the GPUs, gloo in the CPU tests of the host logic).
+`ops` and `comm` are injected so that the same orchestration runs
+  * one process per GPU under torchrun                     (`DeviceOps` + `TorchComm`, the product),
+  * several partitions in one process on one GPU           (`DeviceOps` + `ThreadComm`, GPU tests),
+  * the CPU tests of the exchange logic                    (a numpy double from tests/ + gloo).
+There is no CPU implementation of the device work in this package.
+"""
+from __future__ import annotations
+
+import contextlib
+import threading
+
+import numpy as np
+import torch
+
+from . import api
+
+MISS = np.uint64(0xFFFFFFFFFFFFFFFF)
+ROUND_KMERS = 1 << 31          # k-mer positions routed per exchange round (the plan's offsets are 32 bit)
+
+
+# ------------------------------------------------------------------------------------------------
+# collectives
+# ------------------------------------------------------------------------------------------------
+class TorchComm:
+    """torch.distributed default group: NCCL with CUDA tensors, gloo with CPU tensors."""
+
+    def __init__(self, device: torch.device):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = device
+        self.bytes_sent = 0           # payload handed to all_to_all by this rank, excluding the self segment
+
+    def empty(self, n_words: int) -> torch.Tensor:
+        return torch.empty(max(int(n_words), 1), dtype=torch.int64, device=self.device)
+
+    def exchange_counts(self, counts: np.ndarray) -> np.ndarray:
+        """counts[p] = elements this rank sends to p  ->  elements this rank receives from p"""
+        send = torch.as_tensor(np.ascontiguousarray(counts, dtype=np.int64)).to(self.device)
+        recv = torch.empty_like(send)
+        self.dist.all_to_all_single(recv, send)
+        return recv.cpu().numpy()
+
+    def all_to_all(self, send: torch.Tensor, send_counts, recv_counts, width: int) -> torch.Tensor:
+        """elements are `width` int64 words; segment p of `send` goes to rank p"""
+        ssz = [int(c) * width for c in send_counts]
+        rsz = [int(c) * width for c in recv_counts]
+        recv = self.empty(sum(rsz))
+        self.dist.all_to_all_single(recv[: sum(rsz)], send[: sum(ssz)], rsz, ssz)
+        self.bytes_sent += 8 * (sum(ssz) - ssz[self.rank])
+        return recv
+
+    def all_reduce(self, values, op: str = "sum") -> np.ndarray:
+        t = torch.as_tensor(np.asarray(values, dtype=np.int64)).to(self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM if op == "sum" else self.dist.ReduceOp.MAX)
+        return t.cpu().numpy()
+
+
+class ThreadGroup:
+    def __init__(self, world: int):
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots = [None] * world
+
+
+class ThreadComm:
+    """`world` partitions driven by `world` threads of one process (GPU tests on a single device;
+    also the shape a single-process multi-GPU host would use).  `sync` must drain the caller's
+    stream: tensors are handed to other threads' streams."""
+
+    def __init__(self, group: ThreadGroup, rank: int, device: torch.device, sync=lambda: None):
+        self.g, self.rank, self.world, self.device, self.sync = group, rank, group.world, device, sync
+        self.bytes_sent = 0
+
+    def empty(self, n_words: int) -> torch.Tensor:
+        return torch.empty(max(int(n_words), 1), dtype=torch.int64, device=self.device)
+
+    def _publish(self, obj):
+        self.sync()
+        self.g.slots[self.rank] = obj
+        self.g.barrier.wait()
+        return list(self.g.slots)
+
+    def _done(self):
+        self.sync()
+        self.g.barrier.wait()
+
+    def exchange_counts(self, counts: np.ndarray) -> np.ndarray:
+        allc = self._publish(np.array(counts, dtype=np.int64))
+        out = np.array([allc[p][self.rank] for p in range(self.world)], dtype=np.int64)
+        self._done()
+        return out
+
+    def all_to_all(self, send: torch.Tensor, send_counts, recv_counts, width: int) -> torch.Tensor:
+        pubs = self._publish((send, [int(c) for c in send_counts]))
+        pieces = []
+        for p in range(self.world):
+            t, cnt = pubs[p]
+            off = sum(cnt[: self.rank]) * width
+            assert cnt[self.rank] == int(recv_counts[p])
+            pieces.append(t[off: off + cnt[self.rank] * width])
+        recv = self.empty(sum(int(c) for c in recv_counts) * width)
+        if pieces:
+            cat = torch.cat(pieces)
+            recv[: cat.numel()] = cat
+        self.bytes_sent += 8 * width * (sum(int(c) for c in send_counts) - int(send_counts[self.rank]))
+        self._done()
+        return recv
+
+    def all_reduce(self, values, op: str = "sum") -> np.ndarray:
+        allv = self._publish(np.asarray(values, dtype=np.int64))
+        out = np.sum(allv, axis=0) if op == "sum" else np.max(allv, axis=0)
+        self._done()
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# device work (the C ABI)
+# ------------------------------------------------------------------------------------------------
+class DeviceOps:
+    """libgcgpu through api.Context; tensors are CUDA int64 tensors whose data_ptr is handed to
+    the library.  All torch work is issued on the library's stream so that kernels, allocator and
+    collectives are ordered without extra events."""
+
+    def __init__(self, ctx: api.Context, device_index: int):
+        self.ctx = ctx
+        self.device = torch.device("cuda", device_index)
+        self._stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=self.device)
+
+    def stream(self):
+        return torch.cuda.stream(self._stream)
+
+    def sync(self):
+        self.ctx.sync()
+
+    def tiles(self, seqs) -> int:
+        return seqs.tiles
+
+    def plan(self, seqs, k, n_part, t0, t1):
+        return self.ctx.route_plan(seqs, k, n_part, t0, t1)
+
+    def route_keys(self, route, t: torch.Tensor):
+        route.keys(t.data_ptr())
+
+    def route_records(self, route, t: torch.Tensor):
+        route.records(t.data_ptr())
+
+    def table_create(self, n, k):
+        return self.ctx.table_create(n, k)
+
+    def insert(self, table, t: torch.Tensor, n: int):
+        table.insert_records(t.data_ptr(), n)
+
+    def lookup(self, table, keys: torch.Tensor, n: int, answers: torch.Tensor):
+        table.lookup_keys(keys.data_ptr(), n, answers.data_ptr())
+
+    def collect(self, route, answers: torch.Tensor):
+        return route.collect(answers.data_ptr())
+
+    def stats(self, table):
+        return table.stats()
+
+
+# ------------------------------------------------------------------------------------------------
+# the partitioned index
+# ------------------------------------------------------------------------------------------------
+def tile_slice(n_tiles: int, rank: int, world: int):
+    """contiguous share of [0, n_tiles) owned by `rank` when `world` ranks split the chop work"""
+    return n_tiles * rank // world, n_tiles * (rank + 1) // world
+
+
+def search_rounds(n_tiles: int, round_kmers: int = ROUND_KMERS):
+    """tile ranges of one rank's read batch, each holding fewer than `round_kmers` positions"""
+    per = max(1, round_kmers // 1024 - 1)
+    return [(a, min(n_tiles, a + per)) for a in range(0, n_tiles, per)] or [(0, 0)]
+
+
+class PartitionedKmerIndex:
+    """contig k-mer table partitioned over comm.world GPUs by hash of the canonical k-mer"""
+
+    def __init__(self, ops, comm, k: int, round_kmers: int = ROUND_KMERS):
+        if not 1 <= comm.world <= api.MAX_PART:
+            raise ValueError("world size %d outside [1,%d]" % (comm.world, api.MAX_PART))
+        self.ops, self.comm, self.k, self.round_kmers = ops, comm, k, round_kmers
+        self.table = None
+        self.n_local_records = 0
+
+    def _stream(self):
+        return self.ops.stream() if hasattr(self.ops, "stream") else contextlib.nullcontext()
+
+    # ---- build: kmer.c:155-213 across ranks ------------------------------------------------------
+    def build(self, contigs) -> "PartitionedKmerIndex":
+        """`contigs`: the full contig set, uploaded on every rank (2 bits per base; the *table* is
+        what is partitioned).  Each rank chops 1/world of the tiles."""
+        ops, comm = self.ops, self.comm
+        with self._stream():
+            t0, t1 = tile_slice(ops.tiles(contigs), comm.rank, comm.world)
+            route = ops.plan(contigs, self.k, comm.world, t0, t1)
+            recv_counts = comm.exchange_counts(route.counts)
+            send = comm.empty(2 * int(route.counts.sum()))
+            ops.route_records(route, send)
+            recv = comm.all_to_all(send, route.counts, recv_counts, width=2)
+            n = int(recv_counts.sum())
+            self.table = ops.table_create(n, self.k)
+            ops.insert(self.table, recv, n)
+            ops.sync()                      # recv/send are released after the inserts ran
+            route.free()
+            self.n_local_records = n
+        return self
+
+    # ---- search: ont.c:141-254 across ranks ------------------------------------------------------
+    def search(self, reads, keep_on_device: bool = False):
+        """anchors of this rank's read batch in (read,pos) order (read = index in `reads`).
+        Every rank must call it (the exchange is collective), with its own batch."""
+        ops, comm = self.ops, self.comm
+        parts, n_total = [], 0
+        with self._stream():
+            rounds = search_rounds(ops.tiles(reads), self.round_kmers)
+            n_rounds = int(comm.all_reduce([len(rounds)], "max")[0])
+            for i in range(n_rounds):
+                t0, t1 = rounds[i] if i < len(rounds) else (0, 0)
+                route = ops.plan(reads, self.k, comm.world, t0, t1)
+                recv_counts = comm.exchange_counts(route.counts)
+                n_send, n_recv = int(route.counts.sum()), int(recv_counts.sum())
+                keys = comm.empty(n_send)
+                ops.route_keys(route, keys)
+                q = comm.all_to_all(keys, route.counts, recv_counts, width=1)
+                a = comm.empty(n_recv)
+                ops.lookup(self.table, q, n_recv, a)
+                answers = comm.all_to_all(a, recv_counts, route.counts, width=1)
+                h = ops.collect(route, answers)
+                ops.sync()
+                route.free()
+                n_total += h.n
+                if keep_on_device:
+                    h.free()
+                else:
+                    parts.append(h.download())
+                    h.free()
+        if keep_on_device:
+            return n_total
+        return np.concatenate(parts) if parts else np.zeros(0, dtype=api.HIT_DTYPE)
+
+    # ---- stats: kmer.c:265-312 -------------------------------------------------------------------
+    def stats(self):
+        with self._stream():
+            return tuple(int(x) for x in self.comm.all_reduce(self.ops.stats(self.table), "sum"))
+
+    def free(self):
+        if self.table is not None:
+            self.table.free()
+            self.table = None
+
+
+def run_threaded(world: int, fn, device: torch.device, make_ops):
+    """run fn(rank, ops, comm) on `world` threads sharing one process (ThreadComm); returns the
+    list of results.  Exceptions are re-raised in the caller."""
+    group = ThreadGroup(world)
+    out, err = [None] * world, [None] * world
+
+    def body(r):
+        try:
+            ops = make_ops(r)
+            comm = ThreadComm(group, r, device, sync=getattr(ops, "sync", lambda: None))
+            out[r] = fn(r, ops, comm)
+        except BaseException as e:          # noqa: BLE001 - reported below
+            err[r] = e
+            group.barrier.abort()
+
+    th = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for e in err:
+        if e is not None and not isinstance(e, threading.BrokenBarrierError):
+            raise e
+    for e in err:
+        if e is not None:
+            raise e
+    return out
