@@ -277,6 +277,41 @@ def run_ours(args, rank, local_rank, world):
     kprof = ctx.prof_report()
     kmer_launches = ctx.launches() - launches0
 
+    # ---- hash-partitioned table (BASELINE configs[3] / SURVEY 8e): same step, the table split over the
+    #      ranks by hash of the canonical k-mer, records / keys / answers exchanged by all-to-all
+    part = None
+    if world > 1 or args.partitioned:
+        from superplus_b200 import dist as gdist
+        ops = gdist.DeviceOps(ctx, local_rank)
+        comm = gdist.TorchComm(ops.device) if dist is not None else gdist.ThreadComm(gdist.ThreadGroup(1), 0, ops.device, ops.sync)
+
+        def part_step():
+            cs = ctx.pack(a_ctg)
+            rs = ctx.pack(a_reads)
+            idx = gdist.PartitionedKmerIndex(ops, comm, K).build(cs)
+            nh = idx.search(rs, keep_on_device=True)
+            st4 = idx.stats()
+            idx.free(); cs.free(); rs.free()
+            return nh, st4
+
+        for _ in range(args.warmup):
+            p_hit, p_st = part_step()
+        ctx.prof_reset()
+        sent0, pl0 = comm.bytes_sent, ctx.launches()
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for _ in range(args.steps):
+            p_hit, p_st = part_step()
+        p1.record(stream)
+        barrier()
+        part_ms = allmax(p0.elapsed_time(p1)) / args.steps
+        pprof = ctx.prof_report()
+        assert p_hit == n_hit, "partitioned and replicated tables disagree on this rank's anchors"
+        part = {"ms_per_step": part_ms, "launches": ctx.launches() - pl0, "stats": list(p_st),
+                "bytes_sent_per_step": allsum(float(comm.bytes_sent - sent0)) / args.steps,
+                "kernel_ms_per_step": {k_: v[0] / args.steps for k_, v in sorted(pprof.items())}}
+
     # ---- timed: SW steps
     ctx.prof_reset()
     launches1 = ctx.launches()
@@ -419,6 +454,13 @@ def run_ours(args, rank, local_rank, world):
                 line["cpu_baseline"] = {"value": None, "unit": "k-mers/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref not built"}
         except Exception as e:      # the baseline must never sink the bench line
             line["cpu_baseline"] = {"value": None, "unit": "k-mers/s", "cores": cores, "kind": "reference", "sample": "failed: %r" % (e,)}
+    if part is not None:
+        line["partitioned"] = {
+            "metric": "kmers_per_s", "value": tot_ont_kmers / (part["ms_per_step"] * 1e-3), "unit": "k-mers/s", "ms_per_step": part["ms_per_step"],
+            "config": {"workload": "same step with the contig table hash-partitioned over %d GPU(s): route + all-to-all (16 B per contig k-mer, 8 B key out and 8 B answer back per ONT k-mer) + owner-side insert / lookup + ordered collect" % world,
+                       "collective": ("NCCL all_to_all_single over NVLink" if world > 1 else "single partition, no exchange")},
+            "nvlink_bytes_per_step": part["bytes_sent_per_step"], "stats": part["stats"], "kernel_ms_per_step": part["kernel_ms_per_step"]}
+        line["gpu_launches"] += int(part["launches"])
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -432,6 +474,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sw-pairs", type=int, default=11840)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--partitioned", action="store_true", help="also time the hash-partitioned table at N=1 (always timed at N>1)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                      # timing rule: at least three warm-up steps
