@@ -9,6 +9,7 @@
 #include <thread>
 
 #include "gcg_internal.cuh"
+#include "host_par.h"
 
 static thread_local char g_err[1024] = "";
 
@@ -51,6 +52,7 @@ extern "C" int gcg_init (int device, gcg_ctx ** out)
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->trace = getenv ("GCG_TRACE") != nullptr;
+  if (const char * e = getenv ("GCG_DEVICE_CACHE_MB")) ctx->dparked_limit = (size_t) atoll (e) << 20;
   GCG_CUDA (cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking));
   {
     // keep freed blocks in the stream-ordered pool instead of returning them to the driver
@@ -77,6 +79,9 @@ extern "C" void gcg_destroy (gcg_ctx * ctx)
     if (ctx->stage.d[i]) cudaFree (ctx->stage.d[i]);
     if (ctx->stage.ev[i]) cudaEventDestroy (ctx->stage.ev[i]);
   }
+  gcg_pipe_free (ctx);
+  gcg_workers_destroy (ctx->workers);
+  gcg_dcache_release (ctx);
   cudaFree (ctx->d_counters);
   cudaFreeHost (ctx->h_counters);
   cudaStreamDestroy (ctx->stream);
@@ -87,7 +92,9 @@ extern "C" void gcg_destroy (gcg_ctx * ctx)
 extern "C" int gcg_set_host_threads (gcg_ctx * ctx, int n_thread)
 {
   GCG_CHECK (ctx && n_thread >= 1, GCG_EINVAL, "gcg_set_host_threads: bad argument");
-  ctx->host_threads = n_thread > 64 ? 64 : n_thread;
+  n_thread = n_thread > 64 ? 64 : n_thread;
+  if (n_thread != ctx->host_threads && ctx->workers) { gcg_workers_destroy (ctx->workers); ctx->workers = nullptr; }
+  ctx->host_threads = n_thread;
   return GCG_OK;
 }
 
@@ -163,6 +170,69 @@ int gcg_stage_reserve (gcg_ctx * ctx)
   return GCG_OK;
 }
 
+// ---- device block cache ------------------------------------------------------------------------
+static size_t size_class (size_t bytes)
+{
+  if (bytes < 4096) return 4096;
+  int lg = 63 - __builtin_clzll ((unsigned long long) bytes);
+  size_t step = (size_t) 1 << (lg - 3);                 // eight classes per octave: at most 12.5 % slack
+  return (bytes + step - 1) & ~(step - 1);
+}
+
+void gcg_dcache_release (gcg_ctx * ctx)
+{
+  for (auto & kv : ctx->dparked)
+    for (void * p : kv.second) { ctx->dclass.erase (p); cudaFreeAsync (p, ctx->stream); }
+  ctx->dparked.clear ();
+  ctx->dparked_bytes = 0;
+}
+
+cudaError_t gcg_dmalloc_bytes (gcg_ctx * ctx, void ** p, size_t bytes)
+{
+  const size_t cls = size_class (bytes);
+  auto it = ctx->dparked.find (cls);
+  if (it != ctx->dparked.end () && !it->second.empty ()) {
+    *p = it->second.back ();
+    it->second.pop_back ();
+    ctx->dparked_bytes -= cls;
+    return cudaSuccess;
+  }
+  cudaError_t e = cudaMallocAsync (p, cls, ctx->stream);
+  if (e != cudaSuccess) {
+    // out of memory with blocks parked: give them back and try once more
+    cudaGetLastError ();
+    gcg_dcache_release (ctx);
+    cudaStreamSynchronize (ctx->stream);
+    e = cudaMallocAsync (p, cls, ctx->stream);
+  }
+  if (e == cudaSuccess) ctx->dclass[*p] = cls;
+  return e;
+}
+
+void gcg_dfree (gcg_ctx * ctx, void * p)
+{
+  if (!p) return;
+  auto it = ctx->dclass.find (p);
+  if (it == ctx->dclass.end ()) { cudaFreeAsync (p, ctx->stream); return; }
+  const size_t cls = it->second;
+  if (cls > ctx->dparked_limit / 2) {                    // e.g. the 64 GB trace of an SW batch: never parked
+    ctx->dclass.erase (it);
+    cudaFreeAsync (p, ctx->stream);
+    return;
+  }
+  ctx->dparked[cls].push_back (p);
+  ctx->dparked_bytes += cls;
+  while (ctx->dparked_bytes > ctx->dparked_limit && !ctx->dparked.empty ()) {
+    auto big = std::prev (ctx->dparked.end ());             // drop the largest parked blocks first
+    if (big->second.empty ()) { ctx->dparked.erase (big); continue; }
+    void * q = big->second.back ();
+    big->second.pop_back ();
+    ctx->dparked_bytes -= big->first;
+    ctx->dclass.erase (q);
+    cudaFreeAsync (q, ctx->stream);
+  }
+}
+
 // ---- pinned result buffers ---------------------------------------------------------------------
 // Results handed to the caller (anchor lists, CIGAR pools) live in page-locked host memory.
 // Pinning costs far more than the copy it serves (tens of ms per 100 MB), so blocks released with
@@ -222,15 +292,19 @@ void gcg_trace_mark (gcg_ctx * ctx, const char * label)
   g_trace_t0 = now;
 }
 
+gcg_workers * gcg_ctx_workers (gcg_ctx * ctx)
+{
+  if (!ctx->workers) ctx->workers = gcg_workers_create (ctx->host_threads);
+  return ctx->workers;
+}
+
 void gcg_par_memcpy (gcg_ctx * ctx, void * dst, const void * src, size_t bytes)
 {
   int nt = ctx ? ctx->host_threads : 1;
   if (bytes < ((size_t) 4 << 20) || nt <= 1) { memcpy (dst, src, bytes); return; }
-  std::vector<std::thread> th;
-  for (int t = 0; t < nt; ++t) {
+  gcg_workers_run (gcg_ctx_workers (ctx), nt, [=] (int64_t t) {
     size_t a = bytes * (size_t) t / (size_t) nt, b = bytes * (size_t) (t + 1) / (size_t) nt;
     a &= ~(size_t) 63; if (t + 1 < nt) b &= ~(size_t) 63;
-    th.emplace_back ([=] () { memcpy ((char *) dst + a, (const char *) src + a, b - a); });
-  }
-  for (auto & t : th) t.join ();
+    memcpy ((char *) dst + a, (const char *) src + a, b - a);
+  });
 }

@@ -6,6 +6,7 @@
 
 #include <map>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -43,6 +44,9 @@ struct gcg_stage {
   size_t cap = 0;
 };
 
+struct gcg_workers;
+struct gcg_pipe;
+
 struct gcg_ctx {
   int device = 0;
   int sm_count = 148;
@@ -53,9 +57,15 @@ struct gcg_ctx {
   std::map<std::string, gcg_prof_entry> prof_map;
   int64_t launches = 0;
   gcg_stage stage;
+  gcg_workers * workers = nullptr;   // persistent host threads (staging gather, back copies)
+  gcg_pipe * pipe = nullptr;         // slots and side streams of the streaming host-buffer search
   // small device scratch for reductions / counters
   unsigned long long * d_counters = nullptr;   // 64 x u64 ([16..48) = per-partition totals of gcg_route_plan)
   unsigned long long * h_counters = nullptr;   // pinned mirror
+  // parked device blocks by size class (see gcg_dmalloc)
+  std::map<size_t, std::vector<void *>> dparked;
+  std::unordered_map<void *, size_t> dclass;   // every block handed out or parked -> its class size
+  size_t dparked_bytes = 0, dparked_limit = (size_t) 24 << 30;
 };
 
 // RAII scope around one kernel launch: counts it and, when profiling is on, brackets it
@@ -140,6 +150,8 @@ struct gcg_hits {
 #define GCG_KEY_MULTI 0x8000000000000000ULL
 
 int gcg_stage_reserve (gcg_ctx * ctx);
+gcg_workers * gcg_ctx_workers (gcg_ctx * ctx);   // created on first use with ctx->host_threads threads
+void gcg_pipe_free (gcg_ctx * ctx);
 int gcg_table_alloc (gcg_ctx * ctx, int64_t n_kmers, int k, gcg_table ** out);
 int64_t gcg_mask_scan_blocks (int64_t n_words);
 int gcg_mask_scan (gcg_ctx * ctx, const uint32_t * d_mask, int64_t n_words, uint32_t * d_prefix, uint32_t * d_bsum, int64_t * total);
@@ -148,17 +160,16 @@ void gcg_pinned_trim (void);
 void gcg_trace_mark (gcg_ctx * ctx, const char * label);   // label == NULL restarts the clock
 void gcg_par_memcpy (gcg_ctx * ctx, void * dst, const void * src, size_t bytes);   // memcpy over the ctx's host threads
 
-// stream-ordered device allocations from the context's pool: no device synchronisation, freed
-// blocks are reused by the next call (the pool never trims, see gcg_init)
-static inline cudaError_t gcg_dmalloc (gcg_ctx * ctx, void ** p, size_t bytes)
-{
-  return cudaMallocAsync (p, bytes ? bytes : 16, ctx->stream);
-}
+// Device allocations of a context.  Blocks come from the stream-ordered pool (cudaMallocAsync on
+// the ctx stream) but are PARKED in the context on gcg_dfree and handed out again to the next
+// request of the same size class: the driver pool's own reuse is unpredictable for the 10-100 MB
+// scratch blocks of a search (measured 0.01 .. 360 ms per cudaMallocAsync).  Reuse is safe without
+// events because every kernel of a context runs on its one stream, in order.
+cudaError_t gcg_dmalloc_bytes (gcg_ctx * ctx, void ** p, size_t bytes);
+void gcg_dfree (gcg_ctx * ctx, void * p);
+void gcg_dcache_release (gcg_ctx * ctx);      // return every parked block to the driver
+static inline cudaError_t gcg_dmalloc (gcg_ctx * ctx, void ** p, size_t bytes) { return gcg_dmalloc_bytes (ctx, p, bytes); }
 template <class T> static inline cudaError_t gcg_dmalloc (gcg_ctx * ctx, T ** p, size_t bytes)
 {
-  return gcg_dmalloc (ctx, (void **) p, bytes);
-}
-static inline void gcg_dfree (gcg_ctx * ctx, void * p)
-{
-  if (p) cudaFreeAsync (p, ctx->stream);
+  return gcg_dmalloc_bytes (ctx, (void **) p, bytes);
 }

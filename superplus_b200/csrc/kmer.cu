@@ -13,9 +13,12 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <chrono>
+#include <functional>
 #include <thread>
 
 #include "gcg_internal.cuh"
+#include "host_par.h"
 #include "kmer_dev.cuh"
 
 // =============================================================================================
@@ -242,7 +245,8 @@ __global__ void __launch_bounds__ (256)
 hits_emit_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff, const int32_t * __restrict__ tile_seq,
                   int64_t n_seq, int64_t n_words, int k, const unsigned long long * __restrict__ keys,
                   const unsigned long long * __restrict__ vals, uint32_t * __restrict__ ont, uint32_t n_bucket,
-                  const uint32_t * __restrict__ mask, const uint32_t * __restrict__ prefix, gcg_hit * __restrict__ out)
+                  const uint32_t * __restrict__ mask, const uint32_t * __restrict__ prefix, int32_t read_base,
+                  gcg_hit * __restrict__ out)
 {
   __shared__ uint32_t s_excl[8][33];
   __shared__ uint32_t s_mask[8][32];
@@ -284,7 +288,7 @@ hits_emit_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
         if (((old >> sh) & 3u) == 1u) atomicOr (ont + (slot >> 4), 2u << sh);
       }
       int4 hh;                                      // gcg_hit {read, pos, tid, cpos_flags} as one 16-byte store
-      hh.x = (int32_t) s;
+      hh.x = (int32_t) s + read_base;
       hh.y = p0 + j;
       hh.z = (int32_t) ((v >> 32) & 0x7FFFFFFFu);
       hh.w = (int32_t) ((((uint32_t) (v >> 1) & 0x3FFFFFFFu) << 2) | (uint32_t) (v & 1ULL) | (fw ? 0u : 2u));
@@ -441,7 +445,7 @@ static void gather_range (const seq_src & src, const std::vector<int64_t> & woff
     int64_t b0 = sw0 * 32, b1 = b0 + l;                 // byte range of the sequence in the flat layout
     int64_t c0 = std::max (b0, w0 * 32), c1 = std::min (b1, w1 * 32);
     if (c1 <= c0) continue;
-    memcpy (dst + (c0 - w0 * 32), src.at (s) + (c0 - b0), (size_t) (c1 - c0));
+    gcg_copy_stream (dst + (c0 - w0 * 32), src.at (s) + (c0 - b0), (size_t) (c1 - c0));
   }
 }
 
@@ -455,12 +459,18 @@ static int stream_ascii (gcg_ctx * ctx, const seq_src & src, const std::vector<i
   if (rc) return rc;
   const int64_t chunk_words = (int64_t) (ctx->stage.cap / 32);
   int64_t s_lo = 0;
+  double t_wait = 0, t_gather = 0;
+  auto now = [] () { return std::chrono::steady_clock::now (); };
+  auto ms = [] (std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli> (b - a).count (); };
   for (int64_t w0 = 0; w0 < n_words; w0 += chunk_words) {
     int64_t w1 = std::min (n_words, w0 + chunk_words);
     int slot = ctx->stage.next;
     ctx->stage.next ^= 1;
     // the pinned slot may still feed a copy enqueued by an earlier call on this context
+    auto t0 = now ();
     if (ctx->stage.busy[slot]) { GCG_CUDA (cudaEventSynchronize (ctx->stage.ev[slot])); ctx->stage.busy[slot] = false; }
+    auto t1 = now ();
+    t_wait += ms (t0, t1);
     // sequences overlapping [w0,w1)
     while (s_lo + 1 < n && woff[(size_t) s_lo + 1] <= w0) ++s_lo;
     int64_t s_hi = std::upper_bound (woff.begin () + s_lo, woff.begin () + n, w1 - 1) - woff.begin ();
@@ -471,19 +481,22 @@ static int stream_ascii (gcg_ctx * ctx, const seq_src & src, const std::vector<i
     if ((w1 - w0) * 32 < (1 << 20) || ns < 2 * nt) nt = 1;
     if (nt <= 1) gather_range (src, woff, len, s_lo, s_hi, w0, w1, dst);
     else {
-      std::vector<std::thread> th;
-      for (int t = 0; t < nt; ++t) {
-        int64_t a = s_lo + ns * t / nt, b = s_lo + ns * (t + 1) / nt;
-        th.emplace_back ([&, a, b] () { gather_range (src, woff, len, a, b, w0, w1, dst); });
-      }
-      for (auto & t : th) t.join ();
+      const int64_t n_task = std::min<int64_t> (ns, 4 * nt);
+      gcg_workers_run (gcg_ctx_workers (ctx), n_task, [&] (int64_t t) {
+        gather_range (src, woff, len, s_lo + ns * t / n_task, s_lo + ns * (t + 1) / n_task, w0, w1, dst);
+        gcg_copy_fence ();
+      });
     }
+    gcg_copy_fence ();
+    t_gather += ms (t1, now ());
     GCG_CUDA (cudaMemcpyAsync (ctx->stage.d[slot], dst, (size_t) (w1 - w0) * 32, cudaMemcpyHostToDevice, ctx->stream));
     rc = consume (ctx->stage.d[slot], w0, w1 - w0);
     if (rc) return rc;
     GCG_CUDA (cudaEventRecord (ctx->stage.ev[slot], ctx->stream));
     ctx->stage.busy[slot] = true;
   }
+  if (ctx->trace && n_words * 32 > (1 << 20))
+    fprintf (stderr, "[gcg]   staging %.1f MB: host gather %.3f ms (%d threads), waits on the ring %.3f ms\n", n_words * 32 / 1e6, t_gather, ctx->host_threads, t_wait);
   return GCG_OK;
 }
 
@@ -731,16 +744,25 @@ extern "C" int gcg_table_dump (gcg_ctx * ctx, gcg_table * t, int64_t cap, uint64
 // (n_words + SCAN_TILE - 1) / SCAN_TILE words of scratch.  Synchronises the stream.
 int64_t gcg_mask_scan_blocks (int64_t n_words) { return (n_words + SCAN_TILE - 1) / SCAN_TILE; }
 
-int gcg_mask_scan (gcg_ctx * ctx, const uint32_t * d_mask, int64_t n_words, uint32_t * d_prefix, uint32_t * d_bsum, int64_t * total)
+// launches only: the total lands in *d_total (device, 8 bytes)
+static int mask_scan_launch (gcg_ctx * ctx, const uint32_t * d_mask, int64_t n_words, uint32_t * d_prefix, uint32_t * d_bsum,
+                             unsigned long long * d_total)
 {
   int64_t nb = gcg_mask_scan_blocks (n_words);
   { gcg_kscope ks (ctx, "scan_reduce");
     scan_reduce_kernel<<<(unsigned) nb, SCAN_BLOCK, 0, ctx->stream>>> (d_mask, n_words, d_bsum); }
   { gcg_kscope ks (ctx, "scan_blocksums");
-    scan_blocksums_kernel<<<1, 1024, 0, ctx->stream>>> (d_bsum, nb, ctx->d_counters + 4); }
+    scan_blocksums_kernel<<<1, 1024, 0, ctx->stream>>> (d_bsum, nb, d_total); }
   { gcg_kscope ks (ctx, "scan_apply");
     scan_apply_kernel<<<(unsigned) nb, SCAN_BLOCK, 0, ctx->stream>>> (d_mask, n_words, d_bsum, d_prefix); }
   GCG_CUDA (cudaGetLastError ());
+  return GCG_OK;
+}
+
+int gcg_mask_scan (gcg_ctx * ctx, const uint32_t * d_mask, int64_t n_words, uint32_t * d_prefix, uint32_t * d_bsum, int64_t * total)
+{
+  int rc = mask_scan_launch (ctx, d_mask, n_words, d_prefix, d_bsum, ctx->d_counters + 4);
+  if (rc) return rc;
   GCG_CUDA (cudaMemcpyAsync (ctx->h_counters + 4, ctx->d_counters + 4, 8, cudaMemcpyDeviceToHost, ctx->stream));
   GCG_CUDA (cudaStreamSynchronize (ctx->stream));
   *total = (int64_t) ctx->h_counters[4];
@@ -788,7 +810,9 @@ extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * r
           reads->d_packed, reads->d_woff, reads->d_len, reads->d_tseq, reads->n, n_words, k, t->d_keys, t->n_bucket, d_mask); }
     if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_search: kernel launch failed"); rc = GCG_ECUDA; break; }
     int64_t n_hit = 0;
+    gcg_trace_mark (ctx, "  search_seqs: alloc + launch");
     if ((rc = gcg_mask_scan (ctx, d_mask, n_words, d_prefix, d_bsum, &n_hit)) != 0) break;
+    gcg_trace_mark (ctx, "  search_seqs: probe + scan");
     h->n = n_hit;
     if (n_hit > 0) {
       if ((e = gcg_dmalloc (ctx, &h->d_hits, (size_t) n_hit * sizeof (gcg_hit))) != cudaSuccess) {
@@ -798,9 +822,11 @@ extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * r
       }
       { gcg_kscope ks (ctx, "hits_emit");
         hits_emit_kernel<<<grid_for (ctx, ((n_words + 31) >> 5) * 32, 256, 8), 256, 0, ctx->stream>>> (
-            reads->d_packed, reads->d_woff, reads->d_tseq, reads->n, n_words, k, t->d_keys, t->d_vals, t->d_ont, t->n_bucket, d_mask, d_prefix, h->d_hits); }
+            reads->d_packed, reads->d_woff, reads->d_tseq, reads->n, n_words, k, t->d_keys, t->d_vals, t->d_ont, t->n_bucket, d_mask, d_prefix, 0, h->d_hits); }
+      gcg_trace_mark (ctx, "  search_seqs: hits alloc");
       if (cudaGetLastError () != cudaSuccess || cudaStreamSynchronize (ctx->stream) != cudaSuccess) {
         gcg_set_error ("gcg_search: emit failed: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; }
+      gcg_trace_mark (ctx, "  search_seqs: emit");
     }
     break;
   }
@@ -821,62 +847,288 @@ extern "C" int gcg_hits_download (gcg_ctx * ctx, const gcg_hits * h, gcg_hit * d
   return GCG_OK;
 }
 
-// Host-buffer search.  Read sets with more than 2^31 k-mer start positions (cfg5: 5 G) are cut
-// into consecutive groups of whole reads; every group is uploaded, searched and its anchors are
-// appended (read indices shifted back to the caller's numbering), so the result is still in
-// (read,pos) order.  The ONT multiplicity state accumulates in the table across the groups.
+// ---- host-buffer search: a three-stage stream pipeline ------------------------------------------
+// The reads are cut into chunks of whole reads (16 MiB of bases by default).  For chunk c
+//   host      gathers the reads into a pinned slot (worker pool, streaming stores)
+//   `up`      copies slot -> HBM                                     (PCIe, host -> device)
+//   ctx->stream packs, probes, scans and emits the chunk's anchors into the slot's device buffer
+//   `down`    copies the anchors to their final place in the pinned result     (PCIe, device -> host)
+// so the gather, both PCIe directions and the kernels of neighbouring chunks overlap; the only
+// host wait per chunk is for the anchor count of the PREVIOUS chunk (needed to place its copy).
+// Chunks hold far fewer than 2^32 positions, so any read set size works (cfg5: 5 G positions);
+// anchors come out in (read,pos) order because chunks are consecutive and copies are placed by
+// running offset.  The ONT multiplicity state accumulates in the table across chunks.
+#define PIPE_SLOTS 5
+#define PIPE_LAG 2          // chunks between a submit and the host looking at its anchor count
+
+struct pipe_slot {
+  char * h_ascii = nullptr, * d_ascii = nullptr;     // cap_words * 32 bytes
+  char * h_meta = nullptr, * d_meta = nullptr;       // woff | len | tile_seq of the chunk
+  uint64_t * d_packed = nullptr;
+  uint32_t * d_mask = nullptr, * d_prefix = nullptr, * d_bsum = nullptr;
+  unsigned long long * d_count = nullptr;
+  gcg_hit * d_hits = nullptr;                        // cap_words * 32 anchors (every position could anchor)
+  cudaEvent_t ev_up = nullptr, ev_count = nullptr, ev_emit = nullptr, ev_free = nullptr;
+  bool busy = false, pending = false;                // ev_free recorded / chunk waiting for its download
+  int64_t first_read = 0;
+};
+
+struct gcg_pipe {
+  int64_t cap_words = 0;
+  size_t meta_cap = 0;
+  cudaStream_t up = nullptr, down = nullptr;
+  pipe_slot s[PIPE_SLOTS];
+  unsigned long long * h_count = nullptr;            // pinned, one per slot
+  int64_t last_total = 0;                            // anchors of the previous call: sizes the next result buffer
+};
+
+void gcg_pipe_free (gcg_ctx * ctx)
+{
+  gcg_pipe * p = ctx->pipe;
+  if (!p) return;
+  if (p->up) cudaStreamSynchronize (p->up);
+  if (p->down) cudaStreamSynchronize (p->down);
+  for (pipe_slot & q : p->s) {
+    if (q.h_ascii) cudaFreeHost (q.h_ascii);
+    if (q.h_meta) cudaFreeHost (q.h_meta);
+    cudaFree (q.d_ascii); cudaFree (q.d_meta); cudaFree (q.d_packed); cudaFree (q.d_mask); cudaFree (q.d_prefix);
+    cudaFree (q.d_bsum); cudaFree (q.d_count); cudaFree (q.d_hits);
+    for (cudaEvent_t e : {q.ev_up, q.ev_count, q.ev_emit, q.ev_free}) if (e) cudaEventDestroy (e);
+  }
+  if (p->h_count) cudaFreeHost (p->h_count);
+  if (p->up) cudaStreamDestroy (p->up);
+  if (p->down) cudaStreamDestroy (p->down);
+  delete p;
+  ctx->pipe = nullptr;
+}
+
+static int pipe_reserve (gcg_ctx * ctx, int64_t cap_words)
+{
+  if (ctx->pipe && ctx->pipe->cap_words >= cap_words) return GCG_OK;
+  GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+  gcg_pipe_free (ctx);
+  gcg_pipe * p = new gcg_pipe ();
+  ctx->pipe = p;
+  p->cap_words = cap_words;
+  p->meta_cap = (size_t) 8 << 20;
+  const size_t tiles = (size_t) ((cap_words + 31) >> 5);
+  if (p->meta_cap < tiles * 4 + (1 << 20)) p->meta_cap = tiles * 4 + (1 << 20);
+  GCG_CUDA (cudaStreamCreateWithFlags (&p->up, cudaStreamNonBlocking));
+  GCG_CUDA (cudaStreamCreateWithFlags (&p->down, cudaStreamNonBlocking));
+  GCG_CUDA (cudaHostAlloc (&p->h_count, PIPE_SLOTS * sizeof (unsigned long long), cudaHostAllocDefault));
+  for (pipe_slot & q : p->s) {
+    GCG_CUDA (cudaHostAlloc (&q.h_ascii, (size_t) cap_words * 32, cudaHostAllocDefault));
+    GCG_CUDA (cudaHostAlloc (&q.h_meta, p->meta_cap, cudaHostAllocDefault));
+    GCG_CUDA (cudaMalloc (&q.d_ascii, (size_t) cap_words * 32));
+    GCG_CUDA (cudaMalloc (&q.d_meta, p->meta_cap));
+    GCG_CUDA (cudaMalloc (&q.d_packed, (size_t) (cap_words + 2) * 8));
+    GCG_CUDA (cudaMalloc (&q.d_mask, (size_t) cap_words * 4));
+    GCG_CUDA (cudaMalloc (&q.d_prefix, (size_t) cap_words * 4));
+    GCG_CUDA (cudaMalloc (&q.d_bsum, (size_t) gcg_mask_scan_blocks (cap_words) * 4));
+    GCG_CUDA (cudaMalloc (&q.d_count, 8));
+    GCG_CUDA (cudaMalloc (&q.d_hits, (size_t) cap_words * 32 * sizeof (gcg_hit)));
+    GCG_CUDA (cudaMemset (q.d_packed, 0, (size_t) (cap_words + 2) * 8));
+    for (cudaEvent_t * e : {&q.ev_up, &q.ev_count, &q.ev_emit, &q.ev_free}) GCG_CUDA (cudaEventCreateWithFlags (e, cudaEventDisableTiming));
+  }
+  return GCG_OK;
+}
+
+struct search_result {
+  gcg_ctx * ctx;
+  gcg_hit * buf = nullptr;
+  int64_t cap = 0, n = 0;
+};
+
+// place the anchors of the chunk in slot `q` behind the ones already placed
+static int pipe_download (gcg_ctx * ctx, pipe_slot & q, int slot, search_result & res)
+{
+  gcg_pipe * p = ctx->pipe;
+  GCG_CUDA (cudaEventSynchronize (q.ev_count));
+  const int64_t n = (int64_t) p->h_count[slot];
+  if (res.n + n > res.cap) {
+    // estimate too small: move what is there into a larger block (the copies in flight target the old one)
+    GCG_CUDA (cudaStreamSynchronize (p->down));
+    int64_t ncap = std::max<int64_t> (res.cap * 2, res.n + n + (res.n + n) / 4);
+    gcg_hit * nb = (gcg_hit *) gcg_pinned_alloc ((size_t) ncap * sizeof (gcg_hit));
+    GCG_CHECK (nb != nullptr, GCG_ENOMEM, "gcg_search: pinned alloc of %lld anchors failed", (long long) ncap);
+    if (res.n) gcg_par_memcpy (ctx, nb, res.buf, (size_t) res.n * sizeof (gcg_hit));
+    gcg_free (res.buf);
+    res.buf = nb; res.cap = ncap;
+  }
+  GCG_CUDA (cudaStreamWaitEvent (p->down, q.ev_emit, 0));
+  if (n > 0) GCG_CUDA (cudaMemcpyAsync (res.buf + res.n, q.d_hits, (size_t) n * sizeof (gcg_hit), cudaMemcpyDeviceToHost, p->down));
+  GCG_CUDA (cudaEventRecord (q.ev_free, p->down));
+  q.busy = true; q.pending = false;
+  res.n += n;
+  return GCG_OK;
+}
+
 extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
                            int64_t n_read, int k, gcg_hit ** hits_out, int64_t * n_hit)
 {
   GCG_CHECK (ctx && t && hits_out && n_hit && n_read >= 0 && (n_read == 0 || (read_seq && read_len)), GCG_EINVAL, "gcg_search: bad argument");
+  GCG_CHECK (k == t->k, GCG_EINVAL, "gcg_search: k=%d but the table was built with k=%d", k, t->k);
+  GCG_CHECK (n_read < 0x7FFFFFFF, GCG_ERANGE, "gcg_search: too many reads");
   *hits_out = nullptr;
   *n_hit = 0;
-  int64_t group_limit = (int64_t) 1 << 31;
-  if (const char * e = getenv ("GCG_SEARCH_GROUP_KMERS")) group_limit = std::max<int64_t> (1, atoll (e));
-  std::vector<std::pair<int64_t, int64_t>> groups;       // [first read, last read)
-  int64_t g0 = 0, acc = 0;
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  gcg_trace_mark (ctx, nullptr);
+  int64_t chunk_words = ((int64_t) 16 << 20) / 32, max_words = 0, total_kmers = 0;
+  if (const char * e = getenv ("GCG_SEARCH_CHUNK_BYTES")) chunk_words = std::max<int64_t> (1, atoll (e) / 32);
   for (int64_t r = 0; r < n_read; ++r) {
-    int64_t kk = read_len[r] >= k ? (int64_t) read_len[r] - k + 1 : 0;
-    if (acc + kk > group_limit && r > g0) { groups.emplace_back (g0, r); g0 = r; acc = 0; }
-    acc += kk;
+    GCG_CHECK (read_len[r] >= 0, GCG_ERANGE, "gcg_search: read %lld has a negative length", (long long) r);
+    max_words = std::max<int64_t> (max_words, ((int64_t) read_len[r] + 31) >> 5);
+    if (read_len[r] >= k) total_kmers += (int64_t) read_len[r] - k + 1;
   }
-  groups.emplace_back (g0, n_read);
+  if (total_kmers == 0) return GCG_OK;
+  int rc = pipe_reserve (ctx, std::max (chunk_words, max_words));
+  if (rc) return rc;
+  gcg_pipe * p = ctx->pipe;
+  const int64_t cap_words = std::max (chunk_words, max_words);       // <= p->cap_words
 
-  std::vector<gcg_hits *> parts;
-  int64_t total = 0;
-  int rc = GCG_OK;
-  for (auto & g : groups) {
-    gcg_seqs * s = nullptr;
-    gcg_hits * h = nullptr;
-    gcg_trace_mark (ctx, nullptr);
-    rc = gcg_seqs_upload (ctx, read_seq + g.first, read_len + g.first, g.second - g.first, &s);
-    gcg_trace_mark (ctx, "search: reads to HBM + pack");
-    if (!rc) rc = gcg_search_seqs (ctx, t, s, k, &h);
-    gcg_trace_mark (ctx, "search: probe + emit");
-    gcg_seqs_free (s);
-    if (rc) break;
-    parts.push_back (h);
-    total += h->n;
-  }
-  if (!rc && total > 0) {
-    *hits_out = (gcg_hit *) gcg_pinned_alloc ((size_t) total * sizeof (gcg_hit));
-    if (!*hits_out) { gcg_set_error ("gcg_search: pinned alloc of %lld anchors failed", (long long) total); rc = GCG_ENOMEM; }
-    gcg_trace_mark (ctx, "search: pinned result");
-    int64_t at = 0;
-    for (size_t gi = 0; gi < parts.size () && !rc; ++gi) {
-      rc = gcg_hits_download (ctx, parts[gi], *hits_out + at, parts[gi]->n);
-      if (!rc && groups[gi].first != 0) {
-        int32_t shift = (int32_t) groups[gi].first;
-        for (int64_t i = 0; i < parts[gi]->n; ++i) (*hits_out)[at + i].read += shift;
-      }
-      at += parts[gi]->n;
+  search_result res;
+  res.ctx = ctx;
+  res.cap = std::max<int64_t> (p->last_total + p->last_total / 8, total_kmers / 16) + 4096;
+  res.buf = (gcg_hit *) gcg_pinned_alloc ((size_t) res.cap * sizeof (gcg_hit));
+  GCG_CHECK (res.buf != nullptr, GCG_ENOMEM, "gcg_search: pinned alloc of %lld anchors failed", (long long) res.cap);
+
+  // work on ctx->stream enqueued by earlier calls (the table build) precedes the first probe by stream order
+  struct chunk_desc { int64_t r0 = 0, r1 = 0, nr = 0, nw = 0, kmers = 0, n_tiles = 0; size_t tseq_off = 0; int slot = 0; };
+  int inflight[PIPE_SLOTS], n_inflight = 0;       // submitted, not yet downloaded, oldest first
+  int64_t c = 0;
+  double t_gather = 0, t_wait = 0;
+  auto now = [] () { return std::chrono::steady_clock::now (); };
+  auto ms = [] (std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli> (b - a).count (); };
+  gcg_workers * pool = gcg_ctx_workers (ctx);
+  std::function<void (int64_t)> gather_fn;
+
+  // chunk starting at read r0: whole reads, at most cap_words words, meta within the slot's meta block;
+  // waits for its slot, writes the meta block and starts the gather on the pool
+  auto prepare = [&] (int64_t r0, chunk_desc & d) -> int {
+    int64_t r1 = r0, nw = 0;
+    while (r1 < n_read) {
+      const int64_t w = ((int64_t) read_len[r1] + 31) >> 5;
+      if (r1 > r0 && nw + w > cap_words) break;
+      const int64_t nr = r1 - r0 + 1;
+      if (r1 > r0 && (size_t) ((nr + 2) * 12 + ((nw + w + 31) >> 5) * 4 + 64) > p->meta_cap) break;
+      nw += w; ++r1;
     }
-    if (rc) { gcg_free (*hits_out); *hits_out = nullptr; }
-    gcg_trace_mark (ctx, "search: anchors to host");
+    d.r0 = r0; d.r1 = r1; d.nr = r1 - r0; d.nw = nw; d.n_tiles = (nw + 31) >> 5; d.kmers = 0;
+    d.slot = (int) (c % PIPE_SLOTS);
+    ++c;
+    pipe_slot & q = p->s[d.slot];
+    auto t0 = now ();
+    if (q.pending) { gcg_set_error ("gcg_search: pipeline slot reused before its download"); return GCG_ECUDA; }   // PIPE_SLOTS > PIPE_LAG + 1
+    if (q.busy) { GCG_CUDA (cudaEventSynchronize (q.ev_free)); q.busy = false; }
+    t_wait += ms (t0, now ());
+    if (nw == 0) return GCG_OK;
+    const int64_t nr = d.nr;
+    int64_t * woff = (int64_t *) q.h_meta;
+    int32_t * len = (int32_t *) (q.h_meta + (size_t) (nr + 1) * 8);
+    d.tseq_off = ((size_t) (nr + 1) * 8 + (size_t) nr * 4 + 7) & ~(size_t) 7;
+    int32_t * tseq = (int32_t *) (q.h_meta + d.tseq_off);
+    int64_t w = 0;
+    for (int64_t i = 0; i < nr; ++i) {
+      woff[i] = w; len[i] = read_len[r0 + i];
+      w += ((int64_t) read_len[r0 + i] + 31) >> 5;
+      if (read_len[r0 + i] >= k) d.kmers += (int64_t) read_len[r0 + i] - k + 1;
+    }
+    woff[nr] = w;
+    int64_t cur = 0;
+    for (int64_t tl = 0; tl < d.n_tiles; ++tl) {
+      while (cur + 1 < nr && woff[cur + 1] <= (tl << 5)) ++cur;
+      tseq[tl] = (int32_t) cur;
+    }
+    if (d.kmers == 0) return GCG_OK;
+    const int64_t n_task = nw * 32 < (1 << 18) ? 1 : std::min<int64_t> (nr, 4 * (int64_t) ctx->host_threads);
+    char * dst = q.h_ascii;
+    gather_fn = [=] (int64_t tk) {
+      for (int64_t i = nr * tk / n_task; i < nr * (tk + 1) / n_task; ++i)
+        if (len[i] > 0) gcg_copy_stream (dst + woff[i] * 32, read_seq[r0 + i], (size_t) len[i]);
+      gcg_copy_fence ();
+    };
+    gcg_workers_start (pool, n_task, gather_fn);
+    return GCG_OK;
+  };
+
+  // copy the gathered chunk to the device and enqueue its kernels
+  auto submit = [&] (const chunk_desc & d) -> int {
+    pipe_slot & q = p->s[d.slot];
+    const int64_t nr = d.nr, nw = d.nw;
+    const size_t meta_bytes = d.tseq_off + (size_t) d.n_tiles * 4;
+    GCG_CUDA (cudaMemcpyAsync (q.d_ascii, q.h_ascii, (size_t) nw * 32, cudaMemcpyHostToDevice, p->up));
+    GCG_CUDA (cudaMemcpyAsync (q.d_meta, q.h_meta, meta_bytes, cudaMemcpyHostToDevice, p->up));
+    GCG_CUDA (cudaEventRecord (q.ev_up, p->up));
+    GCG_CUDA (cudaStreamWaitEvent (ctx->stream, q.ev_up, 0));
+    const int64_t * d_woff = (const int64_t *) q.d_meta;
+    const int32_t * d_len = (const int32_t *) (q.d_meta + (size_t) (nr + 1) * 8);
+    const int32_t * d_tseq = (const int32_t *) (q.d_meta + d.tseq_off);
+    int e = launch_pack (ctx, q.d_ascii, q.d_packed, nw);
+    if (e) return e;
+    { gcg_kscope ks (ctx, "k45_search");
+      k45_search_kernel<<<grid_for (ctx, d.n_tiles * 32, 32 * K4_WARPS, 8), 32 * K4_WARPS, 0, ctx->stream>>> (
+          q.d_packed, d_woff, d_len, d_tseq, nr, nw, k, t->d_keys, t->n_bucket, q.d_mask); }
+    if ((e = mask_scan_launch (ctx, q.d_mask, nw, q.d_prefix, q.d_bsum, q.d_count)) != 0) return e;
+    GCG_CUDA (cudaMemcpyAsync (p->h_count + d.slot, q.d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GCG_CUDA (cudaEventRecord (q.ev_count, ctx->stream));
+    { gcg_kscope ks (ctx, "hits_emit");
+      hits_emit_kernel<<<grid_for (ctx, d.n_tiles * 32, 256, 8), 256, 0, ctx->stream>>> (
+          q.d_packed, d_woff, d_tseq, nr, nw, k, t->d_keys, t->d_vals, t->d_ont, t->n_bucket, q.d_mask, q.d_prefix, (int32_t) d.r0, q.d_hits); }
+    GCG_CUDA (cudaEventRecord (q.ev_emit, ctx->stream));
+    GCG_CUDA (cudaGetLastError ());
+    q.pending = true;
+    q.first_read = d.r0;
+    return GCG_OK;
+  };
+
+  chunk_desc cur_c, next_c;
+  rc = prepare (0, cur_c);
+  bool gathering = !rc && cur_c.kmers > 0;
+  while (!rc) {
+    auto t0 = now ();
+    if (gathering) gcg_workers_wait (pool);
+    t_gather += ms (t0, now ());
+    gathering = false;
+    // the next chunk is gathered while this one is copied and probed
+    const bool more = cur_c.r1 < n_read;
+    if (more) {
+      rc = prepare (cur_c.r1, next_c);
+      if (rc) break;
+      gathering = next_c.kmers > 0;
+    }
+    if (cur_c.kmers > 0) {
+      rc = submit (cur_c);
+      if (rc) break;
+      // place the anchors of the chunk submitted PIPE_LAG chunks ago: its count is there by now, so the
+      // host does not stall and the upload stream never runs dry
+      inflight[n_inflight++] = cur_c.slot;
+      if (n_inflight > PIPE_LAG) {
+        rc = pipe_download (ctx, p->s[inflight[0]], inflight[0], res);
+        if (rc) break;
+        for (int i = 1; i < n_inflight; ++i) inflight[i - 1] = inflight[i];
+        --n_inflight;
+      }
+    }
+    if (!more) break;
+    cur_c = next_c;
   }
-  for (gcg_hits * h : parts) gcg_hits_free (h);
-  if (!rc) *n_hit = total;
-  return rc;
+  if (gathering) gcg_workers_wait (pool);
+  // ---- drain, oldest first
+  for (int i = 0; i < n_inflight && !rc; ++i) rc = pipe_download (ctx, p->s[inflight[i]], inflight[i], res);
+  if (cudaStreamSynchronize (p->down) != cudaSuccess || cudaStreamSynchronize (ctx->stream) != cudaSuccess) {
+    if (!rc) { gcg_set_error ("gcg_search: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; }
+  }
+  for (pipe_slot & q : p->s) { q.busy = false; q.pending = false; }
+  if (ctx->trace)
+    fprintf (stderr, "[gcg]   search pipeline: %lld chunks, waits for the gather %.3f ms (%d threads), for a free slot %.3f ms\n",
+             (long long) c, t_gather, ctx->host_threads, t_wait);
+  gcg_trace_mark (ctx, "search: reads -> anchors (pipelined)");
+  if (rc) { gcg_free (res.buf); return rc; }
+  p->last_total = res.n;
+  if (res.n == 0) { gcg_free (res.buf); return GCG_OK; }
+  *hits_out = res.buf;
+  *n_hit = res.n;
+  return GCG_OK;
 }
 
 // ---- contig chop to host kmer_t arrays --------------------------------------------------------

@@ -47,21 +47,33 @@ def test_gap_filled_fasta_is_bit_exact(cfg, n_thread):
 
 
 def test_search_in_groups_matches_single_call():
-    """gcg_search cuts huge read sets into groups; force tiny groups and compare"""
+    """gcg_search streams the reads through a three-slot pipeline in chunks of whole reads: the
+    device-resident search, the default chunking and tiny chunks (many chunks, slot reuse, result
+    buffer growth, a read larger than the chunk) must give the same anchors and statistics"""
     import numpy as np
     from superplus_b200 import api
     ctx = api.Context(0)
-    inp = synth.make_config("tiny")
-    cs = ctx.upload(inp.contigs)
+    inp = synth.make_config("small")
+    reads = inp.reads[:60] + [inp.reads[0][:10], np.zeros(0, np.uint8), inp.reads[1][:24]] + inp.reads[60:]
+    cs, rs = ctx.upload(inp.contigs), ctx.upload(reads)
     t = ctx.table_build(cs, 25)
-    a = ctx.search_host(t, inp.reads)
-    st_a = t.stats()
+    want = ctx.search(t, rs)
+    st_want = t.stats()
     t.free()
-    t = ctx.table_build(cs, 25)
-    os.environ["GCG_SEARCH_GROUP_KMERS"] = "40000"
-    try:
-        b = ctx.search_host(t, inp.reads)
-    finally:
-        del os.environ["GCG_SEARCH_GROUP_KMERS"]
-    assert np.array_equal(a, b) and t.stats() == st_a
-    t.free(); cs.free(); ctx.close()
+    for chunk in (None, 1 << 20, 65536, 4096):
+        t = ctx.table_build(cs, 25)
+        if chunk is not None:
+            os.environ["GCG_SEARCH_CHUNK_BYTES"] = str(chunk)
+        try:
+            got = ctx.search_host(t, reads)
+            again = ctx.search_host(t, reads[:7])          # a second call on the same pipeline
+        finally:
+            os.environ.pop("GCG_SEARCH_CHUNK_BYTES", None)
+        assert np.array_equal(got, want), chunk
+        assert np.array_equal(again, want[want["read"] < 7]), chunk
+        t.free()
+        t = ctx.table_build(cs, 25)
+        ctx.search_host(t, reads)
+        assert t.stats() == st_want
+        t.free()
+    cs.free(); rs.free(); ctx.close()
