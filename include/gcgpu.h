@@ -50,6 +50,9 @@ int  gcg_set_host_threads (gcg_ctx * ctx, int n_thread);
 /* the CUDA stream every kernel of this ctx is launched on, as an opaque cudaStream_t */
 void * gcg_stream (gcg_ctx * ctx);
 int  gcg_sync (gcg_ctx * ctx);
+/* optional: allocate the pinned staging ring and the slots / side streams of the streaming search
+ * now (about 0.2 s of page pinning) instead of inside the first gcg_seqs_upload / gcg_search */
+int  gcg_warmup (gcg_ctx * ctx);
 /* per-kernel CUDA-event timing: enable, run, then read "name ms launches\n" lines */
 int  gcg_prof_enable (gcg_ctx * ctx, int on);
 int  gcg_prof_reset (gcg_ctx * ctx);

@@ -23,7 +23,7 @@ SWRES_DTYPE = np.dtype([("score", "<i4"), ("alignment_offset", "<i4"), ("has_sof
 KMER_DTYPE = np.dtype([("kseq", "<u8"), ("hs_id", "<i4"), ("tid", "<i4"), ("pos", "<i4"), ("flag", "<u2"), ("kmer_len", "<i2")])
 
 EXPORTS = [
-    "gcg_device_count", "gcg_init", "gcg_destroy", "gcg_last_error", "gcg_set_host_threads", "gcg_stream", "gcg_sync",
+    "gcg_device_count", "gcg_init", "gcg_destroy", "gcg_last_error", "gcg_set_host_threads", "gcg_stream", "gcg_sync", "gcg_warmup",
     "gcg_prof_enable", "gcg_prof_reset", "gcg_prof_report", "gcg_launch_count", "gcg_ubench_int16", "gcg_ubench_hbm", "gcg_ubench_gather",
     "gcg_seqs_upload", "gcg_seqs_upload_concat", "gcg_ascii_upload_concat", "gcg_seqs_pack", "gcg_ascii_free",
     "gcg_seqs_free", "gcg_seqs_count", "gcg_seqs_bases", "gcg_seqs_kmers",
@@ -94,6 +94,7 @@ def load_library(path: str = LIB_PATH):
     L.gcg_stream.restype = vp
     L.gcg_stream.argtypes = [vp]
     L.gcg_sync.argtypes = [vp]
+    L.gcg_warmup.argtypes = [vp]
     L.gcg_prof_enable.argtypes = [vp, C.c_int]
     L.gcg_prof_reset.argtypes = [vp]
     L.gcg_prof_report.argtypes = [vp, C.c_char_p, i64]

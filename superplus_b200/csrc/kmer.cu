@@ -933,6 +933,15 @@ static int pipe_reserve (gcg_ctx * ctx, int64_t cap_words)
   return GCG_OK;
 }
 
+extern "C" int gcg_warmup (gcg_ctx * ctx)
+{
+  GCG_CHECK (ctx, GCG_EINVAL, "gcg_warmup: ctx == NULL");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  int rc = gcg_stage_reserve (ctx);
+  if (!rc) rc = pipe_reserve (ctx, ((int64_t) 16 << 20) / 32);
+  return rc;
+}
+
 struct search_result {
   gcg_ctx * ctx;
   gcg_hit * buf = nullptr;

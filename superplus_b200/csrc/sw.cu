@@ -57,6 +57,9 @@ struct sw_consts {
   int border_kind, b_del_o, b_del_e, b_ins_o, b_ins_e;
   int mat16[64];                    // 16*mat + 8
   unsigned prof4[4];                // packed kernel: byte t of prof4[q] = (signed char)(16*mat[q][t]+8)
+  // packed kernel: the four gap constants as s16x2 words, built on the host so that the step loop
+  // reads them as constant-bank operands instead of rebuilding them (IMAD/LOP3 per step)
+  unsigned pk_do, pk_de, pk_io, pk_ie;
 };
 
 __constant__ sw_consts c_sw;
@@ -249,8 +252,10 @@ sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restr
   extern __shared__ unsigned short tsel[];
   const int lane = threadIdx.x;
   uint2 * bnd = bound + (size_t) blockIdx.x * rows_cap;
-  const uint32_t cDO = pack16 (-16 * c_sw.del_o + 4), cDE = pack16 (-16 * c_sw.del_e);
-  const uint32_t cIO = pack16 (-16 * c_sw.ins_o), cIE = pack16 (-16 * c_sw.ins_e);
+#define cDO c_sw.pk_do
+#define cDE c_sw.pk_de
+#define cIO c_sw.pk_io
+#define cIE c_sw.pk_ie
   const uint32_t NEG2 = pack16 (16 * SW_NEG16V);
   for (;;) {
     int item = 0;
@@ -373,6 +378,10 @@ sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restr
     if (has_b) sw_pick_end (eb, tb.qlen, tb.tlen, lane, ends + tb.pair);
     __syncwarp ();
   }
+#undef cDO
+#undef cDE
+#undef cIO
+#undef cIE
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -694,6 +703,11 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
       }
       hc.prof4[q] = w;
     }
+  }
+  {
+    auto pk = [] (int v) { return ((unsigned) v & 0xFFFFu) * 0x10001u; };
+    hc.pk_do = pk (-16 * P->del_o + 4); hc.pk_de = pk (-16 * P->del_e);
+    hc.pk_io = pk (-16 * P->ins_o); hc.pk_ie = pk (-16 * P->ins_e);
   }
   GCG_CUDA (cudaMemcpyToSymbolAsync (c_sw, &hc, sizeof hc, 0, cudaMemcpyHostToDevice, ctx->stream));
 

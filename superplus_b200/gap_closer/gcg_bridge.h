@@ -16,6 +16,7 @@ typedef struct {
 } gcg_bridge_t;
 
 gcg_bridge_t * gcg_bridge (void);            /* lazily creates the context; aborts via err_mesg on failure */
+void gcg_bridge_warmup (void);               /* start opening the device on a helper thread (joined by gcg_bridge) */
 void gcg_bridge_drop_table (void);
 void gcg_bridge_drop_contigs (void);
 void gcg_bridge_shutdown (void);

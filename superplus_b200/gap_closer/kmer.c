@@ -118,7 +118,9 @@ kmer_hash_init (int n_thread)
   khashs = (xh_t **) ckalloc (n_thread, sizeof (xh_t *));
   for (i = 0; i < n_thread; ++i)
     khashs[i] = _xh_init (256, 0.75, kmer_hash_func, kmer_is_equal);
-  gcg_bridge ();
+  /* the tables live in HBM; start opening the device now, in the background, while the unchanged
+   * loaders read the scaffolds and the ONT reads (main.c:149-156) */
+  gcg_bridge_warmup ();
   return khashs;
 }
 

@@ -188,6 +188,7 @@ ont_kseqs_init (mp_t(rs) * ont_seqs, mp_t(okseq) * okseqs)
 {
   int i, nt;
   int64_t cursor = 0, n = mp_cnt (ont_seqs);
+  time_t t_beg = time (NULL);
   long ncpu = sysconf (_SC_NPROCESSORS_ONLN);
   pthread_t * pids;
   init_arg_t arg;
@@ -204,6 +205,7 @@ ont_kseqs_init (mp_t(rs) * ont_seqs, mp_t(okseq) * okseqs)
   for (i = 0; i < nt; ++i)
     ckpthread_join (pids[i]);
   free (pids);
+  if (getenv ("GCG_TRACE")) fprintf (stderr, "[gcg] ont_kseqs_init: %ld reads on %d threads, %ld s\n", (long) n, nt, (long) (time (NULL) - t_beg));
   return 0;
 }
 
