@@ -291,6 +291,8 @@ def run_ours(args, rank, local_rank, world):
             idx = gdist.PartitionedKmerIndex(ops, comm, K).build(cs)
             nh = idx.search(rs, keep_on_device=True)
             st4 = idx.stats()
+            if idx.profile and rank == 0:
+                print("[dist profile, ms] " + "  ".join("%s %.2f" % kv for kv in sorted(idx.timers.items())), file=sys.stderr)
             idx.free(); cs.free(); rs.free()
             return nh, st4
 

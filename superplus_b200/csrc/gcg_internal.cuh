@@ -105,6 +105,7 @@ struct gcg_ascii {
   char * d_ascii = nullptr;                 // n_words * 32 bytes
   int64_t * d_woff = nullptr;               // n + 1
   int32_t * d_len = nullptr;                // n
+  int32_t * d_tseq = nullptr;               // per 32-word tile: index of the sequence holding its first word
   std::vector<int64_t> h_woff;
   std::vector<int32_t> h_len;
 };

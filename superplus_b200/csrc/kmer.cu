@@ -509,6 +509,22 @@ static int launch_pack (gcg_ctx * ctx, const char * d_ascii, uint64_t * d_packed
   return GCG_OK;
 }
 
+// tile -> sequence hints (largest s with woff[s] <= 32*tile), uploaded to *d_tseq
+static int tseq_upload (gcg_ctx * ctx, const std::vector<int64_t> & h_woff, int64_t n, int64_t n_words, int32_t ** d_tseq)
+{
+  const int64_t n_tiles = (n_words + 31) >> 5;
+  std::vector<int32_t> tseq ((size_t) std::max<int64_t> (n_tiles, 1), 0);
+  int64_t cur = 0;
+  for (int64_t t = 0; t < n_tiles; ++t) {
+    while (cur + 1 < n && h_woff[(size_t) cur + 1] <= (t << 5)) ++cur;
+    tseq[(size_t) t] = (int32_t) cur;
+  }
+  GCG_CUDA (gcg_dmalloc (ctx, d_tseq, tseq.size () * 4));
+  // (pageable source: the copy is staged by the runtime before the call returns)
+  GCG_CUDA (cudaMemcpyAsync (*d_tseq, tseq.data (), tseq.size () * 4, cudaMemcpyHostToDevice, ctx->stream));
+  return GCG_OK;
+}
+
 static int seqs_alloc (gcg_ctx * ctx, gcg_seqs * s)
 {
   GCG_CUDA (gcg_dmalloc (ctx, &s->d_packed, (size_t) (s->n_words + 2) * 8));
@@ -517,18 +533,7 @@ static int seqs_alloc (gcg_ctx * ctx, gcg_seqs * s)
   GCG_CUDA (gcg_dmalloc (ctx, &s->d_len, (size_t) std::max<int64_t> (s->n, 1) * 4));
   GCG_CUDA (cudaMemcpyAsync (s->d_woff, s->h_woff.data (), (size_t) (s->n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
   if (s->n) GCG_CUDA (cudaMemcpyAsync (s->d_len, s->h_len.data (), (size_t) s->n * 4, cudaMemcpyHostToDevice, ctx->stream));
-  // tile -> sequence hints (largest s with woff[s] <= 32*tile)
-  const int64_t n_tiles = (s->n_words + 31) >> 5;
-  std::vector<int32_t> tseq ((size_t) std::max<int64_t> (n_tiles, 1), 0);
-  int64_t cur = 0;
-  for (int64_t t = 0; t < n_tiles; ++t) {
-    while (cur + 1 < s->n && s->h_woff[(size_t) cur + 1] <= (t << 5)) ++cur;
-    tseq[(size_t) t] = (int32_t) cur;
-  }
-  GCG_CUDA (gcg_dmalloc (ctx, &s->d_tseq, tseq.size () * 4));
-  // (pageable source: the copy is staged by the runtime before the call returns)
-  GCG_CUDA (cudaMemcpyAsync (s->d_tseq, tseq.data (), tseq.size () * 4, cudaMemcpyHostToDevice, ctx->stream));
-  return GCG_OK;
+  return tseq_upload (ctx, s->h_woff, s->n, s->n_words, &s->d_tseq);
 }
 
 static int seqs_upload_impl (gcg_ctx * ctx, const seq_src & src, const int32_t * len, int64_t n, gcg_seqs ** out)
@@ -575,6 +580,8 @@ extern "C" int gcg_ascii_upload_concat (gcg_ctx * ctx, const char * buf, const i
   GCG_CUDA (gcg_dmalloc (ctx, &a->d_len, (size_t) std::max<int64_t> (n, 1) * 4));
   GCG_CUDA (cudaMemcpyAsync (a->d_woff, a->h_woff.data (), (size_t) (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
   if (n) GCG_CUDA (cudaMemcpyAsync (a->d_len, a->h_len.data (), (size_t) n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  rc = tseq_upload (ctx, a->h_woff, n, a->n_words, &a->d_tseq);
+  if (rc) { gcg_ascii_free (a); return rc; }
   rc = stream_ascii (ctx, src, a->h_woff, a->h_len, n, a->n_words, [&] (char * d, int64_t w0, int64_t nw) {
     GCG_CUDA (cudaMemcpyAsync (a->d_ascii + w0 * 32, d, (size_t) nw * 32, cudaMemcpyDeviceToDevice, ctx->stream));
     return GCG_OK;
@@ -592,8 +599,22 @@ extern "C" int gcg_seqs_pack (gcg_ctx * ctx, const gcg_ascii * a, gcg_seqs ** ou
   gcg_seqs * s = new gcg_seqs ();
   s->ctx = ctx; s->n = a->n; s->n_words = a->n_words; s->n_bases = a->n_bases;
   s->h_woff = a->h_woff; s->h_len = a->h_len;
-  int rc = seqs_alloc (ctx, s);
-  if (!rc) rc = launch_pack (ctx, a->d_ascii, s->d_packed, s->n_words);
+  // the layout arrays are already on the device: copy them there (no host staging, no stream stall)
+  const size_t n_tiles = (size_t) std::max<int64_t> ((s->n_words + 31) >> 5, 1);
+  cudaError_t e;
+  if ((e = gcg_dmalloc (ctx, &s->d_packed, (size_t) (s->n_words + 2) * 8)) != cudaSuccess ||
+      (e = gcg_dmalloc (ctx, &s->d_woff, (size_t) (s->n + 1) * 8)) != cudaSuccess ||
+      (e = gcg_dmalloc (ctx, &s->d_len, (size_t) std::max<int64_t> (s->n, 1) * 4)) != cudaSuccess ||
+      (e = gcg_dmalloc (ctx, &s->d_tseq, n_tiles * 4)) != cudaSuccess ||
+      (e = cudaMemsetAsync (s->d_packed + s->n_words, 0, 16, ctx->stream)) != cudaSuccess ||
+      (e = cudaMemcpyAsync (s->d_woff, a->d_woff, (size_t) (s->n + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream)) != cudaSuccess ||
+      (s->n && (e = cudaMemcpyAsync (s->d_len, a->d_len, (size_t) s->n * 4, cudaMemcpyDeviceToDevice, ctx->stream)) != cudaSuccess) ||
+      (e = cudaMemcpyAsync (s->d_tseq, a->d_tseq, n_tiles * 4, cudaMemcpyDeviceToDevice, ctx->stream)) != cudaSuccess) {
+    gcg_set_error ("gcg_seqs_pack: %s", cudaGetErrorString (e));
+    gcg_seqs_free (s);
+    return GCG_ECUDA;
+  }
+  int rc = launch_pack (ctx, a->d_ascii, s->d_packed, s->n_words);
   if (rc) { gcg_seqs_free (s); return rc; }
   *out = s;
   return GCG_OK;
@@ -602,7 +623,7 @@ extern "C" int gcg_seqs_pack (gcg_ctx * ctx, const gcg_ascii * a, gcg_seqs ** ou
 extern "C" void gcg_ascii_free (gcg_ascii * a)
 {
   if (!a) return;
-  gcg_dfree (a->ctx, a->d_ascii); gcg_dfree (a->ctx, a->d_woff); gcg_dfree (a->ctx, a->d_len);
+  gcg_dfree (a->ctx, a->d_ascii); gcg_dfree (a->ctx, a->d_woff); gcg_dfree (a->ctx, a->d_len); gcg_dfree (a->ctx, a->d_tseq);
   delete a;
 }
 

@@ -25,7 +25,9 @@ There is no CPU implementation of the device work in this package.
 from __future__ import annotations
 
 import contextlib
+import os
 import threading
+import time
 
 import numpy as np
 import torch
@@ -202,6 +204,21 @@ class PartitionedKmerIndex:
         self.ops, self.comm, self.k, self.round_kmers = ops, comm, k, round_kmers
         self.table = None
         self.n_local_records = 0
+        # GCG_DIST_PROFILE=1: wall-clock per phase with a device sync on both sides (diagnosis only;
+        # the syncs serialise what normally overlaps)
+        self.profile = os.environ.get("GCG_DIST_PROFILE") == "1"
+        self.timers = {}
+
+    @contextlib.contextmanager
+    def _phase(self, name):
+        if not self.profile:
+            yield
+            return
+        self.ops.sync()
+        t0 = time.perf_counter()
+        yield
+        self.ops.sync()
+        self.timers[name] = self.timers.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
 
     def _stream(self):
         return self.ops.stream() if hasattr(self.ops, "stream") else contextlib.nullcontext()
@@ -213,15 +230,20 @@ class PartitionedKmerIndex:
         ops, comm = self.ops, self.comm
         with self._stream():
             t0, t1 = tile_slice(ops.tiles(contigs), comm.rank, comm.world)
-            route = ops.plan(contigs, self.k, comm.world, t0, t1)
-            recv_counts = comm.exchange_counts(route.counts)
-            send = comm.empty(2 * int(route.counts.sum()))
-            ops.route_records(route, send)
-            recv = comm.all_to_all(send, route.counts, recv_counts, width=2)
+            with self._phase("build.plan"):
+                route = ops.plan(contigs, self.k, comm.world, t0, t1)
+            with self._phase("build.counts"):
+                recv_counts = comm.exchange_counts(route.counts)
+            with self._phase("build.route"):
+                send = comm.empty(2 * int(route.counts.sum()))
+                ops.route_records(route, send)
+            with self._phase("build.all_to_all"):
+                recv = comm.all_to_all(send, route.counts, recv_counts, width=2)
             n = int(recv_counts.sum())
-            self.table = ops.table_create(n, self.k)
-            ops.insert(self.table, recv, n)
-            ops.sync()                      # recv/send are released after the inserts ran
+            with self._phase("build.insert"):
+                self.table = ops.table_create(n, self.k)
+                ops.insert(self.table, recv, n)
+                ops.sync()                      # recv/send are released after the inserts ran
             route.free()
             self.n_local_records = n
         return self
@@ -237,17 +259,24 @@ class PartitionedKmerIndex:
             n_rounds = int(comm.all_reduce([len(rounds)], "max")[0])
             for i in range(n_rounds):
                 t0, t1 = rounds[i] if i < len(rounds) else (0, 0)
-                route = ops.plan(reads, self.k, comm.world, t0, t1)
-                recv_counts = comm.exchange_counts(route.counts)
+                with self._phase("search.plan"):
+                    route = ops.plan(reads, self.k, comm.world, t0, t1)
+                with self._phase("search.counts"):
+                    recv_counts = comm.exchange_counts(route.counts)
                 n_send, n_recv = int(route.counts.sum()), int(recv_counts.sum())
-                keys = comm.empty(n_send)
-                ops.route_keys(route, keys)
-                q = comm.all_to_all(keys, route.counts, recv_counts, width=1)
-                a = comm.empty(n_recv)
-                ops.lookup(self.table, q, n_recv, a)
-                answers = comm.all_to_all(a, recv_counts, route.counts, width=1)
-                h = ops.collect(route, answers)
-                ops.sync()
+                with self._phase("search.route"):
+                    keys = comm.empty(n_send)
+                    ops.route_keys(route, keys)
+                with self._phase("search.keys_all_to_all"):
+                    q = comm.all_to_all(keys, route.counts, recv_counts, width=1)
+                with self._phase("search.lookup"):
+                    a = comm.empty(n_recv)
+                    ops.lookup(self.table, q, n_recv, a)
+                with self._phase("search.answers_all_to_all"):
+                    answers = comm.all_to_all(a, recv_counts, route.counts, width=1)
+                with self._phase("search.collect"):
+                    h = ops.collect(route, answers)
+                    ops.sync()
                 route.free()
                 n_total += h.n
                 if keep_on_device:
