@@ -279,40 +279,54 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- hash-partitioned table (BASELINE configs[3] / SURVEY 8e): same step, the table split over the
     #      ranks by hash of the canonical k-mer, records / keys / answers exchanged by all-to-all
-    part = None
+    part = {}
     if world > 1 or args.partitioned:
         from superplus_b200 import dist as gdist
         ops = gdist.DeviceOps(ctx, local_rank)
         comm = gdist.TorchComm(ops.device) if dist is not None else gdist.ThreadComm(gdist.ThreadGroup(1), 0, ops.device, ops.sync)
+        for exchange in ("direct", "all_to_all"):
+            idx_keep = [None]
 
-        def part_step():
-            cs = ctx.pack(a_ctg)
-            rs = ctx.pack(a_reads)
-            idx = gdist.PartitionedKmerIndex(ops, comm, K).build(cs)
-            nh = idx.search(rs, keep_on_device=True)
-            st4 = idx.stats()
-            if idx.profile and rank == 0:
-                print("[dist profile, ms] " + "  ".join("%s %.2f" % kv for kv in sorted(idx.timers.items())), file=sys.stderr)
-            idx.free(); cs.free(); rs.free()
-            return nh, st4
+            def part_step():
+                cs = ctx.pack(a_ctg)
+                rs = ctx.pack(a_reads)
+                # the exchange windows of the direct mode live as long as the index: build it once per
+                # step like the replicated leg, but keep the previous one's windows (grown, mapped) alive
+                idx = gdist.PartitionedKmerIndex(ops, comm, K, exchange=exchange)
+                if idx_keep[0] is not None:
+                    prev = idx_keep[0]
+                    idx.qwin, idx.awin, idx.q_refs, idx.a_refs, idx.q_cap, idx.a_cap = prev.qwin, prev.awin, prev.q_refs, prev.a_refs, prev.q_cap, prev.a_cap
+                    prev.qwin = prev.awin = prev.q_refs = prev.a_refs = None
+                    prev.free()
+                idx.build(cs)
+                nh = idx.search(rs, keep_on_device=True)
+                st4 = idx.stats()
+                if idx.profile and rank == 0:
+                    print("[dist profile %s, ms] " % exchange + "  ".join("%s %.2f" % kv for kv in sorted(idx.timers.items())), file=sys.stderr)
+                if idx.table is not None:
+                    idx.table.free(); idx.table = None
+                idx_keep[0] = idx
+                cs.free(); rs.free()
+                return nh, st4
 
-        for _ in range(args.warmup):
-            p_hit, p_st = part_step()
-        ctx.prof_reset()
-        sent0, pl0 = comm.bytes_sent, ctx.launches()
-        barrier()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record(stream)
-        for _ in range(args.steps):
-            p_hit, p_st = part_step()
-        p1.record(stream)
-        barrier()
-        part_ms = allmax(p0.elapsed_time(p1)) / args.steps
-        pprof = ctx.prof_report()
-        assert p_hit == n_hit, "partitioned and replicated tables disagree on this rank's anchors"
-        part = {"ms_per_step": part_ms, "launches": ctx.launches() - pl0, "stats": list(p_st),
-                "bytes_sent_per_step": allsum(float(comm.bytes_sent - sent0)) / args.steps,
-                "kernel_ms_per_step": {k_: v[0] / args.steps for k_, v in sorted(pprof.items())}}
+            for _ in range(args.warmup):
+                p_hit, p_st = part_step()
+            ctx.prof_reset()
+            sent0, pl0 = comm.bytes_sent, ctx.launches()
+            barrier()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record(stream)
+            for _ in range(args.steps):
+                p_hit, p_st = part_step()
+            p1.record(stream)
+            barrier()
+            part_ms = allmax(p0.elapsed_time(p1)) / args.steps
+            pprof = ctx.prof_report()
+            assert p_hit == n_hit, "partitioned and replicated tables disagree on this rank's anchors"
+            part[exchange] = {"ms_per_step": part_ms, "launches": ctx.launches() - pl0, "stats": list(p_st),
+                              "bytes_sent_per_step": allsum(float(comm.bytes_sent - sent0)) / args.steps,
+                              "kernel_ms_per_step": {k_: v[0] / args.steps for k_, v in sorted(pprof.items())}}
+            idx_keep[0].free()
 
     # ---- timed: SW steps
     ctx.prof_reset()
@@ -456,13 +470,14 @@ def run_ours(args, rank, local_rank, world):
                 line["cpu_baseline"] = {"value": None, "unit": "k-mers/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref not built"}
         except Exception as e:      # the baseline must never sink the bench line
             line["cpu_baseline"] = {"value": None, "unit": "k-mers/s", "cores": cores, "kind": "reference", "sample": "failed: %r" % (e,)}
-    if part is not None:
-        line["partitioned"] = {
-            "metric": "kmers_per_s", "value": tot_ont_kmers / (part["ms_per_step"] * 1e-3), "unit": "k-mers/s", "ms_per_step": part["ms_per_step"],
-            "config": {"workload": "same step with the contig table hash-partitioned over %d GPU(s): route + all-to-all (16 B per contig k-mer, 8 B key out and 8 B answer back per ONT k-mer) + owner-side insert / lookup + ordered collect" % world,
-                       "collective": ("NCCL all_to_all_single over NVLink" if world > 1 else "single partition, no exchange")},
-            "nvlink_bytes_per_step": part["bytes_sent_per_step"], "stats": part["stats"], "kernel_ms_per_step": part["kernel_ms_per_step"]}
-        line["gpu_launches"] += int(part["launches"])
+    for exchange, pr in part.items():
+        line["partitioned" if exchange == "direct" else "partitioned_all_to_all"] = {
+            "metric": "kmers_per_s", "value": tot_ont_kmers / (pr["ms_per_step"] * 1e-3), "unit": "k-mers/s", "ms_per_step": pr["ms_per_step"],
+            "config": {"workload": "same step with the contig table hash-partitioned over %d GPU(s): route by owner, owner-side insert / lookup, ordered collect" % world,
+                       "exchange": ("keys (8 B per ONT k-mer) stored by the routing kernel straight into the owner's window and answers (8 B) by the lookup kernel straight into the requester's window over NVLink peer memory (CUDA IPC); two barriers per round, no collective on the data path"
+                                    if exchange == "direct" else "send / receive buffers and NCCL all_to_all_single (8 B key out, 8 B answer back per ONT k-mer)") if world > 1 else "single partition, nothing crosses a link"},
+            "nvlink_bytes_per_step": pr["bytes_sent_per_step"], "stats": pr["stats"], "kernel_ms_per_step": pr["kernel_ms_per_step"]}
+        line["gpu_launches"] += int(pr["launches"])
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

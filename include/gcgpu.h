@@ -171,6 +171,29 @@ int  gcg_table_lookup_keys (gcg_ctx * ctx, gcg_table * t, const void * d_keys, i
 int  gcg_route_collect (gcg_ctx * ctx, gcg_route * r, const void * d_answers, gcg_hits ** out);
 void gcg_route_free (gcg_route * r);
 
+/* Direct exchange over NVLink / NVSwitch peer memory (no staging buffer, no collective on the
+ * data path): every rank owns two WINDOWS — plain device allocations that the other ranks map
+ * (CUDA IPC between processes, peer access inside one process).  The routing kernel stores each
+ * owner's run of keys straight into that owner's key window, and the owner's lookup kernel
+ * stores each answer straight into the requester's answer window, at the position the requester's
+ * collect pass expects.  The caller synchronises the ranks between the phases (all stores of a
+ * phase are complete when every rank has drained its stream).
+ *   gcg_route_keys_direct : owner d's run goes to d_owner_base[d] + owner_off[d] (8-byte elements)
+ *   gcg_table_lookup_keys_direct : the key window holds n_src runs, src_count[r] keys from
+ *       requester r in rank order; the answers of run r go to d_answer_base[r] + answer_off[r] */
+typedef struct gcg_window gcg_window;
+int  gcg_window_create (gcg_ctx * ctx, int64_t bytes, gcg_window ** out);
+void * gcg_window_ptr (gcg_window * w);
+int64_t gcg_window_bytes (gcg_window * w);
+int  gcg_window_export (gcg_window * w, void * handle64);                       /* 64-byte IPC handle */
+int  gcg_window_open (gcg_ctx * ctx, const void * handle64, void ** d_peer);    /* in ANOTHER process */
+int  gcg_window_close (gcg_ctx * ctx, void * d_peer);
+void gcg_window_free (gcg_window * w);
+int  gcg_peer_enable (gcg_ctx * ctx, int peer_device);                          /* same-process peers */
+int  gcg_route_keys_direct (gcg_ctx * ctx, gcg_route * r, void * const * d_owner_base, const int64_t * owner_off);
+int  gcg_table_lookup_keys_direct (gcg_ctx * ctx, gcg_table * t, const void * d_keys, int n_src, const int64_t * src_count,
+                                   void * const * d_answer_base, const int64_t * answer_off);
+
 /* ------------------------------------------------------------------ Smith-Waterman --- */
 #define GCG_SWOS_SOFTCLIP      0   /* sw.h:20-23 */
 #define GCG_SWOS_LEADING_INDEL 1

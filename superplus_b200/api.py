@@ -34,6 +34,8 @@ EXPORTS = [
     "gcg_swbatch_path_counts", "gcg_swbatch_free",
     "gcg_kmer_owner", "gcg_seqs_tiles", "gcg_route_plan", "gcg_route_kmers", "gcg_route_keys", "gcg_route_records",
     "gcg_route_collect", "gcg_route_free", "gcg_table_create", "gcg_table_insert_records", "gcg_table_lookup_keys",
+    "gcg_window_create", "gcg_window_ptr", "gcg_window_bytes", "gcg_window_export", "gcg_window_open", "gcg_window_close",
+    "gcg_window_free", "gcg_peer_enable", "gcg_route_keys_direct", "gcg_table_lookup_keys_direct",
 ]
 MAX_PART = 16
 
@@ -150,6 +152,18 @@ def load_library(path: str = LIB_PATH):
     L.gcg_table_create.argtypes = [vp, i64, C.c_int, C.POINTER(vp)]
     L.gcg_table_insert_records.argtypes = [vp, vp, vp, i64]
     L.gcg_table_lookup_keys.argtypes = [vp, vp, vp, i64, vp]
+    L.gcg_window_create.argtypes = [vp, i64, C.POINTER(vp)]
+    L.gcg_window_ptr.restype = vp
+    L.gcg_window_ptr.argtypes = [vp]
+    L.gcg_window_bytes.restype = i64
+    L.gcg_window_bytes.argtypes = [vp]
+    L.gcg_window_export.argtypes = [vp, vp]
+    L.gcg_window_open.argtypes = [vp, vp, C.POINTER(vp)]
+    L.gcg_window_close.argtypes = [vp, vp]
+    L.gcg_window_free.argtypes = [vp]
+    L.gcg_peer_enable.argtypes = [vp, C.c_int]
+    L.gcg_route_keys_direct.argtypes = [vp, vp, vp, vp]
+    L.gcg_table_lookup_keys_direct.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
     _lib = L
     return L
 
@@ -320,6 +334,21 @@ class Context:
         self._chk(self.L.gcg_route_plan(self.h, seqs.h, k, n_part, tile_begin, tile_end, C.byref(h), counts.ctypes.data))
         return Route(self, h, counts[:n_part].copy())
 
+    def window(self, n_bytes: int) -> "Window":
+        h = C.c_void_p()
+        self._chk(self.L.gcg_window_create(self.h, int(n_bytes), C.byref(h)))
+        return Window(self, h)
+
+    def window_open(self, handle: bytes) -> int:
+        """map another process's window (its 64-byte IPC handle) -> device pointer usable by this context"""
+        buf = C.create_string_buffer(handle, 64)
+        p = C.c_void_p()
+        self._chk(self.L.gcg_window_open(self.h, buf, C.byref(p)))
+        return int(p.value)
+
+    def window_close(self, ptr: int):
+        self._chk(self.L.gcg_window_close(self.h, C.c_void_p(ptr)))
+
     def table_create(self, n_records: int, k: int) -> "KmerTable":
         h = C.c_void_p()
         self._chk(self.L.gcg_table_create(self.h, int(n_records), k, C.byref(h)))
@@ -407,6 +436,24 @@ class Hits(_Handle):
         return out
 
 
+class Window(_Handle):
+    """exchange window: a device allocation other ranks store into over NVLink (gcg_window)"""
+    _free = "gcg_window_free"
+
+    @property
+    def ptr(self) -> int:
+        return int(self.ctx.L.gcg_window_ptr(self.h) or 0)
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.ctx.L.gcg_window_bytes(self.h))
+
+    def export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self.ctx._chk(self.ctx.L.gcg_window_export(self.h, buf))
+        return buf.raw
+
+
 class Route(_Handle):
     """stable partition plan of the k-mers of one tile range by owner (gcg_route)"""
     _free = "gcg_route_free"
@@ -421,6 +468,14 @@ class Route(_Handle):
 
     def keys(self, d_send: int):
         self.ctx._chk(self.ctx.L.gcg_route_keys(self.ctx.h, self.h, d_send))
+
+    def keys_direct(self, owner_ptrs, owner_off):
+        """owner d's run of keys goes to owner_ptrs[d] + 8 * owner_off[d] (a window, possibly on a peer GPU)"""
+        n = len(owner_ptrs)
+        ptrs = (C.c_void_p * MAX_PART)(*[C.c_void_p(int(p)) for p in owner_ptrs])
+        offs = np.zeros(MAX_PART, dtype=np.int64)
+        offs[:n] = owner_off
+        self.ctx._chk(self.ctx.L.gcg_route_keys_direct(self.ctx.h, self.h, C.cast(ptrs, C.c_void_p), offs.ctypes.data))
 
     def records(self, d_send: int):
         self.ctx._chk(self.ctx.L.gcg_route_records(self.ctx.h, self.h, d_send))
@@ -448,6 +503,15 @@ class KmerTable(_Handle):
 
     def lookup_keys(self, d_keys: int, n: int, d_answers: int):
         self.ctx._chk(self.ctx.L.gcg_table_lookup_keys(self.ctx.h, self.h, d_keys, int(n), d_answers))
+
+    def lookup_keys_direct(self, d_keys: int, src_count, answer_ptrs, answer_off):
+        """keys of requester r (src_count[r] of them, in rank order) -> answers at answer_ptrs[r] + 8 * answer_off[r]"""
+        n = len(src_count)
+        cnt = np.ascontiguousarray(src_count, dtype=np.int64)
+        ptrs = (C.c_void_p * MAX_PART)(*[C.c_void_p(int(p)) for p in answer_ptrs])
+        offs = np.ascontiguousarray(answer_off, dtype=np.int64)
+        self.ctx._chk(self.ctx.L.gcg_table_lookup_keys_direct(self.ctx.h, self.h, d_keys, n, cnt.ctypes.data,
+                                                               C.cast(ptrs, C.c_void_p), offs.ctypes.data))
 
     def dump(self):
         """-> key, multi(1|2), tid, pos, rev sorted by key"""

@@ -126,8 +126,10 @@ route_count_kernel (const uint64_t * __restrict__ packed, const int64_t * __rest
 // done on global memory) happens in shared memory.
 //   s_cnt[d][lane]  per-lane count, then the lane's cursor INSIDE THE TILE'S STAGE
 //   s_run[d]        start of owner d's run in the stage (exclusive scan of the tile totals), s_run[n_part] = total
-//   s_glob[d]       global index of the first element of owner d's run
-__device__ __forceinline__ void tile_layout (uint32_t (* cnt)[32], uint32_t * s_run, int64_t * s_glob, const int64_t * s_seg,
+//   s_glob[d]       address of the first element of owner d's run (the owner's segment may be a
+//                   peer GPU's exchange window: the copy-out is then a coalesced store over NVLink)
+__device__ __forceinline__ void tile_layout (uint32_t (* cnt)[32], uint32_t * s_run, unsigned long long ** s_glob,
+                                             unsigned long long * const * s_base,
                                              const uint32_t * __restrict__ off, int64_t n_tiles, int64_t t, uint32_t n_part, int lane)
 {
   // tile totals per owner: lane d keeps tot_d
@@ -141,7 +143,7 @@ __device__ __forceinline__ void tile_layout (uint32_t (* cnt)[32], uint32_t * s_
   __syncwarp ();
   if ((uint32_t) lane < n_part) {
     s_run[lane] = x - mine;
-    s_glob[lane] = s_seg[lane] + __ldg (off + (int64_t) lane * n_tiles + t);
+    s_glob[lane] = s_base[lane] + __ldg (off + (int64_t) lane * n_tiles + t);
   }
   if ((uint32_t) lane == n_part - 1) s_run[n_part] = x;
   __syncwarp ();
@@ -163,19 +165,22 @@ __device__ __forceinline__ uint32_t run_of (const uint32_t * s_run, uint32_t n_p
 
 #define RS_WARPS 4      // warps per block of the staged kernels (8 KB of stage per warp)
 
+// where owner d's segment starts: inside one send buffer (exchange by all-to-all) or inside the
+// owner's own exchange window (direct stores over NVLink / NVSwitch peer memory)
+struct route_dst { unsigned long long * base[GCG_MAX_PART]; };
+
 // 8-byte keys (key + 1) of the range, grouped by owner
 __global__ void __launch_bounds__ (32 * RS_WARPS)
 route_keys_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff, const int32_t * __restrict__ len,
                    const int32_t * __restrict__ tile_seq, int64_t n_seq, int64_t n_words, int k, uint32_t n_part,
-                   int64_t tile0, int64_t n_tiles, const uint32_t * __restrict__ off, const int64_t * __restrict__ seg,
-                   unsigned long long * __restrict__ out)
+                   int64_t tile0, int64_t n_tiles, const uint32_t * __restrict__ off, const __grid_constant__ route_dst dst)
 {
   __shared__ unsigned long long s_stage[RS_WARPS][1024];
   __shared__ uint32_t s_cnt[RS_WARPS][GCG_MAX_PART][32];
   __shared__ uint32_t s_run[RS_WARPS][GCG_MAX_PART + 1];
-  __shared__ int64_t s_glob[RS_WARPS][GCG_MAX_PART];
-  __shared__ int64_t s_seg[GCG_MAX_PART];
-  if (threadIdx.x < n_part) s_seg[threadIdx.x] = seg[threadIdx.x];
+  __shared__ unsigned long long * s_glob[RS_WARPS][GCG_MAX_PART];
+  __shared__ unsigned long long * s_base[GCG_MAX_PART];
+  if (threadIdx.x < n_part) s_base[threadIdx.x] = dst.base[threadIdx.x];
   __syncthreads ();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t wstride = (int64_t) gridDim.x * RS_WARPS;
@@ -185,7 +190,7 @@ route_keys_kernel (const uint64_t * __restrict__ packed, const int64_t * __restr
     const int nvalid = word_valid (woff, len, tile_seq, n_seq, n_words, tile, w, k, &s, &p0);
     __syncwarp ();                                    // the previous tile's copy-out has finished reading the stage
     lane_counts (packed, w, nvalid, k, n_part, s_cnt[wid], lane);
-    tile_layout (s_cnt[wid], s_run[wid], s_glob[wid], s_seg, off, n_tiles, t, n_part, lane);
+    tile_layout (s_cnt[wid], s_run[wid], s_glob[wid], s_base, off, n_tiles, t, n_part, lane);
     if (nvalid) {
       kroll r;
       r.init (__ldg (packed + w), __ldg (packed + w + 1), k);
@@ -199,7 +204,7 @@ route_keys_kernel (const uint64_t * __restrict__ packed, const int64_t * __restr
     const uint32_t total = s_run[wid][n_part];
     for (uint32_t i = lane; i < total; i += 32) {
       const uint32_t d = run_of (s_run[wid], n_part, i);
-      out[s_glob[wid][d] + (i - s_run[wid][d])] = s_stage[wid][i];
+      s_glob[wid][d][i - s_run[wid][d]] = s_stage[wid][i];
     }
   }
 }
@@ -310,12 +315,22 @@ insert_records_kernel (const ulonglong2 * __restrict__ recs, int64_t n, unsigned
   }
 }
 
+// keys [first[r], first[r+1]) came from requester r; their answers go to base[r][i - first[r]] — the
+// requester's own answer buffer (or, exchanged directly, its window on the peer GPU)
+struct lookup_dst { unsigned long long * base[GCG_MAX_PART]; long long first[GCG_MAX_PART + 1]; int n_src; };
+
 #define LK_UNROLL 4
 __global__ void __launch_bounds__ (256)
 lookup_keys_kernel (const unsigned long long * __restrict__ qkeys, int64_t n, const unsigned long long * __restrict__ keys,
                     const unsigned long long * __restrict__ vals, uint32_t * __restrict__ ont, uint32_t n_bucket,
-                    unsigned long long * __restrict__ ans)
+                    const __grid_constant__ lookup_dst dst)
 {
+  __shared__ unsigned long long * s_base[GCG_MAX_PART];
+  __shared__ long long s_first[GCG_MAX_PART + 1];
+  if ((int) threadIdx.x < dst.n_src) s_base[threadIdx.x] = dst.base[threadIdx.x];
+  if ((int) threadIdx.x <= dst.n_src) s_first[threadIdx.x] = dst.first[threadIdx.x];
+  __syncthreads ();
+  const int n_src = dst.n_src;
   const int64_t stride = (int64_t) gridDim.x * blockDim.x;
   for (int64_t i0 = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * LK_UNROLL) {
     unsigned long long key[LK_UNROLL];
@@ -340,7 +355,9 @@ lookup_keys_kernel (const unsigned long long * __restrict__ qkeys, int64_t n, co
         const uint32_t old = atomicOr (ont + (slot >> 4), 1u << sh);
         if (((old >> sh) & 3u) == 1u) atomicOr (ont + (slot >> 4), 2u << sh);
       }
-      ans[i] = a;
+      int r = 0;
+      while (r + 1 < n_src && s_first[r + 1] <= i) ++r;
+      s_base[r][i - s_first[r]] = a;
     }
   }
 }
@@ -529,18 +546,44 @@ static int staged_grid (gcg_ctx * ctx, int64_t n_tiles)
   return (int) std::max<int64_t> (1, std::min (nb, cap));
 }
 
+static int route_keys_launch (gcg_ctx * ctx, gcg_route * r, const route_dst & dst)
+{
+  const gcg_seqs * s = r->seqs;
+  gcg_kscope ks (ctx, "route_keys");
+  route_keys_kernel<<<staged_grid (ctx, r->n_tiles), 32 * RS_WARPS, 0, ctx->stream>>> (
+      s->d_packed, s->d_woff, s->d_len, s->d_tseq, s->n, s->n_words, r->k, (uint32_t) r->n_part, r->tile0, r->n_tiles, r->d_off, dst);
+  GCG_CUDA (cudaGetLastError ());
+  return GCG_OK;
+}
+
 extern "C" int gcg_route_keys (gcg_ctx * ctx, gcg_route * r, void * d_send)
 {
   GCG_CHECK (ctx && r && (d_send || r->n_kmers == 0), GCG_EINVAL, "gcg_route_keys: bad argument");
   GCG_CUDA (cudaSetDevice (ctx->device));
   if (r->n_kmers == 0) return GCG_OK;
-  const gcg_seqs * s = r->seqs;
-  gcg_kscope ks (ctx, "route_keys");
-  route_keys_kernel<<<staged_grid (ctx, r->n_tiles), 32 * RS_WARPS, 0, ctx->stream>>> (
-      s->d_packed, s->d_woff, s->d_len, s->d_tseq, s->n, s->n_words, r->k, (uint32_t) r->n_part, r->tile0, r->n_tiles,
-      r->d_off, r->d_seg, (unsigned long long *) d_send);
-  GCG_CUDA (cudaGetLastError ());
-  return GCG_OK;
+  route_dst dst;
+  int64_t at = 0;
+  for (int d = 0; d < GCG_MAX_PART; ++d) {
+    dst.base[d] = (unsigned long long *) d_send + at;
+    if (d < r->n_part) at += r->counts[d];
+  }
+  return route_keys_launch (ctx, r, dst);
+}
+
+extern "C" int gcg_route_keys_direct (gcg_ctx * ctx, gcg_route * r, void * const * d_owner_base, const int64_t * owner_off)
+{
+  GCG_CHECK (ctx && r && d_owner_base && owner_off, GCG_EINVAL, "gcg_route_keys_direct: bad argument");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  if (r->n_kmers == 0) return GCG_OK;
+  route_dst dst;
+  for (int d = 0; d < GCG_MAX_PART; ++d) {
+    dst.base[d] = nullptr;
+    if (d >= r->n_part) continue;
+    GCG_CHECK (d_owner_base[d] != nullptr || r->counts[d] == 0, GCG_EINVAL, "gcg_route_keys_direct: no window for owner %d", d);
+    GCG_CHECK (owner_off[d] >= 0, GCG_EINVAL, "gcg_route_keys_direct: negative offset for owner %d", d);
+    dst.base[d] = (unsigned long long *) d_owner_base[d] + owner_off[d];
+  }
+  return route_keys_launch (ctx, r, dst);
 }
 
 extern "C" int gcg_route_records (gcg_ctx * ctx, gcg_route * r, void * d_send)
@@ -623,14 +666,126 @@ extern "C" int gcg_table_insert_records (gcg_ctx * ctx, gcg_table * t, const voi
   return GCG_OK;
 }
 
+static int lookup_launch (gcg_ctx * ctx, gcg_table * t, const void * d_keys, int64_t n, const lookup_dst & dst)
+{
+  gcg_kscope ks (ctx, "part_lookup");
+  lookup_keys_kernel<<<flat_grid (ctx, n, LK_UNROLL), 256, 0, ctx->stream>>> (
+      (const unsigned long long *) d_keys, n, t->d_keys, t->d_vals, t->d_ont, t->n_bucket, dst);
+  GCG_CUDA (cudaGetLastError ());
+  return GCG_OK;
+}
+
 extern "C" int gcg_table_lookup_keys (gcg_ctx * ctx, gcg_table * t, const void * d_keys, int64_t n, void * d_answers)
 {
   GCG_CHECK (ctx && t && n >= 0 && ((d_keys && d_answers) || n == 0), GCG_EINVAL, "gcg_table_lookup_keys: bad argument");
   GCG_CUDA (cudaSetDevice (ctx->device));
   if (n == 0) return GCG_OK;
-  gcg_kscope ks (ctx, "part_lookup");
-  lookup_keys_kernel<<<flat_grid (ctx, n, LK_UNROLL), 256, 0, ctx->stream>>> (
-      (const unsigned long long *) d_keys, n, t->d_keys, t->d_vals, t->d_ont, t->n_bucket, (unsigned long long *) d_answers);
-  GCG_CUDA (cudaGetLastError ());
+  lookup_dst dst;
+  memset (&dst, 0, sizeof dst);
+  dst.n_src = 1; dst.base[0] = (unsigned long long *) d_answers; dst.first[0] = 0; dst.first[1] = n;
+  return lookup_launch (ctx, t, d_keys, n, dst);
+}
+
+extern "C" int gcg_table_lookup_keys_direct (gcg_ctx * ctx, gcg_table * t, const void * d_keys, int n_src, const int64_t * src_count,
+                                             void * const * d_answer_base, const int64_t * answer_off)
+{
+  GCG_CHECK (ctx && t && src_count && d_answer_base && answer_off && n_src >= 1 && n_src <= GCG_MAX_PART, GCG_EINVAL,
+             "gcg_table_lookup_keys_direct: bad argument");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  lookup_dst dst;
+  memset (&dst, 0, sizeof dst);
+  dst.n_src = n_src;
+  int64_t n = 0;
+  for (int r = 0; r < n_src; ++r) {
+    GCG_CHECK (src_count[r] >= 0 && answer_off[r] >= 0 && (d_answer_base[r] || src_count[r] == 0), GCG_EINVAL,
+               "gcg_table_lookup_keys_direct: bad source %d", r);
+    dst.first[r] = n;
+    dst.base[r] = (unsigned long long *) d_answer_base[r] + answer_off[r];
+    n += src_count[r];
+  }
+  dst.first[n_src] = n;
+  if (n == 0) return GCG_OK;
+  GCG_CHECK (d_keys != nullptr, GCG_EINVAL, "gcg_table_lookup_keys_direct: no keys");
+  return lookup_launch (ctx, t, d_keys, n, dst);
+}
+
+// ---- exchange windows: plain cudaMalloc blocks that other processes map through CUDA IPC and other
+//      GPUs reach over NVLink (peer access)
+struct gcg_window { gcg_ctx * ctx = nullptr; void * p = nullptr; int64_t bytes = 0; };
+
+extern "C" int gcg_window_create (gcg_ctx * ctx, int64_t bytes, gcg_window ** out)
+{
+  GCG_CHECK (ctx && out && bytes >= 0, GCG_EINVAL, "gcg_window_create: bad argument");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  gcg_window * w = new gcg_window ();
+  w->ctx = ctx; w->bytes = std::max<int64_t> (bytes, 256);
+  cudaError_t e = cudaMalloc (&w->p, (size_t) w->bytes);
+  if (e != cudaSuccess) {
+    // the parked blocks of the context may be what is in the way
+    cudaGetLastError ();
+    gcg_dcache_release (ctx);
+    cudaStreamSynchronize (ctx->stream);
+    e = cudaMalloc (&w->p, (size_t) w->bytes);
+  }
+  if (e != cudaSuccess) { gcg_set_error ("gcg_window_create: cudaMalloc of %lld bytes failed: %s", (long long) w->bytes, cudaGetErrorString (e)); delete w; return GCG_ENOMEM; }
+  *out = w;
   return GCG_OK;
 }
+
+extern "C" void * gcg_window_ptr (gcg_window * w) { return w ? w->p : nullptr; }
+extern "C" int64_t gcg_window_bytes (gcg_window * w) { return w ? w->bytes : 0; }
+
+extern "C" int gcg_window_export (gcg_window * w, void * handle64)
+{
+  GCG_CHECK (w && handle64, GCG_EINVAL, "gcg_window_export: bad argument");
+  static_assert (sizeof (cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  GCG_CUDA (cudaSetDevice (w->ctx->device));
+  cudaIpcMemHandle_t h;
+  GCG_CUDA (cudaIpcGetMemHandle (&h, w->p));
+  memcpy (handle64, &h, 64);
+  return GCG_OK;
+}
+
+extern "C" int gcg_window_open (gcg_ctx * ctx, const void * handle64, void ** d_peer)
+{
+  GCG_CHECK (ctx && handle64 && d_peer, GCG_EINVAL, "gcg_window_open: bad argument");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy (&h, handle64, 64);
+  GCG_CUDA (cudaIpcOpenMemHandle (d_peer, h, cudaIpcMemLazyEnablePeerAccess));
+  return GCG_OK;
+}
+
+extern "C" int gcg_window_close (gcg_ctx * ctx, void * d_peer)
+{
+  GCG_CHECK (ctx, GCG_EINVAL, "gcg_window_close: ctx == NULL");
+  if (!d_peer) return GCG_OK;
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  GCG_CUDA (cudaIpcCloseMemHandle (d_peer));
+  return GCG_OK;
+}
+
+extern "C" void gcg_window_free (gcg_window * w)
+{
+  if (!w) return;
+  cudaSetDevice (w->ctx->device);
+  cudaStreamSynchronize (w->ctx->stream);
+  cudaFree (w->p);
+  delete w;
+}
+
+// same-process peers (one process driving several GPUs): let this context's device reach `peer_device`
+extern "C" int gcg_peer_enable (gcg_ctx * ctx, int peer_device)
+{
+  GCG_CHECK (ctx, GCG_EINVAL, "gcg_peer_enable: ctx == NULL");
+  if (peer_device == ctx->device) return GCG_OK;
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  int can = 0;
+  GCG_CUDA (cudaDeviceCanAccessPeer (&can, ctx->device, peer_device));
+  GCG_CHECK (can, GCG_ECUDA, "gcg_peer_enable: device %d cannot access device %d", ctx->device, peer_device);
+  cudaError_t e = cudaDeviceEnablePeerAccess (peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError (); e = cudaSuccess; }
+  GCG_CUDA (e);
+  return GCG_OK;
+}
+

@@ -75,6 +75,29 @@ class TorchComm:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM if op == "sum" else self.dist.ReduceOp.MAX)
         return t.cpu().numpy()
 
+    def gather_counts(self, counts: np.ndarray) -> np.ndarray:
+        """-> M[world, world], M[r][d] = elements rank r sends to rank d"""
+        send = torch.as_tensor(np.ascontiguousarray(counts, dtype=np.int64)).to(self.device)
+        out = torch.empty(self.world * self.world, dtype=torch.int64, device=self.device)
+        self.dist.all_gather_into_tensor(out, send)
+        return out.cpu().numpy().reshape(self.world, self.world)
+
+    def barrier(self):
+        self.dist.barrier()
+
+    def share(self, ops, window):
+        """every rank's window as a reference this rank's kernels can store through (CUDA IPC)"""
+        if self.device.type != "cuda":
+            raise RuntimeError("direct exchange needs device windows (NVLink peer memory); use the all-to-all exchange on CPU")
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, ops.window_export(window))
+        return [ops.window_ref(window) if r == self.rank else ops.window_open(handles[r]) for r in range(self.world)]
+
+    def unshare(self, ops, refs):
+        for r, ref in enumerate(refs):
+            if r != self.rank:
+                ops.window_close(ref)
+
 
 class ThreadGroup:
     def __init__(self, world: int):
@@ -133,6 +156,24 @@ class ThreadComm:
         self._done()
         return out
 
+    def gather_counts(self, counts: np.ndarray) -> np.ndarray:
+        allc = self._publish(np.array(counts, dtype=np.int64))
+        out = np.stack(allc)
+        self._done()
+        return out
+
+    def barrier(self):
+        self.sync()
+        self.g.barrier.wait()
+
+    def share(self, ops, window):
+        refs = self._publish(ops.window_ref(window))      # one address space: the reference is the window itself
+        self._done()
+        return refs
+
+    def unshare(self, ops, refs):
+        pass
+
 
 # ------------------------------------------------------------------------------------------------
 # device work (the C ABI)
@@ -177,6 +218,31 @@ class DeviceOps:
     def collect(self, route, answers: torch.Tensor):
         return route.collect(answers.data_ptr())
 
+    # direct exchange: windows other ranks store into over NVLink
+    def window(self, n_words: int):
+        return self.ctx.window(8 * max(int(n_words), 1))
+
+    def window_ref(self, window) -> int:
+        return window.ptr
+
+    def window_export(self, window) -> bytes:
+        return window.export()
+
+    def window_open(self, handle: bytes) -> int:
+        return self.ctx.window_open(handle)
+
+    def window_close(self, ref: int):
+        self.ctx.window_close(ref)
+
+    def route_keys_direct(self, route, owner_refs, owner_off):
+        route.keys_direct(owner_refs, owner_off)
+
+    def lookup_direct(self, table, key_window, src_count, answer_refs, answer_off):
+        table.lookup_keys_direct(key_window.ptr, src_count, answer_refs, answer_off)
+
+    def collect_window(self, route, answer_window):
+        return route.collect(answer_window.ptr)
+
     def stats(self, table):
         return table.stats()
 
@@ -198,12 +264,21 @@ def search_rounds(n_tiles: int, round_kmers: int = ROUND_KMERS):
 class PartitionedKmerIndex:
     """contig k-mer table partitioned over comm.world GPUs by hash of the canonical k-mer"""
 
-    def __init__(self, ops, comm, k: int, round_kmers: int = ROUND_KMERS):
+    def __init__(self, ops, comm, k: int, round_kmers: int = ROUND_KMERS, exchange: str = "all_to_all"):
+        """exchange = "all_to_all": keys and answers travel through send / receive buffers and
+                       `all_to_all_single` (NCCL; gloo in the CPU tests);
+           exchange = "direct": the routing and lookup kernels store straight into the peers' windows
+                       over NVLink / NVSwitch peer memory, the ranks only meet at two barriers per round."""
         if not 1 <= comm.world <= api.MAX_PART:
             raise ValueError("world size %d outside [1,%d]" % (comm.world, api.MAX_PART))
-        self.ops, self.comm, self.k, self.round_kmers = ops, comm, k, round_kmers
+        if exchange not in ("all_to_all", "direct"):
+            raise ValueError("exchange must be 'all_to_all' or 'direct'")
+        self.ops, self.comm, self.k, self.round_kmers, self.exchange = ops, comm, k, round_kmers, exchange
         self.table = None
         self.n_local_records = 0
+        self.qwin = self.awin = None              # direct exchange: my key / answer windows ...
+        self.q_refs = self.a_refs = None          # ... and every rank's, as seen from this rank
+        self.q_cap = self.a_cap = 0
         # GCG_DIST_PROFILE=1: wall-clock per phase with a device sync on both sides (diagnosis only;
         # the syncs serialise what normally overlaps)
         self.profile = os.environ.get("GCG_DIST_PROFILE") == "1"
@@ -248,6 +323,55 @@ class PartitionedKmerIndex:
             self.n_local_records = n
         return self
 
+    # ---- direct exchange ------------------------------------------------------------------------
+    def _drop_windows(self):
+        if self.qwin is None:
+            return
+        comm, ops = self.comm, self.ops
+        ops.sync()
+        comm.barrier()                            # nobody stores into a window that is about to go
+        comm.unshare(ops, self.q_refs)
+        comm.unshare(ops, self.a_refs)
+        comm.barrier()                            # every mapping is closed before the memory is freed
+        self.qwin.free(); self.awin.free()
+        self.qwin = self.awin = self.q_refs = self.a_refs = None
+        self.q_cap = self.a_cap = 0
+
+    def _ensure_windows(self, need_q: int, need_a: int):
+        """need_* are maxima over ALL ranks (computed from the gathered counts), so every rank takes
+        the same branch and the (re)creation is collective"""
+        if self.qwin is not None and need_q <= self.q_cap and need_a <= self.a_cap:
+            return
+        self._drop_windows()
+        self.q_cap, self.a_cap = need_q + need_q // 4 + 1024, need_a + need_a // 4 + 1024
+        self.qwin, self.awin = self.ops.window(self.q_cap), self.ops.window(self.a_cap)
+        self.q_refs = self.comm.share(self.ops, self.qwin)
+        self.a_refs = self.comm.share(self.ops, self.awin)
+
+    def _round_direct(self, reads, t0, t1):
+        ops, comm, me, world = self.ops, self.comm, self.comm.rank, self.comm.world
+        with self._phase("search.plan"):
+            route = ops.plan(reads, self.k, world, t0, t1)
+        with self._phase("search.counts"):
+            M = comm.gather_counts(route.counts)            # M[r][d]: keys of rank r owned by rank d
+            self._ensure_windows(int(M.sum(axis=0).max()), int(M.sum(axis=1).max()))
+        with self._phase("search.route+store"):
+            # my run inside owner d's key window starts behind the runs of the lower ranks
+            ops.route_keys_direct(route, self.q_refs, [int(M[:me, d].sum()) for d in range(world)])
+            ops.sync()
+            comm.barrier()                                  # every key window is complete
+        with self._phase("search.lookup+store"):
+            # the answers of requester r go where r's collect pass expects owner `me`: behind the lower owners
+            ops.lookup_direct(self.table, self.qwin, M[:, me], self.a_refs, [int(M[r, :me].sum()) for r in range(world)])
+            ops.sync()
+            comm.barrier()                                  # every answer window is complete
+        with self._phase("search.collect"):
+            h = ops.collect_window(route, self.awin)
+            ops.sync()
+        comm.bytes_sent += 8 * (int(M[me].sum()) - int(M[me, me])) + 8 * (int(M[:, me].sum()) - int(M[me, me]))
+        route.free()
+        return h
+
     # ---- search: ont.c:141-254 across ranks ------------------------------------------------------
     def search(self, reads, keep_on_device: bool = False):
         """anchors of this rank's read batch in (read,pos) order (read = index in `reads`).
@@ -259,6 +383,13 @@ class PartitionedKmerIndex:
             n_rounds = int(comm.all_reduce([len(rounds)], "max")[0])
             for i in range(n_rounds):
                 t0, t1 = rounds[i] if i < len(rounds) else (0, 0)
+                if self.exchange == "direct":
+                    h = self._round_direct(reads, t0, t1)
+                    n_total += h.n
+                    if not keep_on_device:
+                        parts.append(h.download())
+                    h.free()
+                    continue
                 with self._phase("search.plan"):
                     route = ops.plan(reads, self.k, comm.world, t0, t1)
                 with self._phase("search.counts"):
@@ -294,6 +425,9 @@ class PartitionedKmerIndex:
             return tuple(int(x) for x in self.comm.all_reduce(self.ops.stats(self.table), "sum"))
 
     def free(self):
+        """collective when the direct exchange was used (the windows are unmapped everywhere first)"""
+        with self._stream():
+            self._drop_windows()
         if self.table is not None:
             self.table.free()
             self.table = None

@@ -54,6 +54,11 @@ class _Route:
         pass
 
 
+class _FreeableArray(np.ndarray):
+    def free(self):
+        pass
+
+
 class _Hits:
     def __init__(self, arr):
         self.arr = arr
@@ -146,6 +151,35 @@ class NumpyOps:
         cpos = (v >> np.uint64(1)) & np.uint64(0x3FFFFFFF)
         out["cpos_flags"] = ((cpos << np.uint64(2)) | (v & np.uint64(1)) | (route.orev[hit] << np.uint64(1))).astype(np.uint32)
         return _Hits(out)
+
+    # direct exchange between threads of one process: a window is a numpy array, its reference is itself
+    def window(self, n_words):
+        return np.zeros(max(int(n_words), 1), dtype=np.uint64).view(_FreeableArray)
+
+    def window_ref(self, window):
+        return window
+
+    def route_keys_direct(self, route, owner_refs, owner_off):
+        keys = route.keys[route.order] + np.uint64(1)
+        seg = np.concatenate([[0], np.cumsum(route.counts)])
+        for d in range(len(route.counts)):
+            owner_refs[d][owner_off[d]: owner_off[d] + route.counts[d]] = keys[seg[d]: seg[d + 1]]
+
+    def lookup_direct(self, table, key_window, src_count, answer_refs, answer_off):
+        first = 0
+        for r, n in enumerate(src_count):
+            n = int(n)
+            for i, key in enumerate(key_window[first: first + n].tolist()):
+                if table.multi.get(key, 0) == 1:
+                    answer_refs[r][answer_off[r] + i] = table.val[key]
+                    table.ont[key] = table.ont.get(key, 0) + 1
+                else:
+                    answer_refs[r][answer_off[r] + i] = MISS
+            first += n
+
+    def collect_window(self, route, answer_window):
+        import torch
+        return self.collect(route, torch.from_numpy(answer_window.view(np.int64)))
 
     def stats(self, table):
         total = len(table.multi)

@@ -41,17 +41,20 @@ def shard(reads, world):
     return [reads[r::world] for r in range(world)]
 
 
+@pytest.mark.parametrize("exchange", ["all_to_all", "direct"])
 @pytest.mark.parametrize("world", [1, 2, 3, 5])
 @pytest.mark.parametrize("name,k", [("tiny", 25), ("repeats", 17)])
-def test_partitioned_index_threads(oracle, world, name, k):
+def test_partitioned_index_threads(oracle, world, name, k, exchange):
     inp = synth.make_config(name)
     batches = shard(inp.reads, world)
     want_hits, want_stats = oracle_answer(oracle, inp.contigs, batches, k)
 
     def body(rank, ops, comm):
-        idx = gdist.PartitionedKmerIndex(ops, comm, k, round_kmers=40_000).build(HostSeqs(inp.contigs))
+        idx = gdist.PartitionedKmerIndex(ops, comm, k, round_kmers=40_000, exchange=exchange).build(HostSeqs(inp.contigs))
         hits = idx.search(HostSeqs(batches[rank]))
-        return hits, idx.stats(), idx.n_local_records, comm.bytes_sent
+        out = hits, idx.stats(), idx.n_local_records, comm.bytes_sent
+        idx.free()
+        return out
 
     out = gdist.run_threaded(world, body, torch.device("cpu"), lambda r: NumpyOps(oracle))
     n_ctg_kmers = sum(max(0, len(c) - k + 1) for c in inp.contigs)

@@ -95,9 +95,10 @@ def test_owner_side_insert_lookup_collect(ctx, oracle):
         x.free()
 
 
+@pytest.mark.parametrize("exchange", ["all_to_all", "direct"])
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 @pytest.mark.parametrize("name,k,round_kmers", [("tiny", 25, 1 << 31), ("repeats", 17, 50_000), ("small", 31, 300_000)])
-def test_partitioned_index_one_gpu(oracle, world, name, k, round_kmers):
+def test_partitioned_index_one_gpu(oracle, world, name, k, round_kmers, exchange):
     inp = synth.make_config(name)
     batches = shard(inp.reads, world)
     want_hits, want_stats = oracle_answer(oracle, inp.contigs, batches, k)
@@ -107,7 +108,7 @@ def test_partitioned_index_one_gpu(oracle, world, name, k, round_kmers):
 
     def body(rank, ops, comm):
         cs, rs = ops.ctx.upload(inp.contigs), ops.ctx.upload(batches[rank])
-        idx = gdist.PartitionedKmerIndex(ops, comm, k, round_kmers=round_kmers).build(cs)
+        idx = gdist.PartitionedKmerIndex(ops, comm, k, round_kmers=round_kmers, exchange=exchange).build(cs)
         hits = idx.search(rs)
         st = idx.stats()
         n_dev = idx.search(rs, keep_on_device=True)
@@ -139,20 +140,23 @@ NCCL_SCRIPT = textwrap.dedent("""
     ops = gdist.DeviceOps(ctx, local)
     comm = gdist.TorchComm(ops.device)
     cs, rs = ctx.upload(inp.contigs), ctx.upload(inp.reads[rank::world])
-    idx = gdist.PartitionedKmerIndex(ops, comm, k, round_kmers=400_000).build(cs)
+    idx = gdist.PartitionedKmerIndex(ops, comm, k, round_kmers=400_000, exchange=%(exchange)r).build(cs)
     hits = idx.search(rs)
     st = idx.stats()
     np.save(os.path.join(%(out)r, "hits_%%d.npy" %% rank), hits)
     json.dump({"stats": st, "records": idx.n_local_records, "sent": comm.bytes_sent, "launches": ctx.launches()},
               open(os.path.join(%(out)r, "info_%%d.json" %% rank), "w"))
+    idx.free()
     dist.destroy_process_group()
 """)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
-def test_partitioned_index_nccl_world2(oracle, tmp_path):
+@pytest.mark.parametrize("exchange", ["all_to_all", "direct"])
+def test_partitioned_index_nccl_world2(oracle, tmp_path, exchange):
+    """one process per GPU: NCCL all-to-all, and direct stores into CUDA-IPC windows over NVLink"""
     script = tmp_path / "run.py"
-    script.write_text(NCCL_SCRIPT % {"root": ROOT, "out": str(tmp_path)})
+    script.write_text(NCCL_SCRIPT % {"root": ROOT, "out": str(tmp_path), "exchange": exchange})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29631", str(script)]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
