@@ -223,7 +223,8 @@ def run_ours(args, rank, local_rank, world):
         return float(t.item())
 
     torch.cuda.set_device(local_rank)
-    ctx = api.Context(local_rank, host_threads=min(16, max(1, (os.cpu_count() or 8) // max(world, 1))))
+    host_threads = min(16, max(1, (os.cpu_count() or 8) // max(world, 1)))
+    ctx = api.Context(local_rank, host_threads=host_threads)
     stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local_rank))
 
     contigs, reads, inp = make_workload(rank)
@@ -430,6 +431,7 @@ def run_ours(args, rank, local_rank, world):
                    "l2": "inputs larger than L2 (138 MB ASCII reads + 106 MB table per step vs 126 MB L2); no explicit flush"},
         "e2e": {"value": tot_ont_kmers / e2e_kmer_s, "unit": "k-mers/s", "h2d_bytes_per_step": int(read_bytes + ctg_bytes),
                 "d2h_bytes_per_step": int(n_hit * 16 + 32), "ms_per_step": e2e_kmer_s * 1e3,
+                "host_threads_per_rank": host_threads, "host_cores": os.cpu_count(),
                 "api": "gcg_table_build + gcg_search (host pointers in, pinned anchors out) + gcg_table_stats"},
         "gpu_launches": int(kmer_launches + sw_launches),
         "clocks": clocks,
@@ -496,6 +498,13 @@ def main():
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                      # timing rule: at least three warm-up steps
     rank, local_rank, world = dist_env()
+    # stdout carries the one JSON line and nothing else: native libraries that write to file
+    # descriptor 1 (NCCL prints its version banner there) are pointed at stderr, Python's own
+    # sys.stdout keeps the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
