@@ -138,6 +138,12 @@ struct gcg_table {
   unsigned long long * d_vals = nullptr;
   uint32_t * d_ont = nullptr;
   int64_t n_inserted = 0;                  // k-mer occurrences inserted
+  // Pre-filter for tables beyond the L2 (see table_filter_ensure in kmer.cu): one 32-bit word per
+  // probe, 2 or 3 bits per key, holding only the keys that can anchor (present exactly once).
+  uint32_t * d_filter = nullptr;
+  uint32_t filter_words = 0;
+  int filter_k3 = 0;
+  bool filter_valid = false;               // cleared by every insert
 };
 
 struct gcg_hits {
@@ -154,6 +160,7 @@ int gcg_stage_reserve (gcg_ctx * ctx);
 gcg_workers * gcg_ctx_workers (gcg_ctx * ctx);   // created on first use with ctx->host_threads threads
 void gcg_pipe_free (gcg_ctx * ctx);
 int gcg_table_alloc (gcg_ctx * ctx, int64_t n_kmers, int k, gcg_table ** out);
+int gcg_table_filter_ensure (gcg_ctx * ctx, gcg_table * t);     // builds / refreshes the pre-filter when the table wants one
 int64_t gcg_mask_scan_blocks (int64_t n_words);
 int gcg_mask_scan (gcg_ctx * ctx, const uint32_t * d_mask, int64_t n_words, uint32_t * d_prefix, uint32_t * d_bsum, int64_t * total);
 void * gcg_pinned_alloc (size_t bytes);      // parked-block cache, released with gcg_free

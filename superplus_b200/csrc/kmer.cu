@@ -81,10 +81,16 @@ k23_build_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
 #define K4_UNROLL 4
 #define K4_WARPS 8
 
+// FILTER (tables beyond the L2, where a probe is a random HBM access at ~40 G/s): one L2-resident
+// 32-bit filter word is tested first and the bucket is only loaded when all of the key's bits are
+// set.  The filter holds the keys that are present exactly once, i.e. the only ones that anchor, so
+// with 96 % of ONT k-mers absent (sequencing errors) most probes never leave the L2.
+template <bool FILTER>
 __global__ void __launch_bounds__ (32 * K4_WARPS)
 k45_search_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff,
                    const int32_t * __restrict__ len, const int32_t * __restrict__ tile_seq, int64_t n_seq, int64_t n_words, int k,
-                   const unsigned long long * __restrict__ keys, uint32_t n_bucket, uint32_t * __restrict__ hitmask)
+                   const unsigned long long * __restrict__ keys, uint32_t n_bucket, uint32_t * __restrict__ hitmask,
+                   const uint32_t * __restrict__ filter, uint32_t filter_words, int filter_k3)
 {
   __shared__ uint32_t s_excl[K4_WARPS][33];
   __shared__ uint32_t s_pend[K4_WARPS][32];
@@ -110,13 +116,31 @@ k45_search_kernel (const uint64_t * __restrict__ packed, const int64_t * __restr
         unsigned long long key[K4_UNROLL];
         uint32_t fp[K4_UNROLL];
         bucket4 q[K4_UNROLL];
+        if (FILTER) {
+          uint32_t hh[K4_UNROLL], fw[K4_UNROLL];
 #pragma unroll
-        for (int u = 0; u < K4_UNROLL; ++u) {
-          if (j0 + u) r.step ();                     // harmless past nvalid: state is discarded
-          key[u] = (r.fwd < r.rc ? r.fwd : r.rc) + 1ULL;
-          uint32_t h = kmer_hash32 (key[u] - 1ULL);
-          fp[u] = h & 3u;
-          q[u] = ld_bucket (keys + 4ULL * __umulhi (h, n_bucket));
+          for (int u = 0; u < K4_UNROLL; ++u) {
+            if (j0 + u) r.step ();
+            key[u] = (r.fwd < r.rc ? r.fwd : r.rc) + 1ULL;
+            hh[u] = kmer_hash32 (key[u] - 1ULL);
+            fp[u] = hh[u] & 3u;
+            fw[u] = __ldg (filter + __umulhi (kmer_hash32b (key[u] - 1ULL), filter_words));
+          }
+#pragma unroll
+          for (int u = 0; u < K4_UNROLL; ++u) {
+            const uint32_t m = filter_mask (hh[u], filter_k3);
+            q[u].a = q[u].b = q[u].c = q[u].d = 0ULL;        // no match, no overflow mark
+            if ((fw[u] & m) == m) q[u] = ld_bucket (keys + 4ULL * __umulhi (hh[u], n_bucket));
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < K4_UNROLL; ++u) {
+            if (j0 + u) r.step ();                     // harmless past nvalid: state is discarded
+            key[u] = (r.fwd < r.rc ? r.fwd : r.rc) + 1ULL;
+            uint32_t h = kmer_hash32 (key[u] - 1ULL);
+            fp[u] = h & 3u;
+            q[u] = ld_bucket (keys + 4ULL * __umulhi (h, n_bucket));
+          }
         }
 #pragma unroll
         for (int u = 0; u < K4_UNROLL; ++u) {
@@ -648,7 +672,7 @@ extern "C" int64_t gcg_seqs_kmers (const gcg_seqs * s, int k)
 extern "C" void gcg_table_free (gcg_table * t)
 {
   if (!t) return;
-  gcg_dfree (t->ctx, t->d_keys); gcg_dfree (t->ctx, t->d_vals); gcg_dfree (t->ctx, t->d_ont);
+  gcg_dfree (t->ctx, t->d_keys); gcg_dfree (t->ctx, t->d_vals); gcg_dfree (t->ctx, t->d_ont); gcg_dfree (t->ctx, t->d_filter);
   delete t;
 }
 
@@ -760,6 +784,60 @@ extern "C" int gcg_table_dump (gcg_ctx * ctx, gcg_table * t, int64_t cap, uint64
   return GCG_OK;
 }
 
+// ---- pre-filter for tables beyond the L2 ------------------------------------------------------
+__global__ void __launch_bounds__ (256)
+filter_build_kernel (const unsigned long long * __restrict__ keys, uint64_t n_slot, uint32_t * __restrict__ filter,
+                     uint32_t filter_words, int k3)
+{
+  int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t) n_slot; i += stride) {
+    const unsigned long long kw = keys[i];
+    if (!(kw & GCG_KEY_MASK) || (kw & GCG_KEY_MULTI)) continue;      // only keys present exactly once can anchor
+    const unsigned long long key = (kw & GCG_KEY_MASK) - 1ULL;
+    atomicOr (filter + __umulhi (kmer_hash32b (key), filter_words), filter_mask (kmer_hash32 (key), k3));
+  }
+}
+
+// A table whose key array does not fit the L2 gets a filter of about one byte per inserted k-mer,
+// capped so that the filter itself stays L2 resident (GCG_FILTER_MAX_MB, default 64).
+// GCG_FILTER=0 / 1 forces it off / on for any size.
+int gcg_table_filter_ensure (gcg_ctx * ctx, gcg_table * t)
+{
+  int want = t->n_slot * 8 > ((uint64_t) 80 << 20);
+  if (const char * e = getenv ("GCG_FILTER")) want = atoi (e) != 0;
+  if (!want) { t->filter_valid = false; t->filter_words = 0; return GCG_OK; }
+  if (t->filter_valid) return GCG_OK;
+  if (!t->d_filter) {
+    int64_t max_mb = 64;
+    if (const char * e = getenv ("GCG_FILTER_MAX_MB")) max_mb = std::max<int64_t> (1, atoll (e));
+    int64_t bytes = std::min<int64_t> (std::max<int64_t> (t->n_inserted, 1 << 20), max_mb << 20);
+    t->filter_words = (uint32_t) (bytes / 4);
+    t->filter_k3 = bytes * 8 >= 4 * std::max<int64_t> (t->n_inserted, 1);        // three bits per key from 4 bits of filter per key up
+    GCG_CUDA (gcg_dmalloc (ctx, &t->d_filter, (size_t) t->filter_words * 4));
+  }
+  GCG_CUDA (cudaMemsetAsync (t->d_filter, 0, (size_t) t->filter_words * 4, ctx->stream));
+  {
+    gcg_kscope ks (ctx, "filter_build");
+    filter_build_kernel<<<grid_for (ctx, (int64_t) t->n_slot, 256, 8), 256, 0, ctx->stream>>> (t->d_keys, t->n_slot, t->d_filter, t->filter_words, t->filter_k3);
+    GCG_CUDA (cudaGetLastError ());
+  }
+  t->filter_valid = true;
+  return GCG_OK;
+}
+
+static void launch_k45 (gcg_ctx * ctx, const gcg_table * t, const uint64_t * d_packed, const int64_t * d_woff, const int32_t * d_len,
+                        const int32_t * d_tseq, int64_t n_seq, int64_t n_words, int k, uint32_t * d_mask)
+{
+  gcg_kscope ks (ctx, "k45_search");
+  const int grid = grid_for (ctx, ((n_words + 31) >> 5) * 32, 32 * K4_WARPS, 8);
+  if (t->filter_valid && t->filter_words)
+    k45_search_kernel<true><<<grid, 32 * K4_WARPS, 0, ctx->stream>>> (d_packed, d_woff, d_len, d_tseq, n_seq, n_words, k, t->d_keys, t->n_bucket, d_mask,
+                                                                       t->d_filter, t->filter_words, t->filter_k3);
+  else
+    k45_search_kernel<false><<<grid, 32 * K4_WARPS, 0, ctx->stream>>> (d_packed, d_woff, d_len, d_tseq, n_seq, n_words, k, t->d_keys, t->n_bucket, d_mask,
+                                                                        nullptr, 0, 0);
+}
+
 // ---- search -----------------------------------------------------------------------------------
 // exclusive prefix sum of popcount(mask[w]) into prefix[w]; *total = number of set bits.  bsum holds
 // (n_words + SCAN_TILE - 1) / SCAN_TILE words of scratch.  Synchronises the stream.
@@ -826,9 +904,8 @@ extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * r
     rc = GCG_ENOMEM;
   }
   while (!rc) {
-    { gcg_kscope ks (ctx, "k45_search");
-      k45_search_kernel<<<grid_for (ctx, ((n_words + 31) >> 5) * 32, 32 * K4_WARPS, 8), 32 * K4_WARPS, 0, ctx->stream>>> (
-          reads->d_packed, reads->d_woff, reads->d_len, reads->d_tseq, reads->n, n_words, k, t->d_keys, t->n_bucket, d_mask); }
+    if ((rc = gcg_table_filter_ensure (ctx, t)) != 0) break;
+    launch_k45 (ctx, t, reads->d_packed, reads->d_woff, reads->d_len, reads->d_tseq, reads->n, n_words, k, d_mask);
     if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_search: kernel launch failed"); rc = GCG_ECUDA; break; }
     int64_t n_hit = 0;
     gcg_trace_mark (ctx, "  search_seqs: alloc + launch");
@@ -1012,6 +1089,7 @@ extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * re
   }
   if (total_kmers == 0) return GCG_OK;
   int rc = pipe_reserve (ctx, std::max (chunk_words, max_words));
+  if (!rc) rc = gcg_table_filter_ensure (ctx, t);
   if (rc) return rc;
   gcg_pipe * p = ctx->pipe;
   const int64_t cap_words = std::max (chunk_words, max_words);       // <= p->cap_words
@@ -1095,9 +1173,7 @@ extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * re
     const int32_t * d_tseq = (const int32_t *) (q.d_meta + d.tseq_off);
     int e = launch_pack (ctx, q.d_ascii, q.d_packed, nw);
     if (e) return e;
-    { gcg_kscope ks (ctx, "k45_search");
-      k45_search_kernel<<<grid_for (ctx, d.n_tiles * 32, 32 * K4_WARPS, 8), 32 * K4_WARPS, 0, ctx->stream>>> (
-          q.d_packed, d_woff, d_len, d_tseq, nr, nw, k, t->d_keys, t->n_bucket, q.d_mask); }
+    launch_k45 (ctx, t, q.d_packed, d_woff, d_len, d_tseq, nr, nw, k, q.d_mask);
     if ((e = mask_scan_launch (ctx, q.d_mask, nw, q.d_prefix, q.d_bsum, q.d_count)) != 0) return e;
     GCG_CUDA (cudaMemcpyAsync (p->h_count + d.slot, q.d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
     GCG_CUDA (cudaEventRecord (q.ev_count, ctx->stream));

@@ -34,6 +34,22 @@ __device__ __forceinline__ uint32_t kmer_hash32 (uint64_t key)
   return h;
 }
 
+// second, independent 32-bit hash (word index of the pre-filter) and the filter bits of a key
+__device__ __forceinline__ uint32_t kmer_hash32b (uint64_t key)
+{
+  uint32_t h = (uint32_t) (key >> 32) * 0x85EBCA6Bu ^ (uint32_t) key * 0xC2B2AE35u;
+  h ^= h >> 15; h *= 0x2C1B3C6Du;
+  h ^= h >> 12;
+  return h;
+}
+
+__device__ __forceinline__ uint32_t filter_mask (uint32_t h, int k3)
+{
+  uint32_t m = (1u << (h & 31u)) | (1u << ((h >> 5) & 31u));
+  if (k3) m |= 1u << ((h >> 10) & 31u);
+  return m;
+}
+
 // largest s in [0,n) with woff[s] <= w  (woff has n+1 entries, woff[n] > w)
 __device__ __forceinline__ int64_t find_seq (const int64_t * __restrict__ woff, int64_t n, int64_t w)
 {

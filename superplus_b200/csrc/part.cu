@@ -660,6 +660,7 @@ extern "C" int gcg_table_insert_records (gcg_ctx * ctx, gcg_table * t, const voi
   GCG_CHECK (n <= t->n_inserted, GCG_ERANGE, "gcg_table_insert_records: %lld records into a table created for %lld", (long long) n, (long long) t->n_inserted);
   GCG_CUDA (cudaSetDevice (ctx->device));
   if (n == 0) return GCG_OK;
+  t->filter_valid = false;
   gcg_kscope ks (ctx, "part_insert");
   insert_records_kernel<<<flat_grid (ctx, n, 1), 256, 0, ctx->stream>>> ((const ulonglong2 *) d_records, n, t->d_keys, t->d_vals, t->n_bucket);
   GCG_CUDA (cudaGetLastError ());

@@ -748,9 +748,10 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
         cudaMemPoolGetAttribute (pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
         cudaMemPoolGetAttribute (pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
       free_b += (size_t) (reserved - used);
+    free_b += ctx->dparked_bytes;          // so are the blocks parked in the context's own cache (released on demand)
     free_b += b->s_trace.cap;              // this batch's own trace buffer is reused or replaced
   }
-  unsigned long long budget_words = (unsigned long long) (std::min<size_t> (free_b / 2, (size_t) 64 << 30) / 4);
+  unsigned long long budget_words = (unsigned long long) (std::min<size_t> (free_b / 4 * 3, (size_t) 64 << 30) / 4);
   if (const char * e = getenv ("GCG_SW_TRACE_BUDGET_MB")) budget_words = (unsigned long long) atoll (e) * (1 << 20) / 4;
   auto trace_words = [] (const sw_task & t) -> unsigned long long {
     if (t.qlen == 0 || t.tlen == 0) return 0;

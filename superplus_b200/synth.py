@@ -183,6 +183,8 @@ CONFIGS = {
     "cfg2": dict(genome_len=4_600_000, n_gaps=500, coverage=30.0, seed=43),
     "cfg4": dict(genome_len=100_000_000, n_gaps=0, coverage=40.0, seed=44),
     "cfg5": dict(genome_len=250_000_000, n_gaps=20_000, coverage=20.0, seed=45),
+    # cfg4 with a tenth of the reads: the 100 Mb table (HBM resident, 1.6 GB of keys) on one GPU
+    "cfg4s": dict(genome_len=100_000_000, n_gaps=0, coverage=4.0, seed=44),
     # small cases for unit tests
     "tiny": dict(genome_len=60_000, n_gaps=4, coverage=8.0, seed=7),
     "small": dict(genome_len=200_000, n_gaps=10, coverage=10.0, seed=11),

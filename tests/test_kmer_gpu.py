@@ -107,3 +107,23 @@ def test_error_paths(ctx):
         ctx.search(t, rs)
     t.k = 25
     t.free(); cs.free(); rs.free()
+
+
+@pytest.mark.parametrize("max_mb", ["64", "1"])
+def test_prefilter_forced_on(ctx, oracle, max_mb, monkeypatch):
+    """tables beyond the L2 are probed through a Bloom-style pre-filter of the anchoring keys;
+    forced on here (also with a tiny, collision-heavy filter) the results must not change"""
+    monkeypatch.setenv("GCG_FILTER", "1")
+    monkeypatch.setenv("GCG_FILTER_MAX_MB", max_mb)
+    for name, k in (("repeats", 17), ("small", 31), ("tiny", 5)):
+        inp = synth.make_config(name)
+        check_case(ctx, oracle, inp.contigs, inp.reads, k)
+    inp = synth.make_config("small")
+    cs = ctx.upload(inp.contigs)
+    t = ctx.table_build(cs, 25)
+    a = ctx.search_host(t, inp.reads)
+    monkeypatch.setenv("GCG_FILTER", "0")
+    t2 = ctx.table_build(cs, 25)
+    b = ctx.search_host(t2, inp.reads)
+    assert np.array_equal(a, b) and t.stats() == t2.stats()
+    t.free(); t2.free(); cs.free()
