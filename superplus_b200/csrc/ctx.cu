@@ -185,11 +185,17 @@ void gcg_dcache_release (gcg_ctx * ctx)
     for (void * p : kv.second) { ctx->dclass.erase (p); cudaFreeAsync (p, ctx->stream); }
   ctx->dparked.clear ();
   ctx->dparked_bytes = 0;
+  if (ctx->dbig) { ctx->dclass.erase (ctx->dbig); cudaFreeAsync (ctx->dbig, ctx->stream); ctx->dbig = nullptr; ctx->dbig_cls = 0; }
 }
 
 cudaError_t gcg_dmalloc_bytes (gcg_ctx * ctx, void ** p, size_t bytes)
 {
   const size_t cls = size_class (bytes);
+  if (ctx->dbig && cls > ctx->dparked_limit / 2 && ctx->dbig_cls >= cls && ctx->dbig_cls / 2 <= cls) {
+    *p = ctx->dbig;
+    ctx->dbig = nullptr; ctx->dbig_cls = 0;
+    return cudaSuccess;
+  }
   auto it = ctx->dparked.find (cls);
   if (it != ctx->dparked.end () && !it->second.empty ()) {
     *p = it->second.back ();
@@ -215,9 +221,10 @@ void gcg_dfree (gcg_ctx * ctx, void * p)
   auto it = ctx->dclass.find (p);
   if (it == ctx->dclass.end ()) { cudaFreeAsync (p, ctx->stream); return; }
   const size_t cls = it->second;
-  if (cls > ctx->dparked_limit / 2) {                    // e.g. the 64 GB trace of an SW batch: never parked
-    ctx->dclass.erase (it);
-    cudaFreeAsync (p, ctx->stream);
+  if (cls > ctx->dparked_limit / 2) {                    // e.g. the 64 GB trace of an SW batch: one spare, not the cache
+    void * drop = p;
+    if (cls > ctx->dbig_cls) { drop = ctx->dbig; ctx->dbig = p; ctx->dbig_cls = cls; }     // keep the larger of the two
+    if (drop) { ctx->dclass.erase (drop); cudaFreeAsync (drop, ctx->stream); }
     return;
   }
   ctx->dparked[cls].push_back (p);

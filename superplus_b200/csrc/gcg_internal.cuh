@@ -66,6 +66,10 @@ struct gcg_ctx {
   std::map<size_t, std::vector<void *>> dparked;
   std::unordered_map<void *, size_t> dclass;   // every block handed out or parked -> its class size
   size_t dparked_bytes = 0, dparked_limit = (size_t) 24 << 30;
+  // one spare for blocks too large to park (the tens of GB of SW trace of a batch): the next batch
+  // of the same shape takes it over instead of paying cudaMallocAsync for 60 GB again (20-40 ms)
+  void * dbig = nullptr;
+  size_t dbig_cls = 0;
 };
 
 // RAII scope around one kernel launch: counts it and, when profiling is on, brackets it

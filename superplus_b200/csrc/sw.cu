@@ -738,9 +738,11 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
 
   gcg_trace_mark (ctx, "sw.align: classify");
   // ---- memory plan: trace + edge buffers for one wave
-  size_t free_b = 0, total_b = 0;
-  GCG_CUDA (cudaMemGetInfo (&free_b, &total_b));
-  {
+  // (the driver is only asked for the free memory when no trace buffer is at hand: cudaMemGetInfo
+  // was measured at 0.1 .. 11 ms per call)
+  auto query_budget_words = [&] () -> unsigned long long {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo (&free_b, &total_b) != cudaSuccess) { cudaGetLastError (); return (unsigned long long) ((size_t) 8 << 30) / 4; }
     // memory parked in the stream-ordered pool is as good as free: the next allocation reuses it
     cudaMemPool_t pool;
     unsigned long long reserved = 0, used = 0;
@@ -748,17 +750,22 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
         cudaMemPoolGetAttribute (pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
         cudaMemPoolGetAttribute (pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
       free_b += (size_t) (reserved - used);
-    free_b += ctx->dparked_bytes;          // so are the blocks parked in the context's own cache (released on demand)
-    free_b += b->s_trace.cap;              // this batch's own trace buffer is reused or replaced
-  }
-  unsigned long long budget_words = (unsigned long long) (std::min<size_t> (free_b / 4 * 3, (size_t) 64 << 30) / 4);
-  if (const char * e = getenv ("GCG_SW_TRACE_BUDGET_MB")) budget_words = (unsigned long long) atoll (e) * (1 << 20) / 4;
+    free_b += ctx->dparked_bytes + ctx->dbig_cls;   // so are the blocks parked in the context's own cache (released on demand)
+    free_b += b->s_trace.cap;                       // this batch's own trace buffer is reused or replaced
+    return (unsigned long long) (std::min<size_t> (free_b / 4 * 3, (size_t) 64 << 30) / 4);
+  };
   auto trace_words = [] (const sw_task & t) -> unsigned long long {
     if (t.qlen == 0 || t.tlen == 0) return 0;
     return (unsigned long long) ((t.qlen + SW_BAND - 1) / SW_BAND) * (unsigned long long) (t.tlen + 31) * 32ULL;
   };
   unsigned long long max_single = 0;
   for (auto & t : tasks) max_single = std::max (max_single, trace_words (t));
+  unsigned long long total_trace = 0; long long total_edges = 0;
+  for (auto & t : tasks) { total_trace += trace_words (t); total_edges += (long long) t.qlen + t.tlen; }
+  // a buffer that holds the whole batch is already there (this batch's, or the context's spare)?
+  const unsigned long long at_hand = std::max<unsigned long long> (b->s_trace.cap, ctx->dbig_cls > b->s_trace.cap ? ctx->dbig_cls - ctx->dbig_cls / 8 : 0) / 4;
+  unsigned long long budget_words = at_hand >= total_trace ? std::max<unsigned long long> (total_trace, 32) : query_budget_words ();
+  if (const char * e = getenv ("GCG_SW_TRACE_BUDGET_MB")) budget_words = (unsigned long long) atoll (e) * (1 << 20) / 4;
   GCG_CHECK (2 * max_single <= budget_words || max_single == 0, GCG_ENOMEM, "gcg_swbatch_align: one alignment needs %llu MB of trace, more than the budget",
              (unsigned long long) (max_single * 4 >> 20));
 
@@ -772,8 +779,6 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
   int2 * d_bound = nullptr;
   uint2 * d_pbound = nullptr;
   sw_task * d_wave_tasks = nullptr;
-  unsigned long long total_trace = 0; long long total_edges = 0;
-  for (auto & t : tasks) { total_trace += trace_words (t); total_edges += (long long) t.qlen + t.tlen; }
   unsigned long long trace_cap = std::min (budget_words, std::max<unsigned long long> (total_trace, 32));
   int rc = GCG_OK;
   cudaError_t ce;
