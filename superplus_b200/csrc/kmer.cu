@@ -39,28 +39,26 @@ k1_pack_kernel (const uint4 * __restrict__ ascii, uint64_t * __restrict__ packed
 // =============================================================================================
 // K2+K3  contig chop + table insert
 // =============================================================================================
+// One thread per k-mer start position (lane j of a warp takes position j of the warp's word): the
+// inserts of a word are independent chains of load -> CAS -> store, so they are spread over the
+// lanes instead of being walked by one thread (a 4.6 Mb scaffold is only 144 k words).
 __global__ void __launch_bounds__ (256)
 k23_build_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff,
-                  const int32_t * __restrict__ len, int64_t n_seq, int64_t n_words, int k,
+                  const int32_t * __restrict__ len, const int32_t * __restrict__ tile_seq, int64_t n_seq, int64_t n_words, int k,
                   unsigned long long * __restrict__ keys, unsigned long long * __restrict__ vals, uint32_t n_bucket)
 {
-  int64_t stride = (int64_t) gridDim.x * blockDim.x;
-  for (int64_t w = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
-    int64_t s = find_seq (woff, n_seq, w);
+  const int lane = threadIdx.x & 31;
+  const int64_t wstride = (int64_t) gridDim.x * (blockDim.x >> 5);
+  for (int64_t w = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_words; w += wstride) {
+    int64_t s = find_seq_from (woff, n_seq, w, __ldg (tile_seq + (w >> 5)));
     int32_t L = __ldg (len + s);
     int32_t p0 = (int32_t) ((w - __ldg (woff + s)) << 5);
     int32_t nvalid = L - k + 1 - p0;             // number of valid starts in this word
-    if (nvalid <= 0) continue;
-    if (nvalid > 32) nvalid = 32;
-    kroll r;
-    r.init (packed[w], packed[w + 1], k);
-    for (int j = 0; j < nvalid; ++j) {
-      if (j) r.step ();
-      bool fw = r.fwd < r.rc;
-      unsigned long long key = (fw ? r.fwd : r.rc) + 1ULL;
-      unsigned long long val = ((unsigned long long) s << 32) | ((unsigned long long) (uint32_t) (p0 + j) << 1) | (fw ? 0ULL : 1ULL);
-      table_insert (keys, vals, n_bucket, key, val);
-    }
+    if (lane >= nvalid) continue;
+    bool fw;
+    unsigned long long key = key_at (__ldg (packed + w), __ldg (packed + w + 1), lane, k, &fw);
+    unsigned long long val = ((unsigned long long) s << 32) | ((unsigned long long) (uint32_t) (p0 + lane) << 1) | (fw ? 0ULL : 1ULL);
+    table_insert (keys, vals, n_bucket, key, val);
   }
 }
 
@@ -715,8 +713,8 @@ extern "C" int gcg_table_build_seqs (gcg_ctx * ctx, const gcg_seqs * contigs, in
   if (rc) return rc;
   if (contigs->n_words > 0 && n_kmers > 0) {
     gcg_kscope ks (ctx, "k23_build");
-    k23_build_kernel<<<grid_for (ctx, contigs->n_words, 256, 8), 256, 0, ctx->stream>>> (
-        contigs->d_packed, contigs->d_woff, contigs->d_len, contigs->n, contigs->n_words, k, t->d_keys, t->d_vals, t->n_bucket);
+    k23_build_kernel<<<grid_for (ctx, contigs->n_words * 32, 256, 8), 256, 0, ctx->stream>>> (
+        contigs->d_packed, contigs->d_woff, contigs->d_len, contigs->d_tseq, contigs->n, contigs->n_words, k, t->d_keys, t->d_vals, t->n_bucket);
     GCG_CUDA (cudaGetLastError ());
   }
   *out = t;

@@ -157,6 +157,16 @@ __device__ __forceinline__ unsigned long long key_at (uint64_t wh, uint64_t wl, 
 }
 
 
+// coherent 256-bit bucket load for the build (the table is being written by other threads: L2 is
+// the point of coherence, so .cg; one request instead of up to four dependent 8-byte loads)
+__device__ __forceinline__ bucket4 ld_bucket_cg (const unsigned long long * p)
+{
+  bucket4 r;
+  asm volatile ("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
+                : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p) : "memory");
+  return r;
+}
+
 // insert one (key+1, val) pair: claim an empty slot with atomicCAS, or flag the key as seen more
 // than once (kmer.c:124-152 -> hash.c:113-152 counts occurrences; only {1, >=2} is observable)
 __device__ __forceinline__ void table_insert (unsigned long long * __restrict__ keys, unsigned long long * __restrict__ vals,
@@ -166,23 +176,26 @@ __device__ __forceinline__ void table_insert (unsigned long long * __restrict__ 
   uint32_t b = __umulhi (hsh, n_bucket);
   for (;;) {
     unsigned long long * slot = keys + 4ULL * b;
+    const bucket4 q = ld_bucket_cg (slot);
+    unsigned long long cur[4] = {q.a, q.b, q.c, q.d};
     bool done = false;
 #pragma unroll
     for (int i = 0; i < 4 && !done; ++i) {
-      unsigned long long cur = __ldcg (slot + i);
-      if (cur == 0ULL) {
+      if (cur[i] == 0ULL) {
+        // slots fill front to back, so an empty slot ends the bucket: claim it (or see who did)
         unsigned long long old = atomicCAS (slot + i, 0ULL, key);
         if (old == 0ULL) { vals[4ULL * b + i] = val; done = true; break; }
-        cur = old;
+        cur[i] = old;
       }
-      if ((cur & GCG_KEY_MASK) == key) {
-        if (!(cur & GCG_KEY_MULTI)) atomicOr (slot + i, GCG_KEY_MULTI);
+      if ((cur[i] & GCG_KEY_MASK) == key) {
+        if (!(cur[i] & GCG_KEY_MULTI)) atomicOr (slot + i, GCG_KEY_MULTI);
         done = true;
       }
     }
     if (done) return;
     // bucket is full of other keys: leave the key's overflow mark (bit 62 of slot `fp`) and move on
-    if (!(__ldcg (slot + fp) & GCG_KEY_OVF)) atomicOr (slot + fp, GCG_KEY_OVF);
+    const unsigned long long cf = (fp & 2u) ? ((fp & 1u) ? cur[3] : cur[2]) : ((fp & 1u) ? cur[1] : cur[0]);
+    if (!(cf & GCG_KEY_OVF)) atomicOr (slot + fp, GCG_KEY_OVF);
     b = (b + 1 == n_bucket) ? 0 : b + 1;
   }
 }

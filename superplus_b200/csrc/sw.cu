@@ -240,7 +240,8 @@ __device__ __forceinline__ uint32_t pack16 (int v) { return ((uint32_t) v & 0xFF
 __device__ __forceinline__ int half_lo (uint32_t x) { return (int) (short) (x & 0xFFFFu); }
 __device__ __forceinline__ int half_hi (uint32_t x) { return ((int) x) >> 16; }
 
-__global__ void __launch_bounds__ (32, 20)
+template <int MINB>
+__global__ void __launch_bounds__ (32, MINB)
 sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restrict__ tgt,
                        const sw_task * __restrict__ tasks, const int2 * __restrict__ items, int n_items,
                        int * __restrict__ counter, uint32_t * __restrict__ trace, int * __restrict__ edges,
@@ -497,6 +498,20 @@ sw_maxsym_kernel (const uint8_t * __restrict__ qry, const long long * __restrict
 // =============================================================================================
 // host side
 // =============================================================================================
+// resident warps per SM of the packed kernel = its register budget (GCG_SW_OCC: 20 | 24).  Measured on
+// cfg3-shaped waves: 20 warps at 96 registers 62.9 ms; 24 warps at 80 registers (76 bytes spilled) 69.8 ms
+// for the same 2960-warp wave — and a wave that fills 24 warps per SM needs 74 GB of trace.
+typedef void (* sw_packed_fn_t) (const uint8_t *, const uint8_t *, const sw_task *, const int2 *, int, int *, uint32_t *, int *, uint2 *, int, sw_end *);
+static sw_packed_fn_t sw_packed_fn ()
+{
+  static int occ = -1;
+  if (occ < 0) { const char * e = getenv ("GCG_SW_OCC"); occ = e ? atoi (e) : 20; }
+  switch (occ) {
+    case 24: return sw_fill_packed_kernel<24>;
+    default: return sw_fill_packed_kernel<20>;
+  }
+}
+
 // device scratch that survives between align calls on the same batch (cudaMalloc of tens of GB of
 // trace is far more expensive than the kernels that fill it)
 // (all of it comes from the context's stream-ordered pool, which never trims: a batch that is
@@ -828,7 +843,7 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
   if (!rc && !packed_ids.empty ()) {
     int max_t = 32, per_sm = 0;
     for (int id : packed_ids) max_t = std::max (max_t, tasks[(size_t) id].tlen);
-    GCG_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, sw_fill_packed_kernel, 32, (size_t) ((max_t + 31) & ~31) * 2));
+    GCG_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, sw_packed_fn (), 32, (size_t) ((max_t + 31) & ~31) * 2));
     packed_slots = ctx->sm_count * std::max (per_sm, 1);
   }
 
@@ -873,15 +888,15 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
       GCG_CUDA (cudaMemcpyAsync (d_items, pitems.data (), pitems.size () * sizeof (int2), cudaMemcpyHostToDevice, ctx->stream));
       size_t smem = (size_t) rows_cap * 2;
       int per_sm = 0;
-      GCG_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, sw_fill_packed_kernel, 32, smem));
+      GCG_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, sw_packed_fn (), 32, smem));
       if (per_sm < 1) per_sm = 1;
       int grid = (int) std::min<size_t> (pitems.size (), (size_t) ctx->sm_count * per_sm);
       if ((ce = b->s_pbound.reserve (ctx, (size_t) ctx->sm_count * per_sm * rows_cap * sizeof (uint2))) != cudaSuccess) {
         gcg_set_error ("gcg_swbatch_align: boundary scratch: %s", cudaGetErrorString (ce)); rc = GCG_ENOMEM; break; }
       d_pbound = (uint2 *) b->s_pbound.p;
       gcg_kscope ks (ctx, "k7_sw_fill_packed");
-      sw_fill_packed_kernel<<<grid, 32, smem, ctx->stream>>> (b->d_qry, b->d_tgt, d_tasks, (const int2 *) d_items, (int) pitems.size (),
-                                                              d_counter, d_trace, d_edges, d_pbound, rows_cap, b->d_ends);
+      sw_packed_fn ()<<<grid, 32, smem, ctx->stream>>> (b->d_qry, b->d_tgt, d_tasks, (const int2 *) d_items, (int) pitems.size (),
+                                                        d_counter, d_trace, d_edges, d_pbound, rows_cap, b->d_ends);
       GCG_CUDA (cudaGetLastError ());
     }
     if (!gitems.empty ()) {
