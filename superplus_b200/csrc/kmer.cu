@@ -471,7 +471,7 @@ static void gather_range (const seq_src & src, const std::vector<int64_t> & woff
   }
 }
 
-// Streams the flat ASCII layout to the device in 64 MiB chunks through the pinned ring and calls
+// Streams the flat ASCII layout to the device in ring-sized chunks (16 MiB) through the pinned ring and calls
 // `consume(d_chunk, w0, nw)` (enqueued on ctx->stream) for each chunk.
 template <class F>
 static int stream_ascii (gcg_ctx * ctx, const seq_src & src, const std::vector<int64_t> & woff,
@@ -1006,7 +1006,7 @@ static int pipe_reserve (gcg_ctx * ctx, int64_t cap_words)
   gcg_pipe * p = new gcg_pipe ();
   ctx->pipe = p;
   p->cap_words = cap_words;
-  p->meta_cap = (size_t) 8 << 20;
+  p->meta_cap = (size_t) 2 << 20;
   const size_t tiles = (size_t) ((cap_words + 31) >> 5);
   if (p->meta_cap < tiles * 4 + (1 << 20)) p->meta_cap = tiles * 4 + (1 << 20);
   GCG_CUDA (cudaStreamCreateWithFlags (&p->up, cudaStreamNonBlocking));

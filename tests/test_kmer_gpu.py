@@ -127,3 +127,48 @@ def test_prefilter_forced_on(ctx, oracle, max_mb, monkeypatch):
     b = ctx.search_host(t2, inp.reads)
     assert np.array_equal(a, b) and t.stats() == t2.stats()
     t.free(); t2.free(); cs.free()
+
+
+def test_randomised_small_cases(ctx, oracle, monkeypatch):
+    """many tiny inputs with every k, lengths around the 32-base word and 1024-base tile boundaries,
+    empty and shorter-than-k sequences, repeats, N and lowercase: device search, host pipeline with
+    tiny chunks, and the partition routing must all agree with the oracle"""
+    from part_double import HostSeqs, NumpyOps
+    rng = np.random.default_rng(2024)
+    alphabet = np.frombuffer(b"ACGTACGTACGTacgtN", dtype=np.uint8)
+    lens_pool = [0, 1, 2, 24, 25, 30, 31, 32, 33, 34, 63, 64, 65, 95, 96, 97, 127, 128, 129, 1023, 1024, 1025, 1056, 2047, 2049]
+    monkeypatch.setenv("GCG_SEARCH_CHUNK_BYTES", "2048")
+    dbl = NumpyOps(oracle)
+    for case in range(60):
+        k = int(rng.integers(1, 32))
+        base = alphabet[rng.integers(0, len(alphabet), size=int(rng.integers(200, 3000)))]
+        contigs = []
+        for _ in range(int(rng.integers(1, 12))):
+            l = int(rng.choice(lens_pool)) if rng.random() < 0.6 else int(rng.integers(0, 400))
+            a = int(rng.integers(0, max(1, len(base) - l + 1)))
+            contigs.append(base[a:a + l].copy())
+        reads = []
+        for _ in range(int(rng.integers(0, 40))):
+            l = int(rng.choice(lens_pool)) if rng.random() < 0.5 else int(rng.integers(0, 300))
+            a = int(rng.integers(0, max(1, len(base) - l + 1)))
+            r = base[a:a + l].copy()
+            if len(r) and rng.random() < 0.5:
+                r[rng.integers(0, len(r), size=max(1, len(r) // 12))] = ord("A")
+            if rng.random() < 0.3:
+                r = synth.revcomp(np.char.upper(r.view("S1")).view(np.uint8)) if len(r) else r
+            reads.append(r)
+        n_hit = check_case(ctx, oracle, contigs, reads, k, via_ptrs=bool(case & 1))
+        # host pipeline (chunks of 2 KiB: slot reuse, reads larger than a chunk)
+        cs = ctx.upload(contigs)
+        t = ctx.table_build(cs, k)
+        host = ctx.search_host(t, reads)
+        rs0 = ctx.upload(reads)
+        assert len(host) == n_hit and np.array_equal(host, ctx.search(t, rs0))
+        rs0.free(); t.free()
+        # partition routing of the reads
+        rs = ctx.upload(reads)
+        n_part = int(rng.integers(1, 17))
+        want = dbl.plan(HostSeqs(reads), k, n_part, 0, rs.tiles)
+        got = ctx.route_plan(rs, k, n_part, 0, rs.tiles)
+        assert np.array_equal(got.counts, want.counts), (case, k, n_part)
+        got.free(); rs.free(); cs.free()
