@@ -777,9 +777,16 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
   for (auto & t : tasks) max_single = std::max (max_single, trace_words (t));
   unsigned long long total_trace = 0; long long total_edges = 0;
   for (auto & t : tasks) { total_trace += trace_words (t); total_edges += (long long) t.qlen + t.tlen; }
-  // a buffer that holds the whole batch is already there (this batch's, or the context's spare)?
-  const unsigned long long at_hand = std::max<unsigned long long> (b->s_trace.cap, ctx->dbig_cls > b->s_trace.cap ? ctx->dbig_cls - ctx->dbig_cls / 8 : 0) / 4;
-  unsigned long long budget_words = at_hand >= total_trace ? std::max<unsigned long long> (total_trace, 32) : query_budget_words ();
+  // A trace buffer that is already there — this batch's from an earlier align, or the context's spare
+  // from a batch that was freed — sets the budget as long as it holds whole alignments: asking the
+  // driver again would give a slightly different answer every time (free memory moves), and a
+  // different wave size means freeing and re-allocating tens of GB (20-40 ms per align).
+  const unsigned long long need_min = std::max<unsigned long long> (2 * max_single, 32);
+  const unsigned long long own = b->s_trace.cap / 4, spare = ctx->dbig_cls / 4;      // (a parked block has exactly its class size)
+  unsigned long long budget_words;
+  if (own >= need_min) budget_words = own;
+  else if (spare >= need_min) budget_words = spare;
+  else budget_words = query_budget_words ();
   if (const char * e = getenv ("GCG_SW_TRACE_BUDGET_MB")) budget_words = (unsigned long long) atoll (e) * (1 << 20) / 4;
   GCG_CHECK (2 * max_single <= budget_words || max_single == 0, GCG_ENOMEM, "gcg_swbatch_align: one alignment needs %llu MB of trace, more than the budget",
              (unsigned long long) (max_single * 4 >> 20));
