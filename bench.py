@@ -299,27 +299,19 @@ def run_ours(args, rank, local_rank, world):
         ops = gdist.DeviceOps(ctx, local_rank)
         comm = gdist.TorchComm(ops.device) if dist is not None else gdist.ThreadComm(gdist.ThreadGroup(1), 0, ops.device, ops.sync)
         for exchange in ("direct", "all_to_all"):
-            idx_keep = [None]
+            # one index per exchange mode; every step rebuilds its table from the packed contigs (as the
+            # replicated leg does) while the exchange windows of the direct mode stay mapped
+            idx = gdist.PartitionedKmerIndex(ops, comm, K, exchange=exchange)
 
             def part_step():
                 cs = ctx.pack(a_ctg)
                 rs = ctx.pack(a_reads)
-                # the exchange windows of the direct mode live as long as the index: build it once per
-                # step like the replicated leg, but keep the previous one's windows (grown, mapped) alive
-                idx = gdist.PartitionedKmerIndex(ops, comm, K, exchange=exchange)
-                if idx_keep[0] is not None:
-                    prev = idx_keep[0]
-                    idx.qwin, idx.awin, idx.q_refs, idx.a_refs, idx.q_cap, idx.a_cap = prev.qwin, prev.awin, prev.q_refs, prev.a_refs, prev.q_cap, prev.a_cap
-                    prev.qwin = prev.awin = prev.q_refs = prev.a_refs = None
-                    prev.free()
                 idx.build(cs)
                 nh = idx.search(rs, keep_on_device=True)
                 st4 = idx.stats()
                 if idx.profile and rank == 0:
                     print("[dist profile %s, ms] " % exchange + "  ".join("%s %.2f" % kv for kv in sorted(idx.timers.items())), file=sys.stderr)
-                if idx.table is not None:
-                    idx.table.free(); idx.table = None
-                idx_keep[0] = idx
+                    idx.timers.clear()
                 cs.free(); rs.free()
                 return nh, st4
 
@@ -341,7 +333,7 @@ def run_ours(args, rank, local_rank, world):
             part[exchange] = {"ms_per_step": part_ms, "launches": ctx.launches() - pl0, "stats": list(p_st),
                               "bytes_sent_per_step": allsum(float(comm.bytes_sent - sent0)) / args.steps,
                               "kernel_ms_per_step": {k_: v[0] / args.steps for k_, v in sorted(pprof.items())}}
-            idx_keep[0].free()
+            idx.free()
 
     # ---- timed: SW steps
     ctx.prof_reset()

@@ -303,6 +303,9 @@ class PartitionedKmerIndex:
         """`contigs`: the full contig set, uploaded on every rank (2 bits per base; the *table* is
         what is partitioned).  Each rank chops 1/world of the tiles."""
         ops, comm = self.ops, self.comm
+        if self.table is not None:              # rebuilding: the exchange windows of the direct mode are kept
+            self.table.free()
+            self.table = None
         with self._stream():
             t0, t1 = tile_slice(ops.tiles(contigs), comm.rank, comm.world)
             with self._phase("build.plan"):
