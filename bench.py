@@ -331,6 +331,7 @@ def run_ours(args, rank, local_rank, world):
             pprof = ctx.prof_report()
             assert p_hit == n_hit, "partitioned and replicated tables disagree on this rank's anchors"
             part[exchange] = {"ms_per_step": part_ms, "launches": ctx.launches() - pl0, "stats": list(p_st),
+                              "routed_fraction": allsum(float(idx.n_routed)) / max(1.0, allsum(float(idx.n_positions))),
                               "bytes_sent_per_step": allsum(float(comm.bytes_sent - sent0)) / args.steps,
                               "kernel_ms_per_step": {k_: v[0] / args.steps for k_, v in sorted(pprof.items())}}
             idx.free()
@@ -488,7 +489,8 @@ def run_ours(args, rank, local_rank, world):
             "config": {"workload": "same step with the contig table hash-partitioned over %d GPU(s): route by owner, owner-side insert / lookup, ordered collect" % world,
                        "exchange": ("keys (8 B per ONT k-mer) stored by the routing kernel straight into the owner's window and answers (8 B) by the lookup kernel straight into the requester's window over NVLink peer memory (CUDA IPC); two barriers per round, no collective on the data path"
                                     if exchange == "direct" else "send / receive buffers and NCCL all_to_all_single (8 B key out, 8 B answer back per ONT k-mer)") if world > 1 else "single partition, nothing crosses a link"},
-            "nvlink_bytes_per_step": pr["bytes_sent_per_step"], "stats": pr["stats"], "kernel_ms_per_step": pr["kernel_ms_per_step"]}
+            "nvlink_bytes_per_step": pr["bytes_sent_per_step"], "stats": pr["stats"], "kernel_ms_per_step": pr["kernel_ms_per_step"],
+            "prefilter": "union of the partitions' anchoring keys (blocked Bloom filter, all-gathered after the build): %.1f %% of the ONT k-mers are routed" % (100.0 * pr["routed_fraction"])}
         line["gpu_launches"] += int(pr["launches"])
     print(json.dumps(line))
     if dist is not None:

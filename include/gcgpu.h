@@ -151,7 +151,19 @@ int64_t gcg_seqs_tiles (const gcg_seqs * s);
  * and must outlive the plan.  One range holds fewer than 2^32 k-mer positions. */
 int  gcg_route_plan (gcg_ctx * ctx, const gcg_seqs * s, int k, int n_part, int64_t tile_begin, int64_t tile_end,
                      gcg_route ** out, int64_t * counts);
-int64_t gcg_route_kmers (const gcg_route * r);
+int64_t gcg_route_kmers (const gcg_route * r);       /* k-mers the plan routes = elements of the send buffer */
+int64_t gcg_route_positions (const gcg_route * r);   /* k-mer start positions of the range (= routed, without a pre-filter) */
+/* Pre-filter of a routed search.  The filter is a caller-owned device array of 32-bit words (shape
+ * from gcg_filter_shape for the TOTAL number of inserted k-mers, zero-initialised): every owner
+ * adds the keys of its partition that can anchor (present exactly once), the partial filters are
+ * OR-ed together (gcg_filter_or after an all-gather), and gcg_route_plan_filtered routes only the
+ * positions whose k-mer passes — true anchors plus a few percent of false positives instead of
+ * every ONT k-mer.  Positions that fail are misses by construction (no false negatives). */
+int  gcg_filter_shape (int64_t n_keys, int64_t * n_words, int * k3);
+int  gcg_filter_add_table (gcg_ctx * ctx, gcg_table * t, void * d_words, int64_t n_words, int k3);
+int  gcg_filter_or (gcg_ctx * ctx, void * d_words, const void * d_other, int64_t n_words);
+int  gcg_route_plan_filtered (gcg_ctx * ctx, const gcg_seqs * s, int k, int n_part, int64_t tile_begin, int64_t tile_end,
+                              const void * d_filter, int64_t filter_words, int filter_k3, gcg_route ** out, int64_t * counts);
 /* write the range's k-mers grouped by owner (segment d starts at counts[0]+..+counts[d-1]);
  * inside a segment the order is (sequence, position).
  *   keys:    8 bytes  = canonical k-mer + 1                      (search side, ont.c:161-170)

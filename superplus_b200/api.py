@@ -36,6 +36,7 @@ EXPORTS = [
     "gcg_route_collect", "gcg_route_free", "gcg_table_create", "gcg_table_insert_records", "gcg_table_lookup_keys",
     "gcg_window_create", "gcg_window_ptr", "gcg_window_bytes", "gcg_window_export", "gcg_window_open", "gcg_window_close",
     "gcg_window_free", "gcg_peer_enable", "gcg_route_keys_direct", "gcg_table_lookup_keys_direct",
+    "gcg_route_positions", "gcg_filter_shape", "gcg_filter_add_table", "gcg_filter_or", "gcg_route_plan_filtered",
 ]
 MAX_PART = 16
 
@@ -162,6 +163,12 @@ def load_library(path: str = LIB_PATH):
     L.gcg_window_close.argtypes = [vp, vp]
     L.gcg_window_free.argtypes = [vp]
     L.gcg_peer_enable.argtypes = [vp, C.c_int]
+    L.gcg_route_positions.restype = i64
+    L.gcg_route_positions.argtypes = [vp]
+    L.gcg_filter_shape.argtypes = [i64, C.POINTER(i64), C.POINTER(C.c_int)]
+    L.gcg_filter_add_table.argtypes = [vp, vp, vp, i64, C.c_int]
+    L.gcg_filter_or.argtypes = [vp, vp, vp, i64]
+    L.gcg_route_plan_filtered.argtypes = [vp, vp, C.c_int, C.c_int, i64, i64, vp, i64, C.c_int, C.POINTER(vp), vp]
     L.gcg_route_keys_direct.argtypes = [vp, vp, vp, vp]
     L.gcg_table_lookup_keys_direct.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
     _lib = L
@@ -328,11 +335,25 @@ class Context:
         return out
 
     # ---- partitioned table (device pointers; the exchange between the calls is the caller's) ----
-    def route_plan(self, seqs: "Seqs", k: int, n_part: int, tile_begin: int, tile_end: int) -> "Route":
+    def route_plan(self, seqs: "Seqs", k: int, n_part: int, tile_begin: int, tile_end: int, prefilter=None) -> "Route":
+        """prefilter = (device pointer, n_words, k3): route only the positions whose k-mer passes it"""
         h = C.c_void_p()
         counts = np.zeros(MAX_PART, dtype=np.int64)
-        self._chk(self.L.gcg_route_plan(self.h, seqs.h, k, n_part, tile_begin, tile_end, C.byref(h), counts.ctypes.data))
+        if prefilter is None:
+            self._chk(self.L.gcg_route_plan(self.h, seqs.h, k, n_part, tile_begin, tile_end, C.byref(h), counts.ctypes.data))
+        else:
+            ptr, n_words, k3 = prefilter
+            self._chk(self.L.gcg_route_plan_filtered(self.h, seqs.h, k, n_part, tile_begin, tile_end, C.c_void_p(int(ptr)), int(n_words), int(k3),
+                                                     C.byref(h), counts.ctypes.data))
         return Route(self, h, counts[:n_part].copy())
+
+    def filter_shape(self, n_keys: int):
+        nw, k3 = C.c_int64(), C.c_int()
+        self._chk(self.L.gcg_filter_shape(int(n_keys), C.byref(nw), C.byref(k3)))
+        return int(nw.value), int(k3.value)
+
+    def filter_or(self, d_words: int, d_other: int, n_words: int):
+        self._chk(self.L.gcg_filter_or(self.h, C.c_void_p(int(d_words)), C.c_void_p(int(d_other)), int(n_words)))
 
     def window(self, n_bytes: int) -> "Window":
         h = C.c_void_p()
@@ -464,7 +485,13 @@ class Route(_Handle):
 
     @property
     def kmers(self):
+        """k-mers the plan routes (elements of the send buffer)"""
         return int(self.ctx.L.gcg_route_kmers(self.h))
+
+    @property
+    def positions(self):
+        """k-mer start positions of the range"""
+        return int(self.ctx.L.gcg_route_positions(self.h))
 
     def keys(self, d_send: int):
         self.ctx._chk(self.ctx.L.gcg_route_keys(self.ctx.h, self.h, d_send))
@@ -503,6 +530,10 @@ class KmerTable(_Handle):
 
     def lookup_keys(self, d_keys: int, n: int, d_answers: int):
         self.ctx._chk(self.ctx.L.gcg_table_lookup_keys(self.ctx.h, self.h, d_keys, int(n), d_answers))
+
+    def filter_add(self, d_words: int, n_words: int, k3: int):
+        """set the filter bits of this table's anchoring keys (present exactly once)"""
+        self.ctx._chk(self.ctx.L.gcg_filter_add_table(self.ctx.h, self.h, C.c_void_p(int(d_words)), int(n_words), int(k3)))
 
     def lookup_keys_direct(self, d_keys: int, src_count, answer_ptrs, answer_off):
         """keys of requester r (src_count[r] of them, in rank order) -> answers at answer_ptrs[r] + 8 * answer_off[r]"""

@@ -796,6 +796,15 @@ filter_build_kernel (const unsigned long long * __restrict__ keys, uint64_t n_sl
   }
 }
 
+static void filter_shape (int64_t n_keys, int64_t * n_words, int * k3)
+{
+  int64_t max_mb = 64;
+  if (const char * e = getenv ("GCG_FILTER_MAX_MB")) max_mb = std::max<int64_t> (1, atoll (e));
+  const int64_t bytes = std::min<int64_t> (std::max<int64_t> (n_keys, 1 << 20), max_mb << 20);
+  *n_words = bytes / 4;
+  *k3 = bytes * 8 >= 4 * std::max<int64_t> (n_keys, 1);       // three bits per key from 4 bits of filter per key up
+}
+
 // A table whose key array does not fit the L2 gets a filter of about one byte per inserted k-mer,
 // capped so that the filter itself stays L2 resident (GCG_FILTER_MAX_MB, default 64).
 // GCG_FILTER=0 / 1 forces it off / on for any size.
@@ -806,11 +815,9 @@ int gcg_table_filter_ensure (gcg_ctx * ctx, gcg_table * t)
   if (!want) { t->filter_valid = false; t->filter_words = 0; return GCG_OK; }
   if (t->filter_valid) return GCG_OK;
   if (!t->d_filter) {
-    int64_t max_mb = 64;
-    if (const char * e = getenv ("GCG_FILTER_MAX_MB")) max_mb = std::max<int64_t> (1, atoll (e));
-    int64_t bytes = std::min<int64_t> (std::max<int64_t> (t->n_inserted, 1 << 20), max_mb << 20);
-    t->filter_words = (uint32_t) (bytes / 4);
-    t->filter_k3 = bytes * 8 >= 4 * std::max<int64_t> (t->n_inserted, 1);        // three bits per key from 4 bits of filter per key up
+    int64_t words = 0;
+    filter_shape (t->n_inserted, &words, &t->filter_k3);
+    t->filter_words = (uint32_t) words;
     GCG_CUDA (gcg_dmalloc (ctx, &t->d_filter, (size_t) t->filter_words * 4));
   }
   GCG_CUDA (cudaMemsetAsync (t->d_filter, 0, (size_t) t->filter_words * 4, ctx->stream));
@@ -820,6 +827,41 @@ int gcg_table_filter_ensure (gcg_ctx * ctx, gcg_table * t)
     GCG_CUDA (cudaGetLastError ());
   }
   t->filter_valid = true;
+  return GCG_OK;
+}
+
+// ---- the same filter in a caller-owned buffer: the union over the partitions of a partitioned table
+extern "C" int gcg_filter_shape (int64_t n_keys, int64_t * n_words, int * k3)
+{
+  GCG_CHECK (n_keys >= 0 && n_words && k3, GCG_EINVAL, "gcg_filter_shape: bad argument");
+  filter_shape (n_keys, n_words, k3);
+  return GCG_OK;
+}
+
+extern "C" int gcg_filter_add_table (gcg_ctx * ctx, gcg_table * t, void * d_words, int64_t n_words, int k3)
+{
+  GCG_CHECK (ctx && t && d_words && n_words > 0 && n_words < 0xFFFFFFFFLL, GCG_EINVAL, "gcg_filter_add_table: bad argument");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  gcg_kscope ks (ctx, "filter_build");
+  filter_build_kernel<<<grid_for (ctx, (int64_t) t->n_slot, 256, 8), 256, 0, ctx->stream>>> (t->d_keys, t->n_slot, (uint32_t *) d_words, (uint32_t) n_words, k3 != 0);
+  GCG_CUDA (cudaGetLastError ());
+  return GCG_OK;
+}
+
+__global__ void __launch_bounds__ (256)
+filter_or_kernel (uint32_t * __restrict__ dst, const uint32_t * __restrict__ src, int64_t n)
+{
+  int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] |= src[i];
+}
+
+extern "C" int gcg_filter_or (gcg_ctx * ctx, void * d_words, const void * d_other, int64_t n_words)
+{
+  GCG_CHECK (ctx && d_words && d_other && n_words > 0, GCG_EINVAL, "gcg_filter_or: bad argument");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  gcg_kscope ks (ctx, "filter_or");
+  filter_or_kernel<<<grid_for (ctx, n_words, 256, 8), 256, 0, ctx->stream>>> ((uint32_t *) d_words, (const uint32_t *) d_other, n_words);
+  GCG_CUDA (cudaGetLastError ());
   return GCG_OK;
 }
 

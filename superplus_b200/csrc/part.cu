@@ -32,6 +32,8 @@ struct gcg_route {
   int k = 0, n_part = 0;
   int64_t tile0 = 0, n_tiles = 0;           // tiles [tile0, tile0 + n_tiles) of 32 words
   int64_t n_kmers = 0;                      // k-mer start positions in the range
+  int64_t n_routed = 0;                     // of those, the ones that are routed (all, or the pre-filter's survivors)
+  uint32_t * d_pass = nullptr;              // filtered plans: per word of the range, bit j = position j is routed
   uint32_t * d_off = nullptr;               // [n_part][n_tiles]: count, then exclusive offset inside the owner's segment
   uint32_t * d_bsum = nullptr;
   int64_t * d_seg = nullptr;                // [n_part + 1] segment starts (records)
@@ -75,17 +77,71 @@ __device__ __forceinline__ int word_valid (const int64_t * __restrict__ woff, co
 }
 
 // per-lane counts of this word's k-mers by owner, into cnt[d][lane]
+// Calls f (j, canonical k-mer, forward?) for the routed positions of word w, in position order.
+// Without a pre-filter that is every valid position and the k-mers are rolled (kseq1.h:48-59); with
+// one only a few percent of the positions survive, and extracting just those from the two packed
+// words is cheaper than rolling through all 32.
+template <class F>
+__device__ __forceinline__ void for_each_routed (const uint64_t * __restrict__ packed, int64_t w, int nvalid, int k, uint32_t pass,
+                                                 bool sparse, F f)
+{
+  if (!nvalid) return;
+  const uint64_t hi = __ldg (packed + w), lo = __ldg (packed + w + 1);
+  if (sparse) {
+    uint32_t m = nvalid >= 32 ? pass : (pass & ((1u << nvalid) - 1u));
+    while (m) {
+      const int j = __ffs ((int) m) - 1;
+      m &= m - 1u;
+      bool fw;
+      const unsigned long long key = key_at (hi, lo, j, k, &fw) - 1ULL;
+      f (j, key, fw);
+    }
+  } else {
+    kroll r;
+    r.init (hi, lo, k);
+    for (int j = 0; j < nvalid; ++j) {
+      if (j) r.step ();
+      const bool fw = r.fwd < r.rc;
+      f (j, fw ? r.fwd : r.rc, fw);
+    }
+  }
+}
+
+// (`pass`: bit j set = position j takes part; all ones when the plan has no pre-filter)
 __device__ __forceinline__ void lane_counts (const uint64_t * __restrict__ packed, int64_t w, int nvalid, int k, uint32_t n_part,
-                                             uint32_t (* cnt)[32], int lane)
+                                             uint32_t (* cnt)[32], int lane, uint32_t pass, bool sparse)
 {
   for (uint32_t d = 0; d < n_part; ++d) cnt[d][lane] = 0;
-  if (!nvalid) return;
+  for_each_routed (packed, w, nvalid, k, pass, sparse, [&] (int, unsigned long long key, bool) { ++cnt[kmer_owner (key, n_part)][lane]; });
+}
+
+// Pre-filter of a routed search: the union, over all partitions, of the keys that can anchor (same
+// blocked Bloom layout as the table's own pre-filter, kmer.cu).  A position whose k-mer fails it is
+// a miss without asking anybody, so only the survivors (true anchors plus a few percent of false
+// positives) are routed, cross NVLink and are looked up.  Four loads in flight per lane.
+__device__ __forceinline__ uint32_t lane_filter_mask (const uint64_t * __restrict__ packed, int64_t w, int nvalid, int k,
+                                                      const uint32_t * __restrict__ filter, uint32_t filter_words, int k3)
+{
+  uint32_t pass = 0;
+  if (!nvalid) return 0;
   kroll r;
   r.init (__ldg (packed + w), __ldg (packed + w + 1), k);
-  for (int j = 0; j < nvalid; ++j) {
-    if (j) r.step ();
-    ++cnt[kmer_owner (r.fwd < r.rc ? r.fwd : r.rc, n_part)][lane];
+  for (int j0 = 0; j0 < nvalid; j0 += 4) {
+    uint32_t hh[4], fw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (j0 + u) r.step ();
+      const unsigned long long key = r.fwd < r.rc ? r.fwd : r.rc;
+      hh[u] = kmer_hash32 (key);
+      fw[u] = __ldg (filter + __umulhi (kmer_hash32b (key), filter_words));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t m = filter_mask (hh[u], k3);
+      pass |= (uint32_t) ((j0 + u < nvalid) && (fw[u] & m) == m) << (j0 + u);
+    }
   }
+  return pass;
 }
 
 // cnt[d][lane] <- off[d][tile] + exclusive warp scan of cnt[d][.]  (the lane's cursor inside segment d)
@@ -102,7 +158,8 @@ __device__ __forceinline__ void lane_cursors (uint32_t (* cnt)[32], const uint32
 __global__ void __launch_bounds__ (32 * RT_WARPS)
 route_count_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff, const int32_t * __restrict__ len,
                     const int32_t * __restrict__ tile_seq, int64_t n_seq, int64_t n_words, int k, uint32_t n_part,
-                    int64_t tile0, int64_t n_tiles, uint32_t * __restrict__ cnt_out)
+                    int64_t tile0, int64_t n_tiles, uint32_t * __restrict__ cnt_out,
+                    const uint32_t * __restrict__ filter, uint32_t filter_words, int filter_k3, uint32_t * __restrict__ pass_out)
 {
   __shared__ uint32_t s_cnt[RT_WARPS][GCG_MAX_PART][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -111,7 +168,12 @@ route_count_kernel (const uint64_t * __restrict__ packed, const int64_t * __rest
     const int64_t tile = tile0 + t, w = (tile << 5) + lane;
     int64_t s; int32_t p0;
     const int nvalid = word_valid (woff, len, tile_seq, n_seq, n_words, tile, w, k, &s, &p0);
-    lane_counts (packed, w, nvalid, k, n_part, s_cnt[wid], lane);
+    uint32_t pass = 0xffffffffu;
+    if (filter != nullptr) {
+      pass = lane_filter_mask (packed, w, nvalid, k, filter, filter_words, filter_k3);
+      if (w < n_words) pass_out[(t << 5) + lane] = pass;
+    }
+    lane_counts (packed, w, nvalid, k, n_part, s_cnt[wid], lane, pass, filter != nullptr);
     for (uint32_t d = 0; d < n_part; ++d) {
       uint32_t tot = __reduce_add_sync (0xffffffffu, s_cnt[wid][d][lane]);
       if (lane == 0) cnt_out[(int64_t) d * n_tiles + t] = tot;
@@ -173,7 +235,8 @@ struct route_dst { unsigned long long * base[GCG_MAX_PART]; };
 __global__ void __launch_bounds__ (32 * RS_WARPS)
 route_keys_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff, const int32_t * __restrict__ len,
                    const int32_t * __restrict__ tile_seq, int64_t n_seq, int64_t n_words, int k, uint32_t n_part,
-                   int64_t tile0, int64_t n_tiles, const uint32_t * __restrict__ off, const __grid_constant__ route_dst dst)
+                   int64_t tile0, int64_t n_tiles, const uint32_t * __restrict__ off, const __grid_constant__ route_dst dst,
+                   const uint32_t * __restrict__ pass_in)
 {
   __shared__ unsigned long long s_stage[RS_WARPS][1024];
   __shared__ uint32_t s_cnt[RS_WARPS][GCG_MAX_PART][32];
@@ -189,17 +252,12 @@ route_keys_kernel (const uint64_t * __restrict__ packed, const int64_t * __restr
     int64_t s; int32_t p0;
     const int nvalid = word_valid (woff, len, tile_seq, n_seq, n_words, tile, w, k, &s, &p0);
     __syncwarp ();                                    // the previous tile's copy-out has finished reading the stage
-    lane_counts (packed, w, nvalid, k, n_part, s_cnt[wid], lane);
+    const uint32_t pass = (pass_in != nullptr && w < n_words) ? __ldg (pass_in + (t << 5) + lane) : 0xffffffffu;
+    lane_counts (packed, w, nvalid, k, n_part, s_cnt[wid], lane, pass, pass_in != nullptr);
     tile_layout (s_cnt[wid], s_run[wid], s_glob[wid], s_base, off, n_tiles, t, n_part, lane);
-    if (nvalid) {
-      kroll r;
-      r.init (__ldg (packed + w), __ldg (packed + w + 1), k);
-      for (int j = 0; j < nvalid; ++j) {
-        if (j) r.step ();
-        const unsigned long long key = r.fwd < r.rc ? r.fwd : r.rc;
-        s_stage[wid][s_cnt[wid][kmer_owner (key, n_part)][lane]++] = key + 1ULL;
-      }
-    }
+    for_each_routed (packed, w, nvalid, k, pass, pass_in != nullptr, [&] (int, unsigned long long key, bool) {
+      s_stage[wid][s_cnt[wid][kmer_owner (key, n_part)][lane]++] = key + 1ULL;
+    });
     __syncwarp ();
     const uint32_t total = s_run[wid][n_part];
     for (uint32_t i = lane; i < total; i += 32) {
@@ -227,7 +285,7 @@ route_records_kernel (const uint64_t * __restrict__ packed, const int64_t * __re
     const int64_t tile = tile0 + t, w = (tile << 5) + lane;
     int64_t s; int32_t p0;
     const int nvalid = word_valid (woff, len, tile_seq, n_seq, n_words, tile, w, k, &s, &p0);
-    lane_counts (packed, w, nvalid, k, n_part, s_cnt[wid], lane);
+    lane_counts (packed, w, nvalid, k, n_part, s_cnt[wid], lane, 0xffffffffu, false);
     lane_cursors (s_cnt[wid], off, n_tiles, t, n_part, lane);
     if (nvalid) {
       kroll r;
@@ -258,7 +316,7 @@ route_collect_kernel (const uint64_t * __restrict__ packed, const int64_t * __re
                       const int32_t * __restrict__ tile_seq, int64_t n_seq, int64_t n_words, int k, uint32_t n_part,
                       int64_t tile0, int64_t n_tiles, const uint32_t * __restrict__ off, const int64_t * __restrict__ seg,
                       const unsigned long long * __restrict__ ans, uint32_t * __restrict__ mask,
-                      const uint32_t * __restrict__ prefix, gcg_hit * __restrict__ hits)
+                      const uint32_t * __restrict__ prefix, gcg_hit * __restrict__ hits, const uint32_t * __restrict__ pass_in)
 {
   __shared__ uint32_t s_cnt[RT_WARPS][GCG_MAX_PART][32];
   __shared__ int64_t s_seg[GCG_MAX_PART];
@@ -275,30 +333,25 @@ route_collect_kernel (const uint64_t * __restrict__ packed, const int64_t * __re
       const uint32_t m = w < n_words ? __ldg (mask + wl) : 0u;
       if (!__any_sync (0xffffffffu, m != 0u)) continue;
     }
-    lane_counts (packed, w, nvalid, k, n_part, s_cnt[wid], lane);
+    const uint32_t pass = (pass_in != nullptr && w < n_words) ? __ldg (pass_in + wl) : 0xffffffffu;
+    lane_counts (packed, w, nvalid, k, n_part, s_cnt[wid], lane, pass, pass_in != nullptr);
     lane_cursors (s_cnt[wid], off, n_tiles, t, n_part, lane);
     uint32_t m = 0;
-    if (nvalid) {
-      uint32_t at_hit = EMIT ? __ldg (prefix + wl) : 0u;
-      kroll r;
-      r.init (__ldg (packed + w), __ldg (packed + w + 1), k);
-      for (int j = 0; j < nvalid; ++j) {
-        if (j) r.step ();
-        const bool fw = r.fwd < r.rc;
-        const uint32_t d = kmer_owner (fw ? r.fwd : r.rc, n_part);
-        const unsigned long long v = __ldg (ans + s_seg[d] + s_cnt[wid][d][lane]++);
-        if (v == GCG_ANS_MISS) continue;
-        m |= 1u << j;
-        if (EMIT) {
-          int4 hh;                                    // gcg_hit {read, pos, tid, cpos_flags}
-          hh.x = (int32_t) s;
-          hh.y = p0 + j;
-          hh.z = (int32_t) ((v >> 32) & 0x7FFFFFFFu);
-          hh.w = (int32_t) ((((uint32_t) (v >> 1) & 0x3FFFFFFFu) << 2) | (uint32_t) (v & 1ULL) | (fw ? 0u : 2u));
-          reinterpret_cast<int4 *> (hits)[at_hit++] = hh;
-        }
+    uint32_t at_hit = (EMIT && nvalid) ? __ldg (prefix + wl) : 0u;
+    for_each_routed (packed, w, nvalid, k, pass, pass_in != nullptr, [&] (int j, unsigned long long key, bool fw) {
+      const uint32_t d = kmer_owner (key, n_part);
+      const unsigned long long v = __ldg (ans + s_seg[d] + s_cnt[wid][d][lane]++);
+      if (v == GCG_ANS_MISS) return;
+      m |= 1u << j;
+      if (EMIT) {
+        int4 hh;                                    // gcg_hit {read, pos, tid, cpos_flags}
+        hh.x = (int32_t) s;
+        hh.y = p0 + j;
+        hh.z = (int32_t) ((v >> 32) & 0x7FFFFFFFu);
+        hh.w = (int32_t) ((((uint32_t) (v >> 1) & 0x3FFFFFFFu) << 2) | (uint32_t) (v & 1ULL) | (fw ? 0u : 2u));
+        reinterpret_cast<int4 *> (hits)[at_hit++] = hh;
       }
-    }
+    });
     if (!EMIT && w < n_words) mask[wl] = m;
   }
 }
@@ -460,12 +513,12 @@ static int flat_grid (gcg_ctx * ctx, int64_t n, int per_thread)
 extern "C" void gcg_route_free (gcg_route * r)
 {
   if (!r) return;
-  gcg_dfree (r->ctx, r->d_off); gcg_dfree (r->ctx, r->d_bsum); gcg_dfree (r->ctx, r->d_seg);
+  gcg_dfree (r->ctx, r->d_off); gcg_dfree (r->ctx, r->d_bsum); gcg_dfree (r->ctx, r->d_seg); gcg_dfree (r->ctx, r->d_pass);
   delete r;
 }
 
-extern "C" int gcg_route_plan (gcg_ctx * ctx, const gcg_seqs * s, int k, int n_part, int64_t tile_begin, int64_t tile_end,
-                               gcg_route ** out, int64_t * counts)
+static int route_plan_impl (gcg_ctx * ctx, const gcg_seqs * s, int k, int n_part, int64_t tile_begin, int64_t tile_end,
+                            const uint32_t * d_filter, uint32_t filter_words, int filter_k3, gcg_route ** out, int64_t * counts)
 {
   GCG_CHECK (ctx && s && out && counts, GCG_EINVAL, "gcg_route_plan: bad argument");
   GCG_CHECK (k >= 1 && k <= 31, GCG_ERANGE, "gcg_route_plan: k=%d outside [1,31]", k);
@@ -500,7 +553,8 @@ extern "C" int gcg_route_plan (gcg_ctx * ctx, const gcg_seqs * s, int k, int n_p
   int rc = GCG_OK;
   cudaError_t e;
   const int64_t nb = (nt + PS_TILE - 1) / PS_TILE;
-  if ((e = gcg_dmalloc (ctx, &r->d_off, (size_t) std::max<int64_t> (nt, 1) * n_part * 4)) != cudaSuccess ||
+  if ((d_filter != nullptr && (e = gcg_dmalloc (ctx, &r->d_pass, (size_t) std::max<int64_t> (nt, 1) * 32 * 4)) != cudaSuccess) ||
+      (e = gcg_dmalloc (ctx, &r->d_off, (size_t) std::max<int64_t> (nt, 1) * n_part * 4)) != cudaSuccess ||
       (e = gcg_dmalloc (ctx, &r->d_bsum, (size_t) std::max<int64_t> (nb, 1) * n_part * 4)) != cudaSuccess ||
       (e = gcg_dmalloc (ctx, &r->d_seg, (GCG_MAX_PART + 1) * 8)) != cudaSuccess) {
     gcg_set_error ("gcg_route_plan: cudaMalloc failed: %s", cudaGetErrorString (e));
@@ -511,7 +565,8 @@ extern "C" int gcg_route_plan (gcg_ctx * ctx, const gcg_seqs * s, int k, int n_p
   if (nt > 0 && r->n_kmers > 0) {
     { gcg_kscope ks (ctx, "route_count");
       route_count_kernel<<<warp_grid (ctx, nt), 32 * RT_WARPS, 0, ctx->stream>>> (
-          s->d_packed, s->d_woff, s->d_len, s->d_tseq, s->n, s->n_words, k, (uint32_t) n_part, r->tile0, nt, r->d_off); }
+          s->d_packed, s->d_woff, s->d_len, s->d_tseq, s->n, s->n_words, k, (uint32_t) n_part, r->tile0, nt, r->d_off,
+          d_filter, filter_words, filter_k3, r->d_pass); }
     { gcg_kscope ks (ctx, "route_scan");
       rows_reduce_kernel<<<dim3 ((unsigned) nb, (unsigned) n_part), PS_BLOCK, 0, ctx->stream>>> (r->d_off, nt, nb, r->d_bsum); }
     { gcg_kscope ks (ctx, "route_scan");
@@ -525,7 +580,9 @@ extern "C" int gcg_route_plan (gcg_ctx * ctx, const gcg_seqs * s, int k, int n_p
     if (!rc) {
       int64_t tot = 0;
       for (int d = 0; d < n_part; ++d) { counts[d] = r->counts[d] = (int64_t) ctx->h_counters[16 + d]; tot += counts[d]; }
-      if (tot != r->n_kmers) { gcg_set_error ("gcg_route_plan: counted %lld k-mers, expected %lld", (long long) tot, (long long) r->n_kmers); rc = GCG_ECUDA; }
+      r->n_routed = tot;
+      if (d_filter ? tot > r->n_kmers : tot != r->n_kmers) {
+        gcg_set_error ("gcg_route_plan: counted %lld k-mers, expected %lld", (long long) tot, (long long) r->n_kmers); rc = GCG_ECUDA; }
     }
   }
   if (!rc) {
@@ -538,7 +595,22 @@ extern "C" int gcg_route_plan (gcg_ctx * ctx, const gcg_seqs * s, int k, int n_p
   return GCG_OK;
 }
 
-extern "C" int64_t gcg_route_kmers (const gcg_route * r) { return r ? r->n_kmers : 0; }
+extern "C" int gcg_route_plan (gcg_ctx * ctx, const gcg_seqs * s, int k, int n_part, int64_t tile_begin, int64_t tile_end,
+                               gcg_route ** out, int64_t * counts)
+{
+  return route_plan_impl (ctx, s, k, n_part, tile_begin, tile_end, nullptr, 0, 0, out, counts);
+}
+
+extern "C" int gcg_route_plan_filtered (gcg_ctx * ctx, const gcg_seqs * s, int k, int n_part, int64_t tile_begin, int64_t tile_end,
+                                        const void * d_filter, int64_t filter_words, int filter_k3, gcg_route ** out, int64_t * counts)
+{
+  GCG_CHECK (d_filter != nullptr && filter_words > 0 && filter_words < 0xFFFFFFFFLL, GCG_EINVAL, "gcg_route_plan_filtered: bad filter");
+  return route_plan_impl (ctx, s, k, n_part, tile_begin, tile_end, (const uint32_t *) d_filter, (uint32_t) filter_words, filter_k3 != 0, out, counts);
+}
+
+// number of k-mers the plan routes (= buffer elements): all positions of the range, or the pre-filter's survivors
+extern "C" int64_t gcg_route_kmers (const gcg_route * r) { return r ? r->n_routed : 0; }
+extern "C" int64_t gcg_route_positions (const gcg_route * r) { return r ? r->n_kmers : 0; }
 
 static int staged_grid (gcg_ctx * ctx, int64_t n_tiles)
 {
@@ -551,16 +623,16 @@ static int route_keys_launch (gcg_ctx * ctx, gcg_route * r, const route_dst & ds
   const gcg_seqs * s = r->seqs;
   gcg_kscope ks (ctx, "route_keys");
   route_keys_kernel<<<staged_grid (ctx, r->n_tiles), 32 * RS_WARPS, 0, ctx->stream>>> (
-      s->d_packed, s->d_woff, s->d_len, s->d_tseq, s->n, s->n_words, r->k, (uint32_t) r->n_part, r->tile0, r->n_tiles, r->d_off, dst);
+      s->d_packed, s->d_woff, s->d_len, s->d_tseq, s->n, s->n_words, r->k, (uint32_t) r->n_part, r->tile0, r->n_tiles, r->d_off, dst, r->d_pass);
   GCG_CUDA (cudaGetLastError ());
   return GCG_OK;
 }
 
 extern "C" int gcg_route_keys (gcg_ctx * ctx, gcg_route * r, void * d_send)
 {
-  GCG_CHECK (ctx && r && (d_send || r->n_kmers == 0), GCG_EINVAL, "gcg_route_keys: bad argument");
+  GCG_CHECK (ctx && r && (d_send || r->n_routed == 0), GCG_EINVAL, "gcg_route_keys: bad argument");
   GCG_CUDA (cudaSetDevice (ctx->device));
-  if (r->n_kmers == 0) return GCG_OK;
+  if (r->n_routed == 0) return GCG_OK;
   route_dst dst;
   int64_t at = 0;
   for (int d = 0; d < GCG_MAX_PART; ++d) {
@@ -574,7 +646,7 @@ extern "C" int gcg_route_keys_direct (gcg_ctx * ctx, gcg_route * r, void * const
 {
   GCG_CHECK (ctx && r && d_owner_base && owner_off, GCG_EINVAL, "gcg_route_keys_direct: bad argument");
   GCG_CUDA (cudaSetDevice (ctx->device));
-  if (r->n_kmers == 0) return GCG_OK;
+  if (r->n_routed == 0) return GCG_OK;
   route_dst dst;
   for (int d = 0; d < GCG_MAX_PART; ++d) {
     dst.base[d] = nullptr;
@@ -589,6 +661,7 @@ extern "C" int gcg_route_keys_direct (gcg_ctx * ctx, gcg_route * r, void * const
 extern "C" int gcg_route_records (gcg_ctx * ctx, gcg_route * r, void * d_send)
 {
   GCG_CHECK (ctx && r && (d_send || r->n_kmers == 0), GCG_EINVAL, "gcg_route_records: bad argument");
+  GCG_CHECK (r->d_pass == nullptr, GCG_EINVAL, "gcg_route_records: the plan was made with a pre-filter (search side only)");
   GCG_CUDA (cudaSetDevice (ctx->device));
   if (r->n_kmers == 0) return GCG_OK;
   const gcg_seqs * s = r->seqs;
@@ -602,11 +675,11 @@ extern "C" int gcg_route_records (gcg_ctx * ctx, gcg_route * r, void * d_send)
 
 extern "C" int gcg_route_collect (gcg_ctx * ctx, gcg_route * r, const void * d_answers, gcg_hits ** out)
 {
-  GCG_CHECK (ctx && r && out && (d_answers || r->n_kmers == 0), GCG_EINVAL, "gcg_route_collect: bad argument");
+  GCG_CHECK (ctx && r && out && (d_answers || r->n_routed == 0), GCG_EINVAL, "gcg_route_collect: bad argument");
   GCG_CUDA (cudaSetDevice (ctx->device));
   gcg_hits * h = new gcg_hits ();
   h->ctx = ctx;
-  if (r->n_kmers == 0) { *out = h; return GCG_OK; }
+  if (r->n_routed == 0) { *out = h; return GCG_OK; }
   const gcg_seqs * s = r->seqs;
   const int64_t n_words = std::min (s->n_words, (r->tile0 + r->n_tiles) << 5) - (r->tile0 << 5);
   uint32_t * d_mask = nullptr, * d_prefix = nullptr, * d_bsum = nullptr;
@@ -621,7 +694,7 @@ extern "C" int gcg_route_collect (gcg_ctx * ctx, gcg_route * r, const void * d_a
     { gcg_kscope ks (ctx, "route_collect_mask");
       route_collect_kernel<0><<<warp_grid (ctx, r->n_tiles), 32 * RT_WARPS, 0, ctx->stream>>> (
           s->d_packed, s->d_woff, s->d_len, s->d_tseq, s->n, s->n_words, r->k, (uint32_t) r->n_part, r->tile0, r->n_tiles,
-          r->d_off, r->d_seg, (const unsigned long long *) d_answers, d_mask, nullptr, nullptr); }
+          r->d_off, r->d_seg, (const unsigned long long *) d_answers, d_mask, nullptr, nullptr, r->d_pass); }
     if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_route_collect: kernel launch failed"); rc = GCG_ECUDA; break; }
     int64_t n_hit = 0;
     if ((rc = gcg_mask_scan (ctx, d_mask, n_words, d_prefix, d_bsum, &n_hit)) != 0) break;
@@ -635,7 +708,7 @@ extern "C" int gcg_route_collect (gcg_ctx * ctx, gcg_route * r, const void * d_a
       { gcg_kscope ks (ctx, "route_collect_emit");
         route_collect_kernel<1><<<warp_grid (ctx, r->n_tiles), 32 * RT_WARPS, 0, ctx->stream>>> (
             s->d_packed, s->d_woff, s->d_len, s->d_tseq, s->n, s->n_words, r->k, (uint32_t) r->n_part, r->tile0, r->n_tiles,
-            r->d_off, r->d_seg, (const unsigned long long *) d_answers, d_mask, d_prefix, h->d_hits); }
+            r->d_off, r->d_seg, (const unsigned long long *) d_answers, d_mask, d_prefix, h->d_hits, r->d_pass); }
       if (cudaGetLastError () != cudaSuccess || cudaStreamSynchronize (ctx->stream) != cudaSuccess) {
         gcg_set_error ("gcg_route_collect: emit failed: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; }
     }

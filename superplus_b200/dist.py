@@ -85,6 +85,12 @@ class TorchComm:
     def barrier(self):
         self.dist.barrier()
 
+    def all_gather(self, t: torch.Tensor):
+        """-> list of every rank's tensor (same shape everywhere)"""
+        out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t)
+        return list(out.view(self.world, -1))
+
     def share(self, ops, window):
         """every rank's window as a reference this rank's kernels can store through (CUDA IPC)"""
         if self.device.type != "cuda":
@@ -166,6 +172,11 @@ class ThreadComm:
         self.sync()
         self.g.barrier.wait()
 
+    def all_gather(self, t: torch.Tensor):
+        out = [x.clone() if i != self.rank else x for i, x in enumerate(self._publish(t))]
+        self._done()
+        return out
+
     def share(self, ops, window):
         refs = self._publish(ops.window_ref(window))      # one address space: the reference is the window itself
         self._done()
@@ -197,8 +208,24 @@ class DeviceOps:
     def tiles(self, seqs) -> int:
         return seqs.tiles
 
-    def plan(self, seqs, k, n_part, t0, t1):
-        return self.ctx.route_plan(seqs, k, n_part, t0, t1)
+    def plan(self, seqs, k, n_part, t0, t1, prefilter=None):
+        if prefilter is not None:
+            t, n_words, k3 = prefilter
+            prefilter = (t.data_ptr(), n_words, k3)
+        return self.ctx.route_plan(seqs, k, n_part, t0, t1, prefilter)
+
+    # pre-filter of the routed search: an int32 tensor of filter words
+    def filter_new(self, n_keys: int):
+        n_words, k3 = self.ctx.filter_shape(n_keys)
+        return torch.zeros(n_words, dtype=torch.int32, device=self.device), n_words, k3
+
+    def filter_add_table(self, table, flt):
+        t, n_words, k3 = flt
+        table.filter_add(t.data_ptr(), n_words, k3)
+
+    def filter_or(self, flt, other: torch.Tensor):
+        t, n_words, _ = flt
+        self.ctx.filter_or(t.data_ptr(), other.data_ptr(), n_words)
 
     def route_keys(self, route, t: torch.Tensor):
         route.keys(t.data_ptr())
@@ -264,11 +291,17 @@ def search_rounds(n_tiles: int, round_kmers: int = ROUND_KMERS):
 class PartitionedKmerIndex:
     """contig k-mer table partitioned over comm.world GPUs by hash of the canonical k-mer"""
 
-    def __init__(self, ops, comm, k: int, round_kmers: int = ROUND_KMERS, exchange: str = "all_to_all"):
+    def __init__(self, ops, comm, k: int, round_kmers: int = ROUND_KMERS, exchange: str = "all_to_all", prefilter: bool = True):
         """exchange = "all_to_all": keys and answers travel through send / receive buffers and
                        `all_to_all_single` (NCCL; gloo in the CPU tests);
            exchange = "direct": the routing and lookup kernels store straight into the peers' windows
-                       over NVLink / NVSwitch peer memory, the ranks only meet at two barriers per round."""
+                       over NVLink / NVSwitch peer memory, the ranks only meet at two barriers per round.
+           prefilter: after the build every rank adds its anchoring keys (present exactly once) to a
+                       Bloom-style filter, the partial filters are all-gathered and OR-ed, and the
+                       search routes only the ONT k-mers that pass it — the anchors plus a few
+                       percent of false positives instead of all of them (96 % are sequencing-error
+                       k-mers that no table holds), which shrinks the exchange and the owner-side
+                       lookups by an order of magnitude."""
         if not 1 <= comm.world <= api.MAX_PART:
             raise ValueError("world size %d outside [1,%d]" % (comm.world, api.MAX_PART))
         if exchange not in ("all_to_all", "direct"):
@@ -276,6 +309,8 @@ class PartitionedKmerIndex:
         self.ops, self.comm, self.k, self.round_kmers, self.exchange = ops, comm, k, round_kmers, exchange
         self.table = None
         self.n_local_records = 0
+        self.use_prefilter, self.prefilter = prefilter, None
+        self.n_routed = self.n_positions = 0      # of the searches so far: k-mers exchanged / k-mer positions
         self.qwin = self.awin = None              # direct exchange: my key / answer windows ...
         self.q_refs = self.a_refs = None          # ... and every rank's, as seen from this rank
         self.q_cap = self.a_cap = 0
@@ -324,6 +359,18 @@ class PartitionedKmerIndex:
                 ops.sync()                      # recv/send are released after the inserts ran
             route.free()
             self.n_local_records = n
+            self.prefilter = None
+            if self.use_prefilter:
+                with self._phase("build.prefilter"):
+                    n_total = int(comm.all_reduce([n], "sum")[0])
+                    flt = ops.filter_new(n_total)
+                    ops.filter_add_table(self.table, flt)
+                    ops.sync()
+                    for r, part in enumerate(comm.all_gather(flt[0])):
+                        if r != comm.rank:
+                            ops.filter_or(flt, part)
+                    ops.sync()
+                    self.prefilter = flt
         return self
 
     # ---- direct exchange ------------------------------------------------------------------------
@@ -354,7 +401,8 @@ class PartitionedKmerIndex:
     def _round_direct(self, reads, t0, t1):
         ops, comm, me, world = self.ops, self.comm, self.comm.rank, self.comm.world
         with self._phase("search.plan"):
-            route = ops.plan(reads, self.k, world, t0, t1)
+            route = ops.plan(reads, self.k, world, t0, t1, self.prefilter)
+            self.n_routed += route.kmers; self.n_positions += route.positions
         with self._phase("search.counts"):
             M = comm.gather_counts(route.counts)            # M[r][d]: keys of rank r owned by rank d
             self._ensure_windows(int(M.sum(axis=0).max()), int(M.sum(axis=1).max()))
@@ -394,7 +442,8 @@ class PartitionedKmerIndex:
                     h.free()
                     continue
                 with self._phase("search.plan"):
-                    route = ops.plan(reads, self.k, comm.world, t0, t1)
+                    route = ops.plan(reads, self.k, comm.world, t0, t1, self.prefilter)
+                    self.n_routed += route.kmers; self.n_positions += route.positions
                 with self._phase("search.counts"):
                     recv_counts = comm.exchange_counts(route.counts)
                 n_send, n_recv = int(route.counts.sum()), int(recv_counts.sum())

@@ -42,9 +42,10 @@ class HostSeqs:
 
 
 class _Route:
-    def __init__(self, counts, keys, vals, owner, read, pos, orev):
+    def __init__(self, counts, keys, vals, owner, read, pos, orev, positions=None):
         self.counts, self.keys, self.vals, self.owner, self.read, self.pos, self.orev = counts, keys, vals, owner, read, pos, orev
         self.order = np.argsort(owner, kind="stable")
+        self.positions = len(keys) if positions is None else positions
 
     @property
     def kmers(self):
@@ -92,7 +93,32 @@ class NumpyOps:
     def tiles(self, seqs: HostSeqs) -> int:
         return seqs.tiles
 
-    def plan(self, seqs: HostSeqs, k, n_part, t0, t1):
+    # pre-filter: the double keeps its own small Bloom filter (any deterministic hash will do: it is only
+    # ever tested by the double itself); same shape on every rank so that the partial filters can be OR-ed
+    FILTER_WORDS = 1 << 12
+
+    @staticmethod
+    def _filter_bits(keys):
+        with np.errstate(over="ignore"):
+            h = keys.astype(np.uint64) * np.uint64(0xD6E8FEB86659FD93)
+        return ((h >> np.uint64(40)) % np.uint64(NumpyOps.FILTER_WORDS)).astype(np.int64), (np.uint32(1) << ((h >> np.uint64(33)) & np.uint64(31)).astype(np.uint32))
+
+    def filter_new(self, n_keys):
+        import torch
+        return torch.zeros(self.FILTER_WORDS, dtype=torch.int32), self.FILTER_WORDS, 0
+
+    def filter_add_table(self, table, flt):
+        w = flt[0].numpy().view(np.uint32)
+        uniq = np.array([key - 1 for key, m in table.multi.items() if m == 1], dtype=np.uint64)
+        if len(uniq):
+            idx, bit = self._filter_bits(uniq)
+            np.bitwise_or.at(w, idx, bit)
+
+    def filter_or(self, flt, other):
+        w = flt[0].numpy().view(np.uint32)
+        w |= other.numpy().view(np.uint32)
+
+    def plan(self, seqs: HostSeqs, k, n_part, t0, t1, prefilter=None):
         K, V, R, P, O = [], [], [], [], []
         for i, s in enumerate(seqs.seqs):
             if len(s) < k:
@@ -107,10 +133,15 @@ class NumpyOps:
             R.append(np.full(len(pos), i, dtype=np.int64)); P.append(pos.astype(np.int64))
         cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
         keys, orev, read, pos = cat(K, np.uint64), cat(O, np.uint64), cat(R, np.int64), cat(P, np.int64)
+        positions = len(keys)
+        if prefilter is not None and len(keys):
+            idx, bit = self._filter_bits(keys)
+            keep = (prefilter[0].numpy().view(np.uint32)[idx] & bit) != 0
+            keys, orev, read, pos = keys[keep], orev[keep], read[keep], pos[keep]
         vals = (read.astype(np.uint64) << np.uint64(32)) | (pos.astype(np.uint64) << np.uint64(1)) | orev
         own = owner_np(keys, n_part) if len(keys) else np.zeros(0, np.int64)
         counts = np.bincount(own, minlength=n_part).astype(np.int64)
-        return _Route(counts, keys, vals, own, read, pos, orev)
+        return _Route(counts, keys, vals, own, read, pos, orev, positions)
 
     def route_keys(self, route, t):
         t.numpy().view(np.uint64)[: route.kmers] = route.keys[route.order] + np.uint64(1)

@@ -41,17 +41,19 @@ def shard(reads, world):
     return [reads[r::world] for r in range(world)]
 
 
-@pytest.mark.parametrize("exchange", ["all_to_all", "direct"])
+@pytest.mark.parametrize("exchange,prefilter", [("all_to_all", False), ("all_to_all", True), ("direct", False), ("direct", True)])
 @pytest.mark.parametrize("world", [1, 2, 3, 5])
 @pytest.mark.parametrize("name,k", [("tiny", 25), ("repeats", 17)])
-def test_partitioned_index_threads(oracle, world, name, k, exchange):
+def test_partitioned_index_threads(oracle, world, name, k, exchange, prefilter):
     inp = synth.make_config(name)
     batches = shard(inp.reads, world)
     want_hits, want_stats = oracle_answer(oracle, inp.contigs, batches, k)
 
     def body(rank, ops, comm):
-        idx = gdist.PartitionedKmerIndex(ops, comm, k, round_kmers=40_000, exchange=exchange).build(HostSeqs(inp.contigs))
+        idx = gdist.PartitionedKmerIndex(ops, comm, k, round_kmers=40_000, exchange=exchange, prefilter=prefilter).build(HostSeqs(inp.contigs))
         hits = idx.search(HostSeqs(batches[rank]))
+        assert idx.n_routed <= idx.n_positions and (prefilter or idx.n_routed == idx.n_positions)
+        assert not prefilter or world == 1 or idx.n_routed < idx.n_positions // 2      # the filter really thins the exchange
         out = hits, idx.stats(), idx.n_local_records, comm.bytes_sent
         idx.free()
         return out

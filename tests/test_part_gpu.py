@@ -62,6 +62,34 @@ def test_route_kernels_match_double(ctx, oracle, name, k, n_part):
     ds.free()
 
 
+def test_filtered_plan_routes_a_superset_of_the_anchors(ctx, oracle):
+    """a filtered plan routes every anchoring position (no false negatives) and few others"""
+    inp = synth.make_config("small")
+    k = 25
+    cs, rs = ctx.upload(inp.contigs), ctx.upload(inp.reads)
+    plain = ctx.table_build(cs, k)
+    want = ctx.search(plain, rs)
+    n_words, k3 = ctx.filter_shape(cs.kmers(k))
+    flt = torch.zeros(n_words, dtype=torch.int32, device="cuda")
+    plain.filter_add(flt.data_ptr(), n_words, k3)
+    ctx.sync()
+    for n_part in (1, 3):
+        r = ctx.route_plan(rs, k, n_part, 0, rs.tiles, prefilter=(flt.data_ptr(), n_words, k3))
+        assert r.positions == rs.kmers(k) and len(want) <= r.kmers < r.positions // 4
+        n = r.kmers
+        keys, ans = dev_u64(n), dev_u64(n)
+        r.keys(keys.data_ptr())
+        # every key in one table here, whatever its owner segment: answer them all and collect
+        plain2 = ctx.table_build(cs, k)
+        plain2.lookup_keys(keys.data_ptr(), n, ans.data_ptr())
+        h = r.collect(ans.data_ptr())
+        assert np.array_equal(h.download(), want)
+        for x in (h, r, plain2):
+            x.free()
+    for x in (plain, cs, rs):
+        x.free()
+
+
 def test_owner_side_insert_lookup_collect(ctx, oracle):
     """one partition holding everything == the plain table: dump, answers, anchors, statistics"""
     inp = synth.make_config("repeats")
@@ -95,10 +123,10 @@ def test_owner_side_insert_lookup_collect(ctx, oracle):
         x.free()
 
 
-@pytest.mark.parametrize("exchange", ["all_to_all", "direct"])
+@pytest.mark.parametrize("exchange,prefilter", [("all_to_all", False), ("all_to_all", True), ("direct", False), ("direct", True)])
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 @pytest.mark.parametrize("name,k,round_kmers", [("tiny", 25, 1 << 31), ("repeats", 17, 50_000), ("small", 31, 300_000)])
-def test_partitioned_index_one_gpu(oracle, world, name, k, round_kmers, exchange):
+def test_partitioned_index_one_gpu(oracle, world, name, k, round_kmers, exchange, prefilter):
     inp = synth.make_config(name)
     batches = shard(inp.reads, world)
     want_hits, want_stats = oracle_answer(oracle, inp.contigs, batches, k)
@@ -108,9 +136,11 @@ def test_partitioned_index_one_gpu(oracle, world, name, k, round_kmers, exchange
 
     def body(rank, ops, comm):
         cs, rs = ops.ctx.upload(inp.contigs), ops.ctx.upload(batches[rank])
-        idx = gdist.PartitionedKmerIndex(ops, comm, k, round_kmers=round_kmers, exchange=exchange).build(cs)
+        idx = gdist.PartitionedKmerIndex(ops, comm, k, round_kmers=round_kmers, exchange=exchange, prefilter=prefilter).build(cs)
         hits = idx.search(rs)
         st = idx.stats()
+        assert idx.n_routed <= idx.n_positions and (prefilter or idx.n_routed == idx.n_positions)
+        assert not prefilter or len(hits) <= idx.n_routed < max(idx.n_positions // 2, len(hits) + 1)
         n_dev = idx.search(rs, keep_on_device=True)
         out = (hits, st, idx.n_local_records, n_dev, ops.ctx.launches())
         idx.free(); cs.free(); rs.free()
@@ -140,7 +170,7 @@ NCCL_SCRIPT = textwrap.dedent("""
     ops = gdist.DeviceOps(ctx, local)
     comm = gdist.TorchComm(ops.device)
     cs, rs = ctx.upload(inp.contigs), ctx.upload(inp.reads[rank::world])
-    idx = gdist.PartitionedKmerIndex(ops, comm, k, round_kmers=400_000, exchange=%(exchange)r).build(cs)
+    idx = gdist.PartitionedKmerIndex(ops, comm, k, round_kmers=400_000, exchange=%(exchange)r, prefilter=%(prefilter)r).build(cs)
     hits = idx.search(rs)
     st = idx.stats()
     np.save(os.path.join(%(out)r, "hits_%%d.npy" %% rank), hits)
@@ -152,11 +182,11 @@ NCCL_SCRIPT = textwrap.dedent("""
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("exchange", ["all_to_all", "direct"])
-def test_partitioned_index_nccl_world2(oracle, tmp_path, exchange):
+@pytest.mark.parametrize("exchange,prefilter", [("all_to_all", False), ("direct", False), ("direct", True)])
+def test_partitioned_index_nccl_world2(oracle, tmp_path, exchange, prefilter):
     """one process per GPU: NCCL all-to-all, and direct stores into CUDA-IPC windows over NVLink"""
     script = tmp_path / "run.py"
-    script.write_text(NCCL_SCRIPT % {"root": ROOT, "out": str(tmp_path), "exchange": exchange})
+    script.write_text(NCCL_SCRIPT % {"root": ROOT, "out": str(tmp_path), "exchange": exchange, "prefilter": prefilter})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29631", str(script)]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
