@@ -81,10 +81,12 @@ _lib = None
 
 
 def load_library(path: str = LIB_PATH):
-    """Load libgcgpu.so.  Raises when it has not been built — never falls back."""
+    """Load libgcgpu.so.  Raises when it has not been built — never falls back.
+    (GCG_LIB names another build of the same library, for A/B timing of kernel variants.)"""
     global _lib
     if _lib is not None:
         return _lib
+    path = os.environ.get("GCG_LIB", path)
     if not os.path.exists(path):
         raise GcgError("libgcgpu.so is missing (%s): run `python -c 'import __graft_entry__ as g; g.build()'` "
                        "or `make -C superplus_b200/csrc`; there is no CPU fallback" % path)

@@ -31,6 +31,7 @@
 // Trace layout per alignment (what hits HBM, 0.5 byte per cell, fully coalesced 128-byte rows):
 //   word[(band * (tlen+31) + step) * 32 + lane], nibble of column c at bit shift(c)
 #include <algorithm>
+#include <type_traits>
 #include <limits.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -240,6 +241,27 @@ __device__ __forceinline__ uint32_t pack16 (int v) { return ((uint32_t) v & 0xFF
 __device__ __forceinline__ int half_lo (uint32_t x) { return (int) (short) (x & 0xFFFFu); }
 __device__ __forceinline__ int half_hi (uint32_t x) { return ((int) x) >> 16; }
 
+// A task record re-read from global memory at every use (asm volatile: the compiler may neither
+// hoist the load out of the band loop nor keep the fields in registers across the step loop).  The
+// packed kernel runs at its 96-register budget; with the records loaded once per item, their
+// pointers and lengths (about twenty registers) stayed live through the hot loop and the edge code
+// alone cost it 12 % (measured by deleting the block).  48 bytes = three 16-byte loads, L2 hits.
+__device__ __forceinline__ sw_task ld_task (const sw_task * p)
+{
+  static_assert (sizeof (sw_task) == 48, "sw_task is read as three 16-byte words");
+  unsigned long long w[6];
+  asm volatile ("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(p));
+  asm volatile ("ld.global.cg.v2.u64 {%0,%1}, [%2+16];" : "=l"(w[2]), "=l"(w[3]) : "l"(p));
+  asm volatile ("ld.global.cg.v2.u64 {%0,%1}, [%2+32];" : "=l"(w[4]), "=l"(w[5]) : "l"(p));
+  sw_task t;
+  t.qoff = (long long) w[0]; t.toff = (long long) w[1];
+  t.qlen = (int) (uint32_t) w[2]; t.tlen = (int) (uint32_t) (w[2] >> 32);
+  t.trace_off = w[3];
+  t.edge_off = (long long) w[4];
+  t.pair = (int) (uint32_t) w[5]; t.pad = 0;
+  return t;
+}
+
 template <int MINB>
 __global__ void __launch_bounds__ (32, MINB)
 sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restrict__ tgt,
@@ -264,31 +286,48 @@ sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restr
     item = __shfl_sync (0xffffffffu, item, 0);
     if (item >= n_items) break;
     const int2 it = items[item];
-    const sw_task ta = tasks[it.x];
     const bool has_b = it.y >= 0;
-    const sw_task tb = tasks[has_b ? it.y : it.x];
-    const int QL = max (ta.qlen, tb.qlen), TL = max (ta.tlen, tb.tlen);   // both > 0 (host guarantees)
-    const uint8_t * qa = qry + ta.qoff, * qb = qry + tb.qoff, * tga = tgt + ta.toff, * tgb = tgt + tb.toff;
-    uint32_t * tra = trace + ta.trace_off, * trb = trace + tb.trace_off;
-    int * ea = edges + ta.edge_off, * eb = edges + tb.edge_off;
-    const int nsa = ta.tlen + 31, nsb = tb.tlen + 31, nba = (ta.qlen + SW_BAND - 1) / SW_BAND, nbb = (tb.qlen + SW_BAND - 1) / SW_BAND;
-    const int nsteps = TL + 31, nbands = (QL + SW_BAND - 1) / SW_BAND;
-    // per-row PRMT selectors: byte0 <- profA[tA], byte1 <- its sign, byte2 <- profB[tB], byte3 <- its sign
-    __syncwarp ();
-    for (int r = lane; r < TL; r += 32) {
-      uint32_t sa = r < ta.tlen ? tga[r] : 0, sb = r < tb.tlen ? tgb[r] : 0;
-      tsel[r] = (unsigned short) (sa | ((sa | 8u) << 4) | ((4u + sb) << 8) | ((12u + sb) << 12));
+    const sw_task * pta = tasks + it.x, * ptb = tasks + (has_b ? it.y : it.x);
+    int TL, nbands;
+    {
+      // per-row PRMT selectors: byte0 <- profA[tA], byte1 <- its sign, byte2 <- profB[tB], byte3 <- its sign
+      const sw_task ta = ld_task (pta), tb = ld_task (ptb);
+      TL = max (ta.tlen, tb.tlen);                                        // both > 0 (host guarantees)
+      nbands = (max (ta.qlen, tb.qlen) + SW_BAND - 1) / SW_BAND;
+      const uint8_t * tga = tgt + ta.toff, * tgb = tgt + tb.toff;
+      __syncwarp ();
+      for (int r = lane; r < TL; r += 32) {
+        uint32_t sa = r < ta.tlen ? tga[r] : 0, sb = r < tb.tlen ? tgb[r] : 0;
+        tsel[r] = (unsigned short) (sa | ((sa | 8u) << 4) | ((4u + sb) << 8) | ((12u + sb) << 12));
+      }
+      __syncwarp ();
     }
-    __syncwarp ();
+    const int nsteps = TL + 31;
     for (int band = 0; band < nbands; ++band) {
       const int j0 = band * SW_BAND + lane * SW_COLS;
       uint32_t PA[SW_COLS], PB[SW_COLS], Hup[SW_COLS], Dup[SW_COLS];
+      // everything that does not change inside the step loop, from the task records read afresh
+      uint32_t * pa, * pb;
+      bool wrA, wrB, no_owner;
+      int edgeA, edgeB, tlenA, tlenB;
+      {
+        const sw_task ta = ld_task (pta), tb = ld_task (ptb);
+        const uint8_t * qa = qry + ta.qoff, * qb = qry + tb.qoff;
 #pragma unroll
-      for (int c = 0; c < SW_COLS; ++c) {
-        PA[c] = c_sw.prof4[j0 + c < ta.qlen ? qa[j0 + c] : 0];
-        PB[c] = c_sw.prof4[j0 + c < tb.qlen ? qb[j0 + c] : 0];
-        Hup[c] = pack16 (16 * sw_brow (j0 + c + 1));
-        Dup[c] = NEG2;
+        for (int c = 0; c < SW_COLS; ++c) {
+          PA[c] = c_sw.prof4[j0 + c < ta.qlen ? qa[j0 + c] : 0];
+          PB[c] = c_sw.prof4[j0 + c < tb.qlen ? qb[j0 + c] : 0];
+          Hup[c] = pack16 (16 * sw_brow (j0 + c + 1));
+          Dup[c] = NEG2;
+        }
+        const int nba = (ta.qlen + SW_BAND - 1) / SW_BAND, nbb = (tb.qlen + SW_BAND - 1) / SW_BAND;
+        wrA = band < nba; wrB = has_b && band < nbb;
+        pa = trace + ta.trace_off + ((size_t) band * (ta.tlen + 31)) * 32 + lane;
+        pb = trace + tb.trace_off + ((size_t) band * (tb.tlen + 31)) * 32 + lane;
+        const bool ownA = j0 < ta.qlen && ta.qlen <= j0 + SW_COLS, ownB = has_b && j0 < tb.qlen && tb.qlen <= j0 + SW_COLS;
+        edgeA = ownA ? 1 : ta.tlen; edgeB = ownB ? 1 : (has_b ? tb.tlen : 0x7fffffff);   // rows >= edge need the slow path
+        tlenA = ta.tlen; tlenB = tb.tlen;
+        no_owner = band != nba - 1 && (!has_b || band != nbb - 1);
       }
       uint32_t prevInH = pack16 (16 * sw_brow (j0)), outH = 0, outI = NEG2;
       // boundary prefetch registers: rows [32k, 32k+32) of the previous band, one row per lane
@@ -297,17 +336,16 @@ sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restr
         if (lane < TL) pf_cur = __ldcg (bnd + lane);
         if (32 + lane < TL) pf_nxt = __ldcg (bnd + 32 + lane);
       }
-      // everything that does not change inside the step loop
-      const bool wrA = band < nba, wrB = has_b && band < nbb;
-      uint32_t * pa = tra + ((size_t) band * nsa) * 32 + lane;
-      uint32_t * pb = trb + ((size_t) band * nsb) * 32 + lane;
       const bool park = lane == 31 && band + 1 < nbands;
-      const bool ownA = j0 < ta.qlen && ta.qlen <= j0 + SW_COLS, ownB = has_b && j0 < tb.qlen && tb.qlen <= j0 + SW_COLS;
-      const int edgeA = ownA ? 1 : ta.tlen, edgeB = ownB ? 1 : (has_b ? tb.tlen : 0x7fffffff);   // rows >= edge need the slow path
-      const int tlenA = ta.tlen, tlenB = tb.tlen;
       const uint32_t col0H = pack16 (16 * sw_bcol (1)), col0step = pack16 (-16 * c_sw.b_del_e * (c_sw.border_kind ? 1 : 0));
       uint32_t col0 = col0H;                                       // 16 * border score of column 0, row `step + 1`
-      for (int step = 0; step < nsteps; ++step) {
+      // One wavefront step.  STEADY is the common case — every lane is on a valid row of both
+      // alignments and no lane is at an edge (last row, or the last column of an alignment) — in
+      // which the row-range tests, the store predicates on the row and the edge block are compiled
+      // out: without them the eight column recurrences of a step form one basic block that the
+      // scheduler interleaves freely (measured +17 % on the fill kernel).
+      auto wave_step = [&] (const int step, auto steady_tag) {
+        constexpr bool STEADY = decltype (steady_tag)::value;
         uint32_t inH = __shfl_up_sync (0xffffffffu, outH, 1), inI = __shfl_up_sync (0xffffffffu, outI, 1);
         const int i = step - lane + 1;
         if (band > 0) {
@@ -323,7 +361,7 @@ sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restr
           if (lane == 0) { inH = col0; inI = NEG2; }
           col0 = __vadd2 (col0, col0step);
         }
-        if (i >= 1 && i <= TL) {
+        if (STEADY || (i >= 1 && i <= TL)) {
           const uint32_t sel = tsel[i - 1];
           uint32_t Hd = prevInH, Hl = inH, Il = inI, accA = 0, accB = 0;
 #pragma unroll
@@ -342,41 +380,55 @@ sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restr
           }
           prevInH = inH;
           outH = Hl; outI = Il;
-          if (wrA && i <= tlenA) pa[(uint32_t) step * 32u] = __byte_perm (accA, accB, 0x5410);
-          if (wrB && i <= tlenB) pb[(uint32_t) step * 32u] = __byte_perm (accA, accB, 0x7632);
+          if (wrA && (STEADY || i <= tlenA)) pa[(uint32_t) step * 32u] = __byte_perm (accA, accB, 0x5410);
+          if (wrB && (STEADY || i <= tlenB)) pb[(uint32_t) step * 32u] = __byte_perm (accA, accB, 0x7632);
           // park the last column for the next band.  Row r is written at step r+31 and was fetched
           // (for this band) no later than step r-1, so reusing the buffer in place is safe.
           if (park) __stcg (bnd + (i - 1), make_uint2 (outH, outI));
-          if (i >= edgeA || i >= edgeB) {
+          if (!STEADY && (i >= edgeA || i >= edgeB)) {
             // rare: this lane holds the last column of an alignment, or is on its last row
-            if (ownA && i <= tlenA) {
+            const sw_task ta = ld_task (pta), tb = ld_task (ptb);
+            int * ea = edges + ta.edge_off, * eb = edges + tb.edge_off;
+            const bool ownA = j0 < ta.qlen && ta.qlen <= j0 + SW_COLS, ownB = has_b && j0 < tb.qlen && tb.qlen <= j0 + SW_COLS;
+            if (ownA && i <= ta.tlen) {
               uint32_t v = 0; const int cs = (ta.qlen - 1) % SW_COLS;
 #pragma unroll
               for (int c = 0; c < SW_COLS; ++c) if (c == cs) v = Hup[c];
               __stcg (ea + (i - 1), half_lo (v) >> 4);
             }
-            if (ownB && i <= tlenB) {
+            if (ownB && i <= tb.tlen) {
               uint32_t v = 0; const int cs = (tb.qlen - 1) % SW_COLS;
 #pragma unroll
               for (int c = 0; c < SW_COLS; ++c) if (c == cs) v = Hup[c];
               __stcg (eb + (i - 1), half_hi (v) >> 4);
             }
-            if (i == tlenA) {
+            if (i == ta.tlen) {
 #pragma unroll
-              for (int c = 0; c < SW_COLS; ++c) if (j0 + c < ta.qlen) __stcg (ea + tlenA + j0 + c, half_lo (Hup[c]) >> 4);
+              for (int c = 0; c < SW_COLS; ++c) if (j0 + c < ta.qlen) __stcg (ea + ta.tlen + j0 + c, half_lo (Hup[c]) >> 4);
             }
-            if (has_b && i == tlenB) {
+            if (has_b && i == tb.tlen) {
 #pragma unroll
-              for (int c = 0; c < SW_COLS; ++c) if (j0 + c < tb.qlen) __stcg (eb + tlenB + j0 + c, half_hi (Hup[c]) >> 4);
+              for (int c = 0; c < SW_COLS; ++c) if (j0 + c < tb.qlen) __stcg (eb + tb.tlen + j0 + c, half_hi (Hup[c]) >> 4);
             }
           }
         }
+      };
+      // steady steps: all 32 lanes on rows 1 .. min(tlen)-1, in a band where no lane owns a last column
+      const int steady_end = no_owner ? min (nsteps, min (tlenA, tlenB) - 1) : 0;      // steps [31, steady_end)
+      int step = 0;
+      if (steady_end > 31) {
+        for (; step < 31; ++step) wave_step (step, std::false_type ());
+        for (; step < steady_end; ++step) wave_step (step, std::true_type ());
       }
+      for (; step < nsteps; ++step) wave_step (step, std::false_type ());
       __syncwarp ();
     }
     __syncwarp ();
-    sw_pick_end (ea, ta.qlen, ta.tlen, lane, ends + ta.pair);
-    if (has_b) sw_pick_end (eb, tb.qlen, tb.tlen, lane, ends + tb.pair);
+    {
+      const sw_task ta = ld_task (pta), tb = ld_task (ptb);
+      sw_pick_end (edges + ta.edge_off, ta.qlen, ta.tlen, lane, ends + ta.pair);
+      if (has_b) sw_pick_end (edges + tb.edge_off, tb.qlen, tb.tlen, lane, ends + tb.pair);
+    }
     __syncwarp ();
   }
 #undef cDO
