@@ -7,7 +7,7 @@ from superplus_b200 import api, synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 mode = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-qlen, tlen = 10_000, 2_000
+qlen, tlen = int(os.environ.get("QLEN", 10_000)), int(os.environ.get("TLEN", 2_000))
 t0 = time.time()
 base_q, base_t = synth.make_sw_pairs(min(n, 256), qlen, tlen, seed=46)
 reps = (n + len(base_q) - 1) // len(base_q)

@@ -61,6 +61,7 @@ struct sw_consts {
   // packed kernel: the four gap constants as s16x2 words, built on the host so that the step loop
   // reads them as constant-bank operands instead of rebuilding them (IMAD/LOP3 per step)
   unsigned pk_do, pk_de, pk_io, pk_ie;
+  unsigned pk_de32, pk_ie32;        // -16*e * 65537: both halves in one 32-bit add (values are biased, see SW_BIAS2)
 };
 
 __constant__ sw_consts c_sw;
@@ -240,6 +241,15 @@ __device__ __forceinline__ uint32_t prmt (uint32_t a, uint32_t b, uint32_t sel)
 __device__ __forceinline__ uint32_t pack16 (int v) { return ((uint32_t) v & 0xFFFFu) * 0x10001u; }
 __device__ __forceinline__ int half_lo (uint32_t x) { return (int) (short) (x & 0xFFFFu); }
 __device__ __forceinline__ int half_hi (uint32_t x) { return ((int) x) >> 16; }
+// The packed kernel carries its values biased by 0x8000 per half (unsigned order == signed order of
+// the scores).  With both halves non-negative a packed add of two small negative constants is one
+// ordinary 32-bit add — the borrow out of the low half is always the same and is folded into the
+// constant (c * 65537) — which lets the two standalone adds per cell run as IMAD on the FMA pipe
+// instead of VIADD.16x2 on the integer pipe the VIADDMNMX / VIMNMX / PRMT / LOP3 work saturates.
+#define SW_BIAS2 0x80008000u
+__device__ __forceinline__ uint32_t pack16b (int v) { return pack16 (v) ^ SW_BIAS2; }
+__device__ __forceinline__ int bhalf_lo (uint32_t x) { return (int) (x & 0xFFFFu) - 32768; }
+__device__ __forceinline__ int bhalf_hi (uint32_t x) { return (int) (x >> 16) - 32768; }
 
 // A task record re-read from global memory at every use (asm volatile: the compiler may neither
 // hoist the load out of the band loop nor keep the fields in registers across the step loop).  The
@@ -262,24 +272,27 @@ __device__ __forceinline__ sw_task ld_task (const sw_task * p)
   return t;
 }
 
+struct sw_packed_consts { uint32_t pk_do, pk_io, pk_de32, pk_ie32, one; };
+
 template <int MINB>
 __global__ void __launch_bounds__ (32, MINB)
 sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restrict__ tgt,
                        const sw_task * __restrict__ tasks, const int2 * __restrict__ items, int n_items,
                        int * __restrict__ counter, uint32_t * __restrict__ trace, int * __restrict__ edges,
-                       uint2 * __restrict__ bound, int rows_cap, sw_end * __restrict__ ends)
+                       uint2 * __restrict__ bound, int rows_cap, sw_end * __restrict__ ends, const sw_packed_consts gk)
 {
+  // gk: the gap constants and `one` == 1 as kernel arguments: they reach the step loop as uniform-register
+  // operands (no LDC per step, no registers), and x * one + y stays an IMAD (FMA pipe).
   // shared: one PRMT selector per target row.  The last column of the previous band (H, I of both
   // alignments, 8 bytes per row) lives in an L2-resident scratch: lane 31 parks it row by row, all
   // 32 lanes fetch the next 32 rows in one coalesced load a full 32 steps before lane 0 needs them.
   extern __shared__ unsigned short tsel[];
   const int lane = threadIdx.x;
   uint2 * bnd = bound + (size_t) blockIdx.x * rows_cap;
-#define cDO c_sw.pk_do
-#define cDE c_sw.pk_de
-#define cIO c_sw.pk_io
-#define cIE c_sw.pk_ie
-  const uint32_t NEG2 = pack16 (16 * SW_NEG16V);
+#define cDO gk.pk_do
+#define cIO gk.pk_io
+  const uint32_t NEG2 = pack16b (16 * SW_NEG16V);
+  const uint32_t cDE32 = gk.pk_de32, cIE32 = gk.pk_ie32, one = gk.one, sixteen = gk.one << 4;
   for (;;) {
     int item = 0;
     if (lane == 0) item = atomicAdd (counter, 1);
@@ -317,7 +330,7 @@ sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restr
         for (int c = 0; c < SW_COLS; ++c) {
           PA[c] = c_sw.prof4[j0 + c < ta.qlen ? qa[j0 + c] : 0];
           PB[c] = c_sw.prof4[j0 + c < tb.qlen ? qb[j0 + c] : 0];
-          Hup[c] = pack16 (16 * sw_brow (j0 + c + 1));
+          Hup[c] = pack16b (16 * sw_brow (j0 + c + 1));
           Dup[c] = NEG2;
         }
         const int nba = (ta.qlen + SW_BAND - 1) / SW_BAND, nbb = (tb.qlen + SW_BAND - 1) / SW_BAND;
@@ -329,63 +342,68 @@ sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restr
         tlenA = ta.tlen; tlenB = tb.tlen;
         no_owner = band != nba - 1 && (!has_b || band != nbb - 1);
       }
-      uint32_t prevInH = pack16 (16 * sw_brow (j0)), outH = 0, outI = NEG2;
+      uint32_t prevInH = pack16b (16 * sw_brow (j0)), outH = SW_BIAS2, outI = NEG2;
       // boundary prefetch registers: rows [32k, 32k+32) of the previous band, one row per lane
-      uint2 pf_cur = make_uint2 (0u, NEG2), pf_nxt = make_uint2 (0u, NEG2);
+      uint2 pf_cur = make_uint2 (SW_BIAS2, NEG2), pf_nxt = make_uint2 (SW_BIAS2, NEG2);
       if (band > 0) {
         if (lane < TL) pf_cur = __ldcg (bnd + lane);
         if (32 + lane < TL) pf_nxt = __ldcg (bnd + 32 + lane);
       }
       const bool park = lane == 31 && band + 1 < nbands;
-      const uint32_t col0H = pack16 (16 * sw_bcol (1)), col0step = pack16 (-16 * c_sw.b_del_e * (c_sw.border_kind ? 1 : 0));
-      uint32_t col0 = col0H;                                       // 16 * border score of column 0, row `step + 1`
-      // One wavefront step.  STEADY is the common case — every lane is on a valid row of both
-      // alignments and no lane is at an edge (last row, or the last column of an alignment) — in
-      // which the row-range tests, the store predicates on the row and the edge block are compiled
-      // out: without them the eight column recurrences of a step form one basic block that the
-      // scheduler interleaves freely (measured +17 % on the fill kernel).
-      auto wave_step = [&] (const int step, auto steady_tag) {
-        constexpr bool STEADY = decltype (steady_tag)::value;
+      const uint32_t col0step = pack16 (-16 * c_sw.b_del_e * (c_sw.border_kind ? 1 : 0));
+      uint32_t col0 = pack16b (16 * sw_bcol (1));                  // 16 * border score of column 0, row `step + 1`
+      // The eight cells of this lane on one row.  Integer-pipe work per cell pair: PRMT (score),
+      // 3 x VIADDMNMX.U16x2, VIMNMX.U16x2, 4 x LOP3; the two gap-extension adds, the tag of H
+      // (H - Hc) and the two nibble accumulators are IMADs (x * one + y) on the FMA pipe.
+      auto row_cells = [&] (const uint32_t inH, const uint32_t inI, const uint32_t sel, uint32_t & wA, uint32_t & wB) {
+        uint32_t Hd = prevInH, Hl = inH, Il = inI, aH = 0, aT = 0, bH = 0, bT = 0;
+#pragma unroll
+        for (int c = 0; c < SW_COLS; ++c) {
+          const uint32_t s = prmt (PA[c], PB[c], sel);
+          const uint32_t dE = (Dup[c] | 0x00020002u) * one + cDE32;
+          const uint32_t D = __viaddmax_u16x2 (Hup[c], cDO, dE);
+          const uint32_t iE = (Il | 0x00010001u) * one + cIE32;
+          const uint32_t I = __viaddmax_u16x2 (Hl, cIO, iE);
+          const uint32_t g = __vmaxu2 (D, I);
+          const uint32_t H = __viaddmax_u16x2 (Hd, s, g);
+          const uint32_t Hc = H & 0xFFF0FFF0u;
+          const uint32_t tH = H * one - Hc;                        // tag of H: 8 = M, 4|2 = D, 0|1 = I
+          const uint32_t tT = (D | I) & 0x00030003u;               // bit 1 D extended, bit 0 I extended (covers tH & 3)
+          if (c < 4) { aH = aH * sixteen + tH; aT = aT * sixteen + tT; }
+          else       { bH = bH * sixteen + tH; bT = bT * sixteen + tT; }
+          Hd = Hup[c]; Hup[c] = Hc; Dup[c] = D; Hl = Hc; Il = I;
+        }
+        prevInH = inH;
+        outH = Hl; outI = Il;
+        wA = aH | aT; wB = bH | bT;
+      };
+      auto rotate_prefetch = [&] (const int step) {                // after step == 31 (mod 32): rows of the chunk after the next one
+        pf_cur = pf_nxt;
+        const int r = step + 33 + lane;
+        if (r < TL) pf_nxt = __ldcg (bnd + r);
+      };
+      // A step with every test in place: ramps, last rows, last columns.
+      auto edge_step = [&] (const int step) {
         uint32_t inH = __shfl_up_sync (0xffffffffu, outH, 1), inI = __shfl_up_sync (0xffffffffu, outI, 1);
         const int i = step - lane + 1;
         if (band > 0) {
           // lane 0 is on row step+1: its left neighbour is row `step` of the parked column
           uint32_t bh = __shfl_sync (0xffffffffu, pf_cur.x, step & 31), bi = __shfl_sync (0xffffffffu, pf_cur.y, step & 31);
           if (lane == 0) { inH = bh; inI = bi; }
-          if ((step & 31) == 31) {
-            pf_cur = pf_nxt;
-            int r = step + 33 + lane;                    // rows of the chunk after the next one
-            if (r < TL) pf_nxt = __ldcg (bnd + r);
-          }
+          if ((step & 31) == 31) rotate_prefetch (step);
         } else {
           if (lane == 0) { inH = col0; inI = NEG2; }
           col0 = __vadd2 (col0, col0step);
         }
-        if (STEADY || (i >= 1 && i <= TL)) {
-          const uint32_t sel = tsel[i - 1];
-          uint32_t Hd = prevInH, Hl = inH, Il = inI, accA = 0, accB = 0;
-#pragma unroll
-          for (int c = 0; c < SW_COLS; ++c) {
-            uint32_t s = prmt (PA[c], PB[c], sel);
-            uint32_t dE = __vadd2 (Dup[c] | 0x00020002u, cDE);
-            uint32_t D = __viaddmax_s16x2 (Hup[c], cDO, dE);
-            uint32_t iE = __vadd2 (Il | 0x00010001u, cIE);
-            uint32_t I = __viaddmax_s16x2 (Hl, cIO, iE);
-            uint32_t g = __vmaxs2 (D, I);
-            uint32_t H = __viaddmax_s16x2 (Hd, s, g);
-            uint32_t Hc = H & 0xFFF0FFF0u;
-            uint32_t nib = ((D | I) & 0x00030003u) | (H & 0x000C000Cu);
-            if (c < 4) accA = (accA << 4) | nib; else accB = (accB << 4) | nib;
-            Hd = Hup[c]; Hup[c] = Hc; Dup[c] = D; Hl = Hc; Il = I;
-          }
-          prevInH = inH;
-          outH = Hl; outI = Il;
-          if (wrA && (STEADY || i <= tlenA)) pa[(uint32_t) step * 32u] = __byte_perm (accA, accB, 0x5410);
-          if (wrB && (STEADY || i <= tlenB)) pb[(uint32_t) step * 32u] = __byte_perm (accA, accB, 0x7632);
+        if (i >= 1 && i <= TL) {
+          uint32_t wA, wB;
+          row_cells (inH, inI, tsel[i - 1], wA, wB);
+          if (wrA && i <= tlenA) pa[(uint32_t) step * 32u] = __byte_perm (wA, wB, 0x5410);
+          if (wrB && i <= tlenB) pb[(uint32_t) step * 32u] = __byte_perm (wA, wB, 0x7632);
           // park the last column for the next band.  Row r is written at step r+31 and was fetched
           // (for this band) no later than step r-1, so reusing the buffer in place is safe.
           if (park) __stcg (bnd + (i - 1), make_uint2 (outH, outI));
-          if (!STEADY && (i >= edgeA || i >= edgeB)) {
+          if (i >= edgeA || i >= edgeB) {
             // rare: this lane holds the last column of an alignment, or is on its last row
             const sw_task ta = ld_task (pta), tb = ld_task (ptb);
             int * ea = edges + ta.edge_off, * eb = edges + tb.edge_off;
@@ -394,33 +412,68 @@ sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restr
               uint32_t v = 0; const int cs = (ta.qlen - 1) % SW_COLS;
 #pragma unroll
               for (int c = 0; c < SW_COLS; ++c) if (c == cs) v = Hup[c];
-              __stcg (ea + (i - 1), half_lo (v) >> 4);
+              __stcg (ea + (i - 1), bhalf_lo (v) >> 4);
             }
             if (ownB && i <= tb.tlen) {
               uint32_t v = 0; const int cs = (tb.qlen - 1) % SW_COLS;
 #pragma unroll
               for (int c = 0; c < SW_COLS; ++c) if (c == cs) v = Hup[c];
-              __stcg (eb + (i - 1), half_hi (v) >> 4);
+              __stcg (eb + (i - 1), bhalf_hi (v) >> 4);
             }
             if (i == ta.tlen) {
 #pragma unroll
-              for (int c = 0; c < SW_COLS; ++c) if (j0 + c < ta.qlen) __stcg (ea + ta.tlen + j0 + c, half_lo (Hup[c]) >> 4);
+              for (int c = 0; c < SW_COLS; ++c) if (j0 + c < ta.qlen) __stcg (ea + ta.tlen + j0 + c, bhalf_lo (Hup[c]) >> 4);
             }
             if (has_b && i == tb.tlen) {
 #pragma unroll
-              for (int c = 0; c < SW_COLS; ++c) if (j0 + c < tb.qlen) __stcg (eb + tb.tlen + j0 + c, half_hi (Hup[c]) >> 4);
+              for (int c = 0; c < SW_COLS; ++c) if (j0 + c < tb.qlen) __stcg (eb + tb.tlen + j0 + c, bhalf_hi (Hup[c]) >> 4);
             }
           }
         }
       };
-      // steady steps: all 32 lanes on rows 1 .. min(tlen)-1, in a band where no lane owns a last column
-      const int steady_end = no_owner ? min (nsteps, min (tlenA, tlenB) - 1) : 0;      // steps [31, steady_end)
+      // Steady steps — all 32 lanes on rows 1 .. min(tlen)-1 of a band in which no lane owns a last
+      // column — run in chunks of 32 (one prefetch register set per chunk) without row-range tests,
+      // store predicates on the row or edge code: the eight column recurrences of a step form one
+      // basic block that the scheduler interleaves freely.
+      const int steady_end = no_owner ? min (nsteps, min (tlenA, tlenB) - 1) : 0;      // steady steps: [32, steady_end)
       int step = 0;
-      if (steady_end > 31) {
-        for (; step < 31; ++step) wave_step (step, std::false_type ());
-        for (; step < steady_end; ++step) wave_step (step, std::true_type ());
+      while (step < nsteps) {
+        if (step >= 32 && step + 32 <= steady_end) {
+          const unsigned short * ts = tsel + (step - lane);                                  // row i-1 = step - lane
+          uint32_t * qa_ = pa + (size_t) step * 32u, * qb_ = pb + (size_t) step * 32u;
+          uint2 * pk_ = bnd + (step - lane);
+          if (band > 0) {
+#pragma unroll 1
+            for (int k = 0; k < 32; ++k) {
+              uint32_t inH = __shfl_up_sync (0xffffffffu, outH, 1), inI = __shfl_up_sync (0xffffffffu, outI, 1);
+              const uint32_t bh = __shfl_sync (0xffffffffu, pf_cur.x, k), bi = __shfl_sync (0xffffffffu, pf_cur.y, k);
+              if (lane == 0) { inH = bh; inI = bi; }
+              uint32_t wA, wB;
+              row_cells (inH, inI, ts[k], wA, wB);
+              if (wrA) qa_[k * 32] = __byte_perm (wA, wB, 0x5410);
+              if (wrB) qb_[k * 32] = __byte_perm (wA, wB, 0x7632);
+              if (park) __stcg (pk_ + k, make_uint2 (outH, outI));
+            }
+            rotate_prefetch (step + 31);
+          } else {
+#pragma unroll 1
+            for (int k = 0; k < 32; ++k) {
+              uint32_t inH = __shfl_up_sync (0xffffffffu, outH, 1), inI = __shfl_up_sync (0xffffffffu, outI, 1);
+              if (lane == 0) { inH = col0; inI = NEG2; }
+              col0 = __vadd2 (col0, col0step);
+              uint32_t wA, wB;
+              row_cells (inH, inI, ts[k], wA, wB);
+              if (wrA) qa_[k * 32] = __byte_perm (wA, wB, 0x5410);
+              if (wrB) qb_[k * 32] = __byte_perm (wA, wB, 0x7632);
+              if (park) __stcg (pk_ + k, make_uint2 (outH, outI));
+            }
+          }
+          step += 32;
+        } else {
+          edge_step (step);
+          ++step;
+        }
       }
-      for (; step < nsteps; ++step) wave_step (step, std::false_type ());
       __syncwarp ();
     }
     __syncwarp ();
@@ -432,9 +485,7 @@ sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restr
     __syncwarp ();
   }
 #undef cDO
-#undef cDE
 #undef cIO
-#undef cIE
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -553,7 +604,7 @@ sw_maxsym_kernel (const uint8_t * __restrict__ qry, const long long * __restrict
 // resident warps per SM of the packed kernel = its register budget (GCG_SW_OCC: 20 | 24).  Measured on
 // cfg3-shaped waves: 20 warps at 96 registers 62.9 ms; 24 warps at 80 registers (76 bytes spilled) 69.8 ms
 // for the same 2960-warp wave — and a wave that fills 24 warps per SM needs 74 GB of trace.
-typedef void (* sw_packed_fn_t) (const uint8_t *, const uint8_t *, const sw_task *, const int2 *, int, int *, uint32_t *, int *, uint2 *, int, sw_end *);
+typedef void (* sw_packed_fn_t) (const uint8_t *, const uint8_t *, const sw_task *, const int2 *, int, int *, uint32_t *, int *, uint2 *, int, sw_end *, sw_packed_consts);
 static sw_packed_fn_t sw_packed_fn ()
 {
   static int occ = -1;
@@ -775,6 +826,7 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
     auto pk = [] (int v) { return ((unsigned) v & 0xFFFFu) * 0x10001u; };
     hc.pk_do = pk (-16 * P->del_o + 4); hc.pk_de = pk (-16 * P->del_e);
     hc.pk_io = pk (-16 * P->ins_o); hc.pk_ie = pk (-16 * P->ins_e);
+    hc.pk_de32 = (unsigned) (-16 * P->del_e * 65537); hc.pk_ie32 = (unsigned) (-16 * P->ins_e * 65537);
   }
   GCG_CUDA (cudaMemcpyToSymbolAsync (c_sw, &hc, sizeof hc, 0, cudaMemcpyHostToDevice, ctx->stream));
 
@@ -846,7 +898,21 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
   // wave construction: work units in launch order (packed items first, then generic), cut by budget
   struct unit { int a, b; bool packed; };
   std::vector<unit> units;
-  for (size_t i = 0; i < packed_ids.size (); i += 2) units.push_back ({packed_ids[i], i + 1 < packed_ids.size () ? packed_ids[i + 1] : -1, true});
+  // Two alignments share a warp only if neither half can leave its 16 bits anywhere in the common
+  // (band-padded) rectangle: the packed kernel adds both halves with one 32-bit add, so a borrow out
+  // of the low half — harmless garbage past the end of the shorter alignment when the halves were
+  // added separately — would reach the other alignment.  An alignment alone in its warp sits in the
+  // low half, which nothing can reach.
+  auto pair_ok = [&] (int x, int y) -> bool {
+    const sw_task & a = tasks[(size_t) x], & c = tasks[(size_t) y];
+    long long lo, hi, qpad = ((long long) std::max (a.qlen, c.qlen) + SW_BAND - 1) / SW_BAND * SW_BAND;
+    sw_bounds (P, qpad, std::max (a.tlen, c.tlen), &lo, &hi);
+    return lo >= -2030 && hi <= 2040;
+  };
+  for (size_t i = 0; i < packed_ids.size (); ) {
+    if (i + 1 < packed_ids.size () && pair_ok (packed_ids[i], packed_ids[i + 1])) { units.push_back ({packed_ids[i], packed_ids[i + 1], true}); i += 2; }
+    else { units.push_back ({packed_ids[i], -1, true}); i += 1; }
+  }
   for (int id : generic_ids) units.push_back ({id, -1, false});
 
   uint32_t * d_trace = nullptr; int * d_edges = nullptr; sw_task * d_tasks = nullptr; int * d_items = nullptr; int * d_counter = nullptr;
@@ -955,7 +1021,7 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
       d_pbound = (uint2 *) b->s_pbound.p;
       gcg_kscope ks (ctx, "k7_sw_fill_packed");
       sw_packed_fn ()<<<grid, 32, smem, ctx->stream>>> (b->d_qry, b->d_tgt, d_tasks, (const int2 *) d_items, (int) pitems.size (),
-                                                        d_counter, d_trace, d_edges, d_pbound, rows_cap, b->d_ends);
+                                                        d_counter, d_trace, d_edges, d_pbound, rows_cap, b->d_ends, sw_packed_consts {hc.pk_do, hc.pk_io, hc.pk_de32, hc.pk_ie32, 1u});
       GCG_CUDA (cudaGetLastError ());
     }
     if (!gitems.empty ()) {
