@@ -81,6 +81,10 @@ void gcg_seqs_free (gcg_seqs * s);
 int64_t gcg_seqs_count (const gcg_seqs * s);
 int64_t gcg_seqs_bases (const gcg_seqs * s);
 int64_t gcg_seqs_kmers (const gcg_seqs * s, int k);   /* sum over sequences of max(0, len-k+1) */
+/* the same packing on the host (no device needed): what the gather of gcg_search does to every
+ * read on its way into the pinned upload buffer.  words_out receives (len + 31) / 32 words, 32
+ * bases per word, first base in the top two bits, tail padded with code 0. */
+int  gcg_host_pack_2bit (const char * seq, int64_t len, uint64_t * words_out);
 
 /* ------------------------------------------------------------------ contig k-mers ---- */
 /* replaces chop_contig_seqs2kmers (kmer.c:155-184 / 37-121): one 24-byte record per contig

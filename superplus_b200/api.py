@@ -26,7 +26,7 @@ EXPORTS = [
     "gcg_device_count", "gcg_init", "gcg_destroy", "gcg_last_error", "gcg_set_host_threads", "gcg_stream", "gcg_sync", "gcg_warmup",
     "gcg_prof_enable", "gcg_prof_reset", "gcg_prof_report", "gcg_launch_count", "gcg_ubench_int16", "gcg_ubench_hbm", "gcg_ubench_gather",
     "gcg_seqs_upload", "gcg_seqs_upload_concat", "gcg_ascii_upload_concat", "gcg_seqs_pack", "gcg_ascii_free",
-    "gcg_seqs_free", "gcg_seqs_count", "gcg_seqs_bases", "gcg_seqs_kmers",
+    "gcg_seqs_free", "gcg_seqs_count", "gcg_seqs_bases", "gcg_seqs_kmers", "gcg_host_pack_2bit",
     "gcg_chop_contigs", "gcg_table_build_seqs", "gcg_table_build", "gcg_table_free", "gcg_table_stats",
     "gcg_table_size", "gcg_table_dump",
     "gcg_search_seqs", "gcg_hits_count", "gcg_hits_download", "gcg_hits_free", "gcg_search", "gcg_free",
@@ -80,6 +80,17 @@ def make_sw_params(mat=None, del_o=2, del_e=1, ins_o=2, ins_e=1, strategy=SOFTCL
 _lib = None
 
 
+def host_pack_2bit(seq: bytes) -> np.ndarray:
+    """The host-side 2-bit packing of the search gather (no device needed): (len+31)//32 words."""
+    L = load_library()
+    a = np.frombuffer(seq, dtype=np.uint8)
+    out = np.zeros((len(a) + 31) // 32, dtype=np.uint64)
+    rc = L.gcg_host_pack_2bit(a.ctypes.data if len(a) else None, len(a), out.ctypes.data if len(out) else None)
+    if rc:
+        raise GcgError(L.gcg_last_error().decode())
+    return out
+
+
 def load_library(path: str = LIB_PATH):
     """Load libgcgpu.so.  Raises when it has not been built — never falls back.
     (GCG_LIB names another build of the same library, for A/B timing of kernel variants.)"""
@@ -119,6 +130,7 @@ def load_library(path: str = LIB_PATH):
         f.argtypes = [vp]
     L.gcg_seqs_kmers.restype = i64
     L.gcg_seqs_kmers.argtypes = [vp, C.c_int]
+    L.gcg_host_pack_2bit.argtypes = [vp, i64, vp]
     L.gcg_chop_contigs.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
     L.gcg_table_build_seqs.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
     L.gcg_table_build.argtypes = [vp, vp, vp, i32, C.c_int, C.POINTER(vp)]

@@ -7,7 +7,8 @@
 // transfers per byte.  Streaming stores (MOVNTDQ, baseline x86-64) write whole 64-byte lines
 // without the read; destinations are 32-byte aligned by construction (sequences start on packed
 // word boundaries).
-#include <emmintrin.h>
+#include <immintrin.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <condition_variable>
@@ -124,3 +125,98 @@ void gcg_copy_stream (void * dst_, const void * src_, size_t n)
 }
 
 void gcg_copy_fence (void) { _mm_sfence (); }
+
+// ---------------------------------------------------------------------------------------------
+// ASCII -> 2 bit on the host, for the host-buffer search: the gather has to read every base of
+// the caller's strings anyway; writing 2 bits per base instead of 8 cuts the pinned-memory writes
+// and the PCIe upload by four (host memory bandwidth is what bounds the end-to-end rate, see
+// DESIGN.md 6).  Same packing as k1_pack_kernel / pack4: base code (c >> 1) & 3 (bio.h:23-24), 32
+// bases per 64-bit word, first base in the top two bits, tail padded with code 0.
+// ---------------------------------------------------------------------------------------------
+static inline uint32_t pack4_swar (uint32_t x) { return (((x >> 1) & 0x03030303u) * 0x40100401u) >> 24; }
+
+static inline uint64_t pack32_swar (const char * s)
+{
+  uint32_t v[8];
+  memcpy (v, s, 32);
+  uint64_t r = 0;
+  for (int i = 0; i < 8; ++i) r = (r << 8) | pack4_swar (v[i]);
+  return r;
+}
+
+__attribute__ ((target ("bmi2"))) static inline uint64_t pack32_pext (const char * s)
+{
+  // byte-swap so that the first base sits in the most significant byte, then gather bits 1-2 of
+  // every byte: 8 bases -> 16 bits, first base on top
+  const uint64_t M = 0x0606060606060606ULL;
+  uint64_t a, b, c, d;
+  memcpy (&a, s, 8); memcpy (&b, s + 8, 8); memcpy (&c, s + 16, 8); memcpy (&d, s + 24, 8);
+  return (__builtin_ia32_pext_di (__builtin_bswap64 (a), M) << 48) | (__builtin_ia32_pext_di (__builtin_bswap64 (b), M) << 32) |
+         (__builtin_ia32_pext_di (__builtin_bswap64 (c), M) << 16) | __builtin_ia32_pext_di (__builtin_bswap64 (d), M);
+}
+
+static inline void store_word_stream (uint64_t * dst, uint64_t v) { _mm_stream_si64 ((long long *) dst, (long long) v); }
+
+__attribute__ ((target ("bmi2"))) static void pack_stream_pext (uint64_t * dst, const char * src, size_t n)
+{
+  size_t w = 0;
+  for (; (w + 1) * 32 <= n; ++w) store_word_stream (dst + w, pack32_pext (src + w * 32));
+  if (w * 32 < n) {
+    char tail[32] = {0};
+    memcpy (tail, src + w * 32, n - w * 32);
+    store_word_stream (dst + w, pack32_pext (tail));
+  }
+}
+
+// AVX2: 32 bases per iteration.  (x >> 1) & 3 per byte, then two multiply-adds fold four codes into
+// one byte per 32-bit lane (b0*64 + b1*16 + b2*4 + b3), a byte shuffle collects the eight bytes in
+// big-endian order (first base in the top bits of the word).
+__attribute__ ((target ("avx2"))) static inline uint64_t pack32_avx2 (const char * s)
+{
+  const __m256i x = _mm256_loadu_si256 ((const __m256i *) s);
+  const __m256i c = _mm256_and_si256 (_mm256_srli_epi16 (x, 1), _mm256_set1_epi8 (3));
+  const __m256i p = _mm256_maddubs_epi16 (c, _mm256_set1_epi32 (0x01041040));          // bytes 64,16,4,1
+  const __m256i q = _mm256_madd_epi16 (p, _mm256_set1_epi16 (1));
+  const __m256i ctl = _mm256_setr_epi8 (12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                        12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+  const __m256i r = _mm256_shuffle_epi8 (q, ctl);
+  const uint32_t hi = (uint32_t) _mm256_extract_epi32 (r, 0), lo = (uint32_t) _mm256_extract_epi32 (r, 4);
+  return ((uint64_t) hi << 32) | lo;
+}
+
+__attribute__ ((target ("avx2"))) static void pack_stream_avx2 (uint64_t * dst, const char * src, size_t n)
+{
+  size_t w = 0;
+  for (; (w + 1) * 32 <= n; ++w) store_word_stream (dst + w, pack32_avx2 (src + w * 32));
+  if (w * 32 < n) {
+    char tail[32] = {0};
+    memcpy (tail, src + w * 32, n - w * 32);
+    store_word_stream (dst + w, pack32_avx2 (tail));
+  }
+}
+
+static void pack_stream_swar (uint64_t * dst, const char * src, size_t n)
+{
+  size_t w = 0;
+  for (; (w + 1) * 32 <= n; ++w) store_word_stream (dst + w, pack32_swar (src + w * 32));
+  if (w * 32 < n) {
+    char tail[32] = {0};
+    memcpy (tail, src + w * 32, n - w * 32);
+    store_word_stream (dst + w, pack32_swar (tail));
+  }
+}
+
+void gcg_pack_stream (uint64_t * dst, const void * src, size_t n)
+{
+  // GCG_HOST_PACK = avx2 | pext | swar forces a path (tests); default: the best the CPU has
+  static const int path = [] () {
+    const char * e = getenv ("GCG_HOST_PACK");
+    if (e && !strcmp (e, "swar")) return 0;
+    if (e && !strcmp (e, "pext") && __builtin_cpu_supports ("bmi2")) return 1;
+    if (e && !strcmp (e, "avx2") && __builtin_cpu_supports ("avx2")) return 2;
+    return __builtin_cpu_supports ("avx2") ? 2 : __builtin_cpu_supports ("bmi2") ? 1 : 0;
+  } ();
+  if (path == 2) pack_stream_avx2 (dst, (const char *) src, n);
+  else if (path == 1) pack_stream_pext (dst, (const char *) src, n);
+  else pack_stream_swar (dst, (const char *) src, n);
+}

@@ -17,3 +17,6 @@ void gcg_workers_wait (gcg_workers * w);
 // memcpy with non-temporal stores when dst is 16-byte aligned; gcg_copy_fence() before a DMA reads dst
 void gcg_copy_stream (void * dst, const void * src, size_t n);
 void gcg_copy_fence (void);
+// ASCII -> 2-bit packed words (k1_pack_kernel's layout), ceil(n / 32) words with non-temporal stores;
+// gcg_copy_fence() before a DMA reads dst
+void gcg_pack_stream (uint64_t * dst, const void * src, size_t n);

@@ -522,6 +522,13 @@ static int stream_ascii (gcg_ctx * ctx, const seq_src & src, const std::vector<i
   return GCG_OK;
 }
 
+extern "C" int gcg_host_pack_2bit (const char * seq, int64_t len, uint64_t * words_out)
+{
+  GCG_CHECK (len >= 0 && (len == 0 || (seq && words_out)), GCG_EINVAL, "gcg_host_pack_2bit: bad argument");
+  if (len > 0) { gcg_pack_stream (words_out, seq, (size_t) len); gcg_copy_fence (); }
+  return GCG_OK;
+}
+
 static int launch_pack (gcg_ctx * ctx, const char * d_ascii, uint64_t * d_packed, int64_t nw)
 {
   if (nw <= 0) return GCG_OK;
@@ -997,10 +1004,10 @@ extern "C" int gcg_hits_download (gcg_ctx * ctx, const gcg_hits * h, gcg_hit * d
 // anchors come out in (read,pos) order because chunks are consecutive and copies are placed by
 // running offset.  The ONT multiplicity state accumulates in the table across chunks.
 #define PIPE_SLOTS 5
-#define PIPE_LAG 2          // chunks between a submit and the host looking at its anchor count
+#define PIPE_LAG 2          // most chunks between a submit and the host looking at its anchor count (GCG_SEARCH_LAG, default 1)
 
 struct pipe_slot {
-  char * h_ascii = nullptr, * d_ascii = nullptr;     // cap_words * 32 bytes
+  uint64_t * h_packed = nullptr;                     // pinned, cap_words words: the chunk 2-bit packed by the host gather
   char * h_meta = nullptr, * d_meta = nullptr;       // woff | len | tile_seq of the chunk
   uint64_t * d_packed = nullptr;
   uint32_t * d_mask = nullptr, * d_prefix = nullptr, * d_bsum = nullptr;
@@ -1016,7 +1023,9 @@ struct gcg_pipe {
   size_t meta_cap = 0;
   cudaStream_t up = nullptr, down = nullptr;
   pipe_slot s[PIPE_SLOTS];
-  unsigned long long * h_count = nullptr;            // pinned, one per slot
+  unsigned long long * h_count = nullptr;            // pinned + mapped, one per slot: the scan kernel stores the chunk's anchor
+  unsigned long long * hd_count = nullptr;           // count straight into host memory (device alias of h_count) — a copy of
+                                                     // 8 bytes would queue behind the anchor downloads on the D2H copy engine
   int64_t last_total = 0;                            // anchors of the previous call: sizes the next result buffer
 };
 
@@ -1027,9 +1036,9 @@ void gcg_pipe_free (gcg_ctx * ctx)
   if (p->up) cudaStreamSynchronize (p->up);
   if (p->down) cudaStreamSynchronize (p->down);
   for (pipe_slot & q : p->s) {
-    if (q.h_ascii) cudaFreeHost (q.h_ascii);
+    if (q.h_packed) cudaFreeHost (q.h_packed);
     if (q.h_meta) cudaFreeHost (q.h_meta);
-    cudaFree (q.d_ascii); cudaFree (q.d_meta); cudaFree (q.d_packed); cudaFree (q.d_mask); cudaFree (q.d_prefix);
+    cudaFree (q.d_meta); cudaFree (q.d_packed); cudaFree (q.d_mask); cudaFree (q.d_prefix);
     cudaFree (q.d_bsum); cudaFree (q.d_count); cudaFree (q.d_hits);
     for (cudaEvent_t e : {q.ev_up, q.ev_count, q.ev_emit, q.ev_free}) if (e) cudaEventDestroy (e);
   }
@@ -1053,11 +1062,11 @@ static int pipe_reserve (gcg_ctx * ctx, int64_t cap_words)
   if (p->meta_cap < tiles * 4 + (1 << 20)) p->meta_cap = tiles * 4 + (1 << 20);
   GCG_CUDA (cudaStreamCreateWithFlags (&p->up, cudaStreamNonBlocking));
   GCG_CUDA (cudaStreamCreateWithFlags (&p->down, cudaStreamNonBlocking));
-  GCG_CUDA (cudaHostAlloc (&p->h_count, PIPE_SLOTS * sizeof (unsigned long long), cudaHostAllocDefault));
+  GCG_CUDA (cudaHostAlloc (&p->h_count, PIPE_SLOTS * sizeof (unsigned long long), cudaHostAllocMapped));
+  GCG_CUDA (cudaHostGetDevicePointer (&p->hd_count, p->h_count, 0));
   for (pipe_slot & q : p->s) {
-    GCG_CUDA (cudaHostAlloc (&q.h_ascii, (size_t) cap_words * 32, cudaHostAllocDefault));
+    GCG_CUDA (cudaHostAlloc (&q.h_packed, (size_t) cap_words * 8, cudaHostAllocDefault));
     GCG_CUDA (cudaHostAlloc (&q.h_meta, p->meta_cap, cudaHostAllocDefault));
-    GCG_CUDA (cudaMalloc (&q.d_ascii, (size_t) cap_words * 32));
     GCG_CUDA (cudaMalloc (&q.d_meta, p->meta_cap));
     GCG_CUDA (cudaMalloc (&q.d_packed, (size_t) (cap_words + 2) * 8));
     GCG_CUDA (cudaMalloc (&q.d_mask, (size_t) cap_words * 4));
@@ -1076,7 +1085,7 @@ extern "C" int gcg_warmup (gcg_ctx * ctx)
   GCG_CHECK (ctx, GCG_EINVAL, "gcg_warmup: ctx == NULL");
   GCG_CUDA (cudaSetDevice (ctx->device));
   int rc = gcg_stage_reserve (ctx);
-  if (!rc) rc = pipe_reserve (ctx, ((int64_t) 16 << 20) / 32);
+  if (!rc) rc = pipe_reserve (ctx, ((int64_t) 8 << 20) / 32);
   return rc;
 }
 
@@ -1120,7 +1129,7 @@ extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * re
   *n_hit = 0;
   GCG_CUDA (cudaSetDevice (ctx->device));
   gcg_trace_mark (ctx, nullptr);
-  int64_t chunk_words = ((int64_t) 16 << 20) / 32, max_words = 0, total_kmers = 0;
+  int64_t chunk_words = ((int64_t) 8 << 20) / 32, max_words = 0, total_kmers = 0;
   if (const char * e = getenv ("GCG_SEARCH_CHUNK_BYTES")) chunk_words = std::max<int64_t> (1, atoll (e) / 32);
   for (int64_t r = 0; r < n_read; ++r) {
     GCG_CHECK (read_len[r] >= 0, GCG_ERANGE, "gcg_search: read %lld has a negative length", (long long) r);
@@ -1144,15 +1153,15 @@ extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * re
   struct chunk_desc { int64_t r0 = 0, r1 = 0, nr = 0, nw = 0, kmers = 0, n_tiles = 0; size_t tseq_off = 0; int slot = 0; };
   int inflight[PIPE_SLOTS], n_inflight = 0;       // submitted, not yet downloaded, oldest first
   int64_t c = 0;
-  double t_gather = 0, t_wait = 0;
+  double t_gather = 0, t_wait = 0, t_prepare = 0, t_submit = 0, t_download = 0, t_drain = 0;
   auto now = [] () { return std::chrono::steady_clock::now (); };
   auto ms = [] (std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli> (b - a).count (); };
   gcg_workers * pool = gcg_ctx_workers (ctx);
   std::function<void (int64_t)> gather_fn;
 
   // chunk starting at read r0: whole reads, at most cap_words words, meta within the slot's meta block;
-  // waits for its slot, writes the meta block and starts the gather on the pool
-  auto prepare = [&] (int64_t r0, chunk_desc & d) -> int {
+  // waits for its slot and writes the meta block (host work that overlaps the gather of the chunk before)
+  auto plan = [&] (int64_t r0, chunk_desc & d) -> int {
     int64_t r1 = r0, nw = 0;
     while (r1 < n_read) {
       const int64_t w = ((int64_t) read_len[r1] + 31) >> 5;
@@ -1187,16 +1196,22 @@ extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * re
       while (cur + 1 < nr && woff[cur + 1] <= (tl << 5)) ++cur;
       tseq[tl] = (int32_t) cur;
     }
-    if (d.kmers == 0) return GCG_OK;
+    return GCG_OK;
+  };
+  // starts the gather of a planned chunk on the pool (one job at a time: after the wait for the previous one)
+  auto start_gather = [&] (const chunk_desc & d) {
+    pipe_slot & q = p->s[d.slot];
+    const int64_t nr = d.nr, nw = d.nw, r0 = d.r0;
+    const int64_t * woff = (const int64_t *) q.h_meta;
+    const int32_t * len = (const int32_t *) (q.h_meta + (size_t) (nr + 1) * 8);
     const int64_t n_task = nw * 32 < (1 << 18) ? 1 : std::min<int64_t> (nr, 4 * (int64_t) ctx->host_threads);
-    char * dst = q.h_ascii;
-    gather_fn = [=] (int64_t tk) {
+    uint64_t * dst = q.h_packed;
+    gather_fn = [=] (int64_t tk) {                   // gather + 2-bit pack in one pass over the caller's strings
       for (int64_t i = nr * tk / n_task; i < nr * (tk + 1) / n_task; ++i)
-        if (len[i] > 0) gcg_copy_stream (dst + woff[i] * 32, read_seq[r0 + i], (size_t) len[i]);
+        if (len[i] > 0) gcg_pack_stream (dst + woff[i], read_seq[r0 + i], (size_t) len[i]);
       gcg_copy_fence ();
     };
     gcg_workers_start (pool, n_task, gather_fn);
-    return GCG_OK;
   };
 
   // copy the gathered chunk to the device and enqueue its kernels
@@ -1204,18 +1219,16 @@ extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * re
     pipe_slot & q = p->s[d.slot];
     const int64_t nr = d.nr, nw = d.nw;
     const size_t meta_bytes = d.tseq_off + (size_t) d.n_tiles * 4;
-    GCG_CUDA (cudaMemcpyAsync (q.d_ascii, q.h_ascii, (size_t) nw * 32, cudaMemcpyHostToDevice, p->up));
+    GCG_CUDA (cudaMemcpyAsync (q.d_packed, q.h_packed, (size_t) nw * 8, cudaMemcpyHostToDevice, p->up));
     GCG_CUDA (cudaMemcpyAsync (q.d_meta, q.h_meta, meta_bytes, cudaMemcpyHostToDevice, p->up));
     GCG_CUDA (cudaEventRecord (q.ev_up, p->up));
     GCG_CUDA (cudaStreamWaitEvent (ctx->stream, q.ev_up, 0));
     const int64_t * d_woff = (const int64_t *) q.d_meta;
     const int32_t * d_len = (const int32_t *) (q.d_meta + (size_t) (nr + 1) * 8);
     const int32_t * d_tseq = (const int32_t *) (q.d_meta + d.tseq_off);
-    int e = launch_pack (ctx, q.d_ascii, q.d_packed, nw);
-    if (e) return e;
+    int e;
     launch_k45 (ctx, t, q.d_packed, d_woff, d_len, d_tseq, nr, nw, k, q.d_mask);
-    if ((e = mask_scan_launch (ctx, q.d_mask, nw, q.d_prefix, q.d_bsum, q.d_count)) != 0) return e;
-    GCG_CUDA (cudaMemcpyAsync (p->h_count + d.slot, q.d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((e = mask_scan_launch (ctx, q.d_mask, nw, q.d_prefix, q.d_bsum, p->hd_count + d.slot)) != 0) return e;
     GCG_CUDA (cudaEventRecord (q.ev_count, ctx->stream));
     { gcg_kscope ks (ctx, "hits_emit");
       hits_emit_kernel<<<grid_for (ctx, d.n_tiles * 32, 256, 8), 256, 0, ctx->stream>>> (
@@ -1227,29 +1240,38 @@ extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * re
     return GCG_OK;
   };
 
+  int pipe_lag = 1;                                 // (measured on cfg2: 8 MiB chunks, lag 1: 3.0 ms; 16 MiB, lag 2: 3.35 ms)
+  if (const char * e = getenv ("GCG_SEARCH_LAG")) pipe_lag = std::min (PIPE_LAG, std::max (0, atoi (e)));
   chunk_desc cur_c, next_c;
-  rc = prepare (0, cur_c);
+  rc = plan (0, cur_c);
   bool gathering = !rc && cur_c.kmers > 0;
+  if (gathering) start_gather (cur_c);
   while (!rc) {
+    // the next chunk is planned while this one is gathered, and gathered while this one is copied and probed
+    const bool more = cur_c.r1 < n_read;
+    if (more) {
+      auto t1 = now ();
+      rc = plan (cur_c.r1, next_c);
+      t_prepare += ms (t1, now ());
+    }
     auto t0 = now ();
     if (gathering) gcg_workers_wait (pool);
     t_gather += ms (t0, now ());
     gathering = false;
-    // the next chunk is gathered while this one is copied and probed
-    const bool more = cur_c.r1 < n_read;
-    if (more) {
-      rc = prepare (cur_c.r1, next_c);
-      if (rc) break;
-      gathering = next_c.kmers > 0;
-    }
+    if (rc) break;
+    if (more && next_c.kmers > 0) { start_gather (next_c); gathering = true; }
     if (cur_c.kmers > 0) {
+      auto t1 = now ();
       rc = submit (cur_c);
+      t_submit += ms (t1, now ());
       if (rc) break;
       // place the anchors of the chunk submitted PIPE_LAG chunks ago: its count is there by now, so the
       // host does not stall and the upload stream never runs dry
       inflight[n_inflight++] = cur_c.slot;
-      if (n_inflight > PIPE_LAG) {
+      if (n_inflight > pipe_lag) {
+        auto t2 = now ();
         rc = pipe_download (ctx, p->s[inflight[0]], inflight[0], res);
+        t_download += ms (t2, now ());
         if (rc) break;
         for (int i = 1; i < n_inflight; ++i) inflight[i - 1] = inflight[i];
         --n_inflight;
@@ -1260,14 +1282,17 @@ extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * re
   }
   if (gathering) gcg_workers_wait (pool);
   // ---- drain, oldest first
+  auto t_d0 = now ();
   for (int i = 0; i < n_inflight && !rc; ++i) rc = pipe_download (ctx, p->s[inflight[i]], inflight[i], res);
   if (cudaStreamSynchronize (p->down) != cudaSuccess || cudaStreamSynchronize (ctx->stream) != cudaSuccess) {
     if (!rc) { gcg_set_error ("gcg_search: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; }
   }
+  t_drain = ms (t_d0, now ());
   for (pipe_slot & q : p->s) { q.busy = false; q.pending = false; }
   if (ctx->trace)
-    fprintf (stderr, "[gcg]   search pipeline: %lld chunks, waits for the gather %.3f ms (%d threads), for a free slot %.3f ms\n",
-             (long long) c, t_gather, ctx->host_threads, t_wait);
+    fprintf (stderr, "[gcg]   search pipeline: %lld chunks, waits for the gather %.3f ms (%d threads), for a free slot %.3f ms; "
+             "host: prepare %.3f submit %.3f download %.3f drain %.3f ms\n",
+             (long long) c, t_gather, ctx->host_threads, t_wait, t_prepare, t_submit, t_download, t_drain);
   gcg_trace_mark (ctx, "search: reads -> anchors (pipelined)");
   if (rc) { gcg_free (res.buf); return rc; }
   p->last_total = res.n;

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from superplus_b200 import synth
+from superplus_b200 import api, synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SHIM = os.path.join(ROOT, "superplus_b200", "_build", "libgcshim.so")
@@ -111,3 +111,33 @@ def test_shim_hash_set_semantics():
     missing = C.c_uint64(100000)
     assert not L._xh_set_search3(h, C.addressof(missing))
     assert [h.contents.pool[i].id for i in range(5)] == [0, 1, 2, 3, 4]
+
+
+def test_host_pack_2bit_matches_the_oracle_packing():
+    """gcg_host_pack_2bit (what the search gather does on the host) == (c >> 1) & 3 per base, 32
+    bases per word, first base on top, zero tail — for every tail length, any byte value, and all
+    three code paths (AVX2, PEXT, portable multiply)."""
+    import subprocess, sys
+    rng = np.random.default_rng(3)
+
+    def want(b):
+        a = np.frombuffer(b, dtype=np.uint8)
+        codes = ((a >> 1) & 3).astype(np.uint64)
+        nw = (len(a) + 31) // 32
+        pad = np.zeros(nw * 32, dtype=np.uint64)
+        pad[:len(a)] = codes
+        sh = np.uint64(62) - np.uint64(2) * np.arange(32, dtype=np.uint64)
+        return (pad.reshape(nw, 32) << sh).sum(axis=1, dtype=np.uint64)
+
+    cases = [b"", b"A", b"ACGT", b"ACGTNacgtn" * 7]
+    cases += [bytes(rng.integers(0, 256, n, dtype=np.uint8)) for n in (31, 32, 33, 63, 64, 65, 1000, 4097)]
+    cases += [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), n)) for n in (25, 96, 12345)]
+    for c in cases:
+        assert np.array_equal(api.host_pack_2bit(c), want(c)), len(c)
+    # every path in a fresh process (the choice is made once per process)
+    code = ("import numpy as np, sys; sys.path.insert(0, %r); from superplus_b200 import api; "
+            "b = bytes(range(256)) * 3 + b'ACGTTGCA'; print(','.join(str(int(x)) for x in api.host_pack_2bit(b)))" % ROOT)
+    b = bytes(range(256)) * 3 + b"ACGTTGCA"
+    for path in ("swar", "pext", "avx2"):       # a path the CPU lacks falls back to the default one
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GCG_HOST_PACK=path), capture_output=True, text=True, check=True).stdout
+        assert [int(x) for x in out.strip().split(",")] == [int(x) for x in want(b)], path

@@ -145,6 +145,32 @@ def test_band_and_row_boundaries(ctx, oracle, mode):
     check_batch(ctx, oracle, api.make_sw_params(), qs, ts, mode)
 
 
+@pytest.mark.parametrize("mode", [api.SW_ASIS, api.SW_FIXED])
+def test_packed_pairs_near_the_16_bit_range(ctx, oracle, mode):
+    """Affine borders and queries close to the packed kernel's value range.  Each alignment fits
+    the 16-bit halves on its own, but the band-padded rectangle two of them would share does not
+    (border of column 2048 = -2049): such alignments must not share a warp, because the packed
+    kernel adds both halves with one 32-bit add (a borrow out of the low half would reach the
+    other alignment).  Shorter ones in the same batch still pair up."""
+    rng = np.random.default_rng(77)
+    qs, ts = [], []
+    for ql in (1700, 1790, 1795, 300, 1100, 1279, 1281, 1500, 1793, 40):
+        t = rng.integers(0, 4, 60).astype(np.uint8)
+        q = rng.integers(0, 4, ql).astype(np.uint8)
+        a = int(rng.integers(0, ql - 30))
+        q[a:a + 30] = t[10:40]
+        qs.append(q); ts.append(t)
+    for strategy in (api.LEADING_INDEL, api.INDEL, api.IGNORE):
+        P = api.make_sw_params(strategy=strategy)
+        qb, qo = api._concat(qs)
+        tb, to = api._concat(ts)
+        b = ctx.swbatch_upload_concat(qb, qo, tb, to)
+        b.align(P, mode)
+        assert b.path_counts() == (len(qs), 0)              # all of them on the packed kernel
+        b.free()
+        check_batch(ctx, oracle, P, qs, ts, mode)
+
+
 def test_ties_heavy(ctx, oracle):
     """low-complexity sequences: many equal scores exercise every tie rule"""
     rng = np.random.default_rng(33)
