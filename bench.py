@@ -439,7 +439,11 @@ def run_ours(args, rank, local_rank, world):
                    "k": K, "contigs": len(contigs), "reads_per_gpu": len(reads), "ont_kmers_per_gpu": n_ont_kmers, "contig_kmers": n_ctg_kmers,
                    "anchors_per_gpu": int(n_hit), "stats": list(st), "parallelism": "reads sharded by batch, table replicated (no data-path collective)",
                    "l2": "inputs larger than L2 (138 MB ASCII reads + 106 MB table per step vs 126 MB L2); no explicit flush"},
-        "e2e": {"value": tot_ont_kmers / e2e_kmer_s, "unit": "k-mers/s", "h2d_bytes_per_step": int(read_bytes + ctg_bytes),
+        # reads cross PCIe 2-bit packed by the host gather (8 bytes per 32 bases, every read padded to whole words)
+        # plus 12 bytes of layout per read and 4 per 1024 positions; contigs go up as ASCII
+        "e2e": {"value": tot_ont_kmers / e2e_kmer_s, "unit": "k-mers/s",
+                "h2d_bytes_per_step": int(sum((len(r) + 31) // 32 * 8 for r in reads) + 12 * len(reads) + read_bytes // 256 + ctg_bytes),
+                "host_input_bytes_per_step": int(read_bytes + ctg_bytes),
                 "d2h_bytes_per_step": int(n_hit * 16 + 32), "ms_per_step": e2e_kmer_s * 1e3,
                 "host_threads_per_rank": host_threads, "host_cores": os.cpu_count(),
                 "api": "gcg_table_build + gcg_search (host pointers in, pinned anchors out) + gcg_table_stats"},

@@ -272,6 +272,7 @@ hits_emit_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
 {
   __shared__ uint32_t s_excl[8][33];
   __shared__ uint32_t s_mask[8][32];
+  __shared__ uint64_t s_pk[8][33];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int64_t n_tiles = (n_words + 31) >> 5;
   int64_t wstride = (int64_t) gridDim.x * (blockDim.x >> 5);
@@ -287,7 +288,10 @@ hits_emit_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
     __syncwarp ();
     s_excl[wid][lane] = x - c;
     s_mask[wid][lane] = m;
-    if (lane == 31) s_excl[wid][32] = total;
+    // the tile's 33 packed words, one coalesced load (the anchors below pick theirs from shared memory:
+    // one global round trip less in every anchor's dependent chain)
+    s_pk[wid][lane] = w <= n_words ? __ldg (packed + w) : 0ULL;            // (the array has a slack word at n_words)
+    if (lane == 31) { s_excl[wid][32] = total; s_pk[wid][32] = w + 1 <= n_words ? __ldg (packed + w + 1) : 0ULL; }
     __syncwarp ();
     for (uint32_t h = lane; h < total; h += 32) {
       int lo = 0, hi = 32;                          // s_excl[lo] <= h < s_excl[hi]
@@ -296,13 +300,23 @@ hits_emit_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
       uint32_t mm = s_mask[wid][lo];
       int j = __fns (mm, 0, (int) (h - s_excl[wid][lo]) + 1);
       int64_t ww = (tile << 5) + lo;
+      bool fw;
+      unsigned long long kw, key = key_at (s_pk[wid][lo], s_pk[wid][lo + 1], j, k, &fw);
+      uint32_t hs = kmer_hash32 (key - 1ULL), b = __umulhi (hs, n_bucket);
+      // key bucket and value bucket (one 32-byte sector each) are requested together: the key is almost
+      // always in its home bucket, so the value arrives with the keys instead of one round trip later
+      const bucket4 q = ld_bucket (keys + 4ULL * b), qv = ld_bucket (vals + 4ULL * b);
+      unsigned long long slot, v;
+      const int f = bucket_find (q, key, &kw);
+      if (f >= 0) {
+        slot = 4ULL * b + (unsigned) f;
+        v = f == 0 ? qv.a : f == 1 ? qv.b : f == 2 ? qv.c : qv.d;
+      } else {
+        slot = table_lookup (keys, n_bucket, b, q, key, hs & 3u, &kw);      // walks on to the overflow buckets
+        v = __ldg (vals + slot);                    // slot is valid: the mask bit says the key is present
+      }
       int64_t s = find_seq_from (woff, n_seq, ww, s_hint);
       int32_t p0 = (int32_t) ((ww - __ldg (woff + s)) << 5);
-      bool fw;
-      unsigned long long kw, key = key_at (__ldg (packed + ww), __ldg (packed + ww + 1), j, k, &fw);
-      uint32_t hs = kmer_hash32 (key - 1ULL), b = __umulhi (hs, n_bucket);
-      unsigned long long slot = table_lookup (keys, n_bucket, b, ld_bucket (keys + 4ULL * b), key, hs & 3u, &kw);
-      unsigned long long v = __ldg (vals + slot);   // slot is valid: the mask bit says the key is present
       {
         // ONT-side multiplicity state (ont.c:245): 2 bits per slot, saturating at "twice or more"
         uint32_t sh = (uint32_t) (slot & 15) * 2;
