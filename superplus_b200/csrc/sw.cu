@@ -80,7 +80,7 @@ __device__ __forceinline__ int sw_bcol (int i)   // border score of column 0, ro
 // ---------------------------------------------------------------------------------------------
 // end-cell selection by one warp over the parked last column / last row (sw.c:254-280)
 // ---------------------------------------------------------------------------------------------
-__device__ void sw_pick_end (const int * edges, int qlen, int tlen, int lane, sw_end * out)
+__device__ sw_end sw_pick_end (const int * edges, int qlen, int tlen, int lane, sw_end * out)
 {
   const int * lastcol = edges, * lastrow = edges + tlen;
   // last column: the LAST maximum wins (>=)
@@ -118,7 +118,10 @@ __device__ void sw_pick_end (const int * edges, int qlen, int tlen, int lane, sw
     }
   }
   if (score == INT_MIN) score = sw_brow (bt_q);      // only reachable with tlen == 0: cell (0, bt_q)
-  if (lane == 0) { out->score = score; out->bt_tidx = bt_t; out->bt_qidx = bt_q; out->seg_len = seg; }
+  sw_end e;
+  e.score = score; e.bt_tidx = bt_t; e.bt_qidx = bt_q; e.seg_len = seg;     // the same in every lane
+  if (lane == 0) *out = e;
+  return e;
 }
 
 // degenerate alignments (an empty side): the "last column / last row" are border cells
@@ -222,6 +225,114 @@ sw_fill_generic_kernel (const uint8_t * __restrict__ qry, const uint8_t * __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// K9 traceback -> CIGAR, one thread per alignment (sw.c:282-335, cigar.c:82-125).  The generic fill
+// kernel is followed by sw_cigar_kernel; the packed fill kernel calls sw_emit_cigar itself, item by item.
+// ---------------------------------------------------------------------------------------------
+// COHERENT: the trace was written by this very kernel (the packed fill kernel walks its own items):
+// loads go to the L2 (ld.global.cg), never through the non-coherent path, which may still hold
+// lines of the item that used the trace slot before.
+template <bool COHERENT>
+struct sw_cell_view {
+  const uint32_t * tr;
+  int nsteps;
+  __device__ __forceinline__ uint32_t nib (int i, int j) const   // interior cell, 1-based
+  {
+    int col = j - 1, band = col >> 8, lane = (col & 255) >> 3, c = col & 7;
+    const uint32_t * p = tr + ((size_t) band * nsteps + (i - 1 + lane)) * 32 + lane;
+    uint32_t w = COHERENT ? __ldcg (p) : __ldg (p);
+    return (w >> sw_shift (c)) & 15u;
+  }
+  // status as the CIGAR op the reference would take: 0 = M, 2 = D, 1 = I (the else branch, also for border cells)
+  // len = ml / dl / il of that cell (sw.c:221-249)
+  __device__ void fetch (int i, int j, uint32_t * op, uint32_t * len) const
+  {
+    if (i < 1 || j < 1) { *op = 1; *len = 0; return; }
+    uint32_t n = nib (i, j);
+    if (n & 8u) {                              // M: ml = consecutive M cells up the diagonal
+      uint32_t l = 0;
+      while (i >= 1 && j >= 1 && (nib (i, j) & 8u)) { ++l; --i; --j; }
+      *op = 0; *len = l;
+    } else if (n & 4u) {                       // D: dl = 1 + D-extended flags walking up
+      uint32_t l = 0;
+      while (i >= 1) { ++l; if (!(nib (i, j) & 2u)) break; --i; }
+      *op = 2; *len = l;
+    } else {                                   // I: il = 1 + I-extended flags walking left
+      uint32_t l = 0;
+      while (j >= 1) { ++l; if (!(nib (i, j) & 1u)) break; --j; }
+      *op = 1; *len = l;
+    }
+  }
+};
+
+template <bool WRITE, class VIEW>
+__device__ int sw_walk (const VIEW & cv, int mode, int qlen, int tlen, const sw_end & e,
+                        uint32_t * out, int n_total, int * align_off, int * softclip)
+{
+  int n = 0;
+  auto emit = [&] (uint32_t v) { if (WRITE) out[n_total - 1 - n] = v; ++n; };   // written reversed (cigar_reverse)
+  int bt_t = e.bt_tidx, bt_q = e.bt_qidx;
+  uint32_t seg = (uint32_t) e.seg_len, pre = 0, op = 1, len = 0;
+  const int strategy = c_sw.strategy;
+  *softclip = 0;
+  if (seg > 0 && strategy == GCG_SWOS_SOFTCLIP) { emit ((seg << 4) | 4u); seg = 0; *softclip = 1; }
+  cv.fetch (bt_t, bt_q, &op, &len);
+  bool inited = false;
+  do {
+    if (mode == GCG_SW_FIXED && inited) cv.fetch (bt_t, bt_q, &op, &len);
+    if (op == 0) { bt_t -= (int) len; bt_q -= (int) len; }
+    else if (op == 2) bt_t -= (int) len;
+    else bt_q -= (int) len;
+    if (inited && op != pre) { emit ((seg << 4) | pre); seg = 0; }
+    seg += len;
+    pre = op;
+    inited = true;
+    if (len == 0) break;      // border end cell: an index is already 0, the reference leaves the loop as well
+  } while (bt_t > 0 && bt_q > 0);
+  emit ((seg << 4) | pre);
+  if (strategy == GCG_SWOS_SOFTCLIP) {
+    if (bt_q > 0) emit ((((uint32_t) bt_q) << 4) | 4u);
+    *align_off = bt_t;
+  } else {
+    if (bt_t > 0) emit ((((uint32_t) bt_t) << 4) | 2u);
+    if (bt_q > 0) emit ((((uint32_t) bt_q) << 4) | 1u);
+    *align_off = 0;
+  }
+  return n;
+}
+
+// one alignment: count the CIGAR operations, reserve them in the pool, write them (a reservation that
+// ends beyond pool_cap is left unwritten: the host grows the pool and has the alignment done again)
+template <bool COHERENT>
+__device__ void sw_emit_cigar (const uint32_t * tr, int qlen, int tlen, int pair, const sw_end & e, int mode,
+                               uint32_t * __restrict__ pool, unsigned long long pool_cap,
+                               unsigned long long * __restrict__ cursor, gcg_sw_result * __restrict__ results)
+{
+  sw_cell_view<COHERENT> cv;
+  cv.tr = tr;
+  cv.nsteps = tlen + 31;
+  int off = 0, sc = 0;
+  int n = sw_walk<false> (cv, mode, qlen, tlen, e, nullptr, 0, &off, &sc);
+  unsigned long long at = atomicAdd (cursor, (unsigned long long) n);
+  gcg_sw_result r;
+  r.score = e.score; r.alignment_offset = off; r.has_softclip = sc;
+  r.bt_tidx = e.bt_tidx; r.bt_qidx = e.bt_qidx; r.n_cigar = n; r.cigar_off = (long long) at;
+  results[pair] = r;
+  if (at + (unsigned long long) n <= pool_cap) sw_walk<true> (cv, mode, qlen, tlen, e, pool + at, n, &off, &sc);
+}
+
+__global__ void __launch_bounds__ (128)
+sw_cigar_kernel (const sw_task * __restrict__ tasks, int n_tasks, const uint32_t * __restrict__ trace,
+                 const sw_end * __restrict__ ends, int mode, uint32_t * __restrict__ pool, unsigned long long pool_cap,
+                 unsigned long long * __restrict__ cursor, gcg_sw_result * __restrict__ results)
+{
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_tasks) return;
+  const sw_task tk = tasks[idx];
+  sw_emit_cigar<false> (trace + tk.trace_off, tk.qlen, tk.tlen, tk.pair, ends[tk.pair], mode, pool, pool_cap, cursor, results);
+}
+
+
+// ---------------------------------------------------------------------------------------------
 // K7 packed: two alignments per warp in s16x2 halves.  Shared memory per warp (rows = tmax):
 //   bH[rows], bI[rows]  last column of the previous band (both alignments packed)
 //   tsel[rows]          PRMT selector for the two target symbols of that row
@@ -273,14 +384,20 @@ __device__ __forceinline__ sw_task ld_task (const sw_task * p)
 }
 
 struct sw_packed_consts { uint32_t pk_do, pk_io, pk_de32, pk_ie32, one; };
+struct sw_cigar_args { int mode; uint32_t * pool; unsigned long long pool_cap; unsigned long long * cursor; gcg_sw_result * results; };
 
 template <int MINB>
 __global__ void __launch_bounds__ (32, MINB)
 sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restrict__ tgt,
                        const sw_task * __restrict__ tasks, const int2 * __restrict__ items, int n_items,
-                       int * __restrict__ counter, uint32_t * __restrict__ trace, int * __restrict__ edges,
-                       uint2 * __restrict__ bound, int rows_cap, sw_end * __restrict__ ends, const sw_packed_consts gk)
+                       int * __restrict__ counter, uint32_t * __restrict__ trace_slots, unsigned long long slot_words,
+                       int * __restrict__ edges, uint2 * __restrict__ bound, int rows_cap, sw_end * __restrict__ ends,
+                       const sw_packed_consts gk, const sw_cigar_args cg)
 {
+  // Persistent warps: every warp owns one trace slot (room for its largest item) and pulls items until
+  // the list is empty; it walks the traceback of an item (sw_emit_cigar) right after filling it, so the
+  // slot is free again and a batch of any size runs as ONE launch — no wave boundary at which the
+  // whole GPU drains (measured on cfg3 shapes: the drain of a one-item-per-warp launch costs 14 %).
   // gk: the gap constants and `one` == 1 as kernel arguments: they reach the step loop as uniform-register
   // operands (no LDC per step, no registers), and x * one + y stays an IMAD (FMA pipe).
   // shared: one PRMT selector per target row.  The last column of the previous band (H, I of both
@@ -289,6 +406,7 @@ sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restr
   extern __shared__ unsigned short tsel[];
   const int lane = threadIdx.x;
   uint2 * bnd = bound + (size_t) blockIdx.x * rows_cap;
+  uint32_t * const trace = trace_slots + (size_t) blockIdx.x * slot_words;      // task.trace_off is relative to the slot
 #define cDO gk.pk_do
 #define cIO gk.pk_io
   const uint32_t NEG2 = pack16b (16 * SW_NEG16V);
@@ -478,106 +596,19 @@ sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restr
     }
     __syncwarp ();
     {
+      // end cells (all lanes), then lane 0 walks alignment A and lane 1 alignment B
       const sw_task ta = ld_task (pta), tb = ld_task (ptb);
-      sw_pick_end (edges + ta.edge_off, ta.qlen, ta.tlen, lane, ends + ta.pair);
-      if (has_b) sw_pick_end (edges + tb.edge_off, tb.qlen, tb.tlen, lane, ends + tb.pair);
+      const sw_end ea = sw_pick_end (edges + ta.edge_off, ta.qlen, ta.tlen, lane, ends + ta.pair);
+      sw_end eb = ea;
+      if (has_b) eb = sw_pick_end (edges + tb.edge_off, tb.qlen, tb.tlen, lane, ends + tb.pair);
+      __syncwarp ();                                 // the trace stores of all lanes are visible to the walkers
+      if (lane == 0) sw_emit_cigar<true> (trace + ta.trace_off, ta.qlen, ta.tlen, ta.pair, ea, cg.mode, cg.pool, cg.pool_cap, cg.cursor, cg.results);
+      if (lane == 1 && has_b) sw_emit_cigar<true> (trace + tb.trace_off, tb.qlen, tb.tlen, tb.pair, eb, cg.mode, cg.pool, cg.pool_cap, cg.cursor, cg.results);
     }
-    __syncwarp ();
+    __syncwarp ();                                   // the slot is rewritten by the next item only after the walks
   }
 #undef cDO
 #undef cIO
-}
-
-// ---------------------------------------------------------------------------------------------
-// K9 traceback -> CIGAR, one thread per alignment (sw.c:282-335, cigar.c:82-125)
-// ---------------------------------------------------------------------------------------------
-struct sw_cell_view {
-  const uint32_t * tr;
-  int nsteps;
-  __device__ __forceinline__ uint32_t nib (int i, int j) const   // interior cell, 1-based
-  {
-    int col = j - 1, band = col >> 8, lane = (col & 255) >> 3, c = col & 7;
-    uint32_t w = __ldg (tr + ((size_t) band * nsteps + (i - 1 + lane)) * 32 + lane);
-    return (w >> sw_shift (c)) & 15u;
-  }
-  // status as the CIGAR op the reference would take: 0 = M, 2 = D, 1 = I (the else branch, also for border cells)
-  // len = ml / dl / il of that cell (sw.c:221-249)
-  __device__ void fetch (int i, int j, uint32_t * op, uint32_t * len) const
-  {
-    if (i < 1 || j < 1) { *op = 1; *len = 0; return; }
-    uint32_t n = nib (i, j);
-    if (n & 8u) {                              // M: ml = consecutive M cells up the diagonal
-      uint32_t l = 0;
-      while (i >= 1 && j >= 1 && (nib (i, j) & 8u)) { ++l; --i; --j; }
-      *op = 0; *len = l;
-    } else if (n & 4u) {                       // D: dl = 1 + D-extended flags walking up
-      uint32_t l = 0;
-      while (i >= 1) { ++l; if (!(nib (i, j) & 2u)) break; --i; }
-      *op = 2; *len = l;
-    } else {                                   // I: il = 1 + I-extended flags walking left
-      uint32_t l = 0;
-      while (j >= 1) { ++l; if (!(nib (i, j) & 1u)) break; --j; }
-      *op = 1; *len = l;
-    }
-  }
-};
-
-template <bool WRITE>
-__device__ int sw_walk (const sw_cell_view & cv, int mode, int qlen, int tlen, const sw_end & e,
-                        uint32_t * out, int n_total, int * align_off, int * softclip)
-{
-  int n = 0;
-  auto emit = [&] (uint32_t v) { if (WRITE) out[n_total - 1 - n] = v; ++n; };   // written reversed (cigar_reverse)
-  int bt_t = e.bt_tidx, bt_q = e.bt_qidx;
-  uint32_t seg = (uint32_t) e.seg_len, pre = 0, op = 1, len = 0;
-  const int strategy = c_sw.strategy;
-  *softclip = 0;
-  if (seg > 0 && strategy == GCG_SWOS_SOFTCLIP) { emit ((seg << 4) | 4u); seg = 0; *softclip = 1; }
-  cv.fetch (bt_t, bt_q, &op, &len);
-  bool inited = false;
-  do {
-    if (mode == GCG_SW_FIXED && inited) cv.fetch (bt_t, bt_q, &op, &len);
-    if (op == 0) { bt_t -= (int) len; bt_q -= (int) len; }
-    else if (op == 2) bt_t -= (int) len;
-    else bt_q -= (int) len;
-    if (inited && op != pre) { emit ((seg << 4) | pre); seg = 0; }
-    seg += len;
-    pre = op;
-    inited = true;
-    if (len == 0) break;      // border end cell: an index is already 0, the reference leaves the loop as well
-  } while (bt_t > 0 && bt_q > 0);
-  emit ((seg << 4) | pre);
-  if (strategy == GCG_SWOS_SOFTCLIP) {
-    if (bt_q > 0) emit ((((uint32_t) bt_q) << 4) | 4u);
-    *align_off = bt_t;
-  } else {
-    if (bt_t > 0) emit ((((uint32_t) bt_t) << 4) | 2u);
-    if (bt_q > 0) emit ((((uint32_t) bt_q) << 4) | 1u);
-    *align_off = 0;
-  }
-  return n;
-}
-
-__global__ void __launch_bounds__ (128)
-sw_cigar_kernel (const sw_task * __restrict__ tasks, int n_tasks, const uint32_t * __restrict__ trace,
-                 const sw_end * __restrict__ ends, int mode, uint32_t * __restrict__ pool, unsigned long long pool_cap,
-                 unsigned long long * __restrict__ cursor, gcg_sw_result * __restrict__ results)
-{
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_tasks) return;
-  const sw_task tk = tasks[idx];
-  const sw_end e = ends[tk.pair];
-  sw_cell_view cv;
-  cv.tr = trace + tk.trace_off;
-  cv.nsteps = tk.tlen + 31;
-  int off = 0, sc = 0;
-  int n = sw_walk<false> (cv, mode, tk.qlen, tk.tlen, e, nullptr, 0, &off, &sc);
-  unsigned long long at = atomicAdd (cursor, (unsigned long long) n);
-  gcg_sw_result r;
-  r.score = e.score; r.alignment_offset = off; r.has_softclip = sc;
-  r.bt_tidx = e.bt_tidx; r.bt_qidx = e.bt_qidx; r.n_cigar = n; r.cigar_off = (long long) at;
-  results[tk.pair] = r;
-  if (at + (unsigned long long) n <= pool_cap) sw_walk<true> (cv, mode, tk.qlen, tk.tlen, e, pool + at, n, &off, &sc);
 }
 
 // per-pair maximum symbol (decides whether a pair may use the 4-letter packed kernel)
@@ -604,7 +635,8 @@ sw_maxsym_kernel (const uint8_t * __restrict__ qry, const long long * __restrict
 // resident warps per SM of the packed kernel = its register budget (GCG_SW_OCC: 20 | 24).  Measured on
 // cfg3-shaped waves: 20 warps at 96 registers 62.9 ms; 24 warps at 80 registers (76 bytes spilled) 69.8 ms
 // for the same 2960-warp wave — and a wave that fills 24 warps per SM needs 74 GB of trace.
-typedef void (* sw_packed_fn_t) (const uint8_t *, const uint8_t *, const sw_task *, const int2 *, int, int *, uint32_t *, int *, uint2 *, int, sw_end *, sw_packed_consts);
+typedef void (* sw_packed_fn_t) (const uint8_t *, const uint8_t *, const sw_task *, const int2 *, int, int *, uint32_t *, unsigned long long, int *, uint2 *,
+                                 int, sw_end *, sw_packed_consts, sw_cigar_args);
 static sw_packed_fn_t sw_packed_fn ()
 {
   static int occ = -1;
@@ -895,9 +927,8 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
   GCG_CHECK (2 * max_single <= budget_words || max_single == 0, GCG_ENOMEM, "gcg_swbatch_align: one alignment needs %llu MB of trace, more than the budget",
              (unsigned long long) (max_single * 4 >> 20));
 
-  // wave construction: work units in launch order (packed items first, then generic), cut by budget
+  // work units: packed items (two alignments per warp where they may share one) and generic alignments
   struct unit { int a, b; bool packed; };
-  std::vector<unit> units;
   // Two alignments share a warp only if neither half can leave its 16 bits anywhere in the common
   // (band-padded) rectangle: the packed kernel adds both halves with one 32-bit add, so a borrow out
   // of the low half — harmless garbage past the end of the shorter alignment when the halves were
@@ -909,17 +940,36 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
     sw_bounds (P, qpad, std::max (a.tlen, c.tlen), &lo, &hi);
     return lo >= -2030 && hi <= 2040;
   };
-  for (size_t i = 0; i < packed_ids.size (); ) {
-    if (i + 1 < packed_ids.size () && pair_ok (packed_ids[i], packed_ids[i + 1])) { units.push_back ({packed_ids[i], packed_ids[i + 1], true}); i += 2; }
-    else { units.push_back ({packed_ids[i], -1, true}); i += 1; }
-  }
+  auto pair_up = [&] (const std::vector<int> & ids) {          // ids sorted by (tlen, qlen): neighbours are alike
+    std::vector<unit> u;
+    for (size_t i = 0; i < ids.size (); ) {
+      if (i + 1 < ids.size () && pair_ok (ids[i], ids[i + 1])) { u.push_back ({ids[i], ids[i + 1], true}); i += 2; }
+      else { u.push_back ({ids[i], -1, true}); i += 1; }
+    }
+    return u;
+  };
+  std::vector<unit> punits = pair_up (packed_ids), units;
   for (int id : generic_ids) units.push_back ({id, -1, false});
+  auto unit_words = [&] (const unit & u) { return trace_words (tasks[(size_t) u.a]) + (u.b >= 0 ? trace_words (tasks[(size_t) u.b]) : 0ULL); };
+  // The packed kernel is persistent: every resident warp owns one trace slot that holds its largest item.
+  unsigned long long slot_words = 0, generic_trace = 0;
+  for (auto & u : punits) slot_words = std::max (slot_words, unit_words (u));
+  for (auto & u : units) generic_trace += unit_words (u);
+  int packed_slots = 0, packed_rows_cap = 32;
+  if (!punits.empty ()) {
+    int per_sm = 0;
+    for (int id : packed_ids) packed_rows_cap = std::max (packed_rows_cap, tasks[(size_t) id].tlen);
+    packed_rows_cap = (packed_rows_cap + 31) & ~31;
+    GCG_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, sw_packed_fn (), 32, (size_t) packed_rows_cap * 2));
+    packed_slots = (int) std::min<size_t> (punits.size (), (size_t) ctx->sm_count * std::max (per_sm, 1));
+  }
+  const unsigned long long need_trace = std::max<unsigned long long> (std::max ((unsigned long long) packed_slots * slot_words, generic_trace), 32);
 
   uint32_t * d_trace = nullptr; int * d_edges = nullptr; sw_task * d_tasks = nullptr; int * d_items = nullptr; int * d_counter = nullptr;
   int2 * d_bound = nullptr;
   uint2 * d_pbound = nullptr;
   sw_task * d_wave_tasks = nullptr;
-  unsigned long long trace_cap = std::min (budget_words, std::max<unsigned long long> (total_trace, 32));
+  unsigned long long trace_cap = std::min (budget_words, need_trace);
   int rc = GCG_OK;
   cudaError_t ce;
   // the per-launch work lists are small; allocate for the whole batch once
@@ -930,7 +980,7 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
   // keep the trace buffer of an earlier align on this batch whenever it can hold whole alignments
   // (the memory it occupies is no longer "free", so the budget above shrinks on later calls)
   if (b->s_trace.cap / 4 >= std::max<unsigned long long> (2 * max_single, 32))
-    trace_cap = std::min<unsigned long long> (std::max<unsigned long long> (total_trace, 32), b->s_trace.cap / 4);
+    trace_cap = std::min<unsigned long long> (need_trace, b->s_trace.cap / 4);
   if ((ce = b->s_trace.reserve (ctx, (size_t) trace_cap * 4)) != cudaSuccess ||
       (ce = b->s_edges.reserve (ctx, (size_t) std::max<long long> (total_edges, 1) * 4)) != cudaSuccess ||
       (ce = b->s_tasks.reserve (ctx, (size_t) n * sizeof (sw_task))) != cudaSuccess ||
@@ -951,7 +1001,11 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
   }
   // CIGAR pool: start from a typical size, grow on demand
   if (!rc) {
-    unsigned long long want = std::max<unsigned long long> (1 << 16, (unsigned long long) n * 64);
+    // as-is CIGARs are a handful of operations; a re-fetching traceback of a noisy read changes operation
+    // every few bases.  (A pool that turns out too small costs a second pass over the alignments it failed.)
+    unsigned long long want = (unsigned long long) n * 64;
+    if (mode == GCG_SW_FIXED) for (auto & t : tasks) want += (unsigned long long) std::min (t.qlen, t.tlen) / 2;
+    want = std::max<unsigned long long> (1 << 16, want);
     if (const char * e = getenv ("GCG_SW_POOL_INIT")) { want = (unsigned long long) atoll (e); gcg_dfree (ctx, b->d_pool); b->d_pool = nullptr; b->pool_cap = 0; }
     if (b->pool_cap < want) {
       gcg_dfree (ctx, b->d_pool); b->d_pool = nullptr; b->pool_cap = 0;
@@ -963,13 +1017,64 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
   if (!rc) GCG_CUDA (cudaMemsetAsync (d_cursor, 0, 8, ctx->stream));
   gcg_trace_mark (ctx, "sw.align: scratch");
 
-  // resident warps of the packed kernel (one warp per block)
-  int packed_slots = 0;
-  if (!rc && !packed_ids.empty ()) {
-    int max_t = 32, per_sm = 0;
-    for (int id : packed_ids) max_t = std::max (max_t, tasks[(size_t) id].tlen);
-    GCG_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, sw_packed_fn (), 32, (size_t) ((max_t + 31) & ~31) * 2));
-    packed_slots = ctx->sm_count * std::max (per_sm, 1);
+  // ---- packed items: ONE persistent launch; alignments whose CIGAR did not fit the pool are done again
+  for (int attempt = 0; !rc && !punits.empty (); ++attempt) {
+    const int n_slots = (int) std::max<unsigned long long> (1, std::min<unsigned long long> ((unsigned long long) packed_slots, trace_cap / std::max<unsigned long long> (slot_words, 1)));
+    // largest items first: the launch ends with the short ones
+    std::vector<int2> pitems (punits.size ());
+    for (size_t i = 0; i < punits.size (); ++i) {
+      const unit & u = punits[punits.size () - 1 - i];
+      pitems[i] = make_int2 (u.a, u.b);
+      tasks[(size_t) u.a].trace_off = 0;                                     // relative to the warp's slot
+      if (u.b >= 0) tasks[(size_t) u.b].trace_off = trace_words (tasks[(size_t) u.a]);
+    }
+    const int grid = (int) std::min<size_t> (pitems.size (), (size_t) n_slots);
+    if ((ce = b->s_pbound.reserve (ctx, (size_t) grid * packed_rows_cap * sizeof (uint2))) != cudaSuccess) {
+      gcg_set_error ("gcg_swbatch_align: boundary scratch: %s", cudaGetErrorString (ce)); rc = GCG_ENOMEM; break; }
+    d_pbound = (uint2 *) b->s_pbound.p;
+    GCG_CUDA (cudaMemcpyAsync (d_tasks, tasks.data (), (size_t) n * sizeof (sw_task), cudaMemcpyHostToDevice, ctx->stream));
+    GCG_CUDA (cudaMemcpyAsync (d_items, pitems.data (), pitems.size () * sizeof (int2), cudaMemcpyHostToDevice, ctx->stream));
+    GCG_CUDA (cudaMemsetAsync (d_counter, 0, 2 * sizeof (int), ctx->stream));
+    { gcg_kscope ks (ctx, "k7_sw_fill_packed");
+      sw_packed_fn ()<<<grid, 32, (size_t) packed_rows_cap * 2, ctx->stream>>> (
+          b->d_qry, b->d_tgt, d_tasks, (const int2 *) d_items, (int) pitems.size (), d_counter, d_trace, slot_words, d_edges, d_pbound,
+          packed_rows_cap, b->d_ends, sw_packed_consts {hc.pk_do, hc.pk_io, hc.pk_de32, hc.pk_ie32, 1u},
+          sw_cigar_args {mode, b->d_pool, b->pool_cap, d_cursor, b->d_results});
+      GCG_CUDA (cudaGetLastError ()); }
+    GCG_CUDA (cudaMemcpyAsync (ctx->h_counters + 10, d_cursor, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+    gcg_trace_mark (ctx, "sw.align: packed items done");
+    const unsigned long long cur = ctx->h_counters[10];
+    if (cur <= b->pool_cap) { b->pool_used = cur; break; }
+    if (attempt == 2) { gcg_set_error ("gcg_swbatch_align: cigar pool overflow persists"); rc = GCG_ERANGE; break; }
+    // Reservations are handed out in increasing order, so everything from the first one that ended
+    // beyond the pool is unwritten: grow the pool (now the size is known), rewind the cursor to that
+    // reservation and run those alignments again.
+    std::vector<gcg_sw_result> hres ((size_t) n);
+    GCG_CUDA (cudaMemcpy (hres.data (), b->d_results, (size_t) n * sizeof (gcg_sw_result), cudaMemcpyDeviceToHost));
+    std::vector<int> failed;
+    unsigned long long base = cur;
+    for (int id : packed_ids) {                      // (sorted order is kept: the failed ones pair up as before)
+      const gcg_sw_result & r = hres[(size_t) id];
+      if ((unsigned long long) r.cigar_off + (unsigned long long) r.n_cigar > b->pool_cap) { failed.push_back (id); base = std::min (base, (unsigned long long) r.cigar_off); }
+    }
+    if (attempt > 0) {                               // only the alignments of the previous attempt can have failed
+      std::vector<char> in_prev ((size_t) n, 0);
+      for (auto & u : punits) { in_prev[(size_t) u.a] = 1; if (u.b >= 0) in_prev[(size_t) u.b] = 1; }
+      std::vector<int> f2; base = cur;
+      for (int id : failed) if (in_prev[(size_t) id]) { f2.push_back (id); base = std::min (base, (unsigned long long) hres[(size_t) id].cigar_off); }
+      failed.swap (f2);
+    }
+    const unsigned long long ncap = std::max (b->pool_cap * 2, cur + (cur - base) / 8 + 1024);
+    uint32_t * np = nullptr;
+    if ((ce = gcg_dmalloc (ctx, &np, (size_t) ncap * 4)) != cudaSuccess) { gcg_set_error ("gcg_swbatch_align: cigar pool growth to %llu ops failed: %s", ncap, cudaGetErrorString (ce)); rc = GCG_ENOMEM; break; }
+    if (base) GCG_CUDA (cudaMemcpyAsync (np, b->d_pool, (size_t) base * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->h_counters[10] = base;
+    GCG_CUDA (cudaMemcpyAsync (d_cursor, ctx->h_counters + 10, 8, cudaMemcpyHostToDevice, ctx->stream));
+    GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+    gcg_dfree (ctx, b->d_pool);
+    b->d_pool = np; b->pool_cap = ncap; b->pool_used = base;
+    punits = pair_up (failed);
   }
 
   size_t u0 = 0;
@@ -983,49 +1088,23 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
       used += need;
       ++u1;
     }
-    // A wave that was cut by the trace budget runs as whole rounds of the resident warps: with
-    // equal-cost units (the usual batch) a partial last round would leave most SMs idle.
-    if (u1 < units.size () && units[u0].packed && packed_slots > 0) {
-      size_t np = 0;
-      while (u0 + np < u1 && units[u0 + np].packed) ++np;
-      if (np >= (size_t) packed_slots) u1 = u0 + (np / packed_slots) * packed_slots;
-    }
     // assign trace offsets, build launch lists
-    std::vector<int2> pitems; std::vector<int> gitems; std::vector<sw_task> wave_tasks;
+    std::vector<int> gitems; std::vector<sw_task> wave_tasks;
     unsigned long long off = 0;
-    int rows_cap = 32;
     for (size_t u = u0; u < u1; ++u) {
       for (int id : {units[u].a, units[u].b}) {
         if (id < 0) continue;
         sw_task & t = tasks[(size_t) id];
         t.trace_off = off; off += trace_words (t);
         wave_tasks.push_back (t);
-        if (units[u].packed) rows_cap = std::max (rows_cap, t.tlen);
       }
-      if (units[u].packed) pitems.push_back (make_int2 (units[u].a, units[u].b));
-      else gitems.push_back (units[u].a);
+      gitems.push_back (units[u].a);
     }
-    rows_cap = (rows_cap + 31) & ~31;
     GCG_CUDA (cudaMemcpyAsync (d_tasks, tasks.data (), (size_t) n * sizeof (sw_task), cudaMemcpyHostToDevice, ctx->stream));
     GCG_CUDA (cudaMemcpyAsync (d_wave_tasks, wave_tasks.data (), wave_tasks.size () * sizeof (sw_task), cudaMemcpyHostToDevice, ctx->stream));
     GCG_CUDA (cudaMemsetAsync (d_counter, 0, 2 * sizeof (int), ctx->stream));
-    if (!pitems.empty ()) {
-      GCG_CUDA (cudaMemcpyAsync (d_items, pitems.data (), pitems.size () * sizeof (int2), cudaMemcpyHostToDevice, ctx->stream));
-      size_t smem = (size_t) rows_cap * 2;
-      int per_sm = 0;
-      GCG_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, sw_packed_fn (), 32, smem));
-      if (per_sm < 1) per_sm = 1;
-      int grid = (int) std::min<size_t> (pitems.size (), (size_t) ctx->sm_count * per_sm);
-      if ((ce = b->s_pbound.reserve (ctx, (size_t) ctx->sm_count * per_sm * rows_cap * sizeof (uint2))) != cudaSuccess) {
-        gcg_set_error ("gcg_swbatch_align: boundary scratch: %s", cudaGetErrorString (ce)); rc = GCG_ENOMEM; break; }
-      d_pbound = (uint2 *) b->s_pbound.p;
-      gcg_kscope ks (ctx, "k7_sw_fill_packed");
-      sw_packed_fn ()<<<grid, 32, smem, ctx->stream>>> (b->d_qry, b->d_tgt, d_tasks, (const int2 *) d_items, (int) pitems.size (),
-                                                        d_counter, d_trace, d_edges, d_pbound, rows_cap, b->d_ends, sw_packed_consts {hc.pk_do, hc.pk_io, hc.pk_de32, hc.pk_ie32, 1u});
-      GCG_CUDA (cudaGetLastError ());
-    }
     if (!gitems.empty ()) {
-      int * d_gitems = d_items + 2 * pitems.size ();
+      int * d_gitems = d_items;
       GCG_CUDA (cudaMemcpyAsync (d_gitems, gitems.data (), gitems.size () * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
       int grid = (int) std::min<size_t> ((gitems.size () + 3) / 4, (size_t) gen_blocks);
       gcg_kscope ks (ctx, "k7_sw_fill_generic");
