@@ -28,7 +28,7 @@ for mb in (53, 424, 1600, 8000):
 print("hbm copy %.0f GB/s  int16 %.2f T lane-ops/s" % (c.ubench_hbm() / 1e9, c.ubench_int16() / 1e12))
 PY
 # ---- ncu: launch list of the bench command (shares of the step), then one full capture per kernel
-BCMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --sw-pairs 5920"
+BCMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --sw-pairs 11840"
 $BCMD > $O/plain_bench.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv $BCMD > $O/ncu_bench.log 2>&1
 echo "ncu launches rc=$?"
@@ -36,6 +36,8 @@ KCMD="python scripts/perf_kmer.py cfg2 25 3"
 $KCMD > $O/plain_kmer.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:k45_search -s 2 -c 1 -o $O/prof_k45_$TAG -f $KCMD > $O/ncu_k45.log 2>&1
 echo "ncu k45 rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:hits_emit -s 2 -c 1 -o $O/prof_emit_$TAG -f $KCMD > $O/ncu_emit.log 2>&1
+echo "ncu emit rc=$?"
 SCMD="python scripts/perf_sw.py 5920 0 1"
 $SCMD > $O/plain_sw.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:sw_fill_packed -c 1 -o $O/prof_sw_packed_$TAG -f $SCMD > $O/ncu_sw.log 2>&1
