@@ -431,6 +431,10 @@ def run_ours(args, rank, local_rank, world):
     fill = sprof.get("k7_sw_fill_packed", (0.0, 1))
     fill_gcups = sw_cells / (fill[0] / args.steps * 1e-3) / 1e9 if fill[0] > 0 else 0.0
     sw_peak = r_int16 * 2.0 / OPS_PER_CELL / 1e9          # 16-bit results per second / 12 ops per cell
+    # DRAM bytes of one fill launch: the ncu capture is one launch over a known number of cfg3 pairs
+    sw_traffic, cap_pairs = ncu_traffic("sw_fill_packed_kernel"), ncu_traffic("sw_fill_packed_kernel_pairs")
+    if sw_traffic is not None and cap_pairs:
+        sw_traffic = sw_traffic / cap_pairs * sw_pairs
 
     line = {
         "metric": "kmers_per_s", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -461,7 +465,7 @@ def run_ours(args, rank, local_rank, world):
                "e2e": {"value": tot_e2e_cells / e2e_sw_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(sw_e2e_pairs * (SW_QLEN + SW_TLEN)),
                        "d2h_bytes_per_step": int(sw_e2e_pairs * 32 + n_ops * 4), "pairs_per_step": int(sw_e2e_pairs), "api": "gcg_sw_batch (host buffers)"},
                "roofline": {"bound": "int_alu", "kernel": "sw_fill_packed_kernel", "achieved": fill_gcups, "peak": sw_peak, "unit": "GCUPS",
-                            "frac": fill_gcups / sw_peak if sw_peak else None, "traffic": ncu_traffic("sw_fill_packed_kernel"),
+                            "frac": fill_gcups / sw_peak if sw_peak else None, "traffic": sw_traffic,
                             "peak_source": "measured in this run: VIADDMNMX.S16x2 issue rate %.2f T lane-ops/s x 2 halves / 12 integer ops per cell (SURVEY 8d)" % (r_int16 / 1e12),
                             "secondary": {"bound": "hbm", "achieved": 0.5 * sw_cells / (fill[0] / args.steps * 1e-3) / 1e9 if fill[0] > 0 else 0.0,
                                           "peak": peak_gbs, "unit": "GB/s", "note": "trace spill, 0.5 byte per cell"},

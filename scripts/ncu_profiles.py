@@ -6,6 +6,7 @@ that bench.py reports as roofline.traffic).
 usage: python scripts/ncu_profiles.py <tag> [round-label]     e.g.  r01b r01
 """
 import collections
+import re
 import csv
 import io
 import json
@@ -115,6 +116,9 @@ def launch_list(path, fh):
     fh.write("\n")
 
 
+SW_CAPTURE_PAIRS = 5920
+
+
 def main():
     tag = sys.argv[1]
     label = sys.argv[2] if len(sys.argv) > 2 else tag
@@ -122,7 +126,7 @@ def main():
     traffic = {}
     tpath = os.path.join(PROF, "roofline_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath))
+        traffic = {k: v for k, v in json.load(open(tpath)).items() if "<" not in k}
     with open(os.path.join(PROF, "%s_ncu_summary.txt" % label), "w") as fh:
         fh.write("ncu evidence of round %s (captures tagged %s); regenerate with scripts/ncu_profiles.py\n\n" % (label, tag))
         ll = os.path.join(OUT, "launches_%s.csv" % tag)
@@ -132,7 +136,13 @@ def main():
             if f.endswith("_%s.ncu-rep" % tag):
                 rep = os.path.join(OUT, f)
                 t = sheet(rep, f[: -len(".ncu-rep")], fh)
-                traffic.update(t)
+                # plain kernel names ("void k<0>(...)" -> "k"); the SW capture is one launch over
+                # SW_CAPTURE_PAIRS pairs (gpu_round.sh), bench.py scales it to the pairs of its own launch
+                for name, v in t.items():
+                    name = re.sub(r"<.*", "", name.replace("void ", "")).strip()
+                    traffic[name] = v
+                    if name == "sw_fill_packed_kernel":
+                        traffic["sw_fill_packed_kernel_pairs"] = SW_CAPTURE_PAIRS
                 sass_summary(rep, fh)
     json.dump(traffic, open(tpath, "w"), indent=1, sort_keys=True)
     print(open(os.path.join(PROF, "%s_ncu_summary.txt" % label)).read())
