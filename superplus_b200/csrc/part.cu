@@ -155,6 +155,62 @@ __device__ __forceinline__ void lane_cursors (uint32_t (* cnt)[32], const uint32
   }
 }
 
+// ---- pre-filtered tiles: the survivors dealt over the lanes ------------------------------------------
+// With the pre-filter a few percent of a tile's 1024 positions are routed, unevenly spread over the
+// words: a loop "every lane walks the set bits of its own word" runs as long as the fullest word while
+// most lanes idle (ncu: 8 of 32 lanes active).  Instead the warp lists the survivors of the tile in
+// position order in shared memory and deals them out 32 per round.  The place of a k-mer inside its
+// owner's segment is still "its rank among the tile's k-mers of that owner, in position order": lanes
+// of a round that hold the same owner find each other with __match_any_sync, and a running count per
+// owner carries over the rounds — the same layout the per-lane cursors produce, so the owner side and
+// the unfiltered path are untouched.
+struct sparse_tile {                     // one per warp, shared memory
+  uint64_t pk[33];                       // the tile's packed words (+ the one after)
+  unsigned short list[1024];             // (word in tile) << 5 | position in word, in position order
+  uint32_t run[GCG_MAX_PART];            // k-mers of owner d handed out so far
+  uint32_t m[32];                        // collect: anchor mask per word
+};
+
+// returns the number of survivors of the tile (the same in every lane)
+__device__ __forceinline__ uint32_t sparse_build (sparse_tile & st, const uint64_t * __restrict__ packed, int64_t w, int64_t n_words,
+                                                  int nvalid, uint32_t pass, uint32_t n_part, int lane)
+{
+  const uint32_t m = nvalid >= 32 ? pass : (nvalid > 0 ? (pass & ((1u << nvalid) - 1u)) : 0u);
+  const uint32_t c = __popc (m);
+  uint32_t x = c;
+  for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (0xffffffffu, x, o); if (lane >= o) x += y; }
+  const uint32_t total = __shfl_sync (0xffffffffu, x, 31);
+  __syncwarp ();                                    // the previous tile's rounds are done with the arrays
+  if (total == 0) return 0;
+  st.pk[lane] = w <= n_words ? __ldg (packed + w) : 0ULL;           // (index n_words is the array's slack word)
+  if (lane == 31) st.pk[32] = w + 1 <= n_words ? __ldg (packed + w + 1) : 0ULL;
+  if ((uint32_t) lane < n_part) st.run[lane] = 0;
+  st.m[lane] = 0;
+  uint32_t at = x - c, mm = m;
+  while (mm) { const int j = __ffs ((int) mm) - 1; mm &= mm - 1u; st.list[at++] = (unsigned short) ((lane << 5) | j); }
+  __syncwarp ();
+  return total;
+}
+
+// survivor h of the tile: its word, position, canonical key and strand
+__device__ __forceinline__ void sparse_item (const sparse_tile & st, uint32_t h, int k, int * wl, int * j, unsigned long long * key, bool * fw)
+{
+  const uint32_t code = st.list[h];
+  *wl = (int) (code >> 5); *j = (int) (code & 31u);
+  *key = key_at (st.pk[*wl], st.pk[*wl + 1], *j, k, fw) - 1ULL;
+}
+
+// rank of this lane's k-mer inside owner d's segment part of the tile; every lane of `active` calls it
+__device__ __forceinline__ uint32_t sparse_rank (sparse_tile & st, uint32_t active, uint32_t d, int lane)
+{
+  const uint32_t peers = __match_any_sync (active, d);
+  const uint32_t r = st.run[d] + __popc (peers & ((1u << lane) - 1u));
+  __syncwarp (active);
+  if (lane == __ffs ((int) peers) - 1) st.run[d] += __popc (peers);
+  __syncwarp (active);
+  return r;
+}
+
 __global__ void __launch_bounds__ (32 * RT_WARPS)
 route_count_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff, const int32_t * __restrict__ len,
                     const int32_t * __restrict__ tile_seq, int64_t n_seq, int64_t n_words, int k, uint32_t n_part,
@@ -173,6 +229,8 @@ route_count_kernel (const uint64_t * __restrict__ packed, const int64_t * __rest
       pass = lane_filter_mask (packed, w, nvalid, k, filter, filter_words, filter_k3);
       if (w < n_words) pass_out[(t << 5) + lane] = pass;
     }
+    // (the survivors are counted by the lane that owns their word: next to the filter pass of this
+    // kernel the uneven loop costs nothing, dealing them out through shared memory cost 0.5 ms)
     lane_counts (packed, w, nvalid, k, n_part, s_cnt[wid], lane, pass, filter != nullptr);
     for (uint32_t d = 0; d < n_part; ++d) {
       uint32_t tot = __reduce_add_sync (0xffffffffu, s_cnt[wid][d][lane]);
@@ -243,6 +301,7 @@ route_keys_kernel (const uint64_t * __restrict__ packed, const int64_t * __restr
   __shared__ uint32_t s_run[RS_WARPS][GCG_MAX_PART + 1];
   __shared__ unsigned long long * s_glob[RS_WARPS][GCG_MAX_PART];
   __shared__ unsigned long long * s_base[GCG_MAX_PART];
+  static_assert (sizeof (sparse_tile) <= sizeof (unsigned long long) * 1024, "the sparse tile lives in the warp's stage");
   if (threadIdx.x < n_part) s_base[threadIdx.x] = dst.base[threadIdx.x];
   __syncthreads ();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -253,9 +312,25 @@ route_keys_kernel (const uint64_t * __restrict__ packed, const int64_t * __restr
     const int nvalid = word_valid (woff, len, tile_seq, n_seq, n_words, tile, w, k, &s, &p0);
     __syncwarp ();                                    // the previous tile's copy-out has finished reading the stage
     const uint32_t pass = (pass_in != nullptr && w < n_words) ? __ldg (pass_in + (t << 5) + lane) : 0xffffffffu;
-    lane_counts (packed, w, nvalid, k, n_part, s_cnt[wid], lane, pass, pass_in != nullptr);
+    if (pass_in != nullptr) {
+      // pre-filtered: the few survivors go straight to their owners' segments, 32 per round; the lanes of
+      // a round that share an owner write one contiguous run (the stage is not needed: it holds the list)
+      sparse_tile & st = * reinterpret_cast<sparse_tile *> (s_stage[wid]);
+      const uint32_t total = sparse_build (st, packed, w, n_words, nvalid, pass, n_part, lane);
+      for (uint32_t h0 = 0; h0 < total; h0 += 32) {
+        const uint32_t h = h0 + lane, active = __ballot_sync (0xffffffffu, h < total);
+        if (h < total) {
+          int wl, j; unsigned long long key; bool fw;
+          sparse_item (st, h, k, &wl, &j, &key, &fw);
+          const uint32_t d = kmer_owner (key, n_part), r = sparse_rank (st, active, d, lane);
+          s_base[d][__ldg (off + (int64_t) d * n_tiles + t) + r] = key + 1ULL;
+        }
+      }
+      continue;
+    }
+    lane_counts (packed, w, nvalid, k, n_part, s_cnt[wid], lane, pass, false);
     tile_layout (s_cnt[wid], s_run[wid], s_glob[wid], s_base, off, n_tiles, t, n_part, lane);
-    for_each_routed (packed, w, nvalid, k, pass, pass_in != nullptr, [&] (int, unsigned long long key, bool) {
+    for_each_routed (packed, w, nvalid, k, pass, false, [&] (int, unsigned long long key, bool) {
       s_stage[wid][s_cnt[wid][kmer_owner (key, n_part)][lane]++] = key + 1ULL;
     });
     __syncwarp ();
@@ -320,6 +395,7 @@ route_collect_kernel (const uint64_t * __restrict__ packed, const int64_t * __re
 {
   __shared__ uint32_t s_cnt[RT_WARPS][GCG_MAX_PART][32];
   __shared__ int64_t s_seg[GCG_MAX_PART];
+  __shared__ sparse_tile s_sp[RT_WARPS];
   if (threadIdx.x < n_part) s_seg[threadIdx.x] = seg[threadIdx.x];
   __syncthreads ();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -334,11 +410,48 @@ route_collect_kernel (const uint64_t * __restrict__ packed, const int64_t * __re
       if (!__any_sync (0xffffffffu, m != 0u)) continue;
     }
     const uint32_t pass = (pass_in != nullptr && w < n_words) ? __ldg (pass_in + wl) : 0xffffffffu;
-    lane_counts (packed, w, nvalid, k, n_part, s_cnt[wid], lane, pass, pass_in != nullptr);
+    if (pass_in != nullptr) {
+      // pre-filtered: answers of the survivors, 32 per round (same ranks as route_keys_kernel)
+      sparse_tile & st = s_sp[wid];
+      const uint32_t total = sparse_build (st, packed, w, n_words, nvalid, pass, n_part, lane);
+      uint32_t n_before = 0;                          // anchors of the tile found in earlier rounds
+      const uint32_t tile_at = EMIT && total ? __ldg (prefix + (t << 5)) : 0u;
+      const int64_t s0 = __shfl_sync (0xffffffffu, s, 0);      // (lanes past the last word hold no sequence)
+      for (uint32_t h0 = 0; h0 < total; h0 += 32) {
+        const uint32_t h = h0 + lane, active = __ballot_sync (0xffffffffu, h < total);
+        bool hit = false;
+        int wl2 = 0, j = 0; unsigned long long key = 0, v = 0; bool fw = false;
+        if (h < total) {
+          sparse_item (st, h, k, &wl2, &j, &key, &fw);
+          const uint32_t d = kmer_owner (key, n_part), r = sparse_rank (st, active, d, lane);
+          v = __ldg (ans + s_seg[d] + __ldg (off + (int64_t) d * n_tiles + t) + r);
+          hit = v != GCG_ANS_MISS;
+          if (!EMIT && hit) atomicOr (&st.m[wl2], 1u << j);
+        }
+        if (EMIT) {
+          const uint32_t hb = __ballot_sync (0xffffffffu, hit);
+          if (hit) {
+            // sequence and first position of word wl2 of the tile: recomputed from the word index
+            const int64_t ww = (tile << 5) + wl2;
+            const int64_t sq = find_seq_from (woff, n_seq, ww, s0 >= 0 ? s0 : 0);
+            int4 hh;                                  // gcg_hit {read, pos, tid, cpos_flags}
+            hh.x = (int32_t) sq;
+            hh.y = (int32_t) ((ww - __ldg (woff + sq)) << 5) + j;
+            hh.z = (int32_t) ((v >> 32) & 0x7FFFFFFFu);
+            hh.w = (int32_t) ((((uint32_t) (v >> 1) & 0x3FFFFFFFu) << 2) | (uint32_t) (v & 1ULL) | (fw ? 0u : 2u));
+            reinterpret_cast<int4 *> (hits)[tile_at + n_before + __popc (hb & ((1u << lane) - 1u))] = hh;
+          }
+          n_before += __popc (hb);
+        }
+      }
+      if (!EMIT) { __syncwarp (); if (w < n_words) mask[wl] = total ? st.m[lane] : 0u; }
+      continue;
+    }
+    lane_counts (packed, w, nvalid, k, n_part, s_cnt[wid], lane, pass, false);
     lane_cursors (s_cnt[wid], off, n_tiles, t, n_part, lane);
     uint32_t m = 0;
     uint32_t at_hit = (EMIT && nvalid) ? __ldg (prefix + wl) : 0u;
-    for_each_routed (packed, w, nvalid, k, pass, pass_in != nullptr, [&] (int j, unsigned long long key, bool fw) {
+    for_each_routed (packed, w, nvalid, k, pass, false, [&] (int j, unsigned long long key, bool fw) {
       const uint32_t d = kmer_owner (key, n_part);
       const unsigned long long v = __ldg (ans + s_seg[d] + s_cnt[wid][d][lane]++);
       if (v == GCG_ANS_MISS) return;
