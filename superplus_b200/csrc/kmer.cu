@@ -83,16 +83,22 @@ k23_build_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
 // 32-bit filter word is tested first and the bucket is only loaded when all of the key's bits are
 // set.  The filter holds the keys that are present exactly once, i.e. the only ones that anchor, so
 // with 96 % of ONT k-mers absent (sequencing errors) most probes never leave the L2.
-template <bool FILTER>
+// KC: k as a compile-time constant (25, the gc CLI's; 31, configs[3]) so that the rolling masks and
+// shifts are immediates; 0 = any k at run time.
+// (32 registers, 8 blocks per SM.  The kernel sits at 85 % of the L1 wavefront rate: a random 32-byte
+// bucket load is one wavefront per lane, 138 M of them at one per clock and SM are 0.47 ms at cfg2.
+// Asking for fewer, fatter blocks to keep four loads in flight per thread measured slower, 0.60 ms.)
+template <bool FILTER, int KC>
 __global__ void __launch_bounds__ (32 * K4_WARPS)
 k45_search_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff,
-                   const int32_t * __restrict__ len, const int32_t * __restrict__ tile_seq, int64_t n_seq, int64_t n_words, int k,
+                   const int32_t * __restrict__ len, const int32_t * __restrict__ tile_seq, int64_t n_seq, int64_t n_words, const int k_arg,
                    const unsigned long long * __restrict__ keys, uint32_t n_bucket, uint32_t * __restrict__ hitmask,
                    const uint32_t * __restrict__ filter, uint32_t filter_words, int filter_k3)
 {
   __shared__ uint32_t s_excl[K4_WARPS][33];
   __shared__ uint32_t s_pend[K4_WARPS][32];
   __shared__ uint32_t s_add[K4_WARPS][32];
+  const int k = KC > 0 ? KC : k_arg;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t n_tiles = (n_words + 31) >> 5;
   const int64_t wstride = (int64_t) gridDim.x * K4_WARPS;
@@ -140,15 +146,19 @@ k45_search_kernel (const uint64_t * __restrict__ packed, const int64_t * __restr
             q[u] = ld_bucket (keys + 4ULL * __umulhi (h, n_bucket));
           }
         }
+        // four result bits per group at constant positions, one variable shift per group; positions
+        // past the end of the read are cleared once per word
+        uint32_t hb = 0, ob = 0;
 #pragma unroll
         for (int u = 0; u < K4_UNROLL; ++u) {
-          const bool valid = j0 + u < nvalid;
-          const bool hit = bucket_has_unique (q[u], key[u]);        // multi == 1  (ont.c:171,195)
-          const bool more = !hit && bucket_ovf (q[u], fp[u]);
-          mymask |= (uint32_t) (valid && hit) << (j0 + u);
-          pend |= (uint32_t) (valid && more) << (j0 + u);
+          hb |= bucket_has_unique (q[u], key[u]) ? (1u << u) : 0u;   // multi == 1  (ont.c:171,195)
+          ob |= bucket_ovf_bit (q[u], fp[u], u);
         }
+        mymask |= hb << j0;
+        pend |= (ob & ~hb) << j0;
       }
+      const uint32_t vmask = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+      mymask &= vmask; pend &= vmask;
     }
     // ---- the rare probes that have to look at later buckets, dealt round-robin over the lanes
     uint32_t c = __popc (pend), x = c;
@@ -891,12 +901,11 @@ static void launch_k45 (gcg_ctx * ctx, const gcg_table * t, const uint64_t * d_p
 {
   gcg_kscope ks (ctx, "k45_search");
   const int grid = grid_for (ctx, ((n_words + 31) >> 5) * 32, 32 * K4_WARPS, 8);
-  if (t->filter_valid && t->filter_words)
-    k45_search_kernel<true><<<grid, 32 * K4_WARPS, 0, ctx->stream>>> (d_packed, d_woff, d_len, d_tseq, n_seq, n_words, k, t->d_keys, t->n_bucket, d_mask,
-                                                                       t->d_filter, t->filter_words, t->filter_k3);
-  else
-    k45_search_kernel<false><<<grid, 32 * K4_WARPS, 0, ctx->stream>>> (d_packed, d_woff, d_len, d_tseq, n_seq, n_words, k, t->d_keys, t->n_bucket, d_mask,
-                                                                        nullptr, 0, 0);
+  const bool flt = t->filter_valid && t->filter_words;
+  auto fn = flt ? (k == 25 ? k45_search_kernel<true, 25> : k == 31 ? k45_search_kernel<true, 31> : k45_search_kernel<true, 0>)
+                : (k == 25 ? k45_search_kernel<false, 25> : k == 31 ? k45_search_kernel<false, 31> : k45_search_kernel<false, 0>);
+  fn<<<grid, 32 * K4_WARPS, 0, ctx->stream>>> (d_packed, d_woff, d_len, d_tseq, n_seq, n_words, k, t->d_keys, t->n_bucket, d_mask,
+                                              flt ? t->d_filter : nullptr, flt ? t->filter_words : 0u, flt ? t->filter_k3 : 0);
 }
 
 // ---- search -----------------------------------------------------------------------------------

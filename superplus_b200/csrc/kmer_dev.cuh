@@ -128,6 +128,16 @@ __device__ __forceinline__ bool bucket_ovf (const bucket4 & q, uint32_t fp)
   return (h & 0x40000000u) != 0;
 }
 
+// the same test as a bit at position u (u < 7, a compile-time constant in the search loop), without
+// branches: the top bytes of the four slots side by side, bit 6 of byte fp is the mark
+__device__ __forceinline__ uint32_t bucket_ovf_bit (const bucket4 & q, uint32_t fp, int u)
+{
+  const uint32_t t01 = __byte_perm ((uint32_t) (q.a >> 32), (uint32_t) (q.b >> 32), 0x0073);
+  const uint32_t t23 = __byte_perm ((uint32_t) (q.c >> 32), (uint32_t) (q.d >> 32), 0x0073);
+  const uint32_t w = __byte_perm (t01, t23, 0x5410);
+  return (w >> (fp * 8u + (uint32_t) (6 - u))) & (1u << u);
+}
+
 // key present with multiplicity 1 in this bucket (key has bits 62/63 clear, so one compare does both)
 __device__ __forceinline__ bool bucket_has_unique (const bucket4 & q, unsigned long long key)
 {
