@@ -185,6 +185,9 @@ CONFIGS = {
     "cfg5": dict(genome_len=250_000_000, n_gaps=20_000, coverage=20.0, seed=45),
     # cfg4 with a tenth of the reads: the 100 Mb table (HBM resident, 1.6 GB of keys) on one GPU
     "cfg4s": dict(genome_len=100_000_000, n_gaps=0, coverage=4.0, seed=44),
+    # cfg5's gap density (80 per Mb) at 20 Mb / 6x: a table beyond the L2 (320 MB of keys: the pre-filter
+    # path) and a read set of many pipeline chunks, small enough for the reference to make its fixture
+    "cfg5s": dict(genome_len=20_000_000, n_gaps=1_600, coverage=6.0, seed=45),
     # small cases for unit tests
     "tiny": dict(genome_len=60_000, n_gaps=4, coverage=8.0, seed=7),
     "small": dict(genome_len=200_000, n_gaps=10, coverage=10.0, seed=11),

@@ -41,10 +41,10 @@ def kmer_fixture(tmp, cfg, k):
     print("kmer", cfg, k, info["n_hits"], "anchors")
 
 
-def gc_fixture(tmp, cfg):
+def gc_fixture(tmp, cfg, nts=(1, 4)):
     fa, fq, _ = synth.materialise(cfg, tmp)
     res = {}
-    for nt in (1, 4):
+    for nt in nts:
         wd = os.path.join(tmp, "gc_%s_%d" % (cfg, nt))
         out = orc.run_ref_gc(fa, fq, wd, n_thread=nt)
         stat = [int(x) for x in re.findall(r"(?:total|unique) kmer count: (\d+)", out)]
@@ -119,6 +119,14 @@ def sw_fixture():
 
 def main():
     assert orc.have_ref(), "build oracle/_ref first (bash oracle/build_ref.sh)"
+    if len(sys.argv) > 2 and sys.argv[1] == "--gc":        # add / refresh the CLI fixtures of the named configs only
+        path = os.path.join(OUT, "gc_e2e.json")
+        gc = json.load(open(path))
+        with tempfile.TemporaryDirectory() as tmp:
+            for cfg in sys.argv[2:]:
+                gc[cfg] = gc_fixture(tmp, cfg, nts=(3, 8))
+        json.dump(gc, open(path, "w"), indent=1)
+        return
     with tempfile.TemporaryDirectory() as tmp:
         for cfg, k in (("tiny", 25), ("repeats", 25), ("repeats", 17), ("tiny", 31)):
             kmer_fixture(tmp, cfg, k)

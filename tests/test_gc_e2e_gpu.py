@@ -24,8 +24,10 @@ def md5(path):
     return hashlib.md5(open(path, "rb").read()).hexdigest()
 
 
-@pytest.mark.parametrize("cfg,n_thread", [("tiny", 1), ("small", 4), ("repeats", 3), ("cfg1", 8)])
+@pytest.mark.parametrize("cfg,n_thread", [("tiny", 1), ("small", 4), ("repeats", 3), ("cfg1", 8), ("cfg5s", 8)])
 def test_gap_filled_fasta_is_bit_exact(cfg, n_thread):
+    # cfg5s: cfg5's gap density at 20 Mb / 6x — the contig table is beyond the L2 (pre-filter path) and
+    # the reads go through the host pipeline in 15 chunks
     assert os.path.exists(GC), "gc_b200 was not built (python -c 'import __graft_entry__ as g; g.build()')"
     with tempfile.TemporaryDirectory() as tmp:
         fa, fq, _ = synth.materialise(cfg, tmp)
