@@ -992,9 +992,9 @@ extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * r
         hits_emit_kernel<<<grid_for (ctx, ((n_words + 31) >> 5) * 32, 256, 8), 256, 0, ctx->stream>>> (
             reads->d_packed, reads->d_woff, reads->d_tseq, reads->n, n_words, k, t->d_keys, t->d_vals, t->d_ont, t->n_bucket, d_mask, d_prefix, 0, h->d_hits); }
       gcg_trace_mark (ctx, "  search_seqs: hits alloc");
-      if (cudaGetLastError () != cudaSuccess || cudaStreamSynchronize (ctx->stream) != cudaSuccess) {
-        gcg_set_error ("gcg_search: emit failed: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; }
-      gcg_trace_mark (ctx, "  search_seqs: emit");
+      // no wait for the emit kernel: the anchors stay on the device and everything that reads them
+      // (download, statistics, the next search) is ordered behind it on the context's stream
+      if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_search: emit launch failed"); rc = GCG_ECUDA; }
     }
     break;
   }
