@@ -140,7 +140,7 @@ struct gcg_table {
   uint64_t n_slot = 0;
   unsigned long long * d_keys = nullptr;
   unsigned long long * d_vals = nullptr;
-  uint32_t * d_ont = nullptr;
+
   int64_t n_inserted = 0;                  // k-mer occurrences inserted
   // Pre-filter for tables beyond the L2 (see table_filter_ensure in kmer.cu): one 32-bit word per
   // probe, 2 or 3 bits per key, holding only the keys that can anchor (present exactly once).
@@ -159,6 +159,11 @@ struct gcg_hits {
 #define GCG_KEY_MASK 0x3FFFFFFFFFFFFFFFULL
 #define GCG_KEY_OVF  0x4000000000000000ULL
 #define GCG_KEY_MULTI 0x8000000000000000ULL
+// value word: contig index << 32 | position << 1 | KMER_REV; contigs hold at most 2^30 bases and there
+// are fewer than 2^31 of them, so bits 31 and 63 are free: they carry the ONT-side multiplicity of
+// ont.c:245 (anchored at least once / more than once), set by the kernels that emit anchors
+#define GCG_VAL_ONT1 0x0000000080000000ULL
+#define GCG_VAL_ONT2 0x8000000000000000ULL
 
 int gcg_stage_reserve (gcg_ctx * ctx);
 gcg_workers * gcg_ctx_workers (gcg_ctx * ctx);   // created on first use with ctx->host_threads threads

@@ -276,7 +276,7 @@ scan_apply_kernel (const uint32_t * __restrict__ mask, int64_t n, const uint32_t
 __global__ void __launch_bounds__ (256)
 hits_emit_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff, const int32_t * __restrict__ tile_seq,
                   int64_t n_seq, int64_t n_words, int k, const unsigned long long * __restrict__ keys,
-                  const unsigned long long * __restrict__ vals, uint32_t * __restrict__ ont, uint32_t n_bucket,
+                  unsigned long long * __restrict__ vals, uint32_t n_bucket,
                   const uint32_t * __restrict__ mask, const uint32_t * __restrict__ prefix, int32_t read_base,
                   gcg_hit * __restrict__ out)
 {
@@ -313,26 +313,17 @@ hits_emit_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
       bool fw;
       unsigned long long kw, key = key_at (s_pk[wid][lo], s_pk[wid][lo + 1], j, k, &fw);
       uint32_t hs = kmer_hash32 (key - 1ULL), b = __umulhi (hs, n_bucket);
-      // key bucket and value bucket (one 32-byte sector each) are requested together: the key is almost
-      // always in its home bucket, so the value arrives with the keys instead of one round trip later
-      const bucket4 q = ld_bucket (keys + 4ULL * b), qv = ld_bucket (vals + 4ULL * b);
-      unsigned long long slot, v;
+      const bucket4 q = ld_bucket (keys + 4ULL * b);
       const int f = bucket_find (q, key, &kw);
-      if (f >= 0) {
-        slot = 4ULL * b + (unsigned) f;
-        v = f == 0 ? qv.a : f == 1 ? qv.b : f == 2 ? qv.c : qv.d;
-      } else {
-        slot = table_lookup (keys, n_bucket, b, q, key, hs & 3u, &kw);      // walks on to the overflow buckets
-        v = __ldg (vals + slot);                    // slot is valid: the mask bit says the key is present
-      }
+      const unsigned long long slot = f >= 0 ? 4ULL * b + (unsigned) f
+                                             : table_lookup (keys, n_bucket, b, q, key, hs & 3u, &kw);   // walks on to the overflow buckets
       int64_t s = find_seq_from (woff, n_seq, ww, s_hint);
       int32_t p0 = (int32_t) ((ww - __ldg (woff + s)) << 5);
-      {
-        // ONT-side multiplicity state (ont.c:245): 2 bits per slot, saturating at "twice or more"
-        uint32_t sh = (uint32_t) (slot & 15) * 2;
-        uint32_t old = atomicOr (ont + (slot >> 4), 1u << sh);
-        if (((old >> sh) & 3u) == 1u) atomicOr (ont + (slot >> 4), 2u << sh);
-      }
+      // The ONT-side multiplicity state (ont.c:245: anchored once / more than once) lives in two spare
+      // bits of the value word, so ONE atomic both records the anchor and returns (tid, pos, flag):
+      // two random sectors per anchor (key bucket, value word) instead of three.
+      unsigned long long v = atomicOr (vals + slot, GCG_VAL_ONT1);        // slot is valid: the mask bit says the key is present
+      if ((v & (GCG_VAL_ONT1 | GCG_VAL_ONT2)) == GCG_VAL_ONT1) atomicOr (vals + slot, GCG_VAL_ONT2);
       int4 hh;                                      // gcg_hit {read, pos, tid, cpos_flags} as one 16-byte store
       hh.x = (int32_t) s + read_base;
       hh.y = p0 + j;
@@ -347,21 +338,21 @@ hits_emit_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
 // K6  statistics
 // =============================================================================================
 __global__ void __launch_bounds__ (256)
-k6_stats_kernel (const unsigned long long * __restrict__ keys, uint64_t n_slot, const uint32_t * __restrict__ ont,
+k6_stats_kernel (const unsigned long long * __restrict__ keys, const unsigned long long * __restrict__ vals, uint64_t n_slot,
                  unsigned long long * __restrict__ out4)
 {
   unsigned long long total = 0, uniq = 0, ot = 0, ou = 0;
   int64_t stride = (int64_t) gridDim.x * blockDim.x;
   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t) n_slot; i += stride) {
     unsigned long long kw = keys[i];
-    if (kw & GCG_KEY_MASK) { ++total; if (!(kw & GCG_KEY_MULTI)) ++uniq; }
-  }
-  int64_t n_ont = (int64_t) ((n_slot + 15) >> 4);
-  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_ont; i += stride) {
-    uint32_t v = ont[i];
-    uint32_t ge1 = v & 0x55555555u, ge2 = (v >> 1) & 0x55555555u;
-    ot += __popc (ge1);
-    ou += __popc (ge1 & ~ge2);
+    if (kw & GCG_KEY_MASK) {
+      ++total;
+      if (!(kw & GCG_KEY_MULTI)) {
+        ++uniq;
+        const unsigned long long v = vals[i];         // (only keys present once can anchor)
+        if (v & GCG_VAL_ONT1) { ++ot; if (!(v & GCG_VAL_ONT2)) ++ou; }
+      }
+    }
   }
   for (int o = 16; o; o >>= 1) {
     total += __shfl_down_sync (0xffffffffu, total, o);
@@ -393,7 +384,7 @@ table_dump_kernel (const unsigned long long * __restrict__ keys, const unsigned 
     key_out[o] = (kw & GCG_KEY_MASK) - 1ULL;
     multi[o] = (kw & GCG_KEY_MULTI) ? 2 : 1;
     tid[o] = (int32_t) ((v >> 32) & 0x7FFFFFFFu);
-    pos[o] = (int32_t) ((v >> 1) & 0x7FFFFFFFu);
+    pos[o] = (int32_t) ((v >> 1) & 0x3FFFFFFFu);            // (bits 31 and 63 hold the ONT-side state)
     rev[o] = (uint8_t) (v & 1ULL);
   }
 }
@@ -701,7 +692,7 @@ extern "C" int64_t gcg_seqs_kmers (const gcg_seqs * s, int k)
 extern "C" void gcg_table_free (gcg_table * t)
 {
   if (!t) return;
-  gcg_dfree (t->ctx, t->d_keys); gcg_dfree (t->ctx, t->d_vals); gcg_dfree (t->ctx, t->d_ont); gcg_dfree (t->ctx, t->d_filter);
+  gcg_dfree (t->ctx, t->d_keys); gcg_dfree (t->ctx, t->d_vals); gcg_dfree (t->ctx, t->d_filter);
   delete t;
 }
 
@@ -717,16 +708,13 @@ int gcg_table_alloc (gcg_ctx * ctx, int64_t n_kmers, int k, gcg_table ** out)
   t->n_bucket = (uint32_t) nb;
   t->n_slot = (uint64_t) nb * 4;
   t->n_inserted = n_kmers;
-  size_t ont_words = (size_t) ((t->n_slot + 15) >> 4);
   cudaError_t e;
-  if ((e = gcg_dmalloc (ctx, &t->d_keys, t->n_slot * 8)) != cudaSuccess || (e = gcg_dmalloc (ctx, &t->d_vals, t->n_slot * 8)) != cudaSuccess ||
-      (e = gcg_dmalloc (ctx, &t->d_ont, ont_words * 4)) != cudaSuccess) {
+  if ((e = gcg_dmalloc (ctx, &t->d_keys, t->n_slot * 8)) != cudaSuccess || (e = gcg_dmalloc (ctx, &t->d_vals, t->n_slot * 8)) != cudaSuccess) {
     gcg_set_error ("gcg_table: cudaMalloc of %llu slots failed: %s", (unsigned long long) t->n_slot, cudaGetErrorString (e));
     gcg_table_free (t);
     return GCG_ENOMEM;
   }
   GCG_CUDA (cudaMemsetAsync (t->d_keys, 0, t->n_slot * 8, ctx->stream));
-  GCG_CUDA (cudaMemsetAsync (t->d_ont, 0, ont_words * 4, ctx->stream));
   *out = t;
   return GCG_OK;
 }
@@ -771,7 +759,7 @@ extern "C" int gcg_table_stats (gcg_ctx * ctx, gcg_table * t, int64_t out[4])
   GCG_CUDA (cudaMemsetAsync (ctx->d_counters, 0, 4 * 8, ctx->stream));
   {
     gcg_kscope ks (ctx, "k6_stats");
-    k6_stats_kernel<<<grid_for (ctx, (int64_t) t->n_slot, 256, 8), 256, 0, ctx->stream>>> (t->d_keys, t->n_slot, t->d_ont, ctx->d_counters);
+    k6_stats_kernel<<<grid_for (ctx, (int64_t) t->n_slot, 256, 8), 256, 0, ctx->stream>>> (t->d_keys, t->d_vals, t->n_slot, ctx->d_counters);
     GCG_CUDA (cudaGetLastError ());
   }
   GCG_CUDA (cudaMemcpyAsync (ctx->h_counters, ctx->d_counters, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -990,7 +978,7 @@ extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * r
       }
       { gcg_kscope ks (ctx, "hits_emit");
         hits_emit_kernel<<<grid_for (ctx, ((n_words + 31) >> 5) * 32, 256, 8), 256, 0, ctx->stream>>> (
-            reads->d_packed, reads->d_woff, reads->d_tseq, reads->n, n_words, k, t->d_keys, t->d_vals, t->d_ont, t->n_bucket, d_mask, d_prefix, 0, h->d_hits); }
+            reads->d_packed, reads->d_woff, reads->d_tseq, reads->n, n_words, k, t->d_keys, t->d_vals, t->n_bucket, d_mask, d_prefix, 0, h->d_hits); }
       gcg_trace_mark (ctx, "  search_seqs: hits alloc");
       // no wait for the emit kernel: the anchors stay on the device and everything that reads them
       // (download, statistics, the next search) is ordered behind it on the context's stream
@@ -1255,7 +1243,7 @@ extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * re
     GCG_CUDA (cudaEventRecord (q.ev_count, ctx->stream));
     { gcg_kscope ks (ctx, "hits_emit");
       hits_emit_kernel<<<grid_for (ctx, d.n_tiles * 32, 256, 8), 256, 0, ctx->stream>>> (
-          q.d_packed, d_woff, d_tseq, nr, nw, k, t->d_keys, t->d_vals, t->d_ont, t->n_bucket, q.d_mask, q.d_prefix, (int32_t) d.r0, q.d_hits); }
+          q.d_packed, d_woff, d_tseq, nr, nw, k, t->d_keys, t->d_vals, t->n_bucket, q.d_mask, q.d_prefix, (int32_t) d.r0, q.d_hits); }
     GCG_CUDA (cudaEventRecord (q.ev_emit, ctx->stream));
     GCG_CUDA (cudaGetLastError ());
     q.pending = true;

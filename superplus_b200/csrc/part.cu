@@ -488,7 +488,7 @@ struct lookup_dst { unsigned long long * base[GCG_MAX_PART]; long long first[GCG
 #define LK_UNROLL 4
 __global__ void __launch_bounds__ (256)
 lookup_keys_kernel (const unsigned long long * __restrict__ qkeys, int64_t n, const unsigned long long * __restrict__ keys,
-                    const unsigned long long * __restrict__ vals, uint32_t * __restrict__ ont, uint32_t n_bucket,
+                    unsigned long long * __restrict__ vals, uint32_t n_bucket,
                     const __grid_constant__ lookup_dst dst)
 {
   __shared__ unsigned long long * s_base[GCG_MAX_PART];
@@ -516,10 +516,11 @@ lookup_keys_kernel (const unsigned long long * __restrict__ qkeys, int64_t n, co
       unsigned long long kw, a = GCG_ANS_MISS;
       const unsigned long long slot = table_lookup (keys, n_bucket, __umulhi (hs[u], n_bucket), q[u], key[u], hs[u] & 3u, &kw);
       if (slot != ~0ULL && !(kw & GCG_KEY_MULTI)) {            // multi == 1  (ont.c:171,195)
-        a = __ldg (vals + slot);
-        const uint32_t sh = (uint32_t) (slot & 15) * 2;        // ONT-side multiplicity (ont.c:245), saturating at 2
-        const uint32_t old = atomicOr (ont + (slot >> 4), 1u << sh);
-        if (((old >> sh) & 3u) == 1u) atomicOr (ont + (slot >> 4), 2u << sh);
+        // one atomic returns the value word and records the anchor (ONT-side multiplicity, ont.c:245,
+        // saturating at 2, in the word's two spare bits)
+        const unsigned long long old = atomicOr (vals + slot, GCG_VAL_ONT1);
+        if ((old & (GCG_VAL_ONT1 | GCG_VAL_ONT2)) == GCG_VAL_ONT1) atomicOr (vals + slot, GCG_VAL_ONT2);
+        a = old & ~(GCG_VAL_ONT1 | GCG_VAL_ONT2);
       }
       int r = 0;
       while (r + 1 < n_src && s_first[r + 1] <= i) ++r;
@@ -857,7 +858,7 @@ static int lookup_launch (gcg_ctx * ctx, gcg_table * t, const void * d_keys, int
 {
   gcg_kscope ks (ctx, "part_lookup");
   lookup_keys_kernel<<<flat_grid (ctx, n, LK_UNROLL), 256, 0, ctx->stream>>> (
-      (const unsigned long long *) d_keys, n, t->d_keys, t->d_vals, t->d_ont, t->n_bucket, dst);
+      (const unsigned long long *) d_keys, n, t->d_keys, t->d_vals, t->n_bucket, dst);
   GCG_CUDA (cudaGetLastError ());
   return GCG_OK;
 }
