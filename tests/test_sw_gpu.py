@@ -206,6 +206,35 @@ def test_cfg3_shape_pairs(ctx, oracle):
         assert int(res["score"].min()) > 500            # the embedded flank copy aligns
 
 
+def test_largest_sizes_of_each_kernel(ctx, oracle):
+    """The largest alignments each kernel takes, both traceback modes: target lengths around the
+    packed kernel's provable 16-bit range (default scoring: 2 020 rows fit, 2 030 do not and go to the
+    s32 kernel), a 20 kb query on the packed kernel, and a 20 kb x 4 kb pair on the s32 kernel."""
+    rng = np.random.default_rng(91)
+
+    def pair(ql, tl):
+        t = rng.integers(0, 4, tl).astype(np.uint8)
+        q = rng.integers(0, 4, ql).astype(np.uint8)
+        cp = synth.mutate(t, 0.1, rng) % 4
+        cp = cp[:ql]
+        a = int(rng.integers(0, ql - len(cp) + 1))
+        q[a:a + len(cp)] = cp
+        return q, t
+
+    P = api.make_sw_params()
+    for (ql, tl), want_paths in (((20_000, 2_020), (1, 0)), ((12_000, 2_030), (0, 1)), ((20_000, 4_000), (0, 1))):
+        q, t = pair(ql, tl)
+        qb, qo = api._concat([q])
+        tb, to = api._concat([t])
+        b = ctx.swbatch_upload_concat(qb, qo, tb, to)
+        b.align(P, api.SW_ASIS)
+        assert b.path_counts() == want_paths, (ql, tl)
+        b.free()
+        for mode in (api.SW_ASIS, api.SW_FIXED):
+            res = check_batch(ctx, oracle, P, [q], [t], mode)
+            assert int(res["score"][0]) > tl // 4          # the embedded copy aligns
+
+
 def test_multi_wave_and_pool_growth(ctx, oracle):
     rng = np.random.default_rng(2)
     qs, ts = random_pairs(rng, 200, 600, 500)
