@@ -112,6 +112,18 @@ int  gcg_table_stats (gcg_ctx * ctx, gcg_table * t, int64_t out[4]);
 int64_t gcg_table_size (gcg_ctx * ctx, gcg_table * t);
 int  gcg_table_dump (gcg_ctx * ctx, gcg_table * t, int64_t cap, uint64_t * key, int32_t * multi_out,
                      int32_t * tid, int32_t * pos, uint8_t * rev);
+/* Replicas for read batches sharded over the GPUs of a box inside ONE process (SURVEY 8e,
+ * "replicated"; what the reference does with its n_thread work-stealing loop over reads,
+ * ont.c:316-400).  gcg_table_clone copies a built table slot for slot into the device of
+ * `dst_ctx` (device-to-device, NVLink when the GPUs are peers); every replica is then searched
+ * with its own share of the reads from its own host thread.  gcg_table_merge_ont folds the
+ * ONT-side multiplicity a replica has collected (ont.c:245: multi = number of ONT hits of the
+ * k-mer) into `dst`, saturating at "more than once", so that gcg_table_stats on `dst` reports
+ * out[2] / out[3] over ALL reads, as the reference's anchored sets do.  The two tables must be
+ * clones of each other (same slot layout).  The counts MOVE: `src`'s ONT-side state is cleared
+ * once folded, so further searches on the replicas followed by further merges keep adding up. */
+int  gcg_table_clone (gcg_ctx * dst_ctx, gcg_table * src, gcg_table ** out);
+int  gcg_table_merge_ont (gcg_ctx * ctx, gcg_table * dst, gcg_table * src);
 
 /* ------------------------------------------------------------------ ONT search ------- */
 /* one anchored ONT position (ont.c:171-178,195-202): the canonical k-mer at `pos` of read

@@ -1,6 +1,7 @@
 """Wall-clock of the whole gap_closer CLI on one config: reference gc (oracle/_ref, host cores) vs
 gc_b200 (same callers + the CUDA path), outputs compared by md5, stdout lines time-stamped through
-a pty so that the phases the CLI does not time itself show up.  usage: gc_e2e_time.py cfg2 [threads]"""
+a pty so that the phases the CLI does not time itself show up.  usage: gc_e2e_time.py cfg2 [threads] [devices]
+(devices, e.g. 0,1: one more gc_b200 run with GC_DEVICES set — the reads sharded over those GPUs)"""
 import hashlib, os, pty, select, subprocess, sys, tempfile, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from superplus_b200 import synth
@@ -10,10 +11,10 @@ nt = sys.argv[2] if len(sys.argv) > 2 else str(os.cpu_count())
 md5 = lambda p: hashlib.md5(open(p, "rb").read()).hexdigest()
 
 
-def run(exe, args, cwd):
+def run(exe, args, cwd, extra_env=None):
     m, s = pty.openpty()
     t0 = time.perf_counter()
-    p = subprocess.Popen([exe] + args, cwd=cwd, stdout=s, stderr=s, env=dict(os.environ, GCG_TRACE='1'))
+    p = subprocess.Popen([exe] + args, cwd=cwd, stdout=s, stderr=s, env=dict(os.environ, GCG_TRACE='1', **(extra_env or {})))
     os.close(s)
     buf, lines = b"", []
     while True:
@@ -38,11 +39,14 @@ def run(exe, args, cwd):
 with tempfile.TemporaryDirectory() as tmp:
     fa, fq, _ = synth.materialise(cfg, tmp)
     res = {}
-    for name, exe in (("reference_gc", os.path.join(ROOT, "oracle", "_ref", "gc")), ("gc_b200", os.path.join(ROOT, "superplus_b200", "_build", "gc_b200")),
-                      ("gc_b200_again", os.path.join(ROOT, "superplus_b200", "_build", "gc_b200"))):
+    runs = [("reference_gc", os.path.join(ROOT, "oracle", "_ref", "gc"), None), ("gc_b200", os.path.join(ROOT, "superplus_b200", "_build", "gc_b200"), None),
+            ("gc_b200_again", os.path.join(ROOT, "superplus_b200", "_build", "gc_b200"), None)]
+    if len(sys.argv) > 3:
+        runs.append(("gc_b200_devices_" + sys.argv[3], os.path.join(ROOT, "superplus_b200", "_build", "gc_b200"), {"GC_DEVICES": sys.argv[3]}))
+    for name, exe, extra in runs:
         wd = os.path.join(tmp, name)
         os.makedirs(wd)
-        rc, dt, lines = run(exe, [fa, fq, nt, "out"], wd)
+        rc, dt, lines = run(exe, [fa, fq, nt, "out"], wd, extra)
         print("== %s: rc %d, %.2f s wall, %s threads" % (name, rc, dt, nt))
         for t, l in lines:
             if l and ("cost" in l.lower() or "kmer count" in l or "gcg" in l):

@@ -28,7 +28,7 @@ EXPORTS = [
     "gcg_seqs_upload", "gcg_seqs_upload_concat", "gcg_ascii_upload_concat", "gcg_seqs_pack", "gcg_ascii_free",
     "gcg_seqs_free", "gcg_seqs_count", "gcg_seqs_bases", "gcg_seqs_kmers", "gcg_host_pack_2bit",
     "gcg_chop_contigs", "gcg_table_build_seqs", "gcg_table_build", "gcg_table_free", "gcg_table_stats",
-    "gcg_table_size", "gcg_table_dump",
+    "gcg_table_size", "gcg_table_dump", "gcg_table_clone", "gcg_table_merge_ont",
     "gcg_search_seqs", "gcg_hits_count", "gcg_hits_download", "gcg_hits_free", "gcg_search", "gcg_free",
     "gcg_sw_batch", "gcg_swbatch_upload", "gcg_swbatch_align", "gcg_swbatch_download", "gcg_swbatch_cells",
     "gcg_swbatch_path_counts", "gcg_swbatch_free",
@@ -139,6 +139,8 @@ def load_library(path: str = LIB_PATH):
     L.gcg_table_size.restype = i64
     L.gcg_table_size.argtypes = [vp, vp]
     L.gcg_table_dump.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
+    L.gcg_table_clone.argtypes = [vp, vp, C.POINTER(vp)]
+    L.gcg_table_merge_ont.argtypes = [vp, vp, vp]
     L.gcg_search_seqs.argtypes = [vp, vp, vp, C.c_int, C.POINTER(vp)]
     L.gcg_hits_count.restype = i64
     L.gcg_hits_count.argtypes = [vp]
@@ -539,6 +541,16 @@ class KmerTable(_Handle):
         self.ctx._chk(self.ctx.L.gcg_table_stats(self.ctx.h, self.h, out.ctypes.data))
         return tuple(int(x) for x in out)
 
+    def clone(self, ctx: "Context") -> "KmerTable":
+        """slot-for-slot replica on the device of `ctx` (read batches sharded over the GPUs of a box)"""
+        h = C.c_void_p()
+        ctx._chk(ctx.L.gcg_table_clone(ctx.h, self.h, C.byref(h)))
+        return KmerTable(ctx, h, self.k)
+
+    def merge_ont(self, replica: "KmerTable"):
+        """fold the ONT-side multiplicity collected by a replica into this table (stats over all reads)"""
+        self.ctx._chk(self.ctx.L.gcg_table_merge_ont(self.ctx.h, self.h, replica.h))
+
     def insert_records(self, d_records: int, n: int):
         self.ctx._chk(self.ctx.L.gcg_table_insert_records(self.ctx.h, self.h, d_records, int(n)))
 
@@ -598,3 +610,58 @@ class SWBatch(_Handle):
             self.ctx.L.gcg_free(pool)
         cigs = [cp[int(r["cigar_off"]):int(r["cigar_off"]) + int(r["n_cigar"])] for r in res]
         return res, cigs
+
+
+def split_reads_by_bases(lens, n_share: int):
+    """Contiguous read ranges [b_i, b_{i+1}) with about equal bases each (the shim's split, ont.c of this
+    repo): share i ends at the first read where the running base count reaches (i + 1) / n of the total."""
+    lens = np.asarray(lens, dtype=np.int64)
+    cum = np.concatenate([[0], np.cumsum(lens)])
+    total = int(cum[-1])
+    bounds = [0]
+    for i in range(1, n_share):
+        bounds.append(max(bounds[-1], int(np.searchsorted(cum, (total * i + n_share - 1) // n_share, side="left"))))
+    bounds.append(len(lens))
+    return [min(b, len(lens)) for b in bounds]
+
+
+class ReplicatedSearch:
+    """ONT reads sharded by batch over the GPUs of one box inside one process (replicated
+    table): the table built on ctxs[0] is cloned slot for slot onto the other contexts, every context
+    searches a contiguous share of the reads from its own host thread (the library call releases the
+    GIL), the anchors are concatenated in read order and the replicas' ONT-side multiplicity is folded
+    back into the primary table, whose statistics then cover all reads.  Mirrors what gc_b200 does with
+    GC_DEVICES=0,1,... (superplus_b200/gap_closer/ont.c)."""
+
+    def __init__(self, ctxs, table: KmerTable):
+        assert table.ctx is ctxs[0]
+        self.ctxs = list(ctxs)
+        self.tables = [table] + [table.clone(c) for c in self.ctxs[1:]]
+
+    def search_host(self, reads) -> np.ndarray:
+        import threading
+        bounds = split_reads_by_bases([len(r) for r in reads], len(self.ctxs))
+        parts = [None] * len(self.ctxs)
+        errs = []
+
+        def work(i):
+            try:
+                parts[i] = self.ctxs[i].search_host(self.tables[i], reads[bounds[i]:bounds[i + 1]])
+                parts[i]["read"] += bounds[i]
+            except Exception as e:      # noqa: BLE001 - re-raised on the calling thread
+                errs.append(e)
+        th = [threading.Thread(target=work, args=(i,)) for i in range(len(self.ctxs))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+        for rep in self.tables[1:]:
+            self.tables[0].merge_ont(rep)
+        return np.concatenate(parts) if parts else np.zeros(0, dtype=HIT_DTYPE)
+
+    def free(self):
+        for rep in self.tables[1:]:
+            rep.free()
+        self.tables = self.tables[:1]

@@ -368,6 +368,35 @@ k6_stats_kernel (const unsigned long long * __restrict__ keys, const unsigned lo
   }
 }
 
+// ONT-side multiplicity of a replica folded into the primary table (gcg_table_merge_ont): the state
+// of a slot is 0 / once (ONT1) / more than once (ONT1|ONT2); the sum of two states saturates at the
+// last.  Slots without a key hold unspecified value words on both sides and are left alone.
+__global__ void __launch_bounds__ (256)
+ont_merge_kernel (const unsigned long long * __restrict__ keys, unsigned long long * __restrict__ vals,
+                  const unsigned long long * __restrict__ other, int64_t n)
+{
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned long long b = other[i] & (GCG_VAL_ONT1 | GCG_VAL_ONT2);
+    if (b == 0 || (keys[i] & GCG_KEY_MASK) == 0) continue;
+    const unsigned long long a = vals[i];
+    unsigned long long m = a | b;
+    if (a & b & GCG_VAL_ONT1) m |= GCG_VAL_ONT2;
+    if (m != a) vals[i] = m;
+  }
+}
+
+// ... and the replica's own state cleared once it has been folded: what it collects next is added on top
+__global__ void __launch_bounds__ (256)
+ont_clear_kernel (const unsigned long long * __restrict__ keys, unsigned long long * __restrict__ vals, int64_t n)
+{
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned long long a = vals[i];
+    if ((a & (GCG_VAL_ONT1 | GCG_VAL_ONT2)) != 0 && (keys[i] & GCG_KEY_MASK) != 0) vals[i] = a & ~(GCG_VAL_ONT1 | GCG_VAL_ONT2);
+  }
+}
+
 __global__ void __launch_bounds__ (256)
 table_dump_kernel (const unsigned long long * __restrict__ keys, const unsigned long long * __restrict__ vals,
                    uint64_t n_slot, unsigned long long * __restrict__ counter, int64_t cap,
@@ -773,6 +802,83 @@ extern "C" int64_t gcg_table_size (gcg_ctx * ctx, gcg_table * t)
   int64_t st[4];
   if (gcg_table_stats (ctx, t, st)) return -1;
   return st[0];
+}
+
+extern "C" int gcg_table_clone (gcg_ctx * dst_ctx, gcg_table * src, gcg_table ** out)
+{
+  GCG_CHECK (dst_ctx && src && out, GCG_EINVAL, "gcg_table_clone: bad argument");
+  // everything queued on the source's stream (build, searches) must have landed before the copy
+  GCG_CUDA (cudaSetDevice (src->ctx->device));
+  GCG_CUDA (cudaStreamSynchronize (src->ctx->stream));
+  GCG_CUDA (cudaSetDevice (dst_ctx->device));
+  gcg_table * t = new gcg_table ();
+  t->ctx = dst_ctx; t->k = src->k; t->n_bucket = src->n_bucket; t->n_slot = src->n_slot; t->n_inserted = src->n_inserted;
+  cudaError_t e;
+  if ((e = gcg_dmalloc (dst_ctx, &t->d_keys, t->n_slot * 8)) != cudaSuccess || (e = gcg_dmalloc (dst_ctx, &t->d_vals, t->n_slot * 8)) != cudaSuccess) {
+    gcg_set_error ("gcg_table_clone: cudaMalloc of %llu slots failed: %s", (unsigned long long) t->n_slot, cudaGetErrorString (e));
+    gcg_table_free (t);
+    return GCG_ENOMEM;
+  }
+  // (the pre-filter is not copied: gcg_table_filter_ensure rebuilds it on the first search that wants it)
+  if ((e = cudaMemcpyPeerAsync (t->d_keys, dst_ctx->device, src->d_keys, src->ctx->device, t->n_slot * 8, dst_ctx->stream)) != cudaSuccess ||
+      (e = cudaMemcpyPeerAsync (t->d_vals, dst_ctx->device, src->d_vals, src->ctx->device, t->n_slot * 8, dst_ctx->stream)) != cudaSuccess ||
+      (e = cudaStreamSynchronize (dst_ctx->stream)) != cudaSuccess) {
+    gcg_set_error ("gcg_table_clone: device %d -> device %d copy failed: %s", src->ctx->device, dst_ctx->device, cudaGetErrorString (e));
+    gcg_table_free (t);
+    return GCG_ECUDA;
+  }
+  {
+    // a replica counts only what IT finds: whatever the source had already collected stays with the source
+    gcg_kscope ks (dst_ctx, "ont_clear");
+    ont_clear_kernel<<<grid_for (dst_ctx, (int64_t) t->n_slot, 256, 8), 256, 0, dst_ctx->stream>>> (t->d_keys, t->d_vals, (int64_t) t->n_slot);
+    if (cudaGetLastError () != cudaSuccess || cudaStreamSynchronize (dst_ctx->stream) != cudaSuccess) {
+      gcg_set_error ("gcg_table_clone: clearing the replica's ONT state failed");
+      gcg_table_free (t);
+      return GCG_ECUDA;
+    }
+  }
+  *out = t;
+  return GCG_OK;
+}
+
+extern "C" int gcg_table_merge_ont (gcg_ctx * ctx, gcg_table * dst, gcg_table * src)
+{
+  GCG_CHECK (ctx && dst && src && dst->ctx == ctx, GCG_EINVAL, "gcg_table_merge_ont: bad argument (dst must belong to ctx)");
+  GCG_CHECK (dst != src, GCG_EINVAL, "gcg_table_merge_ont: a table cannot be merged into itself");
+  GCG_CHECK (dst->n_slot == src->n_slot && dst->k == src->k && dst->n_inserted == src->n_inserted, GCG_EINVAL,
+             "gcg_table_merge_ont: the tables are not clones of each other (%llu / %llu slots)", (unsigned long long) dst->n_slot, (unsigned long long) src->n_slot);
+  GCG_CUDA (cudaSetDevice (src->ctx->device));
+  GCG_CUDA (cudaStreamSynchronize (src->ctx->stream));          // the replica's searches have finished
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  // value words of the replica come over in pieces of at most 512 MB (a whole cfg5 value array is 4 GB)
+  const int64_t n = (int64_t) dst->n_slot, piece = std::min<int64_t> (n, (int64_t) 64 << 20);
+  unsigned long long * tmp = nullptr;
+  const bool same_dev = src->ctx->device == ctx->device;
+  if (!same_dev) GCG_CUDA (gcg_dmalloc (ctx, &tmp, (size_t) piece * 8));
+  for (int64_t at = 0; at < n; at += piece) {
+    const int64_t m = std::min (piece, n - at);
+    const unsigned long long * other = src->d_vals + at;
+    if (!same_dev) {
+      cudaError_t e = cudaMemcpyPeerAsync (tmp, ctx->device, src->d_vals + at, src->ctx->device, (size_t) m * 8, ctx->stream);
+      if (e != cudaSuccess) { gcg_dfree (ctx, tmp); gcg_set_error ("gcg_table_merge_ont: peer copy failed: %s", cudaGetErrorString (e)); return GCG_ECUDA; }
+      other = tmp;
+    }
+    gcg_kscope ks (ctx, "ont_merge");
+    ont_merge_kernel<<<grid_for (ctx, m, 256, 8), 256, 0, ctx->stream>>> (dst->d_keys + at, dst->d_vals + at, other, m);
+    GCG_CUDA (cudaGetLastError ());
+  }
+  GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+  if (tmp) gcg_dfree (ctx, tmp);
+  // the counts have moved: the replica starts its next batch from zero
+  GCG_CUDA (cudaSetDevice (src->ctx->device));
+  {
+    gcg_kscope ks (src->ctx, "ont_clear");
+    ont_clear_kernel<<<grid_for (src->ctx, n, 256, 8), 256, 0, src->ctx->stream>>> (src->d_keys, src->d_vals, n);
+    GCG_CUDA (cudaGetLastError ());
+  }
+  GCG_CUDA (cudaStreamSynchronize (src->ctx->stream));
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  return GCG_OK;
 }
 
 extern "C" int gcg_table_dump (gcg_ctx * ctx, gcg_table * t, int64_t cap, uint64_t * key, int32_t * multi_out,

@@ -1,10 +1,13 @@
-/* Lazily created libgcgpu context shared by the replacement kmer.c / ont.c / sw.c.
+/* Lazily created libgcgpu contexts shared by the replacement kmer.c / ont.c / sw.c.
  *
  * Opening a CUDA device costs 0.3 .. 5 s per process (driver start-up without a persistence
- * daemon) and pinning the staging buffers another ~0.2 s.  gcg_bridge_warmup () does both on a
- * helper thread while the unchanged host code is still reading its inputs (contig_seqs_load,
- * sefq_load: main.c:152-156); gcg_bridge () joins it at the first device call.  Without a
- * warm-up the context is created on first use, as before. */
+ * daemon) and pinning the staging buffers another ~0.2 s.  gcg_bridge_warmup () does both on
+ * helper threads (one per device) while the unchanged host code is still reading its inputs
+ * (contig_seqs_load, sefq_load: main.c:152-156); gcg_bridge () joins them at the first device
+ * call.  Without a warm-up the contexts are created on first use, as before.
+ *
+ * Devices: $GC_DEVICES = "0,1,2,3" or "all" shards the ONT read batch over several GPUs of the
+ * box (table replicated, ont.c of this directory); otherwise the single device $GC_DEVICE (0). */
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -14,17 +17,41 @@
 #include "utils.h"
 #include "gcg_bridge.h"
 
-static gcg_bridge_t g_bridge = { NULL, NULL, NULL, 0, 1 };
-static pthread_t g_warm_thread;
-static int g_warm_started = 0, g_warm_rc = 0;
-static gcg_ctx * g_warm_ctx = NULL;
-static char g_warm_err[600] = "";
+static gcg_bridge_t g_bridge = { NULL, NULL, NULL, 0, 1, 0, {0}, {NULL}, {NULL} };
+static pthread_t g_warm_thread[GCG_BRIDGE_MAX_DEV];
+static int g_warm_started = 0, g_warm_rc[GCG_BRIDGE_MAX_DEV];
+static gcg_ctx * g_warm_ctx[GCG_BRIDGE_MAX_DEV];
+static char g_warm_err[GCG_BRIDGE_MAX_DEV][600];
 
-static int
-bridge_device (void)
+/* fills g_bridge.devs / n_dev once */
+static void
+bridge_devices (void)
 {
-  const char * dev = getenv ("GC_DEVICE");
-  return dev ? atoi (dev) : 0;
+  const char * list = getenv ("GC_DEVICES"), * one = getenv ("GC_DEVICE");
+  if (g_bridge.n_dev > 0) return;
+  if (list != NULL && strcmp (list, "all") == 0) {
+    int i, n = gcg_device_count ();
+    if (n < 1) err_mesg ("[gcg_bridge] GC_DEVICES=all but no CUDA device is visible (there is no CPU fallback)");
+    if (n > GCG_BRIDGE_MAX_DEV) n = GCG_BRIDGE_MAX_DEV;
+    for (i = 0; i < n; ++i) g_bridge.devs[i] = i;
+    g_bridge.n_dev = n;
+  } else if (list != NULL && *list) {
+    const char * p = list;
+    while (*p) {
+      char * end;
+      long d = strtol (p, &end, 10);
+      if (end == p || d < 0) err_mesg ("[gcg_bridge] cannot parse GC_DEVICES='%s' (expected e.g. 0,1,2,3 or all)", list);
+      if (g_bridge.n_dev == GCG_BRIDGE_MAX_DEV) err_mesg ("[gcg_bridge] GC_DEVICES names more than %d devices", GCG_BRIDGE_MAX_DEV);
+      g_bridge.devs[g_bridge.n_dev++] = (int) d;
+      p = end;
+      if (*p == ',') ++p;
+      else if (*p) err_mesg ("[gcg_bridge] cannot parse GC_DEVICES='%s' (expected e.g. 0,1,2,3 or all)", list);
+    }
+    if (g_bridge.n_dev == 0) err_mesg ("[gcg_bridge] GC_DEVICES is empty");
+  } else {
+    g_bridge.devs[0] = one ? atoi (one) : 0;
+    g_bridge.n_dev = 1;
+  }
 }
 
 static double
@@ -38,41 +65,50 @@ now_ms (void)
 static void *
 warm_main (void * arg)
 {
+  const int i = (int) (long) arg;
   double t0 = now_ms (), t1;
-  (void) arg;
-  g_warm_rc = gcg_init (bridge_device (), &g_warm_ctx);
+  g_warm_rc[i] = gcg_init (g_bridge.devs[i], &g_warm_ctx[i]);
   t1 = now_ms ();
-  if (g_warm_rc == 0) g_warm_rc = gcg_warmup (g_warm_ctx);
-  if (getenv ("GCG_TRACE")) fprintf (stderr, "[gcg] warm-up thread: device open %.0f ms, staging buffers %.0f ms\n", t1 - t0, now_ms () - t1);
-  if (g_warm_rc != 0) snprintf (g_warm_err, sizeof g_warm_err, "%s", gcg_last_error ());
+  if (g_warm_rc[i] == 0) g_warm_rc[i] = gcg_warmup (g_warm_ctx[i]);
+  if (getenv ("GCG_TRACE")) fprintf (stderr, "[gcg] warm-up thread: device %d open %.0f ms, staging buffers %.0f ms\n", g_bridge.devs[i], t1 - t0, now_ms () - t1);
+  if (g_warm_rc[i] != 0) snprintf (g_warm_err[i], sizeof g_warm_err[i], "%s", gcg_last_error ());
   return NULL;
 }
 
 void
 gcg_bridge_warmup (void)
 {
+  int i;
   if (g_bridge.ctx != NULL || g_warm_started) return;
   if (getenv ("GC_NO_WARMUP") != NULL) return;
-  if (pthread_create (&g_warm_thread, NULL, warm_main, NULL) == 0) g_warm_started = 1;
+  bridge_devices ();
+  for (i = 0; i < g_bridge.n_dev; ++i) {
+    if (pthread_create (&g_warm_thread[i], NULL, warm_main, (void *) (long) i) != 0) break;
+    ++g_warm_started;
+  }
 }
 
 gcg_bridge_t *
 gcg_bridge (void)
 {
+  int i;
   if (g_bridge.ctx == NULL) {
-    if (g_warm_started) {
-      double t0 = now_ms ();
-      pthread_join (g_warm_thread, NULL);
-      if (getenv ("GCG_TRACE")) fprintf (stderr, "[gcg] first device call waited %.0f ms for the warm-up thread\n", now_ms () - t0);
-      g_warm_started = 0;
-      if (g_warm_rc != 0)
-        err_mesg ("[gcg_bridge] cannot open the CUDA device: %s (there is no CPU fallback)", g_warm_err);
-      g_bridge.ctx = g_warm_ctx;
-    } else {
-      int rc = gcg_init (bridge_device (), &g_bridge.ctx);
-      if (rc != 0)
-        err_mesg ("[gcg_bridge] cannot open the CUDA device: %s (there is no CPU fallback)", gcg_last_error ());
+    double t0 = now_ms ();
+    bridge_devices ();
+    for (i = 0; i < g_warm_started; ++i) {
+      pthread_join (g_warm_thread[i], NULL);
+      if (g_warm_rc[i] != 0)
+        err_mesg ("[gcg_bridge] cannot open CUDA device %d: %s (there is no CPU fallback)", g_bridge.devs[i], g_warm_err[i]);
+      g_bridge.ctxs[i] = g_warm_ctx[i];
     }
+    if (g_warm_started && getenv ("GCG_TRACE")) fprintf (stderr, "[gcg] first device call waited %.0f ms for the warm-up thread\n", now_ms () - t0);
+    for (i = g_warm_started; i < g_bridge.n_dev; ++i) {
+      int rc = gcg_init (g_bridge.devs[i], &g_bridge.ctxs[i]);
+      if (rc != 0)
+        err_mesg ("[gcg_bridge] cannot open CUDA device %d: %s (there is no CPU fallback)", g_bridge.devs[i], gcg_last_error ());
+    }
+    g_warm_started = 0;
+    g_bridge.ctx = g_bridge.ctxs[0];
   }
   return &g_bridge;
 }
@@ -80,7 +116,21 @@ gcg_bridge (void)
 void
 gcg_bridge_drop_table (void)
 {
+  int i;
+  for (i = 1; i < g_bridge.n_dev; ++i)
+    if (g_bridge.replicas[i]) { gcg_table_free (g_bridge.replicas[i]); g_bridge.replicas[i] = NULL; }
   if (g_bridge.table) { gcg_table_free (g_bridge.table); g_bridge.table = NULL; }
+}
+
+void
+gcg_bridge_replicate_table (void)
+{
+  int i;
+  if (g_bridge.table == NULL) return;
+  for (i = 1; i < g_bridge.n_dev; ++i) {
+    if (g_bridge.replicas[i]) { gcg_table_free (g_bridge.replicas[i]); g_bridge.replicas[i] = NULL; }
+    GCG_CK (gcg_table_clone (g_bridge.ctxs[i], g_bridge.table, &g_bridge.replicas[i]));
+  }
 }
 
 void
@@ -92,12 +142,15 @@ gcg_bridge_drop_contigs (void)
 void
 gcg_bridge_shutdown (void)
 {
-  if (g_warm_started) {              /* warmed up but never used */
-    pthread_join (g_warm_thread, NULL);
-    g_warm_started = 0;
-    if (g_warm_rc == 0) g_bridge.ctx = g_warm_ctx;
+  int i;
+  for (i = 0; i < g_warm_started; ++i) {         /* warmed up but never used */
+    pthread_join (g_warm_thread[i], NULL);
+    if (g_warm_rc[i] == 0) g_bridge.ctxs[i] = g_warm_ctx[i];
   }
+  g_warm_started = 0;
   gcg_bridge_drop_table ();
   gcg_bridge_drop_contigs ();
-  if (g_bridge.ctx) { gcg_destroy (g_bridge.ctx); g_bridge.ctx = NULL; }
+  for (i = 0; i < GCG_BRIDGE_MAX_DEV; ++i)
+    if (g_bridge.ctxs[i]) { gcg_destroy (g_bridge.ctxs[i]); g_bridge.ctxs[i] = NULL; }
+  g_bridge.ctx = NULL;
 }

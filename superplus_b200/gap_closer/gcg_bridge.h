@@ -7,17 +7,26 @@
 
 struct ctg_s;
 
+#define GCG_BRIDGE_MAX_DEV 16
+
 typedef struct {
-  gcg_ctx * ctx;          /* one context per process (device from $GC_DEVICE, default 0) */
+  gcg_ctx * ctx;          /* primary context: device $GC_DEVICE (default 0), or the first of $GC_DEVICES */
   gcg_seqs * contigs;     /* 2-bit contigs of the last chop_contig_seqs2kmers */
   gcg_table * table;      /* table of the last put_contig_kmers2hashs */
   int kmer_len;
   int n_thread;
+  /* GC_DEVICES=0,1,... (or "all"): the ONT reads are sharded by batch over these GPUs, every one
+   * holding a replica of the table (replicated layout).  ctxs[0] == ctx, replicas[0] == NULL. */
+  int n_dev;
+  int devs[GCG_BRIDGE_MAX_DEV];
+  gcg_ctx * ctxs[GCG_BRIDGE_MAX_DEV];
+  gcg_table * replicas[GCG_BRIDGE_MAX_DEV];
 } gcg_bridge_t;
 
 gcg_bridge_t * gcg_bridge (void);            /* lazily creates the context; aborts via err_mesg on failure */
 void gcg_bridge_warmup (void);               /* start opening the device on a helper thread (joined by gcg_bridge) */
-void gcg_bridge_drop_table (void);
+void gcg_bridge_drop_table (void);             /* the table and its replicas */
+void gcg_bridge_replicate_table (void);        /* clone the table onto the other devices (no-op with one) */
 void gcg_bridge_drop_contigs (void);
 void gcg_bridge_shutdown (void);
 #define GCG_CK(call) do { int rc_ = (call); if (rc_ != 0) err_mesg ("[%s] %s failed (%d): %s", __func__, #call, rc_, gcg_last_error ()); } while (0)

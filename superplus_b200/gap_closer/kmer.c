@@ -81,6 +81,7 @@ put_contig_kmers2hashs (xh_t ** khashs, mp_t(ctg) * seqs, int n_thread)
   gcg_bridge_drop_table ();
   GCG_CK (gcg_table_build_seqs (br->ctx, br->contigs, br->kmer_len, &br->table));
   GCG_CK (gcg_sync (br->ctx));
+  gcg_bridge_replicate_table ();       /* GC_DEVICES: one replica per further GPU */
 
   fprintf (stdout, "  hash kmers cost: %lds\n", time (NULL) - time_beg);
   return 0;

@@ -11,6 +11,11 @@
  *   UNANKOR  (reference ont.c:381-388 -> find_unankor_segs ont.c:264-309): derived from the
  *            sorted anchor list instead of re-scanning 16 bytes per ONT base
  *
+ * With GC_DEVICES=0,1,... the reads are sharded by batch over several GPUs of the box (SURVEY 8e,
+ * replicated table): contiguous read ranges of about equal bases, one host thread and one table
+ * replica per device, anchors back-filled per share, the replicas' ONT-side multiplicity folded into
+ * the primary table afterwards (gcg_table_merge_ont) so that kmer_stat2 prints the counts over all reads.
+ *
  * okmer->kmer points at &ctgs[tid].kmers[cpos] (what the reference's search phase stores,
  * ont.c:174); the reference later re-points it to a byte-identical copy inside anchored_ksets
  * (ont.c:245,253).  The anchored sets stay empty host objects (main.c:68-72 creates and frees
@@ -34,6 +39,7 @@
 typedef struct {
   const gcg_hit * hits;
   int64_t beg, end;
+  int64_t read_off;           /* index of the share's first read (hits count reads from their share's start) */
   mp_t(okseq) * okseqs;
   mp_t(ctg) * ctgs;
 } fill_arg_t;
@@ -45,7 +51,7 @@ fill_core (void * data)
   int64_t i;
   for (i = a->beg; i < a->end; ++i) {
     const gcg_hit * h = a->hits + i;
-    okseq_t * okseq = a->okseqs->pool + h->read;
+    okseq_t * okseq = a->okseqs->pool + a->read_off + h->read;
     ont_kmer_t * ok = okseq->okmers->pool + h->pos;
     kmer_t * km = a->ctgs->pool[h->tid].kmers + (h->cpos_flags >> 2);
     ok->kmer = km;
@@ -56,13 +62,13 @@ fill_core (void * data)
   return NULL;
 }
 
-/* maximal runs of un-anchored positions of every read, from the sorted anchors */
+/* maximal runs of un-anchored positions of the reads [r0, r1), from their share's sorted anchors */
 static void
-rebuild_segs (mp_t(okseq) * okseqs, const gcg_hit * hits, int64_t n_hit)
+rebuild_segs (mp_t(okseq) * okseqs, int64_t r0, int64_t r1, const gcg_hit * hits, int64_t n_hit)
 {
-  int64_t r, n_reads = mp_cnt (okseqs), h = 0;
+  int64_t r, n_reads = r1 - r0, h = 0;
   for (r = 0; r < n_reads; ++r) {
-    okseq_t * okseq = mp_at (okseq, okseqs, r);
+    okseq_t * okseq = mp_at (okseq, okseqs, r0 + r);
     int64_t n = mp_cnt (okseq->okmers), cur = 0;
     ont_seg_t * seg;
     mp_clear (oseg, okseq->segs, NULL);
@@ -83,19 +89,43 @@ rebuild_segs (mp_t(okseq) * okseqs, const gcg_hit * hits, int64_t n_hit)
   }
 }
 
+/* one share of the read batch on one device */
+typedef struct {
+  gcg_ctx * ctx;
+  gcg_table * table;
+  const char ** ptrs;
+  const int32_t * lens;
+  int64_t r0, r1;
+  int kmer_len;
+  gcg_hit * hits;
+  int64_t n_hit;
+  int rc;
+  char err[600];
+} share_t;
+
+static void *
+share_core (void * data)
+{
+  share_t * s = (share_t *) data;
+  s->rc = gcg_search (s->ctx, s->table, s->ptrs + s->r0, s->lens + s->r0, s->r1 - s->r0, s->kmer_len, &s->hits, &s->n_hit);
+  if (s->rc != 0) snprintf (s->err, sizeof s->err, "%s", gcg_last_error ());   /* the message is thread local */
+  return NULL;
+}
+
 int
 search_kmers_on_ont_reads (mp_t(rs) * ont_seqs, mp_t(ctg) * ctg_seqs,
     xh_t ** ctg_khashs, mp_t(okseq) * okseqs, xh_set_t(kmer) ** anchored_ksets,
     const char * prefix, int n_thread, int kmer_len)
 {
-  int i, nt;
+  int i, d, nt, n_dev, n_fill = 0;
   time_t time_beg, mod_tbeg;
-  int64_t r, n_reads, n_hit = 0;
+  int64_t r, n_reads, n_hit = 0, total_bases = 0, run = 0;
   const char ** ptrs;
   int32_t * lens;
-  gcg_hit * hits = NULL;
   pthread_t * pids;
+  pthread_t dev_pid[GCG_BRIDGE_MAX_DEV];
   fill_arg_t * args;
+  share_t share[GCG_BRIDGE_MAX_DEV];
   gcg_bridge_t * br = gcg_bridge ();
 
   time (&time_beg);
@@ -104,9 +134,11 @@ search_kmers_on_ont_reads (mp_t(rs) * ont_seqs, mp_t(ctg) * ctg_seqs,
   if (kmer_len != br->kmer_len)
     err_mesg ("[%s] kmer_len %d differs from the table's %d", __func__, kmer_len, br->kmer_len);
   nt = n_thread > 0 ? n_thread : 1;
-  GCG_CK (gcg_set_host_threads (br->ctx, nt));
+  n_dev = br->n_dev;
+  for (d = 0; d < n_dev; ++d)
+    GCG_CK (gcg_set_host_threads (br->ctxs[d], nt / n_dev > 0 ? nt / n_dev : 1));
 
-  /* search + ONT-side multiplicity on the device */
+  /* search + ONT-side multiplicity on the device(s) */
   time (&mod_tbeg);
   n_reads = mp_cnt (ont_seqs);
   ptrs = (const char **) ckalloc (n_reads + 1, sizeof (char *));
@@ -116,33 +148,72 @@ search_kmers_on_ont_reads (mp_t(rs) * ont_seqs, mp_t(ctg) * ctg_seqs,
     okseq_t * okseq = mp_at (okseq, okseqs, r);
     ptrs[r] = okseq->seq->b;
     lens[r] = okseq->seq->l;
+    total_bases += lens[r];
   }
-  GCG_CK (gcg_search (br->ctx, br->table, ptrs, lens, n_reads, kmer_len, &hits, &n_hit));
+  /* contiguous shares of about equal bases: share d ends at the first read where the running base
+   * count reaches (d + 1) / n_dev of the total (superplus_b200/api.py split_reads_by_bases) */
+  memset (share, 0, sizeof share);
+  for (d = 0, r = 0; d < n_dev; ++d) {
+    int64_t goal = (total_bases * (d + 1) + n_dev - 1) / n_dev;
+    share[d].ctx = br->ctxs[d];
+    share[d].table = d == 0 ? br->table : br->replicas[d];
+    share[d].ptrs = ptrs; share[d].lens = lens; share[d].kmer_len = kmer_len;
+    share[d].r0 = r;
+    if (d == n_dev - 1) r = n_reads;
+    else while (r < n_reads && run < goal) run += lens[r++];
+    share[d].r1 = r;
+    if (share[d].table == NULL)
+      err_mesg ("[%s] device %d holds no replica of the table", __func__, br->devs[d]);
+  }
+  if (n_dev == 1)
+    share_core (share);
+  else {
+    for (d = 0; d < n_dev; ++d) ckpthread_create (dev_pid + d, NULL, share_core, (void *) (share + d));
+    for (d = 0; d < n_dev; ++d) ckpthread_join (dev_pid[d]);
+  }
+  for (d = 0; d < n_dev; ++d) {
+    if (share[d].rc != 0)
+      err_mesg ("[%s] gcg_search on device %d failed (%d): %s", __func__, br->devs[d], share[d].rc, share[d].err);
+    n_hit += share[d].n_hit;
+  }
+  for (d = 1; d < n_dev; ++d)
+    GCG_CK (gcg_table_merge_ont (br->ctx, br->table, br->replicas[d]));
+  if (n_dev > 1 && getenv ("GCG_TRACE"))
+    for (d = 0; d < n_dev; ++d)
+      fprintf (stderr, "[gcg] device %d: reads [%ld, %ld), %ld anchors\n", br->devs[d], (long) share[d].r0, (long) share[d].r1, (long) share[d].n_hit);
   printf ("\n  chop and search ont kmers cost: %lds\n", time (NULL) - mod_tbeg);
 
   /* back-fill okmers[] (the reference's REHASH phase re-pointed the same entries) */
   time (&mod_tbeg);
   if (nt > n_hit / 4096 + 1) nt = (int) (n_hit / 4096 + 1);
-  pids = (pthread_t *) ckalloc (nt, sizeof (pthread_t));
-  args = (fill_arg_t *) ckalloc (nt, sizeof (fill_arg_t));
-  for (i = 0; i < nt; ++i) {
-    args[i].hits = hits;
-    args[i].beg = n_hit * i / nt;
-    args[i].end = n_hit * (i + 1) / nt;
-    args[i].okseqs = okseqs;
-    args[i].ctgs = ctg_seqs;
-    ckpthread_create (pids + i, NULL, fill_core, (void *) (args + i));
+  pids = (pthread_t *) ckalloc (nt + n_dev, sizeof (pthread_t));
+  args = (fill_arg_t *) ckalloc (nt + n_dev, sizeof (fill_arg_t));
+  for (d = 0; d < n_dev; ++d) {
+    /* host threads in proportion to the share's anchors, at least one */
+    int t, nt_d = n_hit > 0 ? (int) ((share[d].n_hit * nt + n_hit - 1) / n_hit) : 1;
+    if (nt_d < 1) nt_d = 1;
+    if (n_fill + nt_d > nt + n_dev) nt_d = nt + n_dev - n_fill;
+    for (t = 0; t < nt_d; ++t, ++n_fill) {
+      args[n_fill].hits = share[d].hits;
+      args[n_fill].beg = share[d].n_hit * t / nt_d;
+      args[n_fill].end = share[d].n_hit * (t + 1) / nt_d;
+      args[n_fill].read_off = share[d].r0;
+      args[n_fill].okseqs = okseqs;
+      args[n_fill].ctgs = ctg_seqs;
+      ckpthread_create (pids + n_fill, NULL, fill_core, (void *) (args + n_fill));
+    }
   }
-  for (i = 0; i < nt; ++i)
+  for (i = 0; i < n_fill; ++i)
     ckpthread_join (pids[i]);
   printf ("\n  re-hash ont kmers cost: %lds\n", time (NULL) - mod_tbeg);
 
   /* un-anchored segments */
   time (&mod_tbeg);
-  rebuild_segs (okseqs, hits, n_hit);
+  for (d = 0; d < n_dev; ++d)
+    rebuild_segs (okseqs, share[d].r0, share[d].r1, share[d].hits, share[d].n_hit);
   printf ("\n  find un-ankored positions on onts costs: %lds\n", time (NULL) - mod_tbeg);
 
-  gcg_free (hits);
+  for (d = 0; d < n_dev; ++d) gcg_free (share[d].hits);
   free (pids); free (args); free (ptrs); free (lens);
 
   printf ("\n  search ONT kmers total cost: %lds\n", time (NULL) - time_beg);

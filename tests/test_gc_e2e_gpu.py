@@ -48,6 +48,91 @@ def test_gap_filled_fasta_is_bit_exact(cfg, n_thread):
             assert line in out, line
 
 
+def _device_count():
+    from superplus_b200 import api
+    return int(api.load_library().gcg_device_count())
+
+
+@pytest.mark.parametrize("cfg,devices", [("small", "0,0"), ("repeats", "0,0,0"), ("cfg1", "0,0"), ("cfg1", "all"), ("cfg5s", "0,1")])
+def test_reads_sharded_over_devices_same_outputs(cfg, devices):
+    """GC_DEVICES shards the ONT read batch over several GPUs (one table replica and one host thread per
+    device): files and the four statistics must not change.  "0,0" runs two contexts on one
+    GPU (the single-GPU box still covers clone / shares / merge); "0,1" needs a second GPU."""
+    assert os.path.exists(GC), "gc_b200 was not built (python -c 'import __graft_entry__ as g; g.build()')"
+    if devices == "0,1" and _device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with tempfile.TemporaryDirectory() as tmp:
+        fa, fq, _ = synth.materialise(cfg, tmp)
+        wd = os.path.join(tmp, "run")
+        os.makedirs(wd)
+        env = dict(os.environ, GC_DEVICES=devices, GCG_TRACE="1")
+        r = subprocess.run([GC, fa, fq, "8", "out"], cwd=wd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600, env=env)
+        assert r.returncode == 0, r.stderr.decode()[-2000:]
+        stats = [int(x) for x in re.findall(r"(?:total|unique) kmer count: (\d+)", r.stdout.decode())]
+        g = GOLD[cfg]
+        assert stats == g["stats"]
+        assert md5(os.path.join(wd, "gc_fix1.fa")) == g["fa"]
+        assert md5(os.path.join(wd, "ont_link.txt")) == g["link"]
+        assert md5(os.path.join(wd, "valid_ont_link.txt")) == g["valid"]
+        if devices != "all" or _device_count() > 1:
+            assert "reads [" in r.stderr.decode()          # the shares were really spread
+
+
+def test_bad_device_list_fails_loudly():
+    with tempfile.TemporaryDirectory() as tmp:
+        fa, fq, _ = synth.materialise("tiny", tmp)
+        r = subprocess.run([GC, fa, fq, "1", "out"], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120,
+                           env=dict(os.environ, GC_DEVICES="0;1"))
+        assert r.returncode != 0 and b"GC_DEVICES" in r.stderr
+        r = subprocess.run([GC, fa, fq, "1", "out"], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120,
+                           env=dict(os.environ, GC_DEVICES="0,99"))
+        assert r.returncode != 0 and b"cannot open CUDA device 99" in r.stderr
+
+
+def test_replicas_and_merged_statistics():
+    """gcg_table_clone / gcg_table_merge_ont: reads split over 1..4 contexts (all devices of the box in
+    turn) give the anchors and the statistics of one search; a second batch keeps adding up; a table
+    that is not a clone is refused"""
+    import numpy as np
+    from superplus_b200 import api
+    inp = synth.make_config("small")
+    reads = inp.reads[:40] + [np.zeros(0, np.uint8), inp.reads[3][:24]] + inp.reads[40:]
+    ndev = _device_count()
+    ctx0 = api.Context(0)
+    cs = ctx0.upload(inp.contigs)
+    t = ctx0.table_build(cs, 25)
+    want = ctx0.search_host(t, reads)
+    st1 = t.stats()
+    ctx0.search_host(t, reads[:30])
+    st2 = t.stats()
+    t.free()
+    assert st2[2] == st1[2] and st2[3] < st1[3]                       # same k-mers anchored, fewer of them exactly once
+    for n in (1, 2, 3, 4):
+        ctxs = [ctx0] + [api.Context(i % ndev) for i in range(1, n)]
+        t = ctx0.table_build(cs, 25)
+        rep = api.ReplicatedSearch(ctxs, t)
+        got = rep.search_host(reads)
+        assert np.array_equal(got, want), n
+        assert t.stats() == st1, n
+        again = rep.search_host(reads[:30])                            # counts move to the primary and keep adding up
+        assert np.array_equal(again, want[want["read"] < 30]), n
+        assert t.stats() == st2, n
+        if n > 1:
+            late = t.clone(ctxs[1])                                    # a clone starts with nothing collected
+            assert late.stats()[:2] == st2[:2] and late.stats()[2:] == (0, 0)
+            late.free()
+        rep.free(); t.free()
+        for c in ctxs[1:]:
+            c.close()
+    t = ctx0.table_build(cs, 25)
+    other = ctx0.table_build(ctx0.upload(inp.contigs[:1]), 25)
+    with pytest.raises(api.GcgError):
+        t.merge_ont(other)
+    with pytest.raises(api.GcgError):
+        t.merge_ont(t)
+    t.free(); other.free(); cs.free(); ctx0.close()
+
+
 def test_search_in_groups_matches_single_call():
     """gcg_search streams the reads through a three-slot pipeline in chunks of whole reads: the
     device-resident search, the default chunking and tiny chunks (many chunks, slot reuse, result

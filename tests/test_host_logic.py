@@ -141,3 +141,20 @@ def test_host_pack_2bit_matches_the_oracle_packing():
     for path in ("swar", "pext", "avx2"):       # a path the CPU lacks falls back to the default one
         out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GCG_HOST_PACK=path), capture_output=True, text=True, check=True).stdout
         assert [int(x) for x in out.strip().split(",")] == [int(x) for x in want(b)], path
+
+
+def test_split_reads_by_bases_covers_and_balances():
+    """the share boundaries of the multi-device search (api.ReplicatedSearch, gap_closer/ont.c)"""
+    from superplus_b200.api import split_reads_by_bases
+    rng = np.random.default_rng(5)
+    for n_reads in (0, 1, 2, 7, 100, 1000):
+        lens = rng.integers(0, 60000, size=n_reads)
+        for n in (1, 2, 3, 4, 8, 16):
+            b = split_reads_by_bases(lens, n)
+            assert len(b) == n + 1 and b[0] == 0 and b[-1] == n_reads
+            assert all(x <= y for x, y in zip(b, b[1:]))
+            if n_reads:
+                shares = [int(lens[b[i]:b[i + 1]].sum()) for i in range(n)]
+                assert sum(shares) == int(lens.sum())
+                # no share exceeds its fair part by more than one read
+                assert max(shares) <= -(-int(lens.sum()) // n) + int(lens.max())
