@@ -258,6 +258,15 @@ int  gcg_sw_batch (gcg_ctx * ctx, const gcg_sw_params * P, int mode,
                    const char * qry, const int64_t * qoff, const char * tgt, const int64_t * toff, int64_t n,
                    gcg_sw_result * results, uint32_t ** cigar_pool, int64_t * n_cigar_pool);
 
+/* the same batch sharded over several contexts, one per GPU of the box (pairs are
+ * independent): contiguous pair ranges of about equal qry_len x tgt_len, one host thread per
+ * context, no collective; results in input order, one pool (release with gcg_free).  What n
+ * aligners of the reference, one per core, would do with a list of pairs (sw_t is not shared
+ * between threads, sw.h:31-60). */
+int  gcg_sw_batch_multi (gcg_ctx * const * ctxs, int n_ctx, const gcg_sw_params * P, int mode,
+                         const char * qry, const int64_t * qoff, const char * tgt, const int64_t * toff, int64_t n,
+                         gcg_sw_result * results, uint32_t ** cigar_pool, int64_t * n_cigar_pool);
+
 /* device-resident form: upload once, align many times (bench `value`), download results */
 int  gcg_swbatch_upload (gcg_ctx * ctx, const char * qry, const int64_t * qoff, const char * tgt,
                          const int64_t * toff, int64_t n, gcg_swbatch ** out);

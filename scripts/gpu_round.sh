@@ -38,6 +38,9 @@ ncu --set full --clock-control none --import-source on -k regex:k45_search -s 2 
 echo "ncu k45 rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:hits_emit -s 2 -c 1 -o $O/prof_emit_$TAG -f $KCMD > $O/ncu_emit.log 2>&1
 echo "ncu emit rc=$?"
+# the counting kernel: atomicCAS claims + atomicOr flags into the HBM table (atomic throughput, north star)
+ncu --set full --clock-control none --import-source on -k regex:k23_build -s 2 -c 1 -o $O/prof_k23_$TAG -f $KCMD > $O/ncu_k23.log 2>&1
+echo "ncu k23 rc=$?"
 SCMD="python scripts/perf_sw.py 5920 0 1"
 $SCMD > $O/plain_sw.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:sw_fill_packed -c 1 -o $O/prof_sw_packed_$TAG -f $SCMD > $O/ncu_sw.log 2>&1

@@ -32,6 +32,15 @@ KEY_METRICS = [
     "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
     "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "smsp__warp_issue_stalled_not_selected_per_warp_active.pct",
     "smsp__warp_issue_stalled_wait_per_warp_active.pct",
+    # atomics (table build: atomicCAS claims, atomicOr flags; emit: the ONT-count atomicOr)
+    "l1tex__t_requests_pipe_lsu_mem_global_op_atom.sum", "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_atom.sum",
+    "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_atom.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum",
+    "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum",
+    "lts__t_requests_srcunit_tex_op_atom_dot_alu.sum", "lts__t_requests_srcunit_tex_op_atom_dot_cas.sum", "lts__t_requests_srcunit_tex_op_red.sum",
+    "lts__t_sectors_srcunit_tex_op_atom.sum", "lts__t_sectors_srcunit_tex_op_atom.sum.per_second",
+    "lts__t_sectors_srcunit_tex_op_atom.sum.pct_of_peak_sustained_elapsed",
+    "lts__t_sectors_srcunit_tex_op_atom_dot_cas.sum", "lts__t_sectors_srcunit_tex_op_atom_dot_cas.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sectors_srcunit_tex_op_red.sum", "lts__t_sectors_srcunit_tex_op_red.sum.per_second",
 ]
 
 
@@ -60,6 +69,10 @@ def sheet(rep, title, fh):
         dur_us = float(k["gpu__time_duration.sum"][0].replace(",", "")) * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}.get(k["gpu__time_duration.sum"][1], 1)
         fh.write("  -> DRAM traffic per launch %.1f MB (read %.1f + write %.1f) ; %.1f GB/s under the profiler's cold-cache replay\n" %
                  ((rd + wr) / 1e6, rd / 1e6, wr / 1e6, (rd + wr) / dur_us / 1e3))
+        atom = sum(float(k[m][0].replace(",", "")) for m in ("l1tex__m_l1tex2xbar_write_sectors_mem_global_op_atom.sum",
+                                                              "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum") if m in k)
+        if atom:
+            fh.write("  -> global atomic / reduction sectors sent to the L2: %.2f M per launch, %.1f G sectors/s\n" % (atom / 1e6, atom / dur_us / 1e3))
         traffic[short] = rd + wr
     return traffic
 

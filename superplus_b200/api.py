@@ -30,7 +30,7 @@ EXPORTS = [
     "gcg_chop_contigs", "gcg_table_build_seqs", "gcg_table_build", "gcg_table_free", "gcg_table_stats",
     "gcg_table_size", "gcg_table_dump", "gcg_table_clone", "gcg_table_merge_ont",
     "gcg_search_seqs", "gcg_hits_count", "gcg_hits_download", "gcg_hits_free", "gcg_search", "gcg_free",
-    "gcg_sw_batch", "gcg_swbatch_upload", "gcg_swbatch_align", "gcg_swbatch_download", "gcg_swbatch_cells",
+    "gcg_sw_batch", "gcg_sw_batch_multi", "gcg_swbatch_upload", "gcg_swbatch_align", "gcg_swbatch_download", "gcg_swbatch_cells",
     "gcg_swbatch_path_counts", "gcg_swbatch_free",
     "gcg_kmer_owner", "gcg_seqs_tiles", "gcg_route_plan", "gcg_route_kmers", "gcg_route_keys", "gcg_route_records",
     "gcg_route_collect", "gcg_route_free", "gcg_table_create", "gcg_table_insert_records", "gcg_table_lookup_keys",
@@ -149,6 +149,7 @@ def load_library(path: str = LIB_PATH):
     L.gcg_search.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(i64)]
     L.gcg_free.argtypes = [vp]
     L.gcg_sw_batch.argtypes = [vp, C.POINTER(SWParams), C.c_int, vp, vp, vp, vp, i64, vp, C.POINTER(vp), C.POINTER(i64)]
+    L.gcg_sw_batch_multi.argtypes = [vp, C.c_int, C.POINTER(SWParams), C.c_int, vp, vp, vp, vp, i64, vp, C.POINTER(vp), C.POINTER(i64)]
     L.gcg_swbatch_upload.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(vp)]
     L.gcg_swbatch_align.argtypes = [vp, vp, C.POINTER(SWParams), C.c_int]
     L.gcg_swbatch_download.argtypes = [vp, vp, vp, C.POINTER(vp), C.POINTER(i64)]
@@ -402,6 +403,26 @@ class Context:
         npool = C.c_int64()
         self._chk(self.L.gcg_sw_batch(self.h, C.byref(P), mode, qbuf.ctypes.data, qoff.ctypes.data, tbuf.ctypes.data,
                                       toff.ctypes.data, n, res.ctypes.data, C.byref(pool), C.byref(npool)))
+        try:
+            cp = np.frombuffer((C.c_char * (npool.value * 4)).from_address(pool.value), dtype=np.uint32).copy() if npool.value else np.zeros(0, np.uint32)
+        finally:
+            self.L.gcg_free(pool)
+        cigs = [cp[int(r["cigar_off"]):int(r["cigar_off"]) + int(r["n_cigar"])] for r in res]
+        return res, cigs
+
+    def sw_batch_multi(self, others, P: SWParams, qrys, tgts, mode: int = SW_ASIS):
+        """the same batch sharded over this context and `others` (one per GPU): contiguous pair ranges of
+        about equal cells, one host thread per context (gcg_sw_batch_multi)"""
+        qbuf, qoff = _concat(qrys)
+        tbuf, toff = _concat(tgts)
+        n = len(qrys)
+        res = np.zeros(n, dtype=SWRES_DTYPE)
+        pool = C.c_void_p()
+        npool = C.c_int64()
+        ctxs = [self] + list(others)
+        arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        self._chk(self.L.gcg_sw_batch_multi(C.cast(arr, C.c_void_p), len(ctxs), C.byref(P), mode, qbuf.ctypes.data, qoff.ctypes.data,
+                                            tbuf.ctypes.data, toff.ctypes.data, n, res.ctypes.data, C.byref(pool), C.byref(npool)))
         try:
             cp = np.frombuffer((C.c_char * (npool.value * 4)).from_address(pool.value), dtype=np.uint32).copy() if npool.value else np.zeros(0, np.uint32)
         finally:

@@ -42,23 +42,77 @@ k1_pack_kernel (const uint4 * __restrict__ ascii, uint64_t * __restrict__ packed
 // One thread per k-mer start position (lane j of a warp takes position j of the warp's word): the
 // inserts of a word are independent chains of load -> CAS -> store, so they are spread over the
 // lanes instead of being walked by one thread (a 4.6 Mb scaffold is only 144 k words).
-__global__ void __launch_bounds__ (256)
+// ILP > 1 (GCG_BUILD_ILP=2|4, an experiment kept for A/B timing, not the default): every thread carries
+// ILP such chains at once (words w, w + stride, ...) — the bucket loads are issued together, then the
+// claims, and only then is the first CAS result looked at; a chain that does not end with its first
+// claim (duplicate, lost slot, full bucket) falls back to the general probe loop table_insert.  ncu
+// (profiles/r01_ncu_summary.txt, k23) shows 87 % of the stall samples on the long scoreboard, most of
+// them behind the CAS, which suggested more inserts in flight; measured, it is the opposite — cfg2
+// 0.121 ms (ILP 1) -> 0.29 ms (2) -> 0.33 ms (4), cfg5s 1.45 -> 2.42 -> 2.94 ms: the kernel is not
+// short of parallelism, it is at the random-sector rate of the memory system (7.2 M DRAM sectors per
+// launch = 60 G sectors/s, above the 37-52 G/s the gather microbenchmark reaches on tables beyond the
+// L2; the 106 MB table does not stay L2 resident while it is being written: 56 % sector hits), and
+// more requests in flight only lengthen the queues and lose more claims.
+template <int ILP>
+__global__ void __launch_bounds__ (256, ILP == 1 ? 8 : ILP == 2 ? 6 : 4)
 k23_build_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff,
                   const int32_t * __restrict__ len, const int32_t * __restrict__ tile_seq, int64_t n_seq, int64_t n_words, int k,
                   unsigned long long * __restrict__ keys, unsigned long long * __restrict__ vals, uint32_t n_bucket)
 {
   const int lane = threadIdx.x & 31;
   const int64_t wstride = (int64_t) gridDim.x * (blockDim.x >> 5);
-  for (int64_t w = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_words; w += wstride) {
-    int64_t s = find_seq_from (woff, n_seq, w, __ldg (tile_seq + (w >> 5)));
-    int32_t L = __ldg (len + s);
-    int32_t p0 = (int32_t) ((w - __ldg (woff + s)) << 5);
-    int32_t nvalid = L - k + 1 - p0;             // number of valid starts in this word
-    if (lane >= nvalid) continue;
-    bool fw;
-    unsigned long long key = key_at (__ldg (packed + w), __ldg (packed + w + 1), lane, k, &fw);
-    unsigned long long val = ((unsigned long long) s << 32) | ((unsigned long long) (uint32_t) (p0 + lane) << 1) | (fw ? 0ULL : 1ULL);
-    table_insert (keys, vals, n_bucket, key, val);
+  for (int64_t w0 = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w0 < n_words; w0 += wstride * ILP) {
+    unsigned long long key[ILP], val[ILP];
+    uint32_t b[ILP];
+    int act[ILP];                                   // 0 nothing, 1 claim slot idx, 2 general loop
+    int idx[ILP];
+#pragma unroll
+    for (int u = 0; u < ILP; ++u) {
+      const int64_t w = w0 + u * wstride;
+      act[u] = 0; idx[u] = 0; key[u] = 0; val[u] = 0; b[u] = 0;
+      if (w < n_words) {
+        int64_t s = find_seq_from (woff, n_seq, w, __ldg (tile_seq + (w >> 5)));
+        int32_t L = __ldg (len + s);
+        int32_t p0 = (int32_t) ((w - __ldg (woff + s)) << 5);
+        int32_t nvalid = L - k + 1 - p0;             // number of valid starts in this word
+        if (lane < nvalid) {
+          bool fw;
+          key[u] = key_at (__ldg (packed + w), __ldg (packed + w + 1), lane, k, &fw);
+          val[u] = ((unsigned long long) s << 32) | ((unsigned long long) (uint32_t) (p0 + lane) << 1) | (fw ? 0ULL : 1ULL);
+          b[u] = __umulhi (kmer_hash32 (key[u] - 1ULL), n_bucket);
+          act[u] = 2;
+        }
+      }
+    }
+    if (ILP == 1) {
+      if (act[0]) table_insert (keys, vals, n_bucket, key[0], val[0]);
+      continue;
+    }
+    bucket4 q[ILP];
+#pragma unroll
+    for (int u = 0; u < ILP; ++u)
+      if (act[u]) q[u] = ld_bucket_cg (keys + 4ULL * b[u]);
+#pragma unroll
+    for (int u = 0; u < ILP; ++u) {
+      if (!act[u]) continue;
+      const unsigned long long cur[4] = {q[u].a, q[u].b, q[u].c, q[u].d};
+#pragma unroll
+      for (int i = 3; i >= 0; --i) {                // the FIRST empty slot or match decides (slots fill front to back)
+        if (cur[i] == 0ULL) { act[u] = 1; idx[u] = i; }
+        else if ((cur[i] & GCG_KEY_MASK) == key[u]) { act[u] = 2; idx[u] = i; }
+      }
+    }
+    unsigned long long old[ILP];
+#pragma unroll
+    for (int u = 0; u < ILP; ++u) {
+      old[u] = 1ULL;
+      if (act[u] == 1) old[u] = atomicCAS (keys + 4ULL * b[u] + idx[u], 0ULL, key[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < ILP; ++u) {
+      if (act[u] == 1 && old[u] == 0ULL) vals[4ULL * b[u] + idx[u]] = val[u];
+      else if (act[u]) table_insert (keys, vals, n_bucket, key[u], val[u]);      // duplicate, lost claim or full bucket
+    }
   }
 }
 
@@ -761,8 +815,14 @@ extern "C" int gcg_table_build_seqs (gcg_ctx * ctx, const gcg_seqs * contigs, in
   if (rc) return rc;
   if (contigs->n_words > 0 && n_kmers > 0) {
     gcg_kscope ks (ctx, "k23_build");
-    k23_build_kernel<<<grid_for (ctx, contigs->n_words * 32, 256, 8), 256, 0, ctx->stream>>> (
-        contigs->d_packed, contigs->d_woff, contigs->d_len, contigs->d_tseq, contigs->n, contigs->n_words, k, t->d_keys, t->d_vals, t->n_bucket);
+    // GCG_BUILD_ILP=1|2|4: inserts in flight per thread (A/B of the kernel variants; 1 is the default and the fastest)
+    static const int ilp = [] () { const char * e = getenv ("GCG_BUILD_ILP"); int v = e ? atoi (e) : 1; return v == 2 || v == 4 ? v : 1; } ();
+    const int grid = grid_for (ctx, contigs->n_words * 32, 256, 8);
+#define K23_ARGS contigs->d_packed, contigs->d_woff, contigs->d_len, contigs->d_tseq, contigs->n, contigs->n_words, k, t->d_keys, t->d_vals, t->n_bucket
+    if (ilp == 2) k23_build_kernel<2><<<grid, 256, 0, ctx->stream>>> (K23_ARGS);
+    else if (ilp == 4) k23_build_kernel<4><<<grid, 256, 0, ctx->stream>>> (K23_ARGS);
+    else k23_build_kernel<1><<<grid, 256, 0, ctx->stream>>> (K23_ARGS);
+#undef K23_ARGS
     GCG_CUDA (cudaGetLastError ());
   }
   *out = t;

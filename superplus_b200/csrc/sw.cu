@@ -32,6 +32,9 @@
 //   word[(band * (tlen+31) + step) * 32 + lane], nibble of column c at bit shift(c)
 #include <algorithm>
 #include <type_traits>
+#include <string>
+#include <thread>
+#include <vector>
 #include <limits.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1178,4 +1181,68 @@ extern "C" int gcg_sw_batch (gcg_ctx * ctx, const gcg_sw_params * P, int mode,
   gcg_trace_mark (ctx, "sw: results to host");
   gcg_swbatch_free (b);
   return rc;
+}
+
+// The same batch sharded over several contexts, one per GPU (SURVEY 8e, row SW: pairs are independent,
+// contiguous ranges of about equal cells, no collective, results in input order).  One host thread per
+// context runs the ordinary gcg_sw_batch on its range; the CIGAR pools are joined into one pinned
+// array and the offsets of the later ranges moved behind the earlier ones.
+extern "C" int gcg_sw_batch_multi (gcg_ctx * const * ctxs, int n_ctx, const gcg_sw_params * P, int mode,
+                                   const char * qry, const int64_t * qoff, const char * tgt, const int64_t * toff, int64_t n,
+                                   gcg_sw_result * results, uint32_t ** cigar_pool, int64_t * n_cigar_pool)
+{
+  GCG_CHECK (ctxs && n_ctx >= 1 && n_ctx <= 64 && P && qoff && toff && n >= 0 && results && cigar_pool && n_cigar_pool, GCG_EINVAL, "gcg_sw_batch_multi: bad argument");
+  for (int i = 0; i < n_ctx; ++i) GCG_CHECK (ctxs[i] != nullptr, GCG_EINVAL, "gcg_sw_batch_multi: context %d is NULL", i);
+  if (n_ctx == 1) return gcg_sw_batch (ctxs[0], P, mode, qry, qoff, tgt, toff, n, results, cigar_pool, n_cigar_pool);
+  // share d ends at the first pair where the running cell count reaches (d + 1) / n_ctx of the total
+  std::vector<long double> cum ((size_t) n + 1, 0.0L);
+  for (int64_t p = 0; p < n; ++p) cum[(size_t) p + 1] = cum[(size_t) p] + (long double) (qoff[p + 1] - qoff[p]) * (long double) (toff[p + 1] - toff[p]);
+  std::vector<int64_t> bound ((size_t) n_ctx + 1, n);
+  bound[0] = 0;
+  for (int d = 1; d < n_ctx; ++d) {
+    const long double goal = cum[(size_t) n] * d / n_ctx;
+    int64_t r = bound[(size_t) d - 1];
+    while (r < n && cum[(size_t) r] < goal) ++r;
+    bound[(size_t) d] = r;
+  }
+  struct share { int rc = GCG_OK; uint32_t * pool = nullptr; int64_t n_pool = 0; std::string err; };
+  std::vector<share> sh ((size_t) n_ctx);
+  std::vector<std::thread> th;
+  for (int d = 0; d < n_ctx; ++d) {
+    th.emplace_back ([&, d] () {
+      const int64_t b = bound[(size_t) d], m = bound[(size_t) d + 1] - b;
+      share & s = sh[(size_t) d];
+      if (m == 0) return;
+      std::vector<int64_t> qo ((size_t) m + 1), to ((size_t) m + 1);      // offsets counted from the share's first pair
+      for (int64_t p = 0; p <= m; ++p) { qo[(size_t) p] = qoff[b + p] - qoff[b]; to[(size_t) p] = toff[b + p] - toff[b]; }
+      s.rc = gcg_sw_batch (ctxs[d], P, mode, qry + qoff[b], qo.data (), tgt + toff[b], to.data (), m, results + b, &s.pool, &s.n_pool);
+      if (s.rc) s.err = gcg_last_error ();                                  // (the message is thread local)
+    });
+  }
+  for (auto & t : th) t.join ();
+  int rc = GCG_OK;
+  int64_t total = 0;
+  for (int d = 0; d < n_ctx; ++d) {
+    if (sh[(size_t) d].rc && !rc) { rc = sh[(size_t) d].rc; gcg_set_error ("gcg_sw_batch_multi: share %d (device %d): %s", d, ctxs[d]->device, sh[(size_t) d].err.c_str ()); }
+    total += sh[(size_t) d].n_pool;
+  }
+  uint32_t * pool = nullptr;
+  if (!rc) {
+    pool = (uint32_t *) gcg_pinned_alloc ((size_t) std::max<int64_t> (total, 1) * 4);
+    if (!pool) { gcg_set_error ("gcg_sw_batch_multi: pinned allocation of %lld CIGAR words failed", (long long) total); rc = GCG_ENOMEM; }
+  }
+  int64_t at = 0;
+  for (int d = 0; d < n_ctx; ++d) {
+    share & s = sh[(size_t) d];
+    if (!rc && s.n_pool > 0) {
+      memcpy (pool + at, s.pool, (size_t) s.n_pool * 4);
+      for (int64_t p = bound[(size_t) d]; p < bound[(size_t) d + 1]; ++p) results[p].cigar_off += at;
+      at += s.n_pool;
+    }
+    if (s.pool) gcg_free (s.pool);
+  }
+  if (rc) return rc;
+  *cigar_pool = pool;
+  *n_cigar_pool = total;
+  return GCG_OK;
 }

@@ -159,7 +159,11 @@ sw_align_batch (sw_t * sw, int64_t n, const char * qry, const int64_t * qoff, co
   }
   track_growth (sw, max_q, max_t);
   fill_params (sw, &P);
-  GCG_CK (gcg_sw_batch (br->ctx, &P, traceback_mode (), qry, qoff, tgt, toff, n, results, cigar_pool, n_cigar_pool));
+  /* GC_DEVICES: the pairs are sharded over the devices of the bridge (contiguous ranges of equal cells) */
+  if (br->n_dev > 1)
+    GCG_CK (gcg_sw_batch_multi (br->ctxs, br->n_dev, &P, traceback_mode (), qry, qoff, tgt, toff, n, results, cigar_pool, n_cigar_pool));
+  else
+    GCG_CK (gcg_sw_batch (br->ctx, &P, traceback_mode (), qry, qoff, tgt, toff, n, results, cigar_pool, n_cigar_pool));
   return 0;
 }
 

@@ -81,3 +81,21 @@ def test_call_sequences_keep_reference_border_state(shim, mode):
             assert align(shim, sw, st["q"], st["t"]) == st[mode]
         shim.sw_free(sw)
     shim.sw_set_traceback_mode(0)
+
+
+@pytest.mark.parametrize("devices", [None, "0,0", "0,0,0", "all"])
+def test_batch_entry_point_matches_single_calls(devices):
+    """sw_align_batch (sw_batch.h) against sw_align pair by pair on the same aligner; with GC_DEVICES the
+    pairs are sharded over several contexts (gcg_sw_batch_multi) — a fresh process per setting, the
+    bridge reads the variable once"""
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    env.pop("GC_DEVICES", None)
+    if devices:
+        env["GC_DEVICES"] = devices
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "shim_batch_driver.py"), "3"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    out = json.loads(r.stdout.decode().strip().splitlines()[-1])
+    assert len(out["single"]) == 37 and out["batch"] == out["single"]

@@ -251,3 +251,33 @@ def test_symbol_out_of_alphabet_is_rejected(ctx):
     P = api.make_sw_params(api.default_mat(4))
     with pytest.raises(api.GcgError):
         ctx.sw_batch(P, [np.array([0, 4, 1], np.uint8)], [np.array([0, 1], np.uint8)])
+
+
+@pytest.mark.parametrize("n_ctx", [2, 3, 5])
+def test_batch_sharded_over_contexts(ctx, n_ctx):
+    """gcg_sw_batch_multi: contiguous pair ranges of about equal cells on several contexts (every GPU of
+    the box in turn; on a one-GPU box several contexts of that GPU) give exactly the results and CIGARs
+    of one gcg_sw_batch call; empty shares (fewer pairs than contexts, a batch of nothing) included"""
+    ndev = int(api.load_library().gcg_device_count())
+    others = [api.Context(i % ndev) for i in range(1, n_ctx)]
+    try:
+        rng = np.random.default_rng(77 + n_ctx)
+        qs, ts = random_pairs(rng, 41, 300, 200)
+        qs[5], ts[5] = np.zeros(0, np.uint8), ts[5]                      # an empty query inside a share
+        q3, t3 = synth.make_sw_pairs(3, 3000, 700, seed=5)               # a few heavy pairs shift the boundaries
+        qs += list(q3); ts += list(t3)
+        for P in (api.make_sw_params(), api.make_sw_params(strategy=1), api.make_sw_params(api.default_mat(5, 2, -3), 4, 2, 3, 1)):
+            for mode in (api.SW_ASIS, api.SW_FIXED):
+                want_res, want_cig = ctx.sw_batch(P, qs, ts, mode)
+                got_res, got_cig = ctx.sw_batch_multi(others, P, qs, ts, mode)
+                for f in ("score", "alignment_offset", "has_softclip", "bt_tidx", "bt_qidx", "n_cigar"):
+                    assert np.array_equal(got_res[f], want_res[f]), f
+                assert all(np.array_equal(a, b) for a, b in zip(got_cig, want_cig))
+        P = api.make_sw_params()
+        for m in (0, 1, n_ctx - 1):
+            want_res, want_cig = ctx.sw_batch(P, qs[:m], ts[:m])
+            got_res, got_cig = ctx.sw_batch_multi(others, P, qs[:m], ts[:m])
+            assert np.array_equal(got_res["score"], want_res["score"]) and all(np.array_equal(a, b) for a, b in zip(got_cig, want_cig))
+    finally:
+        for c in others:
+            c.close()
