@@ -13,7 +13,12 @@
  *     thread-local message.  (Reference behaviour is err_mesg -> abort, utils.c:217-230; the
  *     shims turn a non-zero return into err_mesg.)
  *   - one gcg_ctx per process and device; calls on one ctx are serialised by the caller
- *     (the reference API is not thread safe either, hash.h:13-15)
+ *     (the reference API is not thread safe either, hash.h:13-15).  Contexts of DIFFERENT devices
+ *     may be driven from different host threads at the same time (gcg_table_clone /
+ *     gcg_sw_batch_multi do so).  Several contexts on ONE device work (the tests use them to
+ *     exercise the multi-device paths on a one-GPU box) with one restriction: the SW scoring
+ *     parameters live in that device's constant memory, so such contexts must not run SW batches
+ *     with different gcg_sw_params concurrently.
  *   - input sequences are borrowed for the duration of the call; outputs returned through
  *     `**` are owned by the library and released with the matching *_free
  *   - there is NO CPU fallback: without a CUDA device gcg_init fails

@@ -17,6 +17,8 @@
 #include <functional>
 #include <thread>
 
+#include <mutex>
+
 #include "gcg_internal.cuh"
 #include "host_par.h"
 #include "kmer_dev.cuh"
@@ -1480,10 +1482,12 @@ extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * re
 }
 
 // ---- contig chop to host kmer_t arrays --------------------------------------------------------
-static bool g_crc_ready = false;
-static int crc_table_upload ()
+static std::mutex g_crc_mu;
+static uint64_t g_crc_ready = 0;                  // bit d: device d holds the table (__constant__ memory is per device)
+static int crc_table_upload (int device)
 {
-  if (g_crc_ready) return GCG_OK;
+  std::lock_guard<std::mutex> lk (g_crc_mu);
+  if (device < 64 && (g_crc_ready >> device & 1)) return GCG_OK;
   uint32_t tbl[256];
   for (uint32_t i = 0; i < 256; ++i) {          // reflected CRC-32, polynomial 0xEDB88320 (== crc32.h:15-68)
     uint32_t c = i;
@@ -1491,7 +1495,7 @@ static int crc_table_upload ()
     tbl[i] = c;
   }
   GCG_CUDA (cudaMemcpyToSymbol (c_crc_table, tbl, sizeof tbl));
-  g_crc_ready = true;
+  if (device < 64) g_crc_ready |= 1ULL << device;
   return GCG_OK;
 }
 
@@ -1501,7 +1505,7 @@ extern "C" int gcg_chop_contigs (gcg_ctx * ctx, const gcg_seqs * contigs, int k,
   GCG_CHECK (ctx && contigs && kmers_out && n_kmer_out, GCG_EINVAL, "gcg_chop_contigs: bad argument");
   GCG_CHECK (k >= 1 && k <= 31 && n_thread >= 1, GCG_ERANGE, "gcg_chop_contigs: k=%d n_thread=%d out of range", k, n_thread);
   GCG_CUDA (cudaSetDevice (ctx->device));
-  int rc = crc_table_upload ();
+  int rc = crc_table_upload (ctx->device);
   if (rc) return rc;
   int64_t n = contigs->n;
   std::vector<int64_t> koff ((size_t) n + 1);
