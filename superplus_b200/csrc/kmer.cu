@@ -393,34 +393,37 @@ hits_emit_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
 // =============================================================================================
 // K6  statistics
 // =============================================================================================
+// A thread takes a whole bucket per step: the four key words as one 256-bit load and, when the bucket
+// holds a key that is present once, its four value words as another (n_slot is a multiple of 4, both
+// arrays are 32-byte aligned).  One 8-byte load per thread and step ran at 1.8 TB/s (0.059 ms at cfg2).
 __global__ void __launch_bounds__ (256)
 k6_stats_kernel (const unsigned long long * __restrict__ keys, const unsigned long long * __restrict__ vals, uint64_t n_slot,
                  unsigned long long * __restrict__ out4)
 {
-  unsigned long long total = 0, uniq = 0, ot = 0, ou = 0;
-  int64_t stride = (int64_t) gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t) n_slot; i += stride) {
-    unsigned long long kw = keys[i];
-    if (kw & GCG_KEY_MASK) {
-      ++total;
-      if (!(kw & GCG_KEY_MULTI)) {
-        ++uniq;
-        const unsigned long long v = vals[i];         // (only keys present once can anchor)
-        if (v & GCG_VAL_ONT1) { ++ot; if (!(v & GCG_VAL_ONT2)) ++ou; }
-      }
+  unsigned int total = 0, uniq = 0, ot = 0, ou = 0;          // per thread: at most 4 per step, far below 2^32
+  const int64_t n_bucket = (int64_t) (n_slot >> 2), stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; b < n_bucket; b += stride) {
+    const bucket4 q = ld_bucket (keys + 4 * b);
+    const unsigned long long kw[4] = {q.a, q.b, q.c, q.d};
+    unsigned int once = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (kw[i] & GCG_KEY_MASK) { ++total; if (!(kw[i] & GCG_KEY_MULTI)) once |= 1u << i; }
+    if (once) {
+      uniq += __popc (once);
+      const bucket4 v = ld_bucket (vals + 4 * b);          // (only keys present once can anchor)
+      const unsigned long long vw[4] = {v.a, v.b, v.c, v.d};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if ((once >> i & 1u) && (vw[i] & GCG_VAL_ONT1)) { ++ot; if (!(vw[i] & GCG_VAL_ONT2)) ++ou; }
     }
   }
-  for (int o = 16; o; o >>= 1) {
-    total += __shfl_down_sync (0xffffffffu, total, o);
-    uniq += __shfl_down_sync (0xffffffffu, uniq, o);
-    ot += __shfl_down_sync (0xffffffffu, ot, o);
-    ou += __shfl_down_sync (0xffffffffu, ou, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    if (total) atomicAdd (out4 + 0, total);
-    if (uniq) atomicAdd (out4 + 1, uniq);
-    if (ot) atomicAdd (out4 + 2, ot);
-    if (ou) atomicAdd (out4 + 3, ou);
+  unsigned long long t4[4] = {total, uniq, ot, ou};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    unsigned long long x = t4[c];
+    for (int o = 16; o; o >>= 1) x += __shfl_down_sync (0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0 && x) atomicAdd (out4 + c, x);
   }
 }
 
