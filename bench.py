@@ -391,7 +391,7 @@ def run_ours(args, rank, local_rank, world):
 
     sw_paths = list(swb.path_counts())
     swb.free()                                     # the resident batch holds up to 64 GB of trace scratch: give it back first
-    sw_e2e_pairs = min(sw_pairs, 2960 * 8)
+    sw_e2e_pairs = sw_pairs                         # the same batch as the device-resident leg, from host buffers
     qe, te = q2[:sw_e2e_pairs], t2[:sw_e2e_pairs]
     e2e_sw_steps = 3
     barrier()
