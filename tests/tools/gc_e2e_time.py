@@ -1,11 +1,11 @@
 """Wall-clock of the whole gap_closer CLI on one config: reference gc (oracle/_ref, host cores) vs
 gc_b200 (same callers + the CUDA path), outputs compared by md5, stdout lines time-stamped through
-a pty so that the phases the CLI does not time itself show up.  usage: gc_e2e_time.py cfg2 [threads] [devices]
+a pty so that the phases the CLI does not time itself show up.  usage: tests/tools/gc_e2e_time.py cfg2 [threads] [devices]
 (devices, e.g. 0,1: one more gc_b200 run with GC_DEVICES set — the reads sharded over those GPUs)"""
 import hashlib, os, pty, select, subprocess, sys, tempfile, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from superplus_b200 import synth
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 nt = sys.argv[2] if len(sys.argv) > 2 else str(os.cpu_count())
 md5 = lambda p: hashlib.md5(open(p, "rb").read()).hexdigest()
