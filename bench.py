@@ -426,7 +426,9 @@ def run_ours(args, rank, local_rank, world):
     peak_gbs, peak_src = measured_peaks()
     k45_ms = kprof.get("k45_search", (0.0, 1))
     k45_avg = k45_ms[0] / max(1, k45_ms[1])
-    alg_bytes = BYTES_PER_LOOKUP * n_ont_kmers + BYTES_PER_HIT * n_hit
+    # the search probes the reads as two halves (two launches per step): bytes per launch = the step's share
+    k45_per_step = max(1.0, k45_ms[1] / max(1, args.steps))
+    alg_bytes = (BYTES_PER_LOOKUP * n_ont_kmers + BYTES_PER_HIT * n_hit) / k45_per_step
     achieved = alg_bytes / (k45_avg * 1e-3) / 1e9 if k45_avg > 0 else 0.0
     fill = sprof.get("k7_sw_fill_packed", (0.0, 1))
     fill_gcups = sw_cells / (fill[0] / args.steps * 1e-3) / 1e9 if fill[0] > 0 else 0.0

@@ -62,6 +62,7 @@ struct gcg_ctx {
   // small device scratch for reductions / counters
   unsigned long long * d_counters = nullptr;   // 64 x u64 ([16..48) = per-partition totals of gcg_route_plan)
   unsigned long long * h_counters = nullptr;   // pinned mirror
+  cudaEvent_t ev_split[2] = {nullptr, nullptr};  // "count of half A / B has landed" (gcg_search_seqs), created on first use
   // parked device blocks by size class (see gcg_dmalloc)
   std::map<size_t, std::vector<void *>> dparked;
   std::unordered_map<void *, size_t> dclass;   // every block handed out or parked -> its class size

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__ (32 * K4_WARPS)
 k45_search_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff,
                    const int32_t * __restrict__ len, const int32_t * __restrict__ tile_seq, int64_t n_seq, int64_t n_words, const int k_arg,
                    const unsigned long long * __restrict__ keys, uint32_t n_bucket, uint32_t * __restrict__ hitmask,
-                   const uint32_t * __restrict__ filter, uint32_t filter_words, int filter_k3)
+                   const uint32_t * __restrict__ filter, uint32_t filter_words, int filter_k3, const int64_t tile0)
 {
   __shared__ uint32_t s_excl[K4_WARPS][33];
   __shared__ uint32_t s_pend[K4_WARPS][32];
@@ -158,7 +158,7 @@ k45_search_kernel (const uint64_t * __restrict__ packed, const int64_t * __restr
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t n_tiles = (n_words + 31) >> 5;
   const int64_t wstride = (int64_t) gridDim.x * K4_WARPS;
-  for (int64_t tile = (int64_t) blockIdx.x * K4_WARPS + wid; tile < n_tiles; tile += wstride) {
+  for (int64_t tile = tile0 + (int64_t) blockIdx.x * K4_WARPS + wid; tile < n_tiles; tile += wstride) {   // tiles [tile0, n_tiles)
     const int64_t w = (tile << 5) + lane;
     uint32_t mymask = 0, pend = 0;
     int nvalid = 0;
@@ -334,7 +334,7 @@ hits_emit_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
                   int64_t n_seq, int64_t n_words, int k, const unsigned long long * __restrict__ keys,
                   unsigned long long * __restrict__ vals, uint32_t n_bucket,
                   const uint32_t * __restrict__ mask, const uint32_t * __restrict__ prefix, int32_t read_base,
-                  gcg_hit * __restrict__ out)
+                  gcg_hit * __restrict__ out, const int64_t tile0)
 {
   __shared__ uint32_t s_excl[8][33];
   __shared__ uint32_t s_mask[8][32];
@@ -342,7 +342,7 @@ hits_emit_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int64_t n_tiles = (n_words + 31) >> 5;
   int64_t wstride = (int64_t) gridDim.x * (blockDim.x >> 5);
-  for (int64_t tile = (int64_t) blockIdx.x * (blockDim.x >> 5) + wid; tile < n_tiles; tile += wstride) {
+  for (int64_t tile = tile0 + (int64_t) blockIdx.x * (blockDim.x >> 5) + wid; tile < n_tiles; tile += wstride) {   // tiles [tile0, n_tiles)
     int64_t w = (tile << 5) + lane;
     uint32_t m = w < n_words ? mask[w] : 0;
     uint32_t c = __popc (m), x = c;
@@ -1055,16 +1055,17 @@ extern "C" int gcg_filter_or (gcg_ctx * ctx, void * d_words, const void * d_othe
   return GCG_OK;
 }
 
+// probes the words of the tiles [tile0, ceil(n_words / 32)); masks, woff and tile hints are indexed by the global word / tile
 static void launch_k45 (gcg_ctx * ctx, const gcg_table * t, const uint64_t * d_packed, const int64_t * d_woff, const int32_t * d_len,
-                        const int32_t * d_tseq, int64_t n_seq, int64_t n_words, int k, uint32_t * d_mask)
+                        const int32_t * d_tseq, int64_t n_seq, int64_t n_words, int k, uint32_t * d_mask, int64_t tile0 = 0)
 {
   gcg_kscope ks (ctx, "k45_search");
-  const int grid = grid_for (ctx, ((n_words + 31) >> 5) * 32, 32 * K4_WARPS, 8);
+  const int grid = grid_for (ctx, (((n_words + 31) >> 5) - tile0) * 32, 32 * K4_WARPS, 8);
   const bool flt = t->filter_valid && t->filter_words;
   auto fn = flt ? (k == 25 ? k45_search_kernel<true, 25> : k == 31 ? k45_search_kernel<true, 31> : k45_search_kernel<true, 0>)
                 : (k == 25 ? k45_search_kernel<false, 25> : k == 31 ? k45_search_kernel<false, 31> : k45_search_kernel<false, 0>);
   fn<<<grid, 32 * K4_WARPS, 0, ctx->stream>>> (d_packed, d_woff, d_len, d_tseq, n_seq, n_words, k, t->d_keys, t->n_bucket, d_mask,
-                                              flt ? t->d_filter : nullptr, flt ? t->filter_words : 0u, flt ? t->filter_k3 : 0);
+                                              flt ? t->d_filter : nullptr, flt ? t->filter_words : 0u, flt ? t->filter_k3 : 0, tile0);
 }
 
 // ---- search -----------------------------------------------------------------------------------
@@ -1132,29 +1133,83 @@ extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * r
     gcg_set_error ("gcg_search: cudaMalloc failed: %s", cudaGetErrorString (e));
     rc = GCG_ENOMEM;
   }
+  // GCG_SEARCH_SPLIT=1 (an experiment kept behind a switch, off by default): two halves (tiles [0, T/2)
+  // and [T/2, T)), so that the host fetches one half's anchor count — which sizes the anchor buffer —
+  // while the GPU works on the other.  Queue order: probe A, scan A, count A -> host | probe B, scan B,
+  // count B -> host; the host picks up count A while probe B runs, launches emit A, and picks up count
+  // B while emit A runs.  The buffer is sized from count A with B estimated pro rata (+25 %); if B does
+  // not fit, a larger buffer takes over A's anchors first.  Measured on cfg2 (bench step): 1.206 ms in
+  // one pass, 1.278 ms in two halves — the tails of twice as many probe / scan / emit launches cost
+  // 0.053 ms of kernel time and the hidden round trip returned none of it, so the single pass stays.
+  const int64_t n_tiles = (n_words + 31) >> 5;
+  // (test hooks, read per call: GCG_SEARCH_SPLIT_MIN_TILES lowers the size from which the split is used,
+  //  GCG_SEARCH_SPLIT_TIGHT=1 sizes the buffer for half A only, so that half B always takes the regrow path)
+  const char * e_split = getenv ("GCG_SEARCH_SPLIT"), * e_min = getenv ("GCG_SEARCH_SPLIT_MIN_TILES"), * e_tight = getenv ("GCG_SEARCH_SPLIT_TIGHT");
+  const int64_t min_tiles = e_min ? std::max (2, atoi (e_min)) : 4096;
+  const bool split = e_split && atoi (e_split) == 1 && n_tiles >= min_tiles;
+  const int64_t tileA = split ? n_tiles / 2 : n_tiles, wordsA = split ? tileA << 5 : n_words;
+  auto emit = [&] (int64_t tile0, int64_t words_end, gcg_hit * dst) {
+    gcg_kscope ks (ctx, "hits_emit");
+    hits_emit_kernel<<<grid_for (ctx, (((words_end + 31) >> 5) - tile0) * 32, 256, 8), 256, 0, ctx->stream>>> (
+        reads->d_packed, reads->d_woff, reads->d_tseq, reads->n, words_end, k, t->d_keys, t->d_vals, t->n_bucket, d_mask, d_prefix, 0, dst, tile0);
+  };
   while (!rc) {
     if ((rc = gcg_table_filter_ensure (ctx, t)) != 0) break;
-    launch_k45 (ctx, t, reads->d_packed, reads->d_woff, reads->d_len, reads->d_tseq, reads->n, n_words, k, d_mask);
-    if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_search: kernel launch failed"); rc = GCG_ECUDA; break; }
-    int64_t n_hit = 0;
-    gcg_trace_mark (ctx, "  search_seqs: alloc + launch");
-    if ((rc = gcg_mask_scan (ctx, d_mask, n_words, d_prefix, d_bsum, &n_hit)) != 0) break;
-    gcg_trace_mark (ctx, "  search_seqs: probe + scan");
-    h->n = n_hit;
-    if (n_hit > 0) {
-      if ((e = gcg_dmalloc (ctx, &h->d_hits, (size_t) n_hit * sizeof (gcg_hit))) != cudaSuccess) {
-        gcg_set_error ("gcg_search: cudaMalloc of %lld anchors failed: %s", (long long) n_hit, cudaGetErrorString (e));
-        rc = GCG_ENOMEM;
-        break;
-      }
-      { gcg_kscope ks (ctx, "hits_emit");
-        hits_emit_kernel<<<grid_for (ctx, ((n_words + 31) >> 5) * 32, 256, 8), 256, 0, ctx->stream>>> (
-            reads->d_packed, reads->d_woff, reads->d_tseq, reads->n, n_words, k, t->d_keys, t->d_vals, t->n_bucket, d_mask, d_prefix, 0, h->d_hits); }
-      gcg_trace_mark (ctx, "  search_seqs: hits alloc");
-      // no wait for the emit kernel: the anchors stay on the device and everything that reads them
-      // (download, statistics, the next search) is ordered behind it on the context's stream
-      if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_search: emit launch failed"); rc = GCG_ECUDA; }
+    if (split && (!ctx->ev_split[0] || !ctx->ev_split[1])) {
+      if (cudaEventCreateWithFlags (&ctx->ev_split[0], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags (&ctx->ev_split[1], cudaEventDisableTiming) != cudaSuccess) { gcg_set_error ("gcg_search: cudaEventCreate failed"); rc = GCG_ECUDA; break; }
     }
+    // ---- queue both halves' probes and prefix sums
+    launch_k45 (ctx, t, reads->d_packed, reads->d_woff, reads->d_len, reads->d_tseq, reads->n, wordsA, k, d_mask, 0);
+    if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_search: kernel launch failed"); rc = GCG_ECUDA; break; }
+    if ((rc = mask_scan_launch (ctx, d_mask, wordsA, d_prefix, d_bsum, ctx->d_counters + 4)) != 0) break;
+    if (cudaMemcpyAsync (ctx->h_counters + 4, ctx->d_counters + 4, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_search: count copy failed"); rc = GCG_ECUDA; break; }
+    if (split) {
+      cudaEventRecord (ctx->ev_split[0], ctx->stream);
+      launch_k45 (ctx, t, reads->d_packed, reads->d_woff, reads->d_len, reads->d_tseq, reads->n, n_words, k, d_mask, tileA);
+      if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_search: kernel launch failed"); rc = GCG_ECUDA; break; }
+      // (the block-sum scratch is free again: scan A has finished with it before scan B starts, same stream)
+      if ((rc = mask_scan_launch (ctx, d_mask + wordsA, n_words - wordsA, d_prefix + wordsA, d_bsum, ctx->d_counters + 5)) != 0) break;
+      if (cudaMemcpyAsync (ctx->h_counters + 5, ctx->d_counters + 5, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_search: count copy failed"); rc = GCG_ECUDA; break; }
+      cudaEventRecord (ctx->ev_split[1], ctx->stream);
+    }
+    gcg_trace_mark (ctx, "  search_seqs: alloc + launch");
+    // ---- count A (probe B is running), buffer, emit A
+    if ((split ? cudaEventSynchronize (ctx->ev_split[0]) : cudaStreamSynchronize (ctx->stream)) != cudaSuccess) { gcg_set_error ("gcg_search: probe / scan failed: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; break; }
+    const int64_t nA = (int64_t) ctx->h_counters[4];
+    int64_t cap = nA;
+    if (split && !(e_tight && atoi (e_tight) == 1)) cap = nA + (int64_t) ((double) nA * (double) (n_words - wordsA) / (double) wordsA * 1.25) + 4096;
+    if (cap > 0 && (e = gcg_dmalloc (ctx, &h->d_hits, (size_t) cap * sizeof (gcg_hit))) != cudaSuccess) {
+      gcg_set_error ("gcg_search: cudaMalloc of %lld anchors failed: %s", (long long) cap, cudaGetErrorString (e));
+      rc = GCG_ENOMEM;
+      break;
+    }
+    if (nA > 0) emit (0, wordsA, h->d_hits);
+    h->n = nA;
+    // ---- count B (emit A is running), emit B behind A's anchors
+    if (split) {
+      if (cudaEventSynchronize (ctx->ev_split[1]) != cudaSuccess) { gcg_set_error ("gcg_search: probe / scan failed: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; break; }
+      const int64_t nB = (int64_t) ctx->h_counters[5];
+      if (nA + nB > cap) {                              // the estimate was too small: a larger buffer takes over A's anchors
+        gcg_hit * bigger = nullptr;
+        if ((e = gcg_dmalloc (ctx, &bigger, (size_t) (nA + nB) * sizeof (gcg_hit))) != cudaSuccess) {
+          gcg_set_error ("gcg_search: cudaMalloc of %lld anchors failed: %s", (long long) (nA + nB), cudaGetErrorString (e));
+          rc = GCG_ENOMEM;
+          break;
+        }
+        if (nA > 0 && cudaMemcpyAsync (bigger, h->d_hits, (size_t) nA * sizeof (gcg_hit), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) {
+          gcg_dfree (ctx, bigger); gcg_set_error ("gcg_search: anchor copy failed"); rc = GCG_ECUDA; break;
+        }
+        gcg_dfree (ctx, h->d_hits);                     // (parked, and reused only by work queued behind the copy)
+        h->d_hits = bigger;
+      }
+      if (nB > 0) emit (tileA, n_words, h->d_hits + nA);
+      h->n = nA + nB;
+    }
+    gcg_trace_mark (ctx, "  search_seqs: counts + emit launches");
+    // no wait for the emit kernels: the anchors stay on the device and everything that reads them
+    // (download, statistics, the next search) is ordered behind them on the context's stream
+    if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_search: emit launch failed"); rc = GCG_ECUDA; }
     break;
   }
   gcg_dfree (ctx, d_mask); gcg_dfree (ctx, d_prefix); gcg_dfree (ctx, d_bsum);
@@ -1414,7 +1469,7 @@ extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * re
     GCG_CUDA (cudaEventRecord (q.ev_count, ctx->stream));
     { gcg_kscope ks (ctx, "hits_emit");
       hits_emit_kernel<<<grid_for (ctx, d.n_tiles * 32, 256, 8), 256, 0, ctx->stream>>> (
-          q.d_packed, d_woff, d_tseq, nr, nw, k, t->d_keys, t->d_vals, t->n_bucket, q.d_mask, q.d_prefix, (int32_t) d.r0, q.d_hits); }
+          q.d_packed, d_woff, d_tseq, nr, nw, k, t->d_keys, t->d_vals, t->n_bucket, q.d_mask, q.d_prefix, (int32_t) d.r0, q.d_hits, 0); }
     GCG_CUDA (cudaEventRecord (q.ev_emit, ctx->stream));
     GCG_CUDA (cudaGetLastError ());
     q.pending = true;

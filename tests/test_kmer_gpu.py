@@ -172,3 +172,34 @@ def test_randomised_small_cases(ctx, oracle, monkeypatch):
         got = ctx.route_plan(rs, k, n_part, 0, rs.tiles)
         assert np.array_equal(got.counts, want.counts), (case, k, n_part)
         got.free(); rs.free(); cs.free()
+
+
+@pytest.mark.parametrize("tight", ["0", "1"])
+def test_search_in_two_halves(ctx, oracle, tight, monkeypatch):
+    """GCG_SEARCH_SPLIT=1: gcg_search_seqs probes the reads as two halves so that the host fetches one
+    half's anchor count while the GPU works on the other (an option, measured slower than one pass):
+    switched on for small inputs here, also with the anchor buffer sized for the first half alone (the
+    second half then takes the regrow path), against the oracle and against the single pass; halves
+    without anchors included"""
+    monkeypatch.setenv("GCG_SEARCH_SPLIT", "1")
+    monkeypatch.setenv("GCG_SEARCH_SPLIT_MIN_TILES", "2")
+    monkeypatch.setenv("GCG_SEARCH_SPLIT_TIGHT", tight)
+    for name, k in (("repeats", 17), ("small", 31), ("tiny", 25)):
+        inp = synth.make_config(name)
+        check_case(ctx, oracle, inp.contigs, inp.reads, k)
+    inp = synth.make_config("small")
+    rng = np.random.default_rng(9)
+    junk = [np.frombuffer(b"ACTG", np.uint8)[rng.integers(0, 4, 3000)] for _ in range(700)]   # as many bases again, none of them anchors
+    cs = ctx.upload(inp.contigs)
+    for reads in (junk + inp.reads, inp.reads + junk, junk + junk):
+        rs = ctx.upload(reads)
+        monkeypatch.setenv("GCG_SEARCH_SPLIT", "1")
+        t = ctx.table_build(cs, 25)
+        a, st_a = ctx.search(t, rs), t.stats()
+        t.free()
+        monkeypatch.setenv("GCG_SEARCH_SPLIT", "0")
+        t = ctx.table_build(cs, 25)
+        b, st_b = ctx.search(t, rs), t.stats()
+        t.free(); rs.free()
+        assert np.array_equal(a, b) and st_a == st_b
+    cs.free()
