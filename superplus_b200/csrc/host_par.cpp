@@ -195,6 +195,46 @@ __attribute__ ((target ("avx2"))) static void pack_stream_avx2 (uint64_t * dst, 
   }
 }
 
+// AVX-512 VBMI: 64 bases per fold (same shift / mask / two multiply-adds on 512 bits), one byte
+// permute collects the sixteen code bytes as two big-endian words; four folds fill a whole 64-byte
+// line that leaves with ONE non-temporal store (a full write-combining buffer per store instead of
+// eight partial ones).  bench_tools/host_pack_bench.cpp on the B200 box's host (profiles/
+// r01_host_pack_bench.log): 13.0 against 9.9 GB/s of ASCII on one core, 25.6 against 19.5 on two (what
+// a rank has when eight ranks share the box's 16 cores), 99 against 87 GB/s on all sixteen.
+#define GCG_T512 __attribute__ ((target ("avx512f,avx512bw,avx512vbmi,avx512vl")))
+GCG_T512 static inline __m512i fold64_avx512 (const char * s)
+{
+  const __m512i x = _mm512_loadu_si512 ((const void *) s);
+  const __m512i c = _mm512_and_si512 (_mm512_srli_epi16 (x, 1), _mm512_set1_epi8 (3));
+  const __m512i q = _mm512_madd_epi16 (_mm512_maddubs_epi16 (c, _mm512_set1_epi32 (0x01041040)), _mm512_set1_epi16 (1));
+  // dword i holds bases 4i..4i+3 in its low byte; word 0 wants dword 0 in its top byte, i.e. last in memory
+  const __m512i idx = _mm512_castsi128_si512 (_mm_setr_epi8 (28, 24, 20, 16, 12, 8, 4, 0, 60, 56, 52, 48, 44, 40, 36, 32));
+  return _mm512_permutexvar_epi8 (idx, q);          // the two words in the low 128 bits
+}
+
+GCG_T512 static void pack_stream_avx512 (uint64_t * dst, const char * src, size_t n)
+{
+  size_t w = 0;
+  const size_t full = n / 32;                       // whole words
+  // head: single words until the destination sits on a 64-byte line
+  for (; w < full && ((uintptr_t) (dst + w) & 63); ++w) store_word_stream (dst + w, pack32_avx2 (src + w * 32));
+  for (; w + 8 <= full; w += 8) {
+    const char * s = src + w * 32;
+    __m512i r = fold64_avx512 (s);
+    r = _mm512_inserti32x4 (r, _mm512_castsi512_si128 (fold64_avx512 (s + 64)), 1);
+    r = _mm512_inserti32x4 (r, _mm512_castsi512_si128 (fold64_avx512 (s + 128)), 2);
+    r = _mm512_inserti32x4 (r, _mm512_castsi512_si128 (fold64_avx512 (s + 192)), 3);
+    _mm512_stream_si512 ((__m512i *) (dst + w), r);
+  }
+  for (; w + 2 <= full; w += 2) _mm_stream_si128 ((__m128i *) (dst + w), _mm512_castsi512_si128 (fold64_avx512 (src + w * 32)));
+  for (; w < full; ++w) store_word_stream (dst + w, pack32_avx2 (src + w * 32));
+  if (w * 32 < n) {
+    char tail[32] = {0};
+    memcpy (tail, src + w * 32, n - w * 32);
+    store_word_stream (dst + w, pack32_avx2 (tail));
+  }
+}
+
 static void pack_stream_swar (uint64_t * dst, const char * src, size_t n)
 {
   size_t w = 0;
@@ -208,15 +248,18 @@ static void pack_stream_swar (uint64_t * dst, const char * src, size_t n)
 
 void gcg_pack_stream (uint64_t * dst, const void * src, size_t n)
 {
-  // GCG_HOST_PACK = avx2 | pext | swar forces a path (tests); default: the best the CPU has
+  // GCG_HOST_PACK = avx512 | avx2 | pext | swar forces a path (tests); default: the best the CPU has
   static const int path = [] () {
     const char * e = getenv ("GCG_HOST_PACK");
+    const bool has512 = __builtin_cpu_supports ("avx512vbmi") && __builtin_cpu_supports ("avx512bw") && __builtin_cpu_supports ("avx512vl") && __builtin_cpu_supports ("avx2");
     if (e && !strcmp (e, "swar")) return 0;
     if (e && !strcmp (e, "pext") && __builtin_cpu_supports ("bmi2")) return 1;
     if (e && !strcmp (e, "avx2") && __builtin_cpu_supports ("avx2")) return 2;
-    return __builtin_cpu_supports ("avx2") ? 2 : __builtin_cpu_supports ("bmi2") ? 1 : 0;
+    if (e && !strcmp (e, "avx512") && has512) return 3;
+    return has512 ? 3 : __builtin_cpu_supports ("avx2") ? 2 : __builtin_cpu_supports ("bmi2") ? 1 : 0;
   } ();
-  if (path == 2) pack_stream_avx2 (dst, (const char *) src, n);
+  if (path == 3) pack_stream_avx512 (dst, (const char *) src, n);
+  else if (path == 2) pack_stream_avx2 (dst, (const char *) src, n);
   else if (path == 1) pack_stream_pext (dst, (const char *) src, n);
   else pack_stream_swar (dst, (const char *) src, n);
 }

@@ -116,7 +116,8 @@ def test_shim_hash_set_semantics():
 def test_host_pack_2bit_matches_the_oracle_packing():
     """gcg_host_pack_2bit (what the search gather does on the host) == (c >> 1) & 3 per base, 32
     bases per word, first base on top, zero tail — for every tail length, any byte value, and all
-    three code paths (AVX2, PEXT, portable multiply)."""
+    four code paths (AVX-512 VBMI, AVX2, PEXT, portable multiply); the AVX-512 path also with every
+    destination alignment inside a 64-byte line (head words, whole lines, pairs, single words, tail)."""
     import subprocess, sys
     rng = np.random.default_rng(3)
 
@@ -134,11 +135,27 @@ def test_host_pack_2bit_matches_the_oracle_packing():
     cases += [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), n)) for n in (25, 96, 12345)]
     for c in cases:
         assert np.array_equal(api.host_pack_2bit(c), want(c)), len(c)
+    # destinations at every 8-byte step of a 64-byte line, lengths around the 256-base blocks
+    import ctypes as C
+    L = api.load_library()
+    L.gcg_host_pack_2bit.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    raw = np.zeros(4096 + 16, dtype=np.uint64)
+    base = (-raw.ctypes.data // 8) % 8                                   # index of the first 64-byte aligned word
+    for shift in range(8):
+        for n in (0, 1, 32, 255, 256, 257, 511, 512, 700, 2048 + 31, 2048 + 96 + 5, 4000):
+            c = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+            src = np.frombuffer(c, dtype=np.uint8) if n else np.zeros(1, np.uint8)
+            raw[:] = np.uint64(0xDEADBEEFDEADBEEF)
+            dst = raw[base + shift:]
+            assert L.gcg_host_pack_2bit(src.ctypes.data, n, dst.ctypes.data) == 0
+            nw = (n + 31) // 32
+            assert np.array_equal(dst[:nw], want(c)), (shift, n)
+            assert dst[nw] == np.uint64(0xDEADBEEFDEADBEEF) and (base + shift == 0 or raw[base + shift - 1] == np.uint64(0xDEADBEEFDEADBEEF))
     # every path in a fresh process (the choice is made once per process)
     code = ("import numpy as np, sys; sys.path.insert(0, %r); from superplus_b200 import api; "
             "b = bytes(range(256)) * 3 + b'ACGTTGCA'; print(','.join(str(int(x)) for x in api.host_pack_2bit(b)))" % ROOT)
     b = bytes(range(256)) * 3 + b"ACGTTGCA"
-    for path in ("swar", "pext", "avx2"):       # a path the CPU lacks falls back to the default one
+    for path in ("swar", "pext", "avx2", "avx512"):       # a path the CPU lacks falls back to the default one
         out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GCG_HOST_PACK=path), capture_output=True, text=True, check=True).stdout
         assert [int(x) for x in out.strip().split(",")] == [int(x) for x in want(b)], path
 
