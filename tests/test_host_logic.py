@@ -175,3 +175,65 @@ def test_split_reads_by_bases_covers_and_balances():
                 assert sum(shares) == int(lens.sum())
                 # no share exceeds its fair part by more than one read
                 assert max(shares) <= -(-int(lens.sum()) // n) + int(lens.max())
+
+
+def test_replicated_search_orchestration_with_a_host_double():
+    """api.ReplicatedSearch (reads sharded over the GPUs of one process) driven with host doubles of the
+    context and the table: shares are contiguous and searched on their own replica, anchors come back
+    in read order with global read indices, and every replica is merged into the primary exactly once
+    per search (the device side of clone / merge is covered by tests/test_gc_e2e_gpu.py)."""
+    import threading
+    log, lock = [], threading.Lock()
+
+    class Tab:
+        def __init__(self, ctx, name):
+            self.ctx, self.name, self.k, self.seen, self.merged = ctx, name, 5, [], []
+
+        def clone(self, ctx):
+            return Tab(ctx, "replica@%s" % ctx.name)
+
+        def merge_ont(self, rep):
+            self.merged.append(rep.name)
+            self.seen += rep.seen
+            rep.seen = []                                  # the counts move
+
+        def free(self):
+            with lock:
+                log.append(("free", self.name))
+
+    class Ctx:
+        def __init__(self, name):
+            self.name = name
+
+        def search_host(self, table, reads):
+            # one "anchor" per read whose first byte is even: (local read index, pos 0, tid = length, 0)
+            out = np.zeros(sum(1 for r in reads if len(r) and r[0] % 2 == 0), dtype=api.HIT_DTYPE)
+            j = 0
+            for i, r in enumerate(reads):
+                if len(r) and r[0] % 2 == 0:
+                    out[j] = (i, 0, len(r), 0); j += 1
+            table.seen += [bytes(r[:4]) for r in reads]
+            with lock:
+                log.append(("search", self.name, table.name, len(reads)))
+            return out
+
+    rng = np.random.default_rng(12)
+    reads = [rng.integers(0, 250, int(rng.integers(0, 400))).astype(np.uint8) for _ in range(57)]
+    want = Ctx("solo").search_host(Tab(None, "t"), reads)
+    for n in (1, 2, 3, 8):
+        ctxs = [Ctx("c%d" % i) for i in range(n)]
+        prim = Tab(ctxs[0], "primary")
+        rep = api.ReplicatedSearch(ctxs, prim)
+        assert [t.name for t in rep.tables] == ["primary"] + ["replica@c%d" % i for i in range(1, n)]
+        del log[:]
+        got = rep.search_host(reads)
+        assert np.array_equal(got, want), n
+        searched = sorted(e for e in log if e[0] == "search")
+        assert [e[2] for e in searched] == sorted(t.name for t in rep.tables) and sum(e[3] for e in searched) == len(reads)
+        assert prim.merged == [t.name for t in rep.tables[1:]]
+        assert sorted(prim.seen) == sorted(bytes(r[:4]) for r in reads)          # every read reached exactly one replica
+        rep.search_host(reads[:5])
+        assert prim.merged == [t.name for t in rep.tables[1:]] * 2 and len(prim.seen) == len(reads) + 5
+        rep.free()
+        assert sorted(e[1] for e in log if e[0] == "free") == sorted(t for t in prim.merged[:n - 1])
+        assert rep.tables == [prim]
