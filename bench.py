@@ -14,7 +14,11 @@ A step is one pass of the hot path over one batch of synthetic input:
       many pairs per step as fill two whole waves of resident warps.  Unit = GCUPS.
 `value` is measured with the inputs resident in HBM (CUDA events on the library's stream, max
 over ranks); `e2e` is the same metric through the host-buffer C-ABI calls the C shims use
-(gcg_table_build + gcg_search, gcg_sw_batch), host<->device copies inside the timed region.
+(gcg_table_build + gcg_search_compact, gcg_sw_batch), host<->device copies inside the timed region.
+Anchors are the compact 8-byte records of include/gcgpu.h in both (SURVEY 8d's hit record).
+The SW headline is the FIXED traceback (configs[2] is the fixed-mode config); the as-shipped
+traceback is timed beside it (`sw.asis`).  `roofline_hbm_table` repeats the k-mer roofline on a
+100 Mb / k = 31 table that does not fit the L2 (BASELINE configs[3]'s table on one GPU).
 N > 1: one process per GPU; reads / pairs are sharded by batch, the contig table is replicated
 (SURVEY §8e), no collective on the data path -> weak scaling.
 
@@ -170,30 +174,47 @@ def run_reference(args, rank, world):
     if not reference_available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built (needs /root/reference at build time)"}))
         return
+    from oracle import oracle as orc
     inp = synth.make_config(WORKLOAD)
-    sub = inp.reads[: max(1, len(inp.reads) // 8)]             # bounded sample: 1/8 of the cfg2 reads
     vals, sw_vals, times = [], [], []
+    budget_s = 150.0                      # the whole arm has to end within a few minutes
     with tempfile.TemporaryDirectory() as tmp:
-        for it in range(args.warmup + args.steps):
+        fa, fq = os.path.join(tmp, "b.fa"), os.path.join(tmp, "b.fq")
+        synth.write_fasta(fa, inp.scaffold)
+        synth.write_fastq(fq, inp.reads)                         # the FULL cfg2 read set: same config as our arm
+        t_start = time.perf_counter()
+        warm, steps = min(args.warmup, 1), args.steps
+        it = 0
+        while it < warm + steps:
             t0 = time.perf_counter()
-            v, info = cpu_kmer(inp.scaffold, sub, cores, tmp)
+            info, _, _, _ = orc.run_ref_kmer(fa, fq, K, os.path.join(tmp, "b"), n_thread=cores, dump=0)
+            v = info["n_ont_kmers"] / (info["t_chop"] + info["t_put"] + info["t_search"])
             g, npairs, _ = cpu_sw(cores, 1)
             dt = time.perf_counter() - t0
-            if it >= args.warmup:
+            if it >= warm:
                 vals.append(v); sw_vals.append(g); times.append(dt)
+            elif warm:
+                # a step reloads the FASTQ with the reference's own loader and re-zeroes 16 bytes per ONT base before
+                # the timed phases: fit as many steps as the budget allows, at least one
+                steps = max(1, min(args.steps, int((budget_s - dt) / dt)))
+            it += 1
+            if it >= warm + 1 and time.perf_counter() - t_start > budget_s:
+                break
     value = statistics.mean(vals)
-    sample = "full cfg2 scaffold (4.6 Mb, 500 gaps) x the first 1/8 of its 30x ONT reads (%d reads, %d k-mers) per step; chop+put+search timed inside ref_kmer" % (len(sub), info["n_ont_kmers"])
+    sample = ("the full cfg2 workload per step (%d reads, %d ONT k-mers, 4.6 Mb scaffold); chop+put+search timed inside ref_kmer "
+              "(loading and okseq set-up outside); %d of the %d requested steps fit the %.0f s budget of this arm" %
+              (len(inp.reads), info["n_ont_kmers"], len(vals), args.steps, budget_s))
     line = {
-        "impl": "reference", "metric": "kmers_per_s", "value": value, "unit": "k-mers/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(times), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": "kmers_per_s", "value": value, "unit": "k-mers/s", "n_gpus": args.gpus, "steps": len(vals),
+        "steps_requested": args.steps, "warmup": warm, "ms_per_step": 1e3 * statistics.mean(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": "cfg2: 4.6 Mb synthetic scaffolds, 500 N-gaps, 30x ONT (10% error), k=25; reference CPU code (kmer.c, hash.c, ont.c) on the host cores",
-                   "k": K, "threads": cores},
+                   "k": K, "threads": cores, "reads": len(inp.reads), "ont_kmers": info["n_ont_kmers"]},
         "cpu_baseline": {"value": value, "unit": "k-mers/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "sw": {"metric": "sw_gcups", "value": statistics.mean(sw_vals), "unit": "GCUPS", "impl": "reference",
                "cpu_baseline": {"value": statistics.mean(sw_vals), "unit": "GCUPS", "cores": cores, "kind": "reference",
-                                "sample": "%d pairs of 10 kb x 2 kb per step, one reference sw_t per core (sw.c:400-414)" % cores},
+                                "sample": "%d pairs of 10 kb x 2 kb per step, one reference sw_t per core (sw.c:400-414), as-shipped traceback" % cores},
                "e2e": {"value": statistics.mean(sw_vals), "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
         "gpu_launches": 0,
     }
@@ -251,7 +272,7 @@ def run_ours(args, rank, local_rank, world):
         cs = ctx.pack(a_ctg)
         rs = ctx.pack(a_reads)
         t = ctx.table_build(cs, K)
-        n_hit = ctx.search_device(t, rs)
+        n_hit = ctx.search_device_compact(t, rs)
         st = t.stats()
         t.free(); cs.free(); rs.free()
         return n_hit, st
@@ -265,13 +286,14 @@ def run_ours(args, rank, local_rank, world):
     P = api.make_sw_params()
     sw_cells = swb.cells()
 
-    def sw_step():
-        swb.align(P, api.SW_ASIS)
+    def sw_step(mode=api.SW_FIXED):
+        swb.align(P, mode)
 
     # ---- warm-up
     for _ in range(args.warmup):
         n_hit, st = kmer_step()
-        sw_step()
+        sw_step(api.SW_FIXED)
+        sw_step(api.SW_ASIS)
     r_int16 = ctx.ubench_int16()
 
     # ---- timed: k-mer steps
@@ -336,22 +358,58 @@ def run_ours(args, rank, local_rank, world):
                               "kernel_ms_per_step": {k_: v[0] / args.steps for k_, v in sorted(pprof.items())}}
             idx.free()
 
-    # ---- timed: SW steps
-    ctx.prof_reset()
-    launches1 = ctx.launches()
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
-    sampler.mark()
-    for _ in range(args.steps):
-        sw_step()
-    e3.record(stream)
-    barrier()
-    sw_ms = allmax(e2.elapsed_time(e3)) / args.steps
-    sprof = ctx.prof_report()
-    sw_launches = ctx.launches() - launches1
+    # ---- timed: SW steps, fixed traceback (headline) and the as-shipped traceback beside it
+    sw_launches = 0
+    sw_timed = {}
+    for mode, name in ((api.SW_FIXED, "fixed"), (api.SW_ASIS, "asis")):
+        ctx.prof_reset()
+        launches1 = ctx.launches()
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record(stream)
+        sampler.mark()
+        for _ in range(args.steps):
+            sw_step(mode)
+        e3.record(stream)
+        barrier()
+        sw_timed[name] = (allmax(e2.elapsed_time(e3)) / args.steps, ctx.prof_report())
+        sw_launches += ctx.launches() - launches1
+    sw_ms, sprof = sw_timed["fixed"]
+    sw_asis_ms, sprof_asis = sw_timed["asis"]
     ctx.prof(False)
     clocks = sampler.result()
+
+    # ---- the k-mer roofline again on a table that does not fit the L2: 100 Mb genome, k = 31 (BASELINE configs[3]'s
+    #      table, 1.6 GB of keys + 1.6 GB of values on this GPU), 2x ONT; device resident, per-kernel CUDA events
+    hbm_leg = None
+    if world == 1 and not args.no_hbm_table:
+        K4 = 31
+        rng4 = np.random.Generator(np.random.PCG64(synth.CONFIGS["cfg4"]["seed"]))
+        genome4 = synth.random_genome(synth.CONFIGS["cfg4"]["genome_len"], rng4)
+        reads4 = synth.make_reads(genome4, args.hbm_coverage, synth.CONFIGS["cfg4"]["seed"] + 1)
+        n4 = sum(max(0, len(r) - K4 + 1) for r in reads4)
+        c4, r4 = ctx.upload([genome4]), ctx.upload(reads4)
+        t4 = ctx.table_build(c4, K4)
+        for _ in range(2):
+            h4 = ctx.search_device_compact(t4, r4)
+        ctx.prof(True); ctx.prof_reset()
+        h_steps = 3
+        for _ in range(h_steps):
+            h4 = ctx.search_device_compact(t4, r4)
+        ctx.sync()
+        p4 = ctx.prof_report()
+        ctx.prof(False)
+        st4 = t4.stats()
+        t4.free(); c4.free(); r4.free()
+        f_ms = p4.get("k45_fused", (0.0, 1))
+        f_avg = f_ms[0] / max(1, f_ms[1])
+        alg4 = BYTES_PER_LOOKUP * n4 + BYTES_PER_HIT * h4
+        hbm_leg = {"kernel": "k45_fused_kernel", "avg_launch_ms": f_avg, "ont_kmers": n4, "anchors": int(h4), "stats": list(st4),
+                   "algorithmic_bytes_per_launch": alg4, "kmers_per_s": n4 / (f_avg * 1e-3) if f_avg > 0 else 0.0,
+                   "achieved": alg4 / (f_avg * 1e-3) / 1e9 if f_avg > 0 else 0.0,
+                   "kernel_ms_per_launch": {k_: v[0] / max(1, v[1]) for k_, v in sorted(p4.items())},
+                   "workload": "100 Mb random genome, k=31: 100 M contig k-mers, 3.2 GB of slots (beyond the 126 MB L2, Bloom pre-filter on), %.1fx ONT (%d reads)" % (args.hbm_coverage, len(reads4))}
+        del genome4, reads4
 
     # ---- end to end through the host-buffer C ABI (what the C shims call)
     arrs = [np.ascontiguousarray(r) for r in reads]
@@ -368,14 +426,17 @@ def run_ours(args, rank, local_rank, world):
         h = C.c_void_p()
         ctx._chk(ctx.L.gcg_table_build(ctx.h, C.cast(cptrs, C.c_void_p), clens.ctypes.data, len(carrs), K, C.byref(h)))
         tab = api.KmerTable(ctx, h, K)
-        hp, nh = C.c_void_p(), C.c_int64()
-        ctx._chk(ctx.L.gcg_search(ctx.h, tab.h, C.cast(rptrs, C.c_void_p), rlens.ctypes.data, len(arrs), K, C.byref(hp), C.byref(nh)))
-        # the anchors are now in (library-owned, pinned) host memory: read the last one, release
+        hp, rp, nh = C.c_void_p(), C.c_void_p(), C.c_int64()
+        ctx._chk(ctx.L.gcg_search_compact(ctx.h, tab.h, C.cast(rptrs, C.c_void_p), rlens.ctypes.data, len(arrs), K, C.byref(hp), C.byref(rp), C.byref(nh)))
+        # the anchors and the per-read offsets are now in (library-owned, pinned) host memory: read the ends, release
+        ro = np.frombuffer((C.c_char * ((len(arrs) + 1) * 8)).from_address(rp.value), dtype=np.int64)
+        assert int(ro[-1]) == nh.value and int(ro[0]) == 0
         if nh.value:
-            view = np.frombuffer((C.c_char * (nh.value * api.HIT_DTYPE.itemsize)).from_address(hp.value), dtype=api.HIT_DTYPE)
-            assert int(view["read"][-1]) < len(arrs)
+            view = np.frombuffer((C.c_char * (nh.value * 8)).from_address(hp.value), dtype=np.uint64)
+            assert (int(view[-1]) >> 36) < len(arrs[-1]) or int(ro[-2]) == int(ro[-1])
             del view
-        ctx.L.gcg_free(hp)
+        del ro
+        ctx.L.gcg_free(hp); ctx.L.gcg_free(rp)
         s4 = tab.stats()
         tab.free()
         return nh.value, s4
@@ -404,7 +465,7 @@ def run_ours(args, rank, local_rank, world):
         tb, to = np.ascontiguousarray(te).reshape(-1), np.arange(sw_e2e_pairs + 1, dtype=np.int64) * SW_TLEN
         res = np.zeros(sw_e2e_pairs, dtype=api.SWRES_DTYPE)
         pool, npool = C.c_void_p(), C.c_int64()
-        ctx._chk(ctx.L.gcg_sw_batch(ctx.h, C.byref(P), api.SW_ASIS, qb.ctypes.data, qo.ctypes.data, tb.ctypes.data, to.ctypes.data,
+        ctx._chk(ctx.L.gcg_sw_batch(ctx.h, C.byref(P), api.SW_FIXED, qb.ctypes.data, qo.ctypes.data, tb.ctypes.data, to.ctypes.data,
                                     sw_e2e_pairs, res.ctypes.data, C.byref(pool), C.byref(npool)))
         n_ops = npool.value
         ctx.L.gcg_free(pool)
@@ -424,14 +485,23 @@ def run_ours(args, rank, local_rank, world):
         return
 
     peak_gbs, peak_src = measured_peaks()
-    k45_ms = kprof.get("k45_search", (0.0, 1))
-    k45_avg = k45_ms[0] / max(1, k45_ms[1])
-    # the search probes the reads as two halves (two launches per step): bytes per launch = the step's share
-    k45_per_step = max(1.0, k45_ms[1] / max(1, args.steps))
-    alg_bytes = (BYTES_PER_LOOKUP * n_ont_kmers + BYTES_PER_HIT * n_hit) / k45_per_step
-    achieved = alg_bytes / (k45_avg * 1e-3) / 1e9 if k45_avg > 0 else 0.0
-    fill = sprof.get("k7_sw_fill_packed", (0.0, 1))
-    fill_gcups = sw_cells / (fill[0] / args.steps * 1e-3) / 1e9 if fill[0] > 0 else 0.0
+    # K4+K5 is ONE kernel now (probe + ordered anchor index + ONT-side multiplicity + anchor records): SURVEY 8d's
+    # algorithmic bytes of the whole unit — 16.25 B per ONT k-mer looked up + 16 B per anchor (8-byte record + 8-byte
+    # count RMW) — are charged to it
+    kf = kprof.get("k45_fused", (0.0, 1))
+    kf_avg = kf[0] / max(1, kf[1])
+    kf_per_step = max(1.0, kf[1] / max(1, args.steps))
+    alg_bytes = (BYTES_PER_LOOKUP * n_ont_kmers + BYTES_PER_HIT * n_hit) / kf_per_step
+    achieved = alg_bytes / (kf_avg * 1e-3) / 1e9 if kf_avg > 0 else 0.0
+    step_alg = BYTES_PER_LOOKUP * n_ont_kmers + BYTES_PER_HIT * n_hit + 32.25 * n_ctg_kmers
+
+    def sw_leg(ms, prof, mode_name):
+        fill = prof.get("k7_sw_fill_packed", (0.0, 1))
+        g = sw_cells / (fill[0] / args.steps * 1e-3) / 1e9 if fill[0] > 0 else 0.0
+        return fill, g
+    fill, fill_gcups = sw_leg(sw_ms, sprof, "fixed")
+    fill_a, fill_gcups_asis = sw_leg(sw_asis_ms, sprof_asis, "asis")
+    sw_value_asis = tot_cells / (sw_asis_ms * 1e-3) / 1e9
     sw_peak = r_int16 * 2.0 / OPS_PER_CELL / 1e9          # 16-bit results per second / 12 ops per cell
     # DRAM bytes of one fill launch: the ncu capture is one launch over a known number of cfg3 pairs
     sw_traffic, cap_pairs = ncu_traffic("sw_fill_packed_kernel"), ncu_traffic("sw_fill_packed_kernel_pairs")
@@ -444,28 +514,34 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": "cfg2: 4.6 Mb synthetic scaffolds, 500 N-gaps, 30x ONT (10% error), k=25 — pack + contig table build + ONT search + ordered anchors + stats per step",
                    "k": K, "contigs": len(contigs), "reads_per_gpu": len(reads), "ont_kmers_per_gpu": n_ont_kmers, "contig_kmers": n_ctg_kmers,
                    "anchors_per_gpu": int(n_hit), "stats": list(st), "parallelism": "reads sharded by batch, table replicated (no data-path collective)",
+                   "anchor_record": "8 bytes (pos << 36 | scaffold coordinate << 2 | flags) + one offset per read, include/gcgpu.h",
                    "l2": "inputs larger than L2 (138 MB ASCII reads + 106 MB table per step vs 126 MB L2); no explicit flush"},
         # reads cross PCIe 2-bit packed by the host gather (8 bytes per 32 bases, every read padded to whole words)
         # plus 12 bytes of layout per read and 4 per 1024 positions; contigs go up as ASCII
         "e2e": {"value": tot_ont_kmers / e2e_kmer_s, "unit": "k-mers/s",
                 "h2d_bytes_per_step": int(sum((len(r) + 31) // 32 * 8 for r in reads) + 12 * len(reads) + read_bytes // 256 + ctg_bytes),
                 "host_input_bytes_per_step": int(read_bytes + ctg_bytes),
-                "d2h_bytes_per_step": int(n_hit * 16 + 32), "ms_per_step": e2e_kmer_s * 1e3,
+                "d2h_bytes_per_step": int(n_hit * 8 + 8 * (len(reads) + 1) + 32), "ms_per_step": e2e_kmer_s * 1e3,
                 "host_threads_per_rank": host_threads, "host_cores": os.cpu_count(),
-                "api": "gcg_table_build + gcg_search (host pointers in, pinned anchors out) + gcg_table_stats"},
+                "api": "gcg_table_build + gcg_search_compact (host pointers in, pinned 8-byte anchors + per-read offsets out) + gcg_table_stats"},
         "gpu_launches": int(kmer_launches + sw_launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k45_search_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": achieved / peak_gbs, "traffic": ncu_traffic("k45_search_kernel"), "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k45_avg,
-                     "note": "the 106 MB cfg2 table is L2 resident: ncu (profiles/r01_ncu_summary.txt) shows 95 % L2 sector hits, DRAM traffic far below the algorithmic bytes and the integer ALU pipe 85 % busy; tables beyond the L2 go through a pre-filter (DESIGN.md 4)",
+        "roofline": {"bound": "hbm", "kernel": "k45_fused_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": achieved / peak_gbs, "traffic": ncu_traffic("k45_fused_kernel"), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kf_avg,
+                     "unit_of_work": "SURVEY K4+K5 as one kernel: probe, ordered anchor index (chained scan), ONT multiplicity, anchor records",
+                     "whole_step": {"algorithmic_bytes": step_alg, "achieved": step_alg / (kmer_ms * 1e-3) / 1e9, "frac": step_alg / (kmer_ms * 1e-3) / 1e9 / peak_gbs,
+                                    "note": "all kernels of the step (pack, build, search, stats) over the step time"},
+                     "note": "the 106 MB cfg2 table is mostly L2 resident, so this is an algorithmic-bytes figure against the HBM copy peak, not DRAM traffic (`traffic`); the probe is bound by the L1 wavefront rate of one random 32-byte bucket load per k-mer (DESIGN.md 4); `roofline_hbm_table` is the same kernel on a table that does not fit the L2",
                      "kernel_ms_per_step": {k_: v[0] / args.steps for k_, v in sorted(kprof.items())}},
         "sw": {"metric": "sw_gcups", "value": sw_value, "unit": "GCUPS", "ms_per_step": sw_ms, "dtype": "s16x2",
-               "config": {"workload": "cfg3 shape: ONT-read(10 kb) x gap-flank(2 kb) pairs, default scoring (+1/-5/2/1, softclip), as-is traceback; fill + trace spill + end cell + CIGAR",
+               "config": {"workload": "cfg3 shape: ONT-read(10 kb) x gap-flank(2 kb) pairs, default scoring (+1/-5/2/1, softclip), FIXED traceback (cell re-fetched every step, SURVEY H4); fill + trace spill + end cell + traceback walk + CIGAR",
                           "pairs_per_gpu_per_step": int(sw_pairs), "cells_per_gpu_per_step": int(sw_cells), "paths": sw_paths,
                           "l2": "10.4 MB of trace per pair streams through L2 (%.0f GB per step; every resident warp reuses one 20.8 MB slot)" % (sw_pairs * 10.4e-3)},
                "e2e": {"value": tot_e2e_cells / e2e_sw_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(sw_e2e_pairs * (SW_QLEN + SW_TLEN)),
-                       "d2h_bytes_per_step": int(sw_e2e_pairs * 32 + n_ops * 4), "pairs_per_step": int(sw_e2e_pairs), "api": "gcg_sw_batch (host buffers)"},
+                       "d2h_bytes_per_step": int(sw_e2e_pairs * 32 + n_ops * 4), "pairs_per_step": int(sw_e2e_pairs), "api": "gcg_sw_batch (host buffers), FIXED traceback"},
+               "asis": {"value": sw_value_asis, "unit": "GCUPS", "ms_per_step": sw_asis_ms, "roofline_frac": fill_gcups_asis / sw_peak if sw_peak else None,
+                        "note": "traceback exactly as shipped (sw.c:289-319 never re-fetches the cell): the CIGAR is a function of the end cell only"},
                "roofline": {"bound": "int_alu", "kernel": "sw_fill_packed_kernel", "achieved": fill_gcups, "peak": sw_peak, "unit": "GCUPS",
                             "frac": fill_gcups / sw_peak if sw_peak else None, "traffic": sw_traffic,
                             "peak_source": "measured in this run: VIADDMNMX.S16x2 issue rate %.2f T lane-ops/s x 2 halves / 12 integer ops per cell (SURVEY 8d)" % (r_int16 / 1e12),
@@ -473,6 +549,9 @@ def run_ours(args, rank, local_rank, world):
                                           "peak": peak_gbs, "unit": "GB/s", "note": "trace spill, 0.5 byte per cell"},
                             "kernel_ms_per_step": {k_: v[0] / args.steps for k_, v in sorted(sprof.items())}}},
     }
+    if hbm_leg is not None:
+        hbm_leg.update({"bound": "hbm", "peak": peak_gbs, "unit": "GB/s", "frac": hbm_leg["achieved"] / peak_gbs, "peak_source": peak_src})
+        line["roofline_hbm_table"] = hbm_leg
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference itself on the host cores
     if world == 1 and not args.no_cpu_baseline:
@@ -515,6 +594,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sw-pairs", type=int, default=47360, help="pairs per GPU per step of the cfg3 leg (16 items per resident warp)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hbm-table", action="store_true", help="skip the second k-mer roofline leg (100 Mb table beyond the L2, N=1 only)")
+    ap.add_argument("--hbm-coverage", type=float, default=2.0, help="ONT coverage of the 100 Mb genome in that leg")
     ap.add_argument("--partitioned", action="store_true", help="also time the hash-partitioned table at N=1 (always timed at N>1)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

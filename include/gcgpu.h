@@ -90,6 +90,10 @@ int64_t gcg_seqs_kmers (const gcg_seqs * s, int k);   /* sum over sequences of m
  * read on its way into the pinned upload buffer.  words_out receives (len + 31) / 32 words, 32
  * bases per word, first base in the top two bits, tail padded with code 0. */
 int  gcg_host_pack_2bit (const char * seq, int64_t len, uint64_t * words_out);
+/* self-test of the host worker pool's one-job rule (no device needed; tests/test_host_logic.py): starts an
+ * asynchronous job of n_async tasks, offers a synchronous one of n_sync tasks while it is out, waits.
+ * Returns n_async * 1000 + n_sync when every task ran exactly once. */
+int64_t gcg_selftest_workers (int n_thread, int n_async, int n_sync);
 
 /* ------------------------------------------------------------------ contig k-mers ---- */
 /* replaces chop_contig_seqs2kmers (kmer.c:155-184 / 37-121): one 24-byte record per contig
@@ -151,6 +155,27 @@ void gcg_hits_free (gcg_hits * h);
 int  gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
                  int64_t n_read, int k, gcg_hit ** hits_out, int64_t * n_hit);
 void gcg_free (void * p);
+
+/* Compact anchors — what the shim asks for (superplus_b200/gap_closer/ont.c): ONE 64-bit word per
+ * anchor instead of the 16-byte gcg_hit, grouped by read through an offset array, so that the
+ * device -> host stream that bounds the end-to-end rate is halved (SURVEY 8d counts an 8-byte hit
+ * record).  Anchor word:
+ *     bits 63..36  pos    position of the k-mer in its read            (reads shorter than 2^28 bases)
+ *     bits 35.. 2  gpos   contig_base[tid] + cpos, contig_base[i] = sum of the lengths of contigs 0..i-1
+ *                         in the order they were given to gcg_table_build* (fewer than 2^34 contig bases)
+ *     bit 1 ONT_KMER_REV (def.h:108), bit 0 KMER_REV of the contig occurrence (def.h:52)
+ * read_off[r] .. read_off[r+1] are the anchors of read r (sorted by pos); read_off has n_read + 1
+ * entries.  Same anchors, same order, same ONT-side multiplicity as gcg_search.  Inputs beyond the bit
+ * budget return GCG_ERANGE (nothing has been searched): fall back to gcg_search.
+ * Both arrays are library-owned pinned memory, released with gcg_free. */
+int  gcg_search_compact (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
+                         int64_t n_read, int k, uint64_t ** anchors_out, int64_t ** read_off_out, int64_t * n_anchor);
+/* device-resident form (bench `value`); download with gcg_hits_download_compact (read_off: n + 1 entries) */
+int  gcg_search_seqs_compact (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * reads, int k, gcg_hits ** out);
+int  gcg_hits_download_compact (gcg_ctx * ctx, const gcg_hits * h, uint64_t * anchors, int64_t cap, int64_t * read_off);
+#define GCG_ANCHOR_POS(a)   ((int32_t) ((a) >> 36))
+#define GCG_ANCHOR_GPOS(a)  ((int64_t) (((a) >> 2) & 0x3FFFFFFFFULL))
+#define GCG_ANCHOR_FLAGS(a) ((uint32_t) ((a) & 3u))
 
 /* ------------------------------------------------------------------ partitioned table  */
 /* Multi-GPU form of the same tables (BASELINE configs[3]): the reference splits its

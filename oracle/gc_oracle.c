@@ -200,6 +200,65 @@ int64_t gco_search (gco_table * t, const char * buf, const int64_t * off, int64_
 }
 
 /* ------------------------------------------------------------------------------------------
+ * 3b. partition id of a k-mer and un-anchored segments of a read
+ * ---------------------------------------------------------------------------------------- */
+
+/* crc32.h:15-81 restated: the table there is the reflected CRC-32 of polynomial 0xEDB88320 (zlib's);
+ * crc32(0, buf, len) starts from ~0, folds one byte per step through the table, returns ~crc.
+ * kmer.h:46-49: kseq_crc32 runs it over the 8 bytes of the kseq1_t as they lie in memory (little
+ * endian on the x86-64 the reference runs on).  kmer.c:88,110: hs_id = that % n_thread. */
+static uint32_t gco_crc_table[256];
+static int gco_crc_ready = 0;
+static void gco_crc_init (void)
+{
+  uint32_t i, c;
+  int j;
+  for (i = 0; i < 256; ++i) {
+    c = i;
+    for (j = 0; j < 8; ++j) c = (c & 1) ? (0xEDB88320u ^ (c >> 1)) : (c >> 1);
+    gco_crc_table[i] = c;
+  }
+  gco_crc_ready = 1;
+}
+
+uint32_t gco_kseq_crc32 (uint64_t kseq)
+{
+  uint32_t crc = 0 ^ 0xffffffffu;
+  int b;
+  if (!gco_crc_ready) gco_crc_init ();
+  for (b = 0; b < 8; ++b) {
+    /* crc32.h:77: the byte is read through a `char *` (signed), the xor is masked with 0xff afterwards */
+    char byte = (char) (kseq >> (8 * b));
+    crc = gco_crc_table[((uint32_t) crc ^ (uint32_t) byte) & 0xff] ^ (crc >> 8);
+  }
+  return crc ^ 0xffffffffu;
+}
+
+void gco_hs_id (const uint64_t * kseq, int64_t n, int32_t n_thread, int32_t * hs_id_out)
+{
+  int64_t i;
+  for (i = 0; i < n; ++i) hs_id_out[i] = (int32_t) (gco_kseq_crc32 (kseq[i]) % (uint32_t) n_thread);
+}
+
+/* ont.c:264-309 find_unankor_segs: okmers[] holds one entry per BASE of the read (ont.c:489-491
+ * resizes to r->l), anchored[i] != 0 where okmers[i].kmer != NULL.  A segment opens at the first
+ * un-anchored index after an anchored one (or at 0) and closes at the next anchored index (or at
+ * n).  Writes {beg,end} pairs; returns the number of segments (only the first cap are stored). */
+int64_t gco_unanchored_segs (const uint8_t * anchored, int64_t n, int32_t * beg_end_out, int64_t cap)
+{
+  int64_t i, n_seg = 0;
+  int prev_anchored = 1, open = 0;
+  for (i = 0; i < n; ++i) {
+    int cur = anchored[i] != 0;
+    if (!prev_anchored && cur) { if (n_seg - 1 < cap) beg_end_out[2 * (n_seg - 1) + 1] = (int32_t) i; open = 0; }
+    else if (prev_anchored && !cur) { if (n_seg < cap) beg_end_out[2 * n_seg] = (int32_t) i; ++n_seg; open = 1; }
+    prev_anchored = cur;
+  }
+  if (open && n_seg - 1 < cap) beg_end_out[2 * (n_seg - 1) + 1] = (int32_t) n;
+  return n_seg;
+}
+
+/* ------------------------------------------------------------------------------------------
  * 4. Smith-Waterman (sw.c) + CIGAR (cigar.c)
  * ---------------------------------------------------------------------------------------- */
 #define GCO_SW_M 1   /* sw.c:41-43 */

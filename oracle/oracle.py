@@ -98,6 +98,11 @@ class Oracle:
         L.gco_cigar2ref_len.argtypes = [C.c_void_p, C.c_int32]
         L.gco_cigar2qry_len.restype = C.c_int32
         L.gco_cigar2qry_len.argtypes = [C.c_void_p, C.c_int32]
+        L.gco_hs_id.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+        L.gco_kseq_crc32.restype = C.c_uint32
+        L.gco_kseq_crc32.argtypes = [C.c_uint64]
+        L.gco_unanchored_segs.restype = C.c_int64
+        L.gco_unanchored_segs.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
 
     # ---- k-mers -------------------------------------------------------------------------
     def chop(self, seq: np.ndarray, k: int):
@@ -108,6 +113,22 @@ class Oracle:
         got = self.L.gco_chop(_as_char_p(seq), len(seq), k, ks.ctypes.data, rv.ctypes.data)
         assert got == n
         return ks, rv
+
+    def hs_id(self, kseq: np.ndarray, n_thread: int) -> np.ndarray:
+        """kmer_t.hs_id = crc32 of the canonical k-mer's 8 bytes % n_thread (kmer.c:88, crc32.h:70-81)"""
+        kseq = np.ascontiguousarray(kseq, dtype=np.uint64)
+        out = np.zeros(len(kseq), dtype=np.int32)
+        self.L.gco_hs_id(kseq.ctypes.data, len(kseq), n_thread, out.ctypes.data)
+        return out
+
+    def unanchored_segs(self, read_len: int, anchored_pos) -> np.ndarray:
+        """okseq->segs of one read after find_unankor_segs (ont.c:264-309): int32 [n_seg, 2] of {beg, end}"""
+        a = np.zeros(max(read_len, 1), dtype=np.uint8)
+        if len(anchored_pos):
+            a[np.asarray(anchored_pos, dtype=np.int64)] = 1
+        out = np.zeros((read_len // 2 + 2, 2), dtype=np.int32)
+        n = self.L.gco_unanchored_segs(a.ctypes.data, read_len, out.ctypes.data, len(out))
+        return out[:n].copy()
 
     @staticmethod
     def concat(seqs):
@@ -279,6 +300,22 @@ def run_ref_kmer(fa: str, fq: str, k: int, prefix: str, n_thread: int = 4, dump:
     table = np.fromfile(prefix + ".table.bin", dtype=TABLE_DTYPE) if dump >= 2 else None
     ctgk = np.fromfile(prefix + ".ctgk.bin", dtype=CTGK_DTYPE) if dump >= 2 else None
     return info, hits, table, ctgk
+
+
+def read_hsid(prefix: str) -> np.ndarray:
+    """<prefix>.hsid.bin of a dump level 2 harness run: kmer_t.hs_id per contig position"""
+    return np.fromfile(prefix + ".hsid.bin", dtype=np.int32)
+
+
+def read_segs(prefix: str):
+    """<prefix>.segs.bin of a dump level >= 1 harness run -> list (per read) of int32 [n_seg, 2] arrays"""
+    raw = np.fromfile(prefix + ".segs.bin", dtype=np.int32)
+    out, i = [], 0
+    while i < len(raw):
+        n = int(raw[i])
+        out.append(raw[i + 1:i + 1 + 2 * n].reshape(n, 2).copy())
+        i += 1 + 2 * n
+    return out
 
 
 def run_ref_gc(fa: str, fq: str, workdir: str, n_thread: int = 4):

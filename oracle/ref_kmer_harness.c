@@ -12,6 +12,16 @@
  *                     u64 kseq, i32 multi, i32 tid, i32 pos, u16 flag, i16 kmer_len   (first occurrence)
  *                   + <prefix>.ctgk.bin   one 20-byte record per contig position:
  *                     u64 kseq, i32 tid, i32 pos, u16 flag, i16 kmer_len
+ *                   + <prefix>.hsid.bin   i32 hs_id per contig position (= crc32(kseq) % n_thread, kmer.c:88)
+ *     dump_level >= 1 also writes <prefix>.segs.bin: per read i32 n_seg, then n_seg x {i32 beg, i32 end}
+ *                     (okseq->segs after find_unankor_segs, ont.c:264-309)
+ *
+ * The same source, compiled with -DGCG_SHIM_HARNESS and linked against the replacement files of
+ * superplus_b200/gap_closer/ instead of the reference's kmer.c / hash.c / ont.c (target shim_kmer of
+ * that directory's Makefile), dumps what the B200 path leaves in the same host structures; the GPU
+ * tests compare the two sets of files byte for byte.  In that build the host tables are empty handles
+ * (the table lives in HBM), so table.bin and the recomputed statistics are skipped — the statistics
+ * are compared through the lines kmer_stat / kmer_stat2 print.
  */
 #include <stdio.h>
 #include <stdint.h>
@@ -96,6 +106,7 @@ int main (int argc, char * argv[])
 
   /* the four integers, recomputed exactly as kmer.c:265-312 does */
   int64_t st[4] = {0, 0, 0, 0};
+#ifndef GCG_SHIM_HARNESS
   for (i = 0; i < n_thread; ++i) {
     xh_t * h = khashs[i];
     st[0] += h->cnt;
@@ -104,6 +115,7 @@ int main (int argc, char * argv[])
     st[2] += h->cnt;
     for (p = 0; p < (int64_t) h->cnt; ++p) if (h->pool[p].multi == 1) ++st[3];
   }
+#endif
 
   int64_t n_ctg_kmers = 0, n_ctg_bases = 0, n_ont_kmers = 0, n_ont_bases = 0, n_hits = 0;
   for (r = 0; r < mp_cnt (ctgs); ++r) {
@@ -134,6 +146,19 @@ int main (int argc, char * argv[])
       }
     }
     fclose (fp);
+    snprintf (path, sizeof path, "%s.segs.bin", prefix);
+    fp = ckopen (path, "wb");
+    for (r = 0; r < mp_cnt (okseqs); ++r) {
+      okseq_t * ok = mp_at (okseq, okseqs, r);
+      int32_t ns = (int32_t) mp_cnt (ok->segs);
+      fwrite (&ns, 4, 1, fp);
+      for (p = 0; p < ns; ++p) {
+        ont_seg_t * sg = mp_at (oseg, ok->segs, p);
+        int32_t be[2] = { sg->beg, sg->end };
+        fwrite (be, 4, 2, fp);
+      }
+    }
+    fclose (fp);
   } else {
     for (r = 0; r < mp_cnt (okseqs); ++r) {
       okseq_t * ok = mp_at (okseq, okseqs, r);
@@ -146,6 +171,7 @@ int main (int argc, char * argv[])
   if (dump >= 2) {
     snprintf (path, sizeof path, "%s.table.bin", prefix);
     FILE * fp = ckopen (path, "wb");
+#ifndef GCG_SHIM_HARNESS
     for (i = 0; i < n_thread; ++i) {
       xh_t * h = khashs[i];
       for (p = 0; p < (int64_t) h->cnt; ++p) {
@@ -158,6 +184,14 @@ int main (int argc, char * argv[])
         fwrite (&km->flag, 2, 1, fp);
         fwrite (&km->kmer_len, 2, 1, fp);
       }
+    }
+#endif
+    fclose (fp);
+    snprintf (path, sizeof path, "%s.hsid.bin", prefix);
+    fp = ckopen (path, "wb");
+    for (r = 0; r < mp_cnt (ctgs); ++r) {
+      ctg_t * c = mp_at (ctg, ctgs, r);
+      for (p = 0; p < c->n_kmer; ++p) fwrite (&c->kmers[p].hs_id, 4, 1, fp);
     }
     fclose (fp);
     snprintf (path, sizeof path, "%s.ctgk.bin", prefix);

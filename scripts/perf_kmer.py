@@ -18,7 +18,7 @@ for it in range(int(sys.argv[3]) if len(sys.argv) > 3 else 4):
     ctx.prof_reset()
     t0 = time.time()
     t = ctx.table_build(cs, k)
-    n = ctx.search_device(t, rs)
+    n = ctx.search_device_compact(t, rs) if os.environ.get('GCG_SEARCH_FUSED', '1') != '0' else ctx.search_device(t, rs)
     st = t.stats()
     dt = time.time() - t0
     rep = ctx.prof_report()
@@ -26,9 +26,12 @@ for it in range(int(sys.argv[3]) if len(sys.argv) > 3 else 4):
     for kname, (ms, nl) in sorted(rep.items()):
         print("   %-18s %9.4f ms  x%d" % (kname, ms, nl))
     nk = rs.kmers(k)
+    if "k45_fused" in rep:
+        ms = rep["k45_fused"][0]
+        print("   K4+K5 fused: %.1f G k-mers/s ; algorithmic %.1f GB/s" % (nk / ms / 1e6, (16.25 * nk + 16 * n) / ms / 1e6))
     if "k45_search" in rep:
-        ms = rep["k45_search"][0]
-        print("   search: %.1f G k-mers/s ; algorithmic %.1f GB/s" % (nk / ms / 1e6, (16.25 * nk + 16 * n) / ms / 1e6))
+        ms = rep["k45_search"][0] + rep.get("hits_emit", (0, 0))[0] + sum(rep.get(x, (0, 0))[0] for x in ("scan_reduce", "scan_blocksums", "scan_apply"))
+        print("   K4+K5 two-pass (probe + scan + emit): %.1f G k-mers/s ; algorithmic %.1f GB/s" % (nk / ms / 1e6, (16.25 * nk + 16 * n) / ms / 1e6))
     if "k23_build" in rep:
         ms = rep["k23_build"][0]
         print("   build : %.2f G k-mers/s ; algorithmic %.1f GB/s" % (cs.kmers(k) / ms / 1e6, 32.25 * cs.kmers(k) / ms / 1e6))
@@ -36,4 +39,10 @@ for it in range(int(sys.argv[3]) if len(sys.argv) > 3 else 4):
 t0 = time.time()
 tb = ctx.table_build(cs, k)
 hits = ctx.search_host(tb, inp.reads)
-print("e2e host search %.3fs hits %d" % (time.time() - t0, len(hits)))
+print("e2e host search (16-byte anchors) %.3fs hits %d" % (time.time() - t0, len(hits)))
+for it in range(3):
+    tb2 = ctx.table_build(cs, k)
+    t0 = time.time()
+    a, ro = ctx.search_host_compact(tb2, inp.reads)
+    print("e2e host search (compact anchors) %.4fs hits %d" % (time.time() - t0, len(a)))
+    tb2.free()

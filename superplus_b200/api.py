@@ -30,6 +30,7 @@ EXPORTS = [
     "gcg_chop_contigs", "gcg_table_build_seqs", "gcg_table_build", "gcg_table_free", "gcg_table_stats",
     "gcg_table_size", "gcg_table_dump", "gcg_table_clone", "gcg_table_merge_ont",
     "gcg_search_seqs", "gcg_hits_count", "gcg_hits_download", "gcg_hits_free", "gcg_search", "gcg_free",
+    "gcg_search_compact", "gcg_search_seqs_compact", "gcg_hits_download_compact", "gcg_selftest_workers",
     "gcg_sw_batch", "gcg_sw_batch_multi", "gcg_swbatch_upload", "gcg_swbatch_align", "gcg_swbatch_download", "gcg_swbatch_cells",
     "gcg_swbatch_path_counts", "gcg_swbatch_free",
     "gcg_kmer_owner", "gcg_seqs_tiles", "gcg_route_plan", "gcg_route_kmers", "gcg_route_keys", "gcg_route_records",
@@ -148,6 +149,9 @@ def load_library(path: str = LIB_PATH):
     L.gcg_hits_free.argtypes = [vp]
     L.gcg_search.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(i64)]
     L.gcg_free.argtypes = [vp]
+    L.gcg_search_compact.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
+    L.gcg_search_seqs_compact.argtypes = [vp, vp, vp, C.c_int, C.POINTER(vp)]
+    L.gcg_hits_download_compact.argtypes = [vp, vp, vp, i64, vp]
     L.gcg_sw_batch.argtypes = [vp, C.POINTER(SWParams), C.c_int, vp, vp, vp, vp, i64, vp, C.POINTER(vp), C.POINTER(i64)]
     L.gcg_sw_batch_multi.argtypes = [vp, C.c_int, C.POINTER(SWParams), C.c_int, vp, vp, vp, vp, i64, vp, C.POINTER(vp), C.POINTER(i64)]
     L.gcg_swbatch_upload.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(vp)]
@@ -329,6 +333,43 @@ class Context:
         n = int(self.L.gcg_hits_count(h))
         self.L.gcg_hits_free(h)
         return n
+
+    def search_compact(self, table: "KmerTable", reads: "Seqs"):
+        """device-resident compact search -> (anchors uint64[n], read_off int64[n_read + 1])"""
+        h = C.c_void_p()
+        self._chk(self.L.gcg_search_seqs_compact(self.h, table.h, reads.h, table.k, C.byref(h)))
+        try:
+            n = int(self.L.gcg_hits_count(h))
+            anchors = np.zeros(n, dtype=np.uint64)
+            read_off = np.zeros(reads.n + 1, dtype=np.int64)
+            self._chk(self.L.gcg_hits_download_compact(self.h, h, anchors.ctypes.data if n else None, n, read_off.ctypes.data))
+        finally:
+            self.L.gcg_hits_free(h)
+        return anchors, read_off
+
+    def search_device_compact(self, table: "KmerTable", reads: "Seqs") -> int:
+        """compact search leaving the anchors on the device (bench `value`); returns the anchor count"""
+        h = C.c_void_p()
+        self._chk(self.L.gcg_search_seqs_compact(self.h, table.h, reads.h, table.k, C.byref(h)))
+        n = int(self.L.gcg_hits_count(h))
+        self.L.gcg_hits_free(h)
+        return n
+
+    def search_host_compact(self, table: "KmerTable", reads):
+        """the call the shim makes: host pointers in, pinned compact anchors + per-read offsets out (gcg_search_compact)"""
+        arrs = [np.ascontiguousarray(s, dtype=np.uint8) for s in reads]
+        n = len(arrs)
+        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+        lens = np.array([len(a) for a in arrs], dtype=np.int32)
+        ap, rp, na = C.c_void_p(), C.c_void_p(), C.c_int64()
+        self._chk(self.L.gcg_search_compact(self.h, table.h, C.cast(ptrs, C.c_void_p), lens.ctypes.data, n, table.k, C.byref(ap), C.byref(rp), C.byref(na)))
+        try:
+            anchors = np.frombuffer((C.c_char * (na.value * 8)).from_address(ap.value), dtype=np.uint64).copy() if na.value else np.zeros(0, np.uint64)
+            read_off = np.frombuffer((C.c_char * ((n + 1) * 8)).from_address(rp.value), dtype=np.int64).copy()
+        finally:
+            self.L.gcg_free(ap)
+            self.L.gcg_free(rp)
+        return anchors, read_off
 
     def search_host(self, table: "KmerTable", reads) -> np.ndarray:
         """the shim-facing call: host pointers in, pinned host anchors out (gcg_search)"""
@@ -631,6 +672,20 @@ class SWBatch(_Handle):
             self.ctx.L.gcg_free(pool)
         cigs = [cp[int(r["cigar_off"]):int(r["cigar_off"]) + int(r["n_cigar"])] for r in res]
         return res, cigs
+
+
+def expand_compact(anchors: np.ndarray, read_off: np.ndarray, contig_lens) -> np.ndarray:
+    """compact anchors (gcgpu.h) -> the same anchors as HIT_DTYPE records, for comparison with gcg_search"""
+    out = np.zeros(len(anchors), dtype=HIT_DTYPE)
+    n_read = len(read_off) - 1
+    out["read"] = np.repeat(np.arange(n_read, dtype=np.int32), np.diff(read_off))
+    out["pos"] = (anchors >> np.uint64(36)).astype(np.int32)
+    gpos = ((anchors >> np.uint64(2)) & np.uint64(0x3FFFFFFFF)).astype(np.int64)
+    cbase = np.concatenate([[0], np.cumsum(np.asarray(contig_lens, dtype=np.int64))])
+    tid = np.searchsorted(cbase, gpos, side="right") - 1
+    out["tid"] = tid.astype(np.int32)
+    out["cpos_flags"] = (((gpos - cbase[tid]) << 2) | (anchors & np.uint64(3)).astype(np.int64)).astype(np.uint32)
+    return out
 
 
 def split_reads_by_bases(lens, n_share: int):

@@ -78,7 +78,6 @@ extern "C" void gcg_destroy (gcg_ctx * ctx)
     if (ctx->stage.h[i]) cudaFreeHost (ctx->stage.h[i]);
     if (ctx->stage.d[i]) cudaFree (ctx->stage.d[i]);
     if (ctx->stage.ev[i]) cudaEventDestroy (ctx->stage.ev[i]);
-    if (ctx->ev_split[i]) cudaEventDestroy (ctx->ev_split[i]);
   }
   gcg_pipe_free (ctx);
   gcg_workers_destroy (ctx->workers);

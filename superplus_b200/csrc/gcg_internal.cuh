@@ -62,7 +62,7 @@ struct gcg_ctx {
   // small device scratch for reductions / counters
   unsigned long long * d_counters = nullptr;   // 64 x u64 ([16..48) = per-partition totals of gcg_route_plan)
   unsigned long long * h_counters = nullptr;   // pinned mirror
-  cudaEvent_t ev_split[2] = {nullptr, nullptr};  // "count of half A / B has landed" (gcg_search_seqs), created on first use
+  double last_anchor_frac = 0.0;               // anchors per ONT k-mer of the previous device-resident search (sizes the next result buffer)
   // parked device blocks by size class (see gcg_dmalloc)
   std::map<size_t, std::vector<void *>> dparked;
   std::unordered_map<void *, size_t> dclass;   // every block handed out or parked -> its class size
@@ -149,12 +149,18 @@ struct gcg_table {
   uint32_t filter_words = 0;
   int filter_k3 = 0;
   bool filter_valid = false;               // cleared by every insert
+  // first base of every contig in the concatenated scaffold coordinate (compact anchors); NULL for an owner-side partition
+  int64_t * d_cbase = nullptr;
+  int64_t n_contig = 0, n_cbases = 0;
 };
 
 struct gcg_hits {
   gcg_ctx * ctx = nullptr;
   int64_t n = 0;
-  gcg_hit * d_hits = nullptr;
+  gcg_hit * d_hits = nullptr;               // fmt 0: gcg_hit[n]; fmt 1: uint64_t[n] compact anchors
+  int fmt = 0;
+  int64_t n_seq = 0;
+  long long * d_read_off = nullptr;         // fmt 1: [n_seq + 1], -1 for reads without a word
 };
 
 #define GCG_KEY_MASK 0x3FFFFFFFFFFFFFFFULL

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -67,10 +68,14 @@ void gcg_workers_destroy (gcg_workers * w)
   delete w;
 }
 
+// The pool holds ONE job at a time.  A second job offered while an asynchronous one is still out
+// (gcg_workers_start without its gcg_workers_wait) must not touch job / n_task / next / running — that
+// would drop the tasks of the first job nobody has taken yet — so it runs on the calling thread.
 void gcg_workers_run (gcg_workers * w, int64_t n_task, const std::function<void (int64_t)> & fn)
 {
   if (!w || w->th.empty () || n_task <= 1) { for (int64_t i = 0; i < n_task; ++i) fn (i); return; }
   std::unique_lock<std::mutex> lk (w->mu);
+  if (w->job != nullptr) { lk.unlock (); for (int64_t i = 0; i < n_task; ++i) fn (i); return; }
   w->job = &fn; w->n_task = n_task; w->next = 0; w->running = 0;
   ++w->gen;
   w->cv_go.notify_all ();
@@ -91,7 +96,8 @@ void gcg_workers_run (gcg_workers * w, int64_t n_task, const std::function<void 
 void gcg_workers_start (gcg_workers * w, int64_t n_task, const std::function<void (int64_t)> & fn)
 {
   if (!w || w->th.empty ()) { for (int64_t i = 0; i < n_task; ++i) fn (i); return; }
-  std::lock_guard<std::mutex> lk (w->mu);
+  std::unique_lock<std::mutex> lk (w->mu);
+  if (w->job != nullptr) { lk.unlock (); for (int64_t i = 0; i < n_task; ++i) fn (i); return; }   // (see gcg_workers_run)
   w->job = &fn; w->n_task = n_task; w->next = 0; w->running = 0;
   ++w->gen;
   w->cv_go.notify_all ();
@@ -101,8 +107,29 @@ void gcg_workers_wait (gcg_workers * w)
 {
   if (!w || w->th.empty ()) return;
   std::unique_lock<std::mutex> lk (w->mu);
+  if (w->job == nullptr) return;                    // nothing out (the job ran inline, or was waited for already)
   w->cv_done.wait (lk, [&] () { return w->running == 0 && w->next >= w->n_task; });
   w->job = nullptr;
+}
+
+// Self-test of the one-job rule (tests/test_host_logic.py): an asynchronous job of n_async slow tasks is
+// started, a synchronous job of n_sync tasks is offered while it is out, then the first is waited for.
+// Returns tasks executed: n_async * 1000 + n_sync when nothing was dropped.
+extern "C" int64_t gcg_selftest_workers (int n_thread, int n_async, int n_sync)
+{
+  gcg_workers * w = gcg_workers_create (n_thread);
+  std::vector<int> a ((size_t) n_async, 0), b ((size_t) n_sync, 0);
+  std::function<void (int64_t)> fa = [&] (int64_t i) { std::this_thread::sleep_for (std::chrono::milliseconds (2)); a[(size_t) i] += 1; };
+  std::function<void (int64_t)> fb = [&] (int64_t i) { b[(size_t) i] += 1; };
+  gcg_workers_start (w, n_async, fa);
+  gcg_workers_run (w, n_sync, fb);
+  gcg_workers_wait (w);
+  gcg_workers_run (w, n_sync, fb);                  // and the pool still works afterwards
+  gcg_workers_destroy (w);
+  int64_t na = 0, nb = 0;
+  for (int v : a) na += v;
+  for (int v : b) nb += v;
+  return na * 1000 + nb / 2;
 }
 
 void gcg_copy_stream (void * dst_, const void * src_, size_t n)

@@ -144,6 +144,112 @@ k23_build_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
 // (32 registers, 8 blocks per SM.  The kernel sits at 85 % of the L1 wavefront rate: a random 32-byte
 // bucket load is one wavefront per lane, 138 M of them at one per clock and SM are 0.47 ms at cfg2.
 // Asking for fewer, fatter blocks to keep four loads in flight per thread measured slower, 0.60 ms.)
+// The probe of one 32-word tile by one warp: returns the lane's 32-bit anchor mask of word (tile << 5) + lane
+// (bit j: the canonical k-mer at position p0 + j is in the table with multiplicity 1).  *seq_out / *p0_out
+// receive the word's read index and its first position (undefined for words past the end).
+struct k4_smem { uint32_t excl[K4_WARPS][33], pend[K4_WARPS][32], add[K4_WARPS][32]; };
+
+template <bool FILTER, int KC>
+__device__ __forceinline__ uint32_t
+k4_probe_tile (k4_smem & sm, const int64_t tile, const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff,
+               const int32_t * __restrict__ len, const int32_t * __restrict__ tile_seq, const int64_t n_seq, const int64_t n_words, const int k,
+               const unsigned long long * __restrict__ keys, const uint32_t n_bucket,
+               const uint32_t * __restrict__ filter, const uint32_t filter_words, const int filter_k3,
+               uint64_t * pk_out, int32_t * seq_out, int32_t * p0_out)
+{
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t w = (tile << 5) + lane;
+  uint32_t mymask = 0, pend = 0;
+  int nvalid = 0;
+  uint64_t pk = 0;
+  int32_t sq = 0, p0 = 0;
+  if (w < n_words) {
+    int64_t s = find_seq_from (woff, n_seq, w, __ldg (tile_seq + tile));
+    int32_t L = __ldg (len + s);
+    p0 = (int32_t) ((w - __ldg (woff + s)) << 5);
+    sq = (int32_t) s;
+    nvalid = L - k + 1 - p0;
+    nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
+    pk = __ldg (packed + w);
+  }
+  *pk_out = pk; *seq_out = sq; *p0_out = p0;
+  if (nvalid) {
+    kroll r;
+    r.init (pk, __ldg (packed + w + 1), k);
+    for (int j0 = 0; j0 < nvalid; j0 += K4_UNROLL) {
+      unsigned long long key[K4_UNROLL];
+      uint32_t fp[K4_UNROLL];
+      bucket4 q[K4_UNROLL];
+      if (FILTER) {
+        uint32_t hh[K4_UNROLL], fw[K4_UNROLL];
+#pragma unroll
+        for (int u = 0; u < K4_UNROLL; ++u) {
+          if (j0 + u) r.step ();
+          key[u] = (r.fwd < r.rc ? r.fwd : r.rc) + 1ULL;
+          hh[u] = kmer_hash32 (key[u] - 1ULL);
+          fp[u] = hh[u] & 3u;
+          fw[u] = __ldg (filter + __umulhi (kmer_hash32b (key[u] - 1ULL), filter_words));
+        }
+#pragma unroll
+        for (int u = 0; u < K4_UNROLL; ++u) {
+          const uint32_t m = filter_mask (hh[u], filter_k3);
+          q[u].a = q[u].b = q[u].c = q[u].d = 0ULL;        // no match, no overflow mark
+          if ((fw[u] & m) == m) q[u] = ld_bucket (keys + 4ULL * __umulhi (hh[u], n_bucket));
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < K4_UNROLL; ++u) {
+          if (j0 + u) r.step ();                     // harmless past nvalid: state is discarded
+          key[u] = (r.fwd < r.rc ? r.fwd : r.rc) + 1ULL;
+          uint32_t h = kmer_hash32 (key[u] - 1ULL);
+          fp[u] = h & 3u;
+          q[u] = ld_bucket (keys + 4ULL * __umulhi (h, n_bucket));
+        }
+      }
+      // four result bits per group at constant positions, one variable shift per group; positions
+      // past the end of the read are cleared once per word
+      uint32_t hb = 0, ob = 0;
+#pragma unroll
+      for (int u = 0; u < K4_UNROLL; ++u) {
+        hb |= bucket_has_unique (q[u], key[u]) ? (1u << u) : 0u;   // multi == 1  (ont.c:171,195)
+        ob |= bucket_ovf_bit (q[u], fp[u], u);
+      }
+      mymask |= hb << j0;
+      pend |= (ob & ~hb) << j0;
+    }
+    const uint32_t vmask = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+    mymask &= vmask; pend &= vmask;
+  }
+  // ---- the rare probes that have to look at later buckets, dealt round-robin over the lanes
+  uint32_t c = __popc (pend), x = c;
+  for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (0xffffffffu, x, o); if (lane >= o) x += y; }
+  const uint32_t total = __shfl_sync (0xffffffffu, x, 31);
+  if (total) {
+    __syncwarp ();
+    sm.excl[wid][lane] = x - c;
+    sm.pend[wid][lane] = pend;
+    sm.add[wid][lane] = 0;
+    if (lane == 31) sm.excl[wid][32] = total;
+    __syncwarp ();
+    for (uint32_t h = lane; h < total; h += 32) {
+      int lo = 0, hi = 32;                          // excl[lo] <= h < excl[hi]
+#pragma unroll
+      for (int it = 0; it < 5; ++it) { int mid = (lo + hi) >> 1; if (sm.excl[wid][mid] <= h) lo = mid; else hi = mid; }
+      const int j = __fns (sm.pend[wid][lo], 0, (int) (h - sm.excl[wid][lo]) + 1);
+      const int64_t ww = (tile << 5) + lo;
+      bool fw;
+      unsigned long long kw, key = key_at (__ldg (packed + ww), __ldg (packed + ww + 1), j, k, &fw);
+      uint32_t hs = kmer_hash32 (key - 1ULL), b = __umulhi (hs, n_bucket);
+      b = (b + 1 == n_bucket) ? 0 : b + 1;          // the home bucket has been looked at
+      unsigned long long slot = table_lookup (keys, n_bucket, b, ld_bucket (keys + 4ULL * b), key, hs & 3u, &kw);
+      if (slot != ~0ULL && !(kw & GCG_KEY_MULTI)) atomicOr (&sm.add[wid][lo], 1u << j);
+    }
+    __syncwarp ();
+    mymask |= sm.add[wid][lane];
+  }
+  return mymask;
+}
+
 template <bool FILTER, int KC>
 __global__ void __launch_bounds__ (32 * K4_WARPS)
 k45_search_kernel (const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff,
@@ -151,99 +257,167 @@ k45_search_kernel (const uint64_t * __restrict__ packed, const int64_t * __restr
                    const unsigned long long * __restrict__ keys, uint32_t n_bucket, uint32_t * __restrict__ hitmask,
                    const uint32_t * __restrict__ filter, uint32_t filter_words, int filter_k3, const int64_t tile0)
 {
-  __shared__ uint32_t s_excl[K4_WARPS][33];
-  __shared__ uint32_t s_pend[K4_WARPS][32];
-  __shared__ uint32_t s_add[K4_WARPS][32];
+  __shared__ k4_smem sm;
   const int k = KC > 0 ? KC : k_arg;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t n_tiles = (n_words + 31) >> 5;
   const int64_t wstride = (int64_t) gridDim.x * K4_WARPS;
   for (int64_t tile = tile0 + (int64_t) blockIdx.x * K4_WARPS + wid; tile < n_tiles; tile += wstride) {   // tiles [tile0, n_tiles)
+    uint64_t pk; int32_t sq, p0;
+    const uint32_t mymask = k4_probe_tile<FILTER, KC> (sm, tile, packed, woff, len, tile_seq, n_seq, n_words, k, keys, n_bucket,
+                                                       filter, filter_words, filter_k3, &pk, &sq, &p0);
     const int64_t w = (tile << 5) + lane;
-    uint32_t mymask = 0, pend = 0;
-    int nvalid = 0;
-    if (w < n_words) {
-      int64_t s = find_seq_from (woff, n_seq, w, __ldg (tile_seq + tile));
-      int32_t L = __ldg (len + s);
-      int32_t p0 = (int32_t) ((w - __ldg (woff + s)) << 5);
-      nvalid = L - k + 1 - p0;
-      nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
-    }
-    if (nvalid) {
-      kroll r;
-      r.init (__ldg (packed + w), __ldg (packed + w + 1), k);
-      for (int j0 = 0; j0 < nvalid; j0 += K4_UNROLL) {
-        unsigned long long key[K4_UNROLL];
-        uint32_t fp[K4_UNROLL];
-        bucket4 q[K4_UNROLL];
-        if (FILTER) {
-          uint32_t hh[K4_UNROLL], fw[K4_UNROLL];
-#pragma unroll
-          for (int u = 0; u < K4_UNROLL; ++u) {
-            if (j0 + u) r.step ();
-            key[u] = (r.fwd < r.rc ? r.fwd : r.rc) + 1ULL;
-            hh[u] = kmer_hash32 (key[u] - 1ULL);
-            fp[u] = hh[u] & 3u;
-            fw[u] = __ldg (filter + __umulhi (kmer_hash32b (key[u] - 1ULL), filter_words));
-          }
-#pragma unroll
-          for (int u = 0; u < K4_UNROLL; ++u) {
-            const uint32_t m = filter_mask (hh[u], filter_k3);
-            q[u].a = q[u].b = q[u].c = q[u].d = 0ULL;        // no match, no overflow mark
-            if ((fw[u] & m) == m) q[u] = ld_bucket (keys + 4ULL * __umulhi (hh[u], n_bucket));
-          }
-        } else {
-#pragma unroll
-          for (int u = 0; u < K4_UNROLL; ++u) {
-            if (j0 + u) r.step ();                     // harmless past nvalid: state is discarded
-            key[u] = (r.fwd < r.rc ? r.fwd : r.rc) + 1ULL;
-            uint32_t h = kmer_hash32 (key[u] - 1ULL);
-            fp[u] = h & 3u;
-            q[u] = ld_bucket (keys + 4ULL * __umulhi (h, n_bucket));
-          }
-        }
-        // four result bits per group at constant positions, one variable shift per group; positions
-        // past the end of the read are cleared once per word
-        uint32_t hb = 0, ob = 0;
-#pragma unroll
-        for (int u = 0; u < K4_UNROLL; ++u) {
-          hb |= bucket_has_unique (q[u], key[u]) ? (1u << u) : 0u;   // multi == 1  (ont.c:171,195)
-          ob |= bucket_ovf_bit (q[u], fp[u], u);
-        }
-        mymask |= hb << j0;
-        pend |= (ob & ~hb) << j0;
-      }
-      const uint32_t vmask = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
-      mymask &= vmask; pend &= vmask;
-    }
-    // ---- the rare probes that have to look at later buckets, dealt round-robin over the lanes
-    uint32_t c = __popc (pend), x = c;
+    if (w < n_words) hitmask[w] = mymask;
+  }
+}
+
+// =============================================================================================
+// K4+K5 in ONE pass: probe, ordered anchor index, ONT-side multiplicity and anchor records
+//   The two-pass form above (probe -> masks, prefix sum, hits_emit re-probing the anchored positions)
+//   walks the masks three times and fetches every anchor's key bucket again after 126 MB of anchor
+//   stream have pushed the table out of the L2 (ncu round 1: hits_emit 5.8 x its algorithmic DRAM
+//   bytes).  Here the warp that probed a tile also emits its anchors, microseconds later, while the
+//   buckets it hit are still in the L2:
+//     * tiles are handed out in increasing order by an atomic counter, so every tile a warp may have
+//       to wait for is already with a running warp (no co-residency assumption);
+//     * the global index of a tile's first anchor comes from a chained scan over the tiles
+//       (decoupled look-back: a tile publishes its anchor count, then sums its predecessors'
+//       published counts back to the nearest one whose inclusive prefix is known) — one 8-byte state
+//       word per tile instead of the mask / prefix arrays and three scan launches;
+//     * the anchors of a tile are dealt round-robin to the lanes in (word, bit) order, so anchors leave
+//       in (read,pos) order as coalesced stores, exactly the order of the two-pass form;
+//     * the ONT-side multiplicity (ont.c:245) is recorded by the same atomicOr that fetches (tid,pos,flag).
+//   Only anchors whose global index lies in [win_lo, win_hi) are materialised (record written,
+//   multiplicity recorded): a result buffer sized from an estimate can overflow without side effects,
+//   and the second launch that finishes the job (win_lo = old capacity) repeats nothing.
+//   FMT 0: 16-byte gcg_hit {read, pos, tid, cpos << 2 | flags}.
+//   FMT 1: 8-byte compact anchor  pos << 36 | (cbase[tid] + cpos) << 2 | flags  with read_off[read] =
+//          index of the read's first anchor (SURVEY 8d's 8-byte hit record).
+// =============================================================================================
+#define SCANST_AGG 0x4000000000000000ULL
+#define SCANST_INC 0x8000000000000000ULL
+#define SCANST_VAL 0x3FFFFFFFFFFFFFFFULL
+
+__device__ __forceinline__ unsigned long long ld_state (const unsigned long long * p)
+{
+  unsigned long long v;
+  asm volatile ("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_state (unsigned long long * p, unsigned long long v)
+{
+  asm volatile ("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+struct k45f_args {
+  const uint64_t * packed; const int64_t * woff; const int32_t * len; const int32_t * tile_seq;
+  int64_t n_seq, n_words;
+  int k;
+  const unsigned long long * keys; unsigned long long * vals; uint32_t n_bucket;
+  const uint32_t * filter; uint32_t filter_words; int filter_k3;
+  unsigned long long * tile_ctr;            // zeroed before the launch
+  unsigned long long * state;               // one word per tile, zeroed before the launch
+  void * out;                               // gcg_hit[] or uint64_t[], indexed by the global anchor index
+  unsigned long long win_lo, win_hi;
+  int32_t read_base;                        // added to the read index of FMT 0 records
+  const int64_t * cbase;                    // FMT 1: first base of every contig in the concatenated scaffold coordinate
+  long long * read_off;                     // FMT 1 (optional for FMT 0): [n_seq], pre-set to -1; written for every read that owns a word
+  unsigned long long * total_out;           // number of anchors of the launch (device or mapped host memory)
+};
+
+template <bool FILTER, int KC, int FMT>
+__global__ void __launch_bounds__ (32 * K4_WARPS)
+k45_fused_kernel (const k45f_args A)
+{
+  __shared__ k4_smem sm;
+  __shared__ uint32_t s_mask[K4_WARPS][32];
+  __shared__ uint64_t s_pk[K4_WARPS][33];
+  __shared__ int32_t s_seq[K4_WARPS][32], s_p0[K4_WARPS][32];
+  const int k = KC > 0 ? KC : A.k;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t n_tiles = (A.n_words + 31) >> 5;
+  for (;;) {
+    unsigned long long t_ = 0;
+    if (lane == 0) t_ = atomicAdd (A.tile_ctr, 1ULL);
+    const int64_t tile = (int64_t) __shfl_sync (0xffffffffu, t_, 0);
+    if (tile >= n_tiles) break;
+    uint64_t pk; int32_t sq, p0;
+    const uint32_t mymask = k4_probe_tile<FILTER, KC> (sm, tile, A.packed, A.woff, A.len, A.tile_seq, A.n_seq, A.n_words, k, A.keys, A.n_bucket,
+                                                       A.filter, A.filter_words, A.filter_k3, &pk, &sq, &p0);
+    const int64_t w = (tile << 5) + lane;
+    const uint32_t c = __popc (mymask);
+    uint32_t x = c;
     for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (0xffffffffu, x, o); if (lane >= o) x += y; }
     const uint32_t total = __shfl_sync (0xffffffffu, x, 31);
-    if (total) {
-      __syncwarp ();
-      s_excl[wid][lane] = x - c;
-      s_pend[wid][lane] = pend;
-      s_add[wid][lane] = 0;
-      if (lane == 31) s_excl[wid][32] = total;
-      __syncwarp ();
-      for (uint32_t h = lane; h < total; h += 32) {
-        int lo = 0, hi = 32;                          // s_excl[lo] <= h < s_excl[hi]
-#pragma unroll
-        for (int it = 0; it < 5; ++it) { int mid = (lo + hi) >> 1; if (s_excl[wid][mid] <= h) lo = mid; else hi = mid; }
-        const int j = __fns (s_pend[wid][lo], 0, (int) (h - s_excl[wid][lo]) + 1);
-        const int64_t ww = (tile << 5) + lo;
-        bool fw;
-        unsigned long long kw, key = key_at (__ldg (packed + ww), __ldg (packed + ww + 1), j, k, &fw);
-        uint32_t hs = kmer_hash32 (key - 1ULL), b = __umulhi (hs, n_bucket);
-        b = (b + 1 == n_bucket) ? 0 : b + 1;          // the home bucket has been looked at
-        unsigned long long slot = table_lookup (keys, n_bucket, b, ld_bucket (keys + 4ULL * b), key, hs & 3u, &kw);
-        if (slot != ~0ULL && !(kw & GCG_KEY_MULTI)) atomicOr (&s_add[wid][lo], 1u << j);
+    // ---- chained scan over the tiles: exclusive prefix of this tile
+    unsigned long long base = 0;
+    if (tile > 0) {
+      if (lane == 0) st_state (A.state + tile, SCANST_AGG | total);
+      int64_t j = tile - 1;
+      for (;;) {
+        const int64_t idx = j - lane;                   // lane 0 looks at the nearest predecessor
+        const unsigned long long st = idx >= 0 ? ld_state (A.state + idx) : SCANST_INC;   // before tile 0: inclusive prefix 0
+        const uint32_t inc = __ballot_sync (0xffffffffu, (st & SCANST_INC) != 0);
+        const uint32_t none = __ballot_sync (0xffffffffu, (st & (SCANST_INC | SCANST_AGG)) == 0);
+        const int f = inc ? __ffs (inc) - 1 : 32;       // nearest tile with a known inclusive prefix
+        const uint32_t need = f < 31 ? ((2u << f) - 1u) : 0xffffffffu;
+        if (none & need) { __nanosleep (40); continue; }     // a tile nearer than that has not published yet
+        const unsigned long long v = (lane <= f) ? (st & SCANST_VAL) : 0ULL;
+        unsigned long long sum = v;
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync (0xffffffffu, sum, o);
+        base += sum;
+        if (f < 32) break;
+        j -= 32;
       }
-      __syncwarp ();
-      mymask |= s_add[wid][lane];
     }
-    if (w < n_words) hitmask[w] = mymask;
+    if (lane == 0) {
+      st_state (A.state + tile, SCANST_INC | (base + total));
+      if (tile == n_tiles - 1) *A.total_out = base + total;
+    }
+    if (A.read_off != nullptr && w < A.n_words && p0 == 0) A.read_off[sq] = (long long) (base + (x - c));
+    if (total == 0) continue;
+    // ---- emit: the tile's anchors in (word, bit) order, 32 per round
+    __syncwarp ();
+    sm.excl[wid][lane] = x - c;
+    s_mask[wid][lane] = mymask;
+    s_pk[wid][lane] = pk;
+    s_seq[wid][lane] = sq;
+    s_p0[wid][lane] = p0;
+    if (lane == 31) { sm.excl[wid][32] = total; s_pk[wid][32] = w + 1 <= A.n_words ? __ldg (A.packed + w + 1) : 0ULL; }   // (slack word at n_words)
+    __syncwarp ();
+    for (uint32_t h = lane; h < total; h += 32) {
+      const unsigned long long g = base + h;
+      if (g < A.win_lo || g >= A.win_hi) continue;
+      int lo = 0, hi = 32;                          // excl[lo] <= h < excl[hi]
+#pragma unroll
+      for (int it = 0; it < 5; ++it) { int mid = (lo + hi) >> 1; if (sm.excl[wid][mid] <= h) lo = mid; else hi = mid; }
+      const int j = __fns (s_mask[wid][lo], 0, (int) (h - sm.excl[wid][lo]) + 1);
+      bool fw;
+      unsigned long long kw;
+      const unsigned long long key = key_at (s_pk[wid][lo], s_pk[wid][lo + 1], j, k, &fw);
+      const uint32_t hs = kmer_hash32 (key - 1ULL), b = __umulhi (hs, A.n_bucket);
+      const bucket4 q = ld_bucket (A.keys + 4ULL * b);
+      const int f = bucket_find (q, key, &kw);
+      const unsigned long long slot = f >= 0 ? 4ULL * b + (unsigned) f
+                                             : table_lookup (A.keys, A.n_bucket, b, q, key, hs & 3u, &kw);   // walks on to the overflow buckets
+      // one atomic both records the anchor (ONT-side multiplicity, ont.c:245) and returns (tid, pos, flag)
+      const unsigned long long v = atomicOr (A.vals + slot, GCG_VAL_ONT1);
+      if ((v & (GCG_VAL_ONT1 | GCG_VAL_ONT2)) == GCG_VAL_ONT1) atomicOr (A.vals + slot, GCG_VAL_ONT2);
+      const uint32_t tid = (uint32_t) (v >> 32) & 0x7FFFFFFFu, cpos = (uint32_t) (v >> 1) & 0x3FFFFFFFu;
+      const uint32_t flags = (uint32_t) (v & 1ULL) | (fw ? 0u : 2u);
+      if (FMT == 0) {
+        int4 hh;                                    // gcg_hit {read, pos, tid, cpos_flags} as one 16-byte store
+        hh.x = s_seq[wid][lo] + A.read_base;
+        hh.y = s_p0[wid][lo] + j;
+        hh.z = (int32_t) tid;
+        hh.w = (int32_t) ((cpos << 2) | flags);
+        __stcs (reinterpret_cast<int4 *> (A.out) + g, hh);
+      } else {
+        const unsigned long long gpos = (unsigned long long) __ldg (A.cbase + tid) + cpos;
+        __stcs (reinterpret_cast<unsigned long long *> (A.out) + g,
+                ((unsigned long long) (uint32_t) (s_p0[wid][lo] + j) << 36) | (gpos << 2) | flags);
+      }
+    }
   }
 }
 
@@ -780,7 +954,7 @@ extern "C" int64_t gcg_seqs_kmers (const gcg_seqs * s, int k)
 extern "C" void gcg_table_free (gcg_table * t)
 {
   if (!t) return;
-  gcg_dfree (t->ctx, t->d_keys); gcg_dfree (t->ctx, t->d_vals); gcg_dfree (t->ctx, t->d_filter);
+  gcg_dfree (t->ctx, t->d_keys); gcg_dfree (t->ctx, t->d_vals); gcg_dfree (t->ctx, t->d_filter); gcg_dfree (t->ctx, t->d_cbase);
   delete t;
 }
 
@@ -818,6 +992,21 @@ extern "C" int gcg_table_build_seqs (gcg_ctx * ctx, const gcg_seqs * contigs, in
   gcg_table * t = nullptr;
   int rc = gcg_table_alloc (ctx, n_kmers, k, &t);
   if (rc) return rc;
+  {
+    // scaffold coordinate of the compact anchors: contig i starts at base cbase[i] of the concatenated contigs
+    std::vector<int64_t> cb ((size_t) contigs->n + 1);
+    int64_t run = 0;
+    for (int64_t i = 0; i < contigs->n; ++i) { cb[(size_t) i] = run; run += contigs->h_len[(size_t) i]; }
+    cb[(size_t) contigs->n] = run;
+    t->n_contig = contigs->n; t->n_cbases = run;
+    cudaError_t e;
+    if ((e = gcg_dmalloc (ctx, &t->d_cbase, cb.size () * 8)) != cudaSuccess ||
+        (e = cudaMemcpyAsync (t->d_cbase, cb.data (), cb.size () * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
+      gcg_set_error ("gcg_table_build: contig offsets: %s", cudaGetErrorString (e));
+      gcg_table_free (t);
+      return GCG_ECUDA;
+    }
+  }
   if (contigs->n_words > 0 && n_kmers > 0) {
     gcg_kscope ks (ctx, "k23_build");
     // GCG_BUILD_ILP=1|2|4: inserts in flight per thread (A/B of the kernel variants; 1 is the default and the fastest)
@@ -878,8 +1067,10 @@ extern "C" int gcg_table_clone (gcg_ctx * dst_ctx, gcg_table * src, gcg_table **
   GCG_CUDA (cudaSetDevice (dst_ctx->device));
   gcg_table * t = new gcg_table ();
   t->ctx = dst_ctx; t->k = src->k; t->n_bucket = src->n_bucket; t->n_slot = src->n_slot; t->n_inserted = src->n_inserted;
+  t->n_contig = src->n_contig; t->n_cbases = src->n_cbases;
   cudaError_t e;
-  if ((e = gcg_dmalloc (dst_ctx, &t->d_keys, t->n_slot * 8)) != cudaSuccess || (e = gcg_dmalloc (dst_ctx, &t->d_vals, t->n_slot * 8)) != cudaSuccess) {
+  if ((e = gcg_dmalloc (dst_ctx, &t->d_keys, t->n_slot * 8)) != cudaSuccess || (e = gcg_dmalloc (dst_ctx, &t->d_vals, t->n_slot * 8)) != cudaSuccess ||
+      (src->d_cbase && (e = gcg_dmalloc (dst_ctx, &t->d_cbase, (size_t) (t->n_contig + 1) * 8)) != cudaSuccess)) {
     gcg_set_error ("gcg_table_clone: cudaMalloc of %llu slots failed: %s", (unsigned long long) t->n_slot, cudaGetErrorString (e));
     gcg_table_free (t);
     return GCG_ENOMEM;
@@ -887,6 +1078,7 @@ extern "C" int gcg_table_clone (gcg_ctx * dst_ctx, gcg_table * src, gcg_table **
   // (the pre-filter is not copied: gcg_table_filter_ensure rebuilds it on the first search that wants it)
   if ((e = cudaMemcpyPeerAsync (t->d_keys, dst_ctx->device, src->d_keys, src->ctx->device, t->n_slot * 8, dst_ctx->stream)) != cudaSuccess ||
       (e = cudaMemcpyPeerAsync (t->d_vals, dst_ctx->device, src->d_vals, src->ctx->device, t->n_slot * 8, dst_ctx->stream)) != cudaSuccess ||
+      (src->d_cbase && (e = cudaMemcpyPeerAsync (t->d_cbase, dst_ctx->device, src->d_cbase, src->ctx->device, (size_t) (t->n_contig + 1) * 8, dst_ctx->stream)) != cudaSuccess) ||
       (e = cudaStreamSynchronize (dst_ctx->stream)) != cudaSuccess) {
     gcg_set_error ("gcg_table_clone: device %d -> device %d copy failed: %s", src->ctx->device, dst_ctx->device, cudaGetErrorString (e));
     gcg_table_free (t);
@@ -1101,31 +1293,57 @@ int gcg_mask_scan (gcg_ctx * ctx, const uint32_t * d_mask, int64_t n_words, uint
 extern "C" void gcg_hits_free (gcg_hits * h)
 {
   if (!h) return;
-  gcg_dfree (h->ctx, h->d_hits);
+  gcg_dfree (h->ctx, h->d_hits); gcg_dfree (h->ctx, h->d_read_off);
   delete h;
 }
 
 extern "C" int64_t gcg_hits_count (const gcg_hits * h) { return h ? h->n : 0; }
 
-extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * reads, int k, gcg_hits ** out)
+// ---- the one-pass search: launch helper -------------------------------------------------------
+// d_state holds n_tiles + 1 words (the last one is the tile counter); both are zeroed here.
+static int launch_fused (gcg_ctx * ctx, const gcg_table * t, const uint64_t * d_packed, const int64_t * d_woff, const int32_t * d_len,
+                         const int32_t * d_tseq, int64_t n_seq, int64_t n_words, int k, int fmt, void * d_out,
+                         unsigned long long win_lo, unsigned long long win_hi, int32_t read_base, long long * d_read_off,
+                         unsigned long long * d_state, unsigned long long * total_out)
 {
-  GCG_CHECK (ctx && t && reads && out, GCG_EINVAL, "gcg_search: bad argument");
-  GCG_CHECK (k == t->k, GCG_EINVAL, "gcg_search: k=%d but the table was built with k=%d", k, t->k);
-  GCG_CHECK (reads->n < 0x7FFFFFFF, GCG_ERANGE, "gcg_search: too many reads");
-  GCG_CUDA (cudaSetDevice (ctx->device));
-  gcg_hits * h = new gcg_hits ();
-  h->ctx = ctx;
-  int64_t n_words = reads->n_words;
-  int64_t n_kmers = gcg_seqs_kmers (reads, k);
-  if (n_words == 0 || n_kmers == 0) { *out = h; return GCG_OK; }
-  if (n_kmers >= 0xFFFFFFFFLL) {
-    gcg_set_error ("gcg_search: %lld positions in one call exceed the 32-bit anchor index; split the read set (gcg_search does)", (long long) n_kmers);
-    gcg_hits_free (h);
-    return GCG_ERANGE;
-  }
+  const int64_t n_tiles = (n_words + 31) >> 5;
+  GCG_CUDA (cudaMemsetAsync (d_state, 0, (size_t) (n_tiles + 1) * 8, ctx->stream));
+  if (d_read_off) GCG_CUDA (cudaMemsetAsync (d_read_off, 0xFF, (size_t) std::max<int64_t> (n_seq, 1) * 8, ctx->stream));
+  k45f_args A;
+  A.packed = d_packed; A.woff = d_woff; A.len = d_len; A.tile_seq = d_tseq; A.n_seq = n_seq; A.n_words = n_words; A.k = k;
+  A.keys = t->d_keys; A.vals = t->d_vals; A.n_bucket = t->n_bucket;
+  const bool flt = t->filter_valid && t->filter_words;
+  A.filter = flt ? t->d_filter : nullptr; A.filter_words = flt ? t->filter_words : 0u; A.filter_k3 = flt ? t->filter_k3 : 0;
+  A.tile_ctr = d_state + n_tiles; A.state = d_state; A.out = d_out; A.win_lo = win_lo; A.win_hi = win_hi;
+  A.read_base = read_base; A.cbase = t->d_cbase; A.read_off = d_read_off; A.total_out = total_out;
+  gcg_kscope ks (ctx, "k45_fused");
+  const int grid = grid_for (ctx, n_tiles * 32, 32 * K4_WARPS, 8);
+#define K45F(F, KC) (fmt ? k45_fused_kernel<F, KC, 1> : k45_fused_kernel<F, KC, 0>)
+  auto fn = flt ? (k == 25 ? K45F (true, 25) : k == 31 ? K45F (true, 31) : K45F (true, 0))
+                : (k == 25 ? K45F (false, 25) : k == 31 ? K45F (false, 31) : K45F (false, 0));
+#undef K45F
+  fn<<<grid, 32 * K4_WARPS, 0, ctx->stream>>> (A);
+  GCG_CUDA (cudaGetLastError ());
+  return GCG_OK;
+}
 
+static size_t anchor_bytes (int fmt) { return fmt ? 8 : sizeof (gcg_hit); }
+
+static int compact_limits_ok (const gcg_table * t, int64_t max_read_len)
+{
+  GCG_CHECK (t->d_cbase != nullptr, GCG_EINVAL, "compact anchors need a table built from contigs (gcg_table_build*), not an owner-side partition");
+  GCG_CHECK (t->n_cbases < (1LL << 34) && max_read_len < (1LL << 28), GCG_ERANGE,
+             "compact anchors hold 34 bits of scaffold coordinate and 28 bits of read position (%lld contig bases, longest read %lld): use the 16-byte form",
+             (long long) t->n_cbases, (long long) max_read_len);
+  return GCG_OK;
+}
+
+// two-pass form (probe -> masks, prefix sum, emit), kept behind GCG_SEARCH_FUSED=0 for A/B timing (16-byte records only)
+static int search_seqs_two_pass (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * reads, int k, gcg_hits * h)
+{
+  const int64_t n_words = reads->n_words;
   uint32_t * d_mask = nullptr, * d_prefix = nullptr, * d_bsum = nullptr;
-  int64_t nb = (n_words + SCAN_TILE - 1) / SCAN_TILE;
+  const int64_t nb = gcg_mask_scan_blocks (n_words);
   int rc = GCG_OK;
   cudaError_t e;
   if ((e = gcg_dmalloc (ctx, &d_mask, (size_t) n_words * 4)) != cudaSuccess || (e = gcg_dmalloc (ctx, &d_prefix, (size_t) n_words * 4)) != cudaSuccess ||
@@ -1133,94 +1351,144 @@ extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * r
     gcg_set_error ("gcg_search: cudaMalloc failed: %s", cudaGetErrorString (e));
     rc = GCG_ENOMEM;
   }
-  // GCG_SEARCH_SPLIT=1 (an experiment kept behind a switch, off by default): two halves (tiles [0, T/2)
-  // and [T/2, T)), so that the host fetches one half's anchor count — which sizes the anchor buffer —
-  // while the GPU works on the other.  Queue order: probe A, scan A, count A -> host | probe B, scan B,
-  // count B -> host; the host picks up count A while probe B runs, launches emit A, and picks up count
-  // B while emit A runs.  The buffer is sized from count A with B estimated pro rata (+25 %); if B does
-  // not fit, a larger buffer takes over A's anchors first.  Measured on cfg2 (bench step): 1.206 ms in
-  // one pass, 1.278 ms in two halves — the tails of twice as many probe / scan / emit launches cost
-  // 0.053 ms of kernel time and the hidden round trip returned none of it, so the single pass stays.
-  const int64_t n_tiles = (n_words + 31) >> 5;
-  // (test hooks, read per call: GCG_SEARCH_SPLIT_MIN_TILES lowers the size from which the split is used,
-  //  GCG_SEARCH_SPLIT_TIGHT=1 sizes the buffer for half A only, so that half B always takes the regrow path)
-  const char * e_split = getenv ("GCG_SEARCH_SPLIT"), * e_min = getenv ("GCG_SEARCH_SPLIT_MIN_TILES"), * e_tight = getenv ("GCG_SEARCH_SPLIT_TIGHT");
-  const int64_t min_tiles = e_min ? std::max (2, atoi (e_min)) : 4096;
-  const bool split = e_split && atoi (e_split) == 1 && n_tiles >= min_tiles;
-  const int64_t tileA = split ? n_tiles / 2 : n_tiles, wordsA = split ? tileA << 5 : n_words;
-  auto emit = [&] (int64_t tile0, int64_t words_end, gcg_hit * dst) {
-    gcg_kscope ks (ctx, "hits_emit");
-    hits_emit_kernel<<<grid_for (ctx, (((words_end + 31) >> 5) - tile0) * 32, 256, 8), 256, 0, ctx->stream>>> (
-        reads->d_packed, reads->d_woff, reads->d_tseq, reads->n, words_end, k, t->d_keys, t->d_vals, t->n_bucket, d_mask, d_prefix, 0, dst, tile0);
-  };
   while (!rc) {
-    if ((rc = gcg_table_filter_ensure (ctx, t)) != 0) break;
-    if (split && (!ctx->ev_split[0] || !ctx->ev_split[1])) {
-      if (cudaEventCreateWithFlags (&ctx->ev_split[0], cudaEventDisableTiming) != cudaSuccess ||
-          cudaEventCreateWithFlags (&ctx->ev_split[1], cudaEventDisableTiming) != cudaSuccess) { gcg_set_error ("gcg_search: cudaEventCreate failed"); rc = GCG_ECUDA; break; }
-    }
-    // ---- queue both halves' probes and prefix sums
-    launch_k45 (ctx, t, reads->d_packed, reads->d_woff, reads->d_len, reads->d_tseq, reads->n, wordsA, k, d_mask, 0);
+    launch_k45 (ctx, t, reads->d_packed, reads->d_woff, reads->d_len, reads->d_tseq, reads->n, n_words, k, d_mask, 0);
     if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_search: kernel launch failed"); rc = GCG_ECUDA; break; }
-    if ((rc = mask_scan_launch (ctx, d_mask, wordsA, d_prefix, d_bsum, ctx->d_counters + 4)) != 0) break;
-    if (cudaMemcpyAsync (ctx->h_counters + 4, ctx->d_counters + 4, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_search: count copy failed"); rc = GCG_ECUDA; break; }
-    if (split) {
-      cudaEventRecord (ctx->ev_split[0], ctx->stream);
-      launch_k45 (ctx, t, reads->d_packed, reads->d_woff, reads->d_len, reads->d_tseq, reads->n, n_words, k, d_mask, tileA);
-      if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_search: kernel launch failed"); rc = GCG_ECUDA; break; }
-      // (the block-sum scratch is free again: scan A has finished with it before scan B starts, same stream)
-      if ((rc = mask_scan_launch (ctx, d_mask + wordsA, n_words - wordsA, d_prefix + wordsA, d_bsum, ctx->d_counters + 5)) != 0) break;
-      if (cudaMemcpyAsync (ctx->h_counters + 5, ctx->d_counters + 5, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_search: count copy failed"); rc = GCG_ECUDA; break; }
-      cudaEventRecord (ctx->ev_split[1], ctx->stream);
-    }
-    gcg_trace_mark (ctx, "  search_seqs: alloc + launch");
-    // ---- count A (probe B is running), buffer, emit A
-    if ((split ? cudaEventSynchronize (ctx->ev_split[0]) : cudaStreamSynchronize (ctx->stream)) != cudaSuccess) { gcg_set_error ("gcg_search: probe / scan failed: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; break; }
-    const int64_t nA = (int64_t) ctx->h_counters[4];
-    int64_t cap = nA;
-    if (split && !(e_tight && atoi (e_tight) == 1)) cap = nA + (int64_t) ((double) nA * (double) (n_words - wordsA) / (double) wordsA * 1.25) + 4096;
-    if (cap > 0 && (e = gcg_dmalloc (ctx, &h->d_hits, (size_t) cap * sizeof (gcg_hit))) != cudaSuccess) {
-      gcg_set_error ("gcg_search: cudaMalloc of %lld anchors failed: %s", (long long) cap, cudaGetErrorString (e));
+    int64_t n_hit = 0;
+    if ((rc = gcg_mask_scan (ctx, d_mask, n_words, d_prefix, d_bsum, &n_hit)) != 0) break;
+    if (n_hit > 0 && (e = gcg_dmalloc (ctx, &h->d_hits, (size_t) n_hit * sizeof (gcg_hit))) != cudaSuccess) {
+      gcg_set_error ("gcg_search: cudaMalloc of %lld anchors failed: %s", (long long) n_hit, cudaGetErrorString (e));
       rc = GCG_ENOMEM;
       break;
     }
-    if (nA > 0) emit (0, wordsA, h->d_hits);
-    h->n = nA;
-    // ---- count B (emit A is running), emit B behind A's anchors
-    if (split) {
-      if (cudaEventSynchronize (ctx->ev_split[1]) != cudaSuccess) { gcg_set_error ("gcg_search: probe / scan failed: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; break; }
-      const int64_t nB = (int64_t) ctx->h_counters[5];
-      if (nA + nB > cap) {                              // the estimate was too small: a larger buffer takes over A's anchors
-        gcg_hit * bigger = nullptr;
-        if ((e = gcg_dmalloc (ctx, &bigger, (size_t) (nA + nB) * sizeof (gcg_hit))) != cudaSuccess) {
-          gcg_set_error ("gcg_search: cudaMalloc of %lld anchors failed: %s", (long long) (nA + nB), cudaGetErrorString (e));
-          rc = GCG_ENOMEM;
-          break;
-        }
-        if (nA > 0 && cudaMemcpyAsync (bigger, h->d_hits, (size_t) nA * sizeof (gcg_hit), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) {
-          gcg_dfree (ctx, bigger); gcg_set_error ("gcg_search: anchor copy failed"); rc = GCG_ECUDA; break;
-        }
-        gcg_dfree (ctx, h->d_hits);                     // (parked, and reused only by work queued behind the copy)
-        h->d_hits = bigger;
-      }
-      if (nB > 0) emit (tileA, n_words, h->d_hits + nA);
-      h->n = nA + nB;
+    if (n_hit > 0) {
+      gcg_kscope ks (ctx, "hits_emit");
+      hits_emit_kernel<<<grid_for (ctx, ((n_words + 31) >> 5) * 32, 256, 8), 256, 0, ctx->stream>>> (
+          reads->d_packed, reads->d_woff, reads->d_tseq, reads->n, n_words, k, t->d_keys, t->d_vals, t->n_bucket, d_mask, d_prefix, 0, h->d_hits, 0);
+      if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_search: emit launch failed"); rc = GCG_ECUDA; break; }
     }
-    gcg_trace_mark (ctx, "  search_seqs: counts + emit launches");
-    // no wait for the emit kernels: the anchors stay on the device and everything that reads them
-    // (download, statistics, the next search) is ordered behind them on the context's stream
-    if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_search: emit launch failed"); rc = GCG_ECUDA; }
+    h->n = n_hit;
     break;
   }
   gcg_dfree (ctx, d_mask); gcg_dfree (ctx, d_prefix); gcg_dfree (ctx, d_bsum);
+  return rc;
+}
+
+// The anchors stay on the device; everything that reads them (download, statistics, the next search)
+// is ordered behind the kernels on the context's stream.  The result buffer is sized from the anchor
+// density of the previous search on this context (first call: one anchor per 8 k-mers); if the reads
+// anchor more densely than that, the launch materialises what fits and a second launch into a buffer
+// of the now known size finishes the rest (k45_fused_kernel's window).
+static int search_seqs_impl (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * reads, int k, int fmt, gcg_hits ** out)
+{
+  GCG_CHECK (ctx && t && reads && out, GCG_EINVAL, "gcg_search: bad argument");
+  GCG_CHECK (k == t->k, GCG_EINVAL, "gcg_search: k=%d but the table was built with k=%d", k, t->k);
+  GCG_CHECK (reads->n < 0x7FFFFFFF, GCG_ERANGE, "gcg_search: too many reads");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  if (fmt) {
+    int32_t mx = 0;
+    for (int32_t l : reads->h_len) mx = std::max (mx, l);
+    int rcl = compact_limits_ok (t, mx);
+    if (rcl) return rcl;
+  }
+  gcg_hits * h = new gcg_hits ();
+  h->ctx = ctx; h->fmt = fmt; h->n_seq = reads->n;
+  const int64_t n_words = reads->n_words, n_kmers = gcg_seqs_kmers (reads, k);
+  if (n_words == 0 || n_kmers == 0) { *out = h; return GCG_OK; }
+  if (n_kmers >= 0xFFFFFFFFLL) {
+    gcg_set_error ("gcg_search: %lld positions in one call exceed the 32-bit anchor index; split the read set (gcg_search does)", (long long) n_kmers);
+    gcg_hits_free (h);
+    return GCG_ERANGE;
+  }
+  int rc = gcg_table_filter_ensure (ctx, t);
+  static const bool two_pass = [] () { const char * e = getenv ("GCG_SEARCH_FUSED"); return e && atoi (e) == 0; } ();
+  if (!rc && two_pass && fmt == 0) {
+    rc = search_seqs_two_pass (ctx, t, reads, k, h);
+    if (rc) { gcg_hits_free (h); return rc; }
+    *out = h;
+    return GCG_OK;
+  }
+  const int64_t n_tiles = (n_words + 31) >> 5;
+  unsigned long long * d_state = nullptr;
+  cudaError_t e = cudaSuccess;
+  const size_t rec = anchor_bytes (fmt);
+  double frac = ctx->last_anchor_frac > 0 ? ctx->last_anchor_frac * 1.125 : 0.125;
+  if (const char * ef = getenv ("GCG_SEARCH_CAP_FRAC")) frac = atof (ef);        // test hook: force the second launch
+  int64_t cap = std::min<int64_t> (n_kmers, (int64_t) ((double) n_kmers * frac) + 4096);
+  if (!rc && ((e = gcg_dmalloc (ctx, &d_state, (size_t) (n_tiles + 1) * 8)) != cudaSuccess ||
+              (e = gcg_dmalloc (ctx, &h->d_hits, (size_t) cap * rec)) != cudaSuccess ||
+              (fmt && (e = gcg_dmalloc (ctx, &h->d_read_off, (size_t) (reads->n + 1) * 8)) != cudaSuccess))) {
+    gcg_set_error ("gcg_search: cudaMalloc failed (%lld anchors): %s", (long long) cap, cudaGetErrorString (e));
+    rc = GCG_ENOMEM;
+  }
+  int64_t total = 0;
+  if (!rc) rc = launch_fused (ctx, t, reads->d_packed, reads->d_woff, reads->d_len, reads->d_tseq, reads->n, n_words, k, fmt, h->d_hits,
+                              0ULL, (unsigned long long) cap, 0, h->d_read_off, d_state, ctx->d_counters + 4);
+  if (!rc && (cudaMemcpyAsync (ctx->h_counters + 4, ctx->d_counters + 4, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+              cudaStreamSynchronize (ctx->stream) != cudaSuccess)) {
+    gcg_set_error ("gcg_search: probe failed: %s", cudaGetErrorString (cudaGetLastError ()));
+    rc = GCG_ECUDA;
+  }
+  if (!rc) total = (int64_t) ctx->h_counters[4];
+  if (!rc && total > cap) {
+    // denser than estimated: the first `cap` anchors are in place (and counted); finish the rest in a buffer of the right size
+    void * bigger = nullptr;
+    if ((e = gcg_dmalloc (ctx, &bigger, (size_t) total * rec)) != cudaSuccess) {
+      gcg_set_error ("gcg_search: cudaMalloc of %lld anchors failed: %s", (long long) total, cudaGetErrorString (e));
+      rc = GCG_ENOMEM;
+    } else {
+      if (cudaMemcpyAsync (bigger, h->d_hits, (size_t) cap * rec, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_search: anchor copy failed"); rc = GCG_ECUDA; }
+      gcg_dfree (ctx, h->d_hits);                     // (parked, and reused only by work queued behind the copy)
+      h->d_hits = (gcg_hit *) bigger;
+      if (!rc) rc = launch_fused (ctx, t, reads->d_packed, reads->d_woff, reads->d_len, reads->d_tseq, reads->n, n_words, k, fmt, h->d_hits,
+                                  (unsigned long long) cap, (unsigned long long) total, 0, h->d_read_off, d_state, ctx->d_counters + 4);
+    }
+  }
+  if (!rc && fmt) {
+    // read_off[n] = total; reads without a word (length 0) are filled in on download
+    const long long tot = total;
+    if (cudaMemcpyAsync (h->d_read_off + reads->n, &tot, 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_search: read offset copy failed"); rc = GCG_ECUDA; }
+  }
+  gcg_dfree (ctx, d_state);
   if (rc) { gcg_hits_free (h); return rc; }
+  h->n = total;
+  ctx->last_anchor_frac = (double) total / (double) n_kmers;
   *out = h;
+  return GCG_OK;
+}
+
+extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * reads, int k, gcg_hits ** out)
+{
+  return search_seqs_impl (ctx, t, reads, k, 0, out);
+}
+
+extern "C" int gcg_search_seqs_compact (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * reads, int k, gcg_hits ** out)
+{
+  return search_seqs_impl (ctx, t, reads, k, 1, out);
+}
+
+// reads that own no anchor index of their own (length 0: no word) start where the next read starts
+static void read_off_fill (int64_t * read_off, int64_t n_read, int64_t total)
+{
+  read_off[n_read] = total;
+  for (int64_t r = n_read - 1; r >= 0; --r) if (read_off[r] < 0) read_off[r] = read_off[r + 1];
+}
+
+extern "C" int gcg_hits_download_compact (gcg_ctx * ctx, const gcg_hits * h, uint64_t * anchors, int64_t cap, int64_t * read_off)
+{
+  GCG_CHECK (ctx && h && h->fmt == 1 && (anchors || cap == 0) && read_off, GCG_EINVAL, "gcg_hits_download_compact: bad argument (or not a compact anchor list)");
+  const int64_t n = std::min (cap, h->n);
+  if (h->d_read_off) GCG_CUDA (cudaMemcpyAsync (read_off, h->d_read_off, (size_t) (h->n_seq + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  else for (int64_t r = 0; r <= h->n_seq; ++r) read_off[r] = -1;
+  if (n > 0) GCG_CUDA (cudaMemcpyAsync (anchors, h->d_hits, (size_t) n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+  read_off_fill (read_off, h->n_seq, h->n);
   return GCG_OK;
 }
 
 extern "C" int gcg_hits_download (gcg_ctx * ctx, const gcg_hits * h, gcg_hit * dst, int64_t cap)
 {
-  GCG_CHECK (ctx && h && (dst || cap == 0), GCG_EINVAL, "gcg_hits_download: bad argument");
+  GCG_CHECK (ctx && h && h->fmt == 0 && (dst || cap == 0), GCG_EINVAL, "gcg_hits_download: bad argument (or a compact anchor list: gcg_hits_download_compact)");
   int64_t n = std::min (cap, h->n);
   if (n > 0) {
     GCG_CUDA (cudaMemcpyAsync (dst, h->d_hits, (size_t) n * sizeof (gcg_hit), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1247,12 +1515,12 @@ struct pipe_slot {
   uint64_t * h_packed = nullptr;                     // pinned, cap_words words: the chunk 2-bit packed by the host gather
   char * h_meta = nullptr, * d_meta = nullptr;       // woff | len | tile_seq of the chunk
   uint64_t * d_packed = nullptr;
-  uint32_t * d_mask = nullptr, * d_prefix = nullptr, * d_bsum = nullptr;
-  unsigned long long * d_count = nullptr;
-  gcg_hit * d_hits = nullptr;                        // cap_words * 32 anchors (every position could anchor)
-  cudaEvent_t ev_up = nullptr, ev_count = nullptr, ev_emit = nullptr, ev_free = nullptr;
+  unsigned long long * d_state = nullptr;            // chained-scan state of the chunk's tiles + the tile counter
+  long long * d_read_off = nullptr;                  // compact form: first anchor of every read of the chunk
+  gcg_hit * d_hits = nullptr;                        // cap_words * 32 anchors of 16 bytes (every position could anchor)
+  cudaEvent_t ev_up = nullptr, ev_emit = nullptr, ev_free = nullptr;
   bool busy = false, pending = false;                // ev_free recorded / chunk waiting for its download
-  int64_t first_read = 0;
+  int64_t first_read = 0, n_read = 0;
 };
 
 struct gcg_pipe {
@@ -1260,7 +1528,7 @@ struct gcg_pipe {
   size_t meta_cap = 0;
   cudaStream_t up = nullptr, down = nullptr;
   pipe_slot s[PIPE_SLOTS];
-  unsigned long long * h_count = nullptr;            // pinned + mapped, one per slot: the scan kernel stores the chunk's anchor
+  unsigned long long * h_count = nullptr;            // pinned + mapped, one per slot: the search kernel stores the chunk's anchor
   unsigned long long * hd_count = nullptr;           // count straight into host memory (device alias of h_count) — a copy of
                                                      // 8 bytes would queue behind the anchor downloads on the D2H copy engine
   int64_t last_total = 0;                            // anchors of the previous call: sizes the next result buffer
@@ -1275,9 +1543,8 @@ void gcg_pipe_free (gcg_ctx * ctx)
   for (pipe_slot & q : p->s) {
     if (q.h_packed) cudaFreeHost (q.h_packed);
     if (q.h_meta) cudaFreeHost (q.h_meta);
-    cudaFree (q.d_meta); cudaFree (q.d_packed); cudaFree (q.d_mask); cudaFree (q.d_prefix);
-    cudaFree (q.d_bsum); cudaFree (q.d_count); cudaFree (q.d_hits);
-    for (cudaEvent_t e : {q.ev_up, q.ev_count, q.ev_emit, q.ev_free}) if (e) cudaEventDestroy (e);
+    cudaFree (q.d_meta); cudaFree (q.d_packed); cudaFree (q.d_state); cudaFree (q.d_read_off); cudaFree (q.d_hits);
+    for (cudaEvent_t e : {q.ev_up, q.ev_emit, q.ev_free}) if (e) cudaEventDestroy (e);
   }
   if (p->h_count) cudaFreeHost (p->h_count);
   if (p->up) cudaStreamDestroy (p->up);
@@ -1306,13 +1573,11 @@ static int pipe_reserve (gcg_ctx * ctx, int64_t cap_words)
     GCG_CUDA (cudaHostAlloc (&q.h_meta, p->meta_cap, cudaHostAllocDefault));
     GCG_CUDA (cudaMalloc (&q.d_meta, p->meta_cap));
     GCG_CUDA (cudaMalloc (&q.d_packed, (size_t) (cap_words + 2) * 8));
-    GCG_CUDA (cudaMalloc (&q.d_mask, (size_t) cap_words * 4));
-    GCG_CUDA (cudaMalloc (&q.d_prefix, (size_t) cap_words * 4));
-    GCG_CUDA (cudaMalloc (&q.d_bsum, (size_t) gcg_mask_scan_blocks (cap_words) * 4));
-    GCG_CUDA (cudaMalloc (&q.d_count, 8));
+    GCG_CUDA (cudaMalloc (&q.d_state, (tiles + 1) * 8));
+    GCG_CUDA (cudaMalloc (&q.d_read_off, (p->meta_cap / 12 + 2) * 8));       // a chunk's reads fit its meta block at 12 bytes each
     GCG_CUDA (cudaMalloc (&q.d_hits, (size_t) cap_words * 32 * sizeof (gcg_hit)));
     GCG_CUDA (cudaMemset (q.d_packed, 0, (size_t) (cap_words + 2) * 8));
-    for (cudaEvent_t * e : {&q.ev_up, &q.ev_count, &q.ev_emit, &q.ev_free}) GCG_CUDA (cudaEventCreateWithFlags (e, cudaEventDisableTiming));
+    for (cudaEvent_t * e : {&q.ev_up, &q.ev_emit, &q.ev_free}) GCG_CUDA (cudaEventCreateWithFlags (e, cudaEventDisableTiming));
   }
   return GCG_OK;
 }
@@ -1328,63 +1593,86 @@ extern "C" int gcg_warmup (gcg_ctx * ctx)
 
 struct search_result {
   gcg_ctx * ctx;
-  gcg_hit * buf = nullptr;
+  int fmt = 0;
+  size_t rec = sizeof (gcg_hit);
+  char * buf = nullptr;                              // pinned: gcg_hit[cap] or uint64_t[cap]
   int64_t cap = 0, n = 0;
+  int64_t * read_off = nullptr;                      // compact form: pinned, [n_read + 1], chunk-relative until the end of the call
+  std::vector<std::pair<int64_t, int64_t>> chunk_base;   // (first read, anchors before the chunk)
 };
 
 // place the anchors of the chunk in slot `q` behind the ones already placed
 static int pipe_download (gcg_ctx * ctx, pipe_slot & q, int slot, search_result & res)
 {
   gcg_pipe * p = ctx->pipe;
-  GCG_CUDA (cudaEventSynchronize (q.ev_count));
+  GCG_CUDA (cudaEventSynchronize (q.ev_emit));
   const int64_t n = (int64_t) p->h_count[slot];
   if (res.n + n > res.cap) {
     // estimate too small: move what is there into a larger block (the copies in flight target the old one)
     GCG_CUDA (cudaStreamSynchronize (p->down));
     int64_t ncap = std::max<int64_t> (res.cap * 2, res.n + n + (res.n + n) / 4);
-    gcg_hit * nb = (gcg_hit *) gcg_pinned_alloc ((size_t) ncap * sizeof (gcg_hit));
+    char * nb = (char *) gcg_pinned_alloc ((size_t) ncap * res.rec);
     GCG_CHECK (nb != nullptr, GCG_ENOMEM, "gcg_search: pinned alloc of %lld anchors failed", (long long) ncap);
-    if (res.n) gcg_par_memcpy (ctx, nb, res.buf, (size_t) res.n * sizeof (gcg_hit));
+    // (the pool may be busy gathering the next chunk: gcg_workers_run then copies on this thread, host_par.cpp)
+    if (res.n) gcg_par_memcpy (ctx, nb, res.buf, (size_t) res.n * res.rec);
     gcg_free (res.buf);
     res.buf = nb; res.cap = ncap;
   }
-  GCG_CUDA (cudaStreamWaitEvent (p->down, q.ev_emit, 0));
-  if (n > 0) GCG_CUDA (cudaMemcpyAsync (res.buf + res.n, q.d_hits, (size_t) n * sizeof (gcg_hit), cudaMemcpyDeviceToHost, p->down));
+  if (n > 0) GCG_CUDA (cudaMemcpyAsync (res.buf + (size_t) res.n * res.rec, q.d_hits, (size_t) n * res.rec, cudaMemcpyDeviceToHost, p->down));
+  if (res.fmt && q.n_read > 0) {
+    GCG_CUDA (cudaMemcpyAsync (res.read_off + q.first_read, q.d_read_off, (size_t) q.n_read * 8, cudaMemcpyDeviceToHost, p->down));
+    res.chunk_base.emplace_back (q.first_read, res.n);
+  }
   GCG_CUDA (cudaEventRecord (q.ev_free, p->down));
   q.busy = true; q.pending = false;
   res.n += n;
   return GCG_OK;
 }
 
-extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
-                           int64_t n_read, int k, gcg_hit ** hits_out, int64_t * n_hit)
+// fmt 0: *hits_out = gcg_hit[*n_hit]; fmt 1: *hits_out = uint64_t[*n_hit] and *read_off_out = int64_t[n_read + 1]
+static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
+                             int64_t n_read, int k, int fmt, void ** hits_out, int64_t * n_hit, int64_t ** read_off_out)
 {
   GCG_CHECK (ctx && t && hits_out && n_hit && n_read >= 0 && (n_read == 0 || (read_seq && read_len)), GCG_EINVAL, "gcg_search: bad argument");
   GCG_CHECK (k == t->k, GCG_EINVAL, "gcg_search: k=%d but the table was built with k=%d", k, t->k);
   GCG_CHECK (n_read < 0x7FFFFFFF, GCG_ERANGE, "gcg_search: too many reads");
   *hits_out = nullptr;
   *n_hit = 0;
+  if (read_off_out) *read_off_out = nullptr;
   GCG_CUDA (cudaSetDevice (ctx->device));
   gcg_trace_mark (ctx, nullptr);
   int64_t chunk_words = ((int64_t) 8 << 20) / 32, max_words = 0, total_kmers = 0;
   if (const char * e = getenv ("GCG_SEARCH_CHUNK_BYTES")) chunk_words = std::max<int64_t> (1, atoll (e) / 32);
+  int32_t max_len = 0;
   for (int64_t r = 0; r < n_read; ++r) {
     GCG_CHECK (read_len[r] >= 0, GCG_ERANGE, "gcg_search: read %lld has a negative length", (long long) r);
     max_words = std::max<int64_t> (max_words, ((int64_t) read_len[r] + 31) >> 5);
+    max_len = std::max (max_len, read_len[r]);
     if (read_len[r] >= k) total_kmers += (int64_t) read_len[r] - k + 1;
   }
-  if (total_kmers == 0) return GCG_OK;
-  int rc = pipe_reserve (ctx, std::max (chunk_words, max_words));
+  int rc = GCG_OK;
+  if (fmt && (rc = compact_limits_ok (t, max_len)) != 0) return rc;
+  search_result res;
+  res.ctx = ctx; res.fmt = fmt; res.rec = anchor_bytes (fmt);
+  if (fmt) {
+    res.read_off = (int64_t *) gcg_pinned_alloc ((size_t) (n_read + 1) * 8);
+    GCG_CHECK (res.read_off != nullptr, GCG_ENOMEM, "gcg_search: pinned alloc of %lld read offsets failed", (long long) n_read + 1);
+    memset (res.read_off, 0xFF, (size_t) (n_read + 1) * 8);
+  }
+  if (total_kmers == 0) {
+    if (fmt) { read_off_fill (res.read_off, n_read, 0); *read_off_out = res.read_off; }
+    return GCG_OK;
+  }
+  rc = pipe_reserve (ctx, std::max (chunk_words, max_words));
   if (!rc) rc = gcg_table_filter_ensure (ctx, t);
-  if (rc) return rc;
+  if (rc) { gcg_free (res.read_off); return rc; }
   gcg_pipe * p = ctx->pipe;
   const int64_t cap_words = std::max (chunk_words, max_words);       // <= p->cap_words
 
-  search_result res;
-  res.ctx = ctx;
   res.cap = std::max<int64_t> (p->last_total + p->last_total / 8, total_kmers / 16) + 4096;
-  res.buf = (gcg_hit *) gcg_pinned_alloc ((size_t) res.cap * sizeof (gcg_hit));
-  GCG_CHECK (res.buf != nullptr, GCG_ENOMEM, "gcg_search: pinned alloc of %lld anchors failed", (long long) res.cap);
+  if (const char * e = getenv ("GCG_SEARCH_RES_CAP")) res.cap = std::max<int64_t> (1, atoll (e));     // test hook: force the grow path
+  res.buf = (char *) gcg_pinned_alloc ((size_t) res.cap * res.rec);
+  if (res.buf == nullptr) { gcg_free (res.read_off); gcg_set_error ("gcg_search: pinned alloc of %lld anchors failed", (long long) res.cap); return GCG_ENOMEM; }
 
   // work on ctx->stream enqueued by earlier calls (the table build) precedes the first probe by stream order
   struct chunk_desc { int64_t r0 = 0, r1 = 0, nr = 0, nw = 0, kmers = 0, n_tiles = 0; size_t tseq_off = 0; int slot = 0; };
@@ -1451,7 +1739,8 @@ extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * re
     gcg_workers_start (pool, n_task, gather_fn);
   };
 
-  // copy the gathered chunk to the device and enqueue its kernels
+  // copy the gathered chunk to the device and enqueue its kernel: probe, ordered anchor index, ONT-side
+  // multiplicity and anchor records in one launch (k45_fused_kernel); the anchor count lands in mapped host memory
   auto submit = [&] (const chunk_desc & d) -> int {
     pipe_slot & q = p->s[d.slot];
     const int64_t nr = d.nr, nw = d.nw;
@@ -1463,17 +1752,13 @@ extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * re
     const int64_t * d_woff = (const int64_t *) q.d_meta;
     const int32_t * d_len = (const int32_t *) (q.d_meta + (size_t) (nr + 1) * 8);
     const int32_t * d_tseq = (const int32_t *) (q.d_meta + d.tseq_off);
-    int e;
-    launch_k45 (ctx, t, q.d_packed, d_woff, d_len, d_tseq, nr, nw, k, q.d_mask);
-    if ((e = mask_scan_launch (ctx, q.d_mask, nw, q.d_prefix, q.d_bsum, p->hd_count + d.slot)) != 0) return e;
-    GCG_CUDA (cudaEventRecord (q.ev_count, ctx->stream));
-    { gcg_kscope ks (ctx, "hits_emit");
-      hits_emit_kernel<<<grid_for (ctx, d.n_tiles * 32, 256, 8), 256, 0, ctx->stream>>> (
-          q.d_packed, d_woff, d_tseq, nr, nw, k, t->d_keys, t->d_vals, t->n_bucket, q.d_mask, q.d_prefix, (int32_t) d.r0, q.d_hits, 0); }
+    int e = launch_fused (ctx, t, q.d_packed, d_woff, d_len, d_tseq, nr, nw, k, fmt, q.d_hits, 0ULL, ~0ULL, (int32_t) d.r0,
+                          fmt ? q.d_read_off : nullptr, q.d_state, p->hd_count + d.slot);
+    if (e) return e;
     GCG_CUDA (cudaEventRecord (q.ev_emit, ctx->stream));
-    GCG_CUDA (cudaGetLastError ());
+    GCG_CUDA (cudaStreamWaitEvent (p->down, q.ev_emit, 0));
     q.pending = true;
-    q.first_read = d.r0;
+    q.first_read = d.r0; q.n_read = nr;
     return GCG_OK;
   };
 
@@ -1531,12 +1816,41 @@ extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * re
              "host: prepare %.3f submit %.3f download %.3f drain %.3f ms\n",
              (long long) c, t_gather, ctx->host_threads, t_wait, t_prepare, t_submit, t_download, t_drain);
   gcg_trace_mark (ctx, "search: reads -> anchors (pipelined)");
-  if (rc) { gcg_free (res.buf); return rc; }
+  if (rc) { gcg_free (res.buf); gcg_free (res.read_off); return rc; }
   p->last_total = res.n;
+  if (fmt) {
+    // chunk-relative offsets -> offsets into the whole anchor array
+    for (size_t ci = 0; ci < res.chunk_base.size (); ++ci) {
+      const int64_t r0 = res.chunk_base[ci].first, base = res.chunk_base[ci].second;
+      const int64_t r1 = ci + 1 < res.chunk_base.size () ? res.chunk_base[ci + 1].first : n_read;
+      if (base) for (int64_t r = r0; r < r1; ++r) if (res.read_off[r] >= 0) res.read_off[r] += base;
+    }
+    read_off_fill (res.read_off, n_read, res.n);
+    *read_off_out = res.read_off;
+  }
   if (res.n == 0) { gcg_free (res.buf); return GCG_OK; }
   *hits_out = res.buf;
   *n_hit = res.n;
   return GCG_OK;
+}
+
+extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
+                           int64_t n_read, int k, gcg_hit ** hits_out, int64_t * n_hit)
+{
+  void * buf = nullptr;
+  int rc = search_host_impl (ctx, t, read_seq, read_len, n_read, k, 0, &buf, n_hit, nullptr);
+  if (hits_out) *hits_out = (gcg_hit *) buf;
+  return rc;
+}
+
+extern "C" int gcg_search_compact (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
+                                   int64_t n_read, int k, uint64_t ** anchors_out, int64_t ** read_off_out, int64_t * n_anchor)
+{
+  GCG_CHECK (anchors_out && read_off_out, GCG_EINVAL, "gcg_search_compact: bad argument");
+  void * buf = nullptr;
+  int rc = search_host_impl (ctx, t, read_seq, read_len, n_read, k, 1, &buf, n_anchor, read_off_out);
+  *anchors_out = (uint64_t *) buf;
+  return rc;
 }
 
 // ---- contig chop to host kmer_t arrays --------------------------------------------------------

@@ -17,7 +17,7 @@
 #include "utils.h"
 #include "gcg_bridge.h"
 
-static gcg_bridge_t g_bridge = { NULL, NULL, NULL, 0, 1, 0, {0}, {NULL}, {NULL} };
+static gcg_bridge_t g_bridge = { .n_thread = 1 };
 static pthread_t g_warm_thread[GCG_BRIDGE_MAX_DEV];
 static int g_warm_started = 0, g_warm_rc[GCG_BRIDGE_MAX_DEV];
 static gcg_ctx * g_warm_ctx[GCG_BRIDGE_MAX_DEV];

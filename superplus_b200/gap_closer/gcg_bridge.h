@@ -15,6 +15,7 @@ typedef struct {
   gcg_table * table;      /* table of the last put_contig_kmers2hashs */
   int kmer_len;
   int n_thread;
+  int searched_k;         /* k-mer length of the first search_kmers_on_ont_reads (0 = none yet) */
   /* GC_DEVICES=0,1,... (or "all"): the ONT reads are sharded by batch over these GPUs, every one
    * holding a replica of the table (replicated layout).  ctxs[0] == ctx, replicas[0] == NULL. */
   int n_dev;

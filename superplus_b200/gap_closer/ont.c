@@ -7,7 +7,8 @@
  *                 -> gcg_search: reads to HBM, canonical k-mers, table probes, ONT-side
  *                    multiplicity, anchors back in (read,pos) order
  *   back-fill of the dense okmers[] the unchanged consumers index by read position
- *            (ctg_graph.c:603-651): host threads, one 16-byte store per anchor
+ *            (ctg_graph.c:603-651): host threads over whole reads, one 16-byte store per anchor,
+ *            from the compact 8-byte anchors the device sends (gcg_search_compact)
  *   UNANKOR  (reference ont.c:381-388 -> find_unankor_segs ont.c:264-309): derived from the
  *            sorted anchor list instead of re-scanning 16 bytes per ONT base
  *
@@ -36,10 +37,19 @@
 #include "gcg_bridge.h"
 
 /* ------------------------------------------------------------------ back-fill ---------- */
+/* The device returns COMPACT anchors (include/gcgpu.h, gcg_search_compact): one 64-bit word per anchor,
+ * pos << 36 | gpos << 2 | flags, grouped by read through read_off[]; gpos counts contig bases in the
+ * order the contigs were uploaded (chop_contig_seqs2kmers), so cbase[] below turns it back into
+ * (tid, cpos).  Inputs beyond the bit budget of that form (a read of 2^28 bases, 2^34 contig bases) come
+ * back as 16-byte gcg_hit records instead (gcg_search); both forms fill the same okmers[]. */
 typedef struct {
-  const gcg_hit * hits;
-  int64_t beg, end;
-  int64_t read_off;           /* index of the share's first read (hits count reads from their share's start) */
+  const uint64_t * anchors;   /* compact form, or NULL */
+  const int64_t * read_off;
+  const gcg_hit * hits;       /* 16-byte form, or NULL */
+  int64_t beg, end;           /* compact: reads [beg, end) of the share; 16-byte: hits [beg, end) */
+  int64_t read_off0;          /* index of the share's first read (both forms count reads from their share's start) */
+  const int64_t * cbase;      /* n_ctg + 1 */
+  int64_t n_ctg;
   mp_t(okseq) * okseqs;
   mp_t(ctg) * ctgs;
 } fill_arg_t;
@@ -48,44 +58,78 @@ static void *
 fill_core (void * data)
 {
   fill_arg_t * a = (fill_arg_t *) data;
-  int64_t i;
-  for (i = a->beg; i < a->end; ++i) {
-    const gcg_hit * h = a->hits + i;
-    okseq_t * okseq = a->okseqs->pool + a->read_off + h->read;
-    ont_kmer_t * ok = okseq->okmers->pool + h->pos;
-    kmer_t * km = a->ctgs->pool[h->tid].kmers + (h->cpos_flags >> 2);
-    ok->kmer = km;
-    ok->ont_pos = h->pos;
-    ok->hs_id = (int16_t) km->hs_id;
-    ok->flag = (h->cpos_flags & 2u) ? ONT_KMER_REV : 0;
+  int64_t i, r, tid = 0;
+  if (a->anchors == NULL) {
+    for (i = a->beg; i < a->end; ++i) {
+      const gcg_hit * h = a->hits + i;
+      okseq_t * okseq = a->okseqs->pool + a->read_off0 + h->read;
+      ont_kmer_t * ok = okseq->okmers->pool + h->pos;
+      kmer_t * km = a->ctgs->pool[h->tid].kmers + (h->cpos_flags >> 2);
+      ok->kmer = km;
+      ok->ont_pos = h->pos;
+      ok->hs_id = (int16_t) km->hs_id;
+      ok->flag = (h->cpos_flags & 2u) ? ONT_KMER_REV : 0;
+    }
+    return NULL;
+  }
+  for (r = a->beg; r < a->end; ++r) {
+    ont_kmer_t * okmers = a->okseqs->pool[a->read_off0 + r].okmers->pool;
+    for (i = a->read_off[r]; i < a->read_off[r + 1]; ++i) {
+      const uint64_t w = a->anchors[i];
+      const int64_t gpos = GCG_ANCHOR_GPOS (w);
+      const int32_t pos = GCG_ANCHOR_POS (w);
+      ont_kmer_t * ok = okmers + pos;
+      kmer_t * km;
+      if (gpos < a->cbase[tid] || gpos >= a->cbase[tid + 1]) {
+        /* neighbouring anchors of a read mostly sit on one contig; otherwise bisect (empty contigs share a base: take the last) */
+        int64_t lo = 0, hi = a->n_ctg;
+        while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (a->cbase[mid] <= gpos) lo = mid; else hi = mid; }
+        tid = lo;
+      }
+      km = a->ctgs->pool[tid].kmers + (gpos - a->cbase[tid]);
+      ok->kmer = km;
+      ok->ont_pos = pos;
+      ok->hs_id = (int16_t) km->hs_id;
+      ok->flag = (w & 2u) ? ONT_KMER_REV : 0;
+    }
   }
   return NULL;
 }
 
-/* maximal runs of un-anchored positions of the reads [r0, r1), from their share's sorted anchors */
+/* maximal runs of un-anchored positions of the reads [r0, r1) (reference find_unankor_segs, ont.c:264-309),
+ * from their share's sorted anchors instead of a scan over 16 bytes per ONT base */
 static void
-rebuild_segs (mp_t(okseq) * okseqs, int64_t r0, int64_t r1, const gcg_hit * hits, int64_t n_hit)
+seg_add (okseq_t * okseq, int64_t beg, int64_t end)
+{
+  ont_seg_t * seg = mp_alloc (oseg, okseq->segs);
+  seg->beg = (int32_t) beg;
+  seg->end = (int32_t) end;
+}
+
+static void
+rebuild_segs (mp_t(okseq) * okseqs, int64_t r0, int64_t r1, const gcg_hit * hits, int64_t n_hit,
+    const uint64_t * anchors, const int64_t * read_off)
 {
   int64_t r, n_reads = r1 - r0, h = 0;
   for (r = 0; r < n_reads; ++r) {
     okseq_t * okseq = mp_at (okseq, okseqs, r0 + r);
-    int64_t n = mp_cnt (okseq->okmers), cur = 0;
-    ont_seg_t * seg;
+    int64_t n = mp_cnt (okseq->okmers), cur = 0, pos;
     mp_clear (oseg, okseq->segs, NULL);
-    while (h < n_hit && hits[h].read == r) {
-      if (hits[h].pos > cur) {
-        seg = mp_alloc (oseg, okseq->segs);
-        seg->beg = (int32_t) cur;
-        seg->end = hits[h].pos;
+    if (anchors != NULL) {
+      for (h = read_off[r]; h < read_off[r + 1]; ++h) {
+        pos = GCG_ANCHOR_POS (anchors[h]);
+        if (pos > cur) seg_add (okseq, cur, pos);
+        cur = pos + 1;
       }
-      cur = (int64_t) hits[h].pos + 1;
-      ++h;
+    } else {
+      while (h < n_hit && hits[h].read == r) {
+        pos = hits[h].pos;
+        if (pos > cur) seg_add (okseq, cur, pos);
+        cur = pos + 1;
+        ++h;
+      }
     }
-    if (cur < n) {
-      seg = mp_alloc (oseg, okseq->segs);
-      seg->beg = (int32_t) cur;
-      seg->end = (int32_t) n;
-    }
+    if (cur < n) seg_add (okseq, cur, n);
   }
 }
 
@@ -97,7 +141,9 @@ typedef struct {
   const int32_t * lens;
   int64_t r0, r1;
   int kmer_len;
-  gcg_hit * hits;
+  uint64_t * anchors;       /* compact form ... */
+  int64_t * read_off;
+  gcg_hit * hits;           /* ... or the 16-byte form */
   int64_t n_hit;
   int rc;
   char err[600];
@@ -107,7 +153,12 @@ static void *
 share_core (void * data)
 {
   share_t * s = (share_t *) data;
-  s->rc = gcg_search (s->ctx, s->table, s->ptrs + s->r0, s->lens + s->r0, s->r1 - s->r0, s->kmer_len, &s->hits, &s->n_hit);
+  s->rc = getenv ("GC_ANCHORS16") ? GCG_ERANGE
+        : gcg_search_compact (s->ctx, s->table, s->ptrs + s->r0, s->lens + s->r0, s->r1 - s->r0, s->kmer_len, &s->anchors, &s->read_off, &s->n_hit);
+  if (s->rc == GCG_ERANGE) {        /* beyond the compact form's bit budget (or GC_ANCHORS16 set: A/B of the two forms) */
+    s->anchors = NULL; s->read_off = NULL;
+    s->rc = gcg_search (s->ctx, s->table, s->ptrs + s->r0, s->lens + s->r0, s->r1 - s->r0, s->kmer_len, &s->hits, &s->n_hit);
+  }
   if (s->rc != 0) snprintf (s->err, sizeof s->err, "%s", gcg_last_error ());   /* the message is thread local */
   return NULL;
 }
@@ -119,7 +170,8 @@ search_kmers_on_ont_reads (mp_t(rs) * ont_seqs, mp_t(ctg) * ctg_seqs,
 {
   int i, d, nt, n_dev, n_fill = 0;
   time_t time_beg, mod_tbeg;
-  int64_t r, n_reads, n_hit = 0, total_bases = 0, run = 0;
+  int64_t r, n_reads, n_hit = 0, total_bases = 0, run = 0, n_ctg;
+  int64_t * cbase;
   const char ** ptrs;
   int32_t * lens;
   pthread_t * pids;
@@ -133,6 +185,13 @@ search_kmers_on_ont_reads (mp_t(rs) * ont_seqs, mp_t(ctg) * ctg_seqs,
     err_mesg ("[%s] put_contig_kmers2hashs has not been called", __func__);
   if (kmer_len != br->kmer_len)
     err_mesg ("[%s] kmer_len %d differs from the table's %d", __func__, kmer_len, br->kmer_len);
+  /* The reference searches only okseq->segs from the second k-mer length on and keeps the anchors of the
+   * earlier lengths (ont.c:207-223); this batcher searches whole reads and points okmer->kmer into
+   * ctg->kmers[], which the next chop overwrites.  The shipped main.c runs one length (n_kmers == 1,
+   * main.c:29); a second one must fail loudly instead of corrupting the earlier anchors. */
+  if (br->searched_k != 0 && br->searched_k != kmer_len)
+    err_mesg ("[%s] a second k-mer length (%d after %d) is not supported by the B200 path (main.c runs n_kmers == 1)", __func__, kmer_len, br->searched_k);
+  br->searched_k = kmer_len;
   nt = n_thread > 0 ? n_thread : 1;
   n_dev = br->n_dev;
   for (d = 0; d < n_dev; ++d)
@@ -150,6 +209,11 @@ search_kmers_on_ont_reads (mp_t(rs) * ont_seqs, mp_t(ctg) * ctg_seqs,
     lens[r] = okseq->seq->l;
     total_bases += lens[r];
   }
+  /* scaffold coordinate of the compact anchors: contigs in upload order (kmer.c of this directory) */
+  n_ctg = mp_cnt (ctg_seqs);
+  cbase = (int64_t *) ckalloc (n_ctg + 2, sizeof (int64_t));
+  for (r = 0; r < n_ctg; ++r)
+    cbase[r + 1] = cbase[r] + mp_at (ctg, ctg_seqs, r)->seq->l;
   /* contiguous shares of about equal bases: share d ends at the first read where the running base
    * count reaches (d + 1) / n_dev of the total (superplus_b200/api.py split_reads_by_bases) */
   memset (share, 0, sizeof share);
@@ -173,7 +237,7 @@ search_kmers_on_ont_reads (mp_t(rs) * ont_seqs, mp_t(ctg) * ctg_seqs,
   }
   for (d = 0; d < n_dev; ++d) {
     if (share[d].rc != 0)
-      err_mesg ("[%s] gcg_search on device %d failed (%d): %s", __func__, br->devs[d], share[d].rc, share[d].err);
+      err_mesg ("[%s] search on device %d failed (%d): %s", __func__, br->devs[d], share[d].rc, share[d].err);
     n_hit += share[d].n_hit;
   }
   for (d = 1; d < n_dev; ++d)
@@ -191,16 +255,28 @@ search_kmers_on_ont_reads (mp_t(rs) * ont_seqs, mp_t(ctg) * ctg_seqs,
   for (d = 0; d < n_dev; ++d) {
     /* host threads in proportion to the share's anchors, at least one */
     int t, nt_d = n_hit > 0 ? (int) ((share[d].n_hit * nt + n_hit - 1) / n_hit) : 1;
+    int64_t prev = 0, n_rd = share[d].r1 - share[d].r0;
     if (nt_d < 1) nt_d = 1;
     if (n_fill + nt_d > nt + n_dev) nt_d = nt + n_dev - n_fill;
     for (t = 0; t < nt_d; ++t, ++n_fill) {
-      args[n_fill].hits = share[d].hits;
-      args[n_fill].beg = share[d].n_hit * t / nt_d;
-      args[n_fill].end = share[d].n_hit * (t + 1) / nt_d;
-      args[n_fill].read_off = share[d].r0;
-      args[n_fill].okseqs = okseqs;
-      args[n_fill].ctgs = ctg_seqs;
-      ckpthread_create (pids + n_fill, NULL, fill_core, (void *) (args + n_fill));
+      fill_arg_t * fa = args + n_fill;
+      fa->anchors = share[d].anchors; fa->read_off = share[d].read_off; fa->hits = share[d].hits;
+      fa->read_off0 = share[d].r0;
+      fa->cbase = cbase; fa->n_ctg = n_ctg;
+      fa->okseqs = okseqs;
+      fa->ctgs = ctg_seqs;
+      if (share[d].anchors != NULL) {
+        /* whole reads per thread, cut where the anchor count reaches (t + 1) / nt_d of the share's */
+        int64_t goal = share[d].n_hit * (t + 1) / nt_d, lo = prev, hi = n_rd;
+        if (t == nt_d - 1) lo = n_rd;
+        else while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (share[d].read_off[mid] < goal) lo = mid + 1; else hi = mid; }
+        fa->beg = prev; fa->end = lo;
+        prev = lo;
+      } else {
+        fa->beg = share[d].n_hit * t / nt_d;
+        fa->end = share[d].n_hit * (t + 1) / nt_d;
+      }
+      ckpthread_create (pids + n_fill, NULL, fill_core, (void *) fa);
     }
   }
   for (i = 0; i < n_fill; ++i)
@@ -210,11 +286,11 @@ search_kmers_on_ont_reads (mp_t(rs) * ont_seqs, mp_t(ctg) * ctg_seqs,
   /* un-anchored segments */
   time (&mod_tbeg);
   for (d = 0; d < n_dev; ++d)
-    rebuild_segs (okseqs, share[d].r0, share[d].r1, share[d].hits, share[d].n_hit);
+    rebuild_segs (okseqs, share[d].r0, share[d].r1, share[d].hits, share[d].n_hit, share[d].anchors, share[d].read_off);
   printf ("\n  find un-ankored positions on onts costs: %lds\n", time (NULL) - mod_tbeg);
 
-  for (d = 0; d < n_dev; ++d) gcg_free (share[d].hits);
-  free (pids); free (args); free (ptrs); free (lens);
+  for (d = 0; d < n_dev; ++d) { gcg_free (share[d].hits); gcg_free (share[d].anchors); gcg_free (share[d].read_off); }
+  free (pids); free (args); free (ptrs); free (lens); free (cbase);
 
   printf ("\n  search ONT kmers total cost: %lds\n", time (NULL) - time_beg);
   return 0;

@@ -6,6 +6,8 @@ oracle/build_ref.sh from /root/reference/gap_closer, unmodified).  Run in the bu
 Outputs (small, committed):
   kmer_<cfg>_k<k>.npz   anchors (read,pos,tid,cpos,kflag,oflag) + the four stat integers, from ref_kmer
   gc_e2e.json           md5 of gc_fix1.fa / ont_link.txt / valid_ont_link.txt + stat lines, from gc
+  kmer_aux_<cfg>_k<k>.npz  kmer_t.hs_id of every contig position for n_thread = 3 and 7 (crc32 % n_thread,
+                        kmer.c:88) and okseq->segs of every read after find_unankor_segs (ont.c:264-309), from ref_kmer
   sw_vectors.json       sw_align results (score, offset, softclip, CIGAR) in as-is and fixed mode,
                         including call sequences that exercise the stale-border state
 """
@@ -39,6 +41,24 @@ def kmer_fixture(tmp, cfg, k):
                         stats=np.array([info["scaf_total"], info["scaf_unique"], info["ont_total"], info["ont_unique"]], dtype=np.int64),
                         counts=np.array([info["n_contigs"], info["n_reads"], info["n_ctg_kmers"], info["n_ont_kmers"]], dtype=np.int64))
     print("kmer", cfg, k, info["n_hits"], "anchors")
+
+
+def aux_fixture(tmp, cfg, k):
+    fa, fq, _ = synth.materialise(cfg, tmp)
+    out = {}
+    for nt in (3, 7):
+        prefix = os.path.join(tmp, "%s_k%d_aux%d" % (cfg, k, nt))
+        info, hits, _, ctgk = orc.run_ref_kmer(fa, fq, k, prefix, n_thread=nt, dump=2)
+        out["hs_id_nt%d" % nt] = orc.read_hsid(prefix)
+        assert len(out["hs_id_nt%d" % nt]) == len(ctgk)
+        segs = orc.read_segs(prefix)
+        flat = np.concatenate([s_.reshape(-1) for s_ in segs]) if segs else np.zeros(0, np.int32)
+        cnt = np.array([len(s_) for s_ in segs], dtype=np.int32)
+        if "seg_count" in out:
+            assert np.array_equal(out["seg_count"], cnt) and np.array_equal(out["seg_flat"], flat), "segs depend on n_thread?"
+        out["seg_count"], out["seg_flat"] = cnt, flat
+    np.savez_compressed(os.path.join(OUT, "kmer_aux_%s_k%d.npz" % (cfg, k)), **out)
+    print("aux", cfg, k, len(out["hs_id_nt3"]), "contig k-mers,", int(out["seg_count"].sum()), "segments")
 
 
 def gc_fixture(tmp, cfg, nts=(1, 4)):
@@ -127,9 +147,14 @@ def main():
                 gc[cfg] = gc_fixture(tmp, cfg, nts=(3, 8))
         json.dump(gc, open(path, "w"), indent=1)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "--aux":
+        with tempfile.TemporaryDirectory() as tmp:
+            aux_fixture(tmp, "tiny", 25)
+        return
     with tempfile.TemporaryDirectory() as tmp:
         for cfg, k in (("tiny", 25), ("repeats", 25), ("repeats", 17), ("tiny", 31)):
             kmer_fixture(tmp, cfg, k)
+        aux_fixture(tmp, "tiny", 25)
         gc = {cfg: gc_fixture(tmp, cfg) for cfg in ("tiny", "small", "repeats", "cfg1")}
         json.dump(gc, open(os.path.join(OUT, "gc_e2e.json"), "w"), indent=1)
     sw_fixture()

@@ -24,8 +24,9 @@ def md5(path):
     return hashlib.md5(open(path, "rb").read()).hexdigest()
 
 
-@pytest.mark.parametrize("cfg,n_thread", [("tiny", 1), ("small", 4), ("repeats", 3), ("cfg1", 8), ("cfg5s", 8)])
+@pytest.mark.parametrize("cfg,n_thread", [("tiny", 1), ("small", 4), ("repeats", 3), ("cfg1", 8), ("cfg5s", 8), ("cfg2", 8)])
 def test_gap_filled_fasta_is_bit_exact(cfg, n_thread):
+    # cfg2: BASELINE configs[1], the bench's headline config, whole CLI
     # cfg5s: cfg5's gap density at 20 Mb / 6x — the contig table is beyond the L2 (pre-filter path) and
     # the reads go through the host pipeline in 15 chunks
     assert os.path.exists(GC), "gc_b200 was not built (python -c 'import __graft_entry__ as g; g.build()')"
@@ -164,3 +165,29 @@ def test_search_in_groups_matches_single_call():
         assert t.stats() == st_want
         t.free()
     cs.free(); rs.free(); ctx.close()
+
+
+@pytest.mark.parametrize("cfg,k,n_thread,env", [("tiny", 25, 3, {}), ("repeats", 17, 7, {}), ("small", 31, 2, {"GC_ANCHORS16": "1"}),
+                                                ("cfg1", 25, 5, {"GC_DEVICES": "0,0"})])
+def test_shim_harness_dumps_equal_the_reference_harness(cfg, k, n_thread, env):
+    """oracle/ref_kmer_harness.c performs main.c's call sequence (main.c:147-187) and dumps the host
+    structures the unchanged consumers read: kmers[] (with hs_id = crc32 % n_thread, kmer.c:88), every
+    non-NULL okmers[] entry, and okseq->segs (find_unankor_segs, ont.c:264-309).  Built once against the
+    reference's own objects (oracle/_ref/ref_kmer) and once against the replacement files + libgcgpu.so
+    (superplus_b200/_build/shim_kmer): the dumps must be byte-identical, the printed statistics equal.
+    GC_ANCHORS16 selects the 16-byte anchor download instead of the compact one."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_kmer")
+    shim = os.path.join(ROOT, "superplus_b200", "_build", "shim_kmer")
+    assert os.path.exists(ref) and os.path.exists(shim), "harness binaries were not built (python -c 'import __graft_entry__ as g; g.build()')"
+    with tempfile.TemporaryDirectory() as tmp:
+        fa, fq, _ = synth.materialise(cfg, tmp)
+        outs = {}
+        for name, exe, e in (("ref", ref, {}), ("shim", shim, env)):
+            r = subprocess.run([exe, fa, fq, str(n_thread), str(k), os.path.join(tmp, name), "2"], cwd=tmp, stdout=subprocess.PIPE,
+                               stderr=subprocess.PIPE, timeout=600, env=dict(os.environ, **e))
+            assert r.returncode == 0, (name, r.stderr.decode()[-2000:])
+            outs[name] = [int(x) for x in re.findall(r"(?:total|unique) kmer count: (\d+)", r.stdout.decode())]
+        assert outs["ref"] == outs["shim"] and len(outs["ref"]) == 4
+        for ext in ("hits.bin", "ctgk.bin", "hsid.bin", "segs.bin"):
+            a, b = open(os.path.join(tmp, "ref." + ext), "rb").read(), open(os.path.join(tmp, "shim." + ext), "rb").read()
+            assert len(a) > 0 and a == b, ext

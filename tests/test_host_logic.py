@@ -237,3 +237,16 @@ def test_replicated_search_orchestration_with_a_host_double():
         rep.free()
         assert sorted(e[1] for e in log if e[0] == "free") == sorted(t for t in prim.merged[:n - 1])
         assert rep.tables == [prim]
+
+
+def test_worker_pool_holds_one_job_at_a_time():
+    """a synchronous job offered to the host worker pool while an asynchronous one
+    (the gather of the next chunk) was still out overwrote its task counters and dropped the tasks nobody
+    had taken yet.  Now the second job runs on the calling thread: every task of both jobs runs exactly once."""
+    import ctypes as C
+    from superplus_b200 import api
+    L = api.load_library()
+    L.gcg_selftest_workers.restype = C.c_int64
+    L.gcg_selftest_workers.argtypes = [C.c_int, C.c_int, C.c_int]
+    for nt, na, nb in ((4, 16, 4), (8, 64, 8), (2, 5, 3), (1, 7, 2)):
+        assert L.gcg_selftest_workers(nt, na, nb) == na * 1000 + nb, (nt, na, nb)

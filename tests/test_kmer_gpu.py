@@ -40,13 +40,23 @@ def check_case(ctx, oracle, contigs, reads, k, via_ptrs=False):
     assert np.array_equal(hits["cpos_flags"] >> 2, o_hits["cpos"].astype(np.uint32))
     assert np.array_equal(hits["cpos_flags"] & 1, o_hits["krev"])
     assert np.array_equal((hits["cpos_flags"] >> 1) & 1, o_hits["orev"])
-    # kmer_t records for the unchanged host consumers
-    recs = ctx.chop_contigs(cs, [len(c) for c in contigs], k, n_thread=3)
+    # the same search as compact anchors (8 bytes per anchor + per-read offsets) on a fresh table:
+    # same anchors, same order, same ONT-side multiplicity
+    t2 = ctx.table_build(cs, k)
+    anchors, read_off = ctx.search_compact(t2, rs)
+    assert len(read_off) == len(reads) + 1 and read_off[0] == 0 and read_off[-1] == len(anchors) and np.all(np.diff(read_off) >= 0)
+    assert np.array_equal(api.expand_compact(anchors, read_off, [len(c) for c in contigs]), hits)
+    assert t2.stats() == st
+    t2.free()
+    # kmer_t records for the unchanged host consumers; hs_id = crc32(kseq) % n_thread (kmer.c:88)
+    n_thread = 1 + (len(hits) + k) % 7
+    recs = ctx.chop_contigs(cs, [len(c) for c in contigs], k, n_thread=n_thread)
     for i, c in enumerate(contigs):
         ks, rv = oracle.chop(c, k)
         r = recs[i]
         assert np.array_equal(r["kseq"], ks) and np.array_equal(r["flag"], rv)
         assert np.all(r["tid"] == i) and np.array_equal(r["pos"], np.arange(len(ks), dtype=np.int32)) and np.all(r["kmer_len"] == k)
+        assert np.array_equal(r["hs_id"], oracle.hs_id(ks, n_thread))
     t.free(); cs.free(); rs.free()
     return len(hits)
 
@@ -174,32 +184,85 @@ def test_randomised_small_cases(ctx, oracle, monkeypatch):
         got.free(); rs.free(); cs.free()
 
 
-@pytest.mark.parametrize("tight", ["0", "1"])
-def test_search_in_two_halves(ctx, oracle, tight, monkeypatch):
-    """GCG_SEARCH_SPLIT=1: gcg_search_seqs probes the reads as two halves so that the host fetches one
-    half's anchor count while the GPU works on the other (an option, measured slower than one pass):
-    switched on for small inputs here, also with the anchor buffer sized for the first half alone (the
-    second half then takes the regrow path), against the oracle and against the single pass; halves
-    without anchors included"""
-    monkeypatch.setenv("GCG_SEARCH_SPLIT", "1")
-    monkeypatch.setenv("GCG_SEARCH_SPLIT_MIN_TILES", "2")
-    monkeypatch.setenv("GCG_SEARCH_SPLIT_TIGHT", tight)
-    for name, k in (("repeats", 17), ("small", 31), ("tiny", 25)):
+def test_search_host_compact_form(ctx, oracle, monkeypatch):
+    """gcg_search_compact (what the shim calls): the anchors of gcg_search, 8 bytes each, grouped by
+    read; default chunks and tiny chunks (read offsets stitched over many chunks, reads without
+    k-mers, empty reads at either end)"""
+    inp = synth.make_config("small")
+    e = np.zeros(0, np.uint8)
+    reads = [e, inp.reads[0][:10]] + inp.reads[:50] + [e, e, inp.reads[1][:24]] + inp.reads[50:] + [e]
+    cs = ctx.upload(inp.contigs)
+    t = ctx.table_build(cs, 25)
+    want = ctx.search_host(t, reads)
+    st = t.stats()
+    t.free()
+    clens = [len(c) for c in inp.contigs]
+    for chunk in (None, 65536, 4096):
+        if chunk is not None:
+            monkeypatch.setenv("GCG_SEARCH_CHUNK_BYTES", str(chunk))
+        t = ctx.table_build(cs, 25)
+        anchors, read_off = ctx.search_host_compact(t, reads)
+        assert len(read_off) == len(reads) + 1 and read_off[-1] == len(anchors)
+        assert np.array_equal(api.expand_compact(anchors, read_off, clens), want), chunk
+        assert t.stats() == st
+        t.free()
+    # nothing to search: offsets are still there
+    t = ctx.table_build(cs, 25)
+    anchors, read_off = ctx.search_host_compact(t, [e, inp.reads[0][:5]])
+    assert len(anchors) == 0 and list(read_off) == [0, 0, 0]
+    t.free(); cs.free()
+
+
+@pytest.mark.parametrize("frac", ["0.0", "0.01", "0.05"])
+def test_result_buffer_smaller_than_the_anchors(ctx, oracle, frac, monkeypatch):
+    """the device-resident search sizes its anchor buffer from an estimate; GCG_SEARCH_CAP_FRAC forces
+    estimates far below the truth: the second launch must finish the job without recording any
+    anchor's ONT-side multiplicity twice (statistics unchanged)"""
+    monkeypatch.setenv("GCG_SEARCH_CAP_FRAC", frac)
+    for name, k in (("repeats", 17), ("small", 25)):
         inp = synth.make_config(name)
         check_case(ctx, oracle, inp.contigs, inp.reads, k)
-    inp = synth.make_config("small")
-    rng = np.random.default_rng(9)
-    junk = [np.frombuffer(b"ACTG", np.uint8)[rng.integers(0, 4, 3000)] for _ in range(700)]   # as many bases again, none of them anchors
-    cs = ctx.upload(inp.contigs)
-    for reads in (junk + inp.reads, inp.reads + junk, junk + junk):
-        rs = ctx.upload(reads)
-        monkeypatch.setenv("GCG_SEARCH_SPLIT", "1")
-        t = ctx.table_build(cs, 25)
-        a, st_a = ctx.search(t, rs), t.stats()
+
+
+def test_host_result_buffer_grows_while_the_pool_gathers(ctx, oracle, monkeypatch):
+    """the pinned result of gcg_search starts from an estimate and is copied into a larger
+    block when a chunk does not fit; with more than 4 MiB already placed that copy used the worker pool
+    while the pool was still gathering the next chunk, which dropped gather tasks.  Force the path: a
+    result buffer of one anchor, several host threads, chunks small enough that many follow."""
+    from superplus_b200 import api as _api
+    inp = synth.make_config("cfg1")
+    c2 = _api.Context(0, host_threads=8)
+    cs = c2.upload(inp.contigs)
+    t = c2.table_build(cs, 25)
+    want = c2.search_host(t, inp.reads)
+    assert len(want) * 16 > (8 << 20)                    # well beyond the 4 MiB threshold of the threaded copy
+    t.free()
+    monkeypatch.setenv("GCG_SEARCH_RES_CAP", "1")
+    monkeypatch.setenv("GCG_SEARCH_CHUNK_BYTES", str(1 << 20))
+    for compact in (False, True):
+        t = c2.table_build(cs, 25)
+        if compact:
+            anchors, read_off = c2.search_host_compact(t, inp.reads)
+            got = _api.expand_compact(anchors, read_off, [len(c) for c in inp.contigs])
+        else:
+            got = c2.search_host(t, inp.reads)
+        assert np.array_equal(got, want), compact
         t.free()
-        monkeypatch.setenv("GCG_SEARCH_SPLIT", "0")
-        t = ctx.table_build(cs, 25)
-        b, st_b = ctx.search(t, rs), t.stats()
-        t.free(); rs.free()
-        assert np.array_equal(a, b) and st_a == st_b
-    cs.free()
+    cs.free(); c2.close()
+
+
+def test_two_pass_search_still_agrees(ctx, oracle):
+    """GCG_SEARCH_FUSED=0 keeps the round-1 form (probe -> masks, prefix sum, emit) for A/B timing; the
+    switch is read once per process, so the comparison runs in a child process"""
+    import subprocess, sys, os as _os
+    code = ("import numpy as np, sys; sys.path.insert(0, %r)\n"
+            "from superplus_b200 import api, synth\n"
+            "inp = synth.make_config('small'); c = api.Context(0)\n"
+            "cs, rs = c.upload(inp.contigs), c.upload(inp.reads); t = c.table_build(cs, 25)\n"
+            "h = c.search(t, rs); print(len(h), int(h['pos'].astype(np.int64).sum()), int(h['cpos_flags'].astype(np.int64).sum()), t.stats())\n") % _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    outs = []
+    for v in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(_os.environ, GCG_SEARCH_FUSED=v), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+        assert r.returncode == 0, r.stderr.decode()[-2000:]
+        outs.append(r.stdout.decode().strip())
+    assert outs[0] == outs[1] and outs[0]

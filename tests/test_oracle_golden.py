@@ -28,6 +28,30 @@ def test_kmer_oracle_matches_reference_fixture(oracle, cfg, k):
     assert np.array_equal(hits["krev"], g["kflag"]) and np.array_equal(hits["orev"], g["oflag"])
 
 
+def test_hs_id_and_unanchored_segments_match_reference_fixture(oracle):
+    """kmer_t.hs_id = crc32(canonical k-mer) % n_thread (kmer.c:88, crc32.h:70-81) and okseq->segs
+    (find_unankor_segs, ont.c:264-309) as dumped by the reference harness"""
+    g = np.load(os.path.join(GOLD, "kmer_aux_tiny_k25.npz"))
+    inp = synth.make_config("tiny")
+    ks = np.concatenate([oracle.chop(c, 25)[0] for c in inp.contigs])
+    for nt in (3, 7):
+        assert np.array_equal(oracle.hs_id(ks, nt), g["hs_id_nt%d" % nt]), nt
+    h = oracle.table_build(inp.contigs, 25)
+    hits, _ = oracle.search(h, inp.reads, 25)
+    oracle.table_free(h)
+    cnt, flat = g["seg_count"], g["seg_flat"]
+    assert len(cnt) == len(inp.reads)
+    at = 0
+    for r, read in enumerate(inp.reads):
+        segs = oracle.unanchored_segs(len(read), hits["pos"][hits["read"] == r])
+        assert len(segs) == cnt[r] and np.array_equal(segs.reshape(-1), flat[at:at + 2 * cnt[r]]), r
+        at += 2 * int(cnt[r])
+    # known answers of the CRC itself: zlib's CRC-32 over the 8 little-endian bytes
+    import zlib
+    for v in (0, 1, 0x123456789ABCDEF, (1 << 50) - 1):
+        assert int(oracle.L.gco_kseq_crc32(v)) & 0xffffffff == zlib.crc32(int(v).to_bytes(8, "little"))
+
+
 def _vectors():
     return json.load(open(os.path.join(GOLD, "sw_vectors.json")))
 

@@ -56,6 +56,7 @@ def test_kmer_pipeline_against_reference_harness(oracle):
         fa, fq = os.path.join(tmp, "r.fa"), os.path.join(tmp, "r.fq")
         synth.write_fasta(fa, inp.scaffold); synth.write_fastq(fq, inp.reads)
         info, hits, table, ctgk = orc.run_ref_kmer(fa, fq, 21, os.path.join(tmp, "out"), n_thread=2, dump=2)
+        hsid, segs = orc.read_hsid(os.path.join(tmp, "out")), orc.read_segs(os.path.join(tmp, "out"))
     contigs = inp.contigs
     h = oracle.table_build(contigs, 21)
     key, multi, tid, pos, rev = oracle.table_dump(h)
@@ -67,6 +68,10 @@ def test_kmer_pipeline_against_reference_harness(oracle):
     assert np.array_equal(H["read"], hits["read"]) and np.array_equal(H["pos"], hits["pos"]) and np.array_equal(H["cpos"], hits["cpos"])
     ks = np.concatenate([oracle.chop(c, 21)[0] for c in contigs])
     assert np.array_equal(ks, ctgk["kseq"])
+    assert np.array_equal(oracle.hs_id(ks, 2), hsid)                          # kmer.c:88
+    assert len(segs) == len(inp.reads)
+    for r, read in enumerate(inp.reads):                                       # ont.c:264-309
+        assert np.array_equal(oracle.unanchored_segs(len(read), H["pos"][H["read"] == r]), segs[r]), r
     oracle.table_free(h)
 
 
