@@ -265,10 +265,12 @@ void * gcg_pinned_alloc (size_t bytes)
   }
   size_t cap = bytes + bytes / 8;
   void * p = nullptr;
-  if (cudaHostAlloc (&p, cap, cudaHostAllocDefault) != cudaSuccess) {
+  // mapped + portable: the search kernels of any context store anchors straight into these blocks (zero-copy results)
+  const unsigned flags = cudaHostAllocMapped | cudaHostAllocPortable;
+  if (cudaHostAlloc (&p, cap, flags) != cudaSuccess) {
     cudaGetLastError ();
     cap = bytes;
-    if (cudaHostAlloc (&p, cap, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError (); return nullptr; }
+    if (cudaHostAlloc (&p, cap, flags) != cudaSuccess) { cudaGetLastError (); return nullptr; }
   }
   g_pin.push_back ({p, cap, true});
   return p;

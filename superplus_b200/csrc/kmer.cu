@@ -149,9 +149,9 @@ k23_build_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
 // receive the word's read index and its first position (undefined for words past the end).
 struct k4_smem { uint32_t excl[K4_WARPS][33], pend[K4_WARPS][32], add[K4_WARPS][32]; };
 
-template <bool FILTER, int KC>
+template <bool FILTER, int KC, bool PF>
 __device__ __forceinline__ uint32_t
-k4_probe_tile (k4_smem & sm, const int64_t tile, const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff,
+k4_probe_tile (k4_smem & sm, const unsigned long long * __restrict__ vals, const int64_t tile, const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff,
                const int32_t * __restrict__ len, const int32_t * __restrict__ tile_seq, const int64_t n_seq, const int64_t n_words, const int k,
                const unsigned long long * __restrict__ keys, const uint32_t n_bucket,
                const uint32_t * __restrict__ filter, const uint32_t filter_words, const int filter_k3,
@@ -178,7 +178,7 @@ k4_probe_tile (k4_smem & sm, const int64_t tile, const uint64_t * __restrict__ p
     r.init (pk, __ldg (packed + w + 1), k);
     for (int j0 = 0; j0 < nvalid; j0 += K4_UNROLL) {
       unsigned long long key[K4_UNROLL];
-      uint32_t fp[K4_UNROLL];
+      uint32_t fp[K4_UNROLL], bk[K4_UNROLL];
       bucket4 q[K4_UNROLL];
       if (FILTER) {
         uint32_t hh[K4_UNROLL], fw[K4_UNROLL];
@@ -194,7 +194,8 @@ k4_probe_tile (k4_smem & sm, const int64_t tile, const uint64_t * __restrict__ p
         for (int u = 0; u < K4_UNROLL; ++u) {
           const uint32_t m = filter_mask (hh[u], filter_k3);
           q[u].a = q[u].b = q[u].c = q[u].d = 0ULL;        // no match, no overflow mark
-          if ((fw[u] & m) == m) q[u] = ld_bucket (keys + 4ULL * __umulhi (hh[u], n_bucket));
+          bk[u] = __umulhi (hh[u], n_bucket);
+          if ((fw[u] & m) == m) q[u] = ld_bucket_keep (keys + 4ULL * bk[u]);
         }
       } else {
 #pragma unroll
@@ -203,7 +204,8 @@ k4_probe_tile (k4_smem & sm, const int64_t tile, const uint64_t * __restrict__ p
           key[u] = (r.fwd < r.rc ? r.fwd : r.rc) + 1ULL;
           uint32_t h = kmer_hash32 (key[u] - 1ULL);
           fp[u] = h & 3u;
-          q[u] = ld_bucket (keys + 4ULL * __umulhi (h, n_bucket));
+          bk[u] = __umulhi (h, n_bucket);
+          q[u] = ld_bucket_keep (keys + 4ULL * bk[u]);
         }
       }
       // four result bits per group at constant positions, one variable shift per group; positions
@@ -211,8 +213,12 @@ k4_probe_tile (k4_smem & sm, const int64_t tile, const uint64_t * __restrict__ p
       uint32_t hb = 0, ob = 0;
 #pragma unroll
       for (int u = 0; u < K4_UNROLL; ++u) {
-        hb |= bucket_has_unique (q[u], key[u]) ? (1u << u) : 0u;   // multi == 1  (ont.c:171,195)
+        const bool hit = bucket_has_unique (q[u], key[u]);           // multi == 1  (ont.c:171,195)
+        hb |= hit ? (1u << u) : 0u;
         ob |= bucket_ovf_bit (q[u], fp[u], u);
+        // the anchor's value word (the four of a bucket share one sector) is wanted a few microseconds from now,
+        // when the tile's anchors are emitted: start it on its way into the L2
+        if (PF && hit) prefetch_l2 (vals + 4ULL * bk[u]);
       }
       mymask |= hb << j0;
       pend |= (ob & ~hb) << j0;
@@ -264,8 +270,8 @@ k45_search_kernel (const uint64_t * __restrict__ packed, const int64_t * __restr
   const int64_t wstride = (int64_t) gridDim.x * K4_WARPS;
   for (int64_t tile = tile0 + (int64_t) blockIdx.x * K4_WARPS + wid; tile < n_tiles; tile += wstride) {   // tiles [tile0, n_tiles)
     uint64_t pk; int32_t sq, p0;
-    const uint32_t mymask = k4_probe_tile<FILTER, KC> (sm, tile, packed, woff, len, tile_seq, n_seq, n_words, k, keys, n_bucket,
-                                                       filter, filter_words, filter_k3, &pk, &sq, &p0);
+    const uint32_t mymask = k4_probe_tile<FILTER, KC, false> (sm, nullptr, tile, packed, woff, len, tile_seq, n_seq, n_words, k, keys, n_bucket,
+                                                              filter, filter_words, filter_k3, &pk, &sq, &p0);
     const int64_t w = (tile << 5) + lane;
     if (w < n_words) hitmask[w] = mymask;
   }
@@ -322,60 +328,129 @@ struct k45f_args {
   int32_t read_base;                        // added to the read index of FMT 0 records
   const int64_t * cbase;                    // FMT 1: first base of every contig in the concatenated scaffold coordinate
   long long * read_off;                     // FMT 1 (optional for FMT 0): [n_seq], pre-set to -1; written for every read that owns a word
-  unsigned long long * total_out;           // number of anchors of the launch (device or mapped host memory)
+  unsigned long long * total_out;           // base + number of anchors of the launch (device or mapped host memory)
+  const unsigned long long * base_in;       // optional: global index of the launch's first anchor (anchors of earlier chunks); must not alias total_out
+  unsigned long long * done_out;            // optional (mapped host memory): receives base_in's value when the launch starts, i.e. the number of
+                                            // anchors that are COMPLETE in `out` (every earlier launch has finished)
 };
 
+// Build-time switches (A/B variants, scripts/build_variants.sh):
+//   K45F_MINB      resident blocks per SM asked of ptxas (8 = 32 registers, full occupancy)
+//   K45F_BLOCKSCAN chained scan over BLOCK tiles (8 warp tiles share one state word) instead of warp tiles:
+//                  the first wave of a launch resolves its prefixes hop by hop, 32 states per hop — with
+//                  9472 warp tiles in flight that is 296 dependent L2 round trips, with 1184 block tiles 37
+//   K45F_PREFETCH  the probe loop starts the value sector of every hit on its way into the L2
+#ifndef K45F_MINB
+#define K45F_MINB 6
+#endif
+#ifndef K45F_BLOCKSCAN
+#define K45F_BLOCKSCAN 1
+#endif
+#ifndef K45F_PREFETCH
+#define K45F_PREFETCH 0
+#endif
+#ifndef K45F_DIAG
+#define K45F_DIAG 0
+#endif
+
+// exclusive prefix of chain element `idx` (whose own count `total` is published here), by the calling warp;
+// idx must have been handed out in increasing order (every predecessor is with a running warp or block)
+__device__ __forceinline__ unsigned long long
+chain_lookback (unsigned long long * __restrict__ state, const int64_t idx, const unsigned long long total, const int lane,
+                const unsigned long long base0)
+{
+  unsigned long long base = base0;
+  if (idx > 0) {
+    base = 0;
+    if (lane == 0) st_state (state + idx, SCANST_AGG | total);
+    int64_t j = idx - 1;
+    for (;;) {
+      const int64_t at = j - lane;                    // lane 0 looks at the nearest predecessor
+      const unsigned long long st = at >= 0 ? ld_state (state + at) : (SCANST_INC | base0);   // before element 0: what earlier launches emitted
+      const uint32_t inc = __ballot_sync (0xffffffffu, (st & SCANST_INC) != 0);
+      const uint32_t none = __ballot_sync (0xffffffffu, (st & (SCANST_INC | SCANST_AGG)) == 0);
+      const int f = inc ? __ffs (inc) - 1 : 32;       // nearest element with a known inclusive prefix
+      const uint32_t need = f < 31 ? ((2u << f) - 1u) : 0xffffffffu;
+      if (none & need) { __nanosleep (40); continue; }     // an element nearer than that has not published yet
+      unsigned long long sum = (lane <= f) ? (st & SCANST_VAL) : 0ULL;
+      for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync (0xffffffffu, sum, o);
+      base += sum;
+      if (f < 32) break;
+      j -= 32;
+    }
+  }
+  if (lane == 0) st_state (state + idx, SCANST_INC | (base + total));
+  return base;
+}
+
 template <bool FILTER, int KC, int FMT>
-__global__ void __launch_bounds__ (32 * K4_WARPS)
+__global__ void __launch_bounds__ (32 * K4_WARPS, K45F_MINB)
 k45_fused_kernel (const k45f_args A)
 {
   __shared__ k4_smem sm;
   __shared__ uint32_t s_mask[K4_WARPS][32];
   __shared__ uint64_t s_pk[K4_WARPS][33];
   __shared__ int32_t s_seq[K4_WARPS][32], s_p0[K4_WARPS][32];
+#if K45F_BLOCKSCAN
+  __shared__ unsigned long long s_bt, s_bbase;
+  __shared__ uint32_t s_wtot[K4_WARPS];
+#endif
   const int k = KC > 0 ? KC : A.k;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t n_tiles = (A.n_words + 31) >> 5;
+  const unsigned long long base0 = A.base_in ? *A.base_in : 0ULL;
+  if (A.done_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *A.done_out = base0;
   for (;;) {
+#if K45F_BLOCKSCAN
+    // ---- a block takes K4_WARPS consecutive warp tiles; chain element = block tile
+    const int64_t n_bt = (n_tiles + K4_WARPS - 1) / K4_WARPS;
+    __syncthreads ();                                  // (the previous round's s_bt / s_wtot / s_bbase have been read)
+    if (threadIdx.x == 0) s_bt = atomicAdd (A.tile_ctr, 1ULL);
+    __syncthreads ();
+    const int64_t bt = (int64_t) s_bt;
+    if (bt >= n_bt) break;
+    const int64_t tile = bt * K4_WARPS + wid;          // may be past the end in the last block tile: probes nothing
+#else
     unsigned long long t_ = 0;
     if (lane == 0) t_ = atomicAdd (A.tile_ctr, 1ULL);
     const int64_t tile = (int64_t) __shfl_sync (0xffffffffu, t_, 0);
     if (tile >= n_tiles) break;
+#endif
     uint64_t pk; int32_t sq, p0;
-    const uint32_t mymask = k4_probe_tile<FILTER, KC> (sm, tile, A.packed, A.woff, A.len, A.tile_seq, A.n_seq, A.n_words, k, A.keys, A.n_bucket,
-                                                       A.filter, A.filter_words, A.filter_k3, &pk, &sq, &p0);
+    const uint32_t mymask = k4_probe_tile<FILTER, KC, K45F_PREFETCH != 0> (sm, A.vals, tile, A.packed, A.woff, A.len, A.tile_seq, A.n_seq, A.n_words, k, A.keys, A.n_bucket,
+                                                                           A.filter, A.filter_words, A.filter_k3, &pk, &sq, &p0);
     const int64_t w = (tile << 5) + lane;
     const uint32_t c = __popc (mymask);
     uint32_t x = c;
     for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (0xffffffffu, x, o); if (lane >= o) x += y; }
     const uint32_t total = __shfl_sync (0xffffffffu, x, 31);
-    // ---- chained scan over the tiles: exclusive prefix of this tile
-    unsigned long long base = 0;
-    if (tile > 0) {
-      if (lane == 0) st_state (A.state + tile, SCANST_AGG | total);
-      int64_t j = tile - 1;
-      for (;;) {
-        const int64_t idx = j - lane;                   // lane 0 looks at the nearest predecessor
-        const unsigned long long st = idx >= 0 ? ld_state (A.state + idx) : SCANST_INC;   // before tile 0: inclusive prefix 0
-        const uint32_t inc = __ballot_sync (0xffffffffu, (st & SCANST_INC) != 0);
-        const uint32_t none = __ballot_sync (0xffffffffu, (st & (SCANST_INC | SCANST_AGG)) == 0);
-        const int f = inc ? __ffs (inc) - 1 : 32;       // nearest tile with a known inclusive prefix
-        const uint32_t need = f < 31 ? ((2u << f) - 1u) : 0xffffffffu;
-        if (none & need) { __nanosleep (40); continue; }     // a tile nearer than that has not published yet
-        const unsigned long long v = (lane <= f) ? (st & SCANST_VAL) : 0ULL;
-        unsigned long long sum = v;
-        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync (0xffffffffu, sum, o);
-        base += sum;
-        if (f < 32) break;
-        j -= 32;
+    // ---- chained scan: global index of this tile's first anchor
+    unsigned long long base;
+#if K45F_BLOCKSCAN
+    if (lane == 0) s_wtot[wid] = total;
+    __syncthreads ();
+    if (wid == 0) {
+      uint32_t bsum = 0;
+#pragma unroll
+      for (int i = 0; i < K4_WARPS; ++i) bsum += s_wtot[i];
+      const unsigned long long bb = chain_lookback (A.state, bt, bsum, lane, base0);
+      if (lane == 0) {
+        s_bbase = bb;
+        if (bt == n_bt - 1) *A.total_out = bb + bsum;
       }
     }
-    if (lane == 0) {
-      st_state (A.state + tile, SCANST_INC | (base + total));
-      if (tile == n_tiles - 1) *A.total_out = base + total;
-    }
+    __syncthreads ();
+    base = s_bbase;
+    for (int i = 0; i < wid; ++i) base += s_wtot[i];
+#else
+    base = chain_lookback (A.state, tile, total, lane, base0);
+    if (lane == 0 && tile == n_tiles - 1) *A.total_out = base + total;
+#endif
     if (A.read_off != nullptr && w < A.n_words && p0 == 0) A.read_off[sq] = (long long) (base + (x - c));
     if (total == 0) continue;
+#if K45F_DIAG == 2
+    continue;                                          // (diagnostic build: probe + scan only — NO anchors, timing only)
+#endif
     // ---- emit: the tile's anchors in (word, bit) order, 32 per round
     __syncwarp ();
     sm.excl[wid][lane] = x - c;
@@ -396,13 +471,17 @@ k45_fused_kernel (const k45f_args A)
       unsigned long long kw;
       const unsigned long long key = key_at (s_pk[wid][lo], s_pk[wid][lo + 1], j, k, &fw);
       const uint32_t hs = kmer_hash32 (key - 1ULL), b = __umulhi (hs, A.n_bucket);
-      const bucket4 q = ld_bucket (A.keys + 4ULL * b);
+      const bucket4 q = ld_bucket_keep (A.keys + 4ULL * b);
       const int f = bucket_find (q, key, &kw);
       const unsigned long long slot = f >= 0 ? 4ULL * b + (unsigned) f
                                              : table_lookup (A.keys, A.n_bucket, b, q, key, hs & 3u, &kw);   // walks on to the overflow buckets
       // one atomic both records the anchor (ONT-side multiplicity, ont.c:245) and returns (tid, pos, flag)
+#if K45F_DIAG == 1
+      const unsigned long long v = slot;               // (diagnostic build: no value access — WRONG results, timing only)
+#else
       const unsigned long long v = atomicOr (A.vals + slot, GCG_VAL_ONT1);
       if ((v & (GCG_VAL_ONT1 | GCG_VAL_ONT2)) == GCG_VAL_ONT1) atomicOr (A.vals + slot, GCG_VAL_ONT2);
+#endif
       const uint32_t tid = (uint32_t) (v >> 32) & 0x7FFFFFFFu, cpos = (uint32_t) (v >> 1) & 0x3FFFFFFFu;
       const uint32_t flags = (uint32_t) (v & 1ULL) | (fw ? 0u : 2u);
       if (FMT == 0) {
@@ -965,7 +1044,10 @@ int gcg_table_alloc (gcg_ctx * ctx, int64_t n_kmers, int k, gcg_table ** out)
   GCG_CUDA (cudaSetDevice (ctx->device));
   gcg_table * t = new gcg_table ();
   t->ctx = ctx; t->k = k;
-  int64_t nb = (n_kmers + 1) / 2 + 64;
+  // buckets of four slots at load factor <= 0.5 (GCG_TABLE_LOAD=<percent> for A/B runs: a denser table is smaller —
+  // closer to the L2 — but more of its buckets overflow)
+  static const int load_pct = [] () { const char * e = getenv ("GCG_TABLE_LOAD"); int v = e ? atoi (e) : 50; return v >= 10 && v <= 90 ? v : 50; } ();
+  int64_t nb = (n_kmers * 25 + load_pct - 1) / load_pct + 64;
   if (nb >= 0xFFFFFFFFLL) { delete t; gcg_set_error ("gcg_table: %lld k-mers exceed the bucket index range", (long long) n_kmers); return GCG_ERANGE; }
   t->n_bucket = (uint32_t) nb;
   t->n_slot = (uint64_t) nb * 4;
@@ -1030,7 +1112,9 @@ extern "C" int gcg_table_build (gcg_ctx * ctx, const char * const * contig_seq, 
   int rc = gcg_seqs_upload (ctx, contig_seq, contig_len, n_contig, &s);
   if (rc) return rc;
   rc = gcg_table_build_seqs (ctx, s, k, out);
-  if (!rc && cudaStreamSynchronize (ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_table_build: sync failed"); rc = GCG_ECUDA; }
+  // no wait for the insert kernel: everything that uses the table is ordered behind it on the context's stream, and
+  // the packed contigs go back to the context's block cache, which only hands them to work queued later on that stream
+  // (the upload above has synchronised, so the caller's strings are no longer read)
   gcg_seqs_free (s);
   return rc;
 }
@@ -1304,18 +1388,19 @@ extern "C" int64_t gcg_hits_count (const gcg_hits * h) { return h ? h->n : 0; }
 static int launch_fused (gcg_ctx * ctx, const gcg_table * t, const uint64_t * d_packed, const int64_t * d_woff, const int32_t * d_len,
                          const int32_t * d_tseq, int64_t n_seq, int64_t n_words, int k, int fmt, void * d_out,
                          unsigned long long win_lo, unsigned long long win_hi, int32_t read_base, long long * d_read_off,
-                         unsigned long long * d_state, unsigned long long * total_out)
+                         unsigned long long * d_state, unsigned long long * total_out,
+                         const unsigned long long * base_in = nullptr, bool preset_read_off = false, unsigned long long * done_out = nullptr)
 {
   const int64_t n_tiles = (n_words + 31) >> 5;
   GCG_CUDA (cudaMemsetAsync (d_state, 0, (size_t) (n_tiles + 1) * 8, ctx->stream));
-  if (d_read_off) GCG_CUDA (cudaMemsetAsync (d_read_off, 0xFF, (size_t) std::max<int64_t> (n_seq, 1) * 8, ctx->stream));
+  if (d_read_off && !preset_read_off) GCG_CUDA (cudaMemsetAsync (d_read_off, 0xFF, (size_t) std::max<int64_t> (n_seq, 1) * 8, ctx->stream));
   k45f_args A;
   A.packed = d_packed; A.woff = d_woff; A.len = d_len; A.tile_seq = d_tseq; A.n_seq = n_seq; A.n_words = n_words; A.k = k;
   A.keys = t->d_keys; A.vals = t->d_vals; A.n_bucket = t->n_bucket;
   const bool flt = t->filter_valid && t->filter_words;
   A.filter = flt ? t->d_filter : nullptr; A.filter_words = flt ? t->filter_words : 0u; A.filter_k3 = flt ? t->filter_k3 : 0;
   A.tile_ctr = d_state + n_tiles; A.state = d_state; A.out = d_out; A.win_lo = win_lo; A.win_hi = win_hi;
-  A.read_base = read_base; A.cbase = t->d_cbase; A.read_off = d_read_off; A.total_out = total_out;
+  A.read_base = read_base; A.cbase = t->d_cbase; A.read_off = d_read_off; A.total_out = total_out; A.base_in = base_in; A.done_out = done_out;
   gcg_kscope ks (ctx, "k45_fused");
   const int grid = grid_for (ctx, n_tiles * 32, 32 * K4_WARPS, 8);
 #define K45F(F, KC) (fmt ? k45_fused_kernel<F, KC, 1> : k45_fused_kernel<F, KC, 0>)
@@ -1497,27 +1582,40 @@ extern "C" int gcg_hits_download (gcg_ctx * ctx, const gcg_hits * h, gcg_hit * d
   return GCG_OK;
 }
 
-// ---- host-buffer search: a three-stage stream pipeline ------------------------------------------
-// The reads are cut into chunks of whole reads (16 MiB of bases by default).  For chunk c
-//   host      gathers the reads into a pinned slot (worker pool, streaming stores)
-//   `up`      copies slot -> HBM                                     (PCIe, host -> device)
-//   ctx->stream packs, probes, scans and emits the chunk's anchors into the slot's device buffer
-//   `down`    copies the anchors to their final place in the pinned result     (PCIe, device -> host)
-// so the gather, both PCIe directions and the kernels of neighbouring chunks overlap; the only
-// host wait per chunk is for the anchor count of the PREVIOUS chunk (needed to place its copy).
+// ---- host-buffer search: a stream pipeline ------------------------------------------------------
+// The reads are cut into chunks of whole reads (8 MiB of bases by default).  For chunk c
+//   host        gathers the reads into a pinned slot and packs them to 2 bits on the way (worker pool)
+//   `up`        copies slot -> HBM                                     (PCIe, host -> device)
+//   ctx->stream probes the chunk and emits its anchors in one launch (k45_fused_kernel)
+// and the anchors reach the caller's pinned result in one of two ways:
+//   direct (default): ONE device result for the whole call; the kernel stores every anchor record — and
+//       every read's offset — at its FINAL index: the chained scan of a chunk starts from the running
+//       anchor count of the chunks before it, which lives in device memory.  Every launch begins by
+//       posting that count into mapped host memory: "anchors [0, n) are complete" (all earlier
+//       launches have finished).  The host loop just reads the word as it passes by and queues D2H
+//       copies of whatever has become complete on the `down` stream — it never waits for the GPU
+//       between a chunk's kernel and its output, only to reuse a slot.  A result sized from an estimate
+//       can overflow: anchors past the capacity are neither stored nor counted (the kernel's window),
+//       the call learns the true total at the end and a second pass materialises exactly the missing tail.
+//       (GCG_SEARCH_ZEROCOPY=1 lets the kernel store straight into the mapped pinned result instead of a
+//       device result + copies: measured slower, 3.0 against 2.6 ms at cfg2 — the posted PCIe writes of the
+//       SMs reach about half the copy engine's rate and back up into the probing warps.)
+//   staged (GCG_SEARCH_DIRECT=0, the round-1 form kept for A/B timing): the kernel fills the slot's device
+//       buffer (sized for the worst case), the host WAITS for the chunk's anchor count one chunk late and
+//       queues a D2H copy to the final place.
 // Chunks hold far fewer than 2^32 positions, so any read set size works (cfg5: 5 G positions);
-// anchors come out in (read,pos) order because chunks are consecutive and copies are placed by
-// running offset.  The ONT multiplicity state accumulates in the table across chunks.
+// anchors come out in (read,pos) order because chunks are consecutive.  The ONT multiplicity state
+// accumulates in the table across chunks.
 #define PIPE_SLOTS 5
-#define PIPE_LAG 2          // most chunks between a submit and the host looking at its anchor count (GCG_SEARCH_LAG, default 1)
+#define PIPE_LAG 2          // staged mode: most chunks between a submit and the host looking at its anchor count (GCG_SEARCH_LAG, default 1)
 
 struct pipe_slot {
   uint64_t * h_packed = nullptr;                     // pinned, cap_words words: the chunk 2-bit packed by the host gather
   char * h_meta = nullptr, * d_meta = nullptr;       // woff | len | tile_seq of the chunk
   uint64_t * d_packed = nullptr;
   unsigned long long * d_state = nullptr;            // chained-scan state of the chunk's tiles + the tile counter
-  long long * d_read_off = nullptr;                  // compact form: first anchor of every read of the chunk
-  gcg_hit * d_hits = nullptr;                        // cap_words * 32 anchors of 16 bytes (every position could anchor)
+  long long * d_read_off = nullptr;                  // staged mode, compact form: first anchor of every read of the chunk
+  gcg_hit * d_hits = nullptr;                        // staged mode: cap_words * 32 anchors of 16 bytes (every position could anchor)
   cudaEvent_t ev_up = nullptr, ev_emit = nullptr, ev_free = nullptr;
   bool busy = false, pending = false;                // ev_free recorded / chunk waiting for its download
   int64_t first_read = 0, n_read = 0;
@@ -1526,11 +1624,14 @@ struct pipe_slot {
 struct gcg_pipe {
   int64_t cap_words = 0;
   size_t meta_cap = 0;
+  bool staged = false;                               // the staged-mode buffers exist
   cudaStream_t up = nullptr, down = nullptr;
   pipe_slot s[PIPE_SLOTS];
   unsigned long long * h_count = nullptr;            // pinned + mapped, one per slot: the search kernel stores the chunk's anchor
   unsigned long long * hd_count = nullptr;           // count straight into host memory (device alias of h_count) — a copy of
                                                      // 8 bytes would queue behind the anchor downloads on the D2H copy engine
+  unsigned long long * d_run = nullptr;              // zero copy: running anchor count, two words used alternately (a launch
+                                                     // reads one and writes the other: late blocks must not see their own total)
   int64_t last_total = 0;                            // anchors of the previous call: sizes the next result buffer
 };
 
@@ -1547,20 +1648,32 @@ void gcg_pipe_free (gcg_ctx * ctx)
     for (cudaEvent_t e : {q.ev_up, q.ev_emit, q.ev_free}) if (e) cudaEventDestroy (e);
   }
   if (p->h_count) cudaFreeHost (p->h_count);
+  cudaFree (p->d_run);
   if (p->up) cudaStreamDestroy (p->up);
   if (p->down) cudaStreamDestroy (p->down);
   delete p;
   ctx->pipe = nullptr;
 }
 
-static int pipe_reserve (gcg_ctx * ctx, int64_t cap_words)
+// 0 staged, 1 direct (device result + lazy copies), 2 zero copy (kernel stores into the mapped pinned result)
+static int pipe_mode (void)
 {
-  if (ctx->pipe && ctx->pipe->cap_words >= cap_words) return GCG_OK;
+  const char * z = getenv ("GCG_SEARCH_ZEROCOPY"), * d = getenv ("GCG_SEARCH_DIRECT");
+  if (z && atoi (z) == 1) return 2;
+  if (d && atoi (d) == 0) return 0;
+  return 1;
+}
+
+static int pipe_reserve (gcg_ctx * ctx, int64_t cap_words, bool staged)
+{
+  if (ctx->pipe && ctx->pipe->cap_words >= cap_words && (ctx->pipe->staged || !staged)) return GCG_OK;
   GCG_CUDA (cudaStreamSynchronize (ctx->stream));
+  if (ctx->pipe) { cap_words = std::max (cap_words, ctx->pipe->cap_words); staged = staged || ctx->pipe->staged; }
   gcg_pipe_free (ctx);
   gcg_pipe * p = new gcg_pipe ();
   ctx->pipe = p;
   p->cap_words = cap_words;
+  p->staged = staged;
   p->meta_cap = (size_t) 2 << 20;
   const size_t tiles = (size_t) ((cap_words + 31) >> 5);
   if (p->meta_cap < tiles * 4 + (1 << 20)) p->meta_cap = tiles * 4 + (1 << 20);
@@ -1568,14 +1681,17 @@ static int pipe_reserve (gcg_ctx * ctx, int64_t cap_words)
   GCG_CUDA (cudaStreamCreateWithFlags (&p->down, cudaStreamNonBlocking));
   GCG_CUDA (cudaHostAlloc (&p->h_count, PIPE_SLOTS * sizeof (unsigned long long), cudaHostAllocMapped));
   GCG_CUDA (cudaHostGetDevicePointer (&p->hd_count, p->h_count, 0));
+  GCG_CUDA (cudaMalloc (&p->d_run, 2 * sizeof (unsigned long long)));
   for (pipe_slot & q : p->s) {
     GCG_CUDA (cudaHostAlloc (&q.h_packed, (size_t) cap_words * 8, cudaHostAllocDefault));
     GCG_CUDA (cudaHostAlloc (&q.h_meta, p->meta_cap, cudaHostAllocDefault));
     GCG_CUDA (cudaMalloc (&q.d_meta, p->meta_cap));
     GCG_CUDA (cudaMalloc (&q.d_packed, (size_t) (cap_words + 2) * 8));
     GCG_CUDA (cudaMalloc (&q.d_state, (tiles + 1) * 8));
-    GCG_CUDA (cudaMalloc (&q.d_read_off, (p->meta_cap / 12 + 2) * 8));       // a chunk's reads fit its meta block at 12 bytes each
-    GCG_CUDA (cudaMalloc (&q.d_hits, (size_t) cap_words * 32 * sizeof (gcg_hit)));
+    if (staged) {
+      GCG_CUDA (cudaMalloc (&q.d_read_off, (p->meta_cap / 12 + 2) * 8));       // a chunk's reads fit its meta block at 12 bytes each
+      GCG_CUDA (cudaMalloc (&q.d_hits, (size_t) cap_words * 32 * sizeof (gcg_hit)));
+    }
     GCG_CUDA (cudaMemset (q.d_packed, 0, (size_t) (cap_words + 2) * 8));
     for (cudaEvent_t * e : {&q.ev_up, &q.ev_emit, &q.ev_free}) GCG_CUDA (cudaEventCreateWithFlags (e, cudaEventDisableTiming));
   }
@@ -1587,7 +1703,7 @@ extern "C" int gcg_warmup (gcg_ctx * ctx)
   GCG_CHECK (ctx, GCG_EINVAL, "gcg_warmup: ctx == NULL");
   GCG_CUDA (cudaSetDevice (ctx->device));
   int rc = gcg_stage_reserve (ctx);
-  if (!rc) rc = pipe_reserve (ctx, ((int64_t) 8 << 20) / 32);
+  if (!rc) rc = pipe_reserve (ctx, ((int64_t) 8 << 20) / 32, pipe_mode () == 0);
   return rc;
 }
 
@@ -1597,11 +1713,11 @@ struct search_result {
   size_t rec = sizeof (gcg_hit);
   char * buf = nullptr;                              // pinned: gcg_hit[cap] or uint64_t[cap]
   int64_t cap = 0, n = 0;
-  int64_t * read_off = nullptr;                      // compact form: pinned, [n_read + 1], chunk-relative until the end of the call
-  std::vector<std::pair<int64_t, int64_t>> chunk_base;   // (first read, anchors before the chunk)
+  int64_t * read_off = nullptr;                      // compact form: pinned, [n_read + 1]
+  std::vector<std::pair<int64_t, int64_t>> chunk_base;   // staged mode: (first read, anchors before the chunk)
 };
 
-// place the anchors of the chunk in slot `q` behind the ones already placed
+// staged mode: place the anchors of the chunk in slot `q` behind the ones already placed
 static int pipe_download (gcg_ctx * ctx, pipe_slot & q, int slot, search_result & res)
 {
   gcg_pipe * p = ctx->pipe;
@@ -1652,6 +1768,8 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
   }
   int rc = GCG_OK;
   if (fmt && (rc = compact_limits_ok (t, max_len)) != 0) return rc;
+  const int mode = pipe_mode ();
+  const bool zc = mode != 0;                         // anchors land at their final index (direct or zero copy)
   search_result res;
   res.ctx = ctx; res.fmt = fmt; res.rec = anchor_bytes (fmt);
   if (fmt) {
@@ -1663,7 +1781,7 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
     if (fmt) { read_off_fill (res.read_off, n_read, 0); *read_off_out = res.read_off; }
     return GCG_OK;
   }
-  rc = pipe_reserve (ctx, std::max (chunk_words, max_words));
+  rc = pipe_reserve (ctx, std::max (chunk_words, max_words), !zc);
   if (!rc) rc = gcg_table_filter_ensure (ctx, t);
   if (rc) { gcg_free (res.read_off); return rc; }
   gcg_pipe * p = ctx->pipe;
@@ -1676,8 +1794,13 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
 
   // work on ctx->stream enqueued by earlier calls (the table build) precedes the first probe by stream order
   struct chunk_desc { int64_t r0 = 0, r1 = 0, nr = 0, nw = 0, kmers = 0, n_tiles = 0; size_t tseq_off = 0; int slot = 0; };
-  int inflight[PIPE_SLOTS], n_inflight = 0;       // submitted, not yet downloaded, oldest first
-  int64_t c = 0;
+  int inflight[PIPE_SLOTS], n_inflight = 0;       // staged mode: submitted, not yet downloaded, oldest first
+  int64_t c = 0, n_sub = 0;
+  unsigned long long win_lo = 0, win_hi = 0;      // zero copy: window of global anchor indices this pass materialises
+  void * d_out = nullptr;                         // direct: the device result; zero copy: device alias of the pinned result
+  long long * d_roff = nullptr;
+  void * d_res = nullptr; long long * d_res_roff = nullptr;     // direct: device blocks behind d_out / d_roff
+  int64_t copied = 0;                             // direct: anchors already queued for download
   double t_gather = 0, t_wait = 0, t_prepare = 0, t_submit = 0, t_download = 0, t_drain = 0;
   auto now = [] () { return std::chrono::steady_clock::now (); };
   auto ms = [] (std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli> (b - a).count (); };
@@ -1740,7 +1863,7 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
   };
 
   // copy the gathered chunk to the device and enqueue its kernel: probe, ordered anchor index, ONT-side
-  // multiplicity and anchor records in one launch (k45_fused_kernel); the anchor count lands in mapped host memory
+  // multiplicity and anchor records in one launch (k45_fused_kernel)
   auto submit = [&] (const chunk_desc & d) -> int {
     pipe_slot & q = p->s[d.slot];
     const int64_t nr = d.nr, nw = d.nw;
@@ -1752,8 +1875,30 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
     const int64_t * d_woff = (const int64_t *) q.d_meta;
     const int32_t * d_len = (const int32_t *) (q.d_meta + (size_t) (nr + 1) * 8);
     const int32_t * d_tseq = (const int32_t *) (q.d_meta + d.tseq_off);
-    int e = launch_fused (ctx, t, q.d_packed, d_woff, d_len, d_tseq, nr, nw, k, fmt, q.d_hits, 0ULL, ~0ULL, (int32_t) d.r0,
-                          fmt ? q.d_read_off : nullptr, q.d_state, p->hd_count + d.slot);
+    int e;
+    if (zc) {
+      // anchors and read offsets go straight to their final place in the pinned result; the running count
+      // alternates between two device words
+      e = launch_fused (ctx, t, q.d_packed, d_woff, d_len, d_tseq, nr, nw, k, fmt, d_out, win_lo, win_hi, (int32_t) d.r0,
+                        fmt ? d_roff + d.r0 : nullptr, q.d_state, p->d_run + ((n_sub + 1) & 1), p->d_run + (n_sub & 1), true,
+                        mode == 1 ? p->hd_count : nullptr);
+      ++n_sub;
+      if (e) return e;
+      GCG_CUDA (cudaEventRecord (q.ev_free, ctx->stream));         // the slot is free again when its kernel has finished
+      q.busy = true;
+      if (mode == 1) {
+        // whatever earlier launches have completed by now goes down (at least 1 MiB at a time)
+        const int64_t done = std::min<int64_t> ((int64_t) *(volatile unsigned long long *) p->h_count, (int64_t) win_hi);
+        const int64_t from = std::max<int64_t> (copied, (int64_t) win_lo);
+        if (done > from && (size_t) (done - from) * res.rec >= ((size_t) 1 << 20)) {
+          GCG_CUDA (cudaMemcpyAsync (res.buf + (size_t) from * res.rec, (char *) d_res + (size_t) from * res.rec, (size_t) (done - from) * res.rec, cudaMemcpyDeviceToHost, p->down));
+          copied = done;
+        }
+      }
+      return GCG_OK;
+    }
+    e = launch_fused (ctx, t, q.d_packed, d_woff, d_len, d_tseq, nr, nw, k, fmt, q.d_hits, 0ULL, ~0ULL, (int32_t) d.r0,
+                      fmt ? q.d_read_off : nullptr, q.d_state, p->hd_count + d.slot);
     if (e) return e;
     GCG_CUDA (cudaEventRecord (q.ev_emit, ctx->stream));
     GCG_CUDA (cudaStreamWaitEvent (p->down, q.ev_emit, 0));
@@ -1764,62 +1909,127 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
 
   int pipe_lag = 1;                                 // (measured on cfg2: 8 MiB chunks, lag 1: 3.0 ms; 16 MiB, lag 2: 3.35 ms)
   if (const char * e = getenv ("GCG_SEARCH_LAG")) pipe_lag = std::min (PIPE_LAG, std::max (0, atoi (e)));
-  chunk_desc cur_c, next_c;
-  rc = plan (0, cur_c);
-  bool gathering = !rc && cur_c.kmers > 0;
-  if (gathering) start_gather (cur_c);
-  while (!rc) {
-    // the next chunk is planned while this one is gathered, and gathered while this one is copied and probed
-    const bool more = cur_c.r1 < n_read;
-    if (more) {
-      auto t1 = now ();
-      rc = plan (cur_c.r1, next_c);
-      t_prepare += ms (t1, now ());
-    }
-    auto t0 = now ();
-    if (gathering) gcg_workers_wait (pool);
-    t_gather += ms (t0, now ());
-    gathering = false;
-    if (rc) break;
-    if (more && next_c.kmers > 0) { start_gather (next_c); gathering = true; }
-    if (cur_c.kmers > 0) {
-      auto t1 = now ();
-      rc = submit (cur_c);
-      t_submit += ms (t1, now ());
-      if (rc) break;
-      // place the anchors of the chunk submitted PIPE_LAG chunks ago: its count is there by now, so the
-      // host does not stall and the upload stream never runs dry
-      inflight[n_inflight++] = cur_c.slot;
-      if (n_inflight > pipe_lag) {
-        auto t2 = now ();
-        rc = pipe_download (ctx, p->s[inflight[0]], inflight[0], res);
-        t_download += ms (t2, now ());
-        if (rc) break;
-        for (int i = 1; i < n_inflight; ++i) inflight[i - 1] = inflight[i];
-        --n_inflight;
+
+  // one pass over all chunks
+  auto run_pass = [&] () -> int {
+    int prc = GCG_OK;
+    chunk_desc cur_c, next_c;
+    c = 0; n_sub = 0; n_inflight = 0;
+    if (zc) GCG_CUDA (cudaMemsetAsync (p->d_run, 0, 2 * sizeof (unsigned long long), ctx->stream));
+    p->h_count[0] = 0;
+    copied = 0;
+    prc = plan (0, cur_c);
+    bool gathering = !prc && cur_c.kmers > 0;
+    if (gathering) start_gather (cur_c);
+    while (!prc) {
+      // the next chunk is planned while this one is gathered, and gathered while this one is copied and probed
+      const bool more = cur_c.r1 < n_read;
+      if (more) {
+        auto t1 = now ();
+        prc = plan (cur_c.r1, next_c);
+        t_prepare += ms (t1, now ());
       }
+      auto t0 = now ();
+      if (gathering) gcg_workers_wait (pool);
+      t_gather += ms (t0, now ());
+      gathering = false;
+      if (prc) break;
+      if (more && next_c.kmers > 0) { start_gather (next_c); gathering = true; }
+      if (cur_c.kmers > 0) {
+        auto t1 = now ();
+        prc = submit (cur_c);
+        t_submit += ms (t1, now ());
+        if (prc) break;
+        if (!zc) {
+          // place the anchors of the chunk submitted PIPE_LAG chunks ago: its count is there by now
+          inflight[n_inflight++] = cur_c.slot;
+          if (n_inflight > pipe_lag) {
+            auto t2 = now ();
+            prc = pipe_download (ctx, p->s[inflight[0]], inflight[0], res);
+            t_download += ms (t2, now ());
+            if (prc) break;
+            for (int i = 1; i < n_inflight; ++i) inflight[i - 1] = inflight[i];
+            --n_inflight;
+          }
+        }
+      }
+      if (!more) break;
+      cur_c = next_c;
     }
-    if (!more) break;
-    cur_c = next_c;
+    if (gathering) gcg_workers_wait (pool);
+    // ---- drain
+    auto t_d0 = now ();
+    for (int i = 0; i < n_inflight && !prc; ++i) prc = pipe_download (ctx, p->s[inflight[i]], inflight[i], res);
+    if (zc && !prc && n_sub > 0 &&
+        cudaMemcpyAsync (ctx->h_counters + 4, p->d_run + (n_sub & 1), 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_search: count copy failed"); prc = GCG_ECUDA; }
+    if (cudaStreamSynchronize (p->down) != cudaSuccess || cudaStreamSynchronize (ctx->stream) != cudaSuccess) {
+      if (!prc) { gcg_set_error ("gcg_search: %s", cudaGetErrorString (cudaGetLastError ())); prc = GCG_ECUDA; }
+    }
+    t_drain += ms (t_d0, now ());
+    for (pipe_slot & q : p->s) { q.busy = false; q.pending = false; }
+    return prc;
+  };
+
+  if (zc) {
+    int64_t total = 0;
+    win_lo = 0;
+    for (int pass = 0; pass < 2 && !rc; ++pass) {
+      win_hi = (unsigned long long) res.cap;
+      if (mode == 2) {
+        if (cudaHostGetDevicePointer (&d_out, res.buf, 0) != cudaSuccess || (fmt && cudaHostGetDevicePointer ((void **) &d_roff, res.read_off, 0) != cudaSuccess)) {
+          gcg_set_error ("gcg_search: the pinned result is not mapped into the device's address space: %s", cudaGetErrorString (cudaGetLastError ()));
+          rc = GCG_ECUDA;
+          break;
+        }
+      } else {
+        // the device result of this pass (parked blocks of the context: no driver call in the steady state)
+        cudaError_t e = gcg_dmalloc (ctx, &d_res, (size_t) res.cap * res.rec);
+        if (e == cudaSuccess && fmt) e = gcg_dmalloc (ctx, &d_res_roff, (size_t) (n_read + 1) * 8);
+        if (e == cudaSuccess && fmt) e = cudaMemsetAsync (d_res_roff, 0xFF, (size_t) (n_read + 1) * 8, ctx->stream);
+        if (e != cudaSuccess) { gcg_set_error ("gcg_search: device result of %lld anchors: %s", (long long) res.cap, cudaGetErrorString (e)); rc = GCG_ENOMEM; break; }
+        d_out = d_res; d_roff = d_res_roff;
+      }
+      rc = run_pass ();
+      if (rc) break;
+      total = (int64_t) ctx->h_counters[4];
+      if (mode == 1) {
+        // the tail the loop has not queued yet, and the read offsets
+        const int64_t done = std::min<int64_t> (total, res.cap), from = std::max<int64_t> (copied, (int64_t) win_lo);
+        cudaError_t e = cudaSuccess;
+        if (done > from) e = cudaMemcpyAsync (res.buf + (size_t) from * res.rec, (char *) d_res + (size_t) from * res.rec, (size_t) (done - from) * res.rec, cudaMemcpyDeviceToHost, p->down);
+        if (e == cudaSuccess && fmt) e = cudaMemcpyAsync (res.read_off, d_res_roff, (size_t) n_read * 8, cudaMemcpyDeviceToHost, p->down);
+        if (e == cudaSuccess) e = cudaStreamSynchronize (p->down);
+        gcg_dfree (ctx, d_res); gcg_dfree (ctx, d_res_roff);
+        d_res = nullptr; d_res_roff = nullptr;
+        if (e != cudaSuccess) { gcg_set_error ("gcg_search: result download: %s", cudaGetErrorString (e)); rc = GCG_ECUDA; break; }
+      }
+      if (total <= res.cap) break;
+      // denser than estimated: anchors [0, cap) are in place and counted; a result of the right size takes them over
+      // and a second pass over the reads materialises [cap, total) only
+      GCG_CHECK (pass == 0, GCG_ECUDA, "gcg_search: anchor count changed between passes (%lld > %lld)", (long long) total, (long long) res.cap);
+      char * nb = (char *) gcg_pinned_alloc ((size_t) total * res.rec);
+      if (nb == nullptr) { gcg_set_error ("gcg_search: pinned alloc of %lld anchors failed", (long long) total); rc = GCG_ENOMEM; break; }
+      gcg_par_memcpy (ctx, nb, res.buf, (size_t) res.cap * res.rec);
+      gcg_free (res.buf);
+      win_lo = (unsigned long long) res.cap;
+      res.buf = nb; res.cap = total;
+      if (ctx->trace) fprintf (stderr, "[gcg]   search pipeline: result sized for %lld anchors, %lld found: second pass for the tail\n", (long long) win_lo, (long long) total);
+    }
+    if (d_res) gcg_dfree (ctx, d_res);
+    if (d_res_roff) gcg_dfree (ctx, d_res_roff);
+    res.n = total;
+  } else {
+    rc = run_pass ();
   }
-  if (gathering) gcg_workers_wait (pool);
-  // ---- drain, oldest first
-  auto t_d0 = now ();
-  for (int i = 0; i < n_inflight && !rc; ++i) rc = pipe_download (ctx, p->s[inflight[i]], inflight[i], res);
-  if (cudaStreamSynchronize (p->down) != cudaSuccess || cudaStreamSynchronize (ctx->stream) != cudaSuccess) {
-    if (!rc) { gcg_set_error ("gcg_search: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; }
-  }
-  t_drain = ms (t_d0, now ());
-  for (pipe_slot & q : p->s) { q.busy = false; q.pending = false; }
   if (ctx->trace)
-    fprintf (stderr, "[gcg]   search pipeline: %lld chunks, waits for the gather %.3f ms (%d threads), for a free slot %.3f ms; "
-             "host: prepare %.3f submit %.3f download %.3f drain %.3f ms\n",
+    fprintf (stderr, "[gcg]   search pipeline (%s): %lld chunks, waits for the gather %.3f ms (%d threads), for a free slot %.3f ms; "
+             "host: prepare %.3f submit %.3f download %.3f drain %.3f ms\n", mode == 2 ? "zero copy" : mode == 1 ? "direct" : "staged",
              (long long) c, t_gather, ctx->host_threads, t_wait, t_prepare, t_submit, t_download, t_drain);
   gcg_trace_mark (ctx, "search: reads -> anchors (pipelined)");
   if (rc) { gcg_free (res.buf); gcg_free (res.read_off); return rc; }
   p->last_total = res.n;
   if (fmt) {
-    // chunk-relative offsets -> offsets into the whole anchor array
+    // staged mode: chunk-relative offsets -> offsets into the whole anchor array
     for (size_t ci = 0; ci < res.chunk_base.size (); ++ci) {
       const int64_t r0 = res.chunk_base[ci].first, base = res.chunk_base[ci].second;
       const int64_t r1 = ci + 1 < res.chunk_base.size () ? res.chunk_base[ci + 1].first : n_read;

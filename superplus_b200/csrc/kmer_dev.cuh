@@ -3,6 +3,11 @@
 #pragma once
 #include "gcg_internal.cuh"
 
+// build-time switches of the search kernels (A/B variants: scripts/build_variants.sh)
+#ifndef K45_EVICT_LAST
+#define K45_EVICT_LAST 0
+#endif
+
 // =============================================================================================
 // device helpers
 // =============================================================================================
@@ -108,6 +113,26 @@ __device__ __forceinline__ bucket4 ld_bucket (const unsigned long long * p)
   asm volatile ("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
                 : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p));
   return r;
+}
+
+// the same load for the probe loop of the search: the table's key sectors are asked to stay in the L2
+// (evict-last) while the packed reads, the anchor records and the value words stream past them
+__device__ __forceinline__ bucket4 ld_bucket_keep (const unsigned long long * p)
+{
+  bucket4 r;
+#if K45_EVICT_LAST
+  asm volatile ("ld.global.nc.L1::no_allocate.L2::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];"
+                : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p));
+#else
+  asm volatile ("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p));
+#endif
+  return r;
+}
+
+__device__ __forceinline__ void prefetch_l2 (const void * p)
+{
+  asm volatile ("prefetch.global.L2 [%0];" :: "l"(p));
 }
 
 // slot index (0..3) of `key` in the bucket or -1; *kw receives the matching key word
