@@ -155,6 +155,9 @@ void gcg_hits_free (gcg_hits * h);
 int  gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
                  int64_t n_read, int k, gcg_hit ** hits_out, int64_t * n_hit);
 void gcg_free (void * p);
+/* page-locked host memory for a caller's own buffers (inputs of gcg_sw_batch / gcg_swbatch_upload are
+ * copied straight from it, without the staging copy pageable memory needs); release with gcg_free */
+void * gcg_host_alloc (int64_t bytes);
 
 /* Compact anchors — what the shim asks for (superplus_b200/gap_closer/ont.c): ONE 64-bit word per
  * anchor instead of the 16-byte gcg_hit, grouped by read through an offset array, so that the
@@ -173,6 +176,19 @@ int  gcg_search_compact (gcg_ctx * ctx, gcg_table * t, const char * const * read
 /* device-resident form (bench `value`); download with gcg_hits_download_compact (read_off: n + 1 entries) */
 int  gcg_search_seqs_compact (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * reads, int k, gcg_hits ** out);
 int  gcg_hits_download_compact (gcg_ctx * ctx, const gcg_hits * h, uint64_t * anchors, int64_t cap, int64_t * read_off);
+/* N3, opt-in: search + the anchor grouping of map_ont2contigs (ctg_graph.c:600-656) on the device.
+ * The reference cuts every read's anchors, in position order, into runs of consecutive anchors on one contig and
+ * keeps per run the contig, the number of anchors whose strand agrees with the scaffold (ONT_KMER_REV == KMER_REV,
+ * ctg_graph.c:617-623: "FORW") and disagrees ("BACK"), and the first / last anchor of the majority direction
+ * (ont_node_init, ctg_graph.c:93-181).  run_off[r] .. run_off[r+1] are the runs of read r in position order;
+ * first_* / last_* are compact anchor words (0 when the count is 0).  Neither the anchors nor a per-base array reach
+ * the host.  Same limits as gcg_search_compact (GCG_ERANGE beyond them).  Arrays are pinned, release with gcg_free. */
+typedef struct {
+  int32_t tid, n_fwd, n_bwd, pad;
+  uint64_t first_fwd, last_fwd, first_bwd, last_bwd;
+} gcg_run;
+int  gcg_search_runs (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
+                      int64_t n_read, int k, gcg_run ** runs_out, int64_t ** run_off_out, int64_t * n_run, int64_t * n_anchor);
 #define GCG_ANCHOR_POS(a)   ((int32_t) ((a) >> 36))
 #define GCG_ANCHOR_GPOS(a)  ((int64_t) (((a) >> 2) & 0x3FFFFFFFFULL))
 #define GCG_ANCHOR_FLAGS(a) ((uint32_t) ((a) & 3u))

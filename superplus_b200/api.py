@@ -30,7 +30,7 @@ EXPORTS = [
     "gcg_chop_contigs", "gcg_table_build_seqs", "gcg_table_build", "gcg_table_free", "gcg_table_stats",
     "gcg_table_size", "gcg_table_dump", "gcg_table_clone", "gcg_table_merge_ont",
     "gcg_search_seqs", "gcg_hits_count", "gcg_hits_download", "gcg_hits_free", "gcg_search", "gcg_free",
-    "gcg_search_compact", "gcg_search_seqs_compact", "gcg_hits_download_compact", "gcg_selftest_workers",
+    "gcg_search_compact", "gcg_search_seqs_compact", "gcg_hits_download_compact", "gcg_selftest_workers", "gcg_host_alloc",
     "gcg_sw_batch", "gcg_sw_batch_multi", "gcg_swbatch_upload", "gcg_swbatch_align", "gcg_swbatch_download", "gcg_swbatch_cells",
     "gcg_swbatch_path_counts", "gcg_swbatch_free",
     "gcg_kmer_owner", "gcg_seqs_tiles", "gcg_route_plan", "gcg_route_kmers", "gcg_route_keys", "gcg_route_records",
@@ -149,6 +149,8 @@ def load_library(path: str = LIB_PATH):
     L.gcg_hits_free.argtypes = [vp]
     L.gcg_search.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(i64)]
     L.gcg_free.argtypes = [vp]
+    L.gcg_host_alloc.restype = vp
+    L.gcg_host_alloc.argtypes = [i64]
     L.gcg_search_compact.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
     L.gcg_search_seqs_compact.argtypes = [vp, vp, vp, C.c_int, C.POINTER(vp)]
     L.gcg_hits_download_compact.argtypes = [vp, vp, vp, i64, vp]
@@ -686,6 +688,24 @@ def expand_compact(anchors: np.ndarray, read_off: np.ndarray, contig_lens) -> np
     out["tid"] = tid.astype(np.int32)
     out["cpos_flags"] = (((gpos - cbase[tid]) << 2) | (anchors & np.uint64(3)).astype(np.int64)).astype(np.uint32)
     return out
+
+
+class PinnedArray:
+    """numpy view of page-locked host memory from gcg_host_alloc (inputs that cross PCIe without a staging copy)"""
+
+    def __init__(self, shape, dtype=np.uint8):
+        self.L = load_library()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.p = self.L.gcg_host_alloc(max(n, 16))
+        if not self.p:
+            raise GcgError("gcg_host_alloc(%d) failed: %s" % (n, self.L.gcg_last_error().decode()))
+        self.array = np.frombuffer((C.c_char * max(n, 16)).from_address(self.p), dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.p:
+            self.array = None
+            self.L.gcg_free(self.p)
+            self.p = None
 
 
 def split_reads_by_bases(lens, n_share: int):

@@ -284,6 +284,16 @@ void gcg_pinned_trim (void)
   }
 }
 
+// pinned (page-locked, mapped, portable) host memory for a caller's own input / output buffers: copies
+// from and to it go straight over PCIe, without the staging copy pageable memory needs
+extern "C" void * gcg_host_alloc (int64_t bytes)
+{
+  if (bytes < 0) { gcg_set_error ("gcg_host_alloc: negative size"); return nullptr; }
+  void * p = gcg_pinned_alloc ((size_t) bytes);
+  if (!p) gcg_set_error ("gcg_host_alloc: pinning %lld bytes failed", (long long) bytes);
+  return p;
+}
+
 extern "C" void gcg_free (void * p)
 {
   if (!p) return;

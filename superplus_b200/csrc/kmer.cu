@@ -1745,9 +1745,15 @@ static int pipe_download (gcg_ctx * ctx, pipe_slot & q, int slot, search_result 
   return GCG_OK;
 }
 
+// the anchors of a host-buffer search left on the device (gcg_search_runs reduces them there): compact anchors
+// and n_read + 1 filled read offsets, both blocks of the context's cache (gcg_dfree)
+struct search_dev_keep { void * d_anchors = nullptr; long long * d_read_off = nullptr; };
+
 // fmt 0: *hits_out = gcg_hit[*n_hit]; fmt 1: *hits_out = uint64_t[*n_hit] and *read_off_out = int64_t[n_read + 1]
+// keep != NULL (fmt 1 only): the anchors are not downloaded, *hits_out stays NULL
 static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
-                             int64_t n_read, int k, int fmt, void ** hits_out, int64_t * n_hit, int64_t ** read_off_out)
+                             int64_t n_read, int k, int fmt, void ** hits_out, int64_t * n_hit, int64_t ** read_off_out,
+                             search_dev_keep * keep = nullptr)
 {
   GCG_CHECK (ctx && t && hits_out && n_hit && n_read >= 0 && (n_read == 0 || (read_seq && read_len)), GCG_EINVAL, "gcg_search: bad argument");
   GCG_CHECK (k == t->k, GCG_EINVAL, "gcg_search: k=%d but the table was built with k=%d", k, t->k);
@@ -1768,7 +1774,7 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
   }
   int rc = GCG_OK;
   if (fmt && (rc = compact_limits_ok (t, max_len)) != 0) return rc;
-  const int mode = pipe_mode ();
+  const int mode = keep ? 1 : pipe_mode ();
   const bool zc = mode != 0;                         // anchors land at their final index (direct or zero copy)
   search_result res;
   res.ctx = ctx; res.fmt = fmt; res.rec = anchor_bytes (fmt);
@@ -1787,10 +1793,13 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
   gcg_pipe * p = ctx->pipe;
   const int64_t cap_words = std::max (chunk_words, max_words);       // <= p->cap_words
 
-  res.cap = std::max<int64_t> (p->last_total + p->last_total / 8, total_kmers / 16) + 4096;
+  // (10 %-error ONT reads anchor 6.3 % of their 25-mers; an estimate that is too small costs a second pass)
+  res.cap = std::max<int64_t> (p->last_total + p->last_total / 8, total_kmers / 10) + 4096;
   if (const char * e = getenv ("GCG_SEARCH_RES_CAP")) res.cap = std::max<int64_t> (1, atoll (e));     // test hook: force the grow path
-  res.buf = (char *) gcg_pinned_alloc ((size_t) res.cap * res.rec);
-  if (res.buf == nullptr) { gcg_free (res.read_off); gcg_set_error ("gcg_search: pinned alloc of %lld anchors failed", (long long) res.cap); return GCG_ENOMEM; }
+  if (!keep) {
+    res.buf = (char *) gcg_pinned_alloc ((size_t) res.cap * res.rec);
+    if (res.buf == nullptr) { gcg_free (res.read_off); gcg_set_error ("gcg_search: pinned alloc of %lld anchors failed", (long long) res.cap); return GCG_ENOMEM; }
+  }
 
   // work on ctx->stream enqueued by earlier calls (the table build) precedes the first probe by stream order
   struct chunk_desc { int64_t r0 = 0, r1 = 0, nr = 0, nw = 0, kmers = 0, n_tiles = 0; size_t tseq_off = 0; int slot = 0; };
@@ -1886,7 +1895,7 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
       if (e) return e;
       GCG_CUDA (cudaEventRecord (q.ev_free, ctx->stream));         // the slot is free again when its kernel has finished
       q.busy = true;
-      if (mode == 1) {
+      if (mode == 1 && !keep) {
         // whatever earlier launches have completed by now goes down (at least 1 MiB at a time)
         const int64_t done = std::min<int64_t> ((int64_t) *(volatile unsigned long long *) p->h_count, (int64_t) win_hi);
         const int64_t from = std::max<int64_t> (copied, (int64_t) win_lo);
@@ -1983,7 +1992,11 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
         }
       } else {
         // the device result of this pass (parked blocks of the context: no driver call in the steady state)
+        void * d_prev = d_res;                             // (kept anchors of a first pass that overflowed)
+        d_res = nullptr;
         cudaError_t e = gcg_dmalloc (ctx, &d_res, (size_t) res.cap * res.rec);
+        if (e == cudaSuccess && d_prev) e = cudaMemcpyAsync (d_res, d_prev, (size_t) win_lo * res.rec, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (d_prev) gcg_dfree (ctx, d_prev);
         if (e == cudaSuccess && fmt) e = gcg_dmalloc (ctx, &d_res_roff, (size_t) (n_read + 1) * 8);
         if (e == cudaSuccess && fmt) e = cudaMemsetAsync (d_res_roff, 0xFF, (size_t) (n_read + 1) * 8, ctx->stream);
         if (e != cudaSuccess) { gcg_set_error ("gcg_search: device result of %lld anchors: %s", (long long) res.cap, cudaGetErrorString (e)); rc = GCG_ENOMEM; break; }
@@ -1996,14 +2009,20 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
         // the tail the loop has not queued yet, and the read offsets
         const int64_t done = std::min<int64_t> (total, res.cap), from = std::max<int64_t> (copied, (int64_t) win_lo);
         cudaError_t e = cudaSuccess;
-        if (done > from) e = cudaMemcpyAsync (res.buf + (size_t) from * res.rec, (char *) d_res + (size_t) from * res.rec, (size_t) (done - from) * res.rec, cudaMemcpyDeviceToHost, p->down);
+        if (!keep && done > from) e = cudaMemcpyAsync (res.buf + (size_t) from * res.rec, (char *) d_res + (size_t) from * res.rec, (size_t) (done - from) * res.rec, cudaMemcpyDeviceToHost, p->down);
         if (e == cudaSuccess && fmt) e = cudaMemcpyAsync (res.read_off, d_res_roff, (size_t) n_read * 8, cudaMemcpyDeviceToHost, p->down);
         if (e == cudaSuccess) e = cudaStreamSynchronize (p->down);
-        gcg_dfree (ctx, d_res); gcg_dfree (ctx, d_res_roff);
-        d_res = nullptr; d_res_roff = nullptr;
+        if (!keep) { gcg_dfree (ctx, d_res); d_res = nullptr; }
+        if (!keep || total > res.cap) { gcg_dfree (ctx, d_res_roff); d_res_roff = nullptr; }
         if (e != cudaSuccess) { gcg_set_error ("gcg_search: result download: %s", cudaGetErrorString (e)); rc = GCG_ECUDA; break; }
       }
       if (total <= res.cap) break;
+      if (keep) {      // the second pass writes [cap, total) behind the kept anchors [0, cap) in a device result of the right size
+        GCG_CHECK (pass == 0, GCG_ECUDA, "gcg_search: anchor count changed between passes (%lld > %lld)", (long long) total, (long long) res.cap);
+        win_lo = (unsigned long long) res.cap;
+        res.cap = total;
+        continue;
+      }
       // denser than estimated: anchors [0, cap) are in place and counted; a result of the right size takes them over
       // and a second pass over the reads materialises [cap, total) only
       GCG_CHECK (pass == 0, GCG_ECUDA, "gcg_search: anchor count changed between passes (%lld > %lld)", (long long) total, (long long) res.cap);
@@ -2014,6 +2033,13 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
       win_lo = (unsigned long long) res.cap;
       res.buf = nb; res.cap = total;
       if (ctx->trace) fprintf (stderr, "[gcg]   search pipeline: result sized for %lld anchors, %lld found: second pass for the tail\n", (long long) win_lo, (long long) total);
+    }
+    if (keep && !rc) {
+      // filled offsets go back up: the reduction kernels read read_off[r + 1] of every read
+      read_off_fill (res.read_off, n_read, total);
+      if (cudaMemcpyAsync (d_res_roff, res.read_off, (size_t) (n_read + 1) * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+          cudaStreamSynchronize (ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_search: read offsets upload failed"); rc = GCG_ECUDA; }
+      else { keep->d_anchors = d_res; keep->d_read_off = d_res_roff; d_res = nullptr; d_res_roff = nullptr; }
     }
     if (d_res) gcg_dfree (ctx, d_res);
     if (d_res_roff) gcg_dfree (ctx, d_res_roff);
@@ -2038,10 +2064,43 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
     read_off_fill (res.read_off, n_read, res.n);
     *read_off_out = res.read_off;
   }
+  if (keep) { *n_hit = res.n; return GCG_OK; }
   if (res.n == 0) { gcg_free (res.buf); return GCG_OK; }
   *hits_out = res.buf;
   *n_hit = res.n;
   return GCG_OK;
+}
+
+int gcg_runs_from_anchors (gcg_ctx * ctx, const gcg_table * t, const void * d_anchors, const long long * d_read_off, int64_t n_read,
+                           gcg_run ** runs_out, int64_t ** run_off_out, int64_t * n_run);      // runs.cu
+
+// N3: search + the anchor grouping of map_ont2contigs (ctg_graph.c:600-656) on the device; neither the anchors
+// nor anything per ONT base reaches the host
+extern "C" int gcg_search_runs (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
+                                int64_t n_read, int k, gcg_run ** runs_out, int64_t ** run_off_out, int64_t * n_run, int64_t * n_anchor)
+{
+  GCG_CHECK (runs_out && run_off_out && n_run && n_anchor, GCG_EINVAL, "gcg_search_runs: bad argument");
+  *runs_out = nullptr; *run_off_out = nullptr; *n_run = 0; *n_anchor = 0;
+  search_dev_keep keep;
+  void * none = nullptr;
+  int64_t * read_off = nullptr;
+  int rc = search_host_impl (ctx, t, read_seq, read_len, n_read, k, 1, &none, n_anchor, &read_off, &keep);
+  if (rc) return rc;
+  if (keep.d_read_off == nullptr) {
+    // nothing was searched (no read holds a k-mer): every read has zero runs
+    int64_t * ro = (int64_t *) gcg_pinned_alloc ((size_t) (n_read + 1) * 8);
+    gcg_free (read_off);
+    GCG_CHECK (ro != nullptr, GCG_ENOMEM, "gcg_search_runs: pinned alloc failed");
+    memset (ro, 0, (size_t) (n_read + 1) * 8);
+    *run_off_out = ro;
+    return GCG_OK;
+  }
+  gcg_free (read_off);
+  gcg_trace_mark (ctx, nullptr);
+  rc = gcg_runs_from_anchors (ctx, t, keep.d_anchors, keep.d_read_off, n_read, runs_out, run_off_out, n_run);
+  gcg_trace_mark (ctx, "search: anchors -> runs");
+  gcg_dfree (ctx, keep.d_anchors); gcg_dfree (ctx, keep.d_read_off);
+  return rc;
 }
 
 extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,

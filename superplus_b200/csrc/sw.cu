@@ -710,6 +710,13 @@ extern "C" int gcg_swbatch_path_counts (const gcg_swbatch * b, int64_t counts[2]
 
 static int h2d_chunked (gcg_ctx * ctx, void * dst, const void * src, size_t bytes)
 {
+  // a source in pinned memory (gcg_host_alloc, cudaHostAlloc, cudaHostRegister) goes over PCIe as it is
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes (&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+    GCG_CUDA (cudaMemcpyAsync (dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return GCG_OK;
+  }
+  cudaGetLastError ();
   // pageable source -> pinned ring -> device, double buffered
   int rc = gcg_stage_reserve (ctx);
   if (rc) return rc;
