@@ -302,6 +302,45 @@ def run_ref_kmer(fa: str, fq: str, k: int, prefix: str, n_thread: int = 4, dump:
     return info, hits, table, ctgk
 
 
+def runs_from_hits(hits, n_read: int, contig_lens):
+    """Restates the anchor grouping of map_ont2contigs (ctg_graph.c:600-656) + what ont_node_init keeps of a run
+    (ctg_graph.c:93-181) on the oracle's anchors (dict of arrays read, pos, tid, cpos, krev, orev in (read,pos)
+    order): a run = maximal stretch of consecutive anchors of one read on one contig; FORW anchors are those whose
+    ONT strand flag equals the contig occurrence's (ctg_graph.c:617-618).  Returns (runs, run_off) with runs a dict of
+    arrays: tid, n_fwd, n_bwd and first_fwd / last_fwd / first_bwd / last_bwd as compact anchor words
+    (pos << 36 | (contig_base[tid] + cpos) << 2 | orev << 1 | krev; 0 when the direction has no anchor)."""
+    read = np.asarray(hits["read"], dtype=np.int64)
+    tid = np.asarray(hits["tid"], dtype=np.int64)
+    n = len(read)
+    cbase = np.concatenate([[0], np.cumsum(np.asarray(contig_lens, dtype=np.int64))])
+    word = ((np.asarray(hits["pos"], dtype=np.uint64) << np.uint64(36)) |
+            ((cbase[tid] + np.asarray(hits["cpos"], dtype=np.int64)).astype(np.uint64) << np.uint64(2)) |
+            (np.asarray(hits["orev"], dtype=np.uint64) << np.uint64(1)) | np.asarray(hits["krev"], dtype=np.uint64))
+    fwd = np.asarray(hits["orev"]) == np.asarray(hits["krev"])
+    start = np.ones(n, dtype=bool)
+    if n > 1:
+        start[1:] = (read[1:] != read[:-1]) | (tid[1:] != tid[:-1])
+    rid = np.cumsum(start) - 1                      # run index of every anchor
+    n_run = int(rid[-1]) + 1 if n else 0
+    out = {k_: np.zeros(n_run, dtype=np.uint64) for k_ in ("first_fwd", "last_fwd", "first_bwd", "last_bwd")}
+    out["tid"] = tid[start].astype(np.int32)
+    out["n_fwd"] = np.bincount(rid[fwd], minlength=n_run).astype(np.int32) if n else np.zeros(0, np.int32)
+    out["n_bwd"] = np.bincount(rid[~fwd], minlength=n_run).astype(np.int32) if n else np.zeros(0, np.int32)
+    idx = np.arange(n)
+    for sel, a, b in ((fwd, "first_fwd", "last_fwd"), (~fwd, "first_bwd", "last_bwd")):
+        r_, i_ = rid[sel], idx[sel]
+        if len(r_):
+            first = np.full(n_run, n, dtype=np.int64); np.minimum.at(first, r_, i_)
+            last = np.full(n_run, -1, dtype=np.int64); np.maximum.at(last, r_, i_)
+            have = last >= 0
+            out[a][have] = word[first[have]]
+            out[b][have] = word[last[have]]
+    run_read = read[start]
+    run_off = np.zeros(n_read + 1, dtype=np.int64)
+    np.cumsum(np.bincount(run_read, minlength=n_read), out=run_off[1:])
+    return out, run_off
+
+
 def read_hsid(prefix: str) -> np.ndarray:
     """<prefix>.hsid.bin of a dump level 2 harness run: kmer_t.hs_id per contig position"""
     return np.fromfile(prefix + ".hsid.bin", dtype=np.int32)

@@ -20,6 +20,8 @@ SW_ASIS, SW_FIXED = 0, 1
 HIT_DTYPE = np.dtype([("read", "<i4"), ("pos", "<i4"), ("tid", "<i4"), ("cpos_flags", "<u4")])
 SWRES_DTYPE = np.dtype([("score", "<i4"), ("alignment_offset", "<i4"), ("has_softclip", "<i4"),
                         ("bt_tidx", "<i4"), ("bt_qidx", "<i4"), ("n_cigar", "<i4"), ("cigar_off", "<i8")])
+RUN_DTYPE = np.dtype([("tid", "<i4"), ("n_fwd", "<i4"), ("n_bwd", "<i4"), ("pad", "<i4"),
+                      ("first_fwd", "<u8"), ("last_fwd", "<u8"), ("first_bwd", "<u8"), ("last_bwd", "<u8")])
 KMER_DTYPE = np.dtype([("kseq", "<u8"), ("hs_id", "<i4"), ("tid", "<i4"), ("pos", "<i4"), ("flag", "<u2"), ("kmer_len", "<i2")])
 
 EXPORTS = [
@@ -30,7 +32,7 @@ EXPORTS = [
     "gcg_chop_contigs", "gcg_table_build_seqs", "gcg_table_build", "gcg_table_free", "gcg_table_stats",
     "gcg_table_size", "gcg_table_dump", "gcg_table_clone", "gcg_table_merge_ont",
     "gcg_search_seqs", "gcg_hits_count", "gcg_hits_download", "gcg_hits_free", "gcg_search", "gcg_free",
-    "gcg_search_compact", "gcg_search_seqs_compact", "gcg_hits_download_compact", "gcg_selftest_workers", "gcg_host_alloc",
+    "gcg_search_compact", "gcg_search_seqs_compact", "gcg_hits_download_compact", "gcg_selftest_workers", "gcg_host_alloc", "gcg_search_runs",
     "gcg_sw_batch", "gcg_sw_batch_multi", "gcg_swbatch_upload", "gcg_swbatch_align", "gcg_swbatch_download", "gcg_swbatch_cells",
     "gcg_swbatch_path_counts", "gcg_swbatch_free",
     "gcg_kmer_owner", "gcg_seqs_tiles", "gcg_route_plan", "gcg_route_kmers", "gcg_route_keys", "gcg_route_records",
@@ -149,6 +151,7 @@ def load_library(path: str = LIB_PATH):
     L.gcg_hits_free.argtypes = [vp]
     L.gcg_search.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(i64)]
     L.gcg_free.argtypes = [vp]
+    L.gcg_search_runs.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
     L.gcg_host_alloc.restype = vp
     L.gcg_host_alloc.argtypes = [i64]
     L.gcg_search_compact.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
@@ -372,6 +375,22 @@ class Context:
             self.L.gcg_free(ap)
             self.L.gcg_free(rp)
         return anchors, read_off
+
+    def search_runs(self, table: "KmerTable", reads):
+        """N3: search + anchor grouping on the device (gcg_search_runs) -> (runs RUN_DTYPE[n_run], run_off int64[n_read + 1], n_anchor)"""
+        arrs = [np.ascontiguousarray(s, dtype=np.uint8) for s in reads]
+        n = len(arrs)
+        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+        lens = np.array([len(a) for a in arrs], dtype=np.int32)
+        rp, op, nr, na = C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
+        self._chk(self.L.gcg_search_runs(self.h, table.h, C.cast(ptrs, C.c_void_p), lens.ctypes.data, n, table.k, C.byref(rp), C.byref(op), C.byref(nr), C.byref(na)))
+        try:
+            runs = np.frombuffer((C.c_char * (nr.value * RUN_DTYPE.itemsize)).from_address(rp.value), dtype=RUN_DTYPE).copy() if nr.value else np.zeros(0, RUN_DTYPE)
+            run_off = np.frombuffer((C.c_char * ((n + 1) * 8)).from_address(op.value), dtype=np.int64).copy()
+        finally:
+            self.L.gcg_free(rp)
+            self.L.gcg_free(op)
+        return runs, run_off, int(na.value)
 
     def search_host(self, table: "KmerTable", reads) -> np.ndarray:
         """the shim-facing call: host pointers in, pinned host anchors out (gcg_search)"""

@@ -88,6 +88,19 @@ gcg_bridge_warmup (void)
   }
 }
 
+int
+gcg_bridge_runs_mode (void)
+{
+  const char * e = getenv ("GC_RUNS");
+  return e != NULL && atoi (e) != 0;
+}
+
+gcg_bridge_t *
+gcg_bridge_peek (void)
+{
+  return &g_bridge;
+}
+
 gcg_bridge_t *
 gcg_bridge (void)
 {
@@ -150,6 +163,8 @@ gcg_bridge_shutdown (void)
   g_warm_started = 0;
   gcg_bridge_drop_table ();
   gcg_bridge_drop_contigs ();
+  free (g_bridge.runs); free (g_bridge.run_off); free (g_bridge.run_kmers);
+  g_bridge.runs = NULL; g_bridge.run_off = NULL; g_bridge.run_kmers = NULL; g_bridge.n_run = 0;
   for (i = 0; i < GCG_BRIDGE_MAX_DEV; ++i)
     if (g_bridge.ctxs[i]) { gcg_destroy (g_bridge.ctxs[i]); g_bridge.ctxs[i] = NULL; }
   g_bridge.ctx = NULL;

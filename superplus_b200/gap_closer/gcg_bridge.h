@@ -16,6 +16,15 @@ typedef struct {
   int kmer_len;
   int n_thread;
   int searched_k;         /* k-mer length of the first search_kmers_on_ont_reads (0 = none yet) */
+  /* GC_RUNS=1 (opt-in, SURVEY 8f rows N2 + N3): the device reduces every read's anchors to the run records
+   * map_ont2contigs needs (ctg_graph.c:600-656); runs[run_off[r] .. run_off[r+1]) belong to read r.  The two boundary
+   * anchors of a run are materialised as okmers[2q], okmers[2q+1] of the read (q = index of the run in the read) with
+   * their kmer_t records in run_kmers[]; neither the dense okmers[] nor ctg->kmers[] is ever written. */
+  int runs_mode;
+  gcg_run * runs;
+  int64_t * run_off;
+  int64_t n_run;
+  struct kmer_s * run_kmers;
   /* GC_DEVICES=0,1,... (or "all"): the ONT reads are sharded by batch over these GPUs, every one
    * holding a replica of the table (replicated layout).  ctxs[0] == ctx, replicas[0] == NULL. */
   int n_dev;
@@ -24,6 +33,8 @@ typedef struct {
   gcg_table * replicas[GCG_BRIDGE_MAX_DEV];
 } gcg_bridge_t;
 
+int gcg_bridge_runs_mode (void);             /* GC_RUNS set and not 0 (no device is opened by asking) */
+gcg_bridge_t * gcg_bridge_peek (void);       /* the handle as it is: no context is created */
 gcg_bridge_t * gcg_bridge (void);            /* lazily creates the context; aborts via err_mesg on failure */
 void gcg_bridge_warmup (void);               /* start opening the device on a helper thread (joined by gcg_bridge) */
 void gcg_bridge_drop_table (void);             /* the table and its replicas */

@@ -58,7 +58,12 @@ chop_contig_seqs2kmers (mp_t(ctg) * seqs, int n_thread, int kmer_len)
   gcg_bridge_drop_table ();
   gcg_bridge_drop_contigs ();
   GCG_CK (gcg_seqs_upload (br->ctx, ptrs, lens, n, &br->contigs));
-  GCG_CK (gcg_chop_contigs (br->ctx, br->contigs, kmer_len, n_thread > 0 ? n_thread : 1, outs, n_kmer));
+  if (gcg_bridge_runs_mode ()) {
+    /* GC_RUNS: nothing reads ctg->kmers[] — the anchors the consumers look at carry their own kmer_t
+     * records (ont.c of this directory) — so the 24 bytes per contig base stay untouched zero pages */
+    for (i = 0; i < n; ++i) n_kmer[i] = lens[i] >= kmer_len ? lens[i] - kmer_len + 1 : 0;
+  } else
+    GCG_CK (gcg_chop_contigs (br->ctx, br->contigs, kmer_len, n_thread > 0 ? n_thread : 1, outs, n_kmer));
   for (i = 0; i < n; ++i)
     mp_at (ctg, seqs, i)->n_kmer += n_kmer[i];   /* the reference appends from the cleared n_kmer (kmer.c:79,103) */
 

@@ -34,6 +34,7 @@
 #include "ont.h"
 #include "rseq.h"
 #include "utils.h"
+#include "kmer.h"
 #include "gcg_bridge.h"
 
 /* ------------------------------------------------------------------ back-fill ---------- */
@@ -133,8 +134,51 @@ rebuild_segs (mp_t(okseq) * okseqs, int64_t r0, int64_t r1, const gcg_hit * hits
   }
 }
 
+/* ------------------------------------------------------------------ GC_RUNS (N2 + N3) -- */
+/* canonical k-mer of the contig occurrence an anchor points at (kmer.c:73-117 restated for ONE position): forward
+ * word from the k bases, its reverse complement by kseq1_fast_reverse_comp's definition (kseq1.h:37-46) */
+static uint64_t
+canon_at (const char * s, int k, int * rev)
+{
+  uint64_t fwd = 0, rc = 0;
+  int i;
+  for (i = 0; i < k; ++i) {
+    uint64_t b = ((unsigned char) s[i] >> 1) & 3;                  /* bio.h:24 */
+    fwd = (fwd << 2) | b;
+    rc |= (b ^ 2) << (2 * i);                                       /* bio.h:22: complement = code ^ 2 */
+  }
+  *rev = !(fwd < rc);                                               /* kmer.c:86 */
+  return *rev ? rc : fwd;
+}
+
+static void
+okmer_from_anchor (ont_kmer_t * ok, kmer_t * km, uint64_t w, mp_t(ctg) * ctgs, const int64_t * cbase, int64_t n_ctg, int kmer_len, int n_thread)
+{
+  const int64_t gpos = GCG_ANCHOR_GPOS (w);
+  int64_t lo = 0, hi = n_ctg;
+  int rev;
+  ctg_t * c;
+  while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (cbase[mid] <= gpos) lo = mid; else hi = mid; }
+  c = mp_at (ctg, ctgs, lo);
+  km->kseq = canon_at (c->seq->s + (gpos - cbase[lo]), kmer_len, &rev);
+  km->hs_id = (int32_t) (kseq_crc32 (&km->kseq) % (uint32_t) n_thread);     /* kmer.c:88 */
+  km->tid = (int32_t) lo;
+  km->pos = (int32_t) (gpos - cbase[lo]);
+  km->flag = (w & 1u) ? KMER_REV : 0;
+  km->kmer_len = (int16_t) kmer_len;
+  ok->kmer = km;
+  ok->ont_pos = GCG_ANCHOR_POS (w);
+  ok->hs_id = (int16_t) km->hs_id;
+  ok->flag = (w & 2u) ? ONT_KMER_REV : 0;
+  if (((w >> 1) ^ w) & 1u) ok->flag |= ONT_SCAF_REV;                /* ctg_graph.c:619-623: set on BACK anchors */
+}
+
+struct share_s;
+static void runs_to_okmers (gcg_bridge_t * br, struct share_s * share, int n_dev, mp_t(okseq) * okseqs, mp_t(ctg) * ctgs,
+    const int64_t * cbase, int64_t n_ctg, int kmer_len);
+
 /* one share of the read batch on one device */
-typedef struct {
+typedef struct share_s {
   gcg_ctx * ctx;
   gcg_table * table;
   const char ** ptrs;
@@ -145,6 +189,9 @@ typedef struct {
   int64_t * read_off;
   gcg_hit * hits;           /* ... or the 16-byte form */
   int64_t n_hit;
+  gcg_run * runs;           /* GC_RUNS: run records instead of anchors */
+  int64_t * run_off;
+  int64_t n_run;
   int rc;
   char err[600];
 } share_t;
@@ -153,6 +200,11 @@ static void *
 share_core (void * data)
 {
   share_t * s = (share_t *) data;
+  if (gcg_bridge_runs_mode ()) {
+    s->rc = gcg_search_runs (s->ctx, s->table, s->ptrs + s->r0, s->lens + s->r0, s->r1 - s->r0, s->kmer_len, &s->runs, &s->run_off, &s->n_run, &s->n_hit);
+    if (s->rc != 0) snprintf (s->err, sizeof s->err, "%s", gcg_last_error ());
+    return NULL;
+  }
   s->rc = getenv ("GC_ANCHORS16") ? GCG_ERANGE
         : gcg_search_compact (s->ctx, s->table, s->ptrs + s->r0, s->lens + s->r0, s->r1 - s->r0, s->kmer_len, &s->anchors, &s->read_off, &s->n_hit);
   if (s->rc == GCG_ERANGE) {        /* beyond the compact form's bit budget (or GC_ANCHORS16 set: A/B of the two forms) */
@@ -161,6 +213,50 @@ share_core (void * data)
   }
   if (s->rc != 0) snprintf (s->err, sizeof s->err, "%s", gcg_last_error ());   /* the message is thread local */
   return NULL;
+}
+
+/* joins the shares' run records in the bridge and gives every read its 2 x (number of runs) boundary anchors:
+ * okmers[2q] / okmers[2q+1] = first / last anchor of run q's majority direction (what ont_node_init keeps of a run,
+ * ctg_graph.c:93-181); a run without a 20-fold majority keeps zeroed entries (its node is deleted) */
+static void
+runs_to_okmers (gcg_bridge_t * br, share_t * share, int n_dev, mp_t(okseq) * okseqs, mp_t(ctg) * ctgs,
+    const int64_t * cbase, int64_t n_ctg, int kmer_len)
+{
+  int d;
+  int64_t r, q, n_reads = mp_cnt (okseqs), n_run = 0, at = 0;
+  const int n_thread = br->n_thread > 0 ? br->n_thread : 1;
+  for (d = 0; d < n_dev; ++d) n_run += share[d].n_run;
+  free (br->runs); free (br->run_off); free (br->run_kmers);
+  br->runs = (gcg_run *) ckalloc (n_run + 1, sizeof (gcg_run));
+  br->run_off = (int64_t *) ckalloc (n_reads + 1, sizeof (int64_t));
+  br->run_kmers = (kmer_t *) ckalloc (2 * n_run + 1, sizeof (kmer_t));
+  br->n_run = n_run;
+  for (d = 0; d < n_dev; ++d) {
+    if (share[d].n_run > 0) memcpy (br->runs + at, share[d].runs, share[d].n_run * sizeof (gcg_run));
+    for (r = share[d].r0; r < share[d].r1; ++r) br->run_off[r] = at + share[d].run_off[r - share[d].r0];
+    at += share[d].n_run;
+  }
+  br->run_off[n_reads] = n_run;
+  for (r = 0; r < n_reads; ++r) {
+    okseq_t * okseq = mp_at (okseq, okseqs, r);
+    const int64_t q0 = br->run_off[r], nq = br->run_off[r + 1] - q0;
+    mp_resize (okmer, okseq->okmers, 2 * nq);
+    okseq->okmers->n = 2 * nq;
+    for (q = 0; q < nq; ++q) {
+      const gcg_run * run = br->runs + q0 + q;
+      ont_kmer_t * ok = okseq->okmers->pool + 2 * q;
+      kmer_t * km = br->run_kmers + 2 * (q0 + q);
+      memset (ok, 0, 2 * sizeof (ont_kmer_t));
+      if (run->n_fwd > 20 * run->n_bwd) {
+        okmer_from_anchor (ok, km, run->first_fwd, ctgs, cbase, n_ctg, kmer_len, n_thread);
+        okmer_from_anchor (ok + 1, km + 1, run->last_fwd, ctgs, cbase, n_ctg, kmer_len, n_thread);
+      } else if (run->n_bwd > 20 * run->n_fwd) {
+        okmer_from_anchor (ok, km, run->first_bwd, ctgs, cbase, n_ctg, kmer_len, n_thread);
+        okmer_from_anchor (ok + 1, km + 1, run->last_bwd, ctgs, cbase, n_ctg, kmer_len, n_thread);
+      }
+    }
+  }
+  br->runs_mode = 1;
 }
 
 int
@@ -247,6 +343,18 @@ search_kmers_on_ont_reads (mp_t(rs) * ont_seqs, mp_t(ctg) * ctg_seqs,
       fprintf (stderr, "[gcg] device %d: reads [%ld, %ld), %ld anchors\n", br->devs[d], (long) share[d].r0, (long) share[d].r1, (long) share[d].n_hit);
   printf ("\n  chop and search ont kmers cost: %lds\n", time (NULL) - mod_tbeg);
 
+  if (gcg_bridge_runs_mode ()) {
+    /* GC_RUNS: the device has reduced the anchors to run records; materialise the two boundary anchors of every run */
+    time (&mod_tbeg);
+    runs_to_okmers (br, share, n_dev, okseqs, ctg_seqs, cbase, n_ctg, kmer_len);
+    printf ("\n  re-hash ont kmers cost: %lds\n", time (NULL) - mod_tbeg);
+    printf ("\n  find un-ankored positions on onts costs: %lds\n", 0L);      /* (segments are not kept in this mode: one k-mer length) */
+    for (d = 0; d < n_dev; ++d) { gcg_free (share[d].runs); gcg_free (share[d].run_off); }
+    free (ptrs); free (lens); free (cbase);
+    printf ("\n  search ONT kmers total cost: %lds\n", time (NULL) - time_beg);
+    return 0;
+  }
+
   /* back-fill okmers[] (the reference's REHASH phase re-pointed the same entries) */
   time (&mod_tbeg);
   if (nt > n_hit / 4096 + 1) nt = (int) (n_hit / 4096 + 1);
@@ -301,6 +409,7 @@ typedef struct {
   int64_t * cursor;
   mp_t(rs) * ont_seqs;
   mp_t(okseq) * okseqs;
+  int runs_mode;
 } init_arg_t;
 
 static void *
@@ -318,8 +427,12 @@ init_core (void * data)
     okseq = a->okseqs->pool + i;
     okseq->seq = r;
     okseq->ont_id = (int) i;
-    mp_resize (okmer, okseq->okmers, r->l);      /* zero-filled: okmer->kmer == NULL means no anchor */
-    okseq->okmers->n = r->l;
+    if (a->runs_mode) {                          /* GC_RUNS: the read gets two entries per run after the search */
+      okseq->okmers->n = 0;
+    } else {
+      mp_resize (okmer, okseq->okmers, r->l);    /* zero-filled: okmer->kmer == NULL means no anchor */
+      okseq->okmers->n = r->l;
+    }
     mp_clear (oseg, okseq->segs, NULL);
     seg = mp_alloc (oseg, okseq->segs);
     seg->beg = 0;
@@ -345,7 +458,7 @@ ont_kseqs_init (mp_t(rs) * ont_seqs, mp_t(okseq) * okseqs)
 
   nt = ncpu > 16 ? 16 : (ncpu < 1 ? 1 : (int) ncpu);
   if (nt > n) nt = n > 0 ? (int) n : 1;
-  arg.cursor = &cursor; arg.ont_seqs = ont_seqs; arg.okseqs = okseqs;
+  arg.cursor = &cursor; arg.ont_seqs = ont_seqs; arg.okseqs = okseqs; arg.runs_mode = gcg_bridge_runs_mode ();
   pids = (pthread_t *) ckalloc (nt, sizeof (pthread_t));
   for (i = 0; i < nt; ++i)
     ckpthread_create (pids + i, NULL, init_core, (void *) &arg);

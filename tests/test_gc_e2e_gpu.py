@@ -196,3 +196,26 @@ def test_shim_harness_dumps_equal_the_reference_harness(cfg, k, n_thread, env):
         for ext in ("hits.bin", "ctgk.bin", "hsid.bin", "segs.bin"):
             a, b = open(os.path.join(tmp, "ref." + ext), "rb").read(), open(os.path.join(tmp, "shim." + ext), "rb").read()
             assert len(a) > 0 and a == b, ext
+
+
+@pytest.mark.parametrize("cfg,env", [("tiny", {}), ("small", {}), ("repeats", {}), ("cfg1", {}), ("cfg5s", {}), ("cfg2", {}),
+                                     ("cfg1", {"GC_DEVICES": "0,0"}), ("repeats", {"GC_DEVICES": "0,0,0"})])
+def test_runs_mode_writes_the_same_files(cfg, env):
+    """GC_RUNS=1 (opt-in, SURVEY 8f rows N2 + N3): anchors are reduced to run records on the device, the dense
+    okmers[] (16 bytes per ONT base) and ctg->kmers[] (24 per contig base) are never written, map_ont2contigs builds its
+    nodes from the records and hands them to the reference's own add_ont_link2graph — files and statistics must be
+    the reference's, byte for byte"""
+    assert os.path.exists(GC), "gc_b200 was not built (python -c 'import __graft_entry__ as g; g.build()')"
+    with tempfile.TemporaryDirectory() as tmp:
+        fa, fq, _ = synth.materialise(cfg, tmp)
+        wd = os.path.join(tmp, "run")
+        os.makedirs(wd)
+        r = subprocess.run([GC, fa, fq, "8", "out"], cwd=wd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900,
+                           env=dict(os.environ, GC_RUNS="1", **env))
+        assert r.returncode == 0, r.stderr.decode()[-2000:]
+        stats = [int(x) for x in re.findall(r"(?:total|unique) kmer count: (\d+)", r.stdout.decode())]
+        g = GOLD[cfg]
+        assert stats == g["stats"]
+        assert md5(os.path.join(wd, "gc_fix1.fa")) == g["fa"]
+        assert md5(os.path.join(wd, "ont_link.txt")) == g["link"]
+        assert md5(os.path.join(wd, "valid_ont_link.txt")) == g["valid"]

@@ -266,3 +266,56 @@ def test_two_pass_search_still_agrees(ctx, oracle):
         assert r.returncode == 0, r.stderr.decode()[-2000:]
         outs.append(r.stdout.decode().strip())
     assert outs[0] == outs[1] and outs[0]
+
+
+def _check_runs(ctx, oracle, contigs, reads, k):
+    h = oracle.table_build(contigs, k)
+    o_hits, o_ont = oracle.search(h, reads, k)
+    o_st = oracle.table_stats(h)
+    oracle.table_free(h)
+    from oracle import oracle as orc
+    want, want_off = orc.runs_from_hits(o_hits, len(reads), [len(c) for c in contigs])
+    cs = ctx.upload(contigs)
+    t = ctx.table_build(cs, k)
+    runs, run_off, n_anchor = ctx.search_runs(t, reads)
+    assert n_anchor == len(o_hits["read"]) and t.stats() == o_st + o_ont
+    assert np.array_equal(run_off, want_off)
+    for f in ("tid", "n_fwd", "n_bwd", "first_fwd", "last_fwd", "first_bwd", "last_bwd"):
+        assert np.array_equal(runs[f], want[f]), f
+    t.free(); cs.free()
+    return len(runs)
+
+
+def test_run_records_match_the_grouping_of_map_ont2contigs(ctx, oracle, monkeypatch):
+    """N3 (gcg_search_runs): per read, maximal stretches of consecutive anchors on one contig with the counts of
+    the two strand directions and the first / last anchor of each — against the oracle's restatement of
+    ctg_graph.c:600-656 on the oracle's anchors.  Repeat-rich input (runs of one anchor, direction flips),
+    reads without anchors, empty reads, many tiny chunks, an anchor estimate that forces the second pass."""
+    e = np.zeros(0, np.uint8)
+    for name, k in (("tiny", 25), ("repeats", 17), ("repeats", 25), ("small", 31)):
+        inp = synth.make_config(name)
+        reads = [e, inp.reads[0][:12]] + inp.reads + [e]
+        assert _check_runs(ctx, oracle, inp.contigs, reads, k) > 0
+    inp = synth.make_config("repeats")
+    monkeypatch.setenv("GCG_SEARCH_CHUNK_BYTES", "4096")
+    _check_runs(ctx, oracle, inp.contigs, inp.reads, 17)
+    monkeypatch.setenv("GCG_SEARCH_RES_CAP", "1000")
+    _check_runs(ctx, oracle, inp.contigs, inp.reads, 17)
+    monkeypatch.delenv("GCG_SEARCH_CHUNK_BYTES")
+    _check_runs(ctx, oracle, inp.contigs, inp.reads, 21)
+    monkeypatch.delenv("GCG_SEARCH_RES_CAP")
+    # chimeric reads: pieces of distant contigs glued together, some reverse-complemented -> several runs per read
+    rng = np.random.default_rng(5)
+    inp = synth.make_config("small")
+    g = inp.genome
+    chim = []
+    for _ in range(40):
+        parts = []
+        for _p in range(int(rng.integers(2, 6))):
+            a = int(rng.integers(0, len(g) - 3000)); l = int(rng.integers(200, 3000))
+            seg = g[a:a + l]
+            parts.append(synth.revcomp(seg) if rng.random() < 0.5 else seg)
+        chim.append(np.concatenate(parts))
+    assert _check_runs(ctx, oracle, inp.contigs, chim + [e], 25) > len(chim)
+    _check_runs(ctx, oracle, inp.contigs, [e, e], 25)
+    _check_runs(ctx, oracle, inp.contigs, [], 25)

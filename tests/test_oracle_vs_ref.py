@@ -81,3 +81,76 @@ def test_blizzard_against_reference(oracle):
         for ht in (0, 1, 2, 3):
             assert oracle.blizzard(w, ht) == R.blizzard(w, ht)
     R.close()
+
+
+def test_run_grouping_against_the_reference_link_file(oracle):
+    """oracle.runs_from_hits restates map_ont2contigs' grouping (ctg_graph.c:600-656) and ont_node_init's 20-fold
+    majority rule (ctg_graph.c:93-181).  The reference prints every node of a read with more than one node into
+    ont_link.txt as "tid <tab> n_okmers <tab> F|B" (add_ont_link2graph, ctg_graph.c:246-257): compare those lines
+    for every read whose runs all pass the majority rule (a deleted node prints stale fields of an earlier read)."""
+    for name in ("repeats", "small"):
+        inp = synth.make_config(name)
+        with tempfile.TemporaryDirectory() as tmp:
+            fa, fq = os.path.join(tmp, "r.fa"), os.path.join(tmp, "r.fq")
+            synth.write_fasta(fa, inp.scaffold); synth.write_fastq(fq, inp.reads)
+            orc.run_ref_gc(fa, fq, os.path.join(tmp, "wd"), n_thread=2)
+            text = open(os.path.join(tmp, "wd", "ont_link.txt")).read()
+        ref = {}
+        cur = None
+        for line in text.splitlines():
+            if line.startswith("> ONT"):
+                cur = int(line.split()[2]); ref[cur] = []
+            elif line.strip():
+                a, b, c = line.split("\t")
+                ref[cur].append((int(a), int(b), c))
+        h = oracle.table_build(inp.contigs, 25)
+        hits, _ = oracle.search(h, inp.reads, 25)
+        oracle.table_free(h)
+        runs, off = orc.runs_from_hits(hits, len(inp.reads), [len(c) for c in inp.contigs])
+        checked = 0
+        for r in range(len(inp.reads)):
+            q0, q1 = int(off[r]), int(off[r + 1])
+            assert (q1 > q0) == (r in ref), r                    # "> ONT r" is printed for every read with an anchor
+            if q1 - q0 < 2:
+                assert r not in ref or ref[r] == []
+                continue
+            nf, nb = runs["n_fwd"][q0:q1].astype(int), runs["n_bwd"][q0:q1].astype(int)
+            ok_f, ok_b = nf > 20 * nb, nb > 20 * nf
+            if not np.all(ok_f | ok_b):
+                continue
+            want = [(int(runs["tid"][q]), int(nf[q - q0] if ok_f[q - q0] else nb[q - q0]), "F" if ok_f[q - q0] else "B") for q in range(q0, q1)]
+            assert ref[r] == want, (name, r)
+            checked += 1
+        assert checked > 0
+
+
+def test_run_grouping_against_a_literal_loop(oracle):
+    """the vectorised restatement against a loop that follows ctg_graph.c:600-656 statement by statement"""
+    inp = synth.make_config("repeats")
+    h = oracle.table_build(inp.contigs, 17)
+    hits, _ = oracle.search(h, inp.reads, 17)
+    oracle.table_free(h)
+    runs, off = orc.runs_from_hits(hits, len(inp.reads), [len(c) for c in inp.contigs])
+    cb = np.concatenate([[0], np.cumsum([len(c) for c in inp.contigs])])
+    res = []
+    for r in range(len(inp.reads)):
+        cur = None
+        for i in np.flatnonzero(hits["read"] == r):
+            w = (int(hits["pos"][i]) << 36) | ((int(cb[hits["tid"][i]]) + int(hits["cpos"][i])) << 2) | (int(hits["orev"][i]) << 1) | int(hits["krev"][i])
+            if cur is None or cur[0] != int(hits["tid"][i]):
+                if cur:
+                    res.append(tuple(cur))
+                cur = [int(hits["tid"][i]), 0, 0, 0, 0, 0, 0]
+            if hits["orev"][i] == hits["krev"][i]:
+                if cur[1] == 0:
+                    cur[3] = w
+                cur[4] = w; cur[1] += 1
+            else:
+                if cur[2] == 0:
+                    cur[5] = w
+                cur[6] = w; cur[2] += 1
+        if cur:
+            res.append(tuple(cur))
+    got = [(int(runs["tid"][i]), int(runs["n_fwd"][i]), int(runs["n_bwd"][i]), int(runs["first_fwd"][i]), int(runs["last_fwd"][i]),
+            int(runs["first_bwd"][i]), int(runs["last_bwd"][i])) for i in range(len(runs["tid"]))]
+    assert got == res and len(res) > 100
