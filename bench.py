@@ -358,6 +358,85 @@ def run_ours(args, rank, local_rank, world):
                               "kernel_ms_per_step": {k_: v[0] / args.steps for k_, v in sorted(pprof.items())}}
             idx.free()
 
+    # ---- BASELINE configs[3] at FULL size (default at N = 8, --cfg4 on|off elsewhere): k = 31 table of a 100 Mb genome
+    #      hash-partitioned over the ranks, 40x ONT in total (40 / N per rank), direct exchange over NVLink peer memory.
+    #      Checked against the CPU oracle, not against ourselves: the all-reduced scaffold statistics against the
+    #      oracle's table over the whole genome, and the anchors of a sample of rank 0's reads against oracle.search.
+    cfg4 = None
+    if (world == 8 and args.cfg4 != "off") or args.cfg4 == "on":
+        from superplus_b200 import dist as gdist
+        K4 = 31
+        c4 = synth.CONFIGS["cfg4"]
+        G4 = int(args.cfg4_genome or c4["genome_len"])
+        rng4 = np.random.Generator(np.random.PCG64(c4["seed"]))
+        genome4 = synth.random_genome(G4, rng4)
+        reads4 = synth.make_reads(genome4, c4["coverage"] / world, c4["seed"] + 1 + 1000 * rank)
+        n4 = sum(max(0, len(r) - K4 + 1) for r in reads4)
+        ops4 = gdist.DeviceOps(ctx, local_rank)
+        comm4 = gdist.TorchComm(ops4.device) if dist is not None else gdist.ThreadComm(gdist.ThreadGroup(1), 0, ops4.device, ops4.sync)
+        cs4, rs4 = ctx.upload([genome4]), ctx.upload(reads4)
+        sample = reads4[:48]
+        ss4 = ctx.upload(sample)
+        idx4 = gdist.PartitionedKmerIndex(ops4, comm4, K4, exchange="direct")
+        idx4.build(cs4)
+        got = idx4.search(ss4)                                  # the sample's anchors (collective: every rank searches its own sample)
+        st_after_sample = idx4.stats()
+        idx4.build(cs4)                                         # fresh ONT-side counts for the timed searches
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(stream)
+        idx4.build(cs4)
+        b1.record(stream)
+        barrier()
+        build4_ms = allmax(b0.elapsed_time(b1))
+        for _ in range(2):
+            h4 = idx4.search(rs4, keep_on_device=True)
+        ctx.prof_reset()
+        sent0 = comm4.bytes_sent
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record(stream)
+        sampler.mark()
+        c4_steps = 3
+        for _ in range(c4_steps):
+            h4 = idx4.search(rs4, keep_on_device=True)
+        q1.record(stream)
+        barrier()
+        search4_ms = allmax(q0.elapsed_time(q1)) / c4_steps
+        prof4 = ctx.prof_report()
+        tot4, hits4 = allsum(float(n4)), allsum(float(h4))
+        nv4 = allsum(float(comm4.bytes_sent - sent0)) / c4_steps
+        routed4 = allsum(float(idx4.n_routed)) / max(1.0, allsum(float(idx4.n_positions)))
+        check = {"kind": "not run (oracle library missing)"}
+        if rank == 0:
+            try:
+                from oracle import oracle as orc
+                O = orc.Oracle()
+                t_or = time.perf_counter()
+                h_or = O.table_build([genome4], K4)
+                want_hits, _ = O.search(h_or, sample, K4)
+                want_st = O.table_stats(h_or)
+                O.table_free(h_or)
+                ok_st = tuple(st_after_sample[:2]) == tuple(want_st)
+                ok_hits = (len(got) == len(want_hits["read"]) and np.array_equal(got["read"], want_hits["read"].astype(np.int32)) and
+                           np.array_equal(got["pos"], want_hits["pos"]) and np.array_equal(got["tid"], want_hits["tid"]) and
+                           np.array_equal(got["cpos_flags"] >> 2, want_hits["cpos"].astype(np.uint32)) and
+                           np.array_equal(got["cpos_flags"] & 1, want_hits["krev"]) and np.array_equal((got["cpos_flags"] >> 1) & 1, want_hits["orev"]))
+                check = {"kind": "CPU oracle (oracle/gc_oracle.c) over the whole genome", "scaffold_stats_equal": bool(ok_st), "oracle_stats": list(want_st),
+                         "sample_reads": len(sample), "sample_anchors": int(len(got)), "sample_anchors_equal": bool(ok_hits), "oracle_s": time.perf_counter() - t_or}
+                assert ok_st and ok_hits, "partitioned cfg4 table disagrees with the CPU oracle: %r" % (check,)
+            except ImportError:
+                pass
+        cfg4 = {"metric": "kmers_per_s", "value": tot4 / (search4_ms * 1e-3), "unit": "k-mers/s", "ms_per_search": search4_ms, "build_ms": build4_ms,
+                "config": {"workload": "BASELINE configs[3]: %d Mb synthetic genome, k=31, %.0fx ONT in total (%.2fx = %d reads per GPU), contig table hash-partitioned over %d GPU(s), direct exchange over NVLink peer memory" %
+                           (G4 // 1_000_000, c4["coverage"], c4["coverage"] / world, len(reads4), world),
+                           "ont_kmers_total": int(tot4), "anchors_total": int(hits4), "stats": list(idx4.stats())},
+                "nvlink_bytes_per_search": nv4, "routed_fraction": routed4, "check": check,
+                "kernel_ms_per_search": {k_: v[0] / c4_steps for k_, v in sorted(prof4.items())}}
+        idx4.free()
+        cs4.free(); rs4.free(); ss4.free()
+        del genome4, reads4
+
     # ---- timed: SW steps, fixed traceback (headline) and the as-shipped traceback beside it
     sw_launches = 0
     sw_timed = {}
@@ -450,6 +529,31 @@ def run_ours(args, rank, local_rank, world):
     e2e_kmer_s = allmax(time.perf_counter() - t0) / e2e_steps
     assert e2e_hits == n_hit and e2e_st == st, "e2e and device-resident paths disagree"
 
+    # the same step through the N3 entry point (GC_RUNS mode of the shim): the anchors are reduced on the device to the
+    # run records map_ont2contigs needs, so the device -> host stream is a few hundred kilobytes instead of 8 bytes per anchor
+    def e2e_runs():
+        h = C.c_void_p()
+        ctx._chk(ctx.L.gcg_table_build(ctx.h, C.cast(cptrs, C.c_void_p), clens.ctypes.data, len(carrs), K, C.byref(h)))
+        tab = api.KmerTable(ctx, h, K)
+        rp, op, nr, na = C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
+        ctx._chk(ctx.L.gcg_search_runs(ctx.h, tab.h, C.cast(rptrs, C.c_void_p), rlens.ctypes.data, len(arrs), K, C.byref(rp), C.byref(op), C.byref(nr), C.byref(na)))
+        ro = np.frombuffer((C.c_char * ((len(arrs) + 1) * 8)).from_address(op.value), dtype=np.int64)
+        assert int(ro[-1]) == nr.value
+        del ro
+        ctx.L.gcg_free(rp); ctx.L.gcg_free(op)
+        s4 = tab.stats()
+        tab.free()
+        return na.value, nr.value, s4
+
+    e2e_runs()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r_hits, r_runs, r_st = e2e_runs()
+    barrier()
+    e2e_runs_s = allmax(time.perf_counter() - t0) / e2e_steps
+    assert r_hits == n_hit and r_st == st, "run-record and anchor paths disagree"
+
     sw_paths = list(swb.path_counts())
     swb.free()                                     # the resident batch holds up to 64 GB of trace scratch: give it back first
     sw_e2e_pairs = sw_pairs                         # the same batch as the device-resident leg, from host buffers
@@ -528,6 +632,9 @@ def run_ours(args, rank, local_rank, world):
                 "d2h_bytes_per_step": int(n_hit * 8 + 8 * (len(reads) + 1) + 32), "ms_per_step": e2e_kmer_s * 1e3,
                 "host_threads_per_rank": host_threads, "host_cores": os.cpu_count(),
                 "api": "gcg_table_build + gcg_search_compact (host pointers in, pinned 8-byte anchors + per-read offsets out) + gcg_table_stats"},
+        "e2e_runs": {"value": tot_ont_kmers / e2e_runs_s, "unit": "k-mers/s", "ms_per_step": e2e_runs_s * 1e3, "runs_per_gpu": int(r_runs),
+                     "d2h_bytes_per_step": int(r_runs * 48 + 16 * (len(reads) + 1) + 32),
+                     "api": "gcg_table_build + gcg_search_runs (N3, opt-in GC_RUNS mode of the shim: anchors reduced on the device to the run records of map_ont2contigs, ctg_graph.c:600-656) + gcg_table_stats"},
         "gpu_launches": int(kmer_launches + sw_launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k45_fused_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
@@ -553,6 +660,8 @@ def run_ours(args, rank, local_rank, world):
                                           "peak": peak_gbs, "unit": "GB/s", "note": "trace spill, 0.5 byte per cell"},
                             "kernel_ms_per_step": {k_: v[0] / args.steps for k_, v in sorted(sprof.items())}}},
     }
+    if cfg4 is not None:
+        line["partitioned_cfg4"] = cfg4
     if hbm_leg is not None:
         hbm_leg.update({"bound": "hbm", "peak": peak_gbs, "unit": "GB/s", "frac": hbm_leg["achieved"] / peak_gbs, "peak_source": peak_src})
         line["roofline_hbm_table"] = hbm_leg
@@ -598,6 +707,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sw-pairs", type=int, default=47360, help="pairs per GPU per step of the cfg3 leg (16 items per resident warp)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cfg4", default="auto", choices=["auto", "on", "off"], help="BASELINE configs[3] at full size on the partitioned table (auto: at 8 GPUs)")
+    ap.add_argument("--cfg4-genome", type=int, default=0, help="genome length of that leg (default: 100 Mb, the config's)")
     ap.add_argument("--no-hbm-table", action="store_true", help="skip the second k-mer roofline leg (100 Mb table beyond the L2, N=1 only)")
     ap.add_argument("--hbm-coverage", type=float, default=2.0, help="ONT coverage of the 100 Mb genome in that leg")
     ap.add_argument("--partitioned", action="store_true", help="also time the hash-partitioned table at N=1 (always timed at N>1)")

@@ -168,6 +168,7 @@ k4_probe_tile (k4_smem & sm, const unsigned long long * __restrict__ vals, const
     int32_t L = __ldg (len + s);
     p0 = (int32_t) ((w - __ldg (woff + s)) << 5);
     sq = (int32_t) s;
+    GCG_DEV_ASSERT (s >= 0 && s < n_seq && p0 >= 0 && (p0 < L || L == 0) && __ldg (woff + s) <= w && w < __ldg (woff + s + 1));
     nvalid = L - k + 1 - p0;
     nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
     pk = __ldg (packed + w);
@@ -242,6 +243,7 @@ k4_probe_tile (k4_smem & sm, const unsigned long long * __restrict__ vals, const
 #pragma unroll
       for (int it = 0; it < 5; ++it) { int mid = (lo + hi) >> 1; if (sm.excl[wid][mid] <= h) lo = mid; else hi = mid; }
       const int j = __fns (sm.pend[wid][lo], 0, (int) (h - sm.excl[wid][lo]) + 1);
+      GCG_DEV_ASSERT (lo >= 0 && lo < 32 && j >= 0 && j < 32 && sm.excl[wid][lo] <= h && h < sm.excl[wid][lo + 1]);
       const int64_t ww = (tile << 5) + lo;
       bool fw;
       unsigned long long kw, key = key_at (__ldg (packed + ww), __ldg (packed + ww + 1), j, k, &fw);
@@ -367,6 +369,7 @@ chain_lookback (unsigned long long * __restrict__ state, const int64_t idx, cons
     for (;;) {
       const int64_t at = j - lane;                    // lane 0 looks at the nearest predecessor
       const unsigned long long st = at >= 0 ? ld_state (state + at) : (SCANST_INC | base0);   // before element 0: what earlier launches emitted
+      GCG_DEV_ASSERT (at < idx);
       const uint32_t inc = __ballot_sync (0xffffffffu, (st & SCANST_INC) != 0);
       const uint32_t none = __ballot_sync (0xffffffffu, (st & (SCANST_INC | SCANST_AGG)) == 0);
       const int f = inc ? __ffs (inc) - 1 : 32;       // nearest element with a known inclusive prefix
@@ -379,6 +382,7 @@ chain_lookback (unsigned long long * __restrict__ state, const int64_t idx, cons
       j -= 32;
     }
   }
+  GCG_DEV_ASSERT (base >= base0 && base + total <= SCANST_VAL);
   if (lane == 0) st_state (state + idx, SCANST_INC | (base + total));
   return base;
 }
@@ -446,7 +450,8 @@ k45_fused_kernel (const k45f_args A)
     base = chain_lookback (A.state, tile, total, lane, base0);
     if (lane == 0 && tile == n_tiles - 1) *A.total_out = base + total;
 #endif
-    if (A.read_off != nullptr && w < A.n_words && p0 == 0) A.read_off[sq] = (long long) (base + (x - c));
+    GCG_DEV_ASSERT (tile < n_tiles || mymask == 0);
+    if (A.read_off != nullptr && w < A.n_words && p0 == 0) { GCG_DEV_ASSERT (sq >= 0 && sq < A.n_seq); A.read_off[sq] = (long long) (base + (x - c)); }
     if (total == 0) continue;
 #if K45F_DIAG == 2
     continue;                                          // (diagnostic build: probe + scan only — NO anchors, timing only)
@@ -467,6 +472,7 @@ k45_fused_kernel (const k45f_args A)
 #pragma unroll
       for (int it = 0; it < 5; ++it) { int mid = (lo + hi) >> 1; if (sm.excl[wid][mid] <= h) lo = mid; else hi = mid; }
       const int j = __fns (s_mask[wid][lo], 0, (int) (h - sm.excl[wid][lo]) + 1);
+      GCG_DEV_ASSERT (lo >= 0 && lo < 32 && j >= 0 && j < 32 && ((s_mask[wid][lo] >> j) & 1u) && sm.excl[wid][lo] <= h && h < sm.excl[wid][lo + 1]);
       bool fw;
       unsigned long long kw;
       const unsigned long long key = key_at (s_pk[wid][lo], s_pk[wid][lo + 1], j, k, &fw);
@@ -475,6 +481,8 @@ k45_fused_kernel (const k45f_args A)
       const int f = bucket_find (q, key, &kw);
       const unsigned long long slot = f >= 0 ? 4ULL * b + (unsigned) f
                                              : table_lookup (A.keys, A.n_bucket, b, q, key, hs & 3u, &kw);   // walks on to the overflow buckets
+      GCG_DEV_ASSERT (slot != ~0ULL && slot < 4ULL * A.n_bucket && (kw & GCG_KEY_MASK) == key && !(kw & GCG_KEY_MULTI));   // the mask bit said: present, once
+      GCG_DEV_ASSERT (g >= base0 && g < A.win_hi);
       // one atomic both records the anchor (ONT-side multiplicity, ont.c:245) and returns (tid, pos, flag)
 #if K45F_DIAG == 1
       const unsigned long long v = slot;               // (diagnostic build: no value access — WRONG results, timing only)

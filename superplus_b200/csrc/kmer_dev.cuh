@@ -7,6 +7,19 @@
 #ifndef K45_EVICT_LAST
 #define K45_EVICT_LAST 0
 #endif
+// GCG_CHECKED=1: bounds and invariant checks inside the kernels (index ranges of every scattered store and of the
+// chained scan, monotonic prefixes, slot ranges); a violation prints its location and traps.  compute-sanitizer is not
+// available on the GPU pool this was developed on (profiles/r02_sanitizer_refused.log), so the GPU test-suite is also run
+// against this build (scripts/build_variants.sh checked "-DGCG_CHECKED=1"; profiles/r02_checked_build.log).
+#ifndef GCG_CHECKED
+#define GCG_CHECKED 0
+#endif
+#if GCG_CHECKED
+#include <stdio.h>
+#define GCG_DEV_ASSERT(c) do { if (!(c)) { printf ("GCG_CHECKED violation: %s  (%s:%d, block %d thread %d)\n", #c, __FILE__, __LINE__, (int) blockIdx.x, (int) threadIdx.x); __trap (); } } while (0)
+#else
+#define GCG_DEV_ASSERT(c) do { } while (0)
+#endif
 
 // =============================================================================================
 // device helpers
@@ -174,6 +187,7 @@ __device__ __forceinline__ unsigned long long table_lookup (const unsigned long 
                                                            uint32_t b, bucket4 q, unsigned long long key, uint32_t fp, unsigned long long * kw)
 {
   for (;;) {
+    GCG_DEV_ASSERT (b < n_bucket);
     int f = bucket_find (q, key, kw);
     if (f >= 0) return 4ULL * b + f;
     if (!bucket_ovf (q, fp)) return ~0ULL;           // no key of this fingerprint ever left the bucket: absent
@@ -210,6 +224,7 @@ __device__ __forceinline__ void table_insert (unsigned long long * __restrict__ 
   const uint32_t hsh = kmer_hash32 (key - 1ULL), fp = hsh & 3u;
   uint32_t b = __umulhi (hsh, n_bucket);
   for (;;) {
+    GCG_DEV_ASSERT (b < n_bucket);
     unsigned long long * slot = keys + 4ULL * b;
     const bucket4 q = ld_bucket_cg (slot);
     unsigned long long cur[4] = {q.a, q.b, q.c, q.d};

@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include "gcg_internal.cuh"
+#include "kmer_dev.cuh"
 
 struct run_acc {
   int32_t tid, n_fwd, n_bwd;
@@ -46,6 +47,7 @@ runs_kernel (const unsigned long long * __restrict__ anchors, const long long * 
   const int64_t wstride = (int64_t) gridDim.x * (blockDim.x >> 5);
   for (int64_t r = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_read; r += wstride) {
     const long long beg = read_off[r], end = read_off[r + 1];
+    GCG_DEV_ASSERT (beg >= 0 && end >= beg && end <= read_off[n_read]);
     run_acc acc;                                    // the open run (replicated in every lane)
     acc.tid = -1; acc.n_fwd = acc.n_bwd = 0; acc.ff = acc.lf = acc.fb = acc.lb = 0;
     uint32_t n_runs = 0;
@@ -56,6 +58,7 @@ runs_kernel (const unsigned long long * __restrict__ anchors, const long long * 
         gcg_run g;
         g.tid = acc.tid; g.n_fwd = acc.n_fwd; g.n_bwd = acc.n_bwd; g.pad = 0;
         g.first_fwd = acc.ff; g.last_fwd = acc.lf; g.first_bwd = acc.fb; g.last_bwd = acc.lb;
+        GCG_DEV_ASSERT (acc.tid < n_ctg && acc.n_fwd + acc.n_bwd > 0 && (r + 1 == n_read || run_base[r] + n_runs < run_base[r + 1]));
         dst[n_runs] = g;
       }
       ++n_runs;

@@ -85,6 +85,15 @@ class TorchComm:
     def barrier(self):
         self.dist.barrier()
 
+    def stream_barrier(self):
+        """a barrier in STREAM order, without a host round trip: a one-element all-reduce enqueued on the current
+        stream (the library's, see DeviceOps.stream).  Kernels queued behind it on any rank start only after every
+        rank's kernels queued before it have finished — a kernel's stores into a peer's window are complete when
+        the kernel is, and a rank joins the all-reduce only then."""
+        if getattr(self, "_flag", None) is None:
+            self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.dist.all_reduce(self._flag)
+
     def all_gather(self, t: torch.Tensor):
         """-> list of every rank's tensor (same shape everywhere)"""
         out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
@@ -133,6 +142,9 @@ class ThreadComm:
     def _done(self):
         self.sync()
         self.g.barrier.wait()
+
+    def stream_barrier(self):
+        self._done()
 
     def exchange_counts(self, counts: np.ndarray) -> np.ndarray:
         allc = self._publish(np.array(counts, dtype=np.int64))
@@ -409,16 +421,13 @@ class PartitionedKmerIndex:
         with self._phase("search.route+store"):
             # my run inside owner d's key window starts behind the runs of the lower ranks
             ops.route_keys_direct(route, self.q_refs, [int(M[:me, d].sum()) for d in range(world)])
-            ops.sync()
-            comm.barrier()                                  # every key window is complete
+            comm.stream_barrier()                           # every key window is complete (stream order: the host does not wait)
         with self._phase("search.lookup+store"):
             # the answers of requester r go where r's collect pass expects owner `me`: behind the lower owners
             ops.lookup_direct(self.table, self.qwin, M[:, me], self.a_refs, [int(M[r, :me].sum()) for r in range(world)])
-            ops.sync()
-            comm.barrier()                                  # every answer window is complete
+            comm.stream_barrier()                           # every answer window is complete
         with self._phase("search.collect"):
-            h = ops.collect_window(route, self.awin)
-            ops.sync()
+            h = ops.collect_window(route, self.awin)        # (returns with the anchor count: the round's one wait besides the counts)
         comm.bytes_sent += 8 * (int(M[me].sum()) - int(M[me, me])) + 8 * (int(M[:, me].sum()) - int(M[me, me]))
         route.free()
         return h
