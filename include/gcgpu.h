@@ -173,6 +173,13 @@ void * gcg_host_alloc (int64_t bytes);
  * Both arrays are library-owned pinned memory, released with gcg_free. */
 int  gcg_search_compact (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
                          int64_t n_read, int k, uint64_t ** anchors_out, int64_t ** read_off_out, int64_t * n_anchor);
+/* The same searches on reads the caller has ALREADY 2-bit packed (the FASTQ loader of
+ * superplus_b200/gap_closer packs every read while it copies its bases, so the search never re-reads the ASCII):
+ * `packed` holds the words gcg_host_pack_2bit writes, read i at words [woff[i], woff[i] + (read_len[i] + 31) / 32).
+ * Words in page-locked memory (gcg_host_alloc) whose reads follow each other without gaps go over PCIe from where
+ * they lie — no host pass; anything else is copied into the pinned ring first (a quarter of the ASCII bytes). */
+int  gcg_search_compact_packed (gcg_ctx * ctx, gcg_table * t, const uint64_t * packed, const int64_t * woff, const int32_t * read_len,
+                                int64_t n_read, int k, uint64_t ** anchors_out, int64_t ** read_off_out, int64_t * n_anchor);
 /* device-resident form (bench `value`); download with gcg_hits_download_compact (read_off: n + 1 entries) */
 int  gcg_search_seqs_compact (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * reads, int k, gcg_hits ** out);
 int  gcg_hits_download_compact (gcg_ctx * ctx, const gcg_hits * h, uint64_t * anchors, int64_t cap, int64_t * read_off);
@@ -189,6 +196,8 @@ typedef struct {
 } gcg_run;
 int  gcg_search_runs (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
                       int64_t n_read, int k, gcg_run ** runs_out, int64_t ** run_off_out, int64_t * n_run, int64_t * n_anchor);
+int  gcg_search_runs_packed (gcg_ctx * ctx, gcg_table * t, const uint64_t * packed, const int64_t * woff, const int32_t * read_len,
+                             int64_t n_read, int k, gcg_run ** runs_out, int64_t ** run_off_out, int64_t * n_run, int64_t * n_anchor);
 #define GCG_ANCHOR_POS(a)   ((int32_t) ((a) >> 36))
 #define GCG_ANCHOR_GPOS(a)  ((int64_t) (((a) >> 2) & 0x3FFFFFFFFULL))
 #define GCG_ANCHOR_FLAGS(a) ((uint32_t) ((a) & 3u))

@@ -112,7 +112,7 @@ def launch_list(path, fh):
     rows = list(csv.DictReader(io.StringIO("".join(txt))))
     agg, n = collections.OrderedDict(), collections.Counter()
     for r in rows:
-        k = r["Kernel Name"].split("(")[0]
+        k = r["Kernel Name"].split("(")[0].replace("void ", "")
         agg[k] = agg.get(k, 0.0) + float(r["Metric Value"]) / 1e3
         n[k] += 1
     tot = sum(agg.values()) or 1
@@ -123,7 +123,7 @@ def launch_list(path, fh):
         fh.write("  %-28s %8d %12.1f %10.1f %7.1f%%\n" % (k, n[k], v, v / n[k], 100 * v / tot))
     kmer = {k: v for k, v in agg.items() if not k.startswith("sw_") and "ubench" not in k}
     kt = sum(kmer.values()) or 1
-    fh.write("k-mer step only (k1/k23/k45/scan/emit/k6):\n")
+    fh.write("k-mer step only (k1 / k23 / k45 / k6; runs_* belong to the e2e_runs leg):\n")
     for k, v in sorted(kmer.items(), key=lambda kv: -kv[1]):
         fh.write("  %-28s %7.1f%%   avg %8.1f us\n" % (k, 100 * v / kt, v / n[k]))
     fh.write("\n")

@@ -42,7 +42,20 @@ hits = ctx.search_host(tb, inp.reads)
 print("e2e host search (16-byte anchors) %.3fs hits %d" % (time.time() - t0, len(hits)))
 for it in range(3):
     tb2 = ctx.table_build(cs, k)
+    ctx.prof_reset()
     t0 = time.time()
     a, ro = ctx.search_host_compact(tb2, inp.reads)
-    print("e2e host search (compact anchors) %.4fs hits %d" % (time.time() - t0, len(a)))
+    print("e2e host search (compact anchors) %.4fs hits %d" % (time.time() - t0, len(a)), {n_: (round(v[0], 3), v[1]) for n_, v in ctx.prof_report().items()})
+    tb2.free()
+words, woff, lens, keep = api.Context.pack_reads(inp.reads, pinned=True)
+import ctypes as C
+for it in range(3):
+    tb2 = ctx.table_build(cs, k)
+    ctx.prof_reset()
+    ap, rp, na = C.c_void_p(), C.c_void_p(), C.c_int64()
+    t0 = time.time()
+    ctx._chk(ctx.L.gcg_search_compact_packed(ctx.h, tb2.h, words.ctypes.data, woff.ctypes.data, lens.ctypes.data, len(lens), k, C.byref(ap), C.byref(rp), C.byref(na)))
+    dt = time.time() - t0
+    ctx.L.gcg_free(ap); ctx.L.gcg_free(rp)
+    print("e2e packed search %.4fs hits %d" % (dt, na.value), {n_: (round(v[0], 3), v[1]) for n_, v in ctx.prof_report().items()})
     tb2.free()

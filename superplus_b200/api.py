@@ -32,7 +32,7 @@ EXPORTS = [
     "gcg_chop_contigs", "gcg_table_build_seqs", "gcg_table_build", "gcg_table_free", "gcg_table_stats",
     "gcg_table_size", "gcg_table_dump", "gcg_table_clone", "gcg_table_merge_ont",
     "gcg_search_seqs", "gcg_hits_count", "gcg_hits_download", "gcg_hits_free", "gcg_search", "gcg_free",
-    "gcg_search_compact", "gcg_search_seqs_compact", "gcg_hits_download_compact", "gcg_selftest_workers", "gcg_host_alloc", "gcg_search_runs",
+    "gcg_search_compact", "gcg_search_seqs_compact", "gcg_hits_download_compact", "gcg_selftest_workers", "gcg_host_alloc", "gcg_search_runs", "gcg_search_compact_packed", "gcg_search_runs_packed",
     "gcg_sw_batch", "gcg_sw_batch_multi", "gcg_swbatch_upload", "gcg_swbatch_align", "gcg_swbatch_download", "gcg_swbatch_cells",
     "gcg_swbatch_path_counts", "gcg_swbatch_free",
     "gcg_kmer_owner", "gcg_seqs_tiles", "gcg_route_plan", "gcg_route_kmers", "gcg_route_keys", "gcg_route_records",
@@ -152,6 +152,8 @@ def load_library(path: str = LIB_PATH):
     L.gcg_search.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(i64)]
     L.gcg_free.argtypes = [vp]
     L.gcg_search_runs.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
+    L.gcg_search_compact_packed.argtypes = [vp, vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
+    L.gcg_search_runs_packed.argtypes = [vp, vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
     L.gcg_host_alloc.restype = vp
     L.gcg_host_alloc.argtypes = [i64]
     L.gcg_search_compact.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
@@ -391,6 +393,35 @@ class Context:
             self.L.gcg_free(rp)
             self.L.gcg_free(op)
         return runs, run_off, int(na.value)
+
+    @staticmethod
+    def pack_reads(reads, pinned: bool = False, gap_words: int = 0):
+        """what a loader that packs on ingest leaves behind: (words, woff int64[n + 1], lens int32[n], keepalive);
+        `gap_words` unused words between consecutive reads (the reads are then not one run)"""
+        lens = np.array([len(r) for r in reads], dtype=np.int32)
+        nw = (lens.astype(np.int64) + 31) // 32
+        woff = np.zeros(len(reads) + 1, dtype=np.int64)
+        np.cumsum(nw + gap_words, out=woff[1:])
+        total = int(woff[-1]) + 2
+        keep = PinnedArray((total,), np.uint64) if pinned else None
+        words = keep.array if pinned else np.zeros(total, dtype=np.uint64)
+        for i, r in enumerate(reads):
+            if len(r):
+                words[int(woff[i]):int(woff[i]) + int(nw[i])] = host_pack_2bit(np.ascontiguousarray(r, dtype=np.uint8).tobytes())
+        return words, woff, lens, keep
+
+    def search_host_compact_packed(self, table: "KmerTable", words, woff, lens):
+        """gcg_search_compact_packed: reads already 2-bit packed by the caller"""
+        n = len(lens)
+        ap, rp, na = C.c_void_p(), C.c_void_p(), C.c_int64()
+        self._chk(self.L.gcg_search_compact_packed(self.h, table.h, words.ctypes.data, woff.ctypes.data, lens.ctypes.data, n, table.k, C.byref(ap), C.byref(rp), C.byref(na)))
+        try:
+            anchors = np.frombuffer((C.c_char * (na.value * 8)).from_address(ap.value), dtype=np.uint64).copy() if na.value else np.zeros(0, np.uint64)
+            read_off = np.frombuffer((C.c_char * ((n + 1) * 8)).from_address(rp.value), dtype=np.int64).copy()
+        finally:
+            self.L.gcg_free(ap)
+            self.L.gcg_free(rp)
+        return anchors, read_off
 
     def search_host(self, table: "KmerTable", reads) -> np.ndarray:
         """the shim-facing call: host pointers in, pinned host anchors out (gcg_search)"""

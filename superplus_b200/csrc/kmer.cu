@@ -18,6 +18,7 @@
 #include <thread>
 
 #include <mutex>
+#include <immintrin.h>
 
 #include "gcg_internal.cuh"
 #include "host_par.h"
@@ -338,15 +339,16 @@ struct k45f_args {
 
 // Build-time switches (A/B variants, scripts/build_variants.sh):
 //   K45F_MINB      resident blocks per SM asked of ptxas (8 = 32 registers, full occupancy)
-//   K45F_BLOCKSCAN chained scan over BLOCK tiles (8 warp tiles share one state word) instead of warp tiles:
-//                  the first wave of a launch resolves its prefixes hop by hop, 32 states per hop — with
+//   K45F_BLOCKSCAN 0: chained scan over warp tiles; 1: over BLOCK tiles (8 warp tiles share one state word; three
+//                  barriers per round); 2 (default): block tiles, emit deferred by one round, no barriers (below).
+//                  The first wave of a launch resolves its prefixes hop by hop, 32 states per hop — with
 //                  9472 warp tiles in flight that is 296 dependent L2 round trips, with 1184 block tiles 37
 //   K45F_PREFETCH  the probe loop starts the value sector of every hit on its way into the L2
 #ifndef K45F_MINB
 #define K45F_MINB 6
 #endif
 #ifndef K45F_BLOCKSCAN
-#define K45F_BLOCKSCAN 1
+#define K45F_BLOCKSCAN 2
 #endif
 #ifndef K45F_PREFETCH
 #define K45F_PREFETCH 0
@@ -387,12 +389,234 @@ chain_lookback (unsigned long long * __restrict__ state, const int64_t idx, cons
   return base;
 }
 
+// bounded spin: a protocol error must end in a trap with a message, not in a hung GPU
+#define K45F_SPIN_LIMIT (1u << 24)
+#define K45F_SPIN_FAIL(what) do { printf ("k45_fused_kernel: %s never arrived (block %d warp %d)\n", what, (int) blockIdx.x, (int) (threadIdx.x >> 5)); __trap (); } while (0)
+
+// the anchors of one staged tile, 32 per round, at their global indices base .. base + total
+template <int FMT>
+__device__ __forceinline__ void
+k45f_emit_tile (const k45f_args & A, const int k, const int lane, const unsigned long long base, const unsigned long long base0, const uint32_t total,
+                const uint32_t * __restrict__ excl, const uint32_t * __restrict__ mask, const uint64_t * __restrict__ pk,
+                const int32_t * __restrict__ seq, const int32_t * __restrict__ p0s)
+{
+  for (uint32_t h = lane; h < total; h += 32) {
+    const unsigned long long g = base + h;
+    if (g < A.win_lo || g >= A.win_hi) continue;
+    int lo = 0, hi = 32;                          // excl[lo] <= h < excl[hi]
+#pragma unroll
+    for (int it = 0; it < 5; ++it) { int mid = (lo + hi) >> 1; if (excl[mid] <= h) lo = mid; else hi = mid; }
+    const int j = __fns (mask[lo], 0, (int) (h - excl[lo]) + 1);
+    GCG_DEV_ASSERT (lo >= 0 && lo < 32 && j >= 0 && j < 32 && ((mask[lo] >> j) & 1u) && excl[lo] <= h && h < excl[lo + 1]);
+    bool fw;
+    unsigned long long kw;
+    const unsigned long long key = key_at (pk[lo], pk[lo + 1], j, k, &fw);
+    const uint32_t hs = kmer_hash32 (key - 1ULL), b = __umulhi (hs, A.n_bucket);
+    const bucket4 q = ld_bucket_keep (A.keys + 4ULL * b);
+    const int f = bucket_find (q, key, &kw);
+    const unsigned long long slot = f >= 0 ? 4ULL * b + (unsigned) f
+                                           : table_lookup (A.keys, A.n_bucket, b, q, key, hs & 3u, &kw);   // walks on to the overflow buckets
+    GCG_DEV_ASSERT (slot != ~0ULL && slot < 4ULL * A.n_bucket && (kw & GCG_KEY_MASK) == key && !(kw & GCG_KEY_MULTI));   // the mask bit said: present, once
+    GCG_DEV_ASSERT (g >= base0 && g < A.win_hi);
+    // one atomic both records the anchor (ONT-side multiplicity, ont.c:245) and returns (tid, pos, flag)
+#if K45F_DIAG == 1
+    const unsigned long long v = slot;               // (diagnostic build: no value access — WRONG results, timing only)
+#else
+    const unsigned long long v = atomicOr (A.vals + slot, GCG_VAL_ONT1);
+    if ((v & (GCG_VAL_ONT1 | GCG_VAL_ONT2)) == GCG_VAL_ONT1) atomicOr (A.vals + slot, GCG_VAL_ONT2);
+#endif
+    const uint32_t tid = (uint32_t) (v >> 32) & 0x7FFFFFFFu, cpos = (uint32_t) (v >> 1) & 0x3FFFFFFFu;
+    const uint32_t flags = (uint32_t) (v & 1ULL) | (fw ? 0u : 2u);
+    if (FMT == 0) {
+      int4 hh;                                    // gcg_hit {read, pos, tid, cpos_flags} as one 16-byte store
+      hh.x = seq[lo] + A.read_base;
+      hh.y = p0s[lo] + j;
+      hh.z = (int32_t) tid;
+      hh.w = (int32_t) ((cpos << 2) | flags);
+      __stcs (reinterpret_cast<int4 *> (A.out) + g, hh);
+    } else {
+      const unsigned long long gpos = (unsigned long long) __ldg (A.cbase + tid) + cpos;
+      __stcs (reinterpret_cast<unsigned long long *> (A.out) + g,
+              ((unsigned long long) (uint32_t) (p0s[lo] + j) << 36) | (gpos << 2) | flags);
+    }
+  }
+}
+
+#if K45F_BLOCKSCAN == 2
+// ---- the pipelined form ------------------------------------------------------------------------
+// A block works in ROUNDS: in round r its eight warps probe the eight warp tiles of block tile bt_r (handed out in
+// increasing order by the global counter).  The chain element is the block tile.  What made the plain block form slow
+// (ncu round 2: 28 % of the stall samples at its three barriers) is that a tile's anchors were emitted right after its
+// probe: every block then waits, at a barrier, for ALL block tiles before it to publish their counts — a convoy of
+// 1184 blocks moving at the pace of the slowest.  Here the emit of round r is DEFERRED to round r + 1: by then the
+// counts of every earlier block tile were published a whole probe (tens of microseconds) ago and the look-back is a
+// couple of L2 reads; and nothing in a round is a barrier:
+//   * the first warp to finish its probe of round r claims the block tile of round r + 1 (so nobody waits for it);
+//   * every warp adds its anchor count into a shared counter; the warp that completes the eight publishes the block
+//     tile's count (SCANST_AGG) to the chain;
+//   * the first warp that wants to emit round r - 1 resolves that block tile's prefix (look-back) for the block, the
+//     others find it in shared memory;
+//   * per-round scalars live in four rotating slots (a warp can be at most two rounds ahead of another: it cannot
+//     resolve round r + 1 before every warp of the block has finished probing it), a warp's staged tile in two.
+// Every spin is bounded and traps with a message instead of hanging the GPU.
+#define K45F_SLOTS 8        // rotating per-round scalars (a warp is at most two rounds ahead of another; writers touch round + 1)
 template <bool FILTER, int KC, int FMT>
 __global__ void __launch_bounds__ (32 * K4_WARPS, K45F_MINB)
 k45_fused_kernel (const k45f_args A)
 {
   __shared__ k4_smem sm;
-  __shared__ uint32_t s_mask[K4_WARPS][32];
+  __shared__ uint32_t s_excl[2][K4_WARPS][33], s_mask[2][K4_WARPS][32];
+  __shared__ uint64_t s_pk[2][K4_WARPS][33];
+  __shared__ int32_t s_seq[2][K4_WARPS][32], s_p0[2][K4_WARPS][32];
+  __shared__ unsigned long long s_bt[K45F_SLOTS], s_bbase[K45F_SLOTS], s_acc[K45F_SLOTS];   // block tile of a round; its exclusive prefix; (arrivals << 48) | anchors
+  __shared__ uint32_t s_wtot[K45F_SLOTS][K4_WARPS];
+  __shared__ int s_btgen[K45F_SLOTS], s_lock[K45F_SLOTS], s_basegen[K45F_SLOTS];            // round + 1 when valid (0 = never)
+  const int k = KC > 0 ? KC : A.k;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t n_tiles = (A.n_words + 31) >> 5;
+  const int64_t n_bt = (n_tiles + K4_WARPS - 1) / K4_WARPS;
+  const unsigned long long base0 = A.base_in ? *A.base_in : 0ULL;
+  if (A.done_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *A.done_out = base0;
+  if (threadIdx.x < K45F_SLOTS) { s_acc[threadIdx.x] = 0; s_btgen[threadIdx.x] = 0; s_lock[threadIdx.x] = 0; s_basegen[threadIdx.x] = 0; }
+  __syncthreads ();
+  if (threadIdx.x == 0) { s_bt[0] = atomicAdd (A.tile_ctr, 1ULL); s_btgen[0] = 1; }
+  __syncthreads ();
+
+  uint32_t prev_total = 0;                             // anchors of the tile this warp staged in the previous round
+  int64_t prev_bt = -1;
+  for (int r = 0;; ++r) {
+    const int qs = r & (K45F_SLOTS - 1), q2 = r & 1;
+    // ---- the block tile of this round (claimed by the first warp that finished the previous round's probe)
+    if (lane == 0) { uint32_t spin = 0; while (*(volatile int *) &s_btgen[qs] != r + 1) if (++spin > K45F_SPIN_LIMIT) K45F_SPIN_FAIL ("the block tile of a round"); }
+    __syncwarp ();
+    const int64_t bt = (int64_t) *(volatile unsigned long long *) &s_bt[qs];
+    const bool live = bt < n_bt;
+    uint32_t total = 0;
+    if (live) {
+      const int64_t tile = bt * K4_WARPS + wid;          // may be past the end in the last block tile: probes nothing
+      uint64_t pk; int32_t sq, p0;
+      const uint32_t mymask = k4_probe_tile<FILTER, KC, K45F_PREFETCH != 0> (sm, A.vals, tile, A.packed, A.woff, A.len, A.tile_seq, A.n_seq, A.n_words, k, A.keys, A.n_bucket,
+                                                                             A.filter, A.filter_words, A.filter_k3, &pk, &sq, &p0);
+      const int64_t w = (tile << 5) + lane;
+      const uint32_t c = __popc (mymask);
+      uint32_t x = c;
+      for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (0xffffffffu, x, o); if (lane >= o) x += y; }
+      total = __shfl_sync (0xffffffffu, x, 31);
+      GCG_DEV_ASSERT (tile < n_tiles || mymask == 0);
+      // stage the tile for the emit one round later
+      s_excl[q2][wid][lane] = x - c;
+      s_mask[q2][wid][lane] = mymask;
+      s_pk[q2][wid][lane] = pk;
+      s_seq[q2][wid][lane] = w < A.n_words ? sq : -1;
+      s_p0[q2][wid][lane] = p0;
+      if (lane == 31) { s_excl[q2][wid][32] = total; s_pk[q2][wid][32] = w + 1 <= A.n_words ? __ldg (A.packed + w + 1) : 0ULL; }   // (slack word at n_words)
+      // ---- count in; the first arrival claims the next round's block tile, the last one publishes this tile's count
+      if (lane == 0) {
+        s_wtot[qs][wid] = total;
+        __threadfence_block ();
+        const unsigned long long old = atomicAdd (&s_acc[qs], (1ULL << 48) | (unsigned long long) total);
+        const int arrived = (int) (old >> 48);
+        GCG_DEV_ASSERT (arrived < K4_WARPS);
+        if (arrived == 0) {
+          const int ns = (r + 1) & (K45F_SLOTS - 1);
+          s_acc[ns] = 0;                                 // (that slot served round r - 7: everybody left it long ago)
+          s_bt[ns] = atomicAdd (A.tile_ctr, 1ULL);
+          __threadfence_block ();
+          *(volatile int *) &s_btgen[ns] = r + 2;
+        }
+        if (arrived == K4_WARPS - 1) {
+          const unsigned long long bsum = (old + total) & 0xFFFFFFFFFFFFULL;
+          __threadfence ();                              // (every warp's s_wtot of this round is written and ordered before the count becomes visible)
+          if (bt > 0) st_state (A.state + bt, SCANST_AGG | bsum);
+          else {
+            st_state (A.state, SCANST_INC | (base0 + bsum));                 // the first element needs no look-back
+            if (n_bt == 1) *A.total_out = base0 + bsum;
+            s_bbase[qs] = base0;
+            __threadfence_block ();
+            *(volatile int *) &s_basegen[qs] = r + 1;
+          }
+        }
+      }
+      __syncwarp ();
+    }
+    // ---- emit the tile staged one round ago
+    if (prev_bt >= 0) {
+      const int ps = (r - 1) & (K45F_SLOTS - 1), p2 = (r - 1) & 1;
+      int ready = 0;
+      if (lane == 0) ready = *(volatile int *) &s_basegen[ps] == r;
+      ready = __shfl_sync (0xffffffffu, ready, 0);
+      if (!ready) {
+        // the first warp to get here resolves the block tile's prefix for the whole block
+        int mine = 0;
+        if (lane == 0) mine = atomicMax (&s_lock[ps], r) < r;
+        mine = __shfl_sync (0xffffffffu, mine, 0);
+        if (mine) {
+          // the tile's own count is published when the last warp of the block has finished that probe; the counts of the
+          // block tiles before it were published about a whole probe ago
+          uint32_t spin = 0;
+          unsigned long long own;
+          do { own = ld_state (A.state + prev_bt); if (++spin > K45F_SPIN_LIMIT) K45F_SPIN_FAIL ("this block tile's own count"); } while ((own & (SCANST_AGG | SCANST_INC)) == 0);
+          __threadfence ();
+          unsigned long long bb = base0;
+          if (!(own & SCANST_INC)) {                     // (block tile 0 is published with its inclusive prefix: nothing before it)
+            const unsigned long long bsum = own & SCANST_VAL;
+            bb = 0;
+            int64_t j = prev_bt - 1;
+            for (;;) {
+              const int64_t at = j - lane;
+              const unsigned long long st = at >= 0 ? ld_state (A.state + at) : (SCANST_INC | base0);
+              const uint32_t inc = __ballot_sync (0xffffffffu, (st & SCANST_INC) != 0);
+              const uint32_t none = __ballot_sync (0xffffffffu, (st & (SCANST_INC | SCANST_AGG)) == 0);
+              const int f = inc ? __ffs (inc) - 1 : 32;
+              const uint32_t need = f < 31 ? ((2u << f) - 1u) : 0xffffffffu;
+              if (none & need) { if (++spin > K45F_SPIN_LIMIT) K45F_SPIN_FAIL ("an earlier block tile's count"); __nanosleep (40); continue; }
+              unsigned long long sum = (lane <= f) ? (st & SCANST_VAL) : 0ULL;
+              for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync (0xffffffffu, sum, o);
+              bb += sum;
+              if (f < 32) break;
+              j -= 32;
+            }
+            GCG_DEV_ASSERT (prev_bt > 0 && bb >= base0 && bb + bsum <= SCANST_VAL);
+            if (lane == 0) {
+              st_state (A.state + prev_bt, SCANST_INC | (bb + bsum));
+              if (prev_bt == n_bt - 1) *A.total_out = bb + bsum;
+            }
+          } else GCG_DEV_ASSERT (prev_bt == 0);
+          if (lane == 0) {
+            s_bbase[ps] = bb;
+            __threadfence_block ();
+            *(volatile int *) &s_basegen[ps] = r;
+          }
+        } else if (lane == 0) {
+          uint32_t spin = 0;
+          while (*(volatile int *) &s_basegen[ps] != r) if (++spin > K45F_SPIN_LIMIT) K45F_SPIN_FAIL ("the block tile's prefix");
+        }
+        __syncwarp ();
+      }
+      unsigned long long base = *(volatile unsigned long long *) &s_bbase[ps];
+      for (int i = 0; i < wid; ++i) base += *(volatile uint32_t *) &s_wtot[ps][i];
+      // first anchor of every read that starts in this tile
+      if (A.read_off != nullptr && s_seq[p2][wid][lane] >= 0 && s_p0[p2][wid][lane] == 0) {
+        GCG_DEV_ASSERT (s_seq[p2][wid][lane] < A.n_seq);
+        A.read_off[s_seq[p2][wid][lane]] = (long long) (base + s_excl[p2][wid][lane]);
+      }
+#if K45F_DIAG != 2
+      if (prev_total) k45f_emit_tile<FMT> (A, k, lane, base, base0, prev_total, s_excl[p2][wid], s_mask[p2][wid], s_pk[p2][wid], s_seq[p2][wid], s_p0[p2][wid]);
+#endif
+      __syncwarp ();
+    }
+    if (!live) break;
+    prev_total = total;
+    prev_bt = bt;
+  }
+}
+#else
+template <bool FILTER, int KC, int FMT>
+__global__ void __launch_bounds__ (32 * K4_WARPS, K45F_MINB)
+k45_fused_kernel (const k45f_args A)
+{
+  __shared__ k4_smem sm;
+  __shared__ uint32_t s_excl[K4_WARPS][33], s_mask[K4_WARPS][32];
   __shared__ uint64_t s_pk[K4_WARPS][33];
   __shared__ int32_t s_seq[K4_WARPS][32], s_p0[K4_WARPS][32];
 #if K45F_BLOCKSCAN
@@ -458,55 +682,17 @@ k45_fused_kernel (const k45f_args A)
 #endif
     // ---- emit: the tile's anchors in (word, bit) order, 32 per round
     __syncwarp ();
-    sm.excl[wid][lane] = x - c;
+    s_excl[wid][lane] = x - c;
     s_mask[wid][lane] = mymask;
     s_pk[wid][lane] = pk;
     s_seq[wid][lane] = sq;
     s_p0[wid][lane] = p0;
-    if (lane == 31) { sm.excl[wid][32] = total; s_pk[wid][32] = w + 1 <= A.n_words ? __ldg (A.packed + w + 1) : 0ULL; }   // (slack word at n_words)
+    if (lane == 31) { s_excl[wid][32] = total; s_pk[wid][32] = w + 1 <= A.n_words ? __ldg (A.packed + w + 1) : 0ULL; }   // (slack word at n_words)
     __syncwarp ();
-    for (uint32_t h = lane; h < total; h += 32) {
-      const unsigned long long g = base + h;
-      if (g < A.win_lo || g >= A.win_hi) continue;
-      int lo = 0, hi = 32;                          // excl[lo] <= h < excl[hi]
-#pragma unroll
-      for (int it = 0; it < 5; ++it) { int mid = (lo + hi) >> 1; if (sm.excl[wid][mid] <= h) lo = mid; else hi = mid; }
-      const int j = __fns (s_mask[wid][lo], 0, (int) (h - sm.excl[wid][lo]) + 1);
-      GCG_DEV_ASSERT (lo >= 0 && lo < 32 && j >= 0 && j < 32 && ((s_mask[wid][lo] >> j) & 1u) && sm.excl[wid][lo] <= h && h < sm.excl[wid][lo + 1]);
-      bool fw;
-      unsigned long long kw;
-      const unsigned long long key = key_at (s_pk[wid][lo], s_pk[wid][lo + 1], j, k, &fw);
-      const uint32_t hs = kmer_hash32 (key - 1ULL), b = __umulhi (hs, A.n_bucket);
-      const bucket4 q = ld_bucket_keep (A.keys + 4ULL * b);
-      const int f = bucket_find (q, key, &kw);
-      const unsigned long long slot = f >= 0 ? 4ULL * b + (unsigned) f
-                                             : table_lookup (A.keys, A.n_bucket, b, q, key, hs & 3u, &kw);   // walks on to the overflow buckets
-      GCG_DEV_ASSERT (slot != ~0ULL && slot < 4ULL * A.n_bucket && (kw & GCG_KEY_MASK) == key && !(kw & GCG_KEY_MULTI));   // the mask bit said: present, once
-      GCG_DEV_ASSERT (g >= base0 && g < A.win_hi);
-      // one atomic both records the anchor (ONT-side multiplicity, ont.c:245) and returns (tid, pos, flag)
-#if K45F_DIAG == 1
-      const unsigned long long v = slot;               // (diagnostic build: no value access — WRONG results, timing only)
-#else
-      const unsigned long long v = atomicOr (A.vals + slot, GCG_VAL_ONT1);
-      if ((v & (GCG_VAL_ONT1 | GCG_VAL_ONT2)) == GCG_VAL_ONT1) atomicOr (A.vals + slot, GCG_VAL_ONT2);
-#endif
-      const uint32_t tid = (uint32_t) (v >> 32) & 0x7FFFFFFFu, cpos = (uint32_t) (v >> 1) & 0x3FFFFFFFu;
-      const uint32_t flags = (uint32_t) (v & 1ULL) | (fw ? 0u : 2u);
-      if (FMT == 0) {
-        int4 hh;                                    // gcg_hit {read, pos, tid, cpos_flags} as one 16-byte store
-        hh.x = s_seq[wid][lo] + A.read_base;
-        hh.y = s_p0[wid][lo] + j;
-        hh.z = (int32_t) tid;
-        hh.w = (int32_t) ((cpos << 2) | flags);
-        __stcs (reinterpret_cast<int4 *> (A.out) + g, hh);
-      } else {
-        const unsigned long long gpos = (unsigned long long) __ldg (A.cbase + tid) + cpos;
-        __stcs (reinterpret_cast<unsigned long long *> (A.out) + g,
-                ((unsigned long long) (uint32_t) (s_p0[wid][lo] + j) << 36) | (gpos << 2) | flags);
-      }
-    }
+    k45f_emit_tile<FMT> (A, k, lane, base, base0, total, s_excl[wid], s_mask[wid], s_pk[wid], s_seq[wid], s_p0[wid]);
   }
 }
+#endif
 
 // ---- ordered compaction: prefix popcount over the per-word hit masks, then scatter ----------
 #define SCAN_ITEMS 8
@@ -1759,11 +1945,24 @@ struct search_dev_keep { void * d_anchors = nullptr; long long * d_read_off = nu
 
 // fmt 0: *hits_out = gcg_hit[*n_hit]; fmt 1: *hits_out = uint64_t[*n_hit] and *read_off_out = int64_t[n_read + 1]
 // keep != NULL (fmt 1 only): the anchors are not downloaded, *hits_out stays NULL
-static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
+// where the reads of a host-buffer search come from: ASCII strings (rseq_t.b of the reference), or words the caller
+// has already 2-bit packed in the library's layout (gcg_host_pack_2bit; the FASTQ loader of superplus_b200/gap_closer
+// packs while it copies the bases): read i = words [pwoff[i], pwoff[i] + (len[i] + 31) / 32)
+struct read_source { const char * const * seq = nullptr; const uint64_t * packed = nullptr; const int64_t * pwoff = nullptr; };
+
+static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const read_source & src, const int32_t * read_len,
                              int64_t n_read, int k, int fmt, void ** hits_out, int64_t * n_hit, int64_t ** read_off_out,
                              search_dev_keep * keep = nullptr)
 {
-  GCG_CHECK (ctx && t && hits_out && n_hit && n_read >= 0 && (n_read == 0 || (read_seq && read_len)), GCG_EINVAL, "gcg_search: bad argument");
+  const char * const * read_seq = src.seq;
+  GCG_CHECK (ctx && t && hits_out && n_hit && n_read >= 0 && (n_read == 0 || ((read_seq || (src.packed && src.pwoff)) && read_len)), GCG_EINVAL, "gcg_search: bad argument");
+  // packed words in page-locked memory go over PCIe from where they lie, chunk by chunk (no host pass at all)
+  bool packed_pinned = false;
+  if (src.packed) {
+    cudaPointerAttributes at;
+    packed_pinned = cudaPointerGetAttributes (&at, src.packed) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError ();
+  }
   GCG_CHECK (k == t->k, GCG_EINVAL, "gcg_search: k=%d but the table was built with k=%d", k, t->k);
   GCG_CHECK (n_read < 0x7FFFFFFF, GCG_ERANGE, "gcg_search: too many reads");
   *hits_out = nullptr;
@@ -1771,13 +1970,23 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
   if (read_off_out) *read_off_out = nullptr;
   GCG_CUDA (cudaSetDevice (ctx->device));
   gcg_trace_mark (ctx, nullptr);
-  int64_t chunk_words = ((int64_t) 8 << 20) / 32, max_words = 0, total_kmers = 0;
-  if (const char * e = getenv ("GCG_SEARCH_CHUNK_BYTES")) chunk_words = std::max<int64_t> (1, atoll (e) / 32);
+  // Chunks GROW: 4, 8, 16, 32, 32, ... MiB of bases (and shrink again towards the end).  A chunk's kernel runs the deferred-emit pipeline of
+  // k45_fused_kernel, which needs several rounds per block to hide its look-back and emit phases: a launch over 8 MiB is
+  // a single round (measured 100-116 us per 8 MiB chunk against 50 us per 8 MiB inside one launch over the whole read
+  // set).  Large chunks fix that, a small first chunk keeps the time until the GPU has something to do short.
+  // GCG_SEARCH_CHUNK_BYTES fixes one size for all chunks (tests; A/B timing).
+  int64_t chunk_words = ((int64_t) 32 << 20) / 32, first_words = ((int64_t) 4 << 20) / 32, last_words = ((int64_t) 8 << 20) / 32, max_words = 0, total_kmers = 0;
+  if (const char * e = getenv ("GCG_SEARCH_CHUNK_MAX_MB")) chunk_words = std::max<int64_t> (1, atoll (e)) * (1 << 20) / 32;      // (A/B timing of the schedule)
+  if (const char * e = getenv ("GCG_SEARCH_CHUNK_FIRST_MB")) first_words = std::max<int64_t> (1, atoll (e)) * (1 << 20) / 32;
+  if (const char * e = getenv ("GCG_SEARCH_CHUNK_LAST_MB")) last_words = std::max<int64_t> (1, atoll (e)) * (1 << 20) / 32;
+  if (const char * e = getenv ("GCG_SEARCH_CHUNK_BYTES")) chunk_words = first_words = last_words = std::max<int64_t> (1, atoll (e) / 32);
+  int64_t total_words = 0, words_done = 0;
   int32_t max_len = 0;
   for (int64_t r = 0; r < n_read; ++r) {
     GCG_CHECK (read_len[r] >= 0, GCG_ERANGE, "gcg_search: read %lld has a negative length", (long long) r);
     max_words = std::max<int64_t> (max_words, ((int64_t) read_len[r] + 31) >> 5);
     max_len = std::max (max_len, read_len[r]);
+    total_words += ((int64_t) read_len[r] + 31) >> 5;
     if (read_len[r] >= k) total_kmers += (int64_t) read_len[r] - k + 1;
   }
   int rc = GCG_OK;
@@ -1810,7 +2019,7 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
   }
 
   // work on ctx->stream enqueued by earlier calls (the table build) precedes the first probe by stream order
-  struct chunk_desc { int64_t r0 = 0, r1 = 0, nr = 0, nw = 0, kmers = 0, n_tiles = 0; size_t tseq_off = 0; int slot = 0; };
+  struct chunk_desc { int64_t r0 = 0, r1 = 0, nr = 0, nw = 0, kmers = 0, n_tiles = 0; size_t tseq_off = 0; int slot = 0; bool direct = false; };
   int inflight[PIPE_SLOTS], n_inflight = 0;       // staged mode: submitted, not yet downloaded, oldest first
   int64_t c = 0, n_sub = 0;
   unsigned long long win_lo = 0, win_hi = 0;      // zero copy: window of global anchor indices this pass materialises
@@ -1828,14 +2037,20 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
   // waits for its slot and writes the meta block (host work that overlaps the gather of the chunk before)
   auto plan = [&] (int64_t r0, chunk_desc & d) -> int {
     int64_t r1 = r0, nw = 0;
+    // this chunk's size: growing from the first, and shrinking again towards the end (what comes after the last
+    // kernel — the download of its anchors — is proportional to the last chunk)
+    int64_t target = std::min (cap_words, first_words << std::min<int64_t> (c, 8));
+    target = std::min (target, std::max (last_words, (total_words - words_done) / 2));
+    target = std::max (max_words, target);
     while (r1 < n_read) {
       const int64_t w = ((int64_t) read_len[r1] + 31) >> 5;
-      if (r1 > r0 && nw + w > cap_words) break;
+      if (r1 > r0 && nw + w > target) break;
       const int64_t nr = r1 - r0 + 1;
       if (r1 > r0 && (size_t) ((nr + 2) * 12 + ((nw + w + 31) >> 5) * 4 + 64) > p->meta_cap) break;
       nw += w; ++r1;
     }
     d.r0 = r0; d.r1 = r1; d.nr = r1 - r0; d.nw = nw; d.n_tiles = (nw + 31) >> 5; d.kmers = 0;
+    words_done += nw;
     d.slot = (int) (c % PIPE_SLOTS);
     ++c;
     pipe_slot & q = p->s[d.slot];
@@ -1850,8 +2065,10 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
     d.tseq_off = ((size_t) (nr + 1) * 8 + (size_t) nr * 4 + 7) & ~(size_t) 7;
     int32_t * tseq = (int32_t *) (q.h_meta + d.tseq_off);
     int64_t w = 0;
+    d.direct = packed_pinned;
     for (int64_t i = 0; i < nr; ++i) {
       woff[i] = w; len[i] = read_len[r0 + i];
+      if (d.direct && src.pwoff[r0 + i] - src.pwoff[r0] != w) d.direct = false;      // (the caller's words of this chunk are not one run)
       w += ((int64_t) read_len[r0 + i] + 31) >> 5;
       if (read_len[r0 + i] >= k) d.kmers += (int64_t) read_len[r0 + i] - k + 1;
     }
@@ -1871,6 +2088,14 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
     const int32_t * len = (const int32_t *) (q.h_meta + (size_t) (nr + 1) * 8);
     const int64_t n_task = nw * 32 < (1 << 18) ? 1 : std::min<int64_t> (nr, 4 * (int64_t) ctx->host_threads);
     uint64_t * dst = q.h_packed;
+    if (src.packed) {
+      const uint64_t * pk = src.packed; const int64_t * pwoff = src.pwoff;
+      gather_fn = [=] (int64_t tk) {                 // the caller's packed words, read by read (8 bytes per 32 bases)
+        for (int64_t i = nr * tk / n_task; i < nr * (tk + 1) / n_task; ++i)
+          if (len[i] > 0) gcg_copy_stream (dst + woff[i], pk + pwoff[r0 + i], (size_t) (((int64_t) len[i] + 31) >> 5) * 8);
+        gcg_copy_fence ();
+      };
+    } else
     gather_fn = [=] (int64_t tk) {                   // gather + 2-bit pack in one pass over the caller's strings
       for (int64_t i = nr * tk / n_task; i < nr * (tk + 1) / n_task; ++i)
         if (len[i] > 0) gcg_pack_stream (dst + woff[i], read_seq[r0 + i], (size_t) len[i]);
@@ -1879,13 +2104,24 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
     gcg_workers_start (pool, n_task, gather_fn);
   };
 
+  // direct mode: queue the download of the anchors that have become complete since the last look (at least min_bytes)
+  auto download_ready = [&] (size_t min_bytes) -> int {
+    const int64_t done = std::min<int64_t> ((int64_t) *(volatile unsigned long long *) p->h_count, (int64_t) win_hi);
+    const int64_t from = std::max<int64_t> (copied, (int64_t) win_lo);
+    if (done > from && (size_t) (done - from) * res.rec >= min_bytes) {
+      GCG_CUDA (cudaMemcpyAsync (res.buf + (size_t) from * res.rec, (char *) d_res + (size_t) from * res.rec, (size_t) (done - from) * res.rec, cudaMemcpyDeviceToHost, p->down));
+      copied = done;
+    }
+    return GCG_OK;
+  };
+
   // copy the gathered chunk to the device and enqueue its kernel: probe, ordered anchor index, ONT-side
   // multiplicity and anchor records in one launch (k45_fused_kernel)
   auto submit = [&] (const chunk_desc & d) -> int {
     pipe_slot & q = p->s[d.slot];
     const int64_t nr = d.nr, nw = d.nw;
     const size_t meta_bytes = d.tseq_off + (size_t) d.n_tiles * 4;
-    GCG_CUDA (cudaMemcpyAsync (q.d_packed, q.h_packed, (size_t) nw * 8, cudaMemcpyHostToDevice, p->up));
+    GCG_CUDA (cudaMemcpyAsync (q.d_packed, d.direct ? (const void *) (src.packed + src.pwoff[d.r0]) : (const void *) q.h_packed, (size_t) nw * 8, cudaMemcpyHostToDevice, p->up));
     GCG_CUDA (cudaMemcpyAsync (q.d_meta, q.h_meta, meta_bytes, cudaMemcpyHostToDevice, p->up));
     GCG_CUDA (cudaEventRecord (q.ev_up, p->up));
     GCG_CUDA (cudaStreamWaitEvent (ctx->stream, q.ev_up, 0));
@@ -1903,15 +2139,7 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
       if (e) return e;
       GCG_CUDA (cudaEventRecord (q.ev_free, ctx->stream));         // the slot is free again when its kernel has finished
       q.busy = true;
-      if (mode == 1 && !keep) {
-        // whatever earlier launches have completed by now goes down (at least 1 MiB at a time)
-        const int64_t done = std::min<int64_t> ((int64_t) *(volatile unsigned long long *) p->h_count, (int64_t) win_hi);
-        const int64_t from = std::max<int64_t> (copied, (int64_t) win_lo);
-        if (done > from && (size_t) (done - from) * res.rec >= ((size_t) 1 << 20)) {
-          GCG_CUDA (cudaMemcpyAsync (res.buf + (size_t) from * res.rec, (char *) d_res + (size_t) from * res.rec, (size_t) (done - from) * res.rec, cudaMemcpyDeviceToHost, p->down));
-          copied = done;
-        }
-      }
+      if (mode == 1 && !keep) return download_ready ((size_t) 1 << 20);     // whatever earlier launches have completed by now goes down
       return GCG_OK;
     }
     e = launch_fused (ctx, t, q.d_packed, d_woff, d_len, d_tseq, nr, nw, k, fmt, q.d_hits, 0ULL, ~0ULL, (int32_t) d.r0,
@@ -1931,12 +2159,12 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
   auto run_pass = [&] () -> int {
     int prc = GCG_OK;
     chunk_desc cur_c, next_c;
-    c = 0; n_sub = 0; n_inflight = 0;
+    c = 0; n_sub = 0; n_inflight = 0; words_done = 0;
     if (zc) GCG_CUDA (cudaMemsetAsync (p->d_run, 0, 2 * sizeof (unsigned long long), ctx->stream));
     p->h_count[0] = 0;
     copied = 0;
     prc = plan (0, cur_c);
-    bool gathering = !prc && cur_c.kmers > 0;
+    bool gathering = !prc && cur_c.kmers > 0 && !cur_c.direct;
     if (gathering) start_gather (cur_c);
     while (!prc) {
       // the next chunk is planned while this one is gathered, and gathered while this one is copied and probed
@@ -1951,7 +2179,7 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
       t_gather += ms (t0, now ());
       gathering = false;
       if (prc) break;
-      if (more && next_c.kmers > 0) { start_gather (next_c); gathering = true; }
+      if (more && next_c.kmers > 0 && !next_c.direct) { start_gather (next_c); gathering = true; }
       if (cur_c.kmers > 0) {
         auto t1 = now ();
         prc = submit (cur_c);
@@ -1977,6 +2205,14 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const char * const * 
     // ---- drain
     auto t_d0 = now ();
     for (int i = 0; i < n_inflight && !prc; ++i) prc = pipe_download (ctx, p->s[inflight[i]], inflight[i], res);
+    if (mode == 1 && !keep && !prc) {
+      // the kernels still queued finish one after the other: keep the download stream fed while they do
+      while (!prc && cudaStreamQuery (ctx->stream) == cudaErrorNotReady) {
+        prc = download_ready ((size_t) 1 << 19);
+        for (int i = 0; i < 64; ++i) _mm_pause ();
+      }
+      cudaGetLastError ();
+    }
     if (zc && !prc && n_sub > 0 &&
         cudaMemcpyAsync (ctx->h_counters + 4, p->d_run + (n_sub & 1), 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_search: count copy failed"); prc = GCG_ECUDA; }
     if (cudaStreamSynchronize (p->down) != cudaSuccess || cudaStreamSynchronize (ctx->stream) != cudaSuccess) {
@@ -2084,15 +2320,16 @@ int gcg_runs_from_anchors (gcg_ctx * ctx, const gcg_table * t, const void * d_an
 
 // N3: search + the anchor grouping of map_ont2contigs (ctg_graph.c:600-656) on the device; neither the anchors
 // nor anything per ONT base reaches the host
-extern "C" int gcg_search_runs (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
-                                int64_t n_read, int k, gcg_run ** runs_out, int64_t ** run_off_out, int64_t * n_run, int64_t * n_anchor)
+static int search_runs_impl (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const uint64_t * packed, const int64_t * pwoff, const int32_t * read_len,
+                             int64_t n_read, int k, gcg_run ** runs_out, int64_t ** run_off_out, int64_t * n_run, int64_t * n_anchor)
 {
   GCG_CHECK (runs_out && run_off_out && n_run && n_anchor, GCG_EINVAL, "gcg_search_runs: bad argument");
   *runs_out = nullptr; *run_off_out = nullptr; *n_run = 0; *n_anchor = 0;
   search_dev_keep keep;
   void * none = nullptr;
   int64_t * read_off = nullptr;
-  int rc = search_host_impl (ctx, t, read_seq, read_len, n_read, k, 1, &none, n_anchor, &read_off, &keep);
+  read_source src; src.seq = read_seq; src.packed = packed; src.pwoff = pwoff;
+  int rc = search_host_impl (ctx, t, src, read_len, n_read, k, 1, &none, n_anchor, &read_off, &keep);
   if (rc) return rc;
   if (keep.d_read_off == nullptr) {
     // nothing was searched (no read holds a k-mer): every read has zero runs
@@ -2111,11 +2348,24 @@ extern "C" int gcg_search_runs (gcg_ctx * ctx, gcg_table * t, const char * const
   return rc;
 }
 
+extern "C" int gcg_search_runs (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
+                                int64_t n_read, int k, gcg_run ** runs_out, int64_t ** run_off_out, int64_t * n_run, int64_t * n_anchor)
+{
+  return search_runs_impl (ctx, t, read_seq, nullptr, nullptr, read_len, n_read, k, runs_out, run_off_out, n_run, n_anchor);
+}
+
+extern "C" int gcg_search_runs_packed (gcg_ctx * ctx, gcg_table * t, const uint64_t * packed, const int64_t * woff, const int32_t * read_len,
+                                       int64_t n_read, int k, gcg_run ** runs_out, int64_t ** run_off_out, int64_t * n_run, int64_t * n_anchor)
+{
+  return search_runs_impl (ctx, t, nullptr, packed, woff, read_len, n_read, k, runs_out, run_off_out, n_run, n_anchor);
+}
+
 extern "C" int gcg_search (gcg_ctx * ctx, gcg_table * t, const char * const * read_seq, const int32_t * read_len,
                            int64_t n_read, int k, gcg_hit ** hits_out, int64_t * n_hit)
 {
   void * buf = nullptr;
-  int rc = search_host_impl (ctx, t, read_seq, read_len, n_read, k, 0, &buf, n_hit, nullptr);
+  read_source src; src.seq = read_seq;
+  int rc = search_host_impl (ctx, t, src, read_len, n_read, k, 0, &buf, n_hit, nullptr);
   if (hits_out) *hits_out = (gcg_hit *) buf;
   return rc;
 }
@@ -2125,7 +2375,19 @@ extern "C" int gcg_search_compact (gcg_ctx * ctx, gcg_table * t, const char * co
 {
   GCG_CHECK (anchors_out && read_off_out, GCG_EINVAL, "gcg_search_compact: bad argument");
   void * buf = nullptr;
-  int rc = search_host_impl (ctx, t, read_seq, read_len, n_read, k, 1, &buf, n_anchor, read_off_out);
+  read_source src; src.seq = read_seq;
+  int rc = search_host_impl (ctx, t, src, read_len, n_read, k, 1, &buf, n_anchor, read_off_out);
+  *anchors_out = (uint64_t *) buf;
+  return rc;
+}
+
+extern "C" int gcg_search_compact_packed (gcg_ctx * ctx, gcg_table * t, const uint64_t * packed, const int64_t * woff, const int32_t * read_len,
+                                          int64_t n_read, int k, uint64_t ** anchors_out, int64_t ** read_off_out, int64_t * n_anchor)
+{
+  GCG_CHECK (anchors_out && read_off_out && (n_read == 0 || (packed && woff)), GCG_EINVAL, "gcg_search_compact_packed: bad argument");
+  void * buf = nullptr;
+  read_source src; src.packed = packed; src.pwoff = woff;
+  int rc = search_host_impl (ctx, t, src, read_len, n_read, k, 1, &buf, n_anchor, read_off_out);
   *anchors_out = (uint64_t *) buf;
   return rc;
 }

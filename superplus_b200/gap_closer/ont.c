@@ -189,6 +189,8 @@ typedef struct share_s {
   int64_t * read_off;
   gcg_hit * hits;           /* ... or the 16-byte form */
   int64_t n_hit;
+  const uint64_t * packed;  /* the loader's 2-bit words of ALL reads (pack on ingest) and their word offsets, or NULL */
+  const int64_t * pwoff;
   gcg_run * runs;           /* GC_RUNS: run records instead of anchors */
   int64_t * run_off;
   int64_t n_run;
@@ -201,11 +203,14 @@ share_core (void * data)
 {
   share_t * s = (share_t *) data;
   if (gcg_bridge_runs_mode ()) {
-    s->rc = gcg_search_runs (s->ctx, s->table, s->ptrs + s->r0, s->lens + s->r0, s->r1 - s->r0, s->kmer_len, &s->runs, &s->run_off, &s->n_run, &s->n_hit);
+    s->rc = s->packed
+          ? gcg_search_runs_packed (s->ctx, s->table, s->packed, s->pwoff + s->r0, s->lens + s->r0, s->r1 - s->r0, s->kmer_len, &s->runs, &s->run_off, &s->n_run, &s->n_hit)
+          : gcg_search_runs (s->ctx, s->table, s->ptrs + s->r0, s->lens + s->r0, s->r1 - s->r0, s->kmer_len, &s->runs, &s->run_off, &s->n_run, &s->n_hit);
     if (s->rc != 0) snprintf (s->err, sizeof s->err, "%s", gcg_last_error ());
     return NULL;
   }
   s->rc = getenv ("GC_ANCHORS16") ? GCG_ERANGE
+        : s->packed ? gcg_search_compact_packed (s->ctx, s->table, s->packed, s->pwoff + s->r0, s->lens + s->r0, s->r1 - s->r0, s->kmer_len, &s->anchors, &s->read_off, &s->n_hit)
         : gcg_search_compact (s->ctx, s->table, s->ptrs + s->r0, s->lens + s->r0, s->r1 - s->r0, s->kmer_len, &s->anchors, &s->read_off, &s->n_hit);
   if (s->rc == GCG_ERANGE) {        /* beyond the compact form's bit budget (or GC_ANCHORS16 set: A/B of the two forms) */
     s->anchors = NULL; s->read_off = NULL;
@@ -313,6 +318,17 @@ search_kmers_on_ont_reads (mp_t(rs) * ont_seqs, mp_t(ctg) * ctg_seqs,
   /* contiguous shares of about equal bases: share d ends at the first read where the running base
    * count reaches (d + 1) / n_dev of the total (superplus_b200/api.py split_reads_by_bases) */
   memset (share, 0, sizeof share);
+  /* reads the loader packed on ingest (rseq_fast.c) are searched from their 2-bit words; okseq->seq must still be
+   * the loader's records, in order (ont_kseqs_init sets them so) */
+  {
+    const uint64_t * pk = NULL; const int64_t * pw = NULL;
+    if (rseq_packed_lookup ((const void *) ont_seqs, n_reads, &pk, &pw)) {
+      for (r = 0; r < n_reads; ++r)
+        if (mp_at (okseq, okseqs, r)->seq != mp_at (rs, ont_seqs, r)) { pk = NULL; break; }
+      for (d = 0; d < n_dev && pk != NULL; ++d) { share[d].packed = pk; share[d].pwoff = pw; }
+      if (pk != NULL && getenv ("GCG_TRACE")) fprintf (stderr, "[gcg] searching the reads from the loader's 2-bit words (pack on ingest)\n");
+    }
+  }
   for (d = 0, r = 0; d < n_dev; ++d) {
     int64_t goal = (total_bases * (d + 1) + n_dev - 1) / n_dev;
     share[d].ctx = br->ctxs[d];

@@ -19,6 +19,12 @@
  *   - prints "Total loading %ld reads, cost %lds".
  * Here the file is mapped, the newlines are located by all host cores, and the per-read
  * allocations and copies are spread over the cores as well.
+ *
+ * Pack on ingest (the rest of row N1): while a read's bases are copied into its rseq_t they are also packed to
+ * 2 bits per base (gcg_host_pack_2bit: the library's word layout) into one array for the whole read set, which
+ * search_kmers_on_ont_reads (ont.c of this directory) hands to gcg_search_*_packed — the search then reads 8 bytes
+ * per 32 bases instead of gathering and packing the ASCII again.  rseq_packed_lookup () finds the array by the
+ * address of the read set; GC_NO_PACK_ON_INGEST=1 switches it off (the search packs, as before).
  */
 #include <fcntl.h>
 #include <pthread.h>
@@ -33,6 +39,18 @@
 
 #include "rseq.h"
 #include "utils.h"
+#include "gcg_bridge.h"
+
+/* the packed words of the last read set loaded (one per process is all gap_closer needs, main.c:156) */
+static struct { const void * set; uint64_t * words; int64_t * woff; int64_t n; } g_packed;
+
+int
+rseq_packed_lookup (const void * set, int64_t n_reads, const uint64_t ** words, const int64_t ** woff)
+{
+  if (g_packed.set == NULL || g_packed.set != set || g_packed.n != n_reads) return 0;
+  *words = g_packed.words; *woff = g_packed.woff;
+  return 1;
+}
 
 #define INIT_SIZE_BT_WIDTH 7     /* private to the reference's rseq.c (rseq.c:22): buffer sizes are multiples of 128 */
 
@@ -71,6 +89,8 @@ typedef struct {
   int64_t n_reads;
   int64_t * cursor;
   int bad;                     /* a record with l_base != l_qual was seen */
+  uint64_t * words;            /* pack on ingest: 2-bit words of all reads, read i at woff[i] (NULL = off) */
+  const int64_t * woff;
 } fill_arg_t;
 
 static void *
@@ -92,6 +112,7 @@ fill_core (void * data)
       r->q = (char *) ckmalloc (r->m);
       memcpy (r->b, a->buf + b0, (size_t) r->l); r->b[r->l] = '\0';
       memcpy (r->q, a->buf + q0, (size_t) r->l); r->q[r->l] = '\0';
+      if (a->words != NULL && r->l > 0) gcg_host_pack_2bit (r->b, r->l, a->words + a->woff[i]);     /* (the bases are in the cache) */
     }
   }
   return NULL;
@@ -145,10 +166,27 @@ sefq_load (const char * fq_file)
   set = mp_init (rs, NULL, NULL);
   mp_resize (rs, set, n_reads);
   set->n = n_reads;
+  free (g_packed.words); free (g_packed.woff);
+  memset (&g_packed, 0, sizeof g_packed);
+  if (n_reads > 0 && getenv ("GC_NO_PACK_ON_INGEST") == NULL) {
+    /* word offset of every read: lengths are known from the newline positions alone */
+    int64_t w = 0;
+    g_packed.woff = (int64_t *) ckalloc (n_reads + 1, sizeof (int64_t));
+    for (i = 0; i < n_reads; ++i) {
+      int64_t l = nl[4 * i + 1] - nl[4 * i] - 1;
+      g_packed.woff[i] = w;
+      w += (l + 31) >> 5;
+    }
+    g_packed.woff[n_reads] = w;
+    if (posix_memalign ((void **) &g_packed.words, 64, (size_t) (w + 2) * 8) != 0) err_mesg ("fail to allocate %ld packed words", (long) w);
+    g_packed.words[w] = g_packed.words[w + 1] = 0;
+    g_packed.set = set; g_packed.n = n_reads;
+  }
   if (n_reads > 0) {
     for (t = 0; t < nt; ++t) {
       fargs[t].buf = buf; fargs[t].nl = nl; fargs[t].reads = set->pool; fargs[t].n_reads = n_reads;
       fargs[t].cursor = &cursor; fargs[t].bad = 0;
+      fargs[t].words = g_packed.words; fargs[t].woff = g_packed.woff;
       ckpthread_create (pids + t, NULL, fill_core, (void *) (fargs + t));
     }
     for (t = 0; t < nt; ++t) {

@@ -71,3 +71,40 @@ def test_loader_matches_reference_large(tmp_path):
     assert os.path.getsize(path) > (1 << 20)
     got, want = load("sefq_load", path), load("sefq_load_reference", path)
     assert len(got) == 600 and got == want
+
+
+def test_loader_packs_on_ingest(tmp_path):
+    """pack on ingest (rest of SURVEY 8f row N1): the loader leaves, beside the rseq_t records, the 2-bit words of
+    every read in the library's layout (what gcg_host_pack_2bit writes) — found through rseq_packed_lookup by the
+    address of the read set; GC_NO_PACK_ON_INGEST switches it off"""
+    from superplus_b200 import api
+    rng = np.random.default_rng(5)
+    reads = [(b"", b"")]
+    for _ in range(300):
+        n = int(rng.integers(1, 6000))
+        reads.append((bytes(rng.choice(np.frombuffer(b"ACGTNacgtRY", np.uint8), n)), b"I" * n))
+    reads += [(b"A" * 32, b"I" * 32), (b"C" * 33, b"I" * 33), (b"", b"")]
+    path = str(tmp_path / "p.fq")
+    open(path, "wb").write(fastq(reads))
+    L = C.CDLL(SHIM)
+    L.sefq_load.restype = C.POINTER(Pool)
+    L.sefq_load.argtypes = [C.c_char_p]
+    L.rseq_packed_lookup.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    p = L.sefq_load(path.encode())
+    n = p.contents.n
+    assert n == len(reads)
+    words, woff = C.c_void_p(), C.c_void_p()
+    assert L.rseq_packed_lookup(p, n, C.byref(words), C.byref(woff)) == 1
+    assert L.rseq_packed_lookup(p, n + 1, C.byref(words), C.byref(woff)) == 0
+    wo = np.frombuffer((C.c_char * ((n + 1) * 8)).from_address(woff.value), dtype=np.int64)
+    wd = np.frombuffer((C.c_char * (int(wo[-1]) * 8 + 8)).from_address(words.value), dtype=np.uint64)
+    for i, (b, _) in enumerate(reads):
+        nw = (len(b) + 31) // 32
+        assert int(wo[i + 1] - wo[i]) == nw
+        assert np.array_equal(wd[int(wo[i]):int(wo[i]) + nw], api.host_pack_2bit(b)), i
+    os.environ["GC_NO_PACK_ON_INGEST"] = "1"
+    try:
+        p2 = L.sefq_load(path.encode())
+        assert L.rseq_packed_lookup(p2, n, C.byref(words), C.byref(woff)) == 0
+    finally:
+        os.environ.pop("GC_NO_PACK_ON_INGEST")

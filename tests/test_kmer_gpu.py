@@ -319,3 +319,29 @@ def test_run_records_match_the_grouping_of_map_ont2contigs(ctx, oracle, monkeypa
     assert _check_runs(ctx, oracle, inp.contigs, chim + [e], 25) > len(chim)
     _check_runs(ctx, oracle, inp.contigs, [e, e], 25)
     _check_runs(ctx, oracle, inp.contigs, [], 25)
+
+
+@pytest.mark.parametrize("pinned,gap", [(False, 0), (True, 0), (True, 3), (False, 1)])
+def test_search_of_reads_packed_by_the_caller(ctx, oracle, pinned, gap, monkeypatch):
+    """gcg_search_compact_packed (pack on ingest): the caller hands over 2-bit words instead of
+    ASCII.  Words in page-locked memory whose reads follow each other go over PCIe from where they lie; pageable
+    words, or reads with gaps between them, are copied into the pinned ring first.  Same anchors either way."""
+    inp = synth.make_config("small")
+    e = np.zeros(0, np.uint8)
+    reads = [e] + inp.reads[:70] + [inp.reads[0][:9], e] + inp.reads[70:]
+    cs = ctx.upload(inp.contigs)
+    t = ctx.table_build(cs, 25)
+    want_a, want_off = ctx.search_host_compact(t, reads)
+    st = t.stats()
+    t.free()
+    words, woff, lens, keep = api.Context.pack_reads(reads, pinned=pinned, gap_words=gap)
+    for chunk in (None, 8192):
+        if chunk:
+            monkeypatch.setenv("GCG_SEARCH_CHUNK_BYTES", str(chunk))
+        t = ctx.table_build(cs, 25)
+        a, off = ctx.search_host_compact_packed(t, words, woff, lens)
+        assert np.array_equal(a, want_a) and np.array_equal(off, want_off) and t.stats() == st, (pinned, gap, chunk)
+        t.free()
+    if keep is not None:
+        keep.free()
+    cs.free()
