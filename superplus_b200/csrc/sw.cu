@@ -234,6 +234,28 @@ sw_fill_generic_kernel (const uint8_t * __restrict__ qry, const uint8_t * __rest
 // COHERENT: the trace was written by this very kernel (the packed fill kernel walks its own items):
 // loads go to the L2 (ld.global.cg), never through the non-coherent path, which may still hold
 // lines of the item that used the trace slot before.
+// build-time switches of the traceback (A/B variants, scripts/build_variants.sh), measured on 47 360 cfg3 pairs,
+// GCUPS in FIXED / ASIS mode (profiles/r02_sw_walk_variants.log):
+//   round-1 form (two walks, one load per cell, inlined)            2481 / 2641
+//   SW_ONE_WALK      one walk into a scratch list, reversed into the pool   2528 / 2658   <- default
+//   SW_BATCH_FETCH   eight cells of a run per round trip            1964 / 2276   (with ONE_WALK 2185 / 2289)
+//   SW_WALK_NOINLINE the walk as a real call                        2451 / 2531
+// The packed kernel runs at its 96-register budget: anything that adds live registers or a call frame to the walk
+// changes the register allocation of the fill loop it is inlined into and costs more than the walk takes (7 %).
+#ifndef SW_BATCH_FETCH
+#define SW_BATCH_FETCH 0
+#endif
+#ifndef SW_ONE_WALK
+#define SW_ONE_WALK 1
+#endif
+#ifndef SW_WALK_NOINLINE
+#define SW_WALK_NOINLINE 0
+#endif
+#if SW_WALK_NOINLINE
+#define SW_WALK_ATTR __noinline__
+#else
+#define SW_WALK_ATTR
+#endif
 template <bool COHERENT>
 struct sw_cell_view {
   const uint32_t * tr;
@@ -245,8 +267,15 @@ struct sw_cell_view {
     uint32_t w = COHERENT ? __ldcg (p) : __ldg (p);
     return (w >> sw_shift (c)) & 15u;
   }
+  __device__ __forceinline__ uint32_t nib_or0 (int i, int j) const { return (i >= 1 && j >= 1) ? nib (i, j) : 0u; }
   // status as the CIGAR op the reference would take: 0 = M, 2 = D, 1 = I (the else branch, also for border cells)
   // len = ml / dl / il of that cell (sw.c:221-249)
+  // The run lengths are walked EIGHT cells per round trip: the cells of a run lie on different 128-byte lines of the
+  // trace (one line per DP row), so a walk that loads a nibble, looks at it and only then knows the next address pays
+  // one L2 / HBM latency per cell — 12 000 of them per cfg3 alignment, 7 % of the whole fill + traceback time in the
+  // FIXED mode.  The next seven cells of the same kind of run are loaded together with the first (independent loads,
+  // wasted when the run ends earlier: runs between two sequencing errors are about ten cells long).
+#if !SW_BATCH_FETCH
   __device__ void fetch (int i, int j, uint32_t * op, uint32_t * len) const
   {
     if (i < 1 || j < 1) { *op = 1; *len = 0; return; }
@@ -265,14 +294,72 @@ struct sw_cell_view {
       *op = 1; *len = l;
     }
   }
+#else
+  __device__ void fetch (int i, int j, uint32_t * op, uint32_t * len) const
+  {
+    if (i < 1 || j < 1) { *op = 1; *len = 0; return; }
+    uint32_t w[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) w[u] = nib_or0 (i - u, j - u);          // the cell and the diagonal behind it
+    const uint32_t n = w[0];
+    if (n & 8u) {                              // M: ml = consecutive M cells up the diagonal
+      uint32_t l = 0;
+      for (;;) {
+        int cnt = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (cnt == u && (w[u] & 8u)) ++cnt;
+        l += (uint32_t) cnt;
+        if (cnt < 8) break;
+        i -= 8; j -= 8;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = nib_or0 (i - u, j - u);
+      }
+      *op = 0; *len = l;
+    } else if (n & 4u) {                       // D: dl = 1 + D-extended flags walking up
+      uint32_t l = 0;
+      bool first = true;
+      for (;;) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = (first && u == 0) ? n : ((i - u >= 1) ? nib (i - u, j) : 0u);
+        first = false;
+        int cnt = 0; bool stop = false;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (!stop && i - u >= 1) { ++cnt; if (!(w[u] & 2u)) stop = true; }
+        l += (uint32_t) cnt;
+        if (stop || cnt < 8) break;
+        i -= 8;
+      }
+      *op = 2; *len = l;
+    } else {                                   // I: il = 1 + I-extended flags walking left
+      uint32_t l = 0;
+      bool first = true;
+      for (;;) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = (first && u == 0) ? n : ((j - u >= 1) ? nib (i, j - u) : 0u);
+        first = false;
+        int cnt = 0; bool stop = false;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (!stop && j - u >= 1) { ++cnt; if (!(w[u] & 1u)) stop = true; }
+        l += (uint32_t) cnt;
+        if (stop || cnt < 8) break;
+        j -= 8;
+      }
+      *op = 1; *len = l;
+    }
+  }
+#endif
 };
 
-template <bool WRITE, class VIEW>
+// WRITE 0: count only; 1: write reversed into out[0 .. n_total) (cigar_reverse); 2: write in walking order into out
+// (a scratch list the caller reverses into the pool once the count is known: ONE walk instead of two)
+template <int WRITE, class VIEW>
 __device__ int sw_walk (const VIEW & cv, int mode, int qlen, int tlen, const sw_end & e,
                         uint32_t * out, int n_total, int * align_off, int * softclip)
 {
   int n = 0;
-  auto emit = [&] (uint32_t v) { if (WRITE) out[n_total - 1 - n] = v; ++n; };   // written reversed (cigar_reverse)
+  auto emit = [&] (uint32_t v) { if (WRITE == 1) out[n_total - 1 - n] = v; else if (WRITE == 2) out[n] = v; ++n; };
   int bt_t = e.bt_tidx, bt_q = e.bt_qidx;
   uint32_t seg = (uint32_t) e.seg_len, pre = 0, op = 1, len = 0;
   const int strategy = c_sw.strategy;
@@ -305,33 +392,45 @@ __device__ int sw_walk (const VIEW & cv, int mode, int qlen, int tlen, const sw_
 
 // one alignment: count the CIGAR operations, reserve them in the pool, write them (a reservation that
 // ends beyond pool_cap is left unwritten: the host grows the pool and has the alignment done again)
+// scratch: room for qlen + tlen + 4 operations (every step of the walk consumes at least one row or column), or NULL
 template <bool COHERENT>
-__device__ void sw_emit_cigar (const uint32_t * tr, int qlen, int tlen, int pair, const sw_end & e, int mode,
+__device__ SW_WALK_ATTR void sw_emit_cigar (const uint32_t * tr, int qlen, int tlen, int pair, const sw_end & e, int mode,
                                uint32_t * __restrict__ pool, unsigned long long pool_cap,
-                               unsigned long long * __restrict__ cursor, gcg_sw_result * __restrict__ results)
+                               unsigned long long * __restrict__ cursor, gcg_sw_result * __restrict__ results,
+                               uint32_t * __restrict__ scratch)
 {
   sw_cell_view<COHERENT> cv;
   cv.tr = tr;
   cv.nsteps = tlen + 31;
   int off = 0, sc = 0;
-  int n = sw_walk<false> (cv, mode, qlen, tlen, e, nullptr, 0, &off, &sc);
+#if !SW_ONE_WALK
+  scratch = nullptr;
+#endif
+  const int n = scratch ? sw_walk<2> (cv, mode, qlen, tlen, e, scratch, 0, &off, &sc)
+                        : sw_walk<0> (cv, mode, qlen, tlen, e, nullptr, 0, &off, &sc);
   unsigned long long at = atomicAdd (cursor, (unsigned long long) n);
   gcg_sw_result r;
   r.score = e.score; r.alignment_offset = off; r.has_softclip = sc;
   r.bt_tidx = e.bt_tidx; r.bt_qidx = e.bt_qidx; r.n_cigar = n; r.cigar_off = (long long) at;
   results[pair] = r;
-  if (at + (unsigned long long) n <= pool_cap) sw_walk<true> (cv, mode, qlen, tlen, e, pool + at, n, &off, &sc);
+  if (at + (unsigned long long) n <= pool_cap) {
+    if (scratch) {                                  // the list in walking order -> the pool in CIGAR order
+      for (int i = 0; i < n; ++i) pool[at + (unsigned long long) (n - 1 - i)] = COHERENT ? __ldcg (scratch + i) : scratch[i];
+    } else sw_walk<1> (cv, mode, qlen, tlen, e, pool + at, n, &off, &sc);
+  }
 }
 
 __global__ void __launch_bounds__ (128)
 sw_cigar_kernel (const sw_task * __restrict__ tasks, int n_tasks, const uint32_t * __restrict__ trace,
                  const sw_end * __restrict__ ends, int mode, uint32_t * __restrict__ pool, unsigned long long pool_cap,
-                 unsigned long long * __restrict__ cursor, gcg_sw_result * __restrict__ results)
+                 unsigned long long * __restrict__ cursor, gcg_sw_result * __restrict__ results, uint32_t * __restrict__ ops)
 {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_tasks) return;
   const sw_task tk = tasks[idx];
-  sw_emit_cigar<false> (trace + tk.trace_off, tk.qlen, tk.tlen, tk.pair, ends[tk.pair], mode, pool, pool_cap, cursor, results);
+  // (scratch list of a pair: behind its edge scores' offset, four more words per pair)
+  sw_emit_cigar<false> (trace + tk.trace_off, tk.qlen, tk.tlen, tk.pair, ends[tk.pair], mode, pool, pool_cap, cursor, results,
+                        ops ? ops + tk.edge_off + 4LL * tk.pair : nullptr);
 }
 
 
@@ -387,7 +486,8 @@ __device__ __forceinline__ sw_task ld_task (const sw_task * p)
 }
 
 struct sw_packed_consts { uint32_t pk_do, pk_io, pk_de32, pk_ie32, one; };
-struct sw_cigar_args { int mode; uint32_t * pool; unsigned long long pool_cap; unsigned long long * cursor; gcg_sw_result * results; };
+struct sw_cigar_args { int mode; uint32_t * pool; unsigned long long pool_cap; unsigned long long * cursor; gcg_sw_result * results;
+                       uint32_t * ops; unsigned long long ops_stride; };     // packed kernel: one scratch list per (block, walking lane)
 
 template <int MINB>
 __global__ void __launch_bounds__ (32, MINB)
@@ -605,8 +705,9 @@ sw_fill_packed_kernel (const uint8_t * __restrict__ qry, const uint8_t * __restr
       sw_end eb = ea;
       if (has_b) eb = sw_pick_end (edges + tb.edge_off, tb.qlen, tb.tlen, lane, ends + tb.pair);
       __syncwarp ();                                 // the trace stores of all lanes are visible to the walkers
-      if (lane == 0) sw_emit_cigar<true> (trace + ta.trace_off, ta.qlen, ta.tlen, ta.pair, ea, cg.mode, cg.pool, cg.pool_cap, cg.cursor, cg.results);
-      if (lane == 1 && has_b) sw_emit_cigar<true> (trace + tb.trace_off, tb.qlen, tb.tlen, tb.pair, eb, cg.mode, cg.pool, cg.pool_cap, cg.cursor, cg.results);
+      uint32_t * const ops = cg.ops ? cg.ops + ((size_t) blockIdx.x * 2 + (size_t) lane) * cg.ops_stride : nullptr;
+      if (lane == 0) sw_emit_cigar<true> (trace + ta.trace_off, ta.qlen, ta.tlen, ta.pair, ea, cg.mode, cg.pool, cg.pool_cap, cg.cursor, cg.results, ops);
+      if (lane == 1 && has_b) sw_emit_cigar<true> (trace + tb.trace_off, tb.qlen, tb.tlen, tb.pair, eb, cg.mode, cg.pool, cg.pool_cap, cg.cursor, cg.results, ops);
     }
     __syncwarp ();                                   // the slot is rewritten by the next item only after the walks
   }
@@ -671,7 +772,7 @@ struct sw_devbuf {
 
 struct gcg_swbatch {
   gcg_ctx * ctx = nullptr;
-  sw_devbuf s_trace, s_edges, s_tasks, s_wave_tasks, s_items, s_counter, s_bound, s_pbound;
+  sw_devbuf s_trace, s_edges, s_tasks, s_wave_tasks, s_items, s_counter, s_bound, s_pbound, s_ops, s_gops;
   int64_t n = 0;
   std::vector<long long> qoff, toff;
   uint8_t * d_qry = nullptr, * d_tgt = nullptr;
@@ -696,6 +797,7 @@ extern "C" void gcg_swbatch_free (gcg_swbatch * b)
   gcg_dfree (ctx, b->d_results); gcg_dfree (ctx, b->d_ends); gcg_dfree (ctx, b->d_pool);
   b->s_trace.release (ctx); b->s_edges.release (ctx); b->s_tasks.release (ctx); b->s_wave_tasks.release (ctx);
   b->s_items.release (ctx); b->s_counter.release (ctx); b->s_bound.release (ctx); b->s_pbound.release (ctx);
+  b->s_ops.release (ctx); b->s_gops.release (ctx);
   delete b;
 }
 
@@ -997,7 +1099,8 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
       (ce = b->s_wave_tasks.reserve (ctx, (size_t) n * sizeof (sw_task))) != cudaSuccess ||
       (ce = b->s_items.reserve (ctx, (size_t) n * 8)) != cudaSuccess ||
       (ce = b->s_counter.reserve (ctx, 2 * sizeof (int))) != cudaSuccess ||
-      (generic_ids.size () && (ce = b->s_bound.reserve (ctx, (size_t) gen_blocks * 4 * (size_t) bound_stride * sizeof (int2))) != cudaSuccess)) {
+      (generic_ids.size () && (ce = b->s_bound.reserve (ctx, (size_t) gen_blocks * 4 * (size_t) bound_stride * sizeof (int2))) != cudaSuccess) ||
+      (generic_ids.size () && (ce = b->s_gops.reserve (ctx, (size_t) (total_edges + 4 * n + 8) * 4)) != cudaSuccess)) {
     gcg_set_error ("gcg_swbatch_align: cudaMalloc failed: %s", cudaGetErrorString (ce));
     rc = GCG_ENOMEM;
   }
@@ -1042,6 +1145,11 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
     if ((ce = b->s_pbound.reserve (ctx, (size_t) grid * packed_rows_cap * sizeof (uint2))) != cudaSuccess) {
       gcg_set_error ("gcg_swbatch_align: boundary scratch: %s", cudaGetErrorString (ce)); rc = GCG_ENOMEM; break; }
     d_pbound = (uint2 *) b->s_pbound.p;
+    // one scratch list of CIGAR operations per walking lane (two per warp): the traceback is walked once
+    unsigned long long ops_stride = 8;
+    for (int id : packed_ids) ops_stride = std::max<unsigned long long> (ops_stride, (unsigned long long) tasks[(size_t) id].qlen + tasks[(size_t) id].tlen + 4);
+    if ((ce = b->s_ops.reserve (ctx, (size_t) grid * 2 * ops_stride * 4)) != cudaSuccess) {
+      gcg_set_error ("gcg_swbatch_align: traceback scratch: %s", cudaGetErrorString (ce)); rc = GCG_ENOMEM; break; }
     GCG_CUDA (cudaMemcpyAsync (d_tasks, tasks.data (), (size_t) n * sizeof (sw_task), cudaMemcpyHostToDevice, ctx->stream));
     GCG_CUDA (cudaMemcpyAsync (d_items, pitems.data (), pitems.size () * sizeof (int2), cudaMemcpyHostToDevice, ctx->stream));
     GCG_CUDA (cudaMemsetAsync (d_counter, 0, 2 * sizeof (int), ctx->stream));
@@ -1049,7 +1157,7 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
       sw_packed_fn ()<<<grid, 32, (size_t) packed_rows_cap * 2, ctx->stream>>> (
           b->d_qry, b->d_tgt, d_tasks, (const int2 *) d_items, (int) pitems.size (), d_counter, d_trace, slot_words, d_edges, d_pbound,
           packed_rows_cap, b->d_ends, sw_packed_consts {hc.pk_do, hc.pk_io, hc.pk_de32, hc.pk_ie32, 1u},
-          sw_cigar_args {mode, b->d_pool, b->pool_cap, d_cursor, b->d_results});
+          sw_cigar_args {mode, b->d_pool, b->pool_cap, d_cursor, b->d_results, (uint32_t *) b->s_ops.p, ops_stride});
       GCG_CUDA (cudaGetLastError ()); }
     GCG_CUDA (cudaMemcpyAsync (ctx->h_counters + 10, d_cursor, 8, cudaMemcpyDeviceToHost, ctx->stream));
     GCG_CUDA (cudaStreamSynchronize (ctx->stream));
@@ -1128,7 +1236,7 @@ extern "C" int gcg_swbatch_align (gcg_ctx * ctx, gcg_swbatch * b, const gcg_sw_p
     for (int attempt = 0; attempt < 3 && !rc; ++attempt) {
       { gcg_kscope ks (ctx, "k9_sw_cigar");
         int nt = (int) wave_tasks.size ();
-        sw_cigar_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>> (d_wave_tasks, nt, d_trace, b->d_ends, mode, b->d_pool, b->pool_cap, d_cursor, b->d_results); }
+        sw_cigar_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>> (d_wave_tasks, nt, d_trace, b->d_ends, mode, b->d_pool, b->pool_cap, d_cursor, b->d_results, (uint32_t *) b->s_gops.p); }
       GCG_CUDA (cudaGetLastError ());
       GCG_CUDA (cudaMemcpyAsync (ctx->h_counters + 10, d_cursor, 8, cudaMemcpyDeviceToHost, ctx->stream));
       GCG_CUDA (cudaStreamSynchronize (ctx->stream));
