@@ -571,6 +571,27 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     e2e_packed_s = allmax(time.perf_counter() - t0) / e2e_steps
     assert p_hits == n_hit and p_st == st, "packed-input and ASCII-input paths disagree"
+
+    # both together — what gc_b200 does with GC_RUNS=1: packed reads up (8 bytes per 32 bases), run records down
+    def e2e_runs_packed():
+        h = C.c_void_p()
+        ctx._chk(ctx.L.gcg_table_build(ctx.h, C.cast(cptrs, C.c_void_p), clens.ctypes.data, len(carrs), K, C.byref(h)))
+        tab = api.KmerTable(ctx, h, K)
+        rp, op, nr, na = C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
+        ctx._chk(ctx.L.gcg_search_runs_packed(ctx.h, tab.h, pk_words.ctypes.data, pk_woff.ctypes.data, pk_lens.ctypes.data, len(arrs), K, C.byref(rp), C.byref(op), C.byref(nr), C.byref(na)))
+        ctx.L.gcg_free(rp); ctx.L.gcg_free(op)
+        s4 = tab.stats()
+        tab.free()
+        return na.value, nr.value, s4
+
+    e2e_runs_packed()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rp_hits, rp_runs, rp_st = e2e_runs_packed()
+    barrier()
+    e2e_runs_packed_s = allmax(time.perf_counter() - t0) / e2e_steps
+    assert rp_hits == n_hit and rp_st == st, "run-record (packed input) and anchor paths disagree"
     pk_keep.free()
 
     e2e_runs()
@@ -664,6 +685,10 @@ def run_ours(args, rank, local_rank, world):
                        "h2d_bytes_per_step": int(sum((len(r) + 31) // 32 * 8 for r in reads) + 12 * len(reads) + read_bytes // 256 + ctg_bytes),
                        "d2h_bytes_per_step": int(n_hit * 8 + 8 * (len(reads) + 1) + 32),
                        "api": "gcg_table_build + gcg_search_compact_packed + gcg_table_stats: the reads as the B200 build's FASTQ loader leaves them (2-bit words in page-locked host memory, packed once on ingest — rseq_fast.c); no host pass over the bases inside the step"},
+        "e2e_runs_packed": {"value": tot_ont_kmers / e2e_runs_packed_s, "unit": "k-mers/s", "ms_per_step": e2e_runs_packed_s * 1e3,
+                            "h2d_bytes_per_step": int(sum((len(r) + 31) // 32 * 8 for r in reads) + 12 * len(reads) + read_bytes // 256 + ctg_bytes),
+                            "d2h_bytes_per_step": int(rp_runs * 48 + 16 * (len(reads) + 1) + 32),
+                            "api": "gcg_table_build + gcg_search_runs_packed + gcg_table_stats: what gc_b200 does with GC_RUNS=1 — the loader's 2-bit words up, run records down"},
         "e2e_runs": {"value": tot_ont_kmers / e2e_runs_s, "unit": "k-mers/s", "ms_per_step": e2e_runs_s * 1e3, "runs_per_gpu": int(r_runs),
                      "d2h_bytes_per_step": int(r_runs * 48 + 16 * (len(reads) + 1) + 32),
                      "api": "gcg_table_build + gcg_search_runs (N3, opt-in GC_RUNS mode of the shim: anchors reduced on the device to the run records of map_ont2contigs, ctg_graph.c:600-656) + gcg_table_stats"},

@@ -2439,10 +2439,20 @@ extern "C" int gcg_chop_contigs (gcg_ctx * ctx, const gcg_seqs * contigs, int k,
         contigs->d_packed, contigs->d_woff, contigs->d_len, d_koff, n, contigs->n_words, k, (uint32_t) n_thread, d_rec);
     GCG_CUDA (cudaGetLastError ());
   }
-  GCG_CUDA (cudaStreamSynchronize (ctx->stream));
-  for (int64_t i = 0; i < n; ++i)
-    if (n_kmer_out[i] > 0)
-      GCG_CUDA (cudaMemcpy (kmers_out[i], d_rec + koff[(size_t) i], (size_t) n_kmer_out[i] * sizeof (kmer_rec), cudaMemcpyDeviceToHost));
+  // One download of all records into a pinned block (a blocking cudaMemcpy per contig into pageable memory costs tens
+  // of microseconds each: seconds for an assembly of 10^5 - 10^6 contigs), then the host threads scatter them into
+  // the callers' per-contig arrays.
+  kmer_rec * h_rec = (kmer_rec *) gcg_pinned_alloc ((size_t) tot * sizeof (kmer_rec));
+  if (h_rec == nullptr) { gcg_dfree (ctx, d_koff); gcg_dfree (ctx, d_rec); gcg_set_error ("gcg_chop_contigs: pinned alloc of %lld records failed", (long long) tot); return GCG_ENOMEM; }
+  cudaError_t ce = cudaMemcpyAsync (h_rec, d_rec, (size_t) tot * sizeof (kmer_rec), cudaMemcpyDeviceToHost, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize (ctx->stream);
   gcg_dfree (ctx, d_koff); gcg_dfree (ctx, d_rec);
+  if (ce != cudaSuccess) { gcg_free (h_rec); gcg_set_error ("gcg_chop_contigs: %s", cudaGetErrorString (ce)); return GCG_ECUDA; }
+  const int64_t n_task = std::min<int64_t> (n, std::max<int64_t> (1, 8 * (int64_t) ctx->host_threads));
+  gcg_workers_run (gcg_ctx_workers (ctx), n_task, [&] (int64_t tk) {
+    for (int64_t i = n * tk / n_task; i < n * (tk + 1) / n_task; ++i)
+      if (n_kmer_out[i] > 0) memcpy (kmers_out[i], h_rec + koff[(size_t) i], (size_t) n_kmer_out[i] * sizeof (kmer_rec));
+  });
+  gcg_free (h_rec);
   return GCG_OK;
 }
