@@ -30,11 +30,14 @@ def run(exe, fa, fq, threads, wd, env=None, as_limit_gb=None):
         # the reference must fail with an allocation error, not take the box down, if it needs more than the host has
         import resource
         resource.setrlimit(resource.RLIMIT_AS, (int(as_limit_gb * 2**30), int(as_limit_gb * 2**30)))
+    import resource
+    ru0 = resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss
     r = subprocess.run([exe, fa, fq, str(threads), "out"], cwd=wd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env,
                        preexec_fn=limit if as_limit_gb else None)
     dt = time.time() - t0
+    ru1 = resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss
     out = r.stdout.decode(errors="replace")
-    res = {"rc": r.returncode, "wall_s": dt, "stats": [int(x) for x in re.findall(r"(?:total|unique) kmer count: (\d+)", out)],
+    res = {"rc": r.returncode, "wall_s": dt, "max_rss_gb_of_children_so_far": round(ru1 / 2**20, 1), "max_rss_gb_before": round(ru0 / 2**20, 1), "stats": [int(x) for x in re.findall(r"(?:total|unique) kmer count: (\d+)", out)],
            "phase_lines": [l.strip() for l in out.splitlines() if "cost" in l.lower()],
            "stderr_tail": r.stderr.decode(errors="replace")[-3000:]}
     if r.returncode == 0:
@@ -52,6 +55,8 @@ def main():
     ap.add_argument("--workdir", default="/tmp/gc_full")
     ap.add_argument("--skip-ref", action="store_true")
     ap.add_argument("--skip-b200", action="store_true")
+    ap.add_argument("--runs-first", action="store_true", help="run gc_b200 with GC_RUNS=1 first (its peak memory is then the first child's)")
+    ap.add_argument("--golden", default=None, help="compare with this entry of tests/golden/gc_e2e.json instead of running the reference")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     info = {"config": a.cfg, "params": synth.CONFIGS[a.cfg], "threads": a.threads, "host_cores": os.cpu_count(),
@@ -76,7 +81,19 @@ def main():
     del inp
     gc.collect()
     print("generated in %.0f s" % info["generate_s"], flush=True)
-    if not a.skip_ref:
+    if a.golden:
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", "gc_e2e.json")))[a.golden]
+        info["reference"] = dict(g, rc=0, wall_s=None, source="tests/golden/gc_e2e.json (the reference's own run, profiles/r02_cli_cfg5_full.json)")
+    if a.runs_first and not a.skip_b200:
+        env = dict(os.environ, GCG_TRACE="1", GC_RUNS="1")
+        info["gc_b200_runs"] = run(os.path.join(ROOT, "superplus_b200", "_build", "gc_b200"), fa, fq, a.threads, os.path.join(a.workdir, "b200r"), env)
+        print("gc_b200 GC_RUNS=1", {k: v for k, v in info["gc_b200_runs"].items() if k != "stderr_tail"}, flush=True)
+        print(info["gc_b200_runs"]["stderr_tail"][-1200:])
+        r, g = info.get("reference"), info["gc_b200_runs"]
+        if r:
+            info["runs_identical"] = bool(g["rc"] == 0 and all(r.get(k) == g.get(k) for k in ("fa", "link", "valid", "stats")))
+            print("GC_RUNS=1:", "IDENTICAL" if info["runs_identical"] else "DIFFERENT", flush=True)
+    if not a.skip_ref and not a.golden:
         info["reference"] = run(os.path.join(ROOT, "oracle", "_ref", "gc"), fa, fq, a.threads, os.path.join(a.workdir, "ref"), as_limit_gb=0.85 * info["host_mem_gb"])
         print("reference", {k: v for k, v in info["reference"].items() if k != "stderr_tail"}, flush=True)
     if not a.skip_b200:
@@ -90,7 +107,7 @@ def main():
     if "reference" in info and "gc_b200" in info:
         r, g = info["reference"], info["gc_b200"]
         info["identical"] = bool(r["rc"] == 0 and g["rc"] == 0 and all(r.get(k) == g.get(k) for k in ("fa", "link", "valid", "stats")))
-        info["speedup_wall"] = r["wall_s"] / g["wall_s"] if g["wall_s"] else None
+        info["speedup_wall"] = r["wall_s"] / g["wall_s"] if (g["wall_s"] and r.get("wall_s")) else None
         print("IDENTICAL" if info["identical"] else "DIFFERENT", "speed-up %.2fx" % (info["speedup_wall"] or 0), flush=True)
     out = a.out or os.path.join(ROOT, "gpurun_out", "cli_%s.json" % a.cfg)
     os.makedirs(os.path.dirname(out), exist_ok=True)
