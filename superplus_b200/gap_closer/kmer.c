@@ -115,6 +115,16 @@ kmer_set_dump (xh_t * khash, int kmer_len)
   free (kmer_seq); free (key); free (multi); free (tid); free (pos); free (rev);
 }
 
+/* The handles returned by kmer_hash_init are empty host tables: the contig k-mers live in HBM.  Unchanged reference
+ * code that probes them on the host (lfr.c ankor_lfr_reads -> _xh_set_search3; disabled in the reference's main.c) would
+ * silently find nothing — so their hash function aborts instead. */
+static uint64_t
+device_table_hash_func (const void * key)
+{
+  err_mesg ("[kmer] the contig k-mer tables of this build live in GPU memory: host-side probes of ctg_khashs (lfr.c) are not supported");
+  return 0;
+}
+
 xh_t **
 kmer_hash_init (int n_thread)
 {
@@ -123,7 +133,7 @@ kmer_hash_init (int n_thread)
 
   khashs = (xh_t **) ckalloc (n_thread, sizeof (xh_t *));
   for (i = 0; i < n_thread; ++i)
-    khashs[i] = _xh_init (256, 0.75, kmer_hash_func, kmer_is_equal);
+    khashs[i] = _xh_init (256, 0.75, device_table_hash_func, kmer_is_equal);
   /* the tables live in HBM; start opening the device now, in the background, while the unchanged
    * loaders read the scaffolds and the ONT reads (main.c:149-156) */
   gcg_bridge_warmup ();
