@@ -320,7 +320,7 @@ def run_ours(args, rank, local_rank, world):
         from superplus_b200 import dist as gdist
         ops = gdist.DeviceOps(ctx, local_rank)
         comm = gdist.TorchComm(ops.device) if dist is not None else gdist.ThreadComm(gdist.ThreadGroup(1), 0, ops.device, ops.sync)
-        for exchange in ("direct", "all_to_all"):
+        for exchange in ("remote", "direct", "all_to_all"):
             # one index per exchange mode; every step rebuilds its table from the packed contigs (as the
             # replicated leg does) while the exchange windows of the direct mode stay mapped
             idx = gdist.PartitionedKmerIndex(ops, comm, K, exchange=exchange)
@@ -377,7 +377,7 @@ def run_ours(args, rank, local_rank, world):
         cs4, rs4 = ctx.upload([genome4]), ctx.upload(reads4)
         sample = reads4[:48]
         ss4 = ctx.upload(sample)
-        idx4 = gdist.PartitionedKmerIndex(ops4, comm4, K4, exchange="direct")
+        idx4 = gdist.PartitionedKmerIndex(ops4, comm4, K4, exchange=args.cfg4_exchange)
         idx4.build(cs4)
         got = idx4.search(ss4)                                  # the sample's anchors (collective: every rank searches its own sample)
         st_after_sample = idx4.stats()
@@ -428,8 +428,8 @@ def run_ours(args, rank, local_rank, world):
             except ImportError:
                 pass
         cfg4 = {"metric": "kmers_per_s", "value": tot4 / (search4_ms * 1e-3), "unit": "k-mers/s", "ms_per_search": search4_ms, "build_ms": build4_ms,
-                "config": {"workload": "BASELINE configs[3]: %d Mb synthetic genome, k=31, %.0fx ONT in total (%.2fx = %d reads per GPU), contig table hash-partitioned over %d GPU(s), direct exchange over NVLink peer memory" %
-                           (G4 // 1_000_000, c4["coverage"], c4["coverage"] / world, len(reads4), world),
+                "config": {"workload": "BASELINE configs[3]: %d Mb synthetic genome, k=31, %.0fx ONT in total (%.2fx = %d reads per GPU), contig table hash-partitioned over %d GPU(s), exchange '%s' (remote = one search kernel per rank probing the owners' partitions over NVLink peer memory)" %
+                           (G4 // 1_000_000, c4["coverage"], c4["coverage"] / world, len(reads4), world, args.cfg4_exchange),
                            "ont_kmers_total": int(tot4), "anchors_total": int(hits4), "stats": list(idx4.stats())},
                 "nvlink_bytes_per_search": nv4, "routed_fraction": routed4, "check": check,
                 "kernel_ms_per_search": {k_: v[0] / c4_steps for k_, v in sorted(prof4.items())}}
@@ -743,13 +743,14 @@ def run_ours(args, rank, local_rank, world):
         except Exception as e:      # the baseline must never sink the bench line
             line["cpu_baseline"] = {"value": None, "unit": "k-mers/s", "cores": cores, "kind": "reference", "sample": "failed: %r" % (e,)}
     for exchange, pr in part.items():
-        line["partitioned" if exchange == "direct" else "partitioned_all_to_all"] = {
+        line[{"remote": "partitioned", "direct": "partitioned_direct", "all_to_all": "partitioned_all_to_all"}[exchange]] = {
             "metric": "kmers_per_s", "value": tot_ont_kmers / (pr["ms_per_step"] * 1e-3), "unit": "k-mers/s", "ms_per_step": pr["ms_per_step"],
-            "config": {"workload": "same step with the contig table hash-partitioned over %d GPU(s): route by owner, owner-side insert / lookup, ordered collect" % world,
-                       "exchange": ("keys (8 B per ONT k-mer) stored by the routing kernel straight into the owner's window and answers (8 B) by the lookup kernel straight into the requester's window over NVLink peer memory (CUDA IPC); two barriers per round, no collective on the data path"
-                                    if exchange == "direct" else "send / receive buffers and NCCL all_to_all_single (8 B key out, 8 B answer back per ONT k-mer)") if world > 1 else "single partition, nothing crosses a link"},
+            "config": {"workload": "same step with the contig table hash-partitioned over %d GPU(s)" % world,
+                       "exchange": ({"remote": "remote probes: the partitions stay where their owners built them (CUDA-IPC mapped blocks) and ONE search kernel per rank reads them where they lie — bucket loads and the anchors' atomicOr over NVLink peer memory, after a replicated union filter; no routing, no exchange buffers, no collective on the data path",
+                                     "direct": "route by owner, owner-side lookup, ordered collect: keys (8 B per ONT k-mer) stored by the routing kernel straight into the owner's window and answers (8 B) by the lookup kernel straight into the requester's window over NVLink peer memory (CUDA IPC); two stream-ordered barriers per round",
+                                     "all_to_all": "route by owner, owner-side lookup, ordered collect through send / receive buffers and NCCL all_to_all_single (8 B key out, 8 B answer back per ONT k-mer)"}[exchange]) if world > 1 else "single partition, nothing crosses a link"},
             "nvlink_bytes_per_step": pr["bytes_sent_per_step"], "stats": pr["stats"], "kernel_ms_per_step": pr["kernel_ms_per_step"],
-            "prefilter": "union of the partitions' anchoring keys (blocked Bloom filter, all-gathered after the build): %.1f %% of the ONT k-mers are routed" % (100.0 * pr["routed_fraction"])}
+            "prefilter": "union of the partitions' anchoring keys (blocked Bloom filter, all-gathered after the build)" + ("" if exchange == "remote" else ": %.1f %% of the ONT k-mers are routed" % (100.0 * pr["routed_fraction"]))}
         line["gpu_launches"] += int(pr["launches"])
     print(json.dumps(line))
     if dist is not None:
@@ -765,6 +766,7 @@ def main():
     ap.add_argument("--sw-pairs", type=int, default=47360, help="pairs per GPU per step of the cfg3 leg (16 items per resident warp)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cfg4", default="auto", choices=["auto", "on", "off"], help="BASELINE configs[3] at full size on the partitioned table (auto: at 8 GPUs)")
+    ap.add_argument("--cfg4-exchange", default="remote", choices=["remote", "direct", "all_to_all"])
     ap.add_argument("--cfg4-genome", type=int, default=0, help="genome length of that leg (default: 100 Mb, the config's)")
     ap.add_argument("--no-hbm-table", action="store_true", help="skip the second k-mer roofline leg (100 Mb table beyond the L2, N=1 only)")
     ap.add_argument("--hbm-coverage", type=float, default=2.0, help="ONT coverage of the 100 Mb genome in that leg")

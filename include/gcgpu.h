@@ -254,6 +254,23 @@ int  gcg_table_lookup_keys (gcg_ctx * ctx, gcg_table * t, const void * d_keys, i
 int  gcg_route_collect (gcg_ctx * ctx, gcg_route * r, const void * d_answers, gcg_hits ** out);
 void gcg_route_free (gcg_route * r);
 
+/* Remote probes (round 2): the partitions stay where their owners built them and the ONE search kernel of the
+ * single-GPU path reads them where they lie — a k-mer that passes the union filter loads its bucket from the owner's
+ * key array over NVLink / NVSwitch peer memory, an anchor's atomicOr travels to the owner's value array (which thereby
+ * counts the hits of every rank, ont.c:245) and returns (tid, pos, flag).  No routing, no exchange buffers, no
+ * collective on the data path.
+ *   gcg_table_create_shared : an owner-side partition whose arrays live in one cudaMalloc block peers can map
+ *   gcg_table_reset_shared  : empty it for a rebuild of about the same size (peers keep their mapping)
+ *   gcg_table_shared_info   : block pointer (same process) / 64-byte IPC handle (another process: gcg_window_open),
+ *                             offset of the value array inside the block, bucket count
+ *   gcg_search_seqs_remote  : d_keys[p] / d_vals[p] = partition p's arrays as this context addresses them; the filter
+ *                             is the union filter of gcg_filter_add_table / gcg_filter_or.  Anchors as gcg_hit records. */
+int  gcg_table_create_shared (gcg_ctx * ctx, int64_t n_records, int k, gcg_table ** out);
+int  gcg_table_reset_shared (gcg_ctx * ctx, gcg_table * t, int64_t n_records);
+int  gcg_table_shared_info (gcg_table * t, void ** d_block, int64_t * vals_offset_bytes, uint32_t * n_bucket, void * ipc_handle64);
+int  gcg_search_seqs_remote (gcg_ctx * ctx, const gcg_seqs * reads, int k, int n_part, const void * const * d_keys, void * const * d_vals,
+                             const uint32_t * n_bucket, const void * d_filter, int64_t filter_words, int filter_k3, gcg_hits ** out);
+
 /* Direct exchange over NVLink / NVSwitch peer memory (no staging buffer, no collective on the
  * data path): every rank owns two WINDOWS — plain device allocations that the other ranks map
  * (CUDA IPC between processes, peer access inside one process).  The routing kernel stores each

@@ -33,6 +33,7 @@ EXPORTS = [
     "gcg_table_size", "gcg_table_dump", "gcg_table_clone", "gcg_table_merge_ont",
     "gcg_search_seqs", "gcg_hits_count", "gcg_hits_download", "gcg_hits_free", "gcg_search", "gcg_free",
     "gcg_search_compact", "gcg_search_seqs_compact", "gcg_hits_download_compact", "gcg_selftest_workers", "gcg_host_alloc", "gcg_search_runs", "gcg_search_compact_packed", "gcg_search_runs_packed",
+    "gcg_table_create_shared", "gcg_table_reset_shared", "gcg_table_shared_info", "gcg_search_seqs_remote",
     "gcg_sw_batch", "gcg_sw_batch_multi", "gcg_swbatch_upload", "gcg_swbatch_align", "gcg_swbatch_download", "gcg_swbatch_cells",
     "gcg_swbatch_path_counts", "gcg_swbatch_free",
     "gcg_kmer_owner", "gcg_seqs_tiles", "gcg_route_plan", "gcg_route_kmers", "gcg_route_keys", "gcg_route_records",
@@ -154,6 +155,10 @@ def load_library(path: str = LIB_PATH):
     L.gcg_search_runs.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
     L.gcg_search_compact_packed.argtypes = [vp, vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
     L.gcg_search_runs_packed.argtypes = [vp, vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
+    L.gcg_table_create_shared.argtypes = [vp, i64, C.c_int, C.POINTER(vp)]
+    L.gcg_table_reset_shared.argtypes = [vp, vp, i64]
+    L.gcg_table_shared_info.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_uint32), vp]
+    L.gcg_search_seqs_remote.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp)]
     L.gcg_host_alloc.restype = vp
     L.gcg_host_alloc.argtypes = [i64]
     L.gcg_search_compact.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
@@ -480,6 +485,24 @@ class Context:
     def window_close(self, ptr: int):
         self._chk(self.L.gcg_window_close(self.h, C.c_void_p(ptr)))
 
+    def table_create_shared(self, n_records: int, k: int) -> "KmerTable":
+        """owner-side partition in one cudaMalloc block that peer GPUs map and probe over NVLink"""
+        h = C.c_void_p()
+        self._chk(self.L.gcg_table_create_shared(self.h, int(n_records), k, C.byref(h)))
+        return KmerTable(self, h, k)
+
+    def search_remote(self, reads: "Seqs", k: int, key_ptrs, val_ptrs, n_buckets, filter_ptr: int, filter_words: int, filter_k3: int) -> "Hits":
+        """one search kernel that probes the partitions of a hash-partitioned table where they lie (gcg_search_seqs_remote)"""
+        n = len(key_ptrs)
+        kp = (C.c_void_p * MAX_PART)(*[C.c_void_p(int(p)) for p in key_ptrs])
+        vp_ = (C.c_void_p * MAX_PART)(*[C.c_void_p(int(p)) for p in val_ptrs])
+        nb = np.zeros(MAX_PART, dtype=np.uint32)
+        nb[:n] = n_buckets
+        h = C.c_void_p()
+        self._chk(self.L.gcg_search_seqs_remote(self.h, reads.h, k, n, C.cast(kp, C.c_void_p), C.cast(vp_, C.c_void_p), nb.ctypes.data,
+                                                C.c_void_p(int(filter_ptr)), int(filter_words), int(filter_k3), C.byref(h)))
+        return Hits(self, h)
+
     def table_create(self, n_records: int, k: int) -> "KmerTable":
         h = C.c_void_p()
         self._chk(self.L.gcg_table_create(self.h, int(n_records), k, C.byref(h)))
@@ -664,6 +687,21 @@ class KmerTable(_Handle):
     def merge_ont(self, replica: "KmerTable"):
         """fold the ONT-side multiplicity collected by a replica into this table (stats over all reads)"""
         self.ctx._chk(self.ctx.L.gcg_table_merge_ont(self.ctx.h, self.h, replica.h))
+
+    def reset_shared(self, n_records: int) -> bool:
+        """empty a shared partition for a rebuild; False when its block is too small (create a new one)"""
+        rc = self.ctx.L.gcg_table_reset_shared(self.ctx.h, self.h, int(n_records))
+        if rc == -4:            # GCG_ERANGE
+            return False
+        self.ctx._chk(rc)
+        return True
+
+    def shared_info(self):
+        """-> (block pointer, byte offset of the value array, bucket count, 64-byte IPC handle)"""
+        p, off, nb = C.c_void_p(), C.c_int64(), C.c_uint32()
+        buf = C.create_string_buffer(64)
+        self.ctx._chk(self.ctx.L.gcg_table_shared_info(self.h, C.byref(p), C.byref(off), C.byref(nb), buf))
+        return int(p.value), int(off.value), int(nb.value), buf.raw
 
     def insert_records(self, d_records: int, n: int):
         self.ctx._chk(self.ctx.L.gcg_table_insert_records(self.ctx.h, self.h, d_records, int(n)))

@@ -152,6 +152,13 @@ struct gcg_table {
   // first base of every contig in the concatenated scaffold coordinate (compact anchors); NULL for an owner-side partition
   int64_t * d_cbase = nullptr;
   int64_t n_contig = 0, n_cbases = 0;
+  // an owner-side partition whose arrays live in ONE cudaMalloc block (keys, then values) that peer GPUs map and probe
+  // over NVLink (gcg_table_create_shared); NULL when the arrays come from the context's block cache
+  void * shared_block = nullptr;
+  uint64_t shared_cap_slots = 0;           // slots the block has room for (a rebuild of the same size reuses it: peers keep their mapping)
+  // a VIEW of a partitioned table for the remote-probe search: no arrays of its own, n_part descriptors on the device
+  const struct gcg_part_desc * d_parts = nullptr;
+  int n_part = 0;
 };
 
 struct gcg_hits {

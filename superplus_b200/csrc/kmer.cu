@@ -150,13 +150,16 @@ k23_build_kernel (const uint64_t * __restrict__ packed, const int64_t * __restri
 // receive the word's read index and its first position (undefined for words past the end).
 struct k4_smem { uint32_t excl[K4_WARPS][33], pend[K4_WARPS][32], add[K4_WARPS][32]; };
 
-template <bool FILTER, int KC, bool PF>
+// PART (remote-probe search of a hash-partitioned table): the key's owner partition picks the arrays — a peer GPU's,
+// reached over NVLink — and the bucket count; only probes that pass the (local, replicated) union filter leave the GPU
+template <bool FILTER, int KC, bool PF, bool PART = false>
 __device__ __forceinline__ uint32_t
 k4_probe_tile (k4_smem & sm, const unsigned long long * __restrict__ vals, const int64_t tile, const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff,
                const int32_t * __restrict__ len, const int32_t * __restrict__ tile_seq, const int64_t n_seq, const int64_t n_words, const int k,
                const unsigned long long * __restrict__ keys, const uint32_t n_bucket,
                const uint32_t * __restrict__ filter, const uint32_t filter_words, const int filter_k3,
-               uint64_t * pk_out, int32_t * seq_out, int32_t * p0_out)
+               uint64_t * pk_out, int32_t * seq_out, int32_t * p0_out,
+               const gcg_part_desc * __restrict__ parts = nullptr, const uint32_t n_part = 1)
 {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t w = (tile << 5) + lane;
@@ -196,8 +199,16 @@ k4_probe_tile (k4_smem & sm, const unsigned long long * __restrict__ vals, const
         for (int u = 0; u < K4_UNROLL; ++u) {
           const uint32_t m = filter_mask (hh[u], filter_k3);
           q[u].a = q[u].b = q[u].c = q[u].d = 0ULL;        // no match, no overflow mark
-          bk[u] = __umulhi (hh[u], n_bucket);
-          if ((fw[u] & m) == m) q[u] = ld_bucket_keep (keys + 4ULL * bk[u]);
+          if (PART) {
+            if ((fw[u] & m) == m) {
+              const gcg_part_desc pd = parts[kmer_owner (key[u] - 1ULL, n_part)];
+              bk[u] = __umulhi (hh[u], pd.n_bucket);
+              q[u] = ld_bucket (pd.keys + 4ULL * bk[u]);
+            }
+          } else {
+            bk[u] = __umulhi (hh[u], n_bucket);
+            if ((fw[u] & m) == m) q[u] = ld_bucket_keep (keys + 4ULL * bk[u]);
+          }
         }
       } else {
 #pragma unroll
@@ -248,9 +259,12 @@ k4_probe_tile (k4_smem & sm, const unsigned long long * __restrict__ vals, const
       const int64_t ww = (tile << 5) + lo;
       bool fw;
       unsigned long long kw, key = key_at (__ldg (packed + ww), __ldg (packed + ww + 1), j, k, &fw);
-      uint32_t hs = kmer_hash32 (key - 1ULL), b = __umulhi (hs, n_bucket);
-      b = (b + 1 == n_bucket) ? 0 : b + 1;          // the home bucket has been looked at
-      unsigned long long slot = table_lookup (keys, n_bucket, b, ld_bucket (keys + 4ULL * b), key, hs & 3u, &kw);
+      const unsigned long long * tk = keys;
+      uint32_t nb = n_bucket;
+      if (PART) { const gcg_part_desc pd = parts[kmer_owner (key - 1ULL, n_part)]; tk = pd.keys; nb = pd.n_bucket; }
+      uint32_t hs = kmer_hash32 (key - 1ULL), b = __umulhi (hs, nb);
+      b = (b + 1 == nb) ? 0 : b + 1;                // the home bucket has been looked at
+      unsigned long long slot = table_lookup (tk, nb, b, ld_bucket (tk + 4ULL * b), key, hs & 3u, &kw);
       if (slot != ~0ULL && !(kw & GCG_KEY_MULTI)) atomicOr (&sm.add[wid][lo], 1u << j);
     }
     __syncwarp ();
@@ -335,6 +349,8 @@ struct k45f_args {
   const unsigned long long * base_in;       // optional: global index of the launch's first anchor (anchors of earlier chunks); must not alias total_out
   unsigned long long * done_out;            // optional (mapped host memory): receives base_in's value when the launch starts, i.e. the number of
                                             // anchors that are COMPLETE in `out` (every earlier launch has finished)
+  const gcg_part_desc * parts;              // remote-probe search: the partitions of the table (device array), else NULL
+  uint32_t n_part;
 };
 
 // Build-time switches (A/B variants, scripts/build_variants.sh):
@@ -394,7 +410,7 @@ chain_lookback (unsigned long long * __restrict__ state, const int64_t idx, cons
 #define K45F_SPIN_FAIL(what) do { printf ("k45_fused_kernel: %s never arrived (block %d warp %d)\n", what, (int) blockIdx.x, (int) (threadIdx.x >> 5)); __trap (); } while (0)
 
 // the anchors of one staged tile, 32 per round, at their global indices base .. base + total
-template <int FMT>
+template <int FMT, bool PART>
 __device__ __forceinline__ void
 k45f_emit_tile (const k45f_args & A, const int k, const int lane, const unsigned long long base, const unsigned long long base0, const uint32_t total,
                 const uint32_t * __restrict__ excl, const uint32_t * __restrict__ mask, const uint64_t * __restrict__ pk,
@@ -411,19 +427,24 @@ k45f_emit_tile (const k45f_args & A, const int k, const int lane, const unsigned
     bool fw;
     unsigned long long kw;
     const unsigned long long key = key_at (pk[lo], pk[lo + 1], j, k, &fw);
-    const uint32_t hs = kmer_hash32 (key - 1ULL), b = __umulhi (hs, A.n_bucket);
-    const bucket4 q = ld_bucket_keep (A.keys + 4ULL * b);
+    const unsigned long long * tk = A.keys;
+    unsigned long long * tv = A.vals;
+    uint32_t nb = A.n_bucket;
+    if (PART) { const gcg_part_desc pd = A.parts[kmer_owner (key - 1ULL, A.n_part)]; tk = pd.keys; tv = pd.vals; nb = pd.n_bucket; }
+    const uint32_t hs = kmer_hash32 (key - 1ULL), b = __umulhi (hs, nb);
+    const bucket4 q = PART ? ld_bucket (tk + 4ULL * b) : ld_bucket_keep (tk + 4ULL * b);
     const int f = bucket_find (q, key, &kw);
     const unsigned long long slot = f >= 0 ? 4ULL * b + (unsigned) f
-                                           : table_lookup (A.keys, A.n_bucket, b, q, key, hs & 3u, &kw);   // walks on to the overflow buckets
-    GCG_DEV_ASSERT (slot != ~0ULL && slot < 4ULL * A.n_bucket && (kw & GCG_KEY_MASK) == key && !(kw & GCG_KEY_MULTI));   // the mask bit said: present, once
+                                           : table_lookup (tk, nb, b, q, key, hs & 3u, &kw);   // walks on to the overflow buckets
+    GCG_DEV_ASSERT (slot != ~0ULL && slot < 4ULL * nb && (kw & GCG_KEY_MASK) == key && !(kw & GCG_KEY_MULTI));   // the mask bit said: present, once
     GCG_DEV_ASSERT (g >= base0 && g < A.win_hi);
-    // one atomic both records the anchor (ONT-side multiplicity, ont.c:245) and returns (tid, pos, flag)
+    // one atomic both records the anchor (ONT-side multiplicity, ont.c:245) and returns (tid, pos, flag); with a
+    // partitioned table it travels over NVLink to the owner, who thereby sees the hits of every rank
 #if K45F_DIAG == 1
     const unsigned long long v = slot;               // (diagnostic build: no value access — WRONG results, timing only)
 #else
-    const unsigned long long v = atomicOr (A.vals + slot, GCG_VAL_ONT1);
-    if ((v & (GCG_VAL_ONT1 | GCG_VAL_ONT2)) == GCG_VAL_ONT1) atomicOr (A.vals + slot, GCG_VAL_ONT2);
+    const unsigned long long v = atomicOr (tv + slot, GCG_VAL_ONT1);
+    if ((v & (GCG_VAL_ONT1 | GCG_VAL_ONT2)) == GCG_VAL_ONT1) atomicOr (tv + slot, GCG_VAL_ONT2);
 #endif
     const uint32_t tid = (uint32_t) (v >> 32) & 0x7FFFFFFFu, cpos = (uint32_t) (v >> 1) & 0x3FFFFFFFu;
     const uint32_t flags = (uint32_t) (v & 1ULL) | (fw ? 0u : 2u);
@@ -460,7 +481,7 @@ k45f_emit_tile (const k45f_args & A, const int k, const int lane, const unsigned
 //     resolve round r + 1 before every warp of the block has finished probing it), a warp's staged tile in two.
 // Every spin is bounded and traps with a message instead of hanging the GPU.
 #define K45F_SLOTS 8        // rotating per-round scalars (a warp is at most two rounds ahead of another; writers touch round + 1)
-template <bool FILTER, int KC, int FMT>
+template <bool FILTER, int KC, int FMT, bool PART = false>
 __global__ void __launch_bounds__ (32 * K4_WARPS, K45F_MINB)
 k45_fused_kernel (const k45f_args A)
 {
@@ -495,8 +516,8 @@ k45_fused_kernel (const k45f_args A)
     if (live) {
       const int64_t tile = bt * K4_WARPS + wid;          // may be past the end in the last block tile: probes nothing
       uint64_t pk; int32_t sq, p0;
-      const uint32_t mymask = k4_probe_tile<FILTER, KC, K45F_PREFETCH != 0> (sm, A.vals, tile, A.packed, A.woff, A.len, A.tile_seq, A.n_seq, A.n_words, k, A.keys, A.n_bucket,
-                                                                             A.filter, A.filter_words, A.filter_k3, &pk, &sq, &p0);
+      const uint32_t mymask = k4_probe_tile<FILTER, KC, K45F_PREFETCH != 0 && !PART, PART> (sm, A.vals, tile, A.packed, A.woff, A.len, A.tile_seq, A.n_seq, A.n_words, k, A.keys, A.n_bucket,
+                                                                                            A.filter, A.filter_words, A.filter_k3, &pk, &sq, &p0, A.parts, A.n_part);
       const int64_t w = (tile << 5) + lane;
       const uint32_t c = __popc (mymask);
       uint32_t x = c;
@@ -601,7 +622,7 @@ k45_fused_kernel (const k45f_args A)
         A.read_off[s_seq[p2][wid][lane]] = (long long) (base + s_excl[p2][wid][lane]);
       }
 #if K45F_DIAG != 2
-      if (prev_total) k45f_emit_tile<FMT> (A, k, lane, base, base0, prev_total, s_excl[p2][wid], s_mask[p2][wid], s_pk[p2][wid], s_seq[p2][wid], s_p0[p2][wid]);
+      if (prev_total) k45f_emit_tile<FMT, PART> (A, k, lane, base, base0, prev_total, s_excl[p2][wid], s_mask[p2][wid], s_pk[p2][wid], s_seq[p2][wid], s_p0[p2][wid]);
 #endif
       __syncwarp ();
     }
@@ -689,7 +710,7 @@ k45_fused_kernel (const k45f_args A)
     s_p0[wid][lane] = p0;
     if (lane == 31) { s_excl[wid][32] = total; s_pk[wid][32] = w + 1 <= A.n_words ? __ldg (A.packed + w + 1) : 0ULL; }   // (slack word at n_words)
     __syncwarp ();
-    k45f_emit_tile<FMT> (A, k, lane, base, base0, total, s_excl[wid], s_mask[wid], s_pk[wid], s_seq[wid], s_p0[wid]);
+    k45f_emit_tile<FMT, false> (A, k, lane, base, base0, total, s_excl[wid], s_mask[wid], s_pk[wid], s_seq[wid], s_p0[wid]);
   }
 }
 #endif
@@ -1227,7 +1248,9 @@ extern "C" int64_t gcg_seqs_kmers (const gcg_seqs * s, int k)
 extern "C" void gcg_table_free (gcg_table * t)
 {
   if (!t) return;
-  gcg_dfree (t->ctx, t->d_keys); gcg_dfree (t->ctx, t->d_vals); gcg_dfree (t->ctx, t->d_filter); gcg_dfree (t->ctx, t->d_cbase);
+  if (t->shared_block) { cudaSetDevice (t->ctx->device); cudaStreamSynchronize (t->ctx->stream); cudaFree (t->shared_block); }
+  else { gcg_dfree (t->ctx, t->d_keys); gcg_dfree (t->ctx, t->d_vals); }
+  gcg_dfree (t->ctx, t->d_filter); gcg_dfree (t->ctx, t->d_cbase);
   delete t;
 }
 
@@ -1595,8 +1618,22 @@ static int launch_fused (gcg_ctx * ctx, const gcg_table * t, const uint64_t * d_
   A.filter = flt ? t->d_filter : nullptr; A.filter_words = flt ? t->filter_words : 0u; A.filter_k3 = flt ? t->filter_k3 : 0;
   A.tile_ctr = d_state + n_tiles; A.state = d_state; A.out = d_out; A.win_lo = win_lo; A.win_hi = win_hi;
   A.read_base = read_base; A.cbase = t->d_cbase; A.read_off = d_read_off; A.total_out = total_out; A.base_in = base_in; A.done_out = done_out;
-  gcg_kscope ks (ctx, "k45_fused");
+  A.parts = t->d_parts; A.n_part = (uint32_t) t->n_part;
   const int grid = grid_for (ctx, n_tiles * 32, 32 * K4_WARPS, 8);
+#if K45F_BLOCKSCAN == 2
+  if (t->d_parts) {
+    // remote-probe search of a hash-partitioned table: filter locally, probe the owner's partition over NVLink
+    GCG_CHECK (flt && fmt == 0 && t->n_part >= 1 && t->n_part <= GCG_MAX_PART, GCG_EINVAL, "gcg_search (partitioned view): needs the union filter and 16-byte records");
+    gcg_kscope ks (ctx, "k45_fused_remote");
+    auto fnp = k == 25 ? k45_fused_kernel<true, 25, 0, true> : k == 31 ? k45_fused_kernel<true, 31, 0, true> : k45_fused_kernel<true, 0, 0, true>;
+    fnp<<<grid, 32 * K4_WARPS, 0, ctx->stream>>> (A);
+    GCG_CUDA (cudaGetLastError ());
+    return GCG_OK;
+  }
+#else
+  GCG_CHECK (t->d_parts == nullptr, GCG_EINVAL, "gcg_search (partitioned view): this build's search kernel has no remote-probe form");
+#endif
+  gcg_kscope ks (ctx, "k45_fused");
 #define K45F(F, KC) (fmt ? k45_fused_kernel<F, KC, 1> : k45_fused_kernel<F, KC, 0>)
   auto fn = flt ? (k == 25 ? K45F (true, 25) : k == 31 ? K45F (true, 31) : K45F (true, 0))
                 : (k == 25 ? K45F (false, 25) : k == 31 ? K45F (false, 31) : K45F (false, 0));
@@ -1679,9 +1716,9 @@ static int search_seqs_impl (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * read
     gcg_hits_free (h);
     return GCG_ERANGE;
   }
-  int rc = gcg_table_filter_ensure (ctx, t);
+  int rc = t->d_parts ? GCG_OK : gcg_table_filter_ensure (ctx, t);      // (a partitioned view brings its union filter)
   static const bool two_pass = [] () { const char * e = getenv ("GCG_SEARCH_FUSED"); return e && atoi (e) == 0; } ();
-  if (!rc && two_pass && fmt == 0) {
+  if (!rc && two_pass && fmt == 0 && !t->d_parts) {
     rc = search_seqs_two_pass (ctx, t, reads, k, h);
     if (rc) { gcg_hits_free (h); return rc; }
     *out = h;
@@ -1739,6 +1776,95 @@ static int search_seqs_impl (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * read
 extern "C" int gcg_search_seqs (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * reads, int k, gcg_hits ** out)
 {
   return search_seqs_impl (ctx, t, reads, k, 0, out);
+}
+
+// ---- hash-partitioned table, probed where it lies ----------------------------------------------------------------
+// The routed form of the partitioned search (part.cu) walks every read position four times — count by owner, write
+// the keys, then two collect passes — and moves 8 bytes out and 8 bytes back per surviving k-mer through windows and
+// barriers.  Here the partitions stay where their owners built them and the ONE search kernel of the single-GPU path
+// reads them directly: a k-mer that passes the union filter (replicated, L2 resident) loads its 32-byte bucket from the
+// owner's key array over NVLink / NVSwitch peer memory, an anchor's atomicOr travels to the owner's value array and
+// comes back with (tid, pos, flag) — so the owner still sees the hits of every rank (ont.c:245) and the statistics
+// are an all-reduce of the partitions', as before.  No routing, no exchange buffers, no collective on the data path;
+// the ranks meet only to know that every partition is built and, afterwards, that every rank has finished probing.
+extern "C" int gcg_table_create_shared (gcg_ctx * ctx, int64_t n_records, int k, gcg_table ** out)
+{
+  GCG_CHECK (ctx && out && n_records >= 0, GCG_EINVAL, "gcg_table_create_shared: bad argument");
+  GCG_CHECK (k >= 1 && k <= 31, GCG_ERANGE, "gcg_table_create_shared: k=%d outside [1,31]", k);
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  int64_t nb = (n_records + 1) / 2 + 64;
+  GCG_CHECK (nb < 0xFFFFFFFFLL, GCG_ERANGE, "gcg_table_create_shared: %lld k-mers exceed the bucket index range", (long long) n_records);
+  gcg_table * t = new gcg_table ();
+  t->ctx = ctx; t->k = k;
+  t->n_bucket = (uint32_t) nb; t->n_slot = (uint64_t) nb * 4; t->n_inserted = n_records;
+  t->shared_cap_slots = (t->n_slot + t->n_slot / 8 + 31) & ~(uint64_t) 31;     // head room: a rebuild of about the same size reuses the block (values stay 256-byte aligned)
+  if (cudaMalloc (&t->shared_block, (size_t) t->shared_cap_slots * 16) != cudaSuccess) {
+    gcg_set_error ("gcg_table_create_shared: cudaMalloc of %llu slots failed: %s", (unsigned long long) t->shared_cap_slots, cudaGetErrorString (cudaGetLastError ()));
+    delete t;
+    return GCG_ENOMEM;
+  }
+  t->d_keys = (unsigned long long *) t->shared_block;
+  t->d_vals = t->d_keys + t->shared_cap_slots;                       // (values start at the CAPACITY: the layout does not move when the table is rebuilt)
+  GCG_CUDA (cudaMemsetAsync (t->d_keys, 0, t->n_slot * 8, ctx->stream));
+  *out = t;
+  return GCG_OK;
+}
+
+// empties a shared table for a rebuild of n_records occurrences; GCG_ERANGE (nothing changed) if the block is too small
+extern "C" int gcg_table_reset_shared (gcg_ctx * ctx, gcg_table * t, int64_t n_records)
+{
+  GCG_CHECK (ctx && t && t->shared_block && n_records >= 0, GCG_EINVAL, "gcg_table_reset_shared: not a shared table");
+  const int64_t nb = (n_records + 1) / 2 + 64;
+  GCG_CHECK ((uint64_t) nb * 4 <= t->shared_cap_slots, GCG_ERANGE, "gcg_table_reset_shared: %lld records do not fit the block", (long long) n_records);
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  t->n_bucket = (uint32_t) nb; t->n_slot = (uint64_t) nb * 4; t->n_inserted = n_records;
+  t->filter_valid = false;
+  GCG_CUDA (cudaMemsetAsync (t->d_keys, 0, t->n_slot * 8, ctx->stream));
+  return GCG_OK;
+}
+
+// what a peer needs to probe the partition: the block (IPC handle for another process, pointer inside this one),
+// the offset of the value array in it, and the bucket count
+extern "C" int gcg_table_shared_info (gcg_table * t, void ** d_block, int64_t * vals_offset_bytes, uint32_t * n_bucket, void * ipc_handle64)
+{
+  GCG_CHECK (t && t->shared_block, GCG_EINVAL, "gcg_table_shared_info: not a shared table");
+  if (d_block) *d_block = t->shared_block;
+  if (vals_offset_bytes) *vals_offset_bytes = (int64_t) t->shared_cap_slots * 8;
+  if (n_bucket) *n_bucket = t->n_bucket;
+  if (ipc_handle64) {
+    static_assert (sizeof (cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    GCG_CUDA (cudaSetDevice (t->ctx->device));
+    GCG_CUDA (cudaIpcGetMemHandle (&h, t->shared_block));
+    memcpy (ipc_handle64, &h, 64);
+  }
+  return GCG_OK;
+}
+
+// d_keys[p] / d_vals[p]: partition p's arrays as THIS context can address them; n_bucket[p] its bucket count;
+// the filter is the union of the partitions' anchoring keys (gcg_filter_add_table + gcg_filter_or)
+extern "C" int gcg_search_seqs_remote (gcg_ctx * ctx, const gcg_seqs * reads, int k, int n_part, const void * const * d_keys, void * const * d_vals,
+                                       const uint32_t * n_bucket, const void * d_filter, int64_t filter_words, int filter_k3, gcg_hits ** out)
+{
+  GCG_CHECK (ctx && reads && out && d_keys && d_vals && n_bucket && d_filter && n_part >= 1 && n_part <= GCG_MAX_PART && filter_words > 0 && filter_words < 0xFFFFFFFFLL,
+             GCG_EINVAL, "gcg_search_seqs_remote: bad argument");
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  gcg_part_desc h_parts[GCG_MAX_PART];
+  memset (h_parts, 0, sizeof h_parts);
+  for (int p = 0; p < n_part; ++p) {
+    GCG_CHECK (d_keys[p] && d_vals[p] && n_bucket[p] > 0, GCG_EINVAL, "gcg_search_seqs_remote: partition %d is not mapped", p);
+    h_parts[p].keys = (const unsigned long long *) d_keys[p]; h_parts[p].vals = (unsigned long long *) d_vals[p]; h_parts[p].n_bucket = n_bucket[p];
+  }
+  gcg_part_desc * d_parts = nullptr;
+  GCG_CUDA (gcg_dmalloc (ctx, &d_parts, sizeof h_parts));
+  GCG_CUDA (cudaMemcpyAsync (d_parts, h_parts, sizeof h_parts, cudaMemcpyHostToDevice, ctx->stream));     // (pageable source: staged before the call returns)
+  gcg_table view;
+  view.ctx = ctx; view.k = k;
+  view.d_filter = (uint32_t *) d_filter; view.filter_words = (uint32_t) filter_words; view.filter_k3 = filter_k3; view.filter_valid = true;
+  view.d_parts = d_parts; view.n_part = n_part;
+  int rc = search_seqs_impl (ctx, &view, reads, k, 0, out);
+  gcg_dfree (ctx, d_parts);
+  return rc;
 }
 
 extern "C" int gcg_search_seqs_compact (gcg_ctx * ctx, gcg_table * t, const gcg_seqs * reads, int k, gcg_hits ** out)

@@ -68,6 +68,25 @@ __device__ __forceinline__ uint32_t filter_mask (uint32_t h, int k3)
   return m;
 }
 
+// owner partition of a canonical k-mer (hash-partitioned table, part.cu / the remote-probe search of kmer.cu): a 64-bit
+// mix that is independent of the in-table bucket hash (which hash picks the owner is unobservable)
+__host__ __device__ __forceinline__ uint32_t kmer_owner (uint64_t key, uint32_t n_part)
+{
+  uint64_t x = key * 0x9E3779B97F4A7C15ULL;
+  x ^= x >> 29;
+  x *= 0xBF58476D1CE4E5B9ULL;
+  const uint32_t hi = (uint32_t) (x >> 32);          // (the usual closing x ^= x >> 32 only touches the low half)
+#ifdef __CUDA_ARCH__
+  return __umulhi (hi, n_part);
+#else
+  return (uint32_t) (((uint64_t) hi * (uint64_t) n_part) >> 32);
+#endif
+}
+
+// one partition of a table as a searching GPU sees it: its key and value arrays — local memory, or a peer GPU's,
+// mapped through CUDA IPC / peer access and reached over NVLink — and its bucket count
+struct gcg_part_desc { const unsigned long long * keys; unsigned long long * vals; uint32_t n_bucket; uint32_t pad; };
+
 // largest s in [0,n) with woff[s] <= w  (woff has n+1 entries, woff[n] > w)
 __device__ __forceinline__ int64_t find_seq (const int64_t * __restrict__ woff, int64_t n, int64_t w)
 {

@@ -40,20 +40,7 @@ struct gcg_route {
   int64_t counts[GCG_MAX_PART] = {0};
 };
 
-// ---- owner of a canonical k-mer ---------------------------------------------------------------
-__host__ __device__ __forceinline__ uint32_t kmer_owner (uint64_t key, uint32_t n_part)
-{
-  uint64_t x = key * 0x9E3779B97F4A7C15ULL;
-  x ^= x >> 29;
-  x *= 0xBF58476D1CE4E5B9ULL;
-  const uint32_t hi = (uint32_t) (x >> 32);          // (the usual closing x ^= x >> 32 only touches the low half)
-#ifdef __CUDA_ARCH__
-  return __umulhi (hi, n_part);
-#else
-  return (uint32_t) (((uint64_t) hi * (uint64_t) n_part) >> 32);
-#endif
-}
-
+// ---- owner of a canonical k-mer: kmer_owner () in kmer_dev.cuh -----------------------------------
 extern "C" int gcg_kmer_owner (uint64_t canonical_kmer, int n_part)
 {
   if (n_part < 1 || n_part > GCG_MAX_PART) return -1;

@@ -85,6 +85,13 @@ class TorchComm:
     def barrier(self):
         self.dist.barrier()
 
+    def gather_ints(self, values) -> np.ndarray:
+        """-> [world, len(values)]: every rank's small integer vector"""
+        send = torch.as_tensor(np.asarray(values, dtype=np.int64)).to(self.device)
+        out = torch.empty(self.world * send.numel(), dtype=torch.int64, device=self.device)
+        self.dist.all_gather_into_tensor(out, send)
+        return out.cpu().numpy().reshape(self.world, -1)
+
     def stream_barrier(self):
         """a barrier in STREAM order, without a host round trip: a one-element all-reduce enqueued on the current
         stream (the library's, see DeviceOps.stream).  Kernels queued behind it on any rank start only after every
@@ -112,6 +119,12 @@ class TorchComm:
         for r, ref in enumerate(refs):
             if r != self.rank:
                 ops.window_close(ref)
+
+    def share_block(self, ops, ptr: int, handle: bytes):
+        """every rank's cudaMalloc block (a shared table partition) as an address this rank's kernels can use"""
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, handle)
+        return [ptr if r == self.rank else ops.window_open(handles[r]) for r in range(self.world)]
 
 
 class ThreadGroup:
@@ -145,6 +158,12 @@ class ThreadComm:
 
     def stream_barrier(self):
         self._done()
+
+    def gather_ints(self, values) -> np.ndarray:
+        allv = self._publish(np.asarray(values, dtype=np.int64))
+        out = np.stack(allv)
+        self._done()
+        return out
 
     def exchange_counts(self, counts: np.ndarray) -> np.ndarray:
         allc = self._publish(np.array(counts, dtype=np.int64))
@@ -197,6 +216,11 @@ class ThreadComm:
     def unshare(self, ops, refs):
         pass
 
+    def share_block(self, ops, ptr: int, handle: bytes):
+        refs = self._publish(ptr)                          # one address space
+        self._done()
+        return refs
+
 
 # ------------------------------------------------------------------------------------------------
 # device work (the C ABI)
@@ -247,6 +271,13 @@ class DeviceOps:
 
     def table_create(self, n, k):
         return self.ctx.table_create(n, k)
+
+    def table_create_shared(self, n, k):
+        return self.ctx.table_create_shared(n, k)
+
+    def search_remote(self, reads, k, key_ptrs, val_ptrs, n_buckets, flt):
+        t, n_words, k3 = flt
+        return self.ctx.search_remote(reads, k, key_ptrs, val_ptrs, n_buckets, t.data_ptr(), n_words, k3)
 
     def insert(self, table, t: torch.Tensor, n: int):
         table.insert_records(t.data_ptr(), n)
@@ -308,6 +339,10 @@ class PartitionedKmerIndex:
                        `all_to_all_single` (NCCL; gloo in the CPU tests);
            exchange = "direct": the routing and lookup kernels store straight into the peers' windows
                        over NVLink / NVSwitch peer memory, the ranks only meet at two barriers per round.
+           exchange = "remote": no routing at all — the partitions stay where their owners built them (one cudaMalloc
+                       block each, mapped by every rank) and ONE search kernel per rank probes them where they lie:
+                       a k-mer that passes the union filter loads its bucket from the owner's key array over NVLink,
+                       an anchor's atomicOr travels to the owner's value array and returns (tid, pos, flag).
            prefilter: after the build every rank adds its anchoring keys (present exactly once) to a
                        Bloom-style filter, the partial filters are all-gathered and OR-ed, and the
                        search routes only the ONT k-mers that pass it — the anchors plus a few
@@ -316,8 +351,10 @@ class PartitionedKmerIndex:
                        lookups by an order of magnitude."""
         if not 1 <= comm.world <= api.MAX_PART:
             raise ValueError("world size %d outside [1,%d]" % (comm.world, api.MAX_PART))
-        if exchange not in ("all_to_all", "direct"):
-            raise ValueError("exchange must be 'all_to_all' or 'direct'")
+        if exchange not in ("all_to_all", "direct", "remote"):
+            raise ValueError("exchange must be 'all_to_all', 'direct' or 'remote'")
+        if exchange == "remote" and not prefilter:
+            raise ValueError("the remote-probe search needs the union pre-filter")
         self.ops, self.comm, self.k, self.round_kmers, self.exchange = ops, comm, k, round_kmers, exchange
         self.table = None
         self.n_local_records = 0
@@ -326,6 +363,8 @@ class PartitionedKmerIndex:
         self.qwin = self.awin = None              # direct exchange: my key / answer windows ...
         self.q_refs = self.a_refs = None          # ... and every rank's, as seen from this rank
         self.q_cap = self.a_cap = 0
+        self.block_refs = None                    # remote probes: every rank's partition block as this rank addresses it
+        self.part_shape = None                    # ... and (value offset, bucket count) of every partition
         # GCG_DIST_PROFILE=1: wall-clock per phase with a device sync on both sides (diagnosis only;
         # the syncs serialise what normally overlaps)
         self.profile = os.environ.get("GCG_DIST_PROFILE") == "1"
@@ -350,9 +389,11 @@ class PartitionedKmerIndex:
         """`contigs`: the full contig set, uploaded on every rank (2 bits per base; the *table* is
         what is partitioned).  Each rank chops 1/world of the tiles."""
         ops, comm = self.ops, self.comm
+        reuse = False
         if self.table is not None:              # rebuilding: the exchange windows of the direct mode are kept
-            self.table.free()
-            self.table = None
+            if self.exchange != "remote":
+                self.table.free()
+                self.table = None
         with self._stream():
             t0, t1 = tile_slice(ops.tiles(contigs), comm.rank, comm.world)
             with self._phase("build.plan"):
@@ -366,7 +407,15 @@ class PartitionedKmerIndex:
                 recv = comm.all_to_all(send, route.counts, recv_counts, width=2)
             n = int(recv_counts.sum())
             with self._phase("build.insert"):
-                self.table = ops.table_create(n, self.k)
+                if self.exchange == "remote":
+                    # the partition lives in a block the peers have mapped: keep the block (and the mappings) when the
+                    # rebuild fits it.  Nobody may still be probing the old contents: the search ends with a barrier.
+                    reuse = self.table is not None and self.table.reset_shared(n)
+                    if not reuse:
+                        self._drop_blocks()
+                        self.table = ops.table_create_shared(n, self.k)
+                else:
+                    self.table = ops.table_create(n, self.k)
                 ops.insert(self.table, recv, n)
                 ops.sync()                      # recv/send are released after the inserts ran
             route.free()
@@ -383,7 +432,35 @@ class PartitionedKmerIndex:
                             ops.filter_or(flt, part)
                     ops.sync()
                     self.prefilter = flt
+            if self.exchange == "remote":
+                with self._phase("build.share"):
+                    ptr, vals_off, nb, handle = self.table.shared_info()
+                    shapes = comm.gather_ints([vals_off, nb, 0 if reuse else 1])
+                    if self.block_refs is None or shapes[:, 2].any():
+                        # some rank has a new block: everybody maps everybody again (rare: the first build, or a larger table)
+                        if self.block_refs is not None:
+                            self._close_block_refs()
+                        self.block_refs = comm.share_block(ops, ptr, handle)
+                    self.part_shape = [(int(shapes[r, 0]), int(shapes[r, 1])) for r in range(comm.world)]
         return self
+
+    def _close_block_refs(self):
+        for r, ref in enumerate(self.block_refs):
+            if r != self.comm.rank and hasattr(self.comm, "dist"):
+                self.ops.window_close(ref)
+        self.block_refs = None
+
+    def _drop_blocks(self):
+        """collective: nobody keeps a mapping of a partition block that is about to be freed"""
+        if self.table is None:
+            return
+        self.ops.sync()
+        self.comm.barrier()
+        if self.block_refs is not None:
+            self._close_block_refs()
+        self.comm.barrier()
+        self.table.free()
+        self.table = None
 
     # ---- direct exchange ------------------------------------------------------------------------
     def _drop_windows(self):
@@ -439,6 +516,21 @@ class PartitionedKmerIndex:
         ops, comm = self.ops, self.comm
         parts, n_total = [], 0
         with self._stream():
+            if self.exchange == "remote":
+                with self._phase("search.remote"):
+                    comm.stream_barrier()               # every partition (and the union filter) is built before anybody probes it
+                    keys = [self.block_refs[r] for r in range(comm.world)]
+                    vals = [self.block_refs[r] + self.part_shape[r][0] for r in range(comm.world)]
+                    h = ops.search_remote(reads, self.k, keys, vals, [self.part_shape[r][1] for r in range(comm.world)], self.prefilter)
+                    comm.stream_barrier()               # every rank has finished probing before statistics are read or a partition is rebuilt
+                self.n_positions += reads.kmers(self.k) if hasattr(reads, "kmers") else 0
+                if keep_on_device:
+                    n = h.n
+                    h.free()
+                    return n
+                out = h.download()
+                h.free()
+                return out
             rounds = search_rounds(ops.tiles(reads), self.round_kmers)
             n_rounds = int(comm.all_reduce([len(rounds)], "max")[0])
             for i in range(n_rounds):
@@ -489,6 +581,8 @@ class PartitionedKmerIndex:
         """collective when the direct exchange was used (the windows are unmapped everywhere first)"""
         with self._stream():
             self._drop_windows()
+            if self.exchange == "remote":
+                self._drop_blocks()
         if self.table is not None:
             self.table.free()
             self.table = None

@@ -123,7 +123,7 @@ def test_owner_side_insert_lookup_collect(ctx, oracle):
         x.free()
 
 
-@pytest.mark.parametrize("exchange,prefilter", [("all_to_all", False), ("all_to_all", True), ("direct", False), ("direct", True)])
+@pytest.mark.parametrize("exchange,prefilter", [("all_to_all", False), ("all_to_all", True), ("direct", False), ("direct", True), ("remote", True)])
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 @pytest.mark.parametrize("name,k,round_kmers", [("tiny", 25, 1 << 31), ("repeats", 17, 50_000), ("small", 31, 300_000)])
 def test_partitioned_index_one_gpu(oracle, world, name, k, round_kmers, exchange, prefilter):
@@ -137,10 +137,14 @@ def test_partitioned_index_one_gpu(oracle, world, name, k, round_kmers, exchange
     def body(rank, ops, comm):
         cs, rs = ops.ctx.upload(inp.contigs), ops.ctx.upload(batches[rank])
         idx = gdist.PartitionedKmerIndex(ops, comm, k, round_kmers=round_kmers, exchange=exchange, prefilter=prefilter).build(cs)
+        if exchange == "remote":
+            idx.search(rs)                  # ... and a rebuild into the same shared blocks (the peers keep their mappings)
+            idx.build(cs)
         hits = idx.search(rs)
         st = idx.stats()
-        assert idx.n_routed <= idx.n_positions and (prefilter or idx.n_routed == idx.n_positions)
-        assert not prefilter or len(hits) <= idx.n_routed < max(idx.n_positions // 2, len(hits) + 1)
+        if exchange != "remote":            # (remote probes route nothing: the search kernel reads the owners' partitions where they lie)
+            assert idx.n_routed <= idx.n_positions and (prefilter or idx.n_routed == idx.n_positions)
+            assert not prefilter or len(hits) <= idx.n_routed < max(idx.n_positions // 2, len(hits) + 1)
         n_dev = idx.search(rs, keep_on_device=True)
         out = (hits, st, idx.n_local_records, n_dev, ops.ctx.launches())
         idx.free(); cs.free(); rs.free()
@@ -182,9 +186,10 @@ NCCL_SCRIPT = textwrap.dedent("""
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("exchange,prefilter", [("all_to_all", False), ("direct", False), ("direct", True)])
+@pytest.mark.parametrize("exchange,prefilter", [("all_to_all", False), ("direct", False), ("direct", True), ("remote", True)])
 def test_partitioned_index_nccl_world2(oracle, tmp_path, exchange, prefilter):
-    """one process per GPU: NCCL all-to-all, and direct stores into CUDA-IPC windows over NVLink"""
+    """one process per GPU: NCCL all-to-all, direct stores into CUDA-IPC windows over NVLink, and remote probes of
+    the owners' partitions (CUDA-IPC mapped table blocks, loads and atomics over NVLink)"""
     script = tmp_path / "run.py"
     script.write_text(NCCL_SCRIPT % {"root": ROOT, "out": str(tmp_path), "exchange": exchange, "prefilter": prefilter})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
@@ -195,5 +200,5 @@ def test_partitioned_index_nccl_world2(oracle, tmp_path, exchange, prefilter):
     want_hits, want_stats = oracle_answer(oracle, inp.contigs, shard(inp.reads, 2), 31)
     for r in range(2):
         info = json.load(open(tmp_path / ("info_%d.json" % r)))
-        assert tuple(info["stats"]) == want_stats and info["sent"] > 0 and info["launches"] > 0
+        assert tuple(info["stats"]) == want_stats and (info["sent"] > 0 or exchange == "remote") and info["launches"] > 0
         assert np.array_equal(np.load(tmp_path / ("hits_%d.npy" % r)), want_hits[r])
