@@ -377,63 +377,66 @@ def run_ours(args, rank, local_rank, world):
         cs4, rs4 = ctx.upload([genome4]), ctx.upload(reads4)
         sample = reads4[:48]
         ss4 = ctx.upload(sample)
-        idx4 = gdist.PartitionedKmerIndex(ops4, comm4, K4, exchange=args.cfg4_exchange)
-        idx4.build(cs4)
-        got = idx4.search(ss4)                                  # the sample's anchors (collective: every rank searches its own sample)
-        st_after_sample = idx4.stats()
-        idx4.build(cs4)                                         # fresh ONT-side counts for the timed searches
-        barrier()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record(stream)
-        idx4.build(cs4)
-        b1.record(stream)
-        barrier()
-        build4_ms = allmax(b0.elapsed_time(b1))
-        for _ in range(2):
-            h4 = idx4.search(rs4, keep_on_device=True)
-        ctx.prof_reset()
-        sent0 = comm4.bytes_sent
-        barrier()
-        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        q0.record(stream)
-        sampler.mark()
-        c4_steps = 3
-        for _ in range(c4_steps):
-            h4 = idx4.search(rs4, keep_on_device=True)
-        q1.record(stream)
-        barrier()
-        search4_ms = allmax(q0.elapsed_time(q1)) / c4_steps
-        prof4 = ctx.prof_report()
-        tot4, hits4 = allsum(float(n4)), allsum(float(h4))
-        nv4 = allsum(float(comm4.bytes_sent - sent0)) / c4_steps
-        routed4 = allsum(float(idx4.n_routed)) / max(1.0, allsum(float(idx4.n_positions)))
-        check = {"kind": "not run (oracle library missing)"}
-        if rank == 0:
-            try:
-                from oracle import oracle as orc
-                O = orc.Oracle()
-                t_or = time.perf_counter()
-                h_or = O.table_build([genome4], K4)
-                want_hits, _ = O.search(h_or, sample, K4)
-                want_st = O.table_stats(h_or)
-                O.table_free(h_or)
-                ok_st = tuple(st_after_sample[:2]) == tuple(want_st)
-                ok_hits = (len(got) == len(want_hits["read"]) and np.array_equal(got["read"], want_hits["read"].astype(np.int32)) and
-                           np.array_equal(got["pos"], want_hits["pos"]) and np.array_equal(got["tid"], want_hits["tid"]) and
-                           np.array_equal(got["cpos_flags"] >> 2, want_hits["cpos"].astype(np.uint32)) and
-                           np.array_equal(got["cpos_flags"] & 1, want_hits["krev"]) and np.array_equal((got["cpos_flags"] >> 1) & 1, want_hits["orev"]))
-                check = {"kind": "CPU oracle (oracle/gc_oracle.c) over the whole genome", "scaffold_stats_equal": bool(ok_st), "oracle_stats": list(want_st),
-                         "sample_reads": len(sample), "sample_anchors": int(len(got)), "sample_anchors_equal": bool(ok_hits), "oracle_s": time.perf_counter() - t_or}
-                assert ok_st and ok_hits, "partitioned cfg4 table disagrees with the CPU oracle: %r" % (check,)
-            except ImportError:
-                pass
-        cfg4 = {"metric": "kmers_per_s", "value": tot4 / (search4_ms * 1e-3), "unit": "k-mers/s", "ms_per_search": search4_ms, "build_ms": build4_ms,
-                "config": {"workload": "BASELINE configs[3]: %d Mb synthetic genome, k=31, %.0fx ONT in total (%.2fx = %d reads per GPU), contig table hash-partitioned over %d GPU(s), exchange '%s' (remote = one search kernel per rank probing the owners' partitions over NVLink peer memory)" %
-                           (G4 // 1_000_000, c4["coverage"], c4["coverage"] / world, len(reads4), world, args.cfg4_exchange),
-                           "ont_kmers_total": int(tot4), "anchors_total": int(hits4), "stats": list(idx4.stats())},
-                "nvlink_bytes_per_search": nv4, "routed_fraction": routed4, "check": check,
-                "kernel_ms_per_search": {k_: v[0] / c4_steps for k_, v in sorted(prof4.items())}}
-        idx4.free()
+        cfg4_all = {}
+        for x4 in ([args.cfg4_exchange] + ([] if args.cfg4_exchange == "direct" or world == 1 else ["direct"])):
+            idx4 = gdist.PartitionedKmerIndex(ops4, comm4, K4, exchange=x4)
+            idx4.build(cs4)
+            got = idx4.search(ss4)                                  # the sample's anchors (collective: every rank searches its own sample)
+            st_after_sample = idx4.stats()
+            idx4.build(cs4)                                         # fresh ONT-side counts for the timed searches
+            barrier()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record(stream)
+            idx4.build(cs4)
+            b1.record(stream)
+            barrier()
+            build4_ms = allmax(b0.elapsed_time(b1))
+            for _ in range(2):
+                h4 = idx4.search(rs4, keep_on_device=True)
+            ctx.prof_reset()
+            sent0 = comm4.bytes_sent
+            barrier()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record(stream)
+            sampler.mark()
+            c4_steps = 3
+            for _ in range(c4_steps):
+                h4 = idx4.search(rs4, keep_on_device=True)
+            q1.record(stream)
+            barrier()
+            search4_ms = allmax(q0.elapsed_time(q1)) / c4_steps
+            prof4 = ctx.prof_report()
+            tot4, hits4 = allsum(float(n4)), allsum(float(h4))
+            nv4 = allsum(float(comm4.bytes_sent - sent0)) / c4_steps
+            routed4 = allsum(float(idx4.n_routed)) / max(1.0, allsum(float(idx4.n_positions)))
+            check = {"kind": "not run (oracle library missing)"}
+            if rank == 0:
+                try:
+                    from oracle import oracle as orc
+                    O = orc.Oracle()
+                    t_or = time.perf_counter()
+                    h_or = O.table_build([genome4], K4)
+                    want_hits, _ = O.search(h_or, sample, K4)
+                    want_st = O.table_stats(h_or)
+                    O.table_free(h_or)
+                    ok_st = tuple(st_after_sample[:2]) == tuple(want_st)
+                    ok_hits = (len(got) == len(want_hits["read"]) and np.array_equal(got["read"], want_hits["read"].astype(np.int32)) and
+                               np.array_equal(got["pos"], want_hits["pos"]) and np.array_equal(got["tid"], want_hits["tid"]) and
+                               np.array_equal(got["cpos_flags"] >> 2, want_hits["cpos"].astype(np.uint32)) and
+                               np.array_equal(got["cpos_flags"] & 1, want_hits["krev"]) and np.array_equal((got["cpos_flags"] >> 1) & 1, want_hits["orev"]))
+                    check = {"kind": "CPU oracle (oracle/gc_oracle.c) over the whole genome", "scaffold_stats_equal": bool(ok_st), "oracle_stats": list(want_st),
+                             "sample_reads": len(sample), "sample_anchors": int(len(got)), "sample_anchors_equal": bool(ok_hits), "oracle_s": time.perf_counter() - t_or}
+                    assert ok_st and ok_hits, "partitioned cfg4 table disagrees with the CPU oracle: %r" % (check,)
+                except ImportError:
+                    pass
+            cfg4_all[x4] = {"metric": "kmers_per_s", "value": tot4 / (search4_ms * 1e-3), "unit": "k-mers/s", "ms_per_search": search4_ms, "build_ms": build4_ms,
+                    "config": {"workload": "BASELINE configs[3]: %d Mb synthetic genome, k=31, %.0fx ONT in total (%.2fx = %d reads per GPU), contig table hash-partitioned over %d GPU(s), exchange '%s' (remote = one search kernel per rank probing the owners' partitions over NVLink peer memory)" %
+                               (G4 // 1_000_000, c4["coverage"], c4["coverage"] / world, len(reads4), world, x4),
+                               "ont_kmers_total": int(tot4), "anchors_total": int(hits4), "stats": list(idx4.stats())},
+                    "nvlink_bytes_per_search": nv4, "routed_fraction": routed4, "check": check,
+                    "kernel_ms_per_search": {k_: v[0] / c4_steps for k_, v in sorted(prof4.items())}}
+            idx4.free()
+        cfg4 = cfg4_all
         cs4.free(); rs4.free(); ss4.free()
         del genome4, reads4
 
@@ -718,7 +721,8 @@ def run_ours(args, rank, local_rank, world):
                             "kernel_ms_per_step": {k_: v[0] / args.steps for k_, v in sorted(sprof.items())}}},
     }
     if cfg4 is not None:
-        line["partitioned_cfg4"] = cfg4
+        for x4, leg in cfg4.items():
+            line["partitioned_cfg4" if x4 == args.cfg4_exchange else "partitioned_cfg4_" + x4] = leg
     if hbm_leg is not None:
         hbm_leg.update({"bound": "hbm", "peak": peak_gbs, "unit": "GB/s", "frac": hbm_leg["achieved"] / peak_gbs, "peak_source": peak_src})
         line["roofline_hbm_table"] = hbm_leg
