@@ -320,7 +320,7 @@ def run_ours(args, rank, local_rank, world):
         from superplus_b200 import dist as gdist
         ops = gdist.DeviceOps(ctx, local_rank)
         comm = gdist.TorchComm(ops.device) if dist is not None else gdist.ThreadComm(gdist.ThreadGroup(1), 0, ops.device, ops.sync)
-        for exchange in ("remote", "direct", "all_to_all"):
+        for exchange in ("direct", "remote", "all_to_all"):
             # one index per exchange mode; every step rebuilds its table from the packed contigs (as the
             # replicated leg does) while the exchange windows of the direct mode stay mapped
             idx = gdist.PartitionedKmerIndex(ops, comm, K, exchange=exchange)
@@ -378,7 +378,7 @@ def run_ours(args, rank, local_rank, world):
         sample = reads4[:48]
         ss4 = ctx.upload(sample)
         cfg4_all = {}
-        for x4 in ([args.cfg4_exchange] + ([] if args.cfg4_exchange == "direct" or world == 1 else ["direct"])):
+        for x4 in [args.cfg4_exchange]:
             idx4 = gdist.PartitionedKmerIndex(ops4, comm4, K4, exchange=x4)
             idx4.build(cs4)
             got = idx4.search(ss4)                                  # the sample's anchors (collective: every rank searches its own sample)
@@ -747,7 +747,7 @@ def run_ours(args, rank, local_rank, world):
         except Exception as e:      # the baseline must never sink the bench line
             line["cpu_baseline"] = {"value": None, "unit": "k-mers/s", "cores": cores, "kind": "reference", "sample": "failed: %r" % (e,)}
     for exchange, pr in part.items():
-        line[{"remote": "partitioned", "direct": "partitioned_direct", "all_to_all": "partitioned_all_to_all"}[exchange]] = {
+        line[{"direct": "partitioned", "remote": "partitioned_remote", "all_to_all": "partitioned_all_to_all"}[exchange]] = {
             "metric": "kmers_per_s", "value": tot_ont_kmers / (pr["ms_per_step"] * 1e-3), "unit": "k-mers/s", "ms_per_step": pr["ms_per_step"],
             "config": {"workload": "same step with the contig table hash-partitioned over %d GPU(s)" % world,
                        "exchange": ({"remote": "remote probes: the partitions stay where their owners built them (CUDA-IPC mapped blocks) and ONE search kernel per rank reads them where they lie — bucket loads and the anchors' atomicOr over NVLink peer memory, after a replicated union filter; no routing, no exchange buffers, no collective on the data path",
@@ -770,7 +770,8 @@ def main():
     ap.add_argument("--sw-pairs", type=int, default=47360, help="pairs per GPU per step of the cfg3 leg (16 items per resident warp)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cfg4", default="auto", choices=["auto", "on", "off"], help="BASELINE configs[3] at full size on the partitioned table (auto: at 8 GPUs)")
-    ap.add_argument("--cfg4-exchange", default="remote", choices=["remote", "direct", "all_to_all"])
+    ap.add_argument("--cfg4-exchange", default="direct", choices=["remote", "direct", "all_to_all"],
+                    help="exchange of the full-size cfg4 leg (remote probes collapse at 8 GPUs x 450 MB partitions: 1.04 s against 10.2 ms per search, profiles/r02_bench_n8_remote_ab.json)")
     ap.add_argument("--cfg4-genome", type=int, default=0, help="genome length of that leg (default: 100 Mb, the config's)")
     ap.add_argument("--no-hbm-table", action="store_true", help="skip the second k-mer roofline leg (100 Mb table beyond the L2, N=1 only)")
     ap.add_argument("--hbm-coverage", type=float, default=2.0, help="ONT coverage of the 100 Mb genome in that leg")
