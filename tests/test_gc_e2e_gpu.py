@@ -219,3 +219,136 @@ def test_runs_mode_writes_the_same_files(cfg, env):
         assert md5(os.path.join(wd, "gc_fix1.fa")) == g["fa"]
         assert md5(os.path.join(wd, "ont_link.txt")) == g["link"]
         assert md5(os.path.join(wd, "valid_ont_link.txt")) == g["valid"]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GC_SW_FILL=1 (opt-in): gap junctions from batched alignments instead of the extrapolation
+def _code(a):
+    return ((a >> 1) & 3).astype("uint8")                                   # bio.h:22-24
+
+
+def _fasta_bytes(scaffolds):
+    import numpy as np
+    out = []
+    for i, seq in enumerate(scaffolds):
+        out.append(b">%d\n" % i)
+        n = len(seq)
+        body = np.full(n + (n + 59) // 60, ord("\n"), np.uint8)
+        idx = np.arange(n)
+        body[idx + idx // 60] = seq
+        out.append(body[: n + n // 60].tobytes() if n % 60 == 0 else body.tobytes())
+    return b"".join(out)
+
+
+def _read_sw_fill(path):
+    rows = []
+    for line in open(path):
+        if line.startswith("#"):
+            continue
+        f = line.split()
+        rows.append((f[0], [int(x) for x in f[1:]]))
+    return rows
+
+
+G_COLS = "gap from_ctg to_ctg ont fwd k pL cL pR cR read_len flank_a head_c jL_ref jR_ref jL jR wL0 wL1 wR0 wR1 score_a score_b".split()
+
+
+@pytest.mark.parametrize("cfg,env", [("tiny", {}), ("small", {}), ("repeats", {"GC_RUNS": "1"}), ("cfg1", {}), ("cfg1", {"GC_RUNS": "1"})])
+def test_sw_fill_junctions_equal_the_cpu_oracle(cfg, env):
+    """Every gap's two alignments are recomputed on the CPU with the oracle's restatement of sw.c (pinned against the
+    reference's own sw.c by tests/test_oracle_vs_ref.py) from the FASTA, the FASTQ and the anchors of sw_fill.tsv: the end
+    cells, scores and therefore junctions must be the batch's, and gc_fix1.fa must be the scaffolds rebuilt from them.
+    The same rebuild with the extrapolated junctions must give the REFERENCE's file (golden md5) — which pins the
+    test's own reading of fix_ont1 / combine_ont_info (ctg_graph.c:455-531, 669-755).  The link files do not change."""
+    import numpy as np
+    from oracle import oracle as orc_mod
+    orc = orc_mod.Oracle()
+    P = orc_mod.make_params(strategy=2)                                       # SWOS_INDEL, +1/-5, open 2 extend 1 (gc_graph.c:74-107)
+    with tempfile.TemporaryDirectory() as tmp:
+        fa, fq, inp = synth.materialise(cfg, tmp)
+        if inp is None:
+            inp = synth.make_config(cfg)
+        wd = os.path.join(tmp, "run")
+        os.makedirs(wd)
+        r = subprocess.run([GC, fa, fq, "8", "out"], cwd=wd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900,
+                           env=dict(os.environ, GC_SW_FILL="1", **env))
+        assert r.returncode == 0, r.stderr.decode()[-2000:]
+        g = GOLD[cfg]
+        assert md5(os.path.join(wd, "ont_link.txt")) == g["link"]
+        assert md5(os.path.join(wd, "valid_ont_link.txt")) == g["valid"]
+        contigs = inp.contigs
+        rows = _read_sw_fill(os.path.join(wd, "sw_fill.tsv"))
+        ref_scafs, sw_scafs, fills = [], [], []
+        n_gap = n_moved = 0
+        for kind, f in rows:
+            if kind == "S":
+                ref_scafs.append([contigs[f[1]]]); sw_scafs.append([contigs[f[1]]])
+            elif kind == "N":
+                for s in (ref_scafs, sw_scafs):
+                    s[-1] += [np.full(max(f[2], 0), ord("N"), np.uint8), contigs[f[1]]]
+            else:
+                d = dict(zip(G_COLS, f))
+                n_gap += 1
+                read = inp.reads[d["ont"]]
+                L, k = len(read), d["k"]
+                assert L == d["read_len"]
+                rs = read if d["fwd"] else synth.revcomp(read)
+                cf, ct = contigs[d["from_ctg"]], contigs[d["to_ctg"]]
+                a, c = len(cf) - d["cL"], d["cR"] + k
+                assert (a, c) == (d["flank_a"], d["head_c"])
+                pLs = d["pL"] if d["fwd"] else L - d["pL"] - k
+                pRs = d["pR"] if d["fwd"] else L - d["pR"] - k
+                jL_ref, jR_ref = pLs + a, pRs - d["cR"]
+                assert (jL_ref, jR_ref) == (d["jL_ref"], d["jR_ref"])
+                jL, jR = jL_ref, jR_ref
+                ok_l = 0 <= pLs and pLs + k <= L and np.array_equal(_code(rs[pLs:pLs + k]), _code(cf[d["cL"]:d["cL"] + k]))
+                ok_r = 0 <= pRs and pRs + k <= L and np.array_equal(_code(rs[pRs:pRs + k]), _code(ct[d["cR"]:d["cR"] + k]))
+                if 1 <= a <= 4000 and ok_l:
+                    w0, w1 = pLs, min(L, pLs + a + a // 4 + 32)
+                    assert (w0, w1) == (d["wL0"], d["wL1"])
+                    res = orc.sw_align(P, _code(cf[d["cL"]:]), _code(rs[w0:w1]))
+                    jL = w0 + res["bt_tidx"]
+                    assert res["score"] == d["score_a"], d
+                if 1 <= c <= 4000 and ok_r:
+                    w1, w0 = pRs + k, max(0, pRs + k - (c + c // 4 + 32))
+                    assert (w0, w1) == (d["wR0"], d["wR1"])
+                    res = orc.sw_align(P, _code(ct[:c])[::-1].copy(), _code(rs[w0:w1])[::-1].copy())
+                    jR = w1 - res["bt_tidx"]
+                    assert res["score"] == d["score_b"], d
+                assert (jL, jR) == (d["jL"], d["jR"]), d
+                n_moved += (jL, jR) != (jL_ref, jR_ref)
+                sw_scafs[-1] += [rs[jL:jR] if jR > jL else rs[:0], ct]
+                fills.append((d["from_ctg"], d["to_ctg"], d["fwd"], sw_scafs[-1][-2]))
+                # the reference's own fill: forward reads start at the extrapolated junction, reverse reads k - 1 bases
+                # behind it (its reverse branch walks down from the k-mer's START in the stored read, ctg_graph.c:516-528)
+                n_ref = jR_ref - jL_ref
+                s0 = jL_ref if d["fwd"] else jL_ref + k - 1
+                ref_scafs[-1] += [rs[s0:s0 + n_ref] if n_ref > 0 else rs[:0], ct]
+                fills[-1] += (ref_scafs[-1][-2],)
+        assert n_gap > 0
+        ref_fa = _fasta_bytes([np.concatenate(s) for s in ref_scafs])
+        assert hashlib.md5(ref_fa).hexdigest() == g["fa"]                   # the test reads fix_ont1 as the reference wrote it
+        sw_fa = _fasta_bytes([np.concatenate(s) for s in sw_scafs])
+        assert open(os.path.join(wd, "gc_fix1.fa"), "rb").read() == sw_fa
+        assert n_moved > 0                                                   # 10 % read errors: the alignment must move some junction
+        # what the junctions are for: the filled gap with 150 contig bases either side, aligned against the true genome
+        # (the synthetic truth) — the aligned junctions must reproduce it at least as well as the extrapolated ones
+        F, tot = 150, {"sw": 0, "ref": 0, "sw_rev": 0, "ref_rev": 0, "gaps": 0, "gaps_rev": 0}
+        for (fc, tc, fwd, f_sw, f_ref) in fills:
+            if tc != fc + 1 or fc >= len(inp.gaps) or len(contigs[fc]) < F or len(contigs[tc]) < F:
+                continue
+            gs, gl = inp.gaps[fc]
+            truth = _code(inp.genome[gs - F: gs + gl + F])
+            for name, fill in (("sw", f_sw), ("ref", f_ref)):
+                sc = orc.sw_align(P, _code(np.concatenate([contigs[fc][-F:], fill, contigs[tc][:F]])), truth)["score"]
+                tot[name] += sc
+                if not fwd:
+                    tot[name + "_rev"] += sc
+            tot["gaps"] += 1
+            tot["gaps_rev"] += not fwd
+        tot.update(cfg=cfg, n_filled=n_gap, n_moved=int(n_moved))
+        print("sw_fill quality:", json.dumps(tot))
+        out_dir = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(out_dir):
+            json.dump(tot, open(os.path.join(out_dir, "sw_fill_quality_%s_%s.json" % (cfg, "runs" if env else "dense")), "w"))
+        assert tot["gaps"] > 0 and tot["sw"] >= tot["ref"], tot
