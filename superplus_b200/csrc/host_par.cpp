@@ -11,6 +11,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <functional>
@@ -20,39 +22,84 @@
 
 #include "host_par.h"
 
+// The pool is used once per pipeline chunk — every ~100-400 us during a search — so what a job costs beyond its tasks
+// matters: workers parked on a condition variable took 40-60 us to get going (16 threads re-acquiring one mutex), a
+// third of an 8 MiB gather.  Workers therefore keep polling the generation counter for GCG_POOL_SPIN_US (default 300 us)
+// after their last task before they go to sleep, tasks are handed out by compare-and-swap on one word that carries
+// the job's generation (a late worker can never take a ticket of a job it has not read), and the waiter polls too.
 struct gcg_workers {
   std::vector<std::thread> th;
   std::mutex mu;
   std::condition_variable cv_go, cv_done;
-  const std::function<void (int64_t)> * job = nullptr;
-  int64_t n_task = 0, next = 0, running = 0;
-  uint64_t gen = 0;
-  bool stop = false;
+  std::atomic<const std::function<void (int64_t)> *> job {nullptr};     // written before gen is advanced, read after it was seen
+  std::atomic<int64_t> n_task {0};
+  std::atomic<uint64_t> njob {0};                            // (generation << 32) | number of tasks: what a worker trusts
+  std::atomic<uint64_t> gen {0};
+  std::atomic<uint64_t> ticket {0};                          // (generation << 32) | next task
+  std::atomic<int64_t> done {0};                             // tasks of the current job that have finished
+  std::atomic<int> sleepers {0};
+  std::atomic<bool> stop {false};
+  std::atomic<bool> busy {false};                            // a job is out (the one-job rule)
+  int64_t spin_us = 300;
 };
+
+static inline int64_t now_us ()
+{
+  return std::chrono::duration_cast<std::chrono::microseconds> (std::chrono::steady_clock::now ().time_since_epoch ()).count ();
+}
+
+// take tasks of generation g until none is left (or the pool has moved on)
+static void take_tasks (gcg_workers * w, uint64_t g, const std::function<void (int64_t)> * fn, int64_t n)
+{
+  for (;;) {
+    uint64_t cur = w->ticket.load (std::memory_order_acquire);
+    if ((cur >> 32) != (g & 0xFFFFFFFFu) || (int64_t) (cur & 0xFFFFFFFFu) >= n) return;
+    if (!w->ticket.compare_exchange_weak (cur, cur + 1, std::memory_order_acq_rel)) continue;
+    (*fn) ((int64_t) (cur & 0xFFFFFFFFu));
+    if (w->done.fetch_add (1, std::memory_order_acq_rel) + 1 == n) {
+      std::lock_guard<std::mutex> lk (w->mu);              // (a waiter that went to sleep is woken; one that polls sees `done`)
+      w->cv_done.notify_all ();
+    }
+  }
+}
 
 static void worker_main (gcg_workers * w)
 {
   uint64_t seen = 0;
-  std::unique_lock<std::mutex> lk (w->mu);
   for (;;) {
-    w->cv_go.wait (lk, [&] () { return w->stop || w->gen != seen; });
-    if (w->stop) return;
-    seen = w->gen;
-    while (w->next < w->n_task) {
-      int64_t i = w->next++;
-      ++w->running;
-      lk.unlock ();
-      (*w->job) (i);
-      lk.lock ();
-      --w->running;
+    uint64_t g = w->gen.load ();
+    if (g == seen && !w->stop.load ()) {
+      const int64_t t_end = now_us () + w->spin_us;
+      for (int it = 0;; ++it) {
+        g = w->gen.load ();
+        if (g != seen || w->stop.load ()) break;
+        _mm_pause ();
+        if ((it & 63) == 63 && now_us () >= t_end) break;
+      }
+      if (g == seen && !w->stop.load ()) {
+        std::unique_lock<std::mutex> lk (w->mu);
+        w->sleepers.fetch_add (1);
+        w->cv_go.wait (lk, [&] () { return w->stop.load () || w->gen.load () != seen; });
+        w->sleepers.fetch_sub (1);
+        g = w->gen.load ();
+      }
     }
-    if (w->running == 0) w->cv_done.notify_all ();
+    if (w->stop.load ()) return;
+    seen = g;
+    // The task count is read together with its generation: a worker that slept through job g must not pair the count
+    // of job g + 1 (being posted) with the tickets of job g.  The function pointer may belong to a later job only when
+    // job g has finished, and then it has no tickets left.
+    const uint64_t nj = w->njob.load ();
+    if ((nj >> 32) != (g & 0xFFFFFFFFu)) continue;
+    const std::function<void (int64_t)> * fn = w->job.load ();
+    if (fn != nullptr) take_tasks (w, g, fn, (int64_t) (nj & 0xFFFFFFFFu));
   }
 }
 
 gcg_workers * gcg_workers_create (int n_thread)
 {
   gcg_workers * w = new gcg_workers ();
+  if (const char * e = getenv ("GCG_POOL_SPIN_US")) w->spin_us = std::max (0, atoi (e));
   for (int i = 1; i < n_thread; ++i) w->th.emplace_back (worker_main, w);     // the caller is worker 0
   return w;
 }
@@ -62,54 +109,72 @@ int gcg_workers_count (const gcg_workers * w) { return w ? (int) w->th.size () +
 void gcg_workers_destroy (gcg_workers * w)
 {
   if (!w) return;
-  { std::lock_guard<std::mutex> lk (w->mu); w->stop = true; }
+  { std::lock_guard<std::mutex> lk (w->mu); w->stop.store (true); }
   w->cv_go.notify_all ();
   for (auto & t : w->th) t.join ();
   delete w;
 }
 
+// publish a job; false when one is already out (the caller then runs its tasks itself)
+static bool post_job (gcg_workers * w, int64_t n_task, const std::function<void (int64_t)> & fn)
+{
+  bool expect = false;
+  if (!w->busy.compare_exchange_strong (expect, true)) return false;
+  const uint64_t g = w->gen.load () + 1;
+  w->job.store (&fn); w->n_task.store (n_task);
+  w->njob.store (((g & 0xFFFFFFFFu) << 32) | (uint64_t) n_task);
+  w->done.store (0);
+  w->ticket.store ((g & 0xFFFFFFFFu) << 32, std::memory_order_release);
+  w->gen.store (g);
+  if (w->sleepers.load () > 0) { std::lock_guard<std::mutex> lk (w->mu); w->cv_go.notify_all (); }
+  return true;
+}
+
+static void wait_job (gcg_workers * w)
+{
+  const int64_t n = w->n_task.load ();
+  const int64_t t_end = now_us () + 2000;
+  for (int it = 0; w->done.load (std::memory_order_acquire) < n; ++it) {
+    _mm_pause ();
+    if ((it & 63) == 63 && now_us () >= t_end) {           // a long job: sleep until the last task reports
+      std::unique_lock<std::mutex> lk (w->mu);
+      w->cv_done.wait (lk, [&] () { return w->done.load () >= n; });
+      break;
+    }
+  }
+  w->job.store (nullptr);
+  w->busy.store (false);
+}
+
 // The pool holds ONE job at a time.  A second job offered while an asynchronous one is still out
-// (gcg_workers_start without its gcg_workers_wait) must not touch job / n_task / next / running — that
-// would drop the tasks of the first job nobody has taken yet — so it runs on the calling thread.
+// (gcg_workers_start without its gcg_workers_wait) must not touch the first one's state — that
+// would drop the tasks nobody has taken yet — so it runs on the calling thread.
 void gcg_workers_run (gcg_workers * w, int64_t n_task, const std::function<void (int64_t)> & fn)
 {
-  if (!w || w->th.empty () || n_task <= 1) { for (int64_t i = 0; i < n_task; ++i) fn (i); return; }
-  std::unique_lock<std::mutex> lk (w->mu);
-  if (w->job != nullptr) { lk.unlock (); for (int64_t i = 0; i < n_task; ++i) fn (i); return; }
-  w->job = &fn; w->n_task = n_task; w->next = 0; w->running = 0;
-  ++w->gen;
-  w->cv_go.notify_all ();
-  while (w->next < w->n_task) {            // the caller takes tasks too
-    int64_t i = w->next++;
-    ++w->running;
-    lk.unlock ();
-    fn (i);
-    lk.lock ();
-    --w->running;
-  }
-  w->cv_done.wait (lk, [&] () { return w->running == 0 && w->next >= w->n_task; });
-  w->job = nullptr;
+  if (!w || w->th.empty () || n_task <= 1 || n_task >= 0x7FFFFFFF || !post_job (w, n_task, fn)) { for (int64_t i = 0; i < n_task; ++i) fn (i); return; }
+  take_tasks (w, w->gen.load (), &fn, n_task);              // the caller takes tasks too
+  wait_job (w);
 }
 
 // asynchronous form: the pool works on fn while the caller does something else; the caller does not
 // take tasks.  gcg_workers_wait() returns when all tasks are done.  fn must stay alive until then.
 void gcg_workers_start (gcg_workers * w, int64_t n_task, const std::function<void (int64_t)> & fn)
 {
-  if (!w || w->th.empty ()) { for (int64_t i = 0; i < n_task; ++i) fn (i); return; }
-  std::unique_lock<std::mutex> lk (w->mu);
-  if (w->job != nullptr) { lk.unlock (); for (int64_t i = 0; i < n_task; ++i) fn (i); return; }   // (see gcg_workers_run)
-  w->job = &fn; w->n_task = n_task; w->next = 0; w->running = 0;
-  ++w->gen;
-  w->cv_go.notify_all ();
+  if (!w || w->th.empty () || n_task >= 0x7FFFFFFF || !post_job (w, n_task, fn)) { for (int64_t i = 0; i < n_task; ++i) fn (i); return; }
+}
+
+// true when nothing is out or the job that is out has finished all its tasks (gcg_workers_wait then returns at once)
+bool gcg_workers_idle (gcg_workers * w)
+{
+  if (!w || w->th.empty () || !w->busy.load ()) return true;
+  return w->done.load (std::memory_order_acquire) >= w->n_task.load ();
 }
 
 void gcg_workers_wait (gcg_workers * w)
 {
   if (!w || w->th.empty ()) return;
-  std::unique_lock<std::mutex> lk (w->mu);
-  if (w->job == nullptr) return;                    // nothing out (the job ran inline, or was waited for already)
-  w->cv_done.wait (lk, [&] () { return w->running == 0 && w->next >= w->n_task; });
-  w->job = nullptr;
+  if (!w->busy.load ()) return;                     // nothing out (the job ran inline, or was waited for already)
+  wait_job (w);
 }
 
 // Self-test of the one-job rule (tests/test_host_logic.py): an asynchronous job of n_async slow tasks is

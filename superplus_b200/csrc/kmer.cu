@@ -1941,6 +1941,14 @@ struct pipe_slot {
   int64_t first_read = 0, n_read = 0;
 };
 
+// direct mode: the anchors of everything launched so far are complete when this runs (stream order behind the chunk's
+// search kernel) — tell the host, which queues their download (a kernel start also posts, but the next kernel may wait
+// a long time for its upload)
+__global__ void post_count_kernel (const unsigned long long * __restrict__ total, unsigned long long * done_out)
+{
+  *done_out = *total;
+}
+
 struct gcg_pipe {
   int64_t cap_words = 0;
   size_t meta_cap = 0;
@@ -1950,6 +1958,7 @@ struct gcg_pipe {
   unsigned long long * h_count = nullptr;            // pinned + mapped, one per slot: the search kernel stores the chunk's anchor
   unsigned long long * hd_count = nullptr;           // count straight into host memory (device alias of h_count) — a copy of
                                                      // 8 bytes would queue behind the anchor downloads on the D2H copy engine
+  cudaEvent_t ev_down[2] = {nullptr, nullptr};       // direct mode: behind the last two queued pieces of the download
   unsigned long long * d_run = nullptr;              // zero copy: running anchor count, two words used alternately (a launch
                                                      // reads one and writes the other: late blocks must not see their own total)
   int64_t last_total = 0;                            // anchors of the previous call: sizes the next result buffer
@@ -1968,6 +1977,7 @@ void gcg_pipe_free (gcg_ctx * ctx)
     for (cudaEvent_t e : {q.ev_up, q.ev_emit, q.ev_free}) if (e) cudaEventDestroy (e);
   }
   if (p->h_count) cudaFreeHost (p->h_count);
+  for (cudaEvent_t e : p->ev_down) if (e) cudaEventDestroy (e);
   cudaFree (p->d_run);
   if (p->up) cudaStreamDestroy (p->up);
   if (p->down) cudaStreamDestroy (p->down);
@@ -1999,6 +2009,7 @@ static int pipe_reserve (gcg_ctx * ctx, int64_t cap_words, bool staged)
   if (p->meta_cap < tiles * 4 + (1 << 20)) p->meta_cap = tiles * 4 + (1 << 20);
   GCG_CUDA (cudaStreamCreateWithFlags (&p->up, cudaStreamNonBlocking));
   GCG_CUDA (cudaStreamCreateWithFlags (&p->down, cudaStreamNonBlocking));
+  for (cudaEvent_t & e : p->ev_down) GCG_CUDA (cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
   GCG_CUDA (cudaHostAlloc (&p->h_count, PIPE_SLOTS * sizeof (unsigned long long), cudaHostAllocMapped));
   GCG_CUDA (cudaHostGetDevicePointer (&p->hd_count, p->h_count, 0));
   GCG_CUDA (cudaMalloc (&p->d_run, 2 * sizeof (unsigned long long)));
@@ -2158,6 +2169,13 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const read_source & s
   auto ms = [] (std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli> (b - a).count (); };
   gcg_workers * pool = gcg_ctx_workers (ctx);
   std::function<void (int64_t)> gather_fn;
+  // GCG_TIMELINE=1: per chunk, when its gather was done and it was submitted (host clock) and when its upload and its
+  // kernel ended (device clock), all in ms after the start of the pass
+  struct tl_rec { double gathered = 0, submitted = 0; cudaEvent_t up = nullptr, kern = nullptr; int64_t words = 0; };
+  const bool timeline = getenv ("GCG_TIMELINE") != nullptr;
+  std::vector<tl_rec> tlv;
+  cudaEvent_t tl_ref = nullptr;
+  std::chrono::steady_clock::time_point tl_t0;
 
   // chunk starting at read r0: whole reads, at most cap_words words, meta within the slot's meta block;
   // waits for its slot and writes the meta block (host work that overlaps the gather of the chunk before)
@@ -2230,15 +2248,27 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const read_source & s
     gcg_workers_start (pool, n_task, gather_fn);
   };
 
-  // direct mode: queue the download of the anchors that have become complete since the last look (at least min_bytes)
+  // direct mode: queue the download of the anchors that have become complete since the last look (at least min_bytes),
+  // in pieces of at most DOWN_PIECE bytes, two in flight: the uploads of the next chunks are on the critical path, and
+  // behind a burst of queued downloads they slow to a third (measured: 0.5 MB up in 155 us behind 8 MB of queued
+  // pieces), while one piece at a time leaves the download stream idle between polls
+  const size_t DOWN_PIECE = (size_t) 2 << 20;
+  int down_n = 0;                                   // pieces queued so far (piece i is followed by ev_down[i & 1])
   auto download_ready = [&] (size_t min_bytes) -> int {
-    const int64_t done = std::min<int64_t> ((int64_t) *(volatile unsigned long long *) p->h_count, (int64_t) win_hi);
-    const int64_t from = std::max<int64_t> (copied, (int64_t) win_lo);
-    if (done > from && (size_t) (done - from) * res.rec >= min_bytes) {
-      GCG_CUDA (cudaMemcpyAsync (res.buf + (size_t) from * res.rec, (char *) d_res + (size_t) from * res.rec, (size_t) (done - from) * res.rec, cudaMemcpyDeviceToHost, p->down));
-      copied = done;
+    for (;;) {
+      const int64_t done = std::min<int64_t> ((int64_t) *(volatile unsigned long long *) p->h_count, (int64_t) win_hi);
+      const int64_t from = std::max<int64_t> (copied, (int64_t) win_lo);
+      if (done <= from || (size_t) (done - from) * res.rec < min_bytes) return GCG_OK;
+      if (down_n >= 2) {                            // the piece before the last one must have landed
+        if (cudaEventQuery (p->ev_down[down_n & 1]) == cudaErrorNotReady) return GCG_OK;
+        cudaGetLastError ();
+      }
+      const int64_t to = std::min<int64_t> (done, from + (int64_t) (DOWN_PIECE / res.rec));
+      GCG_CUDA (cudaMemcpyAsync (res.buf + (size_t) from * res.rec, (char *) d_res + (size_t) from * res.rec, (size_t) (to - from) * res.rec, cudaMemcpyDeviceToHost, p->down));
+      GCG_CUDA (cudaEventRecord (p->ev_down[down_n & 1], p->down));
+      ++down_n;
+      copied = to;
     }
-    return GCG_OK;
   };
 
   // copy the gathered chunk to the device and enqueue its kernel: probe, ordered anchor index, ONT-side
@@ -2251,6 +2281,12 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const read_source & s
     GCG_CUDA (cudaMemcpyAsync (q.d_meta, q.h_meta, meta_bytes, cudaMemcpyHostToDevice, p->up));
     GCG_CUDA (cudaEventRecord (q.ev_up, p->up));
     GCG_CUDA (cudaStreamWaitEvent (ctx->stream, q.ev_up, 0));
+    if (timeline) {
+      tl_rec & tr = tlv.back ();
+      tr.words = nw; tr.submitted = ms (tl_t0, now ());
+      cudaEventCreate (&tr.up); cudaEventCreate (&tr.kern);
+      cudaEventRecord (tr.up, p->up);
+    }
     const int64_t * d_woff = (const int64_t *) q.d_meta;
     const int32_t * d_len = (const int32_t *) (q.d_meta + (size_t) (nr + 1) * 8);
     const int32_t * d_tseq = (const int32_t *) (q.d_meta + d.tseq_off);
@@ -2264,6 +2300,11 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const read_source & s
       ++n_sub;
       if (e) return e;
       GCG_CUDA (cudaEventRecord (q.ev_free, ctx->stream));         // the slot is free again when its kernel has finished
+      if (timeline) cudaEventRecord (tlv.back ().kern, ctx->stream);
+      if (mode == 1 && !keep) {
+        post_count_kernel<<<1, 1, 0, ctx->stream>>> (p->d_run + (n_sub & 1), p->hd_count);      // (n_sub was advanced: the word this launch wrote)
+        GCG_CUDA (cudaGetLastError ());
+      }
       q.busy = true;
       if (mode == 1 && !keep) return download_ready ((size_t) 1 << 20);     // whatever earlier launches have completed by now goes down
       return GCG_OK;
@@ -2289,6 +2330,8 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const read_source & s
     if (zc) GCG_CUDA (cudaMemsetAsync (p->d_run, 0, 2 * sizeof (unsigned long long), ctx->stream));
     p->h_count[0] = 0;
     copied = 0;
+    down_n = 0;
+    if (timeline) { tlv.clear (); cudaEventCreate (&tl_ref); cudaEventRecord (tl_ref, p->up); tl_t0 = now (); }
     prc = plan (0, cur_c);
     bool gathering = !prc && cur_c.kmers > 0 && !cur_c.direct;
     if (gathering) start_gather (cur_c);
@@ -2301,9 +2344,15 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const read_source & s
         t_prepare += ms (t1, now ());
       }
       auto t0 = now ();
-      if (gathering) gcg_workers_wait (pool);
+      if (gathering) {
+        // (the download stream is fed while the pool gathers: the host thread has nothing else to do)
+        if (mode == 1 && !keep)
+          while (!prc && !gcg_workers_idle (pool)) { prc = download_ready ((size_t) 1 << 19); for (int i = 0; i < 32; ++i) _mm_pause (); }
+        gcg_workers_wait (pool);
+      }
       t_gather += ms (t0, now ());
       gathering = false;
+      if (timeline) { tlv.emplace_back (); tlv.back ().gathered = ms (tl_t0, now ()); }
       if (prc) break;
       if (more && next_c.kmers > 0 && !next_c.direct) { start_gather (next_c); gathering = true; }
       if (cur_c.kmers > 0) {
@@ -2339,12 +2388,28 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const read_source & s
       }
       cudaGetLastError ();
     }
-    if (zc && !prc && n_sub > 0 &&
+    bool have_total = false;
+    if (mode == 1 && !keep && !prc && n_sub > 0 && cudaStreamQuery (ctx->stream) == cudaSuccess) {
+      ctx->h_counters[4] = *(volatile unsigned long long *) p->h_count;      // the last launch's post_count_kernel has run
+      have_total = true;
+    }
+    cudaGetLastError ();
+    if (zc && !prc && n_sub > 0 && !have_total &&
         cudaMemcpyAsync (ctx->h_counters + 4, p->d_run + (n_sub & 1), 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_search: count copy failed"); prc = GCG_ECUDA; }
     if (cudaStreamSynchronize (p->down) != cudaSuccess || cudaStreamSynchronize (ctx->stream) != cudaSuccess) {
       if (!prc) { gcg_set_error ("gcg_search: %s", cudaGetErrorString (cudaGetLastError ())); prc = GCG_ECUDA; }
     }
     t_drain += ms (t_d0, now ());
+    if (timeline) {
+      fprintf (stderr, "[gcg]   timeline (ms after the start of the pass; drain began at %.3f, pass ended at %.3f)\n", ms (tl_t0, t_d0), ms (tl_t0, now ()));
+      for (size_t i = 0; i < tlv.size (); ++i) {
+        tl_rec & tr = tlv[i];
+        float up = -1, kn = -1;
+        if (tr.up) { cudaEventElapsedTime (&up, tl_ref, tr.up); cudaEventElapsedTime (&kn, tl_ref, tr.kern); cudaEventDestroy (tr.up); cudaEventDestroy (tr.kern); }
+        fprintf (stderr, "[gcg]     chunk %2zu %6.2f MiB: gathered %.3f submitted %.3f uploaded %.3f kernel done %.3f\n", i, (double) tr.words * 32 / (1 << 20), tr.gathered, tr.submitted, up, kn);
+      }
+      cudaEventDestroy (tl_ref);
+    }
     for (pipe_slot & q : p->s) { q.busy = false; q.pending = false; }
     return prc;
   };
