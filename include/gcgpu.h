@@ -94,6 +94,9 @@ int  gcg_host_pack_2bit (const char * seq, int64_t len, uint64_t * words_out);
  * asynchronous job of n_async tasks, offers a synchronous one of n_sync tasks while it is out, waits.
  * Returns n_async * 1000 + n_sync when every task ran exactly once. */
 int64_t gcg_selftest_workers (int n_thread, int n_async, int n_sync);
+/* stress of the pool's task hand-out (spinning / sleeping workers, tickets by compare-and-swap): n_job jobs of 1..97
+ * tasks back to back; spin_us < 0 keeps the default spin time.  Returns 0 when every task ran exactly once in its job. */
+int64_t gcg_selftest_workers_stress (int n_thread, int n_job, int spin_us);
 
 /* ------------------------------------------------------------------ contig k-mers ---- */
 /* replaces chop_contig_seqs2kmers (kmer.c:155-184 / 37-121): one 24-byte record per contig

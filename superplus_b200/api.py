@@ -32,7 +32,7 @@ EXPORTS = [
     "gcg_chop_contigs", "gcg_table_build_seqs", "gcg_table_build", "gcg_table_free", "gcg_table_stats",
     "gcg_table_size", "gcg_table_dump", "gcg_table_clone", "gcg_table_merge_ont",
     "gcg_search_seqs", "gcg_hits_count", "gcg_hits_download", "gcg_hits_free", "gcg_search", "gcg_free",
-    "gcg_search_compact", "gcg_search_seqs_compact", "gcg_hits_download_compact", "gcg_selftest_workers", "gcg_host_alloc", "gcg_search_runs", "gcg_search_compact_packed", "gcg_search_runs_packed",
+    "gcg_search_compact", "gcg_search_seqs_compact", "gcg_hits_download_compact", "gcg_selftest_workers", "gcg_selftest_workers_stress", "gcg_host_alloc", "gcg_search_runs", "gcg_search_compact_packed", "gcg_search_runs_packed",
     "gcg_table_create_shared", "gcg_table_reset_shared", "gcg_table_shared_info", "gcg_search_seqs_remote",
     "gcg_sw_batch", "gcg_sw_batch_multi", "gcg_swbatch_upload", "gcg_swbatch_align", "gcg_swbatch_download", "gcg_swbatch_cells",
     "gcg_swbatch_path_counts", "gcg_swbatch_free",

@@ -170,6 +170,23 @@ bool gcg_workers_idle (gcg_workers * w)
   return w->done.load (std::memory_order_acquire) >= w->n_task.load ();
 }
 
+// the caller of an asynchronous job lends a hand: runs ONE task of the job that is out, if one is left
+bool gcg_workers_help (gcg_workers * w)
+{
+  if (!w || w->th.empty () || !w->busy.load ()) return false;
+  const uint64_t g = w->gen.load ();
+  const std::function<void (int64_t)> * fn = w->job.load ();
+  const int64_t n = w->n_task.load ();               // (the caller posted this job itself: nothing can be stale)
+  for (;;) {
+    uint64_t cur = w->ticket.load (std::memory_order_acquire);
+    if ((cur >> 32) != (g & 0xFFFFFFFFu) || (int64_t) (cur & 0xFFFFFFFFu) >= n || fn == nullptr) return false;
+    if (!w->ticket.compare_exchange_weak (cur, cur + 1, std::memory_order_acq_rel)) continue;
+    (*fn) ((int64_t) (cur & 0xFFFFFFFFu));
+    w->done.fetch_add (1, std::memory_order_acq_rel);      // (the caller is the only waiter and it is here: nobody to wake)
+    return true;
+  }
+}
+
 void gcg_workers_wait (gcg_workers * w)
 {
   if (!w || w->th.empty ()) return;
@@ -195,6 +212,34 @@ extern "C" int64_t gcg_selftest_workers (int n_thread, int n_async, int n_sync)
   for (int v : a) na += v;
   for (int v : b) nb += v;
   return na * 1000 + nb / 2;
+}
+
+// Stress of the pool's hand-out (tests/test_host_logic.py): n_job jobs of 1..97 tasks back to back, alternately
+// synchronous and asynchronous (some with a second job offered meanwhile); every task must run exactly once in ITS job —
+// a worker that slept through a job must not pair the next job's task count or function with the old job's tickets.
+// Returns 0 when all is well, else the 1-based number of the first job that went wrong.
+extern "C" int64_t gcg_selftest_workers_stress (int n_thread, int n_job, int spin_us)
+{
+  gcg_workers * w = gcg_workers_create (n_thread);
+  if (spin_us >= 0) w->spin_us = spin_us;
+  int64_t bad = 0;
+  std::atomic<int64_t> extra {0};
+  int64_t want_extra = 0;
+  for (int rep = 0; rep < n_job && !bad; ++rep) {
+    const int n = 1 + rep % 97;
+    std::vector<int> hit ((size_t) n, 0);
+    std::function<void (int64_t)> fn = [&] (int64_t i) { hit[(size_t) i] += 1; };
+    if (rep & 1) gcg_workers_run (w, n, fn);
+    else {
+      gcg_workers_start (w, n, fn);
+      if (rep % 6 == 0) { std::function<void (int64_t)> f2 = [&] (int64_t) { extra.fetch_add (1); }; gcg_workers_run (w, 3, f2); want_extra += 3; }
+      gcg_workers_wait (w);
+    }
+    for (int i = 0; i < n; ++i) if (hit[(size_t) i] != 1) bad = rep + 1;
+  }
+  gcg_workers_destroy (w);
+  if (!bad && extra.load () != want_extra) bad = n_job + 1;
+  return bad;
 }
 
 void gcg_copy_stream (void * dst_, const void * src_, size_t n)

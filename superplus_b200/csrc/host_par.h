@@ -16,6 +16,8 @@ void gcg_workers_start (gcg_workers * w, int64_t n_task, const std::function<voi
 void gcg_workers_wait (gcg_workers * w);
 // true when no asynchronous job is out, or all of its tasks have finished (the wait returns at once)
 bool gcg_workers_idle (gcg_workers * w);
+// the thread that started the asynchronous job runs one of its tasks (false: none left)
+bool gcg_workers_help (gcg_workers * w);
 // memcpy with non-temporal stores when dst is 16-byte aligned; gcg_copy_fence() before a DMA reads dst
 void gcg_copy_stream (void * dst, const void * src, size_t n);
 void gcg_copy_fence (void);

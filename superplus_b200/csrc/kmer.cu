@@ -175,12 +175,12 @@ k4_probe_tile (k4_smem & sm, const unsigned long long * __restrict__ vals, const
     GCG_DEV_ASSERT (s >= 0 && s < n_seq && p0 >= 0 && (p0 < L || L == 0) && __ldg (woff + s) <= w && w < __ldg (woff + s + 1));
     nvalid = L - k + 1 - p0;
     nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
-    pk = __ldg (packed + w);
+    pk = __ldcg (packed + w);                       // (.cg: the words may be arriving by DMA while this launch runs — streaming search —, and are read once)
   }
   *pk_out = pk; *seq_out = sq; *p0_out = p0;
   if (nvalid) {
     kroll r;
-    r.init (pk, __ldg (packed + w + 1), k);
+    r.init (pk, __ldcg (packed + w + 1), k);
     for (int j0 = 0; j0 < nvalid; j0 += K4_UNROLL) {
       unsigned long long key[K4_UNROLL];
       uint32_t fp[K4_UNROLL], bk[K4_UNROLL];
@@ -258,7 +258,7 @@ k4_probe_tile (k4_smem & sm, const unsigned long long * __restrict__ vals, const
       GCG_DEV_ASSERT (lo >= 0 && lo < 32 && j >= 0 && j < 32 && sm.excl[wid][lo] <= h && h < sm.excl[wid][lo + 1]);
       const int64_t ww = (tile << 5) + lo;
       bool fw;
-      unsigned long long kw, key = key_at (__ldg (packed + ww), __ldg (packed + ww + 1), j, k, &fw);
+      unsigned long long kw, key = key_at (__ldcg (packed + ww), __ldcg (packed + ww + 1), j, k, &fw);
       const unsigned long long * tk = keys;
       uint32_t nb = n_bucket;
       if (PART) { const gcg_part_desc pd = parts[kmer_owner (key - 1ULL, n_part)]; tk = pd.keys; nb = pd.n_bucket; }
@@ -351,6 +351,12 @@ struct k45f_args {
                                             // anchors that are COMPLETE in `out` (every earlier launch has finished)
   const gcg_part_desc * parts;              // remote-probe search: the partitions of the table (device array), else NULL
   uint32_t n_part;
+  // streaming search (one launch over reads that are still being uploaded, search_host_stream):
+  const unsigned long long * ready;         // optional: number of words of `packed` that have arrived (device word, written in the upload
+                                            // stream's order behind the words themselves); a warp waits for its tile's words + 1
+  unsigned int * group_cnt;                 // optional: one counter per group of 2^group_shift block tiles, zeroed before the launch
+  unsigned long long * group_done;          // (mapped host memory) [group]: 1 + number of anchors complete in `out` once every tile up to the
+  int group_shift;                          // group's last one has been emitted AND all groups before it report too (the host reads in order)
 };
 
 // Build-time switches (A/B variants, scripts/build_variants.sh):
@@ -407,6 +413,7 @@ chain_lookback (unsigned long long * __restrict__ state, const int64_t idx, cons
 
 // bounded spin: a protocol error must end in a trap with a message, not in a hung GPU
 #define K45F_SPIN_LIMIT (1u << 24)
+#define K45F_STREAM_TIMEOUT_NS 120000000000ULL        // streaming search: two minutes without the next words of the reads
 #define K45F_SPIN_FAIL(what) do { printf ("k45_fused_kernel: %s never arrived (block %d warp %d)\n", what, (int) blockIdx.x, (int) (threadIdx.x >> 5)); __trap (); } while (0)
 
 // the anchors of one staged tile, 32 per round, at their global indices base .. base + total
@@ -515,6 +522,24 @@ k45_fused_kernel (const k45f_args A)
     uint32_t total = 0;
     if (live) {
       const int64_t tile = bt * K4_WARPS + wid;          // may be past the end in the last block tile: probes nothing
+      if (A.ready != nullptr && (tile << 5) < A.n_words) {
+        // streaming: this tile's words (and the one behind them, which the last lane's k-mers run into) must have arrived
+        if (lane == 0) {
+          const unsigned long long need = (unsigned long long) (((tile + 1) << 5) < A.n_words ? ((tile + 1) << 5) + 1 : A.n_words + 1);
+          if (*(volatile const unsigned long long *) A.ready < need) {
+            unsigned long long t0;
+            asm volatile ("mov.u64 %0, %%globaltimer;" : "=l" (t0));
+            while (*(volatile const unsigned long long *) A.ready < need) {
+              __nanosleep (200);
+              unsigned long long t1;
+              asm volatile ("mov.u64 %0, %%globaltimer;" : "=l" (t1));
+              if (t1 - t0 > K45F_STREAM_TIMEOUT_NS) K45F_SPIN_FAIL ("the upload of a tile's words");
+            }
+          }
+          __threadfence ();
+        }
+        __syncwarp ();
+      }
       uint64_t pk; int32_t sq, p0;
       const uint32_t mymask = k4_probe_tile<FILTER, KC, K45F_PREFETCH != 0 && !PART, PART> (sm, A.vals, tile, A.packed, A.woff, A.len, A.tile_seq, A.n_seq, A.n_words, k, A.keys, A.n_bucket,
                                                                                             A.filter, A.filter_words, A.filter_k3, &pk, &sq, &p0, A.parts, A.n_part);
@@ -530,7 +555,7 @@ k45_fused_kernel (const k45f_args A)
       s_pk[q2][wid][lane] = pk;
       s_seq[q2][wid][lane] = w < A.n_words ? sq : -1;
       s_p0[q2][wid][lane] = p0;
-      if (lane == 31) { s_excl[q2][wid][32] = total; s_pk[q2][wid][32] = w + 1 <= A.n_words ? __ldg (A.packed + w + 1) : 0ULL; }   // (slack word at n_words)
+      if (lane == 31) { s_excl[q2][wid][32] = total; s_pk[q2][wid][32] = w + 1 <= A.n_words ? __ldcg (A.packed + w + 1) : 0ULL; }   // (slack word at n_words)
       // ---- count in; the first arrival claims the next round's block tile, the last one publishes this tile's count
       if (lane == 0) {
         s_wtot[qs][wid] = total;
@@ -625,6 +650,23 @@ k45_fused_kernel (const k45f_args A)
       if (prev_total) k45f_emit_tile<FMT, PART> (A, k, lane, base, base0, prev_total, s_excl[p2][wid], s_mask[p2][wid], s_pk[p2][wid], s_seq[p2][wid], s_p0[p2][wid]);
 #endif
       __syncwarp ();
+      if (A.group_cnt != nullptr) {
+        // streaming: the last warp to finish a group of block tiles tells the host how many anchors are complete up to
+        // the group's end (the inclusive prefix of its last block tile: resolved before any of its warps emitted)
+        __threadfence ();
+        if (lane == 0) {
+          const int64_t g = prev_bt >> A.group_shift;
+          const int64_t g_end = ((g + 1) << A.group_shift) < n_bt ? ((g + 1) << A.group_shift) : n_bt;
+          const unsigned int want = (unsigned int) (g_end - (g << A.group_shift)) * K4_WARPS;
+          if (atomicAdd (A.group_cnt + g, 1u) + 1u == want) {
+            __threadfence ();
+            const unsigned long long inc = ld_state (A.state + g_end - 1);
+            GCG_DEV_ASSERT ((inc & SCANST_INC) != 0);
+            *(volatile unsigned long long *) (A.group_done + g) = (inc & SCANST_VAL) + 1ULL;
+            __threadfence_system ();
+          }
+        }
+      }
     }
     if (!live) break;
     prev_total = total;
@@ -1601,12 +1643,15 @@ extern "C" void gcg_hits_free (gcg_hits * h)
 extern "C" int64_t gcg_hits_count (const gcg_hits * h) { return h ? h->n : 0; }
 
 // ---- the one-pass search: launch helper -------------------------------------------------------
+// (streaming search: where the launch finds out which words have arrived and where it reports finished groups of block tiles)
+struct fused_stream { const unsigned long long * ready; unsigned int * group_cnt; unsigned long long * group_done; int group_shift; };
 // d_state holds n_tiles + 1 words (the last one is the tile counter); both are zeroed here.
 static int launch_fused (gcg_ctx * ctx, const gcg_table * t, const uint64_t * d_packed, const int64_t * d_woff, const int32_t * d_len,
                          const int32_t * d_tseq, int64_t n_seq, int64_t n_words, int k, int fmt, void * d_out,
                          unsigned long long win_lo, unsigned long long win_hi, int32_t read_base, long long * d_read_off,
                          unsigned long long * d_state, unsigned long long * total_out,
-                         const unsigned long long * base_in = nullptr, bool preset_read_off = false, unsigned long long * done_out = nullptr)
+                         const unsigned long long * base_in = nullptr, bool preset_read_off = false, unsigned long long * done_out = nullptr,
+                         const fused_stream * st = nullptr)
 {
   const int64_t n_tiles = (n_words + 31) >> 5;
   GCG_CUDA (cudaMemsetAsync (d_state, 0, (size_t) (n_tiles + 1) * 8, ctx->stream));
@@ -1619,6 +1664,10 @@ static int launch_fused (gcg_ctx * ctx, const gcg_table * t, const uint64_t * d_
   A.tile_ctr = d_state + n_tiles; A.state = d_state; A.out = d_out; A.win_lo = win_lo; A.win_hi = win_hi;
   A.read_base = read_base; A.cbase = t->d_cbase; A.read_off = d_read_off; A.total_out = total_out; A.base_in = base_in; A.done_out = done_out;
   A.parts = t->d_parts; A.n_part = (uint32_t) t->n_part;
+  A.ready = st ? st->ready : nullptr; A.group_cnt = st ? st->group_cnt : nullptr; A.group_done = st ? st->group_done : nullptr; A.group_shift = st ? st->group_shift : 0;
+#if K45F_BLOCKSCAN != 2
+  GCG_CHECK (st == nullptr, GCG_EINVAL, "gcg_search: this build's search kernel has no streaming form");
+#endif
   const int grid = grid_for (ctx, n_tiles * 32, 32 * K4_WARPS, 8);
 #if K45F_BLOCKSCAN == 2
   if (t->d_parts) {
@@ -2007,8 +2056,14 @@ static int pipe_reserve (gcg_ctx * ctx, int64_t cap_words, bool staged)
   p->meta_cap = (size_t) 2 << 20;
   const size_t tiles = (size_t) ((cap_words + 31) >> 5);
   if (p->meta_cap < tiles * 4 + (1 << 20)) p->meta_cap = tiles * 4 + (1 << 20);
-  GCG_CUDA (cudaStreamCreateWithFlags (&p->up, cudaStreamNonBlocking));
-  GCG_CUDA (cudaStreamCreateWithFlags (&p->down, cudaStreamNonBlocking));
+  {
+    // uploads are on the critical path of a search, downloads are not: ask for the upload stream to be served first
+    int prio_lo = 0, prio_hi = 0;
+    GCG_CUDA (cudaDeviceGetStreamPriorityRange (&prio_lo, &prio_hi));
+    const bool prio = getenv ("GCG_SEARCH_NO_PRIO") == nullptr;
+    GCG_CUDA (cudaStreamCreateWithPriority (&p->up, cudaStreamNonBlocking, prio ? prio_hi : prio_lo));
+    GCG_CUDA (cudaStreamCreateWithPriority (&p->down, cudaStreamNonBlocking, prio_lo));
+  }
   for (cudaEvent_t & e : p->ev_down) GCG_CUDA (cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
   GCG_CUDA (cudaHostAlloc (&p->h_count, PIPE_SLOTS * sizeof (unsigned long long), cudaHostAllocMapped));
   GCG_CUDA (cudaHostGetDevicePointer (&p->hd_count, p->h_count, 0));
@@ -2087,6 +2142,351 @@ struct search_dev_keep { void * d_anchors = nullptr; long long * d_read_off = nu
 // packs while it copies the bases): read i = words [pwoff[i], pwoff[i] + (len[i] + 31) / 32)
 struct read_source { const char * const * seq = nullptr; const uint64_t * packed = nullptr; const int64_t * pwoff = nullptr; };
 
+// ---- streaming search: ONE launch over reads that are still arriving ----------------------------------------------
+// The chunked pipeline below pays for every chunk's launch: the first wave of a launch resolves its chained scan hop by
+// hop, the last wave drains, and a chunk cannot start before its whole upload has landed — 60-70 us per launch, nine
+// launches per cfg2 search, and at the end of the gather the GPU is 0.5 ms behind (GCG_TIMELINE).  Here the search
+// kernel is launched ONCE, right after the table build, over device arrays sized for the whole read set; the host
+// gathers + packs the reads piece by piece (or takes the caller's packed words as they lie), every piece is followed on
+// the upload stream by an 8-byte copy that moves the kernel's `ready` word forward, and a warp whose tile has not
+// arrived yet polls that word.  Tiles are handed out in order, so whatever a warp waits for is the next thing the
+// host sends.  Finished groups of block tiles report their anchor count into mapped host memory; the host queues the
+// download of everything complete while it waits for the gather.  A result that overflows its estimate is finished by a
+// second launch over the words that are already on the device.
+__global__ void tile_seq_kernel (const int64_t * __restrict__ woff, int64_t n_seq, int64_t n_tiles, int32_t * __restrict__ tseq)
+{
+  const int64_t tile = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= n_tiles) return;
+  const int64_t w = tile << 5;
+  int64_t lo = 0, hi = n_seq;                        // the last read with woff <= w (empty reads share their successor's offset)
+  while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (__ldg (woff + mid) <= w) lo = mid; else hi = mid; }
+  tseq[tile] = (int32_t) lo;
+}
+
+static bool stream_mode_on (void)
+{
+#if K45F_BLOCKSCAN != 2
+  return false;
+#else
+  const char * e = getenv ("GCG_SEARCH_STREAM");
+  return !(e && atoi (e) == 0);
+#endif
+}
+
+static int search_host_stream (gcg_ctx * ctx, gcg_table * t, const read_source & src, const int32_t * read_len,
+                               int64_t n_read, int k, int fmt, void ** hits_out, int64_t * n_hit, int64_t ** read_off_out,
+                               search_dev_keep * keep, bool * handled)
+{
+  *handled = false;
+  if (!stream_mode_on () || t->d_parts != nullptr || n_read <= 0 || (!keep && pipe_mode () != 1)) return GCG_OK;
+  int64_t total_words = 0, total_kmers = 0, max_words = 0;
+  int32_t max_len = 0;
+  for (int64_t r = 0; r < n_read; ++r) {
+    if (read_len[r] < 0) return GCG_OK;              // (the chunked path reports it)
+    const int64_t w = ((int64_t) read_len[r] + 31) >> 5;
+    total_words += w; max_words = std::max (max_words, w); max_len = std::max (max_len, read_len[r]);
+    if (read_len[r] >= k) total_kmers += (int64_t) read_len[r] - k + 1;
+  }
+  int64_t limit_mb = 8192;
+  if (const char * e = getenv ("GCG_SEARCH_STREAM_MAX_MB")) limit_mb = std::max<int64_t> (0, atoll (e));
+  if (total_kmers == 0 || total_words * 8 > (limit_mb << 20) || (fmt && compact_limits_ok (t, max_len) != 0)) return GCG_OK;
+  *handled = true;
+
+  GCG_CUDA (cudaSetDevice (ctx->device));
+  gcg_trace_mark (ctx, nullptr);
+  bool packed_pinned = false;
+  if (src.packed) {
+    cudaPointerAttributes at;
+    packed_pinned = cudaPointerGetAttributes (&at, src.packed) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError ();
+  }
+  // pieces: 2, 4, 8, 8, ... MiB of bases (whole reads); a piece is gathered into one of the pipeline's pinned slots
+  int64_t piece_words = ((int64_t) 8 << 20) / 32, first_words = ((int64_t) 2 << 20) / 32, last_words = ((int64_t) 2 << 20) / 32;
+  if (const char * e = getenv ("GCG_SEARCH_PIECE_MB")) piece_words = std::max<int64_t> (1, atoll (e)) * (1 << 20) / 32;
+  if (const char * e = getenv ("GCG_SEARCH_PIECE_FIRST_MB")) first_words = std::max<int64_t> (1, atoll (e)) * (1 << 20) / 32;
+  if (const char * e = getenv ("GCG_SEARCH_PIECE_LAST_MB")) last_words = std::max<int64_t> (1, atoll (e)) * (1 << 20) / 32;
+  if (const char * e = getenv ("GCG_SEARCH_CHUNK_BYTES")) piece_words = first_words = last_words = std::max<int64_t> (1, atoll (e) / 32);      // (tests: many tiny pieces)
+  int rc = pipe_reserve (ctx, std::max (((int64_t) 32 << 20) / 32, std::max (piece_words, max_words)), false);
+  if (!rc) rc = gcg_table_filter_ensure (ctx, t);
+  if (rc) return rc;
+  gcg_pipe * p = ctx->pipe;
+  const int64_t cap_words = p->cap_words;
+  const int64_t n_tiles = (total_words + 31) >> 5, n_bt = (n_tiles + K4_WARPS - 1) / K4_WARPS;
+  const int group_shift = 8;                          // 256 block tiles = 2 M k-mers, about 1 MB of anchors at ONT error rates
+  const int64_t n_group = (n_bt + (1 << group_shift) - 1) >> group_shift;
+
+  search_result res;
+  res.ctx = ctx; res.fmt = fmt; res.rec = anchor_bytes (fmt);
+  res.cap = std::max<int64_t> (p->last_total + p->last_total / 8, total_kmers / 10) + 4096;
+  if (const char * e = getenv ("GCG_SEARCH_RES_CAP")) res.cap = std::max<int64_t> (1, atoll (e));     // test hook: force the second pass
+
+  // ---- host blocks (parked pinned blocks: no driver call in the steady state)
+  const size_t meta_bytes = (size_t) (n_read + 1) * 8 + (size_t) n_read * 4;
+  char * h_meta = (char *) gcg_pinned_alloc (meta_bytes);
+  unsigned long long * h_group = (unsigned long long *) gcg_pinned_alloc ((size_t) n_group * 8);
+  const int64_t max_pieces = total_words / std::max<int64_t> (1, std::min (first_words, piece_words)) + n_read + 8;
+  unsigned long long * h_ready = (unsigned long long *) gcg_pinned_alloc ((size_t) std::min<int64_t> (max_pieces, total_words + 8) * 8 + 64);
+  if (fmt) res.read_off = (int64_t *) gcg_pinned_alloc ((size_t) (n_read + 1) * 8);
+  if (!keep) res.buf = (char *) gcg_pinned_alloc ((size_t) res.cap * res.rec);
+  // ---- device blocks
+  uint64_t * d_packed = nullptr; char * d_meta = nullptr; int32_t * d_tseq = nullptr; unsigned long long * d_state = nullptr, * d_ready = nullptr;
+  unsigned int * d_group = nullptr; void * d_res = nullptr; long long * d_roff = nullptr; unsigned long long * hd_group = nullptr;
+  auto release = [&] () {
+    gcg_dfree (ctx, d_packed); gcg_dfree (ctx, d_meta); gcg_dfree (ctx, d_tseq); gcg_dfree (ctx, d_state); gcg_dfree (ctx, d_ready); gcg_dfree (ctx, d_group);
+    if (d_res) gcg_dfree (ctx, d_res);
+    if (d_roff) gcg_dfree (ctx, d_roff);
+    gcg_free (h_meta); gcg_free (h_group); gcg_free (h_ready);
+  };
+  auto fail = [&] (int code) { release (); gcg_free (res.buf); gcg_free (res.read_off); return code; };
+  if (!h_meta || !h_group || !h_ready || (fmt && !res.read_off) || (!keep && !res.buf)) { gcg_set_error ("gcg_search: pinned host memory for %lld reads / %lld anchors", (long long) n_read, (long long) res.cap); return fail (GCG_ENOMEM); }
+  cudaError_t e = gcg_dmalloc (ctx, &d_packed, (size_t) (total_words + 2) * 8);
+  if (e == cudaSuccess) e = gcg_dmalloc (ctx, &d_meta, meta_bytes);
+  if (e == cudaSuccess) e = gcg_dmalloc (ctx, &d_tseq, (size_t) n_tiles * 4);
+  if (e == cudaSuccess) e = gcg_dmalloc (ctx, &d_state, (size_t) (n_tiles + 1) * 8);
+  if (e == cudaSuccess) e = gcg_dmalloc (ctx, &d_ready, 64);
+  if (e == cudaSuccess) e = gcg_dmalloc (ctx, &d_group, (size_t) n_group * 4);
+  if (e == cudaSuccess) e = gcg_dmalloc (ctx, &d_res, (size_t) res.cap * res.rec);
+  if (e == cudaSuccess && fmt) e = gcg_dmalloc (ctx, &d_roff, (size_t) (n_read + 1) * 8);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer ((void **) &hd_group, h_group, 0);
+  if (e != cudaSuccess) { gcg_set_error ("gcg_search: device memory for %lld words / %lld anchors: %s", (long long) total_words, (long long) res.cap, cudaGetErrorString (e)); cudaGetLastError (); return fail (GCG_ENOMEM); }
+
+  // ---- meta: word offset and length of every read; the first read of every tile is found on the device
+  int64_t * woff = (int64_t *) h_meta;
+  int32_t * len = (int32_t *) (h_meta + (size_t) (n_read + 1) * 8);
+  {
+    int64_t w = 0;
+    for (int64_t r = 0; r < n_read; ++r) { woff[r] = w; len[r] = read_len[r]; w += ((int64_t) read_len[r] + 31) >> 5; }
+    woff[n_read] = w;
+  }
+  const int64_t * d_woff = (const int64_t *) d_meta;
+  const int32_t * d_len = (const int32_t *) (d_meta + (size_t) (n_read + 1) * 8);
+  pipe_slot & q0 = p->s[0];
+  h_ready[0] = 0;
+  cudaStream_t up = p->up, down = p->down, cs = ctx->stream;
+  if ((e = cudaMemcpyAsync (d_meta, h_meta, meta_bytes, cudaMemcpyHostToDevice, up)) != cudaSuccess ||
+      (e = cudaMemcpyAsync (d_ready, h_ready, 8, cudaMemcpyHostToDevice, up)) != cudaSuccess ||
+      (e = cudaMemsetAsync (d_packed + total_words, 0, 16, up)) != cudaSuccess ||
+      (e = cudaEventRecord (q0.ev_up, up)) != cudaSuccess || (e = cudaStreamWaitEvent (cs, q0.ev_up, 0)) != cudaSuccess) {
+    gcg_set_error ("gcg_search: meta upload: %s", cudaGetErrorString (e)); return fail (GCG_ECUDA);
+  }
+  {
+    gcg_kscope ks (ctx, "tile_seq");
+    tile_seq_kernel<<<(unsigned) ((n_tiles + 255) / 256), 256, 0, cs>>> (d_woff, n_read, n_tiles, d_tseq);
+    if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_search: tile_seq launch failed"); return fail (GCG_ECUDA); }
+  }
+
+  double t_gather = 0, t_wait = 0, t_submit = 0, t_drain = 0;
+  auto now = [] () { return std::chrono::steady_clock::now (); };
+  auto ms = [] (std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli> (b - a).count (); };
+  const auto t_call = now ();
+  gcg_workers * pool = gcg_ctx_workers (ctx);
+  std::function<void (int64_t)> gather_fn;
+  unsigned long long win_lo = 0, win_hi = 0;
+  int64_t copied = 0, done_cnt = 0, next_g = 0, total = 0, n_piece = 0, n_flag = 0;
+  int down_n = 0;
+  const size_t DOWN_PIECE = (size_t) 2 << 20;
+  bool launched = false;
+  double t_kernel_seen = 0, t_loop_end = 0;
+  int64_t left_at_end = 0;
+
+  // everything complete so far (groups report in any order, the host reads them in order), and its download
+  auto poll = [&] (size_t min_bytes) -> int {
+    while (next_g < n_group) {
+      const unsigned long long v = *(volatile unsigned long long *) (h_group + next_g);
+      if (v == 0) break;
+      done_cnt = (int64_t) (v - 1); ++next_g;
+    }
+    if (keep) return GCG_OK;
+    for (;;) {
+      const int64_t done = std::min<int64_t> (done_cnt, (int64_t) win_hi), from = std::max<int64_t> (copied, (int64_t) win_lo);
+      if (done <= from || (size_t) (done - from) * res.rec < min_bytes) return GCG_OK;
+      if (down_n >= 2) {
+        if (cudaEventQuery (p->ev_down[down_n & 1]) == cudaErrorNotReady) return GCG_OK;
+        cudaGetLastError ();
+      }
+      const int64_t to = std::min<int64_t> (done, from + (int64_t) (DOWN_PIECE / res.rec));
+      GCG_CUDA (cudaMemcpyAsync (res.buf + (size_t) from * res.rec, (char *) d_res + (size_t) from * res.rec, (size_t) (to - from) * res.rec, cudaMemcpyDeviceToHost, down));
+      GCG_CUDA (cudaEventRecord (p->ev_down[down_n & 1], down));
+      ++down_n;
+      copied = to;
+    }
+  };
+  // if the host gives up while the launch is waiting for words: let it run through whatever is in the buffer
+  auto unblock = [&] () {
+    h_ready[0] = ~0ULL;
+    cudaMemcpyAsync (d_ready, h_ready, 8, cudaMemcpyHostToDevice, up);
+    cudaStreamSynchronize (up); cudaStreamSynchronize (cs); cudaStreamSynchronize (down);
+    cudaGetLastError ();
+  };
+
+  struct piece_desc { int64_t r0 = 0, r1 = 0, w0 = 0, nw = 0; int slot = 0; bool direct = false; };
+  auto plan = [&] (int64_t r0, piece_desc & d) {
+    // growing from the first piece, and shrinking again towards the end: what is left to do when the last piece has
+    // been gathered — its upload and its tiles — is proportional to its size
+    int64_t target = std::min (piece_words, first_words << std::min<int64_t> (n_piece, 8));
+    target = std::min (target, std::max (last_words, (total_words - woff[r0]) / 2));
+    target = std::min (cap_words, std::max (max_words, target));
+    int64_t r1 = r0, nw = 0;
+    while (r1 < n_read) {
+      const int64_t w = woff[r1 + 1] - woff[r1];
+      if (r1 > r0 && nw + w > target) break;
+      nw += w; ++r1;
+    }
+    d.r0 = r0; d.r1 = r1; d.w0 = woff[r0]; d.nw = nw; d.slot = (int) (n_piece % PIPE_SLOTS);
+    d.direct = packed_pinned;
+    if (d.direct) for (int64_t i = r0; i < r1; ++i) if (src.pwoff[i] - src.pwoff[r0] != woff[i] - woff[r0]) { d.direct = false; break; }
+    ++n_piece;
+  };
+  auto start_gather = [&] (const piece_desc & d) -> int {
+    pipe_slot & q = p->s[d.slot];
+    auto t0 = now ();
+    if (q.busy) { GCG_CUDA (cudaEventSynchronize (q.ev_free)); q.busy = false; }      // (its previous upload has left the slot)
+    t_wait += ms (t0, now ());
+    const int64_t nr = d.r1 - d.r0, r0 = d.r0, w0 = d.w0;
+    const int64_t n_task = d.nw * 32 < (1 << 18) ? 1 : std::min<int64_t> (nr, 4 * (int64_t) ctx->host_threads);
+    uint64_t * dst = q.h_packed;
+    const char * const * read_seq = src.seq;
+    const uint64_t * pk = src.packed; const int64_t * pwoff = src.pwoff;
+    gather_fn = [=] (int64_t tk) {
+      for (int64_t i = r0 + nr * tk / n_task; i < r0 + nr * (tk + 1) / n_task; ++i) {
+        if (len[i] <= 0) continue;
+        if (pk) gcg_copy_stream (dst + (woff[i] - w0), pk + pwoff[i], (size_t) (woff[i + 1] - woff[i]) * 8);
+        else gcg_pack_stream (dst + (woff[i] - w0), read_seq[i], (size_t) len[i]);
+      }
+      gcg_copy_fence ();
+    };
+    gcg_workers_start (pool, n_task, gather_fn);
+    return GCG_OK;
+  };
+  auto submit = [&] (const piece_desc & d) -> int {
+    pipe_slot & q = p->s[d.slot];
+    if (d.nw > 0)
+      GCG_CUDA (cudaMemcpyAsync (d_packed + d.w0, d.direct ? (const void *) (src.packed + src.pwoff[d.r0]) : (const void *) q.h_packed, (size_t) d.nw * 8, cudaMemcpyHostToDevice, up));
+    const int64_t slot_i = ++n_flag;                   // (one pinned word per flag copy: it must keep its value until the copy has run)
+    h_ready[slot_i] = d.r1 == n_read ? (unsigned long long) total_words + 1ULL : (unsigned long long) (d.w0 + d.nw);
+    GCG_CUDA (cudaMemcpyAsync (d_ready, h_ready + slot_i, 8, cudaMemcpyHostToDevice, up));
+    if (!d.direct) { GCG_CUDA (cudaEventRecord (q.ev_free, up)); q.busy = true; }
+    return GCG_OK;
+  };
+
+  const bool help = getenv ("GCG_SEARCH_HELP") != nullptr && atoi (getenv ("GCG_SEARCH_HELP")) != 0;
+  fused_stream st;
+  st.ready = d_ready; st.group_cnt = d_group; st.group_done = hd_group; st.group_shift = group_shift;
+  for (int pass = 0; pass < 2 && !rc; ++pass) {
+    win_hi = (unsigned long long) res.cap;
+    memset (h_group, 0, (size_t) n_group * 8);
+    copied = 0; done_cnt = 0; next_g = 0; down_n = 0;
+    cudaError_t e2 = cudaMemsetAsync (d_group, 0, (size_t) n_group * 4, cs);
+    if (e2 == cudaSuccess && fmt && pass == 0) e2 = cudaMemsetAsync (d_roff, 0xFF, (size_t) (n_read + 1) * 8, cs);
+    if (e2 != cudaSuccess) { gcg_set_error ("gcg_search: %s", cudaGetErrorString (e2)); rc = GCG_ECUDA; break; }
+    rc = launch_fused (ctx, t, d_packed, d_woff, d_len, d_tseq, n_read, total_words, k, fmt, d_res, win_lo, win_hi, 0, fmt ? d_roff : nullptr,
+                       d_state, p->d_run, nullptr, true, nullptr, &st);
+    if (rc) break;
+    launched = true;
+    if (pass == 0) {
+      // ---- the reads, piece by piece: the next piece is gathered while this one is sent
+      piece_desc cur, nxt;
+      plan (0, cur);
+      bool gathering = !cur.direct;
+      if (gathering) rc = start_gather (cur);
+      while (!rc) {
+        const bool more = cur.r1 < n_read;
+        if (more) plan (cur.r1, nxt);
+        auto t0 = now ();
+        if (gathering) {
+          // (the host thread feeds the download stream and, in between, takes gather tasks like any worker)
+          while (!rc && !gcg_workers_idle (pool)) { rc = poll ((size_t) 1 << 19); if (!help || !gcg_workers_help (pool)) for (int i = 0; i < 32; ++i) _mm_pause (); }
+          gcg_workers_wait (pool);
+        }
+        t_gather += ms (t0, now ());
+        gathering = false;
+        if (rc) break;
+        if (more && !nxt.direct) { rc = start_gather (nxt); gathering = !rc; }
+        auto t1 = now ();
+        if (!rc) rc = submit (cur);
+        if (!rc) rc = poll ((size_t) 1 << 19);
+        t_submit += ms (t1, now ());
+        if (!more || rc) break;
+        cur = nxt;
+      }
+      if (gathering) gcg_workers_wait (pool);
+      if (rc) { unblock (); break; }
+    }
+    // ---- drain: the launch finishes on its own now; keep the download stream fed
+    auto t_d0 = now ();
+    t_loop_end = ms (t_call, t_d0);
+    cudaError_t qe;
+    while (!rc && (qe = cudaStreamQuery (cs)) == cudaErrorNotReady) { rc = poll ((size_t) 1 << 19); for (int i = 0; i < 64; ++i) _mm_pause (); }
+    cudaGetLastError ();
+    if (!rc) { t_kernel_seen = ms (t_call, now ()); left_at_end = done_cnt - copied; }
+    if (!rc && cudaStreamSynchronize (cs) != cudaSuccess) { gcg_set_error ("gcg_search: %s", cudaGetErrorString (cudaGetLastError ())); rc = GCG_ECUDA; }
+    if (rc) { unblock (); break; }
+    rc = poll (1);
+    if (!rc && next_g != n_group) { gcg_set_error ("gcg_search: the launch ended with %lld of %lld groups reported", (long long) next_g, (long long) n_group); rc = GCG_ECUDA; }
+    if (rc) break;
+    total = done_cnt;
+    // the tail the loop has not queued yet (pieces may still be in flight on the download stream), and the read offsets
+    if (!keep) {
+      const int64_t done = std::min<int64_t> (total, res.cap), from = std::max<int64_t> (copied, (int64_t) win_lo);
+      cudaError_t e3 = cudaSuccess;
+      if (done > from) e3 = cudaMemcpyAsync (res.buf + (size_t) from * res.rec, (char *) d_res + (size_t) from * res.rec, (size_t) (done - from) * res.rec, cudaMemcpyDeviceToHost, down);
+      if (e3 == cudaSuccess && fmt && total <= res.cap) e3 = cudaMemcpyAsync (res.read_off, d_roff, (size_t) n_read * 8, cudaMemcpyDeviceToHost, down);
+      if (e3 == cudaSuccess) e3 = cudaStreamSynchronize (down);
+      if (e3 != cudaSuccess) { gcg_set_error ("gcg_search: result download: %s", cudaGetErrorString (e3)); rc = GCG_ECUDA; break; }
+    } else if (fmt && total <= res.cap) {
+      if (cudaMemcpyAsync (res.read_off, d_roff, (size_t) n_read * 8, cudaMemcpyDeviceToHost, cs) != cudaSuccess || cudaStreamSynchronize (cs) != cudaSuccess) {
+        gcg_set_error ("gcg_search: read offsets download failed"); rc = GCG_ECUDA; break;
+      }
+    }
+    t_drain += ms (t_d0, now ());
+    if (total <= res.cap) break;
+    // denser than estimated: anchors [0, cap) are in place; a result of the right size takes them over and a second
+    // launch over the words already on the device materialises [cap, total) only
+    GCG_CHECK (pass == 0, GCG_ECUDA, "gcg_search: anchor count changed between passes (%lld > %lld)", (long long) total, (long long) res.cap);
+    if (ctx->trace) fprintf (stderr, "[gcg]   streaming search: result sized for %lld anchors, %lld found: second launch for the tail\n", (long long) res.cap, (long long) total);
+    void * d_new = nullptr;
+    cudaError_t e4 = gcg_dmalloc (ctx, &d_new, (size_t) total * res.rec);
+    if (e4 == cudaSuccess) e4 = cudaMemcpyAsync (d_new, d_res, (size_t) res.cap * res.rec, cudaMemcpyDeviceToDevice, cs);
+    if (e4 != cudaSuccess) { if (d_new) gcg_dfree (ctx, d_new); gcg_set_error ("gcg_search: device result of %lld anchors: %s", (long long) total, cudaGetErrorString (e4)); rc = GCG_ENOMEM; break; }
+    gcg_dfree (ctx, d_res);                            // (stream ordered behind the copy: parked blocks are reused by later work on the same stream)
+    d_res = d_new;
+    if (!keep) {
+      char * nb = (char *) gcg_pinned_alloc ((size_t) total * res.rec);
+      if (nb == nullptr) { gcg_set_error ("gcg_search: pinned alloc of %lld anchors failed", (long long) total); rc = GCG_ENOMEM; break; }
+      gcg_par_memcpy (ctx, nb, res.buf, (size_t) res.cap * res.rec);
+      gcg_free (res.buf);
+      res.buf = nb;
+    }
+    win_lo = (unsigned long long) res.cap;
+    res.cap = total;
+  }
+  (void) launched;
+  if (ctx->trace)
+    fprintf (stderr, "[gcg]   search pipeline (streaming, one launch): %lld pieces, waits for the gather %.3f ms (%d threads), for a free slot %.3f ms; "
+             "host: submit %.3f drain %.3f ms; last piece sent at %.3f, launch seen finished at %.3f (%lld reported anchors not yet queued for download), all done at %.3f ms\n",
+             (long long) n_piece, t_gather, ctx->host_threads, t_wait, t_submit, t_drain, t_loop_end, t_kernel_seen, (long long) left_at_end, ms (t_call, now ()));
+  gcg_trace_mark (ctx, "search: reads -> anchors (streaming)");
+  for (pipe_slot & q : p->s) { q.busy = false; q.pending = false; }
+  if (rc) return fail (rc);
+  res.n = total;
+  p->last_total = total;
+  if (fmt) read_off_fill (res.read_off, n_read, total);
+  if (keep) {
+    // filled offsets go back up: the reduction kernels read read_off[r + 1] of every read
+    if (cudaMemcpyAsync (d_roff, res.read_off, (size_t) (n_read + 1) * 8, cudaMemcpyHostToDevice, cs) != cudaSuccess || cudaStreamSynchronize (cs) != cudaSuccess) {
+      gcg_set_error ("gcg_search: read offsets upload failed"); return fail (GCG_ECUDA);
+    }
+    keep->d_anchors = d_res; keep->d_read_off = d_roff; d_res = nullptr; d_roff = nullptr;
+  }
+  release ();
+  if (fmt) *read_off_out = res.read_off;
+  *n_hit = total;
+  if (keep) return GCG_OK;
+  if (total == 0) { gcg_free (res.buf); return GCG_OK; }
+  *hits_out = res.buf;
+  return GCG_OK;
+}
+
 static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const read_source & src, const int32_t * read_len,
                              int64_t n_read, int k, int fmt, void ** hits_out, int64_t * n_hit, int64_t ** read_off_out,
                              search_dev_keep * keep = nullptr)
@@ -2105,6 +2505,12 @@ static int search_host_impl (gcg_ctx * ctx, gcg_table * t, const read_source & s
   *hits_out = nullptr;
   *n_hit = 0;
   if (read_off_out) *read_off_out = nullptr;
+  {
+    // one launch over the whole read set while it is being uploaded (default), else the chunked pipeline below
+    bool handled = false;
+    const int src_rc = search_host_stream (ctx, t, src, read_len, n_read, k, fmt, hits_out, n_hit, read_off_out, keep, &handled);
+    if (handled) return src_rc;
+  }
   GCG_CUDA (cudaSetDevice (ctx->device));
   gcg_trace_mark (ctx, nullptr);
   // Chunks GROW: 4, 8, 16, 32, 32, ... MiB of bases (and shrink again towards the end).  A chunk's kernel runs the deferred-emit pipeline of

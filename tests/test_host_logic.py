@@ -250,3 +250,15 @@ def test_worker_pool_holds_one_job_at_a_time():
     L.gcg_selftest_workers.argtypes = [C.c_int, C.c_int, C.c_int]
     for nt, na, nb in ((4, 16, 4), (8, 64, 8), (2, 5, 3), (1, 7, 2)):
         assert L.gcg_selftest_workers(nt, na, nb) == na * 1000 + nb, (nt, na, nb)
+
+
+def test_worker_pool_hands_every_task_out_once():
+    """the pool's workers poll for the next job for a while before they sleep, and take tasks by compare-and-swap on a
+    ticket that carries the job's generation: thousands of short jobs back to back, spinning, sleeping and mixed"""
+    import ctypes as C
+    from superplus_b200 import api
+    L = api.load_library()
+    L.gcg_selftest_workers_stress.restype = C.c_int64
+    L.gcg_selftest_workers_stress.argtypes = [C.c_int, C.c_int, C.c_int]
+    for nt, spin in ((2, -1), (4, 0), (8, 5), (16, 50), (3, 300)):
+        assert L.gcg_selftest_workers_stress(nt, 6000, spin) == 0, (nt, spin)

@@ -7,6 +7,14 @@ from superplus_b200 import api, synth
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["stream", "chunked"])
+def host_pipeline(request, monkeypatch):
+    """every test runs with both forms of the host-buffer search: one launch over reads that are still being uploaded
+    (default) and one launch per chunk (GCG_SEARCH_STREAM=0); GCG_SEARCH_CHUNK_BYTES sizes the pieces / the chunks"""
+    monkeypatch.setenv("GCG_SEARCH_STREAM", "1" if request.param == "stream" else "0")
+    return request.param
+
+
 def asc(s):
     return np.frombuffer(s.encode(), dtype=np.uint8).copy()
 
