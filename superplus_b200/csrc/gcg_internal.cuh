@@ -62,6 +62,7 @@ struct gcg_ctx {
   // small device scratch for reductions / counters
   unsigned long long * d_counters = nullptr;   // 64 x u64 ([16..48) = per-partition totals of gcg_route_plan)
   unsigned long long * h_counters = nullptr;   // pinned mirror
+  int launch_async = -1;                       // streaming search: 1 when a kernel launch returns before the kernel has run (-1: not probed yet)
   double last_anchor_frac = 0.0;               // anchors per ONT k-mer of the previous device-resident search (sizes the next result buffer)
   // parked device blocks by size class (see gcg_dmalloc)
   std::map<size_t, std::vector<void *>> dparked;

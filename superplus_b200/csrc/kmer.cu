@@ -2163,6 +2163,39 @@ __global__ void tile_seq_kernel (const int64_t * __restrict__ woff, int64_t n_se
   tseq[tile] = (int32_t) lo;
 }
 
+// The streaming search needs the host to keep working AFTER the launch call: it uploads the words the launch is
+// waiting for.  Under a tool that makes launches synchronous (ncu and compute-sanitizer serialise kernels and return
+// from the launch call when the kernel has finished; CUDA_LAUNCH_BLOCKING=1) that would be a dead wait, so the first
+// search of a context finds out: a one-thread kernel waits up to 20 ms for a host flag that is set right after the launch
+// call returns.  If the kernel gave up, launches are synchronous and this context keeps the chunked pipeline.
+__global__ void launch_probe_kernel (volatile unsigned long long * flag, unsigned long long timeout_ns, unsigned long long * out)
+{
+  unsigned long long t0, t1;
+  asm volatile ("mov.u64 %0, %%globaltimer;" : "=l" (t0));
+  while (*flag == 0ULL) {
+    asm volatile ("mov.u64 %0, %%globaltimer;" : "=l" (t1));
+    if (t1 - t0 > timeout_ns) { *out = 1ULL; return; }
+    __nanosleep (500);
+  }
+  *out = 2ULL;
+}
+
+static bool launches_are_async (gcg_ctx * ctx)
+{
+  if (ctx->launch_async >= 0) return ctx->launch_async != 0;
+  gcg_pipe * p = ctx->pipe;                          // (pipe_reserve has run)
+  volatile unsigned long long * h = p->h_count;
+  h[PIPE_SLOTS - 1] = 0ULL; h[PIPE_SLOTS - 2] = 0ULL;
+  launch_probe_kernel<<<1, 1, 0, ctx->stream>>> (p->hd_count + (PIPE_SLOTS - 1), 20000000ULL, p->hd_count + (PIPE_SLOTS - 2));
+  h[PIPE_SLOTS - 1] = 1ULL;
+  const bool ok = cudaGetLastError () == cudaSuccess && cudaStreamSynchronize (ctx->stream) == cudaSuccess;
+  ctx->launch_async = ok && h[PIPE_SLOTS - 2] == 2ULL ? 1 : 0;
+  if (ctx->trace || !ctx->launch_async)
+    fprintf (stderr, "[gcg] kernel launches are %s: the host-buffer search runs %s\n", ctx->launch_async ? "asynchronous" : "SYNCHRONOUS (a profiler or CUDA_LAUNCH_BLOCKING)",
+             ctx->launch_async ? "as one launch over arriving reads" : "one launch per chunk");
+  return ctx->launch_async != 0;
+}
+
 static bool stream_mode_on (void)
 {
 #if K45F_BLOCKSCAN != 2
@@ -2210,6 +2243,7 @@ static int search_host_stream (gcg_ctx * ctx, gcg_table * t, const read_source &
   if (!rc) rc = gcg_table_filter_ensure (ctx, t);
   if (rc) return rc;
   gcg_pipe * p = ctx->pipe;
+  if (!launches_are_async (ctx)) { *handled = false; return GCG_OK; }
   const int64_t cap_words = p->cap_words;
   const int64_t n_tiles = (total_words + 31) >> 5, n_bt = (n_tiles + K4_WARPS - 1) / K4_WARPS;
   const int group_shift = 8;                          // 256 block tiles = 2 M k-mers, about 1 MB of anchors at ONT error rates

@@ -276,6 +276,33 @@ def test_two_pass_search_still_agrees(ctx, oracle):
     assert outs[0] == outs[1] and outs[0]
 
 
+def test_synchronous_launches_keep_the_chunked_pipeline(host_pipeline):
+    """the one-launch search needs the host to keep uploading AFTER the launch call; under ncu, compute-sanitizer or
+    CUDA_LAUNCH_BLOCKING=1 a launch only returns when the kernel has finished, so the first search of a context probes
+    for that and stays with one launch per chunk — same anchors, and it says so"""
+    if host_pipeline != "stream":
+        pytest.skip("only the default form probes")
+    import subprocess, sys, os as _os
+    code = ("import numpy as np, sys; sys.path.insert(0, %r)\n"
+            "from superplus_b200 import api, synth\n"
+            "inp = synth.make_config('small'); c = api.Context(0)\n"
+            "cs = c.upload(inp.contigs); t = c.table_build(cs, 25)\n"
+            "a, off = c.search_host_compact(t, inp.reads); print(len(a), int((a >> np.uint64(36)).sum()), int(off.sum()), t.stats())\n") % _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    outs = []
+    for blocking in ("0", "1"):
+        env = dict(_os.environ, GCG_SEARCH_STREAM="1", GCG_TRACE="1")
+        env.pop("CUDA_LAUNCH_BLOCKING", None)
+        if blocking == "1":
+            env["CUDA_LAUNCH_BLOCKING"] = "1"
+        r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+        assert r.returncode == 0, r.stderr.decode()[-2000:]
+        outs.append(r.stdout.decode().strip())
+        err = r.stderr.decode()
+        assert ("launches are SYNCHRONOUS" in err) == (blocking == "1"), err[-1500:]
+        assert ("(streaming, one launch)" in err) == (blocking == "0"), err[-1500:]
+    assert outs[0] == outs[1] and outs[0]
+
+
 def _check_runs(ctx, oracle, contigs, reads, k):
     h = oracle.table_build(contigs, k)
     o_hits, o_ont = oracle.search(h, reads, k)
