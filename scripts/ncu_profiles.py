@@ -121,9 +121,13 @@ def launch_list(path, fh):
     fh.write("  %-28s %8s %12s %10s %8s\n" % ("kernel", "launches", "total us", "avg us", "share"))
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1]):
         fh.write("  %-28s %8d %12.1f %10.1f %7.1f%%\n" % (k, n[k], v, v / n[k], 100 * v / tot))
-    kmer = {k: v for k, v in agg.items() if not k.startswith("sw_") and "ubench" not in k}
+    # (launch_probe_kernel: the streaming search's one-off test for synchronous launches — under ncu it runs into its 20 ms
+    #  timeout, which is how the library knows to keep one launch per chunk; post_count_kernel: the chunked pipeline's
+    #  completion post; both belong to the end-to-end legs, not to the device-resident step)
+    kmer = {k: v for k, v in agg.items() if not k.startswith("sw_") and "ubench" not in k and "launch_probe" not in k and "post_count" not in k}
     kt = sum(kmer.values()) or 1
-    fh.write("k-mer step only (k1 / k23 / k45 / k6; runs_* belong to the e2e_runs leg):\n")
+    fh.write("k-mer step only (k1 / k23 / k45 / k6; runs_* belong to the e2e_runs leg; under ncu the end-to-end legs run the chunked\n"
+             "pipeline, because launches are synchronous there — launch_probe_kernel finds that out):\n")
     for k, v in sorted(kmer.items(), key=lambda kv: -kv[1]):
         fh.write("  %-28s %7.1f%%   avg %8.1f us\n" % (k, 100 * v / kt, v / n[k]))
     fh.write("\n")

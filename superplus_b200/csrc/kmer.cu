@@ -2403,7 +2403,9 @@ static int search_host_stream (gcg_ctx * ctx, gcg_table * t, const read_source &
     return GCG_OK;
   };
 
-  const bool help = getenv ("GCG_SEARCH_HELP") != nullptr && atoi (getenv ("GCG_SEARCH_HELP")) != 0;
+  // the host thread takes gather tasks between its polls when the pool is small (one GPU of eight gets 4 host threads:
+  // 3 workers + this one); with 16 threads it was measured neutral to slightly slower (the polls come late)
+  const bool help = getenv ("GCG_SEARCH_HELP") != nullptr ? atoi (getenv ("GCG_SEARCH_HELP")) != 0 : ctx->host_threads <= 8;
   fused_stream st;
   st.ready = d_ready; st.group_cnt = d_group; st.group_done = hd_group; st.group_shift = group_shift;
   for (int pass = 0; pass < 2 && !rc; ++pass) {
