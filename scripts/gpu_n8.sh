@@ -1,7 +1,7 @@
 set -u
 O=gpurun_out; mkdir -p $O
 nvidia-smi -L | wc -l; nproc; free -g | head -2
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 10 --warmup 3 > $O/bench_r02_n8b.json 2> $O/bench_r02_n8b.err; echo "bench n8 rc=$?"; tail -4 $O/bench_r02_n8b.err | cut -c1-300
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 10 --warmup 3 ${N8_EXTRA:-} > $O/bench_r02_n8b.json 2> $O/bench_r02_n8b.err; echo "bench n8 rc=$?"; tail -4 $O/bench_r02_n8b.err | cut -c1-300
 python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/bench_r02_n8b.json").read().strip().splitlines()[-1])
