@@ -683,7 +683,8 @@ def run_ours(args, rank, local_rank, world):
                 "host_input_bytes_per_step": int(read_bytes + ctg_bytes),
                 "d2h_bytes_per_step": int(n_hit * 8 + 8 * (len(reads) + 1) + 32), "ms_per_step": e2e_kmer_s * 1e3,
                 "host_threads_per_rank": host_threads, "host_cores": os.cpu_count(),
-                "api": "gcg_table_build + gcg_search_compact (host pointers in, pinned 8-byte anchors + per-read offsets out) + gcg_table_stats"},
+                "api": "gcg_table_build + gcg_search_compact (host pointers in, pinned 8-byte anchors + per-read offsets out) + gcg_table_stats",
+                "pipeline": "one search launch over reads that are still being gathered, packed and uploaded (GCG_SEARCH_STREAM=0: one launch per chunk)" if os.environ.get("GCG_SEARCH_STREAM", "1") != "0" else "one launch per chunk (GCG_SEARCH_STREAM=0)"},
         "e2e_packed": {"value": tot_ont_kmers / e2e_packed_s, "unit": "k-mers/s", "ms_per_step": e2e_packed_s * 1e3,
                        "h2d_bytes_per_step": int(sum((len(r) + 31) // 32 * 8 for r in reads) + 12 * len(reads) + read_bytes // 256 + ctg_bytes),
                        "d2h_bytes_per_step": int(n_hit * 8 + 8 * (len(reads) + 1) + 32),
