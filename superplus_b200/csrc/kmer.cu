@@ -2478,7 +2478,7 @@ static int search_host_stream (gcg_ctx * ctx, gcg_table * t, const read_source &
     if (total <= res.cap) break;
     // denser than estimated: anchors [0, cap) are in place; a result of the right size takes them over and a second
     // launch over the words already on the device materialises [cap, total) only
-    GCG_CHECK (pass == 0, GCG_ECUDA, "gcg_search: anchor count changed between passes (%lld > %lld)", (long long) total, (long long) res.cap);
+    if (pass != 0) { gcg_set_error ("gcg_search: anchor count changed between passes (%lld > %lld)", (long long) total, (long long) res.cap); rc = GCG_ECUDA; break; }
     if (ctx->trace) fprintf (stderr, "[gcg]   streaming search: result sized for %lld anchors, %lld found: second launch for the tail\n", (long long) res.cap, (long long) total);
     void * d_new = nullptr;
     cudaError_t e4 = gcg_dmalloc (ctx, &d_new, (size_t) total * res.rec);
