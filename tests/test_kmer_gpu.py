@@ -380,3 +380,50 @@ def test_search_of_reads_packed_by_the_caller(ctx, oracle, pinned, gap, monkeypa
     if keep is not None:
         keep.free()
     cs.free()
+
+
+@pytest.mark.parametrize("threads", [1, 2, 5])
+def test_streaming_search_piece_sizes_and_pool_sizes(oracle, threads, host_pipeline, monkeypatch):
+    """the one-launch search with pieces from one read each up to the whole read set, with pools of one (no worker
+    thread at all), two and five host threads (the host thread lends a hand below nine), ASCII and packed input
+    (pinned words in one run: sent from where they lie; with gaps: through the slots), anchors, 16-byte hits and run
+    records: always the anchors of the device-resident search"""
+    inp = synth.make_config("small")
+    e = np.zeros(0, np.uint8)
+    reads = [e, inp.reads[0][:7]] + inp.reads[:60] + [e, e, inp.reads[2][:25]] + inp.reads[60:] + [inp.reads[1][:24], e]
+    c = api.Context(0, host_threads=threads)
+    try:
+        cs, rs = c.upload(inp.contigs), c.upload(reads)
+        t = c.table_build(cs, 25)
+        want = c.search(t, rs)
+        st = t.stats()
+        t.free(); rs.free()
+        clens = [len(x) for x in inp.contigs]
+        packed = {gap: api.Context.pack_reads(reads, pinned=True, gap_words=gap) for gap in (0, 2)}
+        for piece in (32, 96, 1000, 5000, 70000, 1 << 22, None):
+            if piece is None:
+                monkeypatch.delenv("GCG_SEARCH_CHUNK_BYTES", raising=False)
+            else:
+                monkeypatch.setenv("GCG_SEARCH_CHUNK_BYTES", str(piece))
+            t = c.table_build(cs, 25)
+            a, off = c.search_host_compact(t, reads)
+            assert np.array_equal(api.expand_compact(a, off, clens), want) and t.stats() == st, (threads, piece, "ascii")
+            t.free()
+            for gap, (words, woff, lens, keep) in packed.items():
+                t = c.table_build(cs, 25)
+                a2, off2 = c.search_host_compact_packed(t, words, woff, lens)
+                assert np.array_equal(a2, a) and np.array_equal(off2, off) and t.stats() == st, (threads, piece, "packed", gap)
+                t.free()
+            if piece in (96, 70000, None):
+                t = c.table_build(cs, 25)
+                assert np.array_equal(c.search_host(t, reads), want) and t.stats() == st, (threads, piece, "hits16")
+                t.free()
+                t = c.table_build(cs, 25)
+                runs, run_off, n_anchor = c.search_runs(t, reads)
+                assert n_anchor == len(want) and run_off[-1] == len(runs) and t.stats() == st, (threads, piece, "runs")
+                t.free()
+        for words, woff, lens, keep in packed.values():
+            keep.free()
+        cs.free()
+    finally:
+        c.close()
