@@ -152,7 +152,8 @@ struct k4_smem { uint32_t excl[K4_WARPS][33], pend[K4_WARPS][32], add[K4_WARPS][
 
 // PART (remote-probe search of a hash-partitioned table): the key's owner partition picks the arrays — a peer GPU's,
 // reached over NVLink — and the bucket count; only probes that pass the (local, replicated) union filter leave the GPU
-template <bool FILTER, int KC, bool PF, bool PART = false>
+// CG (streaming search): the packed words are read with ld.global.cg — they may be arriving by DMA while the launch runs
+template <bool FILTER, int KC, bool PF, bool PART = false, bool CG = false>
 __device__ __forceinline__ uint32_t
 k4_probe_tile (k4_smem & sm, const unsigned long long * __restrict__ vals, const int64_t tile, const uint64_t * __restrict__ packed, const int64_t * __restrict__ woff,
                const int32_t * __restrict__ len, const int32_t * __restrict__ tile_seq, const int64_t n_seq, const int64_t n_words, const int k,
@@ -175,12 +176,12 @@ k4_probe_tile (k4_smem & sm, const unsigned long long * __restrict__ vals, const
     GCG_DEV_ASSERT (s >= 0 && s < n_seq && p0 >= 0 && (p0 < L || L == 0) && __ldg (woff + s) <= w && w < __ldg (woff + s + 1));
     nvalid = L - k + 1 - p0;
     nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
-    pk = __ldcg (packed + w);                       // (.cg: the words may be arriving by DMA while this launch runs — streaming search —, and are read once)
+    pk = CG ? __ldcg (packed + w) : __ldg (packed + w);
   }
   *pk_out = pk; *seq_out = sq; *p0_out = p0;
   if (nvalid) {
     kroll r;
-    r.init (pk, __ldcg (packed + w + 1), k);
+    r.init (pk, CG ? __ldcg (packed + w + 1) : __ldg (packed + w + 1), k);
     for (int j0 = 0; j0 < nvalid; j0 += K4_UNROLL) {
       unsigned long long key[K4_UNROLL];
       uint32_t fp[K4_UNROLL], bk[K4_UNROLL];
@@ -258,7 +259,7 @@ k4_probe_tile (k4_smem & sm, const unsigned long long * __restrict__ vals, const
       GCG_DEV_ASSERT (lo >= 0 && lo < 32 && j >= 0 && j < 32 && sm.excl[wid][lo] <= h && h < sm.excl[wid][lo + 1]);
       const int64_t ww = (tile << 5) + lo;
       bool fw;
-      unsigned long long kw, key = key_at (__ldcg (packed + ww), __ldcg (packed + ww + 1), j, k, &fw);
+      unsigned long long kw, key = CG ? key_at (__ldcg (packed + ww), __ldcg (packed + ww + 1), j, k, &fw) : key_at (__ldg (packed + ww), __ldg (packed + ww + 1), j, k, &fw);
       const unsigned long long * tk = keys;
       uint32_t nb = n_bucket;
       if (PART) { const gcg_part_desc pd = parts[kmer_owner (key - 1ULL, n_part)]; tk = pd.keys; nb = pd.n_bucket; }
@@ -488,7 +489,8 @@ k45f_emit_tile (const k45f_args & A, const int k, const int lane, const unsigned
 //     resolve round r + 1 before every warp of the block has finished probing it), a warp's staged tile in two.
 // Every spin is bounded and traps with a message instead of hanging the GPU.
 #define K45F_SLOTS 8        // rotating per-round scalars (a warp is at most two rounds ahead of another; writers touch round + 1)
-template <bool FILTER, int KC, int FMT, bool PART = false>
+// STREAM: the launch of the streaming search (A.ready / A.group_* are set); the device-resident search carries none of it
+template <bool FILTER, int KC, int FMT, bool PART = false, bool STREAM = false>
 __global__ void __launch_bounds__ (32 * K4_WARPS, K45F_MINB)
 k45_fused_kernel (const k45f_args A)
 {
@@ -522,7 +524,7 @@ k45_fused_kernel (const k45f_args A)
     uint32_t total = 0;
     if (live) {
       const int64_t tile = bt * K4_WARPS + wid;          // may be past the end in the last block tile: probes nothing
-      if (A.ready != nullptr && (tile << 5) < A.n_words) {
+      if (STREAM && A.ready != nullptr && (tile << 5) < A.n_words) {
         // streaming: this tile's words (and the one behind them, which the last lane's k-mers run into) must have arrived
         if (lane == 0) {
           const unsigned long long need = (unsigned long long) (((tile + 1) << 5) < A.n_words ? ((tile + 1) << 5) + 1 : A.n_words + 1);
@@ -541,7 +543,7 @@ k45_fused_kernel (const k45f_args A)
         __syncwarp ();
       }
       uint64_t pk; int32_t sq, p0;
-      const uint32_t mymask = k4_probe_tile<FILTER, KC, K45F_PREFETCH != 0 && !PART, PART> (sm, A.vals, tile, A.packed, A.woff, A.len, A.tile_seq, A.n_seq, A.n_words, k, A.keys, A.n_bucket,
+      const uint32_t mymask = k4_probe_tile<FILTER, KC, K45F_PREFETCH != 0 && !PART, PART, STREAM> (sm, A.vals, tile, A.packed, A.woff, A.len, A.tile_seq, A.n_seq, A.n_words, k, A.keys, A.n_bucket,
                                                                                             A.filter, A.filter_words, A.filter_k3, &pk, &sq, &p0, A.parts, A.n_part);
       const int64_t w = (tile << 5) + lane;
       const uint32_t c = __popc (mymask);
@@ -555,7 +557,7 @@ k45_fused_kernel (const k45f_args A)
       s_pk[q2][wid][lane] = pk;
       s_seq[q2][wid][lane] = w < A.n_words ? sq : -1;
       s_p0[q2][wid][lane] = p0;
-      if (lane == 31) { s_excl[q2][wid][32] = total; s_pk[q2][wid][32] = w + 1 <= A.n_words ? __ldcg (A.packed + w + 1) : 0ULL; }   // (slack word at n_words)
+      if (lane == 31) { s_excl[q2][wid][32] = total; s_pk[q2][wid][32] = w + 1 <= A.n_words ? (STREAM ? __ldcg (A.packed + w + 1) : __ldg (A.packed + w + 1)) : 0ULL; }   // (slack word at n_words)
       // ---- count in; the first arrival claims the next round's block tile, the last one publishes this tile's count
       if (lane == 0) {
         s_wtot[qs][wid] = total;
@@ -650,7 +652,7 @@ k45_fused_kernel (const k45f_args A)
       if (prev_total) k45f_emit_tile<FMT, PART> (A, k, lane, base, base0, prev_total, s_excl[p2][wid], s_mask[p2][wid], s_pk[p2][wid], s_seq[p2][wid], s_p0[p2][wid]);
 #endif
       __syncwarp ();
-      if (A.group_cnt != nullptr) {
+      if (STREAM && A.group_cnt != nullptr) {
         // streaming: the last warp to finish a group of block tiles tells the host how many anchors are complete up to
         // the group's end (the inclusive prefix of its last block tile: resolved before any of its warps emitted)
         __threadfence ();
@@ -1683,7 +1685,11 @@ static int launch_fused (gcg_ctx * ctx, const gcg_table * t, const uint64_t * d_
   GCG_CHECK (t->d_parts == nullptr, GCG_EINVAL, "gcg_search (partitioned view): this build's search kernel has no remote-probe form");
 #endif
   gcg_kscope ks (ctx, "k45_fused");
+#if K45F_BLOCKSCAN == 2
+#define K45F(F, KC) (st ? (fmt ? k45_fused_kernel<F, KC, 1, false, true> : k45_fused_kernel<F, KC, 0, false, true>) : (fmt ? k45_fused_kernel<F, KC, 1> : k45_fused_kernel<F, KC, 0>))
+#else
 #define K45F(F, KC) (fmt ? k45_fused_kernel<F, KC, 1> : k45_fused_kernel<F, KC, 0>)
+#endif
   auto fn = flt ? (k == 25 ? K45F (true, 25) : k == 31 ? K45F (true, 31) : K45F (true, 0))
                 : (k == 25 ? K45F (false, 25) : k == 31 ? K45F (false, 31) : K45F (false, 0));
 #undef K45F
