@@ -95,6 +95,13 @@ gcg_bridge_runs_mode (void)
   return e != NULL && atoi (e) != 0;
 }
 
+int
+gcg_bridge_sparse_kmers (void)
+{
+  const char * e = getenv ("GC_SPARSE_KMERS");
+  return e != NULL && atoi (e) != 0;
+}
+
 gcg_bridge_t *
 gcg_bridge_peek (void)
 {

@@ -35,6 +35,7 @@ typedef struct {
 
 /* rseq_fast.c: the 2-bit words the FASTQ loader packed while loading `set` (0 = none: not that set, or switched off) */
 int rseq_packed_lookup (const void * set, int64_t n_reads, const uint64_t ** words, const int64_t ** woff);
+int gcg_bridge_sparse_kmers (void);          /* GC_SPARSE_KMERS set and not 0: ctg->kmers[] is written only where an anchor points */
 int gcg_bridge_runs_mode (void);             /* GC_RUNS set and not 0 (no device is opened by asking) */
 gcg_bridge_t * gcg_bridge_peek (void);       /* the handle as it is: no context is created */
 gcg_bridge_t * gcg_bridge (void);            /* lazily creates the context; aborts via err_mesg on failure */

@@ -58,8 +58,10 @@ chop_contig_seqs2kmers (mp_t(ctg) * seqs, int n_thread, int kmer_len)
   gcg_bridge_drop_table ();
   gcg_bridge_drop_contigs ();
   GCG_CK (gcg_seqs_upload (br->ctx, ptrs, lens, n, &br->contigs));
-  if (gcg_bridge_runs_mode ()) {
-    /* GC_RUNS: nothing reads ctg->kmers[] — the anchors the consumers look at carry their own kmer_t
+  if (gcg_bridge_runs_mode () || gcg_bridge_sparse_kmers ()) {
+    /* GC_SPARSE_KMERS (ctg_graph.c untouched): the back-fill of the search writes the kmer_t record of
+     * every contig position an anchor points at (ont.c of this directory), nothing else ever reads ctg->kmers[].
+     * GC_RUNS (N2 + N3): nothing reads ctg->kmers[] — the anchors the consumers look at carry their own kmer_t
      * records (ont.c of this directory) — so the 24 bytes per contig base stay untouched zero pages */
     for (i = 0; i < n; ++i) n_kmer[i] = lens[i] >= kmer_len ? lens[i] - kmer_len + 1 : 0;
   } else

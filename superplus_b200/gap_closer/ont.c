@@ -53,7 +53,25 @@ typedef struct {
   int64_t n_ctg;
   mp_t(okseq) * okseqs;
   mp_t(ctg) * ctgs;
+  int sparse, kmer_len, n_thread;   /* GC_SPARSE_KMERS: ctg->kmers[] was not filled by the chop; write the records anchors point at */
 } fill_arg_t;
+
+static uint64_t canon_at (const char * s, int k, int * rev);
+
+/* the kmer_t record of contig position cpos, as chop_kmer_core writes it (kmer.c:73-117); kmer_len is written last and
+ * doubles as the "filled" mark (two threads that meet on one record write the same bytes) */
+static inline void
+sparse_kmer_fill (kmer_t * km, const ctg_t * c, int64_t tid, int64_t cpos, int kmer_len, int n_thread)
+{
+  int rev;
+  if (km->kmer_len != 0) return;
+  km->kseq = canon_at (c->seq->s + cpos, kmer_len, &rev);
+  km->hs_id = (int32_t) (kseq_crc32 (&km->kseq) % (uint32_t) n_thread);     /* kmer.c:88 */
+  km->tid = (int32_t) tid;
+  km->pos = (int32_t) cpos;
+  km->flag = rev ? KMER_REV : 0;
+  __atomic_store_n (&km->kmer_len, (int16_t) kmer_len, __ATOMIC_RELEASE);
+}
 
 static void *
 fill_core (void * data)
@@ -66,6 +84,7 @@ fill_core (void * data)
       okseq_t * okseq = a->okseqs->pool + a->read_off0 + h->read;
       ont_kmer_t * ok = okseq->okmers->pool + h->pos;
       kmer_t * km = a->ctgs->pool[h->tid].kmers + (h->cpos_flags >> 2);
+      if (a->sparse) sparse_kmer_fill (km, a->ctgs->pool + h->tid, h->tid, h->cpos_flags >> 2, a->kmer_len, a->n_thread);
       ok->kmer = km;
       ok->ont_pos = h->pos;
       ok->hs_id = (int16_t) km->hs_id;
@@ -88,6 +107,7 @@ fill_core (void * data)
         tid = lo;
       }
       km = a->ctgs->pool[tid].kmers + (gpos - a->cbase[tid]);
+      if (a->sparse) sparse_kmer_fill (km, a->ctgs->pool + tid, tid, gpos - a->cbase[tid], a->kmer_len, a->n_thread);
       ok->kmer = km;
       ok->ont_pos = pos;
       ok->hs_id = (int16_t) km->hs_id;
@@ -389,6 +409,7 @@ search_kmers_on_ont_reads (mp_t(rs) * ont_seqs, mp_t(ctg) * ctg_seqs,
       fa->cbase = cbase; fa->n_ctg = n_ctg;
       fa->okseqs = okseqs;
       fa->ctgs = ctg_seqs;
+      fa->sparse = gcg_bridge_sparse_kmers (); fa->kmer_len = kmer_len; fa->n_thread = nt;
       if (share[d].anchors != NULL) {
         /* whole reads per thread, cut where the anchor count reaches (t + 1) / nt_d of the share's */
         int64_t goal = share[d].n_hit * (t + 1) / nt_d, lo = prev, hi = n_rd;

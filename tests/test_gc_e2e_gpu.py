@@ -221,6 +221,29 @@ def test_runs_mode_writes_the_same_files(cfg, env):
         assert md5(os.path.join(wd, "valid_ont_link.txt")) == g["valid"]
 
 
+@pytest.mark.parametrize("cfg,env", [("tiny", {}), ("small", {"GC_ANCHORS16": "1"}), ("repeats", {}), ("cfg1", {}), ("cfg5s", {}),
+                                     ("cfg1", {"GC_DEVICES": "0,0"}), ("cfg2", {})])
+def test_sparse_kmers_mode_writes_the_same_files(cfg, env):
+    """GC_SPARSE_KMERS=1 (opt-in, SURVEY 8f row N2 with every file of the reference's consumer side untouched, default
+    map_ont2contigs included): the chop does not download 24 bytes per contig base; the search's back-fill writes the
+    kmer_t record of every contig position an anchor points at (same fields as chop_kmer_core), the rest of
+    ctg->kmers[] stays the loader's untouched zero pages.  Files and statistics must be the reference's."""
+    assert os.path.exists(GC), "gc_b200 was not built (python -c 'import __graft_entry__ as g; g.build()')"
+    with tempfile.TemporaryDirectory() as tmp:
+        fa, fq, _ = synth.materialise(cfg, tmp)
+        wd = os.path.join(tmp, "run")
+        os.makedirs(wd)
+        r = subprocess.run([GC, fa, fq, "8", "out"], cwd=wd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900,
+                           env=dict(os.environ, GC_SPARSE_KMERS="1", **env))
+        assert r.returncode == 0, r.stderr.decode()[-2000:]
+        stats = [int(x) for x in re.findall(r"(?:total|unique) kmer count: (\d+)", r.stdout.decode())]
+        g = GOLD[cfg]
+        assert stats == g["stats"]
+        assert md5(os.path.join(wd, "gc_fix1.fa")) == g["fa"]
+        assert md5(os.path.join(wd, "ont_link.txt")) == g["link"]
+        assert md5(os.path.join(wd, "valid_ont_link.txt")) == g["valid"]
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # GC_SW_FILL=1 (opt-in, SURVEY 8f row N4): gap junctions from batched alignments instead of the extrapolation
 def _code(a):
