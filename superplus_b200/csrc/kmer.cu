@@ -2319,6 +2319,10 @@ static int search_host_stream (gcg_ctx * ctx, gcg_table * t, const read_source &
   auto now = [] () { return std::chrono::steady_clock::now (); };
   auto ms = [] (std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli> (b - a).count (); };
   const auto t_call = now ();
+  // GCG_TIMELINE=1: device clock of the last piece's arrival and of the end of the launch, next to the host's times
+  const bool timeline = getenv ("GCG_TIMELINE") != nullptr;
+  cudaEvent_t tl_ref = nullptr, tl_up = nullptr, tl_kern = nullptr;
+  if (timeline) { cudaEventCreate (&tl_ref); cudaEventCreate (&tl_up); cudaEventCreate (&tl_kern); cudaEventRecord (tl_ref, up); }
   gcg_workers * pool = gcg_ctx_workers (ctx);
   std::function<void (int64_t)> gather_fn;
   unsigned long long win_lo = 0, win_hi = 0;
@@ -2457,6 +2461,7 @@ static int search_host_stream (gcg_ctx * ctx, gcg_table * t, const read_source &
     // ---- drain: the launch finishes on its own now; keep the download stream fed
     auto t_d0 = now ();
     t_loop_end = ms (t_call, t_d0);
+    if (timeline && pass == 0) { cudaEventRecord (tl_up, up); cudaEventRecord (tl_kern, cs); }
     cudaError_t qe;
     while (!rc && (qe = cudaStreamQuery (cs)) == cudaErrorNotReady) { rc = poll ((size_t) 1 << 19); for (int i = 0; i < 64; ++i) _mm_pause (); }
     cudaGetLastError ();
@@ -2507,6 +2512,13 @@ static int search_host_stream (gcg_ctx * ctx, gcg_table * t, const read_source &
     fprintf (stderr, "[gcg]   search pipeline (streaming, one launch): %lld pieces, waits for the gather %.3f ms (%d threads), for a free slot %.3f ms; "
              "host: submit %.3f drain %.3f ms; last piece sent at %.3f, launch seen finished at %.3f (%lld reported anchors not yet queued for download), all done at %.3f ms\n",
              (long long) n_piece, t_gather, ctx->host_threads, t_wait, t_submit, t_drain, t_loop_end, t_kernel_seen, (long long) left_at_end, ms (t_call, now ()));
+  if (timeline) {
+    float t_up = -1, t_k = -1;
+    cudaEventSynchronize (tl_kern);
+    cudaEventElapsedTime (&t_up, tl_ref, tl_up); cudaEventElapsedTime (&t_k, tl_ref, tl_kern);
+    fprintf (stderr, "[gcg]   timeline (device clock, ms after the start): last piece arrived at %.3f, launch ended at %.3f\n", t_up, t_k);
+    cudaEventDestroy (tl_ref); cudaEventDestroy (tl_up); cudaEventDestroy (tl_kern);
+  }
   gcg_trace_mark (ctx, "search: reads -> anchors (streaming)");
   for (pipe_slot & q : p->s) { q.busy = false; q.pending = false; }
   if (rc) return fail (rc);
