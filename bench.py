@@ -523,7 +523,8 @@ def run_ours(args, rank, local_rank, world):
         tab.free()
         return nh.value, s4
 
-    e2e_kmer()
+    for _ in range(3):          # untimed warm-up calls (pinned blocks parked, workers awake), as for the device-resident step
+        e2e_kmer()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -566,7 +567,8 @@ def run_ours(args, rank, local_rank, world):
         tab.free()
         return nh.value, s4
 
-    e2e_packed()
+    for _ in range(3):          # untimed warm-up calls (pinned blocks parked, workers awake), as for the device-resident step
+        e2e_packed()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -587,7 +589,8 @@ def run_ours(args, rank, local_rank, world):
         tab.free()
         return na.value, nr.value, s4
 
-    e2e_runs_packed()
+    for _ in range(3):          # untimed warm-up calls (pinned blocks parked, workers awake), as for the device-resident step
+        e2e_runs_packed()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -597,7 +600,8 @@ def run_ours(args, rank, local_rank, world):
     assert rp_hits == n_hit and rp_st == st, "run-record (packed input) and anchor paths disagree"
     pk_keep.free()
 
-    e2e_runs()
+    for _ in range(3):          # untimed warm-up calls (pinned blocks parked, workers awake), as for the device-resident step
+        e2e_runs()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
