@@ -2202,6 +2202,34 @@ static bool launches_are_async (gcg_ctx * ctx)
   return ctx->launch_async != 0;
 }
 
+// read_off[r] of a read without a word of its own (empty) or without anchors is the offset of the next read that has
+// one (read_off_fill's rule), read_off[n_read] = total: a suffix minimum over offsets that never decrease.  One block,
+// 1024 reads per step from the last read down — n_read is thousands to a few hundred thousand.
+__global__ void __launch_bounds__ (1024)
+read_off_fill_kernel (long long * __restrict__ roff, int64_t n_read, long long total)
+{
+  __shared__ long long s_w[32];
+  __shared__ long long s_carry;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { roff[n_read] = total; s_carry = total; }
+  __syncthreads ();
+  for (int64_t hi = n_read; hi > 0; hi -= 1024) {
+    const int64_t i = hi - 1 - (int64_t) threadIdx.x;          // thread 0 takes the highest index of the step
+    long long v = 0x7FFFFFFFFFFFFFFFLL;
+    if (i >= 0) { const long long x = roff[i]; if (x >= 0) v = x; }
+    for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync (0xffffffffu, v, o); if (lane >= o && y < v) v = y; }
+    if (lane == 31) s_w[wid] = v;
+    __syncthreads ();
+    long long m = s_carry;
+    for (int w = 0; w < wid; ++w) if (s_w[w] < m) m = s_w[w];
+    if (v < m) m = v;
+    if (i >= 0) roff[i] = m;
+    __syncthreads ();
+    if (threadIdx.x == 1023) s_carry = m;
+    __syncthreads ();
+  }
+}
+
 static bool stream_mode_on (void)
 {
 #if K45F_BLOCKSCAN != 2
@@ -2480,11 +2508,7 @@ static int search_host_stream (gcg_ctx * ctx, gcg_table * t, const read_source &
       if (e3 == cudaSuccess && fmt && total <= res.cap) e3 = cudaMemcpyAsync (res.read_off, d_roff, (size_t) n_read * 8, cudaMemcpyDeviceToHost, down);
       if (e3 == cudaSuccess) e3 = cudaStreamSynchronize (down);
       if (e3 != cudaSuccess) { gcg_set_error ("gcg_search: result download: %s", cudaGetErrorString (e3)); rc = GCG_ECUDA; break; }
-    } else if (fmt && total <= res.cap) {
-      if (cudaMemcpyAsync (res.read_off, d_roff, (size_t) n_read * 8, cudaMemcpyDeviceToHost, cs) != cudaSuccess || cudaStreamSynchronize (cs) != cudaSuccess) {
-        gcg_set_error ("gcg_search: read offsets download failed"); rc = GCG_ECUDA; break;
-      }
-    }
+    }    // (keep: the offsets stay on the device too and are completed there, below)
     t_drain += ms (t_d0, now ());
     if (total <= res.cap) break;
     // denser than estimated: anchors [0, cap) are in place; a result of the right size takes them over and a second
@@ -2524,12 +2548,16 @@ static int search_host_stream (gcg_ctx * ctx, gcg_table * t, const read_source &
   if (rc) return fail (rc);
   res.n = total;
   p->last_total = total;
-  if (fmt) read_off_fill (res.read_off, n_read, total);
+  if (fmt && !keep) read_off_fill (res.read_off, n_read, total);
   if (keep) {
-    // filled offsets go back up: the reduction kernels read read_off[r + 1] of every read
-    if (cudaMemcpyAsync (d_roff, res.read_off, (size_t) (n_read + 1) * 8, cudaMemcpyHostToDevice, cs) != cudaSuccess || cudaStreamSynchronize (cs) != cudaSuccess) {
-      gcg_set_error ("gcg_search: read offsets upload failed"); return fail (GCG_ECUDA);
+    // the reduction kernels read read_off[r + 1] of every read: complete the offsets where they are (the host copy
+    // a kept search hands back is only a placeholder its callers release)
+    {
+      gcg_kscope ks (ctx, "read_off_fill");
+      read_off_fill_kernel<<<1, 1024, 0, cs>>> (d_roff, n_read, (long long) total);
     }
+    if (cudaGetLastError () != cudaSuccess) { gcg_set_error ("gcg_search: read offset fill launch failed"); return fail (GCG_ECUDA); }
+    if (fmt) memset (res.read_off, 0, (size_t) (n_read + 1) * 8);
     keep->d_anchors = d_res; keep->d_read_off = d_roff; d_res = nullptr; d_roff = nullptr;
   }
   release ();
