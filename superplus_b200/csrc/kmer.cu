@@ -1180,7 +1180,9 @@ static int seqs_alloc (gcg_ctx * ctx, gcg_seqs * s)
   return tseq_upload (ctx, s->h_woff, s->n, s->n_words, &s->d_tseq);
 }
 
-static int seqs_upload_impl (gcg_ctx * ctx, const seq_src & src, const int32_t * len, int64_t n, gcg_seqs ** out)
+// wait == false: the call returns when the caller's strings have been read (gathered into the pinned ring); the copies
+// and the pack kernel are queued on ctx->stream, where everything that uses the sequences is ordered behind them
+static int seqs_upload_impl (gcg_ctx * ctx, const seq_src & src, const int32_t * len, int64_t n, gcg_seqs ** out, bool wait = true)
 {
   GCG_CHECK (ctx && out && n >= 0, GCG_EINVAL, "gcg_seqs_upload: bad argument");
   GCG_CUDA (cudaSetDevice (ctx->device));
@@ -1190,7 +1192,7 @@ static int seqs_upload_impl (gcg_ctx * ctx, const seq_src & src, const int32_t *
   if (!rc) rc = seqs_alloc (ctx, s);
   if (!rc) rc = stream_ascii (ctx, src, s->h_woff, s->h_len, n, s->n_words,
                               [&] (char * d, int64_t w0, int64_t nw) { return launch_pack (ctx, d, s->d_packed + w0, nw); });
-  if (!rc && cudaStreamSynchronize (ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_seqs_upload: stream sync failed"); rc = GCG_ECUDA; }
+  if (!rc && wait && cudaStreamSynchronize (ctx->stream) != cudaSuccess) { gcg_set_error ("gcg_seqs_upload: stream sync failed"); rc = GCG_ECUDA; }
   if (rc) { gcg_seqs_free (s); return rc; }
   *out = s;
   return GCG_OK;
@@ -1370,12 +1372,15 @@ extern "C" int gcg_table_build (gcg_ctx * ctx, const char * const * contig_seq, 
                                 int32_t n_contig, int k, gcg_table ** out)
 {
   gcg_seqs * s = nullptr;
-  int rc = gcg_seqs_upload (ctx, contig_seq, contig_len, n_contig, &s);
+  GCG_CHECK (n_contig == 0 || (contig_seq && contig_len), GCG_EINVAL, "gcg_table_build: NULL input");
+  seq_src src; src.ptrs = contig_seq;
+  // no wait for the upload, the pack or the insert kernel: the caller's strings have been read when the upload returns
+  // (the gather into the pinned ring is a host pass), everything that uses the table is ordered behind the insert on
+  // the context's stream, and the packed contigs go back to the context's block cache, which only hands them to work
+  // queued later on that stream — so the host can start on the reads (gcg_search*) while the table is being built
+  int rc = seqs_upload_impl (ctx, src, contig_len, n_contig, &s, false);
   if (rc) return rc;
   rc = gcg_table_build_seqs (ctx, s, k, out);
-  // no wait for the insert kernel: everything that uses the table is ordered behind it on the context's stream, and
-  // the packed contigs go back to the context's block cache, which only hands them to work queued later on that stream
-  // (the upload above has synchronised, so the caller's strings are no longer read)
   gcg_seqs_free (s);
   return rc;
 }
@@ -2014,6 +2019,10 @@ struct gcg_pipe {
   unsigned long long * hd_count = nullptr;           // count straight into host memory (device alias of h_count) — a copy of
                                                      // 8 bytes would queue behind the anchor downloads on the D2H copy engine
   cudaEvent_t ev_down[2] = {nullptr, nullptr};       // direct mode: behind the last two queued pieces of the download
+  // one-launch search: what its UPLOAD stream writes (ready word, read offsets / lengths, packed words) lives in a block of
+  // its own — blocks of the context's cache may have been released a moment ago with readers still queued on ctx->stream
+  char * st_buf = nullptr;
+  size_t st_cap = 0;
   unsigned long long * d_run = nullptr;              // zero copy: running anchor count, two words used alternately (a launch
                                                      // reads one and writes the other: late blocks must not see their own total)
   int64_t last_total = 0;                            // anchors of the previous call: sizes the next result buffer
@@ -2031,6 +2040,7 @@ void gcg_pipe_free (gcg_ctx * ctx)
     cudaFree (q.d_meta); cudaFree (q.d_packed); cudaFree (q.d_state); cudaFree (q.d_read_off); cudaFree (q.d_hits);
     for (cudaEvent_t e : {q.ev_up, q.ev_emit, q.ev_free}) if (e) cudaEventDestroy (e);
   }
+  if (p->st_buf) cudaFree (p->st_buf);
   if (p->h_count) cudaFreeHost (p->h_count);
   for (cudaEvent_t e : p->ev_down) if (e) cudaEventDestroy (e);
   cudaFree (p->d_run);
@@ -2300,18 +2310,30 @@ static int search_host_stream (gcg_ctx * ctx, gcg_table * t, const read_source &
   uint64_t * d_packed = nullptr; char * d_meta = nullptr; int32_t * d_tseq = nullptr; unsigned long long * d_state = nullptr, * d_ready = nullptr;
   unsigned int * d_group = nullptr; void * d_res = nullptr; long long * d_roff = nullptr; unsigned long long * hd_group = nullptr;
   auto release = [&] () {
-    gcg_dfree (ctx, d_packed); gcg_dfree (ctx, d_meta); gcg_dfree (ctx, d_tseq); gcg_dfree (ctx, d_state); gcg_dfree (ctx, d_ready); gcg_dfree (ctx, d_group);
+    gcg_dfree (ctx, d_tseq); gcg_dfree (ctx, d_state); gcg_dfree (ctx, d_group);
+    if (p->st_cap > ((size_t) 2 << 30)) { cudaFree (p->st_buf); p->st_buf = nullptr; p->st_cap = 0; }      // (a very large read set: not kept)
     if (d_res) gcg_dfree (ctx, d_res);
     if (d_roff) gcg_dfree (ctx, d_roff);
     gcg_free (h_meta); gcg_free (h_group); gcg_free (h_ready);
   };
   auto fail = [&] (int code) { release (); gcg_free (res.buf); gcg_free (res.read_off); return code; };
   if (!h_meta || !h_group || !h_ready || (fmt && !res.read_off) || (!keep && !res.buf)) { gcg_set_error ("gcg_search: pinned host memory for %lld reads / %lld anchors", (long long) n_read, (long long) res.cap); return fail (GCG_ENOMEM); }
-  cudaError_t e = gcg_dmalloc (ctx, &d_packed, (size_t) (total_words + 2) * 8);
-  if (e == cudaSuccess) e = gcg_dmalloc (ctx, &d_meta, meta_bytes);
+  // (the upload stream's targets: one block of the pipeline's own, kept between calls up to 2 GiB)
+  const size_t meta_pad = (meta_bytes + 255) & ~(size_t) 255, st_need = 256 + meta_pad + (size_t) (total_words + 2) * 8;
+  cudaError_t e = cudaSuccess;
+  if (p->st_cap < st_need) {
+    if (p->st_buf) { cudaFree (p->st_buf); p->st_buf = nullptr; p->st_cap = 0; }
+    const size_t want = st_need + st_need / 8;
+    if ((e = cudaMalloc (&p->st_buf, want)) == cudaSuccess) p->st_cap = want;
+    else { cudaGetLastError (); if ((e = cudaMalloc (&p->st_buf, st_need)) == cudaSuccess) p->st_cap = st_need; }
+  }
+  if (e == cudaSuccess) {
+    d_ready = (unsigned long long *) p->st_buf;
+    d_meta = p->st_buf + 256;
+    d_packed = (uint64_t *) (p->st_buf + 256 + meta_pad);
+  }
   if (e == cudaSuccess) e = gcg_dmalloc (ctx, &d_tseq, (size_t) n_tiles * 4);
   if (e == cudaSuccess) e = gcg_dmalloc (ctx, &d_state, (size_t) (n_tiles + 1) * 8);
-  if (e == cudaSuccess) e = gcg_dmalloc (ctx, &d_ready, 64);
   if (e == cudaSuccess) e = gcg_dmalloc (ctx, &d_group, (size_t) n_group * 4);
   if (e == cudaSuccess) e = gcg_dmalloc (ctx, &d_res, (size_t) res.cap * res.rec);
   if (e == cudaSuccess && fmt) e = gcg_dmalloc (ctx, &d_roff, (size_t) (n_read + 1) * 8);
@@ -2331,6 +2353,9 @@ static int search_host_stream (gcg_ctx * ctx, gcg_table * t, const read_source &
   pipe_slot & q0 = p->s[0];
   h_ready[0] = 0;
   cudaStream_t up = p->up, down = p->down, cs = ctx->stream;
+  // (The upload stream writes only into the pipeline's own block.  Blocks of the context's cache may have been released a
+  //  moment ago with readers still queued on ctx->stream — gcg_table_build releases the packed contigs, their offsets and
+  //  lengths while its insert kernel is pending —, which is safe for work queued on ctx->stream and for nothing else.)
   if ((e = cudaMemcpyAsync (d_meta, h_meta, meta_bytes, cudaMemcpyHostToDevice, up)) != cudaSuccess ||
       (e = cudaMemcpyAsync (d_ready, h_ready, 8, cudaMemcpyHostToDevice, up)) != cudaSuccess ||
       (e = cudaMemsetAsync (d_packed + total_words, 0, 16, up)) != cudaSuccess ||

@@ -427,3 +427,43 @@ def test_streaming_search_piece_sizes_and_pool_sizes(oracle, threads, host_pipel
         cs.free()
     finally:
         c.close()
+
+
+def test_search_right_behind_an_unfinished_table_build(oracle, host_pipeline):
+    """gcg_table_build returns while its upload, pack and insert kernels are still queued, and releases the packed
+    contigs into the context's block cache; a host-buffer search called right behind it takes blocks from that cache
+    for what it writes on the context's stream; what its upload stream writes must NOT come from there (the ready word
+    once landed on the released contig lengths and cleared the first contigs under the pending insert kernel): it has a
+    block of the pipeline's own.  Many rounds, nothing between the two calls, contig sets of several sizes."""
+    import ctypes as C
+    inp = synth.make_config("cfg1")
+    c = api.Context(0, host_threads=8)
+    try:
+        reads = [np.ascontiguousarray(r) for r in inp.reads[:400]]
+        rptrs = (C.c_void_p * len(reads))(*[a.ctypes.data for a in reads])
+        rlens = np.array([len(a) for a in reads], dtype=np.int32)
+        for n_ctg in (len(inp.contigs), 3, 17):
+            ctgs = [np.ascontiguousarray(x) for x in inp.contigs[:n_ctg]]
+            cptrs = (C.c_void_p * len(ctgs))(*[a.ctypes.data for a in ctgs])
+            clens = np.array([len(a) for a in ctgs], dtype=np.int32)
+            cs = c.upload(ctgs)
+            t0 = c.table_build(cs, 25)
+            c.sync()
+            want_a, want_off = c.search_host_compact(t0, reads)
+            want_st = t0.stats()
+            t0.free(); cs.free()
+            for it in range(40):
+                h = C.c_void_p()
+                c._chk(c.L.gcg_table_build(c.h, C.cast(cptrs, C.c_void_p), clens.ctypes.data, len(ctgs), 25, C.byref(h)))
+                ap, rp, na = C.c_void_p(), C.c_void_p(), C.c_int64()
+                c._chk(c.L.gcg_search_compact(c.h, h, C.cast(rptrs, C.c_void_p), rlens.ctypes.data, len(reads), 25, C.byref(ap), C.byref(rp), C.byref(na)))
+                tab = api.KmerTable(c, h, 25)
+                try:
+                    assert na.value == len(want_a), (n_ctg, it, na.value, len(want_a))
+                    a = np.frombuffer((C.c_char * (na.value * 8)).from_address(ap.value), dtype=np.uint64)
+                    assert np.array_equal(a, want_a) and tab.stats() == want_st, (n_ctg, it)
+                    del a
+                finally:
+                    c.L.gcg_free(ap); c.L.gcg_free(rp); tab.free()
+    finally:
+        c.close()
